@@ -1,0 +1,155 @@
+/*
+ * secedo_b200 — C ABI of the B200-native similarity-matrix hot path of SECEDO.
+ *
+ * The reference has no FFI; its boundary for this path is two C++ functions
+ *   Filter::filter(...)            util/is_significant.hpp:68-72   (body util/is_significant.cpp:149-193)
+ *   computeSimilarityMatrix(...)   similarity_matrix.hpp:51-60     (body similarity_matrix.cpp:295-433)
+ * called from divide_cluster (spectral_clustering.cpp:336-356). The entry points below are what a
+ * host-side shim defining those two symbols binds (secedo_b200/host/*.cpp): plain
+ * pointers and sizes, no C++ or torch types. One context drives ONE GPU; multi-GPU runs use one
+ * process (and one context) per GPU and sum the count matrices between sgpu_counts_accumulate and
+ * sgpu_similarity_finalize with a single NCCL reduction (secedo_b200/dist.py).
+ *
+ * Pileup layout (replaces std::vector<std::vector<PosData>>, sequenced_data.hpp:11-47):
+ *   chr_ptr[n_chr+1]    u64  locus offsets per chromosome
+ *   row_ptr[n_loci+1]   u64  entry offsets per locus
+ *   position[n_loci]    u32  strictly increasing inside a chromosome
+ *   read_id[n_entries]  u32  unique inside a chromosome (0xFFFFFFFF is reserved)
+ *   gid_base[n_entries] u16  group id << 2 | base  (PosData::group_ids_bases)
+ *
+ * Every function returns 0 on success or a negative SGPU_E_* code; sgpu_last_error() gives the
+ * text. There is no CPU fallback: without a usable CUDA device sgpu_init fails.
+ */
+#ifndef SECEDO_B200_H
+#define SECEDO_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SGPU_NO_POS 16383u   /* util/is_significant.hpp:11 */
+#define SGPU_MAX_CLASS 64    /* overlap classes x_s, x_d < 64 are supported */
+
+enum {
+    SGPU_OK = 0,
+    SGPU_E_CUDA = -1,          /* CUDA runtime error (text in sgpu_last_error) */
+    SGPU_E_ARG = -2,           /* invalid argument (e.g. unknown normalization: the reference throws
+                                  std::logic_error, similarity_matrix.cpp:264) */
+    SGPU_E_CELL_RANGE = -3,    /* group id >= n_groups or mapped cell >= num_cells (mat.hpp:119 assert) */
+    SGPU_E_FRAGMENT_SPAN = -4, /* a read id spans >= max_fragment_length: undefined in the reference */
+    SGPU_E_CLASS_RANGE = -5,   /* a read pair overlaps at >= SGPU_MAX_CLASS (or >= L) loci */
+    SGPU_E_POSITIONS = -6,     /* loci not strictly increasing inside a chromosome */
+    SGPU_E_COUNT_RANGE = -7    /* internal int8/int32 range exceeded */
+};
+
+/* similarity_matrix.hpp:9-17 */
+enum { SGPU_NORM_ADD_MIN = 0, SGPU_NORM_EXPONENTIATE = 1, SGPU_NORM_SCALE_MAX_1 = 2 };
+
+/* how the first-order same/different read-pair counts are produced */
+enum {
+    SGPU_PATH_AUTO = 0,    /* chosen from measured density */
+    SGPU_PATH_SCATTER = 1, /* per-locus cross-cell pair scatter, int32 atomics */
+    SGPU_PATH_GEMM = 2     /* int8 tcgen05/TMEM GEMM on Hadamard-transformed per-base count planes */
+};
+
+typedef struct sgpu_ctx sgpu_ctx;
+typedef struct sgpu_pileup sgpu_pileup; /* device-resident CSR pileup */
+typedef struct sgpu_counts sgpu_counts; /* device-resident integer read-pair count matrices */
+
+typedef struct sgpu_stats {
+    uint64_t n_loci;            /* loci processed */
+    uint64_t n_entries;         /* pileup entries processed */
+    uint64_t n_reads;           /* distinct reads (fragments) */
+    uint64_t n_dropped_entries; /* entries removed by the paired-end mate rule (similarity_matrix.cpp:387-395) */
+    uint64_t n_multi_reads;     /* reads that keep >= 2 loci */
+    uint64_t n_tail_reads;      /* reads with index >= K (never the first read of a pair) */
+    uint64_t n_pairs_first;     /* cross-cell (read pair, shared locus) incidences counted */
+    uint64_t n_pairs_multi;     /* read pairs overlapping at >= 2 loci */
+    int32_t path_used;          /* SGPU_PATH_SCATTER or SGPU_PATH_GEMM */
+    int32_t reserved;
+    float ms_link;              /* device time: read linking + mate rule + cutoff K */
+    float ms_first_order;       /* device time: scatter or staging + GEMM */
+    float ms_multi;             /* device time: multi-locus correction */
+    float ms_epilogue;          /* device time: log-likelihood transform + normalisation */
+} sgpu_stats;
+
+/* ---- context ---------------------------------------------------------------------------- */
+int sgpu_init(int device, sgpu_ctx **ctx);
+void sgpu_shutdown(sgpu_ctx *ctx);
+const char *sgpu_last_error(const sgpu_ctx *ctx);
+/* Run all work of this context on an existing CUDA stream (cudaStream_t); NULL restores the
+ * context's own stream. */
+int sgpu_set_stream(sgpu_ctx *ctx, void *cuda_stream);
+int sgpu_synchronize(sgpu_ctx *ctx);
+
+/* ---- pileup staging (replaces the host vector<vector<PosData>>) --------------------------- */
+int sgpu_pileup_upload(sgpu_ctx *ctx, uint32_t n_chr, const uint64_t *chr_ptr, const uint64_t *row_ptr,
+                       const uint32_t *position, const uint32_t *read_id, const uint16_t *gid_base,
+                       sgpu_pileup **out);
+/* Adopt arrays that already live on this context's device (not copied, not freed). */
+int sgpu_pileup_wrap_device(sgpu_ctx *ctx, uint32_t n_chr, const uint64_t *host_chr_ptr,
+                            const uint64_t *dev_row_ptr, const uint32_t *dev_position,
+                            const uint32_t *dev_read_id, const uint16_t *dev_gid_base, sgpu_pileup **out);
+int sgpu_pileup_dims(const sgpu_pileup *p, uint32_t *n_chr, uint64_t *n_loci, uint64_t *n_entries);
+int sgpu_pileup_download(sgpu_ctx *ctx, const sgpu_pileup *p, uint64_t *chr_ptr, uint64_t *row_ptr,
+                         uint32_t *position, uint32_t *read_id, uint16_t *gid_base);
+void sgpu_pileup_free(sgpu_ctx *ctx, sgpu_pileup *p);
+
+/* ---- Filter (util/is_significant.cpp) -------------------------------------------------------- */
+/* Filter::is_significant(std::array<uint16_t,4>&) on n count tuples, evaluated on the GPU. */
+int sgpu_is_significant(sgpu_ctx *ctx, const uint16_t *counts4, uint64_t n, double theta,
+                        int cell_proportion, uint8_t *out);
+/* Filter::filter: keeps the entries whose group is in the sub-cluster (id_to_pos[gid] != NO_POS)
+ * at the loci that pass is_significant; result stays on the device. avg_coverage is accumulated in
+ * 64 bits (the reference wraps at 2^32, util/is_significant.cpp:156,187). */
+int sgpu_filter(sgpu_ctx *ctx, const sgpu_pileup *in, const uint32_t *id_to_pos, uint32_t n_groups,
+                double theta, int cell_proportion, sgpu_pileup **filtered, double *avg_coverage);
+
+/* ---- similarity matrix (similarity_matrix.cpp) ------------------------------------------------ */
+/* One call = computeSimilarityMatrix on one GPU; out is caller-owned host memory, num_cells^2
+ * doubles, row-major. num_threads only selects the reference's tail cutoff K. */
+int sgpu_similarity(sgpu_ctx *ctx, const sgpu_pileup *filtered, uint32_t num_cells,
+                    uint32_t max_fragment_length, const uint32_t *group_id_to_pos, uint32_t n_groups,
+                    double mutation_rate, double homozygous_rate, double seq_error_rate,
+                    uint32_t num_threads, int normalization, int path, double *out, sgpu_stats *stats);
+
+/* The same in three steps, so that several GPUs / several batches of chromosomes can share one
+ * result: create -> accumulate (any number of times) -> [sum the buffers over ranks] -> finalize. */
+int sgpu_counts_create(sgpu_ctx *ctx, uint32_t num_cells, sgpu_counts **out);
+int sgpu_counts_zero(sgpu_ctx *ctx, sgpu_counts *c);
+void sgpu_counts_free(sgpu_ctx *ctx, sgpu_counts *c);
+int sgpu_counts_accumulate(sgpu_ctx *ctx, sgpu_counts *c, const sgpu_pileup *filtered,
+                           uint32_t max_fragment_length, const uint32_t *group_id_to_pos,
+                           uint32_t n_groups, double mutation_rate, double homozygous_rate,
+                           double seq_error_rate, uint32_t num_threads, int path, sgpu_stats *stats);
+/* Device buffers to be summed element-wise across ranks before finalize:
+ *   i32     int32 [n_i32]  planes of num_cells^2: S, D (first order), then, when read pairs that
+ *                          overlap at >= 2 loci occurred, the class planes (2,0) (1,1) (0,2)
+ *                          (3,0) (2,1) (1,2) (0,3); only the upper triangle i < j is meaningful
+ *   f64     double [n_f64] num_cells^2, present only if a pair overlapped at >= 4 loci: sum of
+ *                          G(x_s,x_d) = F(x_s,x_d) - x_s F(1,0) - x_d F(0,1) over those pairs
+ *   hist    uint64 [SGPU_MAX_CLASS^2] global histogram of overlap classes with x_s + x_d >= 2
+ * Ranks must agree on the layout before reducing: exchange (n_i32, n_f64), take the maximum and
+ * call sgpu_counts_set_layout (buffers may move), then fetch the pointers again. */
+int sgpu_counts_buffers(sgpu_counts *c, int32_t **i32, uint64_t *n_i32, double **f64, uint64_t *n_f64,
+                        uint64_t **hist, uint64_t *n_hist);
+int sgpu_counts_set_layout(sgpu_ctx *ctx, sgpu_counts *c, int planes_used /* 2 or 9 */, int want_spill);
+/* Symmetric per-cell-pair integers for bit-exact checks (any pointer may be NULL):
+ *   S1, D1  num_cells^2 int32: incidences (read pair, shared locus) with equal / different base
+ *   H       3*num_cells^2 int32: read pairs in overlap class (2,0), (1,1), (0,2)
+ *   hist    SGPU_MAX_CLASS^2 uint64: read pairs per class (x_s, x_d) with x_s + x_d >= 2 */
+int sgpu_counts_download(sgpu_ctx *ctx, sgpu_counts *c, int32_t *S1, int32_t *D1, int32_t *H, uint64_t *hist);
+/* Log-likelihood transform (LS/LD of similarity_matrix.cpp:117-170) + normalisation (:271-293). */
+int sgpu_similarity_finalize(sgpu_ctx *ctx, sgpu_counts *c, uint32_t max_fragment_length,
+                             double mutation_rate, double homozygous_rate, double seq_error_rate,
+                             int normalization, double *out, sgpu_stats *stats);
+/* LS / LD tables as evaluated on the device, n*n row-major (parity with similarity_matrix.cpp:117-170). */
+int sgpu_log_probs(sgpu_ctx *ctx, double mutation_rate, double homozygous_rate, double seq_error_rate,
+                   uint32_t max_fragment_length, uint32_t n, double *ls, double *ld);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,310 @@
+"""Host-side mirror of the reference's interface for the hot path, on top of the C ABI.
+
+Same names, argument order/meaning and error behaviour as the reference:
+
+    Filter(theta, cell_proportion=4)                       util/is_significant.hpp:40-52
+    Filter.is_significant(base_count)                      util/is_significant.hpp:60
+    Filter.filter(pos_data, id_to_pos, marker, num_threads) -> (filtered, avg_coverage)   :68-72
+    compute_similarity_matrix(pos_data, num_cells, max_fragment_length, group_id_to_pos,
+        mutation_rate, homozygous_rate, seq_error_rate, num_threads, marker, normalization)
+                                                           similarity_matrix.hpp:51-60
+
+``pos_data`` is a :class:`secedo_b200.pileup.Pileup` (host CSR, the flat form of
+``vector<vector<PosData>>``) or a :class:`DevicePileup` already staged in HBM. The C++ flavour of
+this shim, which defines the reference's own symbols, lives in ``secedo_b200/host``.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional, Sequence, Tuple, Union
+
+import numpy as np
+
+from . import _lib
+from ._lib import NORMALIZATIONS, PATHS, SgpuError, Stats
+from .pileup import NO_POS, Pileup
+
+
+def _ptr(a: Optional[np.ndarray]):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+class Context:
+    """One GPU. All work of a context is issued on one CUDA stream."""
+
+    def __init__(self, device: int = 0):
+        self._lib = _lib.load()
+        self._h = C.c_void_p()
+        rc = self._lib.sgpu_init(int(device), C.byref(self._h))
+        if rc != 0:
+            msg = self._lib.sgpu_last_error(self._h).decode() if self._h else "sgpu_init failed"
+            if self._h:
+                self._lib.sgpu_shutdown(self._h)
+                self._h = C.c_void_p()
+            raise SgpuError(rc, msg)
+        self.device = int(device)
+
+    def check(self, rc: int) -> None:
+        if rc != 0:
+            raise SgpuError(rc, self._lib.sgpu_last_error(self._h).decode())
+
+    def set_stream(self, cuda_stream: Optional[int]) -> None:
+        self.check(self._lib.sgpu_set_stream(self._h, C.c_void_p(cuda_stream) if cuda_stream else None))
+
+    def synchronize(self) -> None:
+        self.check(self._lib.sgpu_synchronize(self._h))
+
+    def close(self) -> None:
+        if self._h:
+            self._lib.sgpu_shutdown(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ------------------------------------------------------------------ staging
+    def upload(self, p: Pileup) -> "DevicePileup":
+        h = C.c_void_p()
+        self.check(self._lib.sgpu_pileup_upload(self._h, p.n_chr, _ptr(p.chr_ptr), _ptr(p.row_ptr), _ptr(p.position),
+                                                _ptr(p.read_id), _ptr(p.gid_base), C.byref(h)))
+        return DevicePileup(self, h)
+
+    def wrap_device(self, chr_ptr: np.ndarray, d_row_ptr: int, d_position: int, d_read_id: int, d_gid_base: int,
+                    keepalive=None) -> "DevicePileup":
+        chr_ptr = np.ascontiguousarray(chr_ptr, np.uint64)
+        h = C.c_void_p()
+        self.check(self._lib.sgpu_pileup_wrap_device(self._h, chr_ptr.size - 1, _ptr(chr_ptr), C.c_void_p(d_row_ptr),
+                                                     C.c_void_p(d_position), C.c_void_p(d_read_id),
+                                                     C.c_void_p(d_gid_base), C.byref(h)))
+        dp = DevicePileup(self, h)
+        dp._keepalive = keepalive
+        return dp
+
+
+_default_ctx: Optional[Context] = None
+
+
+def default_context() -> Context:
+    global _default_ctx
+    if _default_ctx is None:
+        _default_ctx = Context(0)
+    return _default_ctx
+
+
+class DevicePileup:
+    """Device-resident CSR pileup (``sgpu_pileup``)."""
+
+    def __init__(self, ctx: Context, handle: C.c_void_p):
+        self.ctx, self._h, self._keepalive = ctx, handle, None
+
+    def dims(self) -> Tuple[int, int, int]:
+        a, b, c = C.c_uint32(), C.c_uint64(), C.c_uint64()
+        self.ctx.check(self.ctx._lib.sgpu_pileup_dims(self._h, C.byref(a), C.byref(b), C.byref(c)))
+        return a.value, b.value, c.value
+
+    @property
+    def n_chr(self) -> int:
+        return self.dims()[0]
+
+    @property
+    def n_loci(self) -> int:
+        return self.dims()[1]
+
+    @property
+    def n_entries(self) -> int:
+        return self.dims()[2]
+
+    def download(self) -> Pileup:
+        n_chr, n_loci, n_entries = self.dims()
+        chr_ptr, row_ptr = np.zeros(n_chr + 1, np.uint64), np.zeros(n_loci + 1, np.uint64)
+        pos, rid, gb = np.zeros(n_loci, np.uint32), np.zeros(n_entries, np.uint32), np.zeros(n_entries, np.uint16)
+        self.ctx.check(self.ctx._lib.sgpu_pileup_download(self.ctx._h, self._h, _ptr(chr_ptr), _ptr(row_ptr), _ptr(pos),
+                                                          _ptr(rid), _ptr(gb)))
+        return Pileup(chr_ptr, row_ptr, pos, rid, gb)
+
+    def free(self) -> None:
+        if self._h and self.ctx._h:
+            self.ctx._lib.sgpu_pileup_free(self.ctx._h, self._h)
+        self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
+PosDataLike = Union[Pileup, DevicePileup]
+
+
+def _staged(ctx: Context, p: PosDataLike) -> Tuple[DevicePileup, bool]:
+    if isinstance(p, DevicePileup):
+        return p, False
+    return ctx.upload(p), True
+
+
+class Filter:
+    """Mirror of the reference's ``Filter`` (util/is_significant.hpp:13-80)."""
+
+    def __init__(self, theta: float, cell_proportion: int = 4, ctx: Optional[Context] = None):
+        self.theta, self.cell_proportion = float(theta), int(cell_proportion)
+        self.ctx = ctx or default_context()
+
+    def is_significant(self, base_count: Sequence[int]) -> Union[bool, np.ndarray]:
+        """``base_count``: 4 pooled counts (any base order) or an (n, 4) array of them."""
+        a = np.ascontiguousarray(base_count, np.uint16)
+        single = a.ndim == 1
+        a = a.reshape(-1, 4)
+        out = np.zeros(a.shape[0], np.uint8)
+        self.ctx.check(self.ctx._lib.sgpu_is_significant(self.ctx._h, _ptr(a), a.shape[0], self.theta,
+                                                         self.cell_proportion, _ptr(out)))
+        return bool(out[0]) if single else out.astype(bool)
+
+    def filter_device(self, pos_data: PosDataLike, id_to_pos: Sequence[int]) -> Tuple[DevicePileup, float]:
+        ctx = self.ctx
+        id_to_pos = np.ascontiguousarray(id_to_pos, np.uint32)
+        dp, owned = _staged(ctx, pos_data)
+        try:
+            h, cov = C.c_void_p(), C.c_double()
+            ctx.check(ctx._lib.sgpu_filter(ctx._h, dp._h, _ptr(id_to_pos), id_to_pos.size, self.theta,
+                                           self.cell_proportion, C.byref(h), C.byref(cov)))
+        finally:
+            if owned:
+                dp.free()
+        return DevicePileup(ctx, h), cov.value
+
+    def filter(self, pos_data: PosDataLike, id_to_pos: Sequence[int], marker: str = "",
+               num_threads: int = 1) -> Tuple[Pileup, float]:
+        """Returns (filtered pileup on the host, average coverage) like the reference; ``marker`` and
+        ``num_threads`` are accepted for signature parity (the reference only logs / ignores them)."""
+        del marker, num_threads
+        dev, cov = self.filter_device(pos_data, id_to_pos)
+        try:
+            return dev.download(), cov
+        finally:
+            dev.free()
+
+
+class Counts:
+    """Device-resident integer read-pair count matrices (``sgpu_counts``)."""
+
+    def __init__(self, ctx: Context, num_cells: int):
+        self.ctx, self.num_cells = ctx, int(num_cells)
+        self._h = C.c_void_p()
+        ctx.check(ctx._lib.sgpu_counts_create(ctx._h, self.num_cells, C.byref(self._h)))
+        self.last_stats: Optional[dict] = None
+
+    def zero(self) -> None:
+        self.ctx.check(self.ctx._lib.sgpu_counts_zero(self.ctx._h, self._h))
+
+    def accumulate(self, filtered: PosDataLike, max_fragment_length: int, group_id_to_pos: Sequence[int],
+                   mutation_rate: float, homozygous_rate: float, seq_error_rate: float, num_threads: int,
+                   path: str = "auto") -> dict:
+        ctx = self.ctx
+        g = np.ascontiguousarray(group_id_to_pos, np.uint32)
+        dp, owned = _staged(ctx, filtered)
+        st = Stats()
+        try:
+            ctx.check(ctx._lib.sgpu_counts_accumulate(ctx._h, self._h, dp._h, int(max_fragment_length), _ptr(g), g.size,
+                                                      float(mutation_rate), float(homozygous_rate),
+                                                      float(seq_error_rate), int(num_threads), PATHS[path],
+                                                      C.byref(st)))
+        finally:
+            if owned:
+                dp.free()
+        self.last_stats = st.as_dict()
+        return self.last_stats
+
+    def buffers(self):
+        """(i32 device pointer, n_i32, f64 device pointer or None, n_f64, hist device pointer, n_hist)."""
+        i32, f64, hist = C.c_void_p(), C.c_void_p(), C.c_void_p()
+        n_i32, n_f64, n_hist = C.c_uint64(), C.c_uint64(), C.c_uint64()
+        self.ctx.check(self.ctx._lib.sgpu_counts_buffers(self._h, C.byref(i32), C.byref(n_i32), C.byref(f64),
+                                                         C.byref(n_f64), C.byref(hist), C.byref(n_hist)))
+        return i32.value, n_i32.value, f64.value, n_f64.value, hist.value, n_hist.value
+
+    def set_layout(self, planes_used: int, want_spill: bool) -> None:
+        self.ctx.check(self.ctx._lib.sgpu_counts_set_layout(self.ctx._h, self._h, int(planes_used), int(want_spill)))
+
+    def download(self):
+        """Symmetric host copies: (S1, D1, H[3], class_hist) for bit-exact checks."""
+        n = self.num_cells
+        S1, D1 = np.zeros((n, n), np.int32), np.zeros((n, n), np.int32)
+        H = np.zeros((3, n, n), np.int32)
+        hist = np.zeros((_lib.MAX_CLASS, _lib.MAX_CLASS), np.uint64)
+        self.ctx.check(self.ctx._lib.sgpu_counts_download(self.ctx._h, self._h, _ptr(S1), _ptr(D1), _ptr(H), _ptr(hist)))
+        return S1, D1, H, hist
+
+    def finalize(self, max_fragment_length: int, mutation_rate: float, homozygous_rate: float,
+                 seq_error_rate: float, normalization: str, out: Optional[np.ndarray] = None) -> np.ndarray:
+        if normalization not in NORMALIZATIONS:
+            raise ValueError("Invalid normalization: " + str(normalization))  # similarity_matrix.cpp:264
+        n = self.num_cells
+        if out is None:
+            out = np.zeros((n, n), np.float64)
+        assert out.dtype == np.float64 and out.flags.c_contiguous and out.size == n * n
+        st = Stats()
+        self.ctx.check(self.ctx._lib.sgpu_similarity_finalize(self.ctx._h, self._h, int(max_fragment_length),
+                                                              float(mutation_rate), float(homozygous_rate),
+                                                              float(seq_error_rate), NORMALIZATIONS[normalization],
+                                                              _ptr(out), C.byref(st)))
+        if self.last_stats is not None:
+            self.last_stats["ms_epilogue"] = st.ms_epilogue
+        return out
+
+    def free(self) -> None:
+        if self._h and self.ctx._h:
+            self.ctx._lib.sgpu_counts_free(self.ctx._h, self._h)
+        self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
+def compute_similarity_matrix(pos_data: PosDataLike, num_cells: int, max_fragment_length: int,
+                              group_id_to_pos: Sequence[int], mutation_rate: float, homozygous_rate: float,
+                              seq_error_rate: float, num_threads: int, marker: str = "",
+                              normalization: str = "ADD_MIN", *, ctx: Optional[Context] = None, path: str = "auto",
+                              out: Optional[np.ndarray] = None, return_stats: bool = False):
+    """``computeSimilarityMatrix`` (similarity_matrix.hpp:51-60) on one GPU. ``num_threads`` selects
+    the reference's tail cutoff (the result of the reference depends on it)."""
+    del marker
+    if normalization not in NORMALIZATIONS:
+        raise ValueError("Invalid normalization: " + str(normalization))  # std::logic_error in the reference
+    ctx = ctx or default_context()
+    g = np.ascontiguousarray(group_id_to_pos, np.uint32)
+    n = int(num_cells)
+    if out is None:
+        out = np.zeros((n, n), np.float64)
+    assert out.dtype == np.float64 and out.flags.c_contiguous and out.size == n * n
+    dp, owned = _staged(ctx, pos_data)
+    st = Stats()
+    try:
+        ctx.check(ctx._lib.sgpu_similarity(ctx._h, dp._h, n, int(max_fragment_length), _ptr(g), g.size,
+                                           float(mutation_rate), float(homozygous_rate), float(seq_error_rate),
+                                           int(num_threads), NORMALIZATIONS[normalization], PATHS[path], _ptr(out),
+                                           C.byref(st)))
+    finally:
+        if owned:
+            dp.free()
+    return (out, st.as_dict()) if return_stats else out
+
+
+def log_probs(mutation_rate: float, homozygous_rate: float, seq_error_rate: float, max_fragment_length: int, n: int,
+              ctx: Optional[Context] = None):
+    """LS / LD tables evaluated on the device (similarity_matrix.cpp:117-170)."""
+    ctx = ctx or default_context()
+    ls, ld = np.zeros((n, n)), np.zeros((n, n))
+    ctx.check(ctx._lib.sgpu_log_probs(ctx._h, float(mutation_rate), float(homozygous_rate), float(seq_error_rate),
+                                      int(max_fragment_length), int(n), _ptr(ls), _ptr(ld)))
+    return ls, ld
+
+
+__all__ = ["Context", "DevicePileup", "Filter", "Counts", "compute_similarity_matrix", "log_probs", "default_context",
+           "NO_POS", "SgpuError"]

@@ -1,0 +1,478 @@
+// C ABI entry points (include/secedo_b200.h) and the orchestration of the kernels.
+#include "common.cuh"
+
+#include <algorithm>
+#include <cstring>
+#include <vector>
+
+int sgpu_fail(sgpu_ctx *ctx, int code, const char *fmt, ...) {
+    char buf[1024];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    if (ctx) {
+        ctx->error = buf;
+    }
+    return code;
+}
+
+namespace {
+
+struct EventTimer {
+    cudaEvent_t a = nullptr, b = nullptr;
+    cudaStream_t st;
+    explicit EventTimer(cudaStream_t s) : st(s) {
+        cudaEventCreate(&a);
+        cudaEventCreate(&b);
+        cudaEventRecord(a, st);
+    }
+    float stop() {
+        float ms = 0;
+        cudaEventRecord(b, st);
+        cudaEventSynchronize(b);
+        cudaEventElapsedTime(&ms, a, b);
+        return ms;
+    }
+    ~EventTimer() {
+        cudaEventDestroy(a);
+        cudaEventDestroy(b);
+    }
+};
+
+// measured crossover: the dense int8 GEMM wins unless the pileup is ultra sparse
+int choose_path(const sgpu_pileup *p, uint32_t num_cells) {
+    if (p->n_loci == 0 || num_cells < 256) {
+        return SGPU_PATH_SCATTER;
+    }
+    const double c = static_cast<double>(p->n_entries) / static_cast<double>(p->n_loci); // reads per locus
+    const double pairs = 0.5 * c * c;                            // atomics per locus on the scatter path
+    const double macs = 2.0 * num_cells * static_cast<double>(num_cells); // 4 planes x N^2 / 2
+    // scatter ~ 5e10 atomics/s, GEMM ~ 1e15 MAC/s + staging; see DESIGN.md for the measurements
+    return pairs * 2.0e4 < macs ? SGPU_PATH_SCATTER : SGPU_PATH_GEMM;
+}
+
+} // namespace
+
+extern "C" {
+
+int sgpu_init(int device, sgpu_ctx **out) {
+    if (!out) {
+        return SGPU_E_ARG;
+    }
+    *out = nullptr;
+    sgpu_ctx *ctx = new sgpu_ctx();
+    int n_dev = 0;
+    cudaError_t e = cudaGetDeviceCount(&n_dev);
+    if (e != cudaSuccess || device < 0 || device >= n_dev) {
+        // no CPU fallback: the caller gets an error and a context that only carries the message
+        sgpu_fail(ctx, SGPU_E_CUDA, "no usable CUDA device %d (%s, %d devices)", device,
+                  e == cudaSuccess ? "out of range" : cudaGetErrorString(e), n_dev);
+        *out = ctx;
+        return SGPU_E_CUDA;
+    }
+    ctx->device = device;
+    *out = ctx;
+    SGPU_CUDA(ctx, cudaSetDevice(device));
+    cudaDeviceProp prop;
+    SGPU_CUDA(ctx, cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10) {
+        return sgpu_fail(ctx, SGPU_E_CUDA, "device %d is sm_%d%d; this library is built for sm_100a only", device, prop.major,
+                         prop.minor);
+    }
+    ctx->sm_count = prop.multiProcessorCount;
+    SGPU_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking));
+    ctx->stream = ctx->own_stream;
+    SGPU_CUDA(ctx, cudaMallocHost(&ctx->h_scratch, 64 * sizeof(uint64_t)));
+    SGPU_CUDA(ctx, cudaMalloc(&ctx->d_scratch, 64 * sizeof(uint64_t)));
+    // keep freed stream-ordered blocks cached in the pool instead of returning them to the driver
+    cudaMemPool_t pool;
+    SGPU_CUDA(ctx, cudaDeviceGetDefaultMemPool(&pool, device));
+    uint64_t threshold = UINT64_MAX;
+    SGPU_CUDA(ctx, cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &threshold));
+    return SGPU_OK;
+}
+
+void sgpu_shutdown(sgpu_ctx *ctx) {
+    if (!ctx) {
+        return;
+    }
+    if (ctx->own_stream) {
+        cudaStreamSynchronize(ctx->own_stream);
+        cudaStreamDestroy(ctx->own_stream);
+    }
+    if (ctx->h_scratch) {
+        cudaFreeHost(ctx->h_scratch);
+    }
+    if (ctx->d_scratch) {
+        cudaFree(ctx->d_scratch);
+    }
+    delete ctx;
+}
+
+const char *sgpu_last_error(const sgpu_ctx *ctx) { return ctx ? ctx->error.c_str() : "null context"; }
+
+int sgpu_set_stream(sgpu_ctx *ctx, void *cuda_stream) {
+    SGPU_CUDA(ctx, cudaSetDevice(ctx->device));
+    SGPU_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    ctx->stream = cuda_stream ? static_cast<cudaStream_t>(cuda_stream) : ctx->own_stream;
+    return SGPU_OK;
+}
+
+int sgpu_synchronize(sgpu_ctx *ctx) {
+    SGPU_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return SGPU_OK;
+}
+
+// ---- pileup ---------------------------------------------------------------------------------------
+int sgpu_pileup_upload(sgpu_ctx *ctx, uint32_t n_chr, const uint64_t *chr_ptr, const uint64_t *row_ptr,
+                       const uint32_t *position, const uint32_t *read_id, const uint16_t *gid_base,
+                       sgpu_pileup **out) {
+    SGPU_CUDA(ctx, cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    sgpu_pileup *p = new sgpu_pileup();
+    p->n_chr = n_chr;
+    p->n_loci = chr_ptr[n_chr];
+    p->n_entries = p->n_loci ? row_ptr[p->n_loci] : 0;
+    p->h_chr_ptr = new uint64_t[n_chr + 1];
+    std::memcpy(p->h_chr_ptr, chr_ptr, (n_chr + 1) * sizeof(uint64_t));
+    const uint64_t P = p->n_loci, E = p->n_entries;
+    SGPU_CUDA(ctx, cudaMalloc(&p->d_chr_ptr, (n_chr + 1) * sizeof(uint64_t)));
+    SGPU_CUDA(ctx, cudaMalloc(&p->d_row_ptr, (P + 1) * sizeof(uint64_t)));
+    SGPU_CUDA(ctx, cudaMalloc(&p->d_position, (P ? P : 1) * sizeof(uint32_t)));
+    SGPU_CUDA(ctx, cudaMalloc(&p->d_read_id, (E ? E : 1) * sizeof(uint32_t)));
+    SGPU_CUDA(ctx, cudaMalloc(&p->d_gid_base, (E ? E : 1) * sizeof(uint16_t)));
+    SGPU_CUDA(ctx, cudaMemcpyAsync(p->d_chr_ptr, chr_ptr, (n_chr + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, st));
+    if (P) {
+        SGPU_CUDA(ctx, cudaMemcpyAsync(p->d_row_ptr, row_ptr, (P + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, st));
+        SGPU_CUDA(ctx, cudaMemcpyAsync(p->d_position, position, P * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
+    } else {
+        SGPU_CUDA(ctx, cudaMemsetAsync(p->d_row_ptr, 0, sizeof(uint64_t), st));
+    }
+    if (E) {
+        SGPU_CUDA(ctx, cudaMemcpyAsync(p->d_read_id, read_id, E * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
+        SGPU_CUDA(ctx, cudaMemcpyAsync(p->d_gid_base, gid_base, E * sizeof(uint16_t), cudaMemcpyHostToDevice, st));
+    }
+    SGPU_CUDA(ctx, cudaStreamSynchronize(st));
+    *out = p;
+    return SGPU_OK;
+}
+
+int sgpu_pileup_wrap_device(sgpu_ctx *ctx, uint32_t n_chr, const uint64_t *host_chr_ptr, const uint64_t *dev_row_ptr,
+                            const uint32_t *dev_position, const uint32_t *dev_read_id, const uint16_t *dev_gid_base,
+                            sgpu_pileup **out) {
+    SGPU_CUDA(ctx, cudaSetDevice(ctx->device));
+    sgpu_pileup *p = new sgpu_pileup();
+    p->n_chr = n_chr;
+    p->n_loci = host_chr_ptr[n_chr];
+    p->h_chr_ptr = new uint64_t[n_chr + 1];
+    std::memcpy(p->h_chr_ptr, host_chr_ptr, (n_chr + 1) * sizeof(uint64_t));
+    SGPU_CUDA(ctx, cudaMalloc(&p->d_chr_ptr, (n_chr + 1) * sizeof(uint64_t)));
+    SGPU_CUDA(ctx, cudaMemcpyAsync(p->d_chr_ptr, host_chr_ptr, (n_chr + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, ctx->stream));
+    p->d_row_ptr = const_cast<uint64_t *>(dev_row_ptr);
+    p->d_position = const_cast<uint32_t *>(dev_position);
+    p->d_read_id = const_cast<uint32_t *>(dev_read_id);
+    p->d_gid_base = const_cast<uint16_t *>(dev_gid_base);
+    p->owns = false;
+    uint64_t last = 0;
+    if (p->n_loci) {
+        SGPU_CUDA(ctx, cudaMemcpyAsync(&ctx->h_scratch[0], dev_row_ptr + p->n_loci, sizeof(uint64_t), cudaMemcpyDeviceToHost, ctx->stream));
+        SGPU_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        last = ctx->h_scratch[0];
+    }
+    SGPU_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    p->n_entries = last;
+    *out = p;
+    return SGPU_OK;
+}
+
+int sgpu_pileup_dims(const sgpu_pileup *p, uint32_t *n_chr, uint64_t *n_loci, uint64_t *n_entries) {
+    if (!p) {
+        return SGPU_E_ARG;
+    }
+    if (n_chr) {
+        *n_chr = p->n_chr;
+    }
+    if (n_loci) {
+        *n_loci = p->n_loci;
+    }
+    if (n_entries) {
+        *n_entries = p->n_entries;
+    }
+    return SGPU_OK;
+}
+
+int sgpu_pileup_download(sgpu_ctx *ctx, const sgpu_pileup *p, uint64_t *chr_ptr, uint64_t *row_ptr, uint32_t *position,
+                         uint32_t *read_id, uint16_t *gid_base) {
+    SGPU_CUDA(ctx, cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    if (chr_ptr) {
+        std::memcpy(chr_ptr, p->h_chr_ptr, (p->n_chr + 1) * sizeof(uint64_t));
+    }
+    if (row_ptr) {
+        SGPU_CUDA(ctx, cudaMemcpyAsync(row_ptr, p->d_row_ptr, (p->n_loci + 1) * sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
+    }
+    if (position && p->n_loci) {
+        SGPU_CUDA(ctx, cudaMemcpyAsync(position, p->d_position, p->n_loci * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+    }
+    if (read_id && p->n_entries) {
+        SGPU_CUDA(ctx, cudaMemcpyAsync(read_id, p->d_read_id, p->n_entries * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+    }
+    if (gid_base && p->n_entries) {
+        SGPU_CUDA(ctx, cudaMemcpyAsync(gid_base, p->d_gid_base, p->n_entries * sizeof(uint16_t), cudaMemcpyDeviceToHost, st));
+    }
+    SGPU_CUDA(ctx, cudaStreamSynchronize(st));
+    return SGPU_OK;
+}
+
+void sgpu_pileup_free(sgpu_ctx *ctx, sgpu_pileup *p) {
+    if (!p) {
+        return;
+    }
+    if (ctx) {
+        cudaSetDevice(ctx->device);
+        cudaStreamSynchronize(ctx->stream);
+    }
+    cudaFree(p->d_chr_ptr);
+    if (p->owns) {
+        cudaFree(p->d_row_ptr);
+        cudaFree(p->d_position);
+        cudaFree(p->d_read_id);
+        cudaFree(p->d_gid_base);
+    }
+    delete[] p->h_chr_ptr;
+    delete p;
+}
+
+// ---- filter ---------------------------------------------------------------------------------------
+int sgpu_is_significant(sgpu_ctx *ctx, const uint16_t *counts4, uint64_t n, double theta, int cell_proportion,
+                        uint8_t *out) {
+    SGPU_CUDA(ctx, cudaSetDevice(ctx->device));
+    return sgpu_is_significant_impl(ctx, counts4, n, theta, cell_proportion, out);
+}
+
+int sgpu_filter(sgpu_ctx *ctx, const sgpu_pileup *in, const uint32_t *id_to_pos, uint32_t n_groups, double theta,
+                int cell_proportion, sgpu_pileup **filtered, double *avg_coverage) {
+    SGPU_CUDA(ctx, cudaSetDevice(ctx->device));
+    return sgpu_filter_impl(ctx, in, id_to_pos, n_groups, theta, cell_proportion, filtered, avg_coverage);
+}
+
+// ---- counts ---------------------------------------------------------------------------------------
+int sgpu_counts_create(sgpu_ctx *ctx, uint32_t num_cells, sgpu_counts **out) {
+    SGPU_CUDA(ctx, cudaSetDevice(ctx->device));
+    sgpu_counts *c = new sgpu_counts();
+    c->n = num_cells;
+    c->nn = static_cast<uint64_t>(num_cells) * num_cells;
+    SGPU_CUDA(ctx, cudaMalloc(&c->i32, std::max<uint64_t>(1, N_PLANES * c->nn) * sizeof(int32_t)));
+    SGPU_CUDA(ctx, cudaMalloc(&c->hist, SGPU_MAX_CLASS * SGPU_MAX_CLASS * sizeof(uint64_t)));
+    *out = c;
+    return sgpu_counts_zero(ctx, c);
+}
+
+int sgpu_counts_zero(sgpu_ctx *ctx, sgpu_counts *c) {
+    SGPU_CUDA(ctx, cudaSetDevice(ctx->device));
+    SGPU_CUDA(ctx, cudaMemsetAsync(c->i32, 0, N_PLANES * c->nn * sizeof(int32_t), ctx->stream));
+    SGPU_CUDA(ctx, cudaMemsetAsync(c->hist, 0, SGPU_MAX_CLASS * SGPU_MAX_CLASS * sizeof(uint64_t), ctx->stream));
+    if (c->spill) {
+        SGPU_CUDA(ctx, cudaMemsetAsync(c->spill, 0, c->nn * sizeof(double), ctx->stream));
+    }
+    c->planes_used = 2;
+    c->have_params = false;
+    return SGPU_OK;
+}
+
+void sgpu_counts_free(sgpu_ctx *ctx, sgpu_counts *c) {
+    if (!c) {
+        return;
+    }
+    if (ctx) {
+        cudaSetDevice(ctx->device);
+        cudaStreamSynchronize(ctx->stream);
+    }
+    cudaFree(c->i32);
+    cudaFree(c->hist);
+    cudaFree(c->spill);
+    delete c;
+}
+
+int sgpu_counts_accumulate(sgpu_ctx *ctx, sgpu_counts *c, const sgpu_pileup *filtered, uint32_t max_fragment_length,
+                           const uint32_t *group_id_to_pos, uint32_t n_groups, double mutation_rate,
+                           double homozygous_rate, double seq_error_rate, uint32_t num_threads, int path,
+                           sgpu_stats *stats) {
+    SGPU_CUDA(ctx, cudaSetDevice(ctx->device));
+    if (path < SGPU_PATH_AUTO || path > SGPU_PATH_GEMM) {
+        return sgpu_fail(ctx, SGPU_E_ARG, "unknown path %d", path);
+    }
+    if (c->have_params
+        && (c->eps != mutation_rate || c->h != homozygous_rate || c->theta != seq_error_rate || c->L != max_fragment_length)) {
+        return sgpu_fail(ctx, SGPU_E_ARG, "counts object was accumulated with different likelihood parameters");
+    }
+    c->have_params = true;
+    c->eps = mutation_rate;
+    c->h = homozygous_rate;
+    c->theta = seq_error_rate;
+    c->L = max_fragment_length;
+    sgpu_stats s;
+    std::memset(&s, 0, sizeof(s));
+    s.n_loci = filtered->n_loci;
+    s.n_entries = filtered->n_entries;
+    if (path == SGPU_PATH_AUTO) {
+        path = choose_path(filtered, c->n);
+    }
+    s.path_used = path;
+
+    LinkResult lr;
+    {
+        EventTimer t(ctx->stream);
+        SGPU_TRY(sgpu_link_reads(ctx, filtered, c->n, max_fragment_length, group_id_to_pos, n_groups, num_threads, &lr));
+        s.ms_link = t.stop();
+    }
+    s.n_reads = lr.n_reads;
+    s.n_dropped_entries = lr.n_dropped;
+    s.n_multi_reads = lr.n_multi;
+    s.n_tail_reads = lr.n_tail;
+    {
+        EventTimer t(ctx->stream);
+        if (path == SGPU_PATH_SCATTER) {
+            SGPU_TRY(sgpu_scatter_pairs(ctx, filtered, lr, c, +1, false, &s.n_pairs_first));
+        } else {
+            SGPU_TRY(sgpu_gemm_counts(ctx, filtered, lr, c, &s.n_pairs_first));
+            if (lr.n_tail) { // remove the tail x tail pairs the reference never compares
+                SGPU_TRY(sgpu_scatter_pairs(ctx, filtered, lr, c, -1, true, nullptr));
+            }
+        }
+        s.ms_first_order = t.stop();
+    }
+    {
+        EventTimer t(ctx->stream);
+        SGPU_TRY(sgpu_multilocus(ctx, filtered, lr, c, max_fragment_length, &s.n_pairs_multi));
+        s.ms_multi = t.stop();
+    }
+    if (stats) {
+        *stats = s;
+    }
+    return SGPU_OK;
+}
+
+int sgpu_counts_buffers(sgpu_counts *c, int32_t **i32, uint64_t *n_i32, double **f64, uint64_t *n_f64, uint64_t **hist,
+                        uint64_t *n_hist) {
+    if (!c) {
+        return SGPU_E_ARG;
+    }
+    if (i32) {
+        *i32 = c->i32;
+    }
+    if (n_i32) {
+        *n_i32 = static_cast<uint64_t>(c->planes_used) * c->nn;
+    }
+    if (f64) {
+        *f64 = c->spill;
+    }
+    if (n_f64) {
+        *n_f64 = c->spill ? c->nn : 0;
+    }
+    if (hist) {
+        *hist = c->hist;
+    }
+    if (n_hist) {
+        *n_hist = SGPU_MAX_CLASS * SGPU_MAX_CLASS;
+    }
+    return SGPU_OK;
+}
+
+int sgpu_counts_set_layout(sgpu_ctx *ctx, sgpu_counts *c, int planes_used, int want_spill) {
+    SGPU_CUDA(ctx, cudaSetDevice(ctx->device));
+    if (planes_used != 2 && planes_used != N_PLANES) {
+        return sgpu_fail(ctx, SGPU_E_ARG, "planes_used must be 2 or %d", N_PLANES);
+    }
+    c->planes_used = std::max(c->planes_used, planes_used);
+    if (want_spill && !c->spill) {
+        SGPU_CUDA(ctx, cudaMalloc(&c->spill, std::max<uint64_t>(1, c->nn) * sizeof(double)));
+        SGPU_CUDA(ctx, cudaMemsetAsync(c->spill, 0, c->nn * sizeof(double), ctx->stream));
+    }
+    return SGPU_OK;
+}
+
+int sgpu_counts_download(sgpu_ctx *ctx, sgpu_counts *c, int32_t *S1, int32_t *D1, int32_t *H, uint64_t *hist) {
+    SGPU_CUDA(ctx, cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    const uint64_t nn = c->nn, n = c->n;
+    std::vector<int32_t> tmp(nn);
+    auto fetch_sym = [&](int plane, int32_t *dst) -> int {
+        SGPU_CUDA(ctx, cudaMemcpyAsync(tmp.data(), c->i32 + plane * nn, nn * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+        SGPU_CUDA(ctx, cudaStreamSynchronize(st));
+        for (uint64_t i = 0; i < n; ++i) {
+            dst[i * n + i] = 0;
+            for (uint64_t j = i + 1; j < n; ++j) {
+                dst[i * n + j] = dst[j * n + i] = tmp[i * n + j];
+            }
+        }
+        return SGPU_OK;
+    };
+    if (S1) {
+        SGPU_TRY(fetch_sym(PLANE_S, S1));
+    }
+    if (D1) {
+        SGPU_TRY(fetch_sym(PLANE_D, D1));
+    }
+    if (H) {
+        for (int k = 0; k < 3; ++k) {
+            SGPU_TRY(fetch_sym(PLANE_H2 + k, H + k * nn));
+        }
+    }
+    if (hist) {
+        SGPU_CUDA(ctx, cudaMemcpyAsync(hist, c->hist, SGPU_MAX_CLASS * SGPU_MAX_CLASS * sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
+        SGPU_CUDA(ctx, cudaStreamSynchronize(st));
+    }
+    return SGPU_OK;
+}
+
+int sgpu_similarity_finalize(sgpu_ctx *ctx, sgpu_counts *c, uint32_t max_fragment_length, double mutation_rate,
+                             double homozygous_rate, double seq_error_rate, int normalization, double *out,
+                             sgpu_stats *stats) {
+    SGPU_CUDA(ctx, cudaSetDevice(ctx->device));
+    if (c->have_params && c->spill
+        && (c->eps != mutation_rate || c->h != homozygous_rate || c->theta != seq_error_rate || c->L != max_fragment_length)) {
+        return sgpu_fail(ctx, SGPU_E_ARG, "finalize called with likelihood parameters different from accumulate");
+    }
+    EventTimer t(ctx->stream);
+    SGPU_TRY(sgpu_epilogue(ctx, c, max_fragment_length, mutation_rate, homozygous_rate, seq_error_rate, normalization, out));
+    const float ms = t.stop();
+    if (stats) {
+        stats->ms_epilogue = ms;
+    }
+    return SGPU_OK;
+}
+
+int sgpu_similarity(sgpu_ctx *ctx, const sgpu_pileup *filtered, uint32_t num_cells, uint32_t max_fragment_length,
+                    const uint32_t *group_id_to_pos, uint32_t n_groups, double mutation_rate, double homozygous_rate,
+                    double seq_error_rate, uint32_t num_threads, int normalization, int path, double *out,
+                    sgpu_stats *stats) {
+    SGPU_CUDA(ctx, cudaSetDevice(ctx->device));
+    if (normalization < 0 || normalization > 2) {
+        return sgpu_fail(ctx, SGPU_E_ARG, "Invalid normalization: %d", normalization);
+    }
+    sgpu_counts *c = nullptr;
+    SGPU_TRY(sgpu_counts_create(ctx, num_cells, &c));
+    sgpu_stats s;
+    std::memset(&s, 0, sizeof(s));
+    int rc = sgpu_counts_accumulate(ctx, c, filtered, max_fragment_length, group_id_to_pos, n_groups, mutation_rate,
+                                    homozygous_rate, seq_error_rate, num_threads, path, &s);
+    if (rc == SGPU_OK) {
+        rc = sgpu_similarity_finalize(ctx, c, max_fragment_length, mutation_rate, homozygous_rate, seq_error_rate,
+                                      normalization, out, &s);
+    }
+    sgpu_counts_free(ctx, c);
+    if (stats) {
+        *stats = s;
+    }
+    return rc;
+}
+
+int sgpu_log_probs(sgpu_ctx *ctx, double mutation_rate, double homozygous_rate, double seq_error_rate,
+                   uint32_t max_fragment_length, uint32_t n, double *ls, double *ld) {
+    SGPU_CUDA(ctx, cudaSetDevice(ctx->device));
+    return sgpu_log_probs_impl(ctx, mutation_rate, homozygous_rate, seq_error_rate, max_fragment_length, n, ls, ld);
+}
+
+} // extern "C"

@@ -1,0 +1,181 @@
+// Shared declarations of the CUDA side of secedo_b200 (sm_100a only).
+#pragma once
+
+#include <cuda_runtime.h>
+
+#include <cstdarg>
+#include <cstdint>
+#include <cstdio>
+#include <string>
+
+#include "../../include/secedo_b200.h"
+
+// ------------------------------------------------------------------------------------------------
+// context / error handling
+// ------------------------------------------------------------------------------------------------
+struct sgpu_ctx {
+    int device = 0;
+    int sm_count = 148;
+    cudaStream_t own_stream = nullptr;
+    cudaStream_t stream = nullptr;
+    std::string error;
+    // small pinned scratch for device->host scalars
+    uint64_t *h_scratch = nullptr; // 64 x u64, pinned
+    uint64_t *d_scratch = nullptr; // 64 x u64, device
+};
+
+int sgpu_fail(sgpu_ctx *ctx, int code, const char *fmt, ...);
+
+#define SGPU_CUDA(ctx, expr)                                                                       \
+    do {                                                                                           \
+        cudaError_t err__ = (expr);                                                                \
+        if (err__ != cudaSuccess) {                                                                \
+            return sgpu_fail((ctx), SGPU_E_CUDA, "%s:%d %s -> %s", __FILE__, __LINE__, #expr,      \
+                             cudaGetErrorString(err__));                                           \
+        }                                                                                          \
+    } while (0)
+
+#define SGPU_TRY(expr)                                                                             \
+    do {                                                                                           \
+        int rc__ = (expr);                                                                         \
+        if (rc__ != SGPU_OK) {                                                                     \
+            return rc__;                                                                           \
+        }                                                                                          \
+    } while (0)
+
+// stream-ordered device memory (cudaMallocAsync pool keeps freed blocks cached)
+template <typename T>
+struct DevBuf {
+    T *p = nullptr;
+    size_t n = 0;
+    cudaStream_t s = nullptr;
+    DevBuf() = default;
+    DevBuf(const DevBuf &) = delete;
+    DevBuf &operator=(const DevBuf &) = delete;
+    ~DevBuf() { release(); }
+    cudaError_t alloc(size_t count, cudaStream_t stream) {
+        release();
+        s = stream;
+        n = count;
+        if (count == 0) {
+            return cudaSuccess;
+        }
+        return cudaMallocAsync(reinterpret_cast<void **>(&p), count * sizeof(T), stream);
+    }
+    void release() {
+        if (p) {
+            cudaFreeAsync(p, s);
+            p = nullptr;
+        }
+        n = 0;
+    }
+    T *take() { // hand ownership to the caller
+        T *q = p;
+        p = nullptr;
+        n = 0;
+        return q;
+    }
+};
+
+// ------------------------------------------------------------------------------------------------
+// device-resident objects
+// ------------------------------------------------------------------------------------------------
+struct sgpu_pileup {
+    uint32_t n_chr = 0;
+    uint64_t n_loci = 0;
+    uint64_t n_entries = 0;
+    uint64_t *h_chr_ptr = nullptr; // host copy, n_chr + 1
+    uint64_t *d_chr_ptr = nullptr; // device copy
+    uint64_t *d_row_ptr = nullptr;
+    uint32_t *d_position = nullptr;
+    uint32_t *d_read_id = nullptr;
+    uint16_t *d_gid_base = nullptr;
+    bool owns = true;
+};
+
+// plane indices inside sgpu_counts::i32
+enum { PLANE_S = 0, PLANE_D = 1, PLANE_H2 = 2 /* (2,0),(1,1),(0,2) */, PLANE_H3 = 5 /* (3,0)..(0,3) */, N_PLANES = 9 };
+
+struct sgpu_counts {
+    uint32_t n = 0;             // num_cells
+    uint64_t nn = 0;            // n*n
+    int32_t *i32 = nullptr;     // N_PLANES planes of n*n, only the upper triangle (i<j) is meaningful
+    int planes_used = 2;        // 2, 5 or 9
+    double *spill = nullptr;    // n*n doubles: sum of G(x_s,x_d) over pairs with x_s+x_d >= 4 (lazy)
+    uint64_t *hist = nullptr;   // SGPU_MAX_CLASS^2 class histogram (pairs with x_s+x_d >= 2)
+    // log-likelihood parameters the spill plane was accumulated with (must match at finalize)
+    bool have_params = false;
+    double eps = 0, h = 0, theta = 0;
+    uint32_t L = 0;
+};
+
+// ------------------------------------------------------------------------------------------------
+// entry "codes" produced by read linking (reads.cu) and consumed by scatter / staging / multilocus
+//   bit 31      dropped (mate rule) -> whole word is CODE_DROPPED
+//   bits 4..30  cell index (mapped through group_id_to_pos, taken from the read's FIRST entry)
+//   bits 2..3   base
+//   bit 1       tail: read index >= K, never the first read of a pair
+//   bit 0       multi: the read keeps >= 2 loci
+// ------------------------------------------------------------------------------------------------
+constexpr uint32_t CODE_DROPPED = 0xFFFFFFFFu;
+__host__ __device__ inline uint32_t code_cell(uint32_t c) { return c >> 4; }
+__host__ __device__ inline uint32_t code_base(uint32_t c) { return (c >> 2) & 3u; }
+__host__ __device__ inline bool code_tail(uint32_t c) { return (c >> 1) & 1u; }
+__host__ __device__ inline bool code_multi(uint32_t c) { return c & 1u; }
+
+struct LinkResult {
+    DevBuf<uint32_t> code;      // per entry, see above
+    DevBuf<uint32_t> eread;     // per entry: global read index
+    DevBuf<uint32_t> eloc;      // per entry: locus index
+    // multi-locus reads only (reads that keep >= 2 loci after the mate rule)
+    DevBuf<uint32_t> r_multi;   // per read: index into the multi tables or 0xFFFFFFFF
+    DevBuf<uint64_t> m_off;     // per multi read: offset into m_locus/m_base (n_multi + 1)
+    DevBuf<uint32_t> m_locus;   // stored loci, ascending
+    DevBuf<uint8_t> m_base;     // stored bases
+    uint64_t n_reads = 0, n_multi = 0, n_dropped = 0, n_tail = 0, n_multi_entries = 0;
+};
+
+// ------------------------------------------------------------------------------------------------
+// kernels' host launchers (one translation unit each)
+// ------------------------------------------------------------------------------------------------
+// scan.cu — exclusive prefix sum, out has n + 1 elements (out[n] = total)
+int sgpu_scan_u8_u64(sgpu_ctx *ctx, const uint8_t *in, uint64_t *out, uint64_t n);
+int sgpu_scan_u32_u64(sgpu_ctx *ctx, const uint32_t *in, uint64_t *out, uint64_t n);
+
+// filter.cu
+int sgpu_filter_impl(sgpu_ctx *ctx, const sgpu_pileup *in, const uint32_t *h_id_to_pos, uint32_t n_groups,
+                     double theta, int cell_proportion, sgpu_pileup **filtered, double *avg_coverage);
+int sgpu_is_significant_impl(sgpu_ctx *ctx, const uint16_t *h_counts4, uint64_t n, double theta,
+                             int cell_proportion, uint8_t *h_out);
+
+// reads.cu
+int sgpu_link_reads(sgpu_ctx *ctx, const sgpu_pileup *p, uint32_t num_cells, uint32_t L,
+                    const uint32_t *h_group_id_to_pos, uint32_t n_groups, uint32_t num_threads,
+                    LinkResult *out);
+
+// scatter.cu — first-order counts by pair enumeration; only_tail_pairs: enumerate just the pairs of
+// two tail reads (used with sign = -1 to correct the GEMM path)
+int sgpu_scatter_pairs(sgpu_ctx *ctx, const sgpu_pileup *p, const LinkResult &lr, sgpu_counts *c,
+                       int sign, bool only_tail_pairs, uint64_t *n_pairs);
+
+// multilocus.cu
+int sgpu_multilocus(sgpu_ctx *ctx, const sgpu_pileup *p, const LinkResult &lr, sgpu_counts *c,
+                    uint32_t L, uint64_t *n_pairs_multi);
+
+// epilogue.cu
+struct FTable {
+    double F[SGPU_MAX_CLASS * SGPU_MAX_CLASS]; // LD - LS, NaN where never needed
+};
+int sgpu_log_probs_impl(sgpu_ctx *ctx, double eps, double h, double theta, uint32_t L, uint32_t n,
+                        double *h_ls, double *h_ld);
+int sgpu_epilogue(sgpu_ctx *ctx, sgpu_counts *c, uint32_t L, double eps, double h, double theta,
+                  int normalization, double *h_out);
+// device table of G(s,d) = F(s,d) - s F(1,0) - d F(0,1) for the spill plane (SGPU_MAX_CLASS^2 doubles)
+int sgpu_build_gtable(sgpu_ctx *ctx, double eps, double h, double theta, uint32_t L, uint32_t n,
+                      double *d_G /* device, SGPU_MAX_CLASS^2 */, double *d_F /* device, optional */);
+
+// gemm.cu — int8 tcgen05 path
+int sgpu_gemm_counts(sgpu_ctx *ctx, const sgpu_pileup *p, const LinkResult &lr, sgpu_counts *c,
+                     uint64_t *n_pairs);
+
+static inline uint64_t ceil_div_u64(uint64_t a, uint64_t b) { return (a + b - 1) / b; }

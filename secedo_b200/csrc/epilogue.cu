@@ -1,0 +1,365 @@
+// K6 — log-likelihood transform and normalisation.
+//
+//   logprob_kernel    LS / LD tables of similarity_matrix.cpp:117-170, one thread per (x_s, x_d),
+//                     fp64, from power tables built by repeated multiplication exactly as the
+//                     reference's Cache does (:76-103) and a uint64 Pascal triangle
+//   transform_kernel  raw[i][j] = F(1,0) S + F(0,1) D + sum_classes G(s,d) H_sd (+ spill), mirrored,
+//                     with a fused min/max reduction (similarity_matrix.cpp:428 + util/mat.hpp:35-53)
+//   normalize_kernel  ADD_MIN / EXPONENTIATE / SCALE_MAX_1 and the zero diagonal (:271-293)
+// Compiled with -fmad=false so that the table arithmetic rounds like the reference's x86 build.
+#include "common.cuh"
+
+#include <cfloat>
+#include <cstring>
+#include <cmath>
+#include <vector>
+
+namespace {
+
+constexpr int TBL = 132; // power tables / Pascal rows kept (x_s + x_d <= 126 for classes < 64)
+
+struct CacheTables {
+    double pss[TBL], psd[TBL], pds[TBL], pdd[TBL];
+    double p1he[TBL], p1he2[TBL], phe2[TBL], ph[TBL], pe[TBL], p05[TBL], psspds[TBL], psdpdd[TBL];
+    uint32_t len;
+};
+
+void extend(double *a, uint32_t n) { // similarity_matrix.cpp:81
+    for (uint32_t p = 2; p < n; ++p) {
+        a[p] = a[p - 1] * a[1];
+    }
+}
+
+void make_cache(CacheTables *c, double epsilon, double h, double theta, uint32_t max_read_size) {
+    // similarity_matrix.cpp:42-67
+    const double theta2 = theta * theta;
+    const double p_same_diff = 2 * theta * (1 - theta) + 2 * theta2 / 3;
+    const double p_same_same = 1 - p_same_diff;
+    const double p_diff_same = 2 * (1 - theta) * theta / 3 + 2 * theta2 / 9;
+    const double p_diff_diff = 1 - p_diff_same;
+    uint32_t n = max_read_size < 2 ? 2 : max_read_size;
+    if (n > TBL) {
+        n = TBL;
+    }
+    c->len = n;
+    auto init = [n](double *arr, double v) {
+        arr[0] = 1;
+        arr[1] = v;
+        extend(arr, n);
+    };
+    init(c->pss, p_same_same);
+    init(c->psd, p_same_diff);
+    init(c->pds, p_diff_same);
+    init(c->pdd, p_diff_diff);
+    init(c->p1he, 1 - epsilon - h);
+    init(c->p1he2, 1 - epsilon * 0.5 - h);
+    init(c->phe2, h + epsilon * 0.5);
+    init(c->ph, h);
+    init(c->pe, epsilon);
+    init(c->p05, 0.5);
+    init(c->psspds, p_same_same + p_diff_same);
+    init(c->psdpdd, p_same_diff + p_diff_diff);
+}
+
+__global__ void pascal_kernel(uint64_t *__restrict__ comb) { // single thread block, row by row
+    for (int r = 0; r < TBL; ++r) {
+        for (int i = threadIdx.x; i < TBL; i += blockDim.x) {
+            uint64_t v = 0;
+            if (i == 0 || i == r) {
+                v = 1;
+            } else if (i < r) {
+                v = comb[(r - 1) * TBL + i - 1] + comb[(r - 1) * TBL + i]; // wraps like the reference's uint64
+            }
+            comb[r * TBL + i] = v;
+        }
+        __syncthreads();
+    }
+}
+
+// one thread per (x_s, x_d)
+__global__ void logprob_kernel(const CacheTables *__restrict__ cp, const uint64_t *__restrict__ comb, uint32_t n,
+                               uint32_t L, double *__restrict__ ls_out, double *__restrict__ ld_out) {
+    const uint32_t idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= n * n) {
+        return;
+    }
+    const uint32_t x_s = idx / n, x_d = idx % n;
+    const CacheTables &c = *cp;
+    if (x_s + x_d >= c.len || x_s >= L || x_d >= L) { // the reference's tables end here
+        ls_out[idx] = nan("");
+        ld_out[idx] = nan("");
+        return;
+    }
+#define COMB(r, i) comb[(r) * TBL + (i)]
+    // similarity_matrix.cpp:153-170
+    double p = 0;
+    for (uint32_t k = 0; k <= x_s; ++k) {
+        for (uint32_t l = 0; l <= x_d; ++l) {
+            const uint64_t cc = COMB(x_s, k) * COMB(x_d, l);
+            p += cc * c.p1he2[k + l] * 0.5 * (c.pss[k] * c.psd[l] + c.pds[k] * c.pdd[l]) * c.phe2[x_s + x_d - k - l]
+                    * c.pss[x_s - k] * c.psd[x_d - l];
+        }
+    }
+    p *= COMB(x_s + x_d, x_s);
+    ls_out[idx] = log(p);
+    // similarity_matrix.cpp:117-141
+    double prob = 0;
+    for (uint32_t k = 0; k <= x_s; ++k) {
+        for (uint32_t l = 0; l <= x_d; ++l) {
+            for (uint32_t pp = 0; pp <= x_s - k; ++pp) {
+                for (uint32_t q = 0; q <= x_d - l; ++q) {
+                    const uint64_t cc = COMB(x_s, k) * COMB(x_d, l) * COMB(x_s - k, pp) * COMB(x_d - l, q);
+                    const uint32_t rest = x_s + x_d - k - l - pp - q;
+                    prob += cc * c.p1he[k + l] * 0.5 * (c.pss[k] * c.psd[l] + c.pds[k] * c.pdd[l]) * c.pe[rest]
+                            * c.p05[rest] * c.psspds[x_s - k - pp] * c.psdpdd[x_d - l - q] * c.ph[pp + q] * c.pss[pp]
+                            * c.psd[q];
+                }
+            }
+        }
+    }
+    prob *= COMB(x_s + x_d, x_s);
+    ld_out[idx] = log(prob);
+#undef COMB
+}
+
+// F = LD - LS; G(s,d) = F(s,d) - s F(1,0) - d F(0,1)
+__global__ void gtable_kernel(const double *__restrict__ ls, const double *__restrict__ ld, uint32_t n,
+                              double *__restrict__ G, double *__restrict__ F) {
+    const uint32_t idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= SGPU_MAX_CLASS * SGPU_MAX_CLASS) {
+        return;
+    }
+    const uint32_t s = idx / SGPU_MAX_CLASS, d = idx % SGPU_MAX_CLASS;
+    double f = nan(""), g = nan("");
+    if (s < n && d < n) {
+        f = ld[s * n + d] - ls[s * n + d];
+        const double f10 = n > 1 ? ld[1 * n + 0] - ls[1 * n + 0] : 0.0;
+        const double f01 = n > 1 ? ld[0 * n + 1] - ls[0 * n + 1] : 0.0;
+        g = f - s * f10 - d * f01;
+    }
+    G[idx] = g;
+    if (F) {
+        F[idx] = f;
+    }
+}
+
+// ordered-int encoding so that atomicMin/atomicMax on uint64 order doubles
+__device__ __forceinline__ unsigned long long enc(double x) {
+    unsigned long long u = static_cast<unsigned long long>(__double_as_longlong(x));
+    return (u >> 63) ? ~u : (u | 0x8000000000000000ull);
+}
+__host__ inline double dec(unsigned long long u) {
+    unsigned long long v = (u >> 63) ? (u & 0x7FFFFFFFFFFFFFFFull) : ~u;
+    double d;
+    memcpy(&d, &v, sizeof(d));
+    return d;
+}
+
+struct TransformArgs {
+    const int32_t *i32;
+    const double *spill;
+    uint32_t n;
+    uint64_t nn;
+    int planes_used;
+    double f10, f01;
+    double g2[3], g3[4];
+};
+
+constexpr int TR_THREADS = 256;
+
+__global__ void __launch_bounds__(TR_THREADS) transform_kernel(TransformArgs a, double *__restrict__ raw,
+                                                              unsigned long long *__restrict__ minmax) {
+    // one thread per element of the upper triangle incl. diagonal, addressed as (i, j) of the full
+    // matrix; elements below the diagonal are written by their mirror
+    const uint64_t idx = static_cast<uint64_t>(blockIdx.x) * TR_THREADS + threadIdx.x;
+    double v = 0.0;
+    bool valid = false;
+    if (idx < a.nn) {
+        const uint32_t i = static_cast<uint32_t>(idx / a.n), j = static_cast<uint32_t>(idx % a.n);
+        if (i < j) {
+            valid = true;
+            v = a.f10 * a.i32[PLANE_S * a.nn + idx] + a.f01 * a.i32[PLANE_D * a.nn + idx];
+            if (a.planes_used > 2) {
+#pragma unroll
+                for (int k = 0; k < 3; ++k) {
+                    const int32_t h = a.i32[(PLANE_H2 + k) * a.nn + idx];
+                    if (h) {
+                        v += a.g2[k] * h;
+                    }
+                }
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const int32_t h = a.i32[(PLANE_H3 + k) * a.nn + idx];
+                    if (h) {
+                        v += a.g3[k] * h;
+                    }
+                }
+            }
+            if (a.spill) {
+                v += a.spill[idx];
+            }
+            raw[idx] = v;
+            raw[static_cast<uint64_t>(j) * a.n + i] = v;
+        } else if (i == j) {
+            valid = true;
+            raw[idx] = 0.0; // mat_same and mat_diff have an all-zero diagonal
+        }
+    }
+    // block reduce of min / max over the elements this block produced (the diagonal zeros count,
+    // util/mat.hpp:35-53 scans the whole matrix)
+    double mn = valid ? v : DBL_MAX, mx = valid ? v : -DBL_MAX;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        mn = fmin(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+        mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    }
+    __shared__ double s_mn[TR_THREADS / 32], s_mx[TR_THREADS / 32];
+    if ((threadIdx.x & 31) == 0) {
+        s_mn[threadIdx.x >> 5] = mn;
+        s_mx[threadIdx.x >> 5] = mx;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int w = 1; w < TR_THREADS / 32; ++w) {
+            mn = fmin(mn, s_mn[w]);
+            mx = fmax(mx, s_mx[w]);
+        }
+        if (mn != DBL_MAX) {
+            atomicMin(&minmax[0], enc(mn));
+            atomicMax(&minmax[1], enc(mx));
+        }
+    }
+}
+
+__global__ void __launch_bounds__(TR_THREADS) normalize_kernel(double *__restrict__ m, uint32_t n, uint64_t nn,
+                                                              int normalization, double mn, double mx) {
+    const uint64_t idx = static_cast<uint64_t>(blockIdx.x) * TR_THREADS + threadIdx.x;
+    if (idx >= nn) {
+        return;
+    }
+    const uint32_t i = static_cast<uint32_t>(idx / n), j = static_cast<uint32_t>(idx % n);
+    double v = m[idx];
+    switch (normalization) {
+        case SGPU_NORM_ADD_MIN: { // M *= -1; M += |min(M)|   (min(-raw) = -max(raw))
+            v = v * -1;
+            v += fabs(-mx);
+            break;
+        }
+        case SGPU_NORM_EXPONENTIATE:
+            v = 1. / (exp(v) + 1);
+            break;
+        case SGPU_NORM_SCALE_MAX_1:
+            v = v * (1. / mx);
+            break;
+    }
+    (void)mn;
+    m[idx] = i == j ? 0.0 : v; // fill_diagonal(0), similarity_matrix.cpp:292
+}
+
+int device_log_probs(sgpu_ctx *ctx, double eps, double h, double theta, uint32_t L, uint32_t n, DevBuf<double> &ls,
+                     DevBuf<double> &ld) {
+    cudaStream_t st = ctx->stream;
+    CacheTables hc;
+    make_cache(&hc, eps, h, theta, L);
+    DevBuf<CacheTables> dc;
+    DevBuf<uint64_t> comb;
+    SGPU_CUDA(ctx, dc.alloc(1, st));
+    SGPU_CUDA(ctx, comb.alloc(TBL * TBL, st));
+    SGPU_CUDA(ctx, ls.alloc(static_cast<size_t>(n) * n, st));
+    SGPU_CUDA(ctx, ld.alloc(static_cast<size_t>(n) * n, st));
+    SGPU_CUDA(ctx, cudaMemcpyAsync(dc.p, &hc, sizeof(hc), cudaMemcpyHostToDevice, st));
+    SGPU_CUDA(ctx, cudaStreamSynchronize(st)); // hc lives on this stack frame
+    pascal_kernel<<<1, 128, 0, st>>>(comb.p);
+    logprob_kernel<<<(n * n + 63) / 64, 64, 0, st>>>(dc.p, comb.p, n, L, ls.p, ld.p);
+    SGPU_CUDA(ctx, cudaGetLastError());
+    SGPU_CUDA(ctx, cudaStreamSynchronize(st));
+    return SGPU_OK;
+}
+
+} // namespace
+
+int sgpu_log_probs_impl(sgpu_ctx *ctx, double eps, double h, double theta, uint32_t L, uint32_t n, double *h_ls,
+                        double *h_ld) {
+    if (n == 0 || n > SGPU_MAX_CLASS) {
+        return sgpu_fail(ctx, SGPU_E_ARG, "n must be 1..%d", SGPU_MAX_CLASS);
+    }
+    DevBuf<double> ls, ld;
+    SGPU_TRY(device_log_probs(ctx, eps, h, theta, L, n, ls, ld));
+    SGPU_CUDA(ctx, cudaMemcpyAsync(h_ls, ls.p, sizeof(double) * n * n, cudaMemcpyDeviceToHost, ctx->stream));
+    SGPU_CUDA(ctx, cudaMemcpyAsync(h_ld, ld.p, sizeof(double) * n * n, cudaMemcpyDeviceToHost, ctx->stream));
+    SGPU_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return SGPU_OK;
+}
+
+int sgpu_build_gtable(sgpu_ctx *ctx, double eps, double h, double theta, uint32_t L, uint32_t n, double *d_G,
+                      double *d_F) {
+    DevBuf<double> ls, ld;
+    SGPU_TRY(device_log_probs(ctx, eps, h, theta, L, n, ls, ld));
+    gtable_kernel<<<(SGPU_MAX_CLASS * SGPU_MAX_CLASS + 255) / 256, 256, 0, ctx->stream>>>(ls.p, ld.p, n, d_G, d_F);
+    SGPU_CUDA(ctx, cudaGetLastError());
+    SGPU_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return SGPU_OK;
+}
+
+int sgpu_epilogue(sgpu_ctx *ctx, sgpu_counts *c, uint32_t L, double eps, double h, double theta, int normalization,
+                  double *h_out) {
+    cudaStream_t st = ctx->stream;
+    if (normalization < 0 || normalization > 2) {
+        return sgpu_fail(ctx, SGPU_E_ARG, "Invalid normalization: %d", normalization); // similarity_matrix.cpp:264
+    }
+    if (c->nn == 0) {
+        return SGPU_OK;
+    }
+    // classes needed by the integer planes: all (s,d) with s + d <= 3
+    DevBuf<double> d_G, d_F, raw;
+    DevBuf<unsigned long long> d_minmax;
+    SGPU_CUDA(ctx, d_G.alloc(SGPU_MAX_CLASS * SGPU_MAX_CLASS, st));
+    SGPU_CUDA(ctx, d_F.alloc(SGPU_MAX_CLASS * SGPU_MAX_CLASS, st));
+    SGPU_TRY(sgpu_build_gtable(ctx, eps, h, theta, L, 4, d_G.p, d_F.p));
+    std::vector<double> G(SGPU_MAX_CLASS * SGPU_MAX_CLASS), F(SGPU_MAX_CLASS * SGPU_MAX_CLASS);
+    SGPU_CUDA(ctx, cudaMemcpyAsync(G.data(), d_G.p, G.size() * sizeof(double), cudaMemcpyDeviceToHost, st));
+    SGPU_CUDA(ctx, cudaMemcpyAsync(F.data(), d_F.p, F.size() * sizeof(double), cudaMemcpyDeviceToHost, st));
+    SGPU_CUDA(ctx, cudaStreamSynchronize(st));
+
+    TransformArgs a;
+    a.i32 = c->i32;
+    a.spill = c->spill;
+    a.n = c->n;
+    a.nn = c->nn;
+    a.planes_used = c->planes_used;
+    a.f10 = F[1 * SGPU_MAX_CLASS + 0];
+    a.f01 = F[0 * SGPU_MAX_CLASS + 1];
+    for (int d = 0; d < 3; ++d) {
+        a.g2[d] = G[(2 - d) * SGPU_MAX_CLASS + d];
+    }
+    for (int d = 0; d < 4; ++d) {
+        a.g3[d] = G[(3 - d) * SGPU_MAX_CLASS + d];
+    }
+    if (c->planes_used > 2) {
+        for (int d = 0; d < 3; ++d) {
+            if (std::isnan(a.g2[d])) {
+                a.g2[d] = 0.0; // class impossible with this max_fragment_length; its plane is all zero
+            }
+        }
+        for (int d = 0; d < 4; ++d) {
+            if (std::isnan(a.g3[d])) {
+                a.g3[d] = 0.0;
+            }
+        }
+    }
+    SGPU_CUDA(ctx, raw.alloc(c->nn, st));
+    SGPU_CUDA(ctx, d_minmax.alloc(2, st));
+    const unsigned long long init[2] = { ~0ull, 0ull };
+    SGPU_CUDA(ctx, cudaMemcpyAsync(d_minmax.p, init, sizeof(init), cudaMemcpyHostToDevice, st));
+    const unsigned grid = static_cast<unsigned>(ceil_div_u64(c->nn, TR_THREADS));
+    transform_kernel<<<grid, TR_THREADS, 0, st>>>(a, raw.p, d_minmax.p);
+    SGPU_CUDA(ctx, cudaGetLastError());
+    SGPU_CUDA(ctx, cudaMemcpyAsync(&ctx->h_scratch[0], d_minmax.p, 2 * sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
+    SGPU_CUDA(ctx, cudaStreamSynchronize(st));
+    const double mn = dec(ctx->h_scratch[0]), mx = dec(ctx->h_scratch[1]);
+    normalize_kernel<<<grid, TR_THREADS, 0, st>>>(raw.p, c->n, c->nn, normalization, mn, mx);
+    SGPU_CUDA(ctx, cudaGetLastError());
+    SGPU_CUDA(ctx, cudaMemcpyAsync(h_out, raw.p, c->nn * sizeof(double), cudaMemcpyDeviceToHost, st));
+    SGPU_CUDA(ctx, cudaStreamSynchronize(st));
+    return SGPU_OK;
+}

@@ -1,0 +1,340 @@
+// K1 — the per-locus significance filter (reference: util/is_significant.cpp:78-193).
+//
+//   filter_count_kernel    one warp per locus: pooled A/C/G/T counts over the entries whose group is
+//                          in the current sub-cluster, then the Bayesian test in fp64 (lane 0)
+//   filter_compact_kernel  one warp per kept locus: ballot compaction of the in-cluster entries
+//                          into the filtered CSR (order preserved, as Filter::filter does)
+// Both are pure streaming kernels bounded by HBM: 2 B/entry read by the first, 6 B/entry read +
+// 6 B/kept entry written by the second.
+#include "common.cuh"
+
+#include <cmath>
+#include <algorithm>
+#include <vector>
+
+namespace {
+
+// util/is_significant.cpp:11-36
+__constant__ double c_Ks[5][20] = {
+    { -1.64504967001201, -1.38868450353301, -1.38780664765677, -1.38779600211955, -1.3877952855556,
+      -1.38779524274215, -1.38779524274142, -1.38779524274141, -1.3877952427414, -1.38779524274139,
+      -1.38779524274138, -1.38779524274138, -1.38779524274138, -1.38779524274138, -1.38779524274139,
+      -1.38780870444455, -1.38780870444455, -1.38780870444455, -1.38780870444455, -1.38780870444455 },
+    { -1.56013904495168, -1.38819451352203, -1.38781438946096, -1.38779659244035, -1.38779537799054,
+      -1.3877952484612, -1.3877952427842, -1.38779524274906, -1.3877952427457, -1.38779524274275,
+      -1.38780870444458, -1.38780870444459, -1.38780870444459, -1.38780870444469, -1.38780870444459,
+      -1.42736056742577, -1.42736056742575, -6.19144172018466, -6.19144172018466, -14.1885779508362 },
+    { -1.47780038365618, -1.3885722463397, -1.38781428162649, -1.3877984410546, -1.38779548312685,
+      -1.3877952855556, -1.38779524455204, -1.38779524331456, -1.38780873675669, -1.38780870687333,
+      -1.42737804009806, -6.19144172131432, -14.1885779508648, -6.1914418045659, -30.1993093269287,
+      -30.1993093268559, -30.1993093268539, -54.2154105288032, -62.2207775961199, -46.2100434614866 },
+    { -1.47780038365618, -1.38868450353301, -1.38782829051844, -1.3877984410546, -1.38779625512927,
+      -1.38779556321717, -1.38780972304588, -1.3878087226245, -6.21747860711653, -22.1939432034943,
+      -14.1886670526002, -22.1939422903721, -46.2100434614866, -54.2154105288069, -70.2261446634366,
+      -62.2207775961199, -86.2368787980699, -110.25298000002, -118.258347067337, -102.247612932703 },
+    { -1.52859626647315, -1.38967447346712, -1.38787138908447, -1.38780282263764, -1.387805349423,
+      -1.38882047800373, -1.49793700616569, -6.19975747800726, -22.197881249831, -38.2046765807324,
+      -38.2046769835162, -70.2261446634383, -54.2154105303641, -78.2315117307532, -86.2368787980699,
+      -118.258347067337, -126.263714134653, -134.26908120197, -158.28518240392, -158.28518240392 }
+};
+
+struct FilterParams {
+    double theta;
+    double log_theta_3;         // log(theta/3)
+    double log_one_minus_theta; // log(1-theta)
+    double log_1_4;             // log(1/4)
+    double log_homo_prior;      // log(hetero_prior): quirk of util/is_significant.cpp:45, reproduced
+    int cell_proportion;
+};
+
+// util/is_significant.cpp:78-138 on uint16 counts (the reference's base_count is uint16 and wraps)
+__device__ bool is_significant_dev(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, const FilterParams &fp) {
+    uint32_t b[4] = { c0 & 0xFFFFu, c1 & 0xFFFFu, c2 & 0xFFFFu, c3 & 0xFFFFu };
+    const uint32_t coverage = b[0] + b[1] + b[2] + b[3];
+    if (coverage < 2) {
+        return false;
+    }
+    // sorting network, ascending
+#define CSWAP(i, j)                 \
+    if (b[i] > b[j]) {              \
+        uint32_t t = b[i];          \
+        b[i] = b[j];                \
+        b[j] = t;                   \
+    }
+    CSWAP(0, 1) CSWAP(2, 3) CSWAP(0, 2) CSWAP(1, 3) CSWAP(1, 2)
+#undef CSWAP
+    if (b[2] == 0) {
+        return false;
+    }
+    if (b[2] + b[1] + b[0] < 5) {
+        return false;
+    }
+    if (static_cast<double>(b[3]) < 1.5 * static_cast<double>(b[2])) {
+        return false;
+    }
+    // threshold for the closest coverage, round half to even (:67-70,106-107)
+    double t = rint(coverage / 10.) - 1;
+    t = fmin(fmax(t, 0.), 19.);
+    const uint32_t threshold_idx = static_cast<uint32_t>(t);
+
+    const double theta = fp.theta;
+    const double hetero_prior = 0.0005;
+    const double mut_prior = 1e-6;
+    const double homo_prior = 1 - hetero_prior - mut_prior;
+
+    double log_prob_homozygous = b[3] * fp.log_one_minus_theta + (coverage - b[3]) * fp.log_theta_3;
+    log_prob_homozygous += fp.log_1_4;
+    log_prob_homozygous += fp.log_homo_prior;
+
+    const double t3 = theta / 3;
+    double prob_all_c1 = homo_prior * pow(1 - theta, static_cast<double>(b[3])) * pow(t3, static_cast<double>(coverage - b[3]));
+    double prob_hetero = hetero_prior * pow(0.5 - t3, static_cast<double>(b[3] + b[2])) * pow(t3, static_cast<double>(b[0] + b[1]));
+    double prob_homo_som = homo_prior * mut_prior * pow(0.75 - 2 * theta / 3, static_cast<double>(b[3]))
+            * pow(0.25, static_cast<double>(b[2])) * pow(t3, static_cast<double>(b[0] + b[1]));
+    double prob_hetero_som = hetero_prior * mut_prior * pow(0.5 - theta, static_cast<double>(b[3]))
+            * pow(0.25, static_cast<double>(b[1] + b[2])) * pow(t3, static_cast<double>(b[0]));
+    double prob_two_somatic = hetero_prior * mut_prior * mut_prior * pow(1 - theta, static_cast<double>(coverage));
+    double log_evidence = log(prob_all_c1 + prob_hetero + prob_homo_som + prob_hetero_som + prob_two_somatic);
+    return log_prob_homozygous - log_evidence < c_Ks[fp.cell_proportion][threshold_idx];
+}
+
+constexpr int FILTER_THREADS = 256;
+
+__global__ void __launch_bounds__(FILTER_THREADS) filter_count_kernel(
+        const uint64_t *__restrict__ row_ptr, const uint16_t *__restrict__ gid_base, uint64_t n_loci,
+        const uint32_t *__restrict__ in_mask /* bit per group id */, uint32_t n_groups, FilterParams fp,
+        uint8_t *__restrict__ keep, uint32_t *__restrict__ kept_cnt, int *__restrict__ err) {
+    extern __shared__ uint32_t s_mask[];
+    const uint32_t mask_words = (n_groups + 31) / 32;
+    for (uint32_t i = threadIdx.x; i < mask_words; i += blockDim.x) {
+        s_mask[i] = in_mask[i];
+    }
+    __syncthreads();
+    const int lane = threadIdx.x & 31;
+    const uint64_t warps_total = static_cast<uint64_t>(gridDim.x) * (FILTER_THREADS / 32);
+    for (uint64_t l = static_cast<uint64_t>(blockIdx.x) * (FILTER_THREADS / 32) + (threadIdx.x >> 5); l < n_loci;
+         l += warps_total) {
+        const uint64_t e0 = row_ptr[l], e1 = row_ptr[l + 1];
+        // per-lane counters packed 4 x 16 bit would overflow above 64k reads per lane; keep 32-bit
+        uint32_t c0 = 0, c1 = 0, c2 = 0, c3 = 0;
+        bool bad = false;
+        for (uint64_t e = e0 + lane; e < e1; e += 32) {
+            const uint32_t gb = gid_base[e];
+            const uint32_t gid = gb >> 2;
+            if (gid >= n_groups) {
+                bad = true;
+                continue;
+            }
+            const uint32_t in = (s_mask[gid >> 5] >> (gid & 31)) & 1u;
+            const uint32_t b = gb & 3u;
+            c0 += in & (b == 0);
+            c1 += in & (b == 1);
+            c2 += in & (b == 2);
+            c3 += in & (b == 3);
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            c0 += __shfl_xor_sync(0xffffffffu, c0, o);
+            c1 += __shfl_xor_sync(0xffffffffu, c1, o);
+            c2 += __shfl_xor_sync(0xffffffffu, c2, o);
+            c3 += __shfl_xor_sync(0xffffffffu, c3, o);
+        }
+        if (__any_sync(0xffffffffu, bad) && lane == 0) {
+            atomicExch(err, SGPU_E_CELL_RANGE);
+        }
+        if (lane == 0) {
+            const bool sig = is_significant_dev(c0, c1, c2, c3, fp);
+            keep[l] = sig ? 1 : 0;
+            kept_cnt[l] = sig ? (c0 + c1 + c2 + c3) : 0;
+        }
+    }
+}
+
+__global__ void __launch_bounds__(FILTER_THREADS) filter_compact_kernel(
+        const uint64_t *__restrict__ row_ptr, const uint32_t *__restrict__ position,
+        const uint32_t *__restrict__ read_id, const uint16_t *__restrict__ gid_base, uint64_t n_loci,
+        const uint32_t *__restrict__ in_mask, uint32_t n_groups, const uint8_t *__restrict__ keep,
+        const uint64_t *__restrict__ new_locus /* exclusive scan of keep */,
+        const uint64_t *__restrict__ new_row /* exclusive scan of kept_cnt, n_loci + 1 */,
+        uint64_t *__restrict__ out_row_ptr, uint32_t *__restrict__ out_position,
+        uint32_t *__restrict__ out_read_id, uint16_t *__restrict__ out_gid_base) {
+    extern __shared__ uint32_t s_mask[];
+    const uint32_t mask_words = (n_groups + 31) / 32;
+    for (uint32_t i = threadIdx.x; i < mask_words; i += blockDim.x) {
+        s_mask[i] = in_mask[i];
+    }
+    __syncthreads();
+    const int lane = threadIdx.x & 31;
+    const uint64_t warps_total = static_cast<uint64_t>(gridDim.x) * (FILTER_THREADS / 32);
+    for (uint64_t l = static_cast<uint64_t>(blockIdx.x) * (FILTER_THREADS / 32) + (threadIdx.x >> 5); l < n_loci;
+         l += warps_total) {
+        if (!keep[l]) {
+            continue;
+        }
+        const uint64_t nl = new_locus[l];
+        uint64_t w = new_row[l];
+        if (lane == 0) {
+            out_row_ptr[nl] = w;
+            out_position[nl] = position[l];
+        }
+        const uint64_t e0 = row_ptr[l], e1 = row_ptr[l + 1];
+        for (uint64_t base = e0; base < e1; base += 32) {
+            const uint64_t e = base + lane;
+            uint32_t gb = 0, rid = 0;
+            bool in = false;
+            if (e < e1) {
+                gb = gid_base[e];
+                rid = read_id[e];
+                const uint32_t gid = gb >> 2;
+                in = gid < n_groups && ((s_mask[gid >> 5] >> (gid & 31)) & 1u);
+            }
+            const uint32_t ballot = __ballot_sync(0xffffffffu, in);
+            if (in) {
+                const uint64_t dst = w + __popc(ballot & ((1u << lane) - 1u));
+                out_read_id[dst] = rid;
+                out_gid_base[dst] = static_cast<uint16_t>(gb);
+            }
+            w += __popc(ballot);
+        }
+    }
+}
+
+__global__ void remap_chr_ptr_kernel(const uint64_t *__restrict__ chr_ptr, uint32_t n_chr,
+                                     const uint64_t *__restrict__ new_locus, uint64_t *__restrict__ out_chr_ptr,
+                                     uint64_t *__restrict__ out_row_ptr, const uint64_t *__restrict__ new_row,
+                                     uint64_t n_loci) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i <= n_chr) {
+        out_chr_ptr[i] = new_locus[chr_ptr[i]];
+    }
+    if (i == 0) {
+        out_row_ptr[new_locus[n_loci]] = new_row[n_loci]; // closing offset
+    }
+}
+
+__global__ void is_significant_kernel(const uint16_t *__restrict__ counts4, uint64_t n, FilterParams fp,
+                                      uint8_t *__restrict__ out) {
+    const uint64_t i = static_cast<uint64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i < n) {
+        out[i] = is_significant_dev(counts4[4 * i], counts4[4 * i + 1], counts4[4 * i + 2], counts4[4 * i + 3], fp) ? 1 : 0;
+    }
+}
+
+FilterParams make_params(double theta, int cell_proportion) {
+    FilterParams fp;
+    fp.theta = theta;
+    fp.log_theta_3 = std::log(theta / 3);           // Filter::Filter, util/is_significant.cpp:48-52
+    fp.log_one_minus_theta = std::log(1 - theta);
+    fp.log_1_4 = std::log(1. / 4);                  // :38
+    fp.log_homo_prior = std::log(0.0005);           // :45
+    fp.cell_proportion = cell_proportion;
+    return fp;
+}
+
+} // namespace
+
+int sgpu_is_significant_impl(sgpu_ctx *ctx, const uint16_t *h_counts4, uint64_t n, double theta,
+                             int cell_proportion, uint8_t *h_out) {
+    if (cell_proportion < 0 || cell_proportion > 4) {
+        return sgpu_fail(ctx, SGPU_E_ARG, "cell_proportion must be 0..4");
+    }
+    if (n == 0) {
+        return SGPU_OK;
+    }
+    cudaStream_t st = ctx->stream;
+    DevBuf<uint16_t> d_in;
+    DevBuf<uint8_t> d_out;
+    SGPU_CUDA(ctx, d_in.alloc(4 * n, st));
+    SGPU_CUDA(ctx, d_out.alloc(n, st));
+    SGPU_CUDA(ctx, cudaMemcpyAsync(d_in.p, h_counts4, 4 * n * sizeof(uint16_t), cudaMemcpyHostToDevice, st));
+    is_significant_kernel<<<static_cast<unsigned>(ceil_div_u64(n, 256)), 256, 0, st>>>(d_in.p, n, make_params(theta, cell_proportion), d_out.p);
+    SGPU_CUDA(ctx, cudaGetLastError());
+    SGPU_CUDA(ctx, cudaMemcpyAsync(h_out, d_out.p, n, cudaMemcpyDeviceToHost, st));
+    SGPU_CUDA(ctx, cudaStreamSynchronize(st));
+    return SGPU_OK;
+}
+
+int sgpu_filter_impl(sgpu_ctx *ctx, const sgpu_pileup *in, const uint32_t *h_id_to_pos, uint32_t n_groups,
+                     double theta, int cell_proportion, sgpu_pileup **filtered, double *avg_coverage) {
+    if (cell_proportion < 0 || cell_proportion > 4) {
+        return sgpu_fail(ctx, SGPU_E_ARG, "cell_proportion must be 0..4");
+    }
+    cudaStream_t st = ctx->stream;
+    const uint64_t P = in->n_loci;
+    // sub-cluster membership as a bit mask (id_to_pos[gid] != NO_POS, util/is_significant.cpp:169)
+    const uint32_t mask_words = (n_groups + 31) / 32;
+    std::vector<uint32_t> h_mask(mask_words ? mask_words : 1, 0);
+    for (uint32_t g = 0; g < n_groups; ++g) {
+        if (h_id_to_pos[g] != SGPU_NO_POS) {
+            h_mask[g >> 5] |= 1u << (g & 31);
+        }
+    }
+    const size_t smem = h_mask.size() * sizeof(uint32_t);
+    if (smem > 200 * 1024) {
+        return sgpu_fail(ctx, SGPU_E_ARG, "n_groups too large for the shared-memory membership mask");
+    }
+    DevBuf<uint32_t> d_mask, d_cnt;
+    DevBuf<uint8_t> d_keep;
+    DevBuf<uint64_t> d_new_locus, d_new_row;
+    DevBuf<int> d_err;
+    SGPU_CUDA(ctx, d_mask.alloc(h_mask.size(), st));
+    SGPU_CUDA(ctx, d_cnt.alloc(P, st));
+    SGPU_CUDA(ctx, d_keep.alloc(P, st));
+    SGPU_CUDA(ctx, d_new_locus.alloc(P + 1, st));
+    SGPU_CUDA(ctx, d_new_row.alloc(P + 1, st));
+    SGPU_CUDA(ctx, d_err.alloc(1, st));
+    SGPU_CUDA(ctx, cudaMemsetAsync(d_err.p, 0, sizeof(int), st));
+    SGPU_CUDA(ctx, cudaMemcpyAsync(d_mask.p, h_mask.data(), smem, cudaMemcpyHostToDevice, st));
+
+    const FilterParams fp = make_params(theta, cell_proportion);
+    const unsigned grid = static_cast<unsigned>(std::min<uint64_t>(ceil_div_u64(P ? P : 1, FILTER_THREADS / 32),
+                                                                  static_cast<uint64_t>(ctx->sm_count) * 32));
+    if (smem > 48 * 1024) {
+        SGPU_CUDA(ctx, cudaFuncSetAttribute(filter_count_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        SGPU_CUDA(ctx, cudaFuncSetAttribute(filter_compact_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    }
+    if (P) {
+        filter_count_kernel<<<grid, FILTER_THREADS, smem, st>>>(in->d_row_ptr, in->d_gid_base, P, d_mask.p, n_groups, fp,
+                                                               d_keep.p, d_cnt.p, d_err.p);
+        SGPU_CUDA(ctx, cudaGetLastError());
+    }
+    SGPU_TRY(sgpu_scan_u8_u64(ctx, d_keep.p, d_new_locus.p, P));
+    SGPU_TRY(sgpu_scan_u32_u64(ctx, d_cnt.p, d_new_row.p, P));
+    // totals -> host
+    SGPU_CUDA(ctx, cudaMemcpyAsync(&ctx->h_scratch[0], d_new_locus.p + P, sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
+    SGPU_CUDA(ctx, cudaMemcpyAsync(&ctx->h_scratch[1], d_new_row.p + P, sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
+    SGPU_CUDA(ctx, cudaMemcpyAsync(&ctx->h_scratch[2], d_err.p, sizeof(int), cudaMemcpyDeviceToHost, st));
+    SGPU_CUDA(ctx, cudaStreamSynchronize(st));
+    if (static_cast<int>(ctx->h_scratch[2] & 0xFFFFFFFFu) != 0) {
+        return sgpu_fail(ctx, SGPU_E_CELL_RANGE, "pileup holds a group id >= n_groups (%u)", n_groups);
+    }
+    const uint64_t Lk = ctx->h_scratch[0], Ek = ctx->h_scratch[1];
+
+    sgpu_pileup *out = new sgpu_pileup();
+    out->n_chr = in->n_chr;
+    out->n_loci = Lk;
+    out->n_entries = Ek;
+    out->owns = true;
+    out->h_chr_ptr = new uint64_t[in->n_chr + 1];
+    SGPU_CUDA(ctx, cudaMalloc(&out->d_chr_ptr, (in->n_chr + 1) * sizeof(uint64_t)));
+    SGPU_CUDA(ctx, cudaMalloc(&out->d_row_ptr, (Lk + 1) * sizeof(uint64_t)));
+    SGPU_CUDA(ctx, cudaMalloc(&out->d_position, (Lk ? Lk : 1) * sizeof(uint32_t)));
+    SGPU_CUDA(ctx, cudaMalloc(&out->d_read_id, (Ek ? Ek : 1) * sizeof(uint32_t)));
+    SGPU_CUDA(ctx, cudaMalloc(&out->d_gid_base, (Ek ? Ek : 1) * sizeof(uint16_t)));
+    if (P) {
+        filter_compact_kernel<<<grid, FILTER_THREADS, smem, st>>>(in->d_row_ptr, in->d_position, in->d_read_id, in->d_gid_base,
+                                                                 P, d_mask.p, n_groups, d_keep.p, d_new_locus.p, d_new_row.p,
+                                                                 out->d_row_ptr, out->d_position, out->d_read_id,
+                                                                 out->d_gid_base);
+    }
+    remap_chr_ptr_kernel<<<(in->n_chr + 256) / 256, 256, 0, st>>>(in->d_chr_ptr, in->n_chr, d_new_locus.p, out->d_chr_ptr,
+                                                                 out->d_row_ptr, d_new_row.p, P);
+    SGPU_CUDA(ctx, cudaGetLastError());
+    SGPU_CUDA(ctx, cudaMemcpyAsync(out->h_chr_ptr, out->d_chr_ptr, (in->n_chr + 1) * sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
+    SGPU_CUDA(ctx, cudaStreamSynchronize(st));
+    if (avg_coverage) {
+        *avg_coverage = Lk == 0 ? 0.0 : static_cast<double>(Ek) / static_cast<double>(Lk); // :188, in 64 bits
+    }
+    *filtered = out;
+    return SGPU_OK;
+}

@@ -1,0 +1,166 @@
+"""Parity of the CUDA similarity-matrix path (through the C ABI) with the oracle and with golden
+matrices from the compiled reference. Integer read-pair counts are compared bit-exactly; the final
+fp64 matrix within 1e-6 * max|M| (north_star tolerance; SURVEY.md §8c explains the scaling)."""
+import numpy as np
+import pytest
+
+from conftest import assert_matrix_close, golden_pileup, load_golden
+from oracle import pyoracle as po
+from secedo_b200 import api
+from secedo_b200.pileup import NO_POS, Pileup
+from secedo_b200.synth import SynthConfig, make_pileup
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-6
+PATHS = ["scatter", "gemm"]
+
+CASES = ["sim_ten_rows", "sim_six_cells", "sim_three_rows", "sim_reference_test_style", "sim_synth_multi",
+         "sim_synth_subcluster"]
+
+
+@pytest.mark.parametrize("path", PATHS)
+@pytest.mark.parametrize("name", CASES)
+def test_golden_matrices(gpu_ctx, name, path):
+    g = load_golden(name)
+    p = golden_pileup(g)
+    for t in g["threads"]:
+        for norm in g["norms"]:
+            M = api.compute_similarity_matrix(p, int(g["num_cells"]), int(g["L"]), g["gmap"], float(g["eps"]),
+                                              float(g["h"]), float(g["theta"]), int(t), "", str(norm), ctx=gpu_ctx,
+                                              path=path)
+            assert_matrix_close(M, g[f"M_t{t}_{norm}"], TOL)
+
+
+def check_counts(ctx, f, n_cells, L, gmap, eps, h, theta, threads, path):
+    o = po.similarity(f, n_cells, L, gmap, eps, h, theta, threads, "ADD_MIN")
+    c = api.Counts(ctx, n_cells)
+    st = c.accumulate(f, L, gmap, eps, h, theta, threads, path)
+    S1, D1, H, hist = c.download()
+    assert np.array_equal(S1, o.S1), "S1 (same-base incidences) differs"
+    assert np.array_equal(D1, o.D1), "D1 (different-base incidences) differs"
+    assert np.array_equal(H, o.H), "second-order class counts differ"
+    oh = o.class_hist.copy()
+    oh[0, 0] = oh[0, 1] = oh[1, 0] = 0
+    assert np.array_equal(hist, oh), "overlap class histogram differs"
+    assert st["n_pairs_multi"] == int(oh.sum())
+    for norm in ("ADD_MIN", "EXPONENTIATE", "SCALE_MAX_1"):
+        M = c.finalize(L, eps, h, theta, norm)
+        assert_matrix_close(M, po.normalize(o.raw, norm), TOL)
+    c.free()
+    return st, o
+
+
+@pytest.mark.parametrize("path", PATHS)
+@pytest.mark.parametrize("threads", [1, 2, 8])
+def test_counts_bit_exact_multilocus(gpu_ctx, threads, path):
+    cfg = SynthConfig(n_cells=60, coverage=0.3, n_loci=900, n_chr=3, p_multi=0.45, p_mate=0.15, theta=0.02, seed=7)
+    p = make_pileup(cfg)
+    ident = np.arange(cfg.n_cells, dtype=np.uint32)
+    f, _ = api.Filter(0.01, 4, gpu_ctx).filter(p, ident, "", 1)
+    st, o = check_counts(gpu_ctx, f, cfg.n_cells, 1000, ident, 0.01, 0.5, 0.01, threads, path)
+    assert st["n_multi_reads"] > 0 and st["n_dropped_entries"] > 0 and st["n_tail_reads"] > 0
+
+
+@pytest.mark.parametrize("path", PATHS)
+def test_cfg1_style_500_cells(gpu_ctx, path):
+    """BASELINE.json configs[0] shape: 500 cells, 0.05x, one chromosome (scaled to a few seconds of oracle)."""
+    cfg = SynthConfig(n_cells=500, coverage=0.05, n_loci=20000, n_chr=1, p_multi=0.05, p_mate=0.02, seed=21)
+    p = make_pileup(cfg)
+    ident = np.arange(cfg.n_cells, dtype=np.uint32)
+    f, _ = api.Filter(0.01, 4, gpu_ctx).filter(p, ident, "", 1)
+    assert f.n_loci > 1000
+    check_counts(gpu_ctx, f, cfg.n_cells, 1000, ident, 0.01, 0.5, 0.01, 8, path)
+
+
+@pytest.mark.parametrize("path", PATHS)
+def test_cfg2_style_2000_cells(gpu_ctx, path):
+    """configs[1] shape: 2000 cells at 0.1x (prefix of loci the oracle finishes in seconds)."""
+    cfg = SynthConfig(n_cells=2000, coverage=0.1, n_loci=1500, n_chr=2, p_multi=0.03, p_mate=0.02, theta=0.001,
+                      seed=22)
+    p = make_pileup(cfg)
+    ident = np.arange(cfg.n_cells, dtype=np.uint32)
+    f, _ = api.Filter(0.001, 4, gpu_ctx).filter(p, ident, "", 1)
+    check_counts(gpu_ctx, f, cfg.n_cells, 1000, ident, 0.01, 0.15, 0.001, 8, path)
+
+
+@pytest.mark.parametrize("path", PATHS)
+def test_subcluster_remap(gpu_ctx, path):
+    """second recursion level: cells outside the sub-cluster map to NO_POS, the rest to 0..n-1"""
+    cfg = SynthConfig(n_cells=300, coverage=0.2, n_loci=2500, n_chr=2, n_clones=4, p_multi=0.1, p_mate=0.05, seed=23)
+    p = make_pileup(cfg)
+    rng = np.random.default_rng(5)
+    members = np.sort(rng.choice(cfg.n_cells, 170, replace=False))
+    gmap = np.full(cfg.n_cells, NO_POS, np.uint32)
+    gmap[members] = np.arange(members.size)
+    f, _ = api.Filter(0.01, 4, gpu_ctx).filter(p, gmap, "", 1)
+    check_counts(gpu_ctx, f, members.size, 1000, gmap, 0.01, 0.5, 0.01, 4, path)
+
+
+def test_high_order_overlaps(gpu_ctx):
+    """fragments covering up to 6 close loci: classes of order >= 4 go through the fp64 spill plane"""
+    cfg = SynthConfig(n_cells=25, coverage=1.5, n_loci=300, n_chr=1, spacing=40, p_multi=0.9, p_mate=0.1, seed=31)
+    p = make_pileup(cfg)
+    ident = np.arange(cfg.n_cells, dtype=np.uint32)
+    st, o = check_counts(gpu_ctx, p, cfg.n_cells, 1000, ident, 0.01, 0.5, 0.01, 1, "scatter")
+    hi = o.class_hist.copy()
+    hi[:4, :4][np.add.outer(np.arange(4), np.arange(4)) < 4] = 0
+    assert hi.sum() > 0, "the case must contain overlaps of order >= 4"
+
+
+def test_edge_cases(gpu_ctx):
+    ident = np.arange(4, dtype=np.uint32)
+    # empty pileup, with and without chromosomes
+    for p in (Pileup.empty(0), Pileup.empty(3)):
+        M = api.compute_similarity_matrix(p, 4, 1000, ident, 0.01, 0.5, 0.01, 1, "", "ADD_MIN", ctx=gpu_ctx)
+        assert M.shape == (4, 4) and not M.any()
+    # a single locus: everything is tail -> zero
+    p = Pileup.from_pos_data([[(5, [1, 2, 3], [0 << 2, (1 << 2) | 1, 2 << 2])]])
+    assert not api.compute_similarity_matrix(p, 4, 1000, ident, 0.01, 0.5, 0.01, 1, ctx=gpu_ctx).any()
+    # invalid normalization -> the reference throws std::logic_error
+    with pytest.raises(ValueError):
+        api.compute_similarity_matrix(p, 4, 1000, ident, 0.01, 0.5, 0.01, 1, "", "NOPE", ctx=gpu_ctx)
+    # read id spanning >= L
+    p = Pileup.from_pos_data([[(100, [1, 2], [0 << 2, 1 << 2]), (1600, [1, 3], [0 << 2, 2 << 2])]])
+    with pytest.raises(api.SgpuError):
+        api.compute_similarity_matrix(p, 4, 1000, ident, 0.01, 0.5, 0.01, 1, ctx=gpu_ctx)
+    # cell outside the matrix
+    p = Pileup.from_pos_data([[(100, [1, 2], [0 << 2, 3 << 2])]])
+    with pytest.raises(api.SgpuError):
+        api.compute_similarity_matrix(p, 2, 1000, ident, 0.01, 0.5, 0.01, 1, ctx=gpu_ctx)
+
+
+def test_log_prob_tables(gpu_ctx):
+    g = load_golden("log_probs")
+    i = 0
+    while f"params{i}" in g.files:
+        e, h, t, L = g[f"params{i}"]
+        n = g[f"ls{i}"].shape[0]
+        ls, ld = api.log_probs(e, h, t, int(L), n, ctx=gpu_ctx)
+        ok = ~np.isnan(g[f"ls{i}"])
+        # identical formula and summation order, -fmad=false; CUDA's log() may differ by an ulp
+        assert np.allclose(ls[ok], g[f"ls{i}"][ok], rtol=1e-14, atol=0) and np.allclose(ld[ok], g[f"ld{i}"][ok], rtol=1e-14, atol=0)
+        i += 1
+
+
+def test_linearity_and_idempotence(gpu_ctx):
+    """size-independent properties: counts(A ++ B) == counts(A) + counts(B) for disjoint chromosome
+    sets; accumulating in two calls equals one call; the result is symmetric with a zero diagonal."""
+    cfg = SynthConfig(n_cells=400, coverage=0.3, n_loci=3000, n_chr=4, p_multi=0.05, p_mate=0.02, seed=41)
+    p = make_pileup(cfg)
+    ident = np.arange(cfg.n_cells, dtype=np.uint32)
+    f, _ = api.Filter(0.01, 4, gpu_ctx).filter(p, ident, "", 1)
+    halves = []
+    for chrs in ((0, 1), (2, 3)):
+        parts = [f.loci_range(c, 0, 1 << 40) for c in chrs]
+        halves.append(Pileup.concat(parts))
+    args = (1000, ident, 0.01, 0.5, 0.01, 8)
+    whole = api.Counts(gpu_ctx, cfg.n_cells)
+    whole.accumulate(f, *args, path="scatter")
+    two = api.Counts(gpu_ctx, cfg.n_cells)
+    two.accumulate(halves[0], *args, path="scatter")
+    two.accumulate(halves[1], *args, path="gemm")
+    a, b = whole.download(), two.download()
+    for x, y in zip(a, b):
+        assert np.array_equal(x, y)
+    M = whole.finalize(1000, 0.01, 0.5, 0.01, "ADD_MIN")
+    assert np.array_equal(M, M.T) and not np.diag(M).any() and M.min() == 0.0
