@@ -1,6 +1,437 @@
-// K3 — int8 tcgen05/TMEM GEMM path (placeholder until the kernel lands in this round).
+// K3 — first-order read-pair counts as a dense int8 GEMM on the 5th-generation tensor cores.
+//
+// Per locus l and cell i let c_b(i) be the number of surviving reads of cell i showing base b.
+// The reference's per-locus contributions are  S_ij = sum_b c_b(i) c_b(j)  (same base) and
+// T_ij = c(i) c(j), c = sum_b c_b  (all pairs), D = T - S. With the 4x4 Hadamard matrix H
+// (H H^T = 4 I, first row all ones) and u = H c:
+//        u_0(i) u_0(j)                       = T_ij
+//        u_1(i) u_1(j) + u_2 u_2 + u_3 u_3   = 4 S_ij - T_ij
+// so ONE K-dimension of 4 int8 values per (cell, locus) feeds two int32 accumulators — 4 MMA
+// K-slices per 32 loci instead of the 5 (four base planes + a total plane) of the direct form.
+//
+//   stage_count_kernel   entries -> packed per-(locus, cell) base counts (4 x u8 in a u32), L2 atomics
+//   transform_kernel     packed counts -> Hadamard planes, transposed into the K-major tile layout
+//                        U[cell][k-block][plane][32 loci] (one 128-byte row per cell and k-block)
+//   syrk_kernel          persistent, warp-specialised: warp 0 = TMA producer (cp.async.bulk.tensor,
+//                        128B swizzle, 4-stage mbarrier ring), warp 1 = tcgen05.mma.kind::i8 issuer
+//                        (M=128, N=256, K=32; accumulators Q = 4S - T and T in TMEM, 2 x 256
+//                        columns), warps 2-5 = epilogue (tcgen05.ld, S = (Q+T)/4, D = T - S,
+//                        RED.ADD into the int32 planes, upper triangle only)
+// Only output tiles that intersect the upper triangle are computed; the K range of a panel is
+// split across CTAs when there are fewer tiles than SMs.
 #include "common.cuh"
 
-int sgpu_gemm_counts(sgpu_ctx *ctx, const sgpu_pileup *, const LinkResult &, sgpu_counts *, uint64_t *) {
-    return sgpu_fail(ctx, SGPU_E_ARG, "GEMM path not built");
+#include <cuda.h>
+
+#include <algorithm>
+#include <vector>
+
+namespace {
+
+constexpr int BM = 128;            // rows (cells) of an output tile = UMMA M
+constexpr int BN = 256;            // columns (cells) of an output tile = UMMA N
+constexpr int KB_BYTES = 128;      // bytes of K per stage and row: 32 loci x 4 planes
+constexpr int LOCI_PER_KB = 32;
+constexpr int STAGES = 4;
+constexpr int A_BYTES = BM * KB_BYTES;  // 16 KB
+constexpr int B_BYTES = BN * KB_BYTES;  // 32 KB
+constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /* alignment slack */ + 256 /* barriers */;
+constexpr int GEMM_THREADS = 192;  // 6 warps
+constexpr uint32_t TMEM_COLS = 512;
+
+// ------------------------------------------------------------------------------------------------
+// staging
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) stage_count_kernel(const uint32_t *__restrict__ code,
+                                                          const uint32_t *__restrict__ eloc, uint64_t e_begin,
+                                                          uint64_t e_end, uint32_t l0, uint32_t n_pad,
+                                                          uint32_t *__restrict__ cnt, int *__restrict__ err) {
+    const uint64_t e = e_begin + static_cast<uint64_t>(blockIdx.x) * 256 + threadIdx.x;
+    if (e >= e_end) {
+        return;
+    }
+    const uint32_t c = code[e];
+    if (c == CODE_DROPPED) {
+        return;
+    }
+    const uint32_t sh = 8u * code_base(c);
+    const uint32_t old = atomicAdd(&cnt[static_cast<uint64_t>(eloc[e] - l0) * n_pad + code_cell(c)], 1u << sh);
+    if (((old >> sh) & 0xFFu) >= 127u) {
+        atomicExch(err, SGPU_E_COUNT_RANGE); // > 127 reads of one cell at one locus: outside int8
+    }
+}
+
+// one block: 32 loci (one k-block) x 64 cells
+__global__ void __launch_bounds__(256) transform_kernel(const uint32_t *__restrict__ cnt, uint32_t n_pad,
+                                                        uint32_t n_loci_panel /* valid loci */,
+                                                        uint64_t row_bytes /* k-blocks * 128 */,
+                                                        int8_t *__restrict__ U, int *__restrict__ err) {
+    __shared__ uint32_t tile[64 * 32]; // [cell][32 words = 4 planes x 8 groups of 4 loci], chunk-swizzled
+    const uint32_t kb = blockIdx.x, cell0 = blockIdx.y * 64;
+    bool bad = false;
+#pragma unroll
+    for (int it = 0; it < 2; ++it) {
+        const uint32_t item = threadIdx.x + it * 256; // 512 items: cell (0..63) x group (0..7)
+        const uint32_t tx = item & 63, g = item >> 6;
+        uint32_t w[4] = { 0, 0, 0, 0 }; // per plane, 4 loci packed
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const uint32_t locus = kb * LOCI_PER_KB + g * 4 + q;
+            uint32_t v = 0;
+            if (locus < n_loci_panel) {
+                v = cnt[static_cast<uint64_t>(locus) * n_pad + cell0 + tx];
+            }
+            const int c0 = v & 0xFF, c1 = (v >> 8) & 0xFF, c2 = (v >> 16) & 0xFF, c3 = v >> 24;
+            const int u0 = c0 + c1 + c2 + c3;
+            const int u1 = c0 - c1 + c2 - c3;
+            const int u2 = c0 + c1 - c2 - c3;
+            const int u3 = c0 - c1 - c2 + c3;
+            bad |= u0 > 127;
+            w[0] |= static_cast<uint32_t>(u0 & 0xFF) << (8 * q);
+            w[1] |= static_cast<uint32_t>(u1 & 0xFF) << (8 * q);
+            w[2] |= static_cast<uint32_t>(u2 & 0xFF) << (8 * q);
+            w[3] |= static_cast<uint32_t>(u3 & 0xFF) << (8 * q);
+        }
+#pragma unroll
+        for (int pl = 0; pl < 4; ++pl) {
+            const uint32_t word = pl * 8 + g;
+            tile[tx * 32 + (word ^ ((tx & 7) << 2))] = w[pl];
+        }
+    }
+    if (bad) {
+        atomicExch(err, SGPU_E_COUNT_RANGE);
+    }
+    __syncthreads();
+    // 64 rows x 8 chunks of 16 bytes
+#pragma unroll
+    for (int it = 0; it < 2; ++it) {
+        const uint32_t item = threadIdx.x + it * 256;
+        const uint32_t row = item >> 3, ch = item & 7;
+        const uint4 v = *reinterpret_cast<const uint4 *>(&tile[row * 32 + ((ch ^ (row & 7)) << 2)]);
+        *reinterpret_cast<uint4 *>(U + static_cast<uint64_t>(cell0 + row) * row_bytes + static_cast<uint64_t>(kb) * KB_BYTES + ch * 16) = v;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// PTX helpers
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    asm volatile(
+            "{\n\t"
+            ".reg .pred p;\n\t"
+            "WAIT_LOOP:\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+            "@p bra WAIT_DONE;\n\t"
+            "bra WAIT_LOOP;\n\t"
+            "WAIT_DONE:\n\t"
+            "}" ::"r"(bar),
+            "r"(parity)
+            : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap *map, uint32_t bar, int32_t c0, int32_t c1) {
+    asm volatile(
+            "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(dst),
+            "l"(map), "r"(bar), "r"(c0), "r"(c1)
+            : "memory");
+}
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile(
+            "{\n\t"
+            ".reg .pred P;\n\t"
+            "elect.sync _|P, 0xffffffff;\n\t"
+            "selp.b32 %0, 1, 0, P;\n\t"
+            "}"
+            : "=r"(pred));
+    return pred != 0;
+}
+// UMMA shared-memory descriptor: K-major, 128B swizzle, 8-row groups 1024 B apart (SBO), LBO = 1
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr) {
+    uint64_t d = 0;
+    d |= static_cast<uint64_t>((saddr & 0x3FFFFu) >> 4);      // start address, bits [0,14)
+    d |= static_cast<uint64_t>(1) << 16;                      // leading byte offset (unused for SW128 K-major)
+    d |= static_cast<uint64_t>(1024 >> 4) << 32;              // stride byte offset
+    d |= static_cast<uint64_t>(1) << 46;                      // descriptor version (Blackwell)
+    d |= static_cast<uint64_t>(2) << 61;                      // SWIZZLE_128B
+    return d;
+}
+// instruction descriptor, kind::i8: D = S32, A = B = signed 8 bit, both K-major, N = 256, M = 128
+constexpr uint32_t IDESC = (2u << 4) | (1u << 7) | (1u << 10) | ((BN >> 3) << 17) | ((BM >> 4) << 24);
+
+__device__ __forceinline__ void umma_i8(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t accumulate) {
+    asm volatile(
+            "{\n\t"
+            ".reg .pred p;\n\t"
+            "setp.ne.b32 p, %4, 0;\n\t"
+            "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n\t"
+            "}" ::"r"(d_tmem),
+            "l"(a_desc), "l"(b_desc), "r"(IDESC), "r"(accumulate)
+            : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+    asm volatile(
+            "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+            "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+            "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+            : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+              "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+              "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+              "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+            : "r"(taddr));
+}
+
+struct WorkItem {
+    uint32_t rb, cb;   // row block (x128), column block (x256)
+    uint32_t k0, k1;   // k-block range
+};
+
+// ------------------------------------------------------------------------------------------------
+// the GEMM
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(GEMM_THREADS, 1) syrk_kernel(const __grid_constant__ CUtensorMap map_u,
+                                                               const WorkItem *__restrict__ work, uint32_t n_work,
+                                                               int32_t *__restrict__ S, int32_t *__restrict__ D,
+                                                               uint32_t n_cells) {
+    extern __shared__ uint8_t smem_raw[];
+    // 128B swizzle needs 1024-byte aligned tiles
+    uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+    uint64_t *bars = reinterpret_cast<uint64_t *>(smem + STAGES * STAGE_BYTES);
+    // bars[0..S) full, [S..2S) empty, [2S] tmem_full, [2S+1] tmem_empty, then the TMEM base address
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 2 * STAGES + 2);
+    const uint32_t full0 = smem_u32(bars), empty0 = smem_u32(bars + STAGES);
+    const uint32_t tmem_full = smem_u32(bars + 2 * STAGES), tmem_empty = smem_u32(bars + 2 * STAGES + 1);
+    const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+    if (warp == 0 && lane == 0) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_u) : "memory");
+        for (int s = 0; s < STAGES; ++s) {
+            mbar_init(full0 + 8 * s, 1);
+            mbar_init(empty0 + 8 * s, 1);
+        }
+        mbar_init(tmem_full, 1);
+        mbar_init(tmem_empty, 128);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(TMEM_COLS));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_base = *tmem_slot;
+    const uint32_t tmem_Q = tmem_base, tmem_T = tmem_base + BN; // columns [0,256) and [256,512)
+
+    if (warp == 0) {
+        // ===== TMA producer =====
+        if (elect_one()) {
+            uint32_t stage = 0, phase = 0;
+            for (uint32_t w = blockIdx.x; w < n_work; w += gridDim.x) {
+                const WorkItem wi = work[w];
+                for (uint32_t kb = wi.k0; kb < wi.k1; ++kb) {
+                    mbar_wait(empty0 + 8 * stage, phase ^ 1);
+                    const uint32_t sa = smem_u32(smem + stage * STAGE_BYTES), sb = sa + A_BYTES;
+                    const uint32_t bar = full0 + 8 * stage;
+                    mbar_expect_tx(bar, STAGE_BYTES);
+                    tma_load_2d(sa, &map_u, bar, kb * KB_BYTES, wi.rb * BM);
+                    tma_load_2d(sb, &map_u, bar, kb * KB_BYTES, wi.cb * BN);
+                    tma_load_2d(sb + A_BYTES, &map_u, bar, kb * KB_BYTES, wi.cb * BN + 128);
+                    if (++stage == STAGES) {
+                        stage = 0;
+                        phase ^= 1;
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===== MMA issuer =====
+        if (elect_one()) {
+            uint32_t stage = 0, phase = 0, acc_phase = 0;
+            for (uint32_t w = blockIdx.x; w < n_work; w += gridDim.x) {
+                const WorkItem wi = work[w];
+                mbar_wait(tmem_empty, acc_phase ^ 1); // epilogue has drained the accumulators
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                for (uint32_t kb = wi.k0; kb < wi.k1; ++kb) {
+                    mbar_wait(full0 + 8 * stage, phase);
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                    const uint32_t sa = smem_u32(smem + stage * STAGE_BYTES), sb = sa + A_BYTES;
+                    const uint32_t first = kb == wi.k0 ? 0u : 1u;
+                    // plane 0 (u_0 = reads per cell) -> T; planes 1..3 -> Q = 4S - T
+                    umma_i8(tmem_T, make_desc(sa), make_desc(sb), first);
+                    umma_i8(tmem_Q, make_desc(sa + 32), make_desc(sb + 32), first);
+                    umma_i8(tmem_Q, make_desc(sa + 64), make_desc(sb + 64), 1u);
+                    umma_i8(tmem_Q, make_desc(sa + 96), make_desc(sb + 96), 1u);
+                    umma_commit(empty0 + 8 * stage); // frees the smem slot once these MMAs retire
+                    if (++stage == STAGES) {
+                        stage = 0;
+                        phase ^= 1;
+                    }
+                }
+                umma_commit(tmem_full); // accumulators complete
+                acc_phase ^= 1;
+            }
+        }
+    } else {
+        // ===== epilogue: warps 2..5, TMEM lanes 32*(warp%4) .. +31 =====
+        const uint32_t lane_base = 32 * (warp & 3);
+        uint32_t acc_phase = 0;
+        for (uint32_t w = blockIdx.x; w < n_work; w += gridDim.x) {
+            const WorkItem wi = work[w];
+            mbar_wait(tmem_full, acc_phase);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const uint32_t row = wi.rb * BM + lane_base + lane;
+            int32_t *Srow = S + static_cast<uint64_t>(row) * n_cells;
+            int32_t *Drow = D + static_cast<uint64_t>(row) * n_cells;
+#pragma unroll 1
+            for (uint32_t cc = 0; cc < BN / 32; ++cc) {
+                uint32_t q[32], t[32];
+                tmem_ld32(tmem_Q + (lane_base << 16) + cc * 32, q);
+                tmem_ld32(tmem_T + (lane_base << 16) + cc * 32, t);
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                const uint32_t col0 = wi.cb * BN + cc * 32;
+                if (row < n_cells && col0 + 31 > row) {
+#pragma unroll
+                    for (int k = 0; k < 32; ++k) {
+                        const uint32_t col = col0 + k;
+                        const int32_t tv = static_cast<int32_t>(t[k]);
+                        const int32_t sv = (static_cast<int32_t>(q[k]) + tv) >> 2; // (4S - T + T) / 4
+                        const int32_t dv = tv - sv;
+                        if (col > row && col < n_cells) {
+                            if (sv) {
+                                atomicAdd(Srow + col, sv);
+                            }
+                            if (dv) {
+                                atomicAdd(Drow + col, dv);
+                            }
+                        }
+                    }
+                }
+            }
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            mbar_arrive(tmem_empty);
+            acc_phase ^= 1;
+        }
+    }
+    __syncthreads();
+    if (warp == 1) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TMEM_COLS));
+    }
+}
+
+} // namespace
+
+int sgpu_gemm_counts(sgpu_ctx *ctx, const sgpu_pileup *p, const LinkResult &lr, sgpu_counts *c, uint64_t *n_pairs) {
+    cudaStream_t st = ctx->stream;
+    if (n_pairs) {
+        *n_pairs = 0; // not enumerated on this path
+    }
+    const uint64_t P = p->n_loci;
+    if (P == 0 || p->n_entries == 0 || c->n < 2) {
+        return SGPU_OK;
+    }
+    const uint32_t N = c->n;
+    const uint32_t n_pad = (N + BN - 1) / BN * BN;
+    // panel: at most ~2 GB of packed counts and as much of Hadamard planes
+    uint64_t panel = (1ull << 31) / (4ull * n_pad) / LOCI_PER_KB * LOCI_PER_KB;
+    panel = std::max<uint64_t>(panel, LOCI_PER_KB);
+    panel = std::min<uint64_t>(panel, (P + LOCI_PER_KB - 1) / LOCI_PER_KB * LOCI_PER_KB);
+    const uint64_t kbs_max = panel / LOCI_PER_KB;
+    const uint64_t row_bytes = kbs_max * KB_BYTES;
+
+    DevBuf<uint32_t> cnt;
+    DevBuf<int8_t> U;
+    DevBuf<int> d_err;
+    DevBuf<WorkItem> d_work;
+    SGPU_CUDA(ctx, cnt.alloc(panel * n_pad, st));
+    SGPU_CUDA(ctx, U.alloc(static_cast<uint64_t>(n_pad) * row_bytes, st));
+    SGPU_CUDA(ctx, d_err.alloc(1, st));
+    SGPU_CUDA(ctx, cudaMemsetAsync(d_err.p, 0, sizeof(int), st));
+
+    // tensor map over U: [n_pad rows][row_bytes], box = 128 rows x 128 bytes, 128B swizzle
+    CUtensorMap map;
+    {
+        const cuuint64_t gdim[2] = { row_bytes, n_pad };
+        const cuuint64_t gstride[1] = { row_bytes };
+        const cuuint32_t box[2] = { KB_BYTES, 128 };
+        const cuuint32_t estr[2] = { 1, 1 };
+        CUresult r = cuTensorMapEncodeTiled(&map, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, U.p, gdim, gstride, box, estr,
+                                            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                                            CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) {
+            return sgpu_fail(ctx, SGPU_E_CUDA, "cuTensorMapEncodeTiled failed (%d)", static_cast<int>(r));
+        }
+    }
+    SGPU_CUDA(ctx, cudaFuncSetAttribute(syrk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+
+    // output tiles that intersect the upper triangle: last column of the tile > first row of the tile
+    std::vector<std::pair<uint32_t, uint32_t>> tiles;
+    for (uint32_t cb = 0; cb < n_pad / BN; ++cb) {
+        for (uint32_t rb = 0; rb < n_pad / BM; ++rb) {
+            if (cb * BN + BN - 1 > rb * BM && rb * BM < N && cb * BN < N) {
+                tiles.emplace_back(rb, cb);
+            }
+        }
+    }
+    // panel boundaries in entries
+    std::vector<uint64_t> h_row(2);
+    for (uint64_t l0 = 0; l0 < P; l0 += panel) {
+        const uint64_t l1 = std::min<uint64_t>(P, l0 + panel);
+        const uint64_t nl = l1 - l0;
+        const uint32_t kbs = static_cast<uint32_t>((nl + LOCI_PER_KB - 1) / LOCI_PER_KB);
+        SGPU_CUDA(ctx, cudaMemcpyAsync(&ctx->h_scratch[0], p->d_row_ptr + l0, sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
+        SGPU_CUDA(ctx, cudaMemcpyAsync(&ctx->h_scratch[1], p->d_row_ptr + l1, sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
+        SGPU_CUDA(ctx, cudaStreamSynchronize(st));
+        const uint64_t e0 = ctx->h_scratch[0], e1 = ctx->h_scratch[1];
+        SGPU_CUDA(ctx, cudaMemsetAsync(cnt.p, 0, nl * n_pad * sizeof(uint32_t), st));
+        if (e1 > e0) {
+            stage_count_kernel<<<static_cast<unsigned>(ceil_div_u64(e1 - e0, 256)), 256, 0, st>>>(lr.code.p, lr.eloc.p, e0, e1,
+                                                                                               static_cast<uint32_t>(l0), n_pad, cnt.p, d_err.p);
+        }
+        transform_kernel<<<dim3(kbs, n_pad / 64), 256, 0, st>>>(cnt.p, n_pad, static_cast<uint32_t>(nl), row_bytes, U.p, d_err.p);
+        // work list: split K so that every SM has work even when there are few tiles
+        uint32_t splits = 1;
+        const uint32_t sms = static_cast<uint32_t>(ctx->sm_count);
+        if (tiles.size() < 2 * sms) {
+            splits = static_cast<uint32_t>(std::min<uint64_t>(kbs, (2 * sms + tiles.size() - 1) / tiles.size()));
+        }
+        std::vector<WorkItem> work;
+        const uint32_t per = (kbs + splits - 1) / splits;
+        for (uint32_t s = 0; s < splits; ++s) {
+            const uint32_t k0 = s * per, k1 = std::min(kbs, k0 + per);
+            if (k0 >= k1) {
+                break;
+            }
+            for (auto &t : tiles) {
+                work.push_back(WorkItem{ t.first, t.second, k0, k1 });
+            }
+        }
+        SGPU_CUDA(ctx, d_work.alloc(work.size(), st));
+        SGPU_CUDA(ctx, cudaMemcpyAsync(d_work.p, work.data(), work.size() * sizeof(WorkItem), cudaMemcpyHostToDevice, st));
+        SGPU_CUDA(ctx, cudaStreamSynchronize(st)); // `work` is pageable host memory
+        const unsigned grid = static_cast<unsigned>(std::min<uint64_t>(work.size(), sms));
+        syrk_kernel<<<grid, GEMM_THREADS, SMEM_BYTES, st>>>(map, d_work.p, static_cast<uint32_t>(work.size()),
+                                                           c->i32 + PLANE_S * c->nn, c->i32 + PLANE_D * c->nn, N);
+        SGPU_CUDA(ctx, cudaGetLastError());
+    }
+    SGPU_CUDA(ctx, cudaMemcpyAsync(&ctx->h_scratch[2], d_err.p, sizeof(int), cudaMemcpyDeviceToHost, st));
+    SGPU_CUDA(ctx, cudaStreamSynchronize(st));
+    if (static_cast<int>(ctx->h_scratch[2] & 0xFFFFFFFFu) != 0) {
+        return sgpu_fail(ctx, SGPU_E_COUNT_RANGE, "more than 127 reads of one cell at one locus: outside the int8 GEMM path, use the scatter path");
+    }
+    return SGPU_OK;
 }
