@@ -73,7 +73,17 @@ typedef struct sgpu_stats {
     float ms_first_order;       /* device time: scatter or staging + GEMM */
     float ms_multi;             /* device time: multi-locus correction */
     float ms_epilogue;          /* device time: log-likelihood transform + normalisation */
+    float ms_stage;             /* GEMM path: count staging + Hadamard transform kernels */
+    float ms_gemm;              /* GEMM path: the tcgen05 kernel alone (sum over panels) */
+    uint64_t gemm_launches;     /* GEMM path: number of tcgen05 kernel launches */
 } sgpu_stats;
+
+/* parameters of the device-side synthetic pileup generator (bench / large tests), DESIGN.md */
+typedef struct sgpu_synth_params {
+    uint32_t n_cells, n_chr, loci_per_chr, n_clones, spacing, reserved;
+    float coverage, frac_somatic, frac_germline, theta, p_multi, p_mate, p_mate_mismatch, reserved2;
+    uint64_t seed;
+} sgpu_synth_params;
 
 /* ---- context ---------------------------------------------------------------------------- */
 int sgpu_init(int device, sgpu_ctx **ctx);
@@ -83,6 +93,8 @@ const char *sgpu_last_error(const sgpu_ctx *ctx);
  * context's own stream. */
 int sgpu_set_stream(sgpu_ctx *ctx, void *cuda_stream);
 int sgpu_synchronize(sgpu_ctx *ctx);
+/* number of CUDA kernels this context has launched so far */
+uint64_t sgpu_launch_count(const sgpu_ctx *ctx);
 
 /* ---- pileup staging (replaces the host vector<vector<PosData>>) --------------------------- */
 int sgpu_pileup_upload(sgpu_ctx *ctx, uint32_t n_chr, const uint64_t *chr_ptr, const uint64_t *row_ptr,
@@ -96,6 +108,9 @@ int sgpu_pileup_dims(const sgpu_pileup *p, uint32_t *n_chr, uint64_t *n_loci, ui
 int sgpu_pileup_download(sgpu_ctx *ctx, const sgpu_pileup *p, uint64_t *chr_ptr, uint64_t *row_ptr,
                          uint32_t *position, uint32_t *read_id, uint16_t *gid_base);
 void sgpu_pileup_free(sgpu_ctx *ctx, sgpu_pileup *p);
+/* Deterministic synthetic pileup generated directly in HBM (counter-based: every entry is a pure
+ * function of seed, locus and slot, so any sub-range can be downloaded and replayed on the CPU). */
+int sgpu_synth_pileup(sgpu_ctx *ctx, const sgpu_synth_params *params, sgpu_pileup **out);
 
 /* ---- Filter (util/is_significant.cpp) -------------------------------------------------------- */
 /* Filter::is_significant(std::array<uint16_t,4>&) on n count tuples, evaluated on the GPU. */

@@ -32,12 +32,23 @@ class Stats(C.Structure):
         ("n_pairs_first", C.c_uint64), ("n_pairs_multi", C.c_uint64),
         ("path_used", C.c_int32), ("reserved", C.c_int32),
         ("ms_link", C.c_float), ("ms_first_order", C.c_float), ("ms_multi", C.c_float), ("ms_epilogue", C.c_float),
+        ("ms_stage", C.c_float), ("ms_gemm", C.c_float), ("gemm_launches", C.c_uint64),
     ]
 
     def as_dict(self):
         d = {k: getattr(self, k) for k, _ in self._fields_ if k != "reserved"}
         d["path_used"] = PATH_NAMES.get(d["path_used"], str(d["path_used"]))
         return d
+
+
+class SynthParams(C.Structure):
+    _fields_ = [
+        ("n_cells", C.c_uint32), ("n_chr", C.c_uint32), ("loci_per_chr", C.c_uint32), ("n_clones", C.c_uint32),
+        ("spacing", C.c_uint32), ("reserved", C.c_uint32),
+        ("coverage", C.c_float), ("frac_somatic", C.c_float), ("frac_germline", C.c_float), ("theta", C.c_float),
+        ("p_multi", C.c_float), ("p_mate", C.c_float), ("p_mate_mismatch", C.c_float), ("reserved2", C.c_float),
+        ("seed", C.c_uint64),
+    ]
 
 
 _vp = C.c_void_p
@@ -51,6 +62,8 @@ SIGNATURES = {
     "sgpu_last_error": (C.c_char_p, [_vp]),
     "sgpu_set_stream": (C.c_int, [_vp, _vp]),
     "sgpu_synchronize": (C.c_int, [_vp]),
+    "sgpu_launch_count": (C.c_uint64, [_vp]),
+    "sgpu_synth_pileup": (C.c_int, [_vp, C.POINTER(SynthParams), C.POINTER(_vp)]),
     "sgpu_pileup_upload": (C.c_int, [_vp, C.c_uint32, _vp, _vp, _vp, _vp, _vp, C.POINTER(_vp)]),
     "sgpu_pileup_wrap_device": (C.c_int, [_vp, C.c_uint32, _vp, _vp, _vp, _vp, _vp, C.POINTER(_vp)]),
     "sgpu_pileup_dims": (C.c_int, [_vp, _u32p, _u64p, _u64p]),

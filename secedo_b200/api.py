@@ -54,6 +54,23 @@ class Context:
     def synchronize(self) -> None:
         self.check(self._lib.sgpu_synchronize(self._h))
 
+    def launch_count(self) -> int:
+        """CUDA kernels launched by this context so far."""
+        return int(self._lib.sgpu_launch_count(self._h))
+
+    def synth_pileup(self, n_cells: int, coverage: float, n_chr: int, loci_per_chr: int, *, n_clones: int = 2,
+                     frac_somatic: float = 0.5, frac_germline: float = 0.1, theta: float = 0.001,
+                     spacing: int = 400, p_multi: float = 0.0, p_mate: float = 0.0, p_mate_mismatch: float = 0.2,
+                     seed: int = 1) -> "DevicePileup":
+        """Deterministic synthetic pileup generated in HBM (csrc/synth.cu); bench-scale input."""
+        sp = _lib.SynthParams(n_cells=n_cells, n_chr=n_chr, loci_per_chr=loci_per_chr, n_clones=n_clones,
+                              spacing=spacing, coverage=coverage, frac_somatic=frac_somatic,
+                              frac_germline=frac_germline, theta=theta, p_multi=p_multi, p_mate=p_mate,
+                              p_mate_mismatch=p_mate_mismatch, seed=seed)
+        h = C.c_void_p()
+        self.check(self._lib.sgpu_synth_pileup(self._h, C.byref(sp), C.byref(h)))
+        return DevicePileup(self, h)
+
     def close(self) -> None:
         if self._h:
             self._lib.sgpu_shutdown(self._h)
@@ -239,13 +256,18 @@ class Counts:
         return S1, D1, H, hist
 
     def finalize(self, max_fragment_length: int, mutation_rate: float, homozygous_rate: float,
-                 seq_error_rate: float, normalization: str, out: Optional[np.ndarray] = None) -> np.ndarray:
+                 seq_error_rate: float, normalization: str, out: Optional[np.ndarray] = None,
+                 to_host: bool = True) -> Optional[np.ndarray]:
+        """``to_host=False`` runs the epilogue but leaves the matrix in HBM (device-only timing)."""
         if normalization not in NORMALIZATIONS:
             raise ValueError("Invalid normalization: " + str(normalization))  # similarity_matrix.cpp:264
         n = self.num_cells
-        if out is None:
-            out = np.zeros((n, n), np.float64)
-        assert out.dtype == np.float64 and out.flags.c_contiguous and out.size == n * n
+        if to_host:
+            if out is None:
+                out = np.zeros((n, n), np.float64)
+            assert out.dtype == np.float64 and out.flags.c_contiguous and out.size == n * n
+        else:
+            out = None
         st = Stats()
         self.ctx.check(self.ctx._lib.sgpu_similarity_finalize(self.ctx._h, self._h, int(max_fragment_length),
                                                               float(mutation_rate), float(homozygous_rate),

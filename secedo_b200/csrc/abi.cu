@@ -119,6 +119,8 @@ int sgpu_set_stream(sgpu_ctx *ctx, void *cuda_stream) {
     return SGPU_OK;
 }
 
+uint64_t sgpu_launch_count(const sgpu_ctx *ctx) { return ctx ? ctx->launches : 0; }
+
 int sgpu_synchronize(sgpu_ctx *ctx) {
     SGPU_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     return SGPU_OK;
@@ -331,6 +333,8 @@ int sgpu_counts_accumulate(sgpu_ctx *ctx, sgpu_counts *c, const sgpu_pileup *fil
     s.n_dropped_entries = lr.n_dropped;
     s.n_multi_reads = lr.n_multi;
     s.n_tail_reads = lr.n_tail;
+    ctx->ms_syrk = ctx->ms_stage = 0.f;
+    ctx->n_syrk = 0;
     {
         EventTimer t(ctx->stream);
         if (path == SGPU_PATH_SCATTER) {
@@ -342,6 +346,9 @@ int sgpu_counts_accumulate(sgpu_ctx *ctx, sgpu_counts *c, const sgpu_pileup *fil
             }
         }
         s.ms_first_order = t.stop();
+        s.ms_stage = ctx->ms_stage;
+        s.ms_gemm = ctx->ms_syrk;
+        s.gemm_launches = ctx->n_syrk;
     }
     {
         EventTimer t(ctx->stream);

@@ -22,7 +22,18 @@ struct sgpu_ctx {
     // small pinned scratch for device->host scalars
     uint64_t *h_scratch = nullptr; // 64 x u64, pinned
     uint64_t *d_scratch = nullptr; // 64 x u64, device
+    uint64_t launches = 0;         // kernels launched by this context (sgpu_launch_count)
+    // device time of the dominant kernels since the last sgpu_kernel_times() reset, from CUDA events
+    // recorded on ctx->stream around the launches
+    float ms_syrk = 0.f, ms_stage = 0.f;
+    uint64_t n_syrk = 0;
 };
+
+#define SGPU_LAUNCH(ctx, call) \
+    do {                       \
+        ++(ctx)->launches;     \
+        call;                  \
+    } while (0)
 
 int sgpu_fail(sgpu_ctx *ctx, int code, const char *fmt, ...);
 

@@ -268,9 +268,9 @@ int device_log_probs(sgpu_ctx *ctx, double eps, double h, double theta, uint32_t
     SGPU_CUDA(ctx, ls.alloc(static_cast<size_t>(n) * n, st));
     SGPU_CUDA(ctx, ld.alloc(static_cast<size_t>(n) * n, st));
     SGPU_CUDA(ctx, cudaMemcpyAsync(dc.p, &hc, sizeof(hc), cudaMemcpyHostToDevice, st));
-    SGPU_CUDA(ctx, cudaStreamSynchronize(st)); // hc lives on this stack frame
-    pascal_kernel<<<1, 128, 0, st>>>(comb.p);
-    logprob_kernel<<<(n * n + 63) / 64, 64, 0, st>>>(dc.p, comb.p, n, L, ls.p, ld.p);
+    SGPU_CUDA(ctx, cudaStreamSynchronize(st)); SGPU_LAUNCH(ctx, (// hc lives on this stack frame
+    pascal_kernel<<<1, 128, 0, st>>>(comb.p)));
+    SGPU_LAUNCH(ctx, (logprob_kernel<<<(n * n + 63) / 64, 64, 0, st>>>(dc.p, comb.p, n, L, ls.p, ld.p)));
     SGPU_CUDA(ctx, cudaGetLastError());
     SGPU_CUDA(ctx, cudaStreamSynchronize(st));
     return SGPU_OK;
@@ -295,7 +295,7 @@ int sgpu_build_gtable(sgpu_ctx *ctx, double eps, double h, double theta, uint32_
                       double *d_F) {
     DevBuf<double> ls, ld;
     SGPU_TRY(device_log_probs(ctx, eps, h, theta, L, n, ls, ld));
-    gtable_kernel<<<(SGPU_MAX_CLASS * SGPU_MAX_CLASS + 255) / 256, 256, 0, ctx->stream>>>(ls.p, ld.p, n, d_G, d_F);
+    SGPU_LAUNCH(ctx, (gtable_kernel<<<(SGPU_MAX_CLASS * SGPU_MAX_CLASS + 255) / 256, 256, 0, ctx->stream>>>(ls.p, ld.p, n, d_G, d_F)));
     SGPU_CUDA(ctx, cudaGetLastError());
     SGPU_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     return SGPU_OK;
@@ -352,14 +352,16 @@ int sgpu_epilogue(sgpu_ctx *ctx, sgpu_counts *c, uint32_t L, double eps, double 
     const unsigned long long init[2] = { ~0ull, 0ull };
     SGPU_CUDA(ctx, cudaMemcpyAsync(d_minmax.p, init, sizeof(init), cudaMemcpyHostToDevice, st));
     const unsigned grid = static_cast<unsigned>(ceil_div_u64(c->nn, TR_THREADS));
-    transform_kernel<<<grid, TR_THREADS, 0, st>>>(a, raw.p, d_minmax.p);
+    SGPU_LAUNCH(ctx, (transform_kernel<<<grid, TR_THREADS, 0, st>>>(a, raw.p, d_minmax.p)));
     SGPU_CUDA(ctx, cudaGetLastError());
     SGPU_CUDA(ctx, cudaMemcpyAsync(&ctx->h_scratch[0], d_minmax.p, 2 * sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
     SGPU_CUDA(ctx, cudaStreamSynchronize(st));
     const double mn = dec(ctx->h_scratch[0]), mx = dec(ctx->h_scratch[1]);
-    normalize_kernel<<<grid, TR_THREADS, 0, st>>>(raw.p, c->n, c->nn, normalization, mn, mx);
+    SGPU_LAUNCH(ctx, (normalize_kernel<<<grid, TR_THREADS, 0, st>>>(raw.p, c->n, c->nn, normalization, mn, mx)));
     SGPU_CUDA(ctx, cudaGetLastError());
-    SGPU_CUDA(ctx, cudaMemcpyAsync(h_out, raw.p, c->nn * sizeof(double), cudaMemcpyDeviceToHost, st));
+    if (h_out) { // NULL: leave the result on the device (timing of the device-resident path)
+        SGPU_CUDA(ctx, cudaMemcpyAsync(h_out, raw.p, c->nn * sizeof(double), cudaMemcpyDeviceToHost, st));
+    }
     SGPU_CUDA(ctx, cudaStreamSynchronize(st));
     return SGPU_OK;
 }

@@ -247,7 +247,7 @@ int sgpu_is_significant_impl(sgpu_ctx *ctx, const uint16_t *h_counts4, uint64_t 
     SGPU_CUDA(ctx, d_in.alloc(4 * n, st));
     SGPU_CUDA(ctx, d_out.alloc(n, st));
     SGPU_CUDA(ctx, cudaMemcpyAsync(d_in.p, h_counts4, 4 * n * sizeof(uint16_t), cudaMemcpyHostToDevice, st));
-    is_significant_kernel<<<static_cast<unsigned>(ceil_div_u64(n, 256)), 256, 0, st>>>(d_in.p, n, make_params(theta, cell_proportion), d_out.p);
+    SGPU_LAUNCH(ctx, (is_significant_kernel<<<static_cast<unsigned>(ceil_div_u64(n, 256)), 256, 0, st>>>(d_in.p, n, make_params(theta, cell_proportion), d_out.p)));
     SGPU_CUDA(ctx, cudaGetLastError());
     SGPU_CUDA(ctx, cudaMemcpyAsync(h_out, d_out.p, n, cudaMemcpyDeviceToHost, st));
     SGPU_CUDA(ctx, cudaStreamSynchronize(st));
@@ -294,8 +294,8 @@ int sgpu_filter_impl(sgpu_ctx *ctx, const sgpu_pileup *in, const uint32_t *h_id_
         SGPU_CUDA(ctx, cudaFuncSetAttribute(filter_compact_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     }
     if (P) {
-        filter_count_kernel<<<grid, FILTER_THREADS, smem, st>>>(in->d_row_ptr, in->d_gid_base, P, d_mask.p, n_groups, fp,
-                                                               d_keep.p, d_cnt.p, d_err.p);
+        SGPU_LAUNCH(ctx, (filter_count_kernel<<<grid, FILTER_THREADS, smem, st>>>(in->d_row_ptr, in->d_gid_base, P, d_mask.p, n_groups, fp,
+                                                               d_keep.p, d_cnt.p, d_err.p)));
         SGPU_CUDA(ctx, cudaGetLastError());
     }
     SGPU_TRY(sgpu_scan_u8_u64(ctx, d_keep.p, d_new_locus.p, P));
@@ -322,13 +322,13 @@ int sgpu_filter_impl(sgpu_ctx *ctx, const sgpu_pileup *in, const uint32_t *h_id_
     SGPU_CUDA(ctx, cudaMalloc(&out->d_read_id, (Ek ? Ek : 1) * sizeof(uint32_t)));
     SGPU_CUDA(ctx, cudaMalloc(&out->d_gid_base, (Ek ? Ek : 1) * sizeof(uint16_t)));
     if (P) {
-        filter_compact_kernel<<<grid, FILTER_THREADS, smem, st>>>(in->d_row_ptr, in->d_position, in->d_read_id, in->d_gid_base,
+        SGPU_LAUNCH(ctx, (filter_compact_kernel<<<grid, FILTER_THREADS, smem, st>>>(in->d_row_ptr, in->d_position, in->d_read_id, in->d_gid_base,
                                                                  P, d_mask.p, n_groups, d_keep.p, d_new_locus.p, d_new_row.p,
                                                                  out->d_row_ptr, out->d_position, out->d_read_id,
-                                                                 out->d_gid_base);
+                                                                 out->d_gid_base)));
     }
-    remap_chr_ptr_kernel<<<(in->n_chr + 256) / 256, 256, 0, st>>>(in->d_chr_ptr, in->n_chr, d_new_locus.p, out->d_chr_ptr,
-                                                                 out->d_row_ptr, d_new_row.p, P);
+    SGPU_LAUNCH(ctx, (remap_chr_ptr_kernel<<<(in->n_chr + 256) / 256, 256, 0, st>>>(in->d_chr_ptr, in->n_chr, d_new_locus.p, out->d_chr_ptr,
+                                                                 out->d_row_ptr, d_new_row.p, P)));
     SGPU_CUDA(ctx, cudaGetLastError());
     SGPU_CUDA(ctx, cudaMemcpyAsync(out->h_chr_ptr, out->d_chr_ptr, (in->n_chr + 1) * sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
     SGPU_CUDA(ctx, cudaStreamSynchronize(st));

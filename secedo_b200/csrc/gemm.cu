@@ -369,7 +369,18 @@ int sgpu_gemm_counts(sgpu_ctx *ctx, const sgpu_pileup *p, const LinkResult &lr, 
         const cuuint64_t gstride[1] = { row_bytes };
         const cuuint32_t box[2] = { KB_BYTES, 128 };
         const cuuint32_t estr[2] = { 1, 1 };
-        CUresult r = cuTensorMapEncodeTiled(&map, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, U.p, gdim, gstride, box, estr,
+        // resolved through the runtime so that the library does not link libcuda.so (it must load, and
+        // fail loudly in sgpu_init, on a machine without a driver)
+        typedef CUresult (*encode_fn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                      const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                      CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+        void *fn = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        SGPU_CUDA(ctx, cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
+        if (fn == nullptr || qres != cudaDriverEntryPointSuccess) {
+            return sgpu_fail(ctx, SGPU_E_CUDA, "driver does not provide cuTensorMapEncodeTiled");
+        }
+        CUresult r = reinterpret_cast<encode_fn>(fn)(&map, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, U.p, gdim, gstride, box, estr,
                                             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
                                             CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         if (r != CUDA_SUCCESS) {
@@ -387,8 +398,14 @@ int sgpu_gemm_counts(sgpu_ctx *ctx, const sgpu_pileup *p, const LinkResult &lr, 
             }
         }
     }
-    // panel boundaries in entries
-    std::vector<uint64_t> h_row(2);
+    // CUDA events on the launching stream around the staging kernels and around the tcgen05 kernel
+    std::vector<cudaEvent_t> evs;
+    auto mark = [&]() {
+        cudaEvent_t e;
+        cudaEventCreate(&e);
+        cudaEventRecord(e, st);
+        evs.push_back(e);
+    };
     for (uint64_t l0 = 0; l0 < P; l0 += panel) {
         const uint64_t l1 = std::min<uint64_t>(P, l0 + panel);
         const uint64_t nl = l1 - l0;
@@ -397,12 +414,13 @@ int sgpu_gemm_counts(sgpu_ctx *ctx, const sgpu_pileup *p, const LinkResult &lr, 
         SGPU_CUDA(ctx, cudaMemcpyAsync(&ctx->h_scratch[1], p->d_row_ptr + l1, sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
         SGPU_CUDA(ctx, cudaStreamSynchronize(st));
         const uint64_t e0 = ctx->h_scratch[0], e1 = ctx->h_scratch[1];
+        mark(); // [3k] staging begins
         SGPU_CUDA(ctx, cudaMemsetAsync(cnt.p, 0, nl * n_pad * sizeof(uint32_t), st));
         if (e1 > e0) {
-            stage_count_kernel<<<static_cast<unsigned>(ceil_div_u64(e1 - e0, 256)), 256, 0, st>>>(lr.code.p, lr.eloc.p, e0, e1,
-                                                                                               static_cast<uint32_t>(l0), n_pad, cnt.p, d_err.p);
+            SGPU_LAUNCH(ctx, (stage_count_kernel<<<static_cast<unsigned>(ceil_div_u64(e1 - e0, 256)), 256, 0, st>>>(lr.code.p, lr.eloc.p, e0, e1,
+                                                                                               static_cast<uint32_t>(l0), n_pad, cnt.p, d_err.p)));
         }
-        transform_kernel<<<dim3(kbs, n_pad / 64), 256, 0, st>>>(cnt.p, n_pad, static_cast<uint32_t>(nl), row_bytes, U.p, d_err.p);
+        SGPU_LAUNCH(ctx, (transform_kernel<<<dim3(kbs, n_pad / 64), 256, 0, st>>>(cnt.p, n_pad, static_cast<uint32_t>(nl), row_bytes, U.p, d_err.p)));
         // work list: split K so that every SM has work even when there are few tiles
         uint32_t splits = 1;
         const uint32_t sms = static_cast<uint32_t>(ctx->sm_count);
@@ -424,12 +442,25 @@ int sgpu_gemm_counts(sgpu_ctx *ctx, const sgpu_pileup *p, const LinkResult &lr, 
         SGPU_CUDA(ctx, cudaMemcpyAsync(d_work.p, work.data(), work.size() * sizeof(WorkItem), cudaMemcpyHostToDevice, st));
         SGPU_CUDA(ctx, cudaStreamSynchronize(st)); // `work` is pageable host memory
         const unsigned grid = static_cast<unsigned>(std::min<uint64_t>(work.size(), sms));
-        syrk_kernel<<<grid, GEMM_THREADS, SMEM_BYTES, st>>>(map, d_work.p, static_cast<uint32_t>(work.size()),
-                                                           c->i32 + PLANE_S * c->nn, c->i32 + PLANE_D * c->nn, N);
+        mark(); // [3k+1] staging done (the host sync above is inside the staging interval), GEMM begins
+        SGPU_LAUNCH(ctx, (syrk_kernel<<<grid, GEMM_THREADS, SMEM_BYTES, st>>>(map, d_work.p, static_cast<uint32_t>(work.size()),
+                                                           c->i32 + PLANE_S * c->nn, c->i32 + PLANE_D * c->nn, N)));
         SGPU_CUDA(ctx, cudaGetLastError());
+        mark(); // [3k+2] GEMM done
+        ++ctx->n_syrk;
     }
     SGPU_CUDA(ctx, cudaMemcpyAsync(&ctx->h_scratch[2], d_err.p, sizeof(int), cudaMemcpyDeviceToHost, st));
     SGPU_CUDA(ctx, cudaStreamSynchronize(st));
+    for (size_t k = 0; k + 2 < evs.size(); k += 3) {
+        float a = 0.f, b = 0.f;
+        cudaEventElapsedTime(&a, evs[k], evs[k + 1]);
+        cudaEventElapsedTime(&b, evs[k + 1], evs[k + 2]);
+        ctx->ms_stage += a;
+        ctx->ms_syrk += b;
+    }
+    for (cudaEvent_t e : evs) {
+        cudaEventDestroy(e);
+    }
     if (static_cast<int>(ctx->h_scratch[2] & 0xFFFFFFFFu) != 0) {
         return sgpu_fail(ctx, SGPU_E_COUNT_RANGE, "more than 127 reads of one cell at one locus: outside the int8 GEMM path, use the scatter path");
     }

@@ -156,7 +156,7 @@ int sgpu_multilocus(sgpu_ctx *ctx, const sgpu_pileup *p, const LinkResult &lr, s
     DevBuf<double> d_G;
     SGPU_CUDA(ctx, flag.alloc(E, st));
     SGPU_CUDA(ctx, idx.alloc(E + 1, st));
-    multi_entry_flag_kernel<<<blocks_for(E), TB, 0, st>>>(lr.code.p, E, flag.p);
+    SGPU_LAUNCH(ctx, (multi_entry_flag_kernel<<<blocks_for(E), TB, 0, st>>>(lr.code.p, E, flag.p)));
     SGPU_TRY(sgpu_scan_u8_u64(ctx, flag.p, idx.p, E));
     SGPU_CUDA(ctx, cudaMemcpyAsync(&ctx->h_scratch[0], idx.p + E, sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
     SGPU_CUDA(ctx, cudaStreamSynchronize(st));
@@ -165,7 +165,7 @@ int sgpu_multilocus(sgpu_ctx *ctx, const sgpu_pileup *p, const LinkResult &lr, s
         return SGPU_OK;
     }
     SGPU_CUDA(ctx, me.alloc(NME, st));
-    multi_entry_compact_kernel<<<blocks_for(E), TB, 0, st>>>(flag.p, idx.p, E, me.p);
+    SGPU_LAUNCH(ctx, (multi_entry_compact_kernel<<<blocks_for(E), TB, 0, st>>>(flag.p, idx.p, E, me.p)));
     SGPU_CUDA(ctx, d_np.alloc(1, st));
     SGPU_CUDA(ctx, d_max.alloc(1, st));
     SGPU_CUDA(ctx, d_err.alloc(1, st));
@@ -200,7 +200,7 @@ int sgpu_multilocus(sgpu_ctx *ctx, const sgpu_pileup *p, const LinkResult &lr, s
     a.max_order = d_max.p;
     a.n_pairs = d_np.p;
     a.err = d_err.p;
-    multilocus_kernel<<<blocks_for(NME), TB, 0, st>>>(a);
+    SGPU_LAUNCH(ctx, (multilocus_kernel<<<blocks_for(NME), TB, 0, st>>>(a)));
     SGPU_CUDA(ctx, cudaGetLastError());
     SGPU_CUDA(ctx, cudaMemcpyAsync(&ctx->h_scratch[0], d_np.p, sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
     SGPU_CUDA(ctx, cudaMemcpyAsync(&ctx->h_scratch[1], d_max.p, sizeof(unsigned int), cudaMemcpyDeviceToHost, st));
@@ -223,7 +223,7 @@ int sgpu_multilocus(sgpu_ctx *ctx, const sgpu_pileup *p, const LinkResult &lr, s
         a.spill = c->spill;
         a.G = d_G.p;
         a.spill_only = 1;
-        multilocus_kernel<<<blocks_for(NME), TB, 0, st>>>(a);
+        SGPU_LAUNCH(ctx, (multilocus_kernel<<<blocks_for(NME), TB, 0, st>>>(a)));
         SGPU_CUDA(ctx, cudaGetLastError());
         SGPU_CUDA(ctx, cudaStreamSynchronize(st));
     }

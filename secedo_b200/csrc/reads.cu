@@ -389,7 +389,7 @@ int sgpu_link_reads(sgpu_ctx *ctx, const sgpu_pileup *p, uint32_t num_cells, uin
     SGPU_CUDA(ctx, cudaMemcpyAsync(gmap.p, h_group_id_to_pos, n_groups * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
 
     const unsigned locus_grid = static_cast<unsigned>(std::min<uint64_t>(ceil_div_u64(P, TB / 32), static_cast<uint64_t>(ctx->sm_count) * 32));
-    locus_fill_kernel<<<locus_grid, TB, 0, st>>>(p->d_row_ptr, p->d_position, p->d_chr_ptr, p->n_chr, P, out->eloc.p, lchr.p, d_err.p);
+    SGPU_LAUNCH(ctx, (locus_fill_kernel<<<locus_grid, TB, 0, st>>>(p->d_row_ptr, p->d_position, p->d_chr_ptr, p->n_chr, P, out->eloc.p, lchr.p, d_err.p)));
 
     // ---- hash: (chromosome, read id) -> first entry
     uint64_t cap = 1024;
@@ -400,8 +400,8 @@ int sgpu_link_reads(sgpu_ctx *ctx, const sgpu_pileup *p, uint32_t num_cells, uin
     SGPU_CUDA(ctx, vals.alloc(cap, st));
     SGPU_CUDA(ctx, cudaMemsetAsync(keys.p, 0xFF, cap * sizeof(uint64_t), st));
     SGPU_CUDA(ctx, cudaMemsetAsync(vals.p, 0xFF, cap * sizeof(uint32_t), st));
-    link_insert_kernel<<<blocks_for(E), TB, 0, st>>>(p->d_read_id, out->eloc.p, lchr.p, E, keys.p, vals.p, cap - 1, efirst.p);
-    link_first_kernel<<<blocks_for(E), TB, 0, st>>>(efirst.p, vals.p, E, isfirst.p);
+    SGPU_LAUNCH(ctx, (link_insert_kernel<<<blocks_for(E), TB, 0, st>>>(p->d_read_id, out->eloc.p, lchr.p, E, keys.p, vals.p, cap - 1, efirst.p)));
+    SGPU_LAUNCH(ctx, (link_first_kernel<<<blocks_for(E), TB, 0, st>>>(efirst.p, vals.p, E, isfirst.p)));
     SGPU_CUDA(ctx, cudaGetLastError());
     keys.release();
     vals.release();
@@ -426,9 +426,9 @@ int sgpu_link_reads(sgpu_ctx *ctx, const sgpu_pileup *p, uint32_t num_cells, uin
     SGPU_CUDA(ctx, cudaMemsetAsync(r_extra.p, 0, R * sizeof(uint32_t), st));
     SGPU_CUDA(ctx, cudaMemsetAsync(cursor.p, 0, R * sizeof(uint32_t), st));
     SGPU_CUDA(ctx, cudaMemsetAsync(nst.p, 0, R * sizeof(uint32_t), st));
-    link_reads_kernel<<<blocks_for(E), TB, 0, st>>>(efirst.p, rscan.p, p->d_gid_base, out->eloc.p, gmap.p, n_groups, num_cells, E,
-                                                   out->eread.p, r_cell.p, r_startloc.p, r_extra.p, d_err.p);
-    cand_flag_kernel<<<blocks_for(R), TB, 0, st>>>(r_extra.p, R, cand.p, clen.p);
+    SGPU_LAUNCH(ctx, (link_reads_kernel<<<blocks_for(E), TB, 0, st>>>(efirst.p, rscan.p, p->d_gid_base, out->eloc.p, gmap.p, n_groups, num_cells, E,
+                                                   out->eread.p, r_cell.p, r_startloc.p, r_extra.p, d_err.p)));
+    SGPU_LAUNCH(ctx, (cand_flag_kernel<<<blocks_for(R), TB, 0, st>>>(r_extra.p, R, cand.p, clen.p)));
     SGPU_CUDA(ctx, cudaGetLastError());
     SGPU_TRY(sgpu_scan_u32_u64(ctx, clen.p, c_off.p, R));
     SGPU_CUDA(ctx, cudaMemcpyAsync(&ctx->h_scratch[0], c_off.p + R, sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
@@ -440,16 +440,16 @@ int sgpu_link_reads(sgpu_ctx *ctx, const sgpu_pileup *p, uint32_t num_cells, uin
     SGPU_CUDA(ctx, c_list.alloc(CE ? CE : 1, st));
     SGPU_CUDA(ctx, c_base.alloc(CE ? CE : 1, st));
     if (CE) {
-        cand_fill_kernel<<<blocks_for(E), TB, 0, st>>>(out->eread.p, cand.p, c_off.p, E, cursor.p, c_list.p);
-        mate_rule_kernel<<<blocks_for(R), TB, 0, st>>>(cand.p, c_off.p, R, c_list.p, c_base.p, out->eloc.p, p->d_gid_base,
-                                                      p->d_position, r_startloc.p, L, edrop.p, nst.p, d_err.p);
+        SGPU_LAUNCH(ctx, (cand_fill_kernel<<<blocks_for(E), TB, 0, st>>>(out->eread.p, cand.p, c_off.p, E, cursor.p, c_list.p)));
+        SGPU_LAUNCH(ctx, (mate_rule_kernel<<<blocks_for(R), TB, 0, st>>>(cand.p, c_off.p, R, c_list.p, c_base.p, out->eloc.p, p->d_gid_base,
+                                                      p->d_position, r_startloc.p, L, edrop.p, nst.p, d_err.p)));
     }
-    // ---- cutoff K per chromosome
-    readbase_kernel<<<blocks_for(P + 1), TB, 0, st>>>(p->d_row_ptr, rscan.p, P, readbase.p);
-    cutoff_kernel<<<(p->n_chr + 31) / 32, 32, 0, st>>>(p->d_chr_ptr, p->n_chr, p->d_position, readbase.p, L, num_threads, Kglob.p);
-    // ---- codes
+    SGPU_LAUNCH(ctx, (// ---- cutoff K per chromosome
+    readbase_kernel<<<blocks_for(P + 1), TB, 0, st>>>(p->d_row_ptr, rscan.p, P, readbase.p)));
+    SGPU_LAUNCH(ctx, (cutoff_kernel<<<(p->n_chr + 31) / 32, 32, 0, st>>>(p->d_chr_ptr, p->n_chr, p->d_position, readbase.p, L, num_threads, Kglob.p)));
+    SGPU_LAUNCH(ctx, (// ---- codes
     make_codes_kernel<<<blocks_for(E), TB, 0, st>>>(out->eread.p, efirst.p, out->eloc.p, lchr.p, p->d_gid_base, r_cell.p, cand.p,
-                                                   nst.p, edrop.p, Kglob.p, E, out->code.p, d_stats.p);
+                                                   nst.p, edrop.p, Kglob.p, E, out->code.p, d_stats.p)));
     SGPU_CUDA(ctx, cudaGetLastError());
 
     // ---- multi-locus read tables
@@ -460,7 +460,7 @@ int sgpu_link_reads(sgpu_ctx *ctx, const sgpu_pileup *p, uint32_t num_cells, uin
     SGPU_CUDA(ctx, mlen.alloc(R, st));
     SGPU_CUDA(ctx, midx.alloc(R + 1, st));
     SGPU_CUDA(ctx, moff_r.alloc(R + 1, st));
-    multi_flag_kernel<<<blocks_for(R), TB, 0, st>>>(cand.p, nst.p, R, mflag.p, mlen.p);
+    SGPU_LAUNCH(ctx, (multi_flag_kernel<<<blocks_for(R), TB, 0, st>>>(cand.p, nst.p, R, mflag.p, mlen.p)));
     SGPU_TRY(sgpu_scan_u8_u64(ctx, mflag.p, midx.p, R));
     SGPU_TRY(sgpu_scan_u32_u64(ctx, mlen.p, moff_r.p, R));
     // scalars to the host: n_multi, total stored, error, stats, K per chromosome, reads per chromosome
@@ -498,8 +498,8 @@ int sgpu_link_reads(sgpu_ctx *ctx, const sgpu_pileup *p, uint32_t num_cells, uin
     SGPU_CUDA(ctx, out->m_off.alloc(NM + 1, st));
     SGPU_CUDA(ctx, out->m_locus.alloc(MS ? MS : 1, st));
     SGPU_CUDA(ctx, out->m_base.alloc(MS ? MS : 1, st));
-    multi_copy_kernel<<<blocks_for(R + 1), TB, 0, st>>>(mflag.p, midx.p, moff_r.p, c_off.p, c_list.p, c_base.p, nst.p, R,
-                                                       out->r_multi.p, out->m_off.p, out->m_locus.p, out->m_base.p);
+    SGPU_LAUNCH(ctx, (multi_copy_kernel<<<blocks_for(R + 1), TB, 0, st>>>(mflag.p, midx.p, moff_r.p, c_off.p, c_list.p, c_base.p, nst.p, R,
+                                                       out->r_multi.p, out->m_off.p, out->m_locus.p, out->m_base.p)));
     SGPU_CUDA(ctx, cudaGetLastError());
     SGPU_CUDA(ctx, cudaStreamSynchronize(st)); // temporaries are released by the destructors below
     return SGPU_OK;

@@ -115,8 +115,8 @@ int sgpu_scatter_pairs(sgpu_ctx *ctx, const sgpu_pileup *p, const LinkResult &lr
     SGPU_CUDA(ctx, d_np.alloc(1, st));
     SGPU_CUDA(ctx, cudaMemsetAsync(d_np.p, 0, sizeof(unsigned long long), st));
     const unsigned grid = static_cast<unsigned>(std::min<uint64_t>(p->n_loci, static_cast<uint64_t>(ctx->sm_count) * 16));
-    scatter_pairs_kernel<<<grid, SC_THREADS, 0, st>>>(p->d_row_ptr, lr.code.p, p->n_loci, c->i32 + PLANE_S * c->nn,
-                                                     c->i32 + PLANE_D * c->nn, c->n, sign, only_tail_pairs ? 1 : 0, d_np.p);
+    SGPU_LAUNCH(ctx, (scatter_pairs_kernel<<<grid, SC_THREADS, 0, st>>>(p->d_row_ptr, lr.code.p, p->n_loci, c->i32 + PLANE_S * c->nn,
+                                                     c->i32 + PLANE_D * c->nn, c->n, sign, only_tail_pairs ? 1 : 0, d_np.p)));
     SGPU_CUDA(ctx, cudaGetLastError());
     if (n_pairs) {
         SGPU_CUDA(ctx, cudaMemcpyAsync(&ctx->h_scratch[0], d_np.p, sizeof(uint64_t), cudaMemcpyDeviceToHost, st));

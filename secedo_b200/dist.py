@@ -1,0 +1,80 @@
+"""Multi-GPU plumbing: one process per GPU (torch.distributed, NCCL over NVLink/NVSwitch).
+
+The path shards by chromosome (independent locus ranges: the reference resets all read state at
+every chromosome boundary, similarity_matrix.cpp:407-408, so no halo is needed). Each rank filters
+and accumulates its chromosomes into its own integer count planes; the planes are summed with ONE
+reduction per buffer (int32 planes, and — only if a read pair overlapped at >= 4 loci — the fp64
+spill plane), and rank ``dst`` runs the log-likelihood epilogue. Integer sums are order independent,
+so the N-GPU count matrices equal the 1-GPU ones bit for bit.
+
+Everything here is backend agnostic (the CPU tests run it with gloo and world_size 2); only
+:func:`counts_tensors` touches device pointers.
+"""
+from __future__ import annotations
+
+from typing import List, Optional, Sequence
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+
+def partition_chromosomes(weights: Sequence[float], world_size: int) -> List[List[int]]:
+    """Longest-processing-time assignment of chromosomes to ranks, balanced by ``weights`` (loci, or
+    sum of squared coverage for the scatter path). Deterministic; every rank computes the same."""
+    order = sorted(range(len(weights)), key=lambda i: (-weights[i], i))
+    loads = [0.0] * world_size
+    parts: List[List[int]] = [[] for _ in range(world_size)]
+    for i in order:
+        r = min(range(world_size), key=lambda k: (loads[k], k))
+        parts[r].append(i)
+        loads[r] += weights[i]
+    return [sorted(p) for p in parts]
+
+
+def agree_layout(planes_used: int, has_spill: bool, device=None, group=None) -> tuple:
+    """Ranks may have seen different overlap classes; the reduction needs identical buffers."""
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+        return planes_used, has_spill
+    t = torch.tensor([planes_used, int(has_spill)], dtype=torch.int32, device=device)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX, group=group)
+    return int(t[0]), bool(t[1])
+
+
+def reduce_buffers(tensors: Sequence[torch.Tensor], dst: int = 0, group=None) -> None:
+    """Element-wise SUM of every tensor onto rank ``dst`` (one collective per buffer)."""
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+        return
+    for t in tensors:
+        if t.numel():
+            dist.reduce(t, dst=dst, op=dist.ReduceOp.SUM, group=group)
+
+
+class _CudaArray:
+    """Minimal __cuda_array_interface__ carrier so torch can alias a raw device pointer."""
+
+    def __init__(self, ptr: int, n: int, typestr: str):
+        self.__cuda_array_interface__ = {"shape": (n,), "typestr": typestr, "data": (ptr, False), "version": 2}
+
+
+def tensor_from_ptr(ptr: int, n: int, dtype: torch.dtype, device: torch.device) -> torch.Tensor:
+    typestr = {torch.int32: "<i4", torch.float64: "<f8", torch.int64: "<i8"}[dtype]
+    if n == 0 or not ptr:
+        return torch.empty(0, dtype=dtype, device=device)
+    return torch.as_tensor(_CudaArray(ptr, n, typestr), device=device)
+
+
+def counts_tensors(counts, device: torch.device) -> List[torch.Tensor]:
+    """Torch views (no copy) of the device buffers of a :class:`secedo_b200.api.Counts`."""
+    i32, n_i32, f64, n_f64, hist, n_hist = counts.buffers()
+    return [tensor_from_ptr(i32, n_i32, torch.int32, device), tensor_from_ptr(f64, n_f64, torch.float64, device),
+            tensor_from_ptr(hist, n_hist, torch.int64, device)]
+
+
+def reduce_counts(counts, device: torch.device, dst: int = 0, group=None) -> None:
+    """Agree on the buffer layout, then sum the count planes of all ranks onto ``dst``."""
+    i32, n_i32, f64, n_f64, hist, n_hist = counts.buffers()
+    nn = counts.num_cells * counts.num_cells
+    planes, spill = agree_layout(n_i32 // nn if nn else 2, n_f64 > 0, device, group)
+    counts.set_layout(planes, spill)
+    reduce_buffers(counts_tensors(counts, device), dst, group)

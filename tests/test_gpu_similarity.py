@@ -164,3 +164,32 @@ def test_linearity_and_idempotence(gpu_ctx):
         assert np.array_equal(x, y)
     M = whole.finalize(1000, 0.01, 0.5, 0.01, "ADD_MIN")
     assert np.array_equal(M, M.T) and not np.diag(M).any() and M.min() == 0.0
+
+
+@pytest.mark.parametrize("path", PATHS)
+def test_device_generated_pileup(gpu_ctx, path):
+    """the bench input generator (csrc/synth.cu): download a generated pileup and replay it through the
+    oracle — validates the generator (increasing positions, fragment spans < L, mate duplicates,
+    two-locus fragments) and the whole path on exactly the kind of data bench.py times"""
+    dev = gpu_ctx.synth_pileup(700, 0.4, 3, 500, n_clones=2, theta=0.001, p_multi=0.08, p_mate=0.05, seed=9)
+    p = dev.download()
+    assert p.n_chr == 3 and p.n_loci == 1500
+    ident = np.arange(700, dtype=np.uint32)
+    kl, ke, _, cov64 = po.filter_flags(p, ident, 0.001)
+    fdev, cov = api.Filter(0.001, 4, gpu_ctx).filter_device(dev, ident)
+    f = fdev.download()
+    assert f == p.select(kl, ke) and cov == cov64
+    assert 200 < f.n_loci < 1300
+    st, o = check_counts(gpu_ctx, f, 700, 1000, ident, 0.01, 0.15, 0.001, 8, path)
+    assert st["n_multi_reads"] > 0 and st["n_dropped_entries"] > 0 and st["n_pairs_multi"] > 0
+
+
+def test_auto_path_and_stats(gpu_ctx):
+    dev = gpu_ctx.synth_pileup(1024, 0.5, 1, 400, theta=0.001, p_multi=0.01, seed=4)
+    ident = np.arange(1024, dtype=np.uint32)
+    fdev, _ = api.Filter(0.001, 4, gpu_ctx).filter_device(dev, ident)
+    c = api.Counts(gpu_ctx, 1024)
+    n0 = gpu_ctx.launch_count()
+    st = c.accumulate(fdev, 1000, ident, 0.01, 0.15, 0.001, 8, "auto")
+    assert st["path_used"] == "gemm" and st["gemm_launches"] >= 1 and st["ms_gemm"] > 0
+    assert gpu_ctx.launch_count() > n0
