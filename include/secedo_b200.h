@@ -5,7 +5,7 @@
  *   Filter::filter(...)            util/is_significant.hpp:68-72   (body util/is_significant.cpp:149-193)
  *   computeSimilarityMatrix(...)   similarity_matrix.hpp:51-60     (body similarity_matrix.cpp:295-433)
  * called from divide_cluster (spectral_clustering.cpp:336-356). The entry points below are what a
- * host-side shim defining those two symbols binds (secedo_b200/host/*.cpp): plain
+ * host-side shim defining those two symbols binds (secedo_b200/host/secedo_b200_shim.cpp): plain
  * pointers and sizes, no C++ or torch types. One context drives ONE GPU; multi-GPU runs use one
  * process (and one context) per GPU and sum the count matrices between sgpu_counts_accumulate and
  * sgpu_similarity_finalize with a single NCCL reduction (secedo_b200/dist.py).

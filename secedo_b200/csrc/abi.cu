@@ -139,11 +139,11 @@ int sgpu_pileup_upload(sgpu_ctx *ctx, uint32_t n_chr, const uint64_t *chr_ptr, c
     p->h_chr_ptr = new uint64_t[n_chr + 1];
     std::memcpy(p->h_chr_ptr, chr_ptr, (n_chr + 1) * sizeof(uint64_t));
     const uint64_t P = p->n_loci, E = p->n_entries;
-    SGPU_CUDA(ctx, cudaMalloc(&p->d_chr_ptr, (n_chr + 1) * sizeof(uint64_t)));
-    SGPU_CUDA(ctx, cudaMalloc(&p->d_row_ptr, (P + 1) * sizeof(uint64_t)));
-    SGPU_CUDA(ctx, cudaMalloc(&p->d_position, (P ? P : 1) * sizeof(uint32_t)));
-    SGPU_CUDA(ctx, cudaMalloc(&p->d_read_id, (E ? E : 1) * sizeof(uint32_t)));
-    SGPU_CUDA(ctx, cudaMalloc(&p->d_gid_base, (E ? E : 1) * sizeof(uint16_t)));
+    SGPU_CUDA(ctx, cudaMallocAsync(reinterpret_cast<void **>(&p->d_chr_ptr), (n_chr + 1) * sizeof(uint64_t), ctx->stream));
+    SGPU_CUDA(ctx, cudaMallocAsync(reinterpret_cast<void **>(&p->d_row_ptr), (P + 1) * sizeof(uint64_t), ctx->stream));
+    SGPU_CUDA(ctx, cudaMallocAsync(reinterpret_cast<void **>(&p->d_position), (P ? P : 1) * sizeof(uint32_t), ctx->stream));
+    SGPU_CUDA(ctx, cudaMallocAsync(reinterpret_cast<void **>(&p->d_read_id), (E ? E : 1) * sizeof(uint32_t), ctx->stream));
+    SGPU_CUDA(ctx, cudaMallocAsync(reinterpret_cast<void **>(&p->d_gid_base), (E ? E : 1) * sizeof(uint16_t), ctx->stream));
     SGPU_CUDA(ctx, cudaMemcpyAsync(p->d_chr_ptr, chr_ptr, (n_chr + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, st));
     if (P) {
         SGPU_CUDA(ctx, cudaMemcpyAsync(p->d_row_ptr, row_ptr, (P + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, st));
@@ -169,7 +169,7 @@ int sgpu_pileup_wrap_device(sgpu_ctx *ctx, uint32_t n_chr, const uint64_t *host_
     p->n_loci = host_chr_ptr[n_chr];
     p->h_chr_ptr = new uint64_t[n_chr + 1];
     std::memcpy(p->h_chr_ptr, host_chr_ptr, (n_chr + 1) * sizeof(uint64_t));
-    SGPU_CUDA(ctx, cudaMalloc(&p->d_chr_ptr, (n_chr + 1) * sizeof(uint64_t)));
+    SGPU_CUDA(ctx, cudaMallocAsync(reinterpret_cast<void **>(&p->d_chr_ptr), (n_chr + 1) * sizeof(uint64_t), ctx->stream));
     SGPU_CUDA(ctx, cudaMemcpyAsync(p->d_chr_ptr, host_chr_ptr, (n_chr + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, ctx->stream));
     p->d_row_ptr = const_cast<uint64_t *>(dev_row_ptr);
     p->d_position = const_cast<uint32_t *>(dev_position);
@@ -231,16 +231,16 @@ void sgpu_pileup_free(sgpu_ctx *ctx, sgpu_pileup *p) {
     if (!p) {
         return;
     }
+    cudaStream_t st = ctx ? ctx->stream : nullptr;
     if (ctx) {
         cudaSetDevice(ctx->device);
-        cudaStreamSynchronize(ctx->stream);
     }
-    cudaFree(p->d_chr_ptr);
+    cudaFreeAsync(p->d_chr_ptr, st); // stream ordered: safe after everything already queued on st
     if (p->owns) {
-        cudaFree(p->d_row_ptr);
-        cudaFree(p->d_position);
-        cudaFree(p->d_read_id);
-        cudaFree(p->d_gid_base);
+        cudaFreeAsync(p->d_row_ptr, st);
+        cudaFreeAsync(p->d_position, st);
+        cudaFreeAsync(p->d_read_id, st);
+        cudaFreeAsync(p->d_gid_base, st);
     }
     delete[] p->h_chr_ptr;
     delete p;
@@ -340,10 +340,7 @@ int sgpu_counts_accumulate(sgpu_ctx *ctx, sgpu_counts *c, const sgpu_pileup *fil
         if (path == SGPU_PATH_SCATTER) {
             SGPU_TRY(sgpu_scatter_pairs(ctx, filtered, lr, c, +1, false, &s.n_pairs_first));
         } else {
-            SGPU_TRY(sgpu_gemm_counts(ctx, filtered, lr, c, &s.n_pairs_first));
-            if (lr.n_tail) { // remove the tail x tail pairs the reference never compares
-                SGPU_TRY(sgpu_scatter_pairs(ctx, filtered, lr, c, -1, true, nullptr));
-            }
+            SGPU_TRY(sgpu_gemm_counts(ctx, filtered, lr, c, &s.n_pairs_first)); // incl. the tail x tail correction
         }
         s.ms_first_order = t.stop();
         s.ms_stage = ctx->ms_stage;

@@ -144,6 +144,8 @@ struct LinkResult {
     DevBuf<uint32_t> m_locus;   // stored loci, ascending
     DevBuf<uint8_t> m_base;     // stored bases
     uint64_t n_reads = 0, n_multi = 0, n_dropped = 0, n_tail = 0, n_multi_entries = 0;
+    DevBuf<uint32_t> tail_loci; // loci that can hold tail reads (from the cutoff locus to the chromosome end)
+    uint64_t n_tail_loci = 0;
 };
 
 // ------------------------------------------------------------------------------------------------

@@ -316,11 +316,11 @@ int sgpu_filter_impl(sgpu_ctx *ctx, const sgpu_pileup *in, const uint32_t *h_id_
     out->n_entries = Ek;
     out->owns = true;
     out->h_chr_ptr = new uint64_t[in->n_chr + 1];
-    SGPU_CUDA(ctx, cudaMalloc(&out->d_chr_ptr, (in->n_chr + 1) * sizeof(uint64_t)));
-    SGPU_CUDA(ctx, cudaMalloc(&out->d_row_ptr, (Lk + 1) * sizeof(uint64_t)));
-    SGPU_CUDA(ctx, cudaMalloc(&out->d_position, (Lk ? Lk : 1) * sizeof(uint32_t)));
-    SGPU_CUDA(ctx, cudaMalloc(&out->d_read_id, (Ek ? Ek : 1) * sizeof(uint32_t)));
-    SGPU_CUDA(ctx, cudaMalloc(&out->d_gid_base, (Ek ? Ek : 1) * sizeof(uint16_t)));
+    SGPU_CUDA(ctx, cudaMallocAsync(reinterpret_cast<void **>(&out->d_chr_ptr), (in->n_chr + 1) * sizeof(uint64_t), st));
+    SGPU_CUDA(ctx, cudaMallocAsync(reinterpret_cast<void **>(&out->d_row_ptr), (Lk + 1) * sizeof(uint64_t), st));
+    SGPU_CUDA(ctx, cudaMallocAsync(reinterpret_cast<void **>(&out->d_position), (Lk ? Lk : 1) * sizeof(uint32_t), st));
+    SGPU_CUDA(ctx, cudaMallocAsync(reinterpret_cast<void **>(&out->d_read_id), (Ek ? Ek : 1) * sizeof(uint32_t), st));
+    SGPU_CUDA(ctx, cudaMallocAsync(reinterpret_cast<void **>(&out->d_gid_base), (Ek ? Ek : 1) * sizeof(uint16_t), st));
     if (P) {
         SGPU_LAUNCH(ctx, (filter_compact_kernel<<<grid, FILTER_THREADS, smem, st>>>(in->d_row_ptr, in->d_position, in->d_read_id, in->d_gid_base,
                                                                  P, d_mask.p, n_groups, d_keep.p, d_new_locus.p, d_new_row.p,

@@ -62,6 +62,26 @@ __global__ void __launch_bounds__(256) stage_count_kernel(const uint32_t *__rest
     }
 }
 
+// tail correction panel: column b of the panel holds ONLY the tail reads of locus tail_loci[b]
+__global__ void __launch_bounds__(256) stage_tail_kernel(const uint64_t *__restrict__ row_ptr,
+                                                         const uint32_t *__restrict__ code,
+                                                         const uint32_t *__restrict__ tail_loci, uint32_t n_pad,
+                                                         uint32_t *__restrict__ cnt, int *__restrict__ err) {
+    const uint32_t l = tail_loci[blockIdx.x];
+    const uint64_t e0 = row_ptr[l], e1 = row_ptr[l + 1];
+    for (uint64_t e = e0 + threadIdx.x; e < e1; e += 256) {
+        const uint32_t c = code[e];
+        if (c == CODE_DROPPED || !code_tail(c)) {
+            continue;
+        }
+        const uint32_t sh = 8u * code_base(c);
+        const uint32_t old = atomicAdd(&cnt[static_cast<uint64_t>(blockIdx.x) * n_pad + code_cell(c)], 1u << sh);
+        if (((old >> sh) & 0xFFu) >= 127u) {
+            atomicExch(err, SGPU_E_COUNT_RANGE);
+        }
+    }
+}
+
 // one block: 32 loci (one k-block) x 64 cells
 __global__ void __launch_bounds__(256) transform_kernel(const uint32_t *__restrict__ cnt, uint32_t n_pad,
                                                         uint32_t n_loci_panel /* valid loci */,
@@ -206,7 +226,7 @@ struct WorkItem {
 __global__ void __launch_bounds__(GEMM_THREADS, 1) syrk_kernel(const __grid_constant__ CUtensorMap map_u,
                                                                const WorkItem *__restrict__ work, uint32_t n_work,
                                                                int32_t *__restrict__ S, int32_t *__restrict__ D,
-                                                               uint32_t n_cells) {
+                                                               uint32_t n_cells, int sign) {
     extern __shared__ uint8_t smem_raw[];
     // 128B swizzle needs 1024-byte aligned tiles
     uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
@@ -313,10 +333,10 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) syrk_kernel(const __grid_cons
                         const int32_t dv = tv - sv;
                         if (col > row && col < n_cells) {
                             if (sv) {
-                                atomicAdd(Srow + col, sv);
+                                atomicAdd(Srow + col, sign * sv);
                             }
                             if (dv) {
-                                atomicAdd(Drow + col, dv);
+                                atomicAdd(Drow + col, sign * dv);
                             }
                         }
                     }
@@ -406,24 +426,13 @@ int sgpu_gemm_counts(sgpu_ctx *ctx, const sgpu_pileup *p, const LinkResult &lr, 
         cudaEventRecord(e, st);
         evs.push_back(e);
     };
-    for (uint64_t l0 = 0; l0 < P; l0 += panel) {
-        const uint64_t l1 = std::min<uint64_t>(P, l0 + panel);
-        const uint64_t nl = l1 - l0;
+    const uint32_t sms = static_cast<uint32_t>(ctx->sm_count);
+    // transform + GEMM of the nl loci currently staged in cnt; sign -1 subtracts
+    auto gemm_panel = [&](uint64_t nl, int sign) -> int {
         const uint32_t kbs = static_cast<uint32_t>((nl + LOCI_PER_KB - 1) / LOCI_PER_KB);
-        SGPU_CUDA(ctx, cudaMemcpyAsync(&ctx->h_scratch[0], p->d_row_ptr + l0, sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
-        SGPU_CUDA(ctx, cudaMemcpyAsync(&ctx->h_scratch[1], p->d_row_ptr + l1, sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
-        SGPU_CUDA(ctx, cudaStreamSynchronize(st));
-        const uint64_t e0 = ctx->h_scratch[0], e1 = ctx->h_scratch[1];
-        mark(); // [3k] staging begins
-        SGPU_CUDA(ctx, cudaMemsetAsync(cnt.p, 0, nl * n_pad * sizeof(uint32_t), st));
-        if (e1 > e0) {
-            SGPU_LAUNCH(ctx, (stage_count_kernel<<<static_cast<unsigned>(ceil_div_u64(e1 - e0, 256)), 256, 0, st>>>(lr.code.p, lr.eloc.p, e0, e1,
-                                                                                               static_cast<uint32_t>(l0), n_pad, cnt.p, d_err.p)));
-        }
         SGPU_LAUNCH(ctx, (transform_kernel<<<dim3(kbs, n_pad / 64), 256, 0, st>>>(cnt.p, n_pad, static_cast<uint32_t>(nl), row_bytes, U.p, d_err.p)));
         // work list: split K so that every SM has work even when there are few tiles
         uint32_t splits = 1;
-        const uint32_t sms = static_cast<uint32_t>(ctx->sm_count);
         if (tiles.size() < 2 * sms) {
             splits = static_cast<uint32_t>(std::min<uint64_t>(kbs, (2 * sms + tiles.size() - 1) / tiles.size()));
         }
@@ -444,10 +453,36 @@ int sgpu_gemm_counts(sgpu_ctx *ctx, const sgpu_pileup *p, const LinkResult &lr, 
         const unsigned grid = static_cast<unsigned>(std::min<uint64_t>(work.size(), sms));
         mark(); // [3k+1] staging done (the host sync above is inside the staging interval), GEMM begins
         SGPU_LAUNCH(ctx, (syrk_kernel<<<grid, GEMM_THREADS, SMEM_BYTES, st>>>(map, d_work.p, static_cast<uint32_t>(work.size()),
-                                                           c->i32 + PLANE_S * c->nn, c->i32 + PLANE_D * c->nn, N)));
+                                                           c->i32 + PLANE_S * c->nn, c->i32 + PLANE_D * c->nn, N, sign)));
         SGPU_CUDA(ctx, cudaGetLastError());
         mark(); // [3k+2] GEMM done
         ++ctx->n_syrk;
+        return SGPU_OK;
+    };
+    for (uint64_t l0 = 0; l0 < P; l0 += panel) {
+        const uint64_t l1 = std::min<uint64_t>(P, l0 + panel);
+        const uint64_t nl = l1 - l0;
+        SGPU_CUDA(ctx, cudaMemcpyAsync(&ctx->h_scratch[0], p->d_row_ptr + l0, sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
+        SGPU_CUDA(ctx, cudaMemcpyAsync(&ctx->h_scratch[1], p->d_row_ptr + l1, sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
+        SGPU_CUDA(ctx, cudaStreamSynchronize(st));
+        const uint64_t e0 = ctx->h_scratch[0], e1 = ctx->h_scratch[1];
+        mark(); // [3k] staging begins
+        SGPU_CUDA(ctx, cudaMemsetAsync(cnt.p, 0, nl * n_pad * sizeof(uint32_t), st));
+        if (e1 > e0) {
+            SGPU_LAUNCH(ctx, (stage_count_kernel<<<static_cast<unsigned>(ceil_div_u64(e1 - e0, 256)), 256, 0, st>>>(lr.code.p, lr.eloc.p, e0, e1,
+                                                                                               static_cast<uint32_t>(l0), n_pad, cnt.p, d_err.p)));
+        }
+        SGPU_TRY(gemm_panel(nl, +1));
+    }
+    // The reference never compares two reads that both lie behind the per-chromosome cutoff K
+    // (SURVEY F2). Those pairs only exist at the few loci behind the cutoff: subtract Z Z^T, Z = counts
+    // of the tail reads alone at those loci, with the same kernel and sign -1.
+    for (uint64_t t0 = 0; t0 < lr.n_tail_loci; t0 += panel) {
+        const uint64_t nl = std::min<uint64_t>(lr.n_tail_loci - t0, panel);
+        mark();
+        SGPU_CUDA(ctx, cudaMemsetAsync(cnt.p, 0, nl * n_pad * sizeof(uint32_t), st));
+        SGPU_LAUNCH(ctx, (stage_tail_kernel<<<static_cast<unsigned>(nl), 256, 0, st>>>(p->d_row_ptr, lr.code.p, lr.tail_loci.p + t0, n_pad, cnt.p, d_err.p)));
+        SGPU_TRY(gemm_panel(nl, -1));
     }
     SGPU_CUDA(ctx, cudaMemcpyAsync(&ctx->h_scratch[2], d_err.p, sizeof(int), cudaMemcpyDeviceToHost, st));
     SGPU_CUDA(ctx, cudaStreamSynchronize(st));

@@ -97,6 +97,123 @@ __global__ void __launch_bounds__(TB) link_insert_kernel(const uint32_t *__restr
     eslot[e] = static_cast<uint32_t>(slot);
 }
 
+// ---- windowed linking ----------------------------------------------------------------------------
+// A fragment spans less than L bp, so all entries of a read lie in the loci within L bp after the
+// locus of its first entry. One CTA per "owner" locus builds a hash table of that locus' read ids in
+// shared memory (value = smallest entry index carrying the id) and streams the entries of the
+// following loci inside the window against it; every entry ends up with efirst[e] = the smallest
+// entry index of its read. No global-memory hash table: reads are 4 B/entry per pass, coalesced.
+constexpr uint32_t ID_EMPTY = 0xFFFFFFFFu;
+constexpr int WIN_THREADS = 512;
+constexpr uint32_t WIN_MAX_SLOTS = 16384; // 128 KB of shared memory
+
+__global__ void __launch_bounds__(TB) max_locus_size_kernel(const uint64_t *__restrict__ row_ptr, uint64_t n_loci,
+                                                            unsigned int *__restrict__ out) {
+    const uint64_t l = static_cast<uint64_t>(blockIdx.x) * TB + threadIdx.x;
+    unsigned int n = 0;
+    if (l < n_loci) {
+        n = static_cast<unsigned int>(min(row_ptr[l + 1] - row_ptr[l], static_cast<uint64_t>(0xFFFFFFFFu)));
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        n = max(n, __shfl_xor_sync(0xffffffffu, n, o));
+    }
+    if ((threadIdx.x & 31) == 0 && n) {
+        atomicMax(out, n);
+    }
+}
+
+__global__ void __launch_bounds__(TB) iota_kernel(uint32_t *__restrict__ a, uint64_t n) {
+    const uint64_t i = static_cast<uint64_t>(blockIdx.x) * TB + threadIdx.x;
+    if (i < n) {
+        a[i] = static_cast<uint32_t>(i);
+    }
+}
+
+__device__ __forceinline__ uint32_t hash32(uint32_t x) {
+    x ^= x >> 16;
+    x *= 0x7feb352du;
+    x ^= x >> 15;
+    x *= 0x846ca68bu;
+    x ^= x >> 16;
+    return x;
+}
+
+__global__ void __launch_bounds__(WIN_THREADS) link_window_kernel(
+        const uint64_t *__restrict__ row_ptr, const uint32_t *__restrict__ position, const uint32_t *__restrict__ read_id,
+        const uint8_t *__restrict__ lchr, const uint64_t *__restrict__ chr_ptr, uint64_t n_loci, uint32_t L,
+        uint32_t slots /* power of two */, uint32_t *__restrict__ efirst) {
+    extern __shared__ uint32_t s_tab[]; // keys[slots], vals[slots]
+    uint32_t *keys = s_tab, *vals = s_tab + slots;
+    const uint32_t mask = slots - 1;
+    for (uint64_t lo = blockIdx.x; lo < n_loci; lo += gridDim.x) {
+        const uint64_t e0 = row_ptr[lo], e1 = row_ptr[lo + 1];
+        const uint64_t chr_end = chr_ptr[lchr[lo] + 1];
+        const uint32_t p0 = position[lo];
+        __syncthreads(); // previous owner's probes are done
+        for (uint32_t i = threadIdx.x; i < slots; i += WIN_THREADS) {
+            keys[i] = ID_EMPTY;
+            vals[i] = 0xFFFFFFFFu;
+        }
+        __syncthreads();
+        // build: id -> smallest entry index at the owner locus
+        for (uint64_t e = e0 + threadIdx.x; e < e1; e += WIN_THREADS) {
+            const uint32_t id = read_id[e];
+            uint32_t s = hash32(id) & mask;
+            for (;;) {
+                const uint32_t prev = atomicCAS(&keys[s], ID_EMPTY, id);
+                if (prev == ID_EMPTY || prev == id) {
+                    break;
+                }
+                s = (s + 1) & mask;
+            }
+            atomicMin(&vals[s], static_cast<uint32_t>(e));
+        }
+        __syncthreads();
+        // the owner's own entries (two entries of one read at one locus: overlapping mates), then the
+        // loci of the window
+        for (uint64_t l = lo; l < chr_end; ++l) {
+            if (l > lo && (position[l] - p0 >= L)) {
+                break;
+            }
+            const uint64_t a0 = row_ptr[l], a1 = row_ptr[l + 1];
+            for (uint64_t e = a0 + threadIdx.x; e < a1; e += WIN_THREADS) {
+                const uint32_t id = read_id[e];
+                uint32_t s = hash32(id) & mask;
+                for (;;) {
+                    const uint32_t k = keys[s];
+                    if (k == id) {
+                        const uint32_t m = vals[s];
+                        if (m < static_cast<uint32_t>(e)) {
+                            atomicMin(&efirst[e], m);
+                        }
+                        break;
+                    }
+                    if (k == ID_EMPTY) {
+                        break;
+                    }
+                    s = (s + 1) & mask;
+                }
+            }
+        }
+    }
+}
+
+// isfirst[e] and the check that first-entry pointers are idempotent (a chain means a read id
+// spanning >= L through intermediate loci)
+__global__ void __launch_bounds__(TB) link_finish_kernel(const uint32_t *__restrict__ efirst, uint64_t n_entries,
+                                                         uint8_t *__restrict__ isfirst, int *__restrict__ err) {
+    const uint64_t e = static_cast<uint64_t>(blockIdx.x) * TB + threadIdx.x;
+    if (e >= n_entries) {
+        return;
+    }
+    const uint32_t f = efirst[e];
+    isfirst[e] = f == static_cast<uint32_t>(e) ? 1 : 0;
+    if (efirst[f] != f) {
+        atomicExch(err, SGPU_E_FRAGMENT_SPAN);
+    }
+}
+
 // efirst[e] (in place over eslot) = first entry of e's read; isfirst[e]
 __global__ void __launch_bounds__(TB) link_first_kernel(uint32_t *__restrict__ eslot_efirst,
                                                         const uint32_t *__restrict__ vals, uint64_t n_entries,
@@ -236,30 +353,60 @@ __global__ void __launch_bounds__(TB) readbase_kernel(const uint64_t *__restrict
     }
 }
 
-// SURVEY Appendix A.4. One thread per chromosome.
-__global__ void cutoff_kernel(const uint64_t *__restrict__ chr_ptr, uint32_t n_chr,
-                              const uint32_t *__restrict__ position, const uint64_t *__restrict__ readbase,
-                              uint32_t L, uint32_t num_threads, uint64_t *__restrict__ Kglob) {
-    const uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
+// SURVEY Appendix A.4. One CTA per chromosome: for a chunk of loci all threads compute
+// u(l) = number of reads whose start + L <= position[l] (a binary search over the positions, reads are
+// created locus by locus), then one thread replays the reference's batching rule over the chunk.
+constexpr int CUT_THREADS = 256;
+constexpr int CUT_CHUNK = 1024;
+__global__ void __launch_bounds__(CUT_THREADS) cutoff_kernel(const uint64_t *__restrict__ chr_ptr, uint32_t n_chr,
+                                                             const uint32_t *__restrict__ position,
+                                                             const uint64_t *__restrict__ readbase, uint32_t L,
+                                                             uint32_t num_threads, uint64_t *__restrict__ Kglob,
+                                                             uint64_t *__restrict__ tail_locus) {
+    __shared__ uint64_t s_u[CUT_CHUNK];
+    __shared__ uint32_t s_j[CUT_CHUNK];
+    const uint32_t c = blockIdx.x;
     if (c >= n_chr) {
         return;
     }
     const uint64_t l0 = chr_ptr[c], l1 = chr_ptr[c + 1];
     const uint64_t rb0 = readbase[l0];
-    uint64_t front = 0;
-    uint64_t j = l0; // first locus whose reads are NOT yet complete at the current position
-    const uint64_t need = 4ull * num_threads; // BATCH_SIZE * num_threads (:354-356)
-    for (uint64_t l = l0; l < l1; ++l) {
-        const uint64_t p = position[l];
-        while (j < l && static_cast<uint64_t>(position[j]) + L <= p) {
-            ++j;
+    const uint64_t need = 4ull * num_threads; // BATCH_SIZE * num_threads (similarity_matrix.cpp:354-356)
+    uint64_t front = 0, jk = l0;              // used by thread 0 only
+    for (uint64_t base = l0; base < l1; base += CUT_CHUNK) {
+        const uint32_t n = static_cast<uint32_t>(min(static_cast<uint64_t>(CUT_CHUNK), l1 - base));
+        for (uint32_t i = threadIdx.x; i < n; i += CUT_THREADS) {
+            const uint64_t l = base + i;
+            const uint64_t p = position[l];
+            // j = first locus in [l0, l] whose reads are NOT complete at p: position[j] + L > p
+            uint64_t lo = l0, hi = l;
+            while (lo < hi) {
+                const uint64_t mid = (lo + hi) >> 1;
+                if (static_cast<uint64_t>(position[mid]) + L > p) {
+                    hi = mid;
+                } else {
+                    lo = mid + 1;
+                }
+            }
+            s_u[i] = readbase[lo] - rb0; // reads with start + L <= p, all created before locus l
+            s_j[i] = static_cast<uint32_t>(lo - l0);
         }
-        const uint64_t u = readbase[j] - rb0; // reads with start + L <= p (all created before locus l)
-        if (u > front && u - front >= need) {
-            front = u;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            for (uint32_t i = 0; i < n; ++i) {
+                const uint64_t u = s_u[i];
+                if (u > front && u - front >= need) {
+                    front = u;
+                    jk = l0 + s_j[i];
+                }
+            }
         }
+        __syncthreads();
     }
-    Kglob[c] = rb0 + front;
+    if (threadIdx.x == 0) {
+        Kglob[c] = rb0 + front;
+        tail_locus[c] = jk; // reads with index >= K are exactly those created at loci >= jk
+    }
 }
 
 __global__ void __launch_bounds__(TB) make_codes_kernel(
@@ -370,7 +517,7 @@ int sgpu_link_reads(sgpu_ctx *ctx, const sgpu_pileup *p, uint32_t num_cells, uin
 
     DevBuf<uint8_t> lchr, isfirst, edrop;
     DevBuf<uint32_t> gmap, efirst, vals;
-    DevBuf<uint64_t> keys, rscan, readbase, Kglob;
+    DevBuf<uint64_t> keys, rscan, readbase, Kglob, tail_locus;
     DevBuf<int> d_err;
     DevBuf<unsigned long long> d_stats;
     SGPU_CUDA(ctx, lchr.alloc(P, st));
@@ -381,6 +528,7 @@ int sgpu_link_reads(sgpu_ctx *ctx, const sgpu_pileup *p, uint32_t num_cells, uin
     SGPU_CUDA(ctx, rscan.alloc(E + 1, st));
     SGPU_CUDA(ctx, readbase.alloc(P + 1, st));
     SGPU_CUDA(ctx, Kglob.alloc(p->n_chr, st));
+    SGPU_CUDA(ctx, tail_locus.alloc(p->n_chr, st));
     SGPU_CUDA(ctx, d_err.alloc(1, st));
     SGPU_CUDA(ctx, d_stats.alloc(2, st));
     SGPU_CUDA(ctx, cudaMemsetAsync(d_err.p, 0, sizeof(int), st));
@@ -391,20 +539,43 @@ int sgpu_link_reads(sgpu_ctx *ctx, const sgpu_pileup *p, uint32_t num_cells, uin
     const unsigned locus_grid = static_cast<unsigned>(std::min<uint64_t>(ceil_div_u64(P, TB / 32), static_cast<uint64_t>(ctx->sm_count) * 32));
     SGPU_LAUNCH(ctx, (locus_fill_kernel<<<locus_grid, TB, 0, st>>>(p->d_row_ptr, p->d_position, p->d_chr_ptr, p->n_chr, P, out->eloc.p, lchr.p, d_err.p)));
 
-    // ---- hash: (chromosome, read id) -> first entry
-    uint64_t cap = 1024;
-    while (cap < 2 * E) {
-        cap <<= 1;
+    // ---- first entry of every read: windowed shared-memory hashing, or (loci too large for shared
+    // memory) a global open-addressing hash (chromosome, read id) -> first entry
+    DevBuf<unsigned int> d_maxn;
+    SGPU_CUDA(ctx, d_maxn.alloc(1, st));
+    SGPU_CUDA(ctx, cudaMemsetAsync(d_maxn.p, 0, sizeof(unsigned int), st));
+    SGPU_LAUNCH(ctx, (max_locus_size_kernel<<<blocks_for(P), TB, 0, st>>>(p->d_row_ptr, P, d_maxn.p)));
+    SGPU_CUDA(ctx, cudaMemcpyAsync(&ctx->h_scratch[0], d_maxn.p, sizeof(unsigned int), cudaMemcpyDeviceToHost, st));
+    SGPU_CUDA(ctx, cudaStreamSynchronize(st));
+    const uint32_t max_n = static_cast<uint32_t>(ctx->h_scratch[0] & 0xFFFFFFFFu);
+    uint32_t slots = 1024;
+    while (slots < max_n + max_n / 2) {
+        slots <<= 1;
     }
-    SGPU_CUDA(ctx, keys.alloc(cap, st));
-    SGPU_CUDA(ctx, vals.alloc(cap, st));
-    SGPU_CUDA(ctx, cudaMemsetAsync(keys.p, 0xFF, cap * sizeof(uint64_t), st));
-    SGPU_CUDA(ctx, cudaMemsetAsync(vals.p, 0xFF, cap * sizeof(uint32_t), st));
-    SGPU_LAUNCH(ctx, (link_insert_kernel<<<blocks_for(E), TB, 0, st>>>(p->d_read_id, out->eloc.p, lchr.p, E, keys.p, vals.p, cap - 1, efirst.p)));
-    SGPU_LAUNCH(ctx, (link_first_kernel<<<blocks_for(E), TB, 0, st>>>(efirst.p, vals.p, E, isfirst.p)));
+    if (slots <= WIN_MAX_SLOTS) {
+        const size_t smem = static_cast<size_t>(slots) * 2 * sizeof(uint32_t);
+        SGPU_CUDA(ctx, cudaFuncSetAttribute(link_window_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+        SGPU_LAUNCH(ctx, (iota_kernel<<<blocks_for(E), TB, 0, st>>>(efirst.p, E)));
+        const unsigned per_sm = static_cast<unsigned>(std::max<size_t>(1, std::min<size_t>(4, (200 * 1024) / smem)));
+        const unsigned wgrid = static_cast<unsigned>(std::min<uint64_t>(P, static_cast<uint64_t>(ctx->sm_count) * per_sm));
+        SGPU_LAUNCH(ctx, (link_window_kernel<<<wgrid, WIN_THREADS, smem, st>>>(p->d_row_ptr, p->d_position, p->d_read_id, lchr.p,
+                                                                              p->d_chr_ptr, P, L, slots, efirst.p)));
+        SGPU_LAUNCH(ctx, (link_finish_kernel<<<blocks_for(E), TB, 0, st>>>(efirst.p, E, isfirst.p, d_err.p)));
+    } else {
+        uint64_t cap = 1024;
+        while (cap < 2 * E) {
+            cap <<= 1;
+        }
+        SGPU_CUDA(ctx, keys.alloc(cap, st));
+        SGPU_CUDA(ctx, vals.alloc(cap, st));
+        SGPU_CUDA(ctx, cudaMemsetAsync(keys.p, 0xFF, cap * sizeof(uint64_t), st));
+        SGPU_CUDA(ctx, cudaMemsetAsync(vals.p, 0xFF, cap * sizeof(uint32_t), st));
+        SGPU_LAUNCH(ctx, (link_insert_kernel<<<blocks_for(E), TB, 0, st>>>(p->d_read_id, out->eloc.p, lchr.p, E, keys.p, vals.p, cap - 1, efirst.p)));
+        SGPU_LAUNCH(ctx, (link_first_kernel<<<blocks_for(E), TB, 0, st>>>(efirst.p, vals.p, E, isfirst.p)));
+        keys.release();
+        vals.release();
+    }
     SGPU_CUDA(ctx, cudaGetLastError());
-    keys.release();
-    vals.release();
     SGPU_TRY(sgpu_scan_u8_u64(ctx, isfirst.p, rscan.p, E));
     SGPU_CUDA(ctx, cudaMemcpyAsync(&ctx->h_scratch[0], rscan.p + E, sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
     SGPU_CUDA(ctx, cudaStreamSynchronize(st));
@@ -446,7 +617,7 @@ int sgpu_link_reads(sgpu_ctx *ctx, const sgpu_pileup *p, uint32_t num_cells, uin
     }
     SGPU_LAUNCH(ctx, (// ---- cutoff K per chromosome
     readbase_kernel<<<blocks_for(P + 1), TB, 0, st>>>(p->d_row_ptr, rscan.p, P, readbase.p)));
-    SGPU_LAUNCH(ctx, (cutoff_kernel<<<(p->n_chr + 31) / 32, 32, 0, st>>>(p->d_chr_ptr, p->n_chr, p->d_position, readbase.p, L, num_threads, Kglob.p)));
+    SGPU_LAUNCH(ctx, (cutoff_kernel<<<p->n_chr, CUT_THREADS, 0, st>>>(p->d_chr_ptr, p->n_chr, p->d_position, readbase.p, L, num_threads, Kglob.p, tail_locus.p)));
     SGPU_LAUNCH(ctx, (// ---- codes
     make_codes_kernel<<<blocks_for(E), TB, 0, st>>>(out->eread.p, efirst.p, out->eloc.p, lchr.p, p->d_gid_base, r_cell.p, cand.p,
                                                    nst.p, edrop.p, Kglob.p, E, out->code.p, d_stats.p)));
@@ -464,7 +635,8 @@ int sgpu_link_reads(sgpu_ctx *ctx, const sgpu_pileup *p, uint32_t num_cells, uin
     SGPU_TRY(sgpu_scan_u8_u64(ctx, mflag.p, midx.p, R));
     SGPU_TRY(sgpu_scan_u32_u64(ctx, mlen.p, moff_r.p, R));
     // scalars to the host: n_multi, total stored, error, stats, K per chromosome, reads per chromosome
-    std::vector<uint64_t> h_K(p->n_chr), h_rb(p->n_chr + 1);
+    std::vector<uint64_t> h_K(p->n_chr), h_rb(p->n_chr + 1), h_tl(p->n_chr);
+    SGPU_CUDA(ctx, cudaMemcpyAsync(h_tl.data(), tail_locus.p, p->n_chr * sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
     SGPU_CUDA(ctx, cudaMemcpyAsync(&ctx->h_scratch[0], midx.p + R, sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
     SGPU_CUDA(ctx, cudaMemcpyAsync(&ctx->h_scratch[1], moff_r.p + R, sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
     SGPU_CUDA(ctx, cudaMemcpyAsync(&ctx->h_scratch[2], d_err.p, sizeof(int), cudaMemcpyDeviceToHost, st));
@@ -490,8 +662,18 @@ int sgpu_link_reads(sgpu_ctx *ctx, const sgpu_pileup *p, uint32_t num_cells, uin
         SGPU_CUDA(ctx, cudaMemcpyAsync(&h_rb[c + 1], readbase.p + p->h_chr_ptr[c + 1], sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
     }
     SGPU_CUDA(ctx, cudaStreamSynchronize(st));
+    std::vector<uint32_t> h_tail_loci;
     for (uint32_t c = 0; c < p->n_chr; ++c) {
         out->n_tail += h_rb[c + 1] - h_K[c];
+        for (uint64_t l = h_tl[c]; l < p->h_chr_ptr[c + 1]; ++l) {
+            h_tail_loci.push_back(static_cast<uint32_t>(l));
+        }
+    }
+    out->n_tail_loci = h_tail_loci.size();
+    SGPU_CUDA(ctx, out->tail_loci.alloc(h_tail_loci.size() ? h_tail_loci.size() : 1, st));
+    if (!h_tail_loci.empty()) {
+        SGPU_CUDA(ctx, cudaMemcpyAsync(out->tail_loci.p, h_tail_loci.data(), h_tail_loci.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
+        SGPU_CUDA(ctx, cudaStreamSynchronize(st));
     }
 
     SGPU_CUDA(ctx, out->r_multi.alloc(R, st));

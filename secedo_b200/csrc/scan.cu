@@ -93,11 +93,21 @@ __global__ void __launch_bounds__(SCAN_THREADS) scan_apply_kernel(const T *__res
     const uint64_t base = static_cast<uint64_t>(blockIdx.x) * SCAN_TILE + static_cast<uint64_t>(threadIdx.x) * SCAN_ITEMS;
     uint64_t v[SCAN_ITEMS];
     uint64_t s = 0;
+    if (sizeof(T) == 1 && SCAN_ITEMS == 8 && base + SCAN_ITEMS <= n && (reinterpret_cast<uintptr_t>(in) & 7) == 0) {
+        // 8 consecutive bytes per thread in one load
+        const uint64_t w = *reinterpret_cast<const uint64_t *>(in + base);
 #pragma unroll
-    for (int k = 0; k < SCAN_ITEMS; ++k) {
-        uint64_t i = base + k;
-        v[k] = i < n ? static_cast<uint64_t>(in[i]) : 0;
-        s += v[k];
+        for (int k = 0; k < SCAN_ITEMS; ++k) {
+            v[k] = (w >> (8 * k)) & 0xFF;
+            s += v[k];
+        }
+    } else {
+#pragma unroll
+        for (int k = 0; k < SCAN_ITEMS; ++k) {
+            uint64_t i = base + k;
+            v[k] = i < n ? static_cast<uint64_t>(in[i]) : 0;
+            s += v[k];
+        }
     }
     uint64_t ex = block_excl_scan(s, &total) + block_sums[blockIdx.x];
 #pragma unroll

@@ -34,11 +34,12 @@ __device__ __forceinline__ void tri_unrank(uint32_t k, uint32_t &i, uint32_t &j)
 __global__ void __launch_bounds__(SC_THREADS) scatter_pairs_kernel(
         const uint64_t *__restrict__ row_ptr, const uint32_t *__restrict__ code, uint64_t n_loci,
         int32_t *__restrict__ S, int32_t *__restrict__ D, uint32_t n_cells, int sign, int only_tail,
-        unsigned long long *__restrict__ n_pairs) {
+        const uint32_t *__restrict__ locus_list /* null: all loci */, unsigned long long *__restrict__ n_pairs) {
     __shared__ uint32_t sA[SC_TILE];
     __shared__ uint32_t sB[SC_TILE];
     unsigned long long local_pairs = 0;
-    for (uint64_t l = blockIdx.x; l < n_loci; l += gridDim.x) {
+    for (uint64_t li = blockIdx.x; li < n_loci; li += gridDim.x) {
+        const uint64_t l = locus_list ? locus_list[li] : li;
         const uint64_t e0 = row_ptr[l];
         const uint64_t n = row_ptr[l + 1] - e0;
         const uint32_t n_tiles = static_cast<uint32_t>((n + SC_TILE - 1) / SC_TILE);
@@ -62,7 +63,7 @@ __global__ void __launch_bounds__(SC_THREADS) scatter_pairs_kernel(
                 }
                 const uint32_t *pB = diag ? sA : sB;
                 const uint32_t total = diag ? nA * (nA - 1) / 2 : nA * nB;
-                for (uint32_t k = threadIdx.x; k < total; k += SC_THREADS) {
+                for (uint32_t k = threadIdx.x + SC_THREADS * blockIdx.y; k < total; k += SC_THREADS * gridDim.y) {
                     uint32_t i, j;
                     if (diag) {
                         tri_unrank(k, i, j);
@@ -114,9 +115,18 @@ int sgpu_scatter_pairs(sgpu_ctx *ctx, const sgpu_pileup *p, const LinkResult &lr
     DevBuf<unsigned long long> d_np;
     SGPU_CUDA(ctx, d_np.alloc(1, st));
     SGPU_CUDA(ctx, cudaMemsetAsync(d_np.p, 0, sizeof(unsigned long long), st));
-    const unsigned grid = static_cast<unsigned>(std::min<uint64_t>(p->n_loci, static_cast<uint64_t>(ctx->sm_count) * 16));
-    SGPU_LAUNCH(ctx, (scatter_pairs_kernel<<<grid, SC_THREADS, 0, st>>>(p->d_row_ptr, lr.code.p, p->n_loci, c->i32 + PLANE_S * c->nn,
-                                                     c->i32 + PLANE_D * c->nn, c->n, sign, only_tail_pairs ? 1 : 0, d_np.p)));
+    // tail x tail pairs only exist at the loci behind the cutoff of each chromosome
+    const uint64_t n_loci = only_tail_pairs ? lr.n_tail_loci : p->n_loci;
+    if (n_loci == 0) {
+        return SGPU_OK;
+    }
+    const unsigned gx = static_cast<unsigned>(std::min<uint64_t>(n_loci, static_cast<uint64_t>(ctx->sm_count) * 16));
+    // few loci: split each locus' pair index space over blockIdx.y so that the whole GPU is busy
+    const unsigned gy = gx >= 4u * ctx->sm_count ? 1u : std::min(64u, (4u * ctx->sm_count + gx - 1) / gx);
+    const dim3 grid(gx, gy);
+    SGPU_LAUNCH(ctx, (scatter_pairs_kernel<<<grid, SC_THREADS, 0, st>>>(p->d_row_ptr, lr.code.p, n_loci, c->i32 + PLANE_S * c->nn,
+                                                     c->i32 + PLANE_D * c->nn, c->n, sign, only_tail_pairs ? 1 : 0,
+                                                     only_tail_pairs ? lr.tail_loci.p : nullptr, d_np.p)));
     SGPU_CUDA(ctx, cudaGetLastError());
     if (n_pairs) {
         SGPU_CUDA(ctx, cudaMemcpyAsync(&ctx->h_scratch[0], d_np.p, sizeof(uint64_t), cudaMemcpyDeviceToHost, st));

@@ -1,0 +1,190 @@
+// Drop-in host shim: defines the reference's own entry points for the hot path on top of the C ABI
+// (include/secedo_b200.h), so that spectral_clustering.cpp / secedo_main.cpp / the reference's tests
+// link unchanged.
+//
+//   Filter::Filter, Filter::is_significant (x2), Filter::filter, Filter::log_fact
+//                                   replaces util/is_significant.cpp:48-193
+//   computeSimilarityMatrix         replaces similarity_matrix.cpp:295-433
+//
+// Build inside SECEDO:  add this file INSTEAD OF util/is_significant.cpp and similarity_matrix.cpp to
+// the `util` / `similarity_matrix` targets, add <repo>/include to the include path and link
+// libsecedo_b200.so. Build stand-alone (tests): -Isecedo_b200/host/compat.
+//
+// Same argument meaning and error behaviour as the reference: an unknown normalization throws
+// std::logic_error("Invalid normalization: ...") (similarity_matrix.cpp:264); every other failure
+// prints the message and exits with status 1 (the reference logs through spdlog and calls
+// std::exit(1)). There is no CPU fallback: without a B200 the first call fails.
+#include "similarity_matrix.hpp"
+#include "util/is_significant.hpp"
+
+#include "secedo_b200.h"
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <stdexcept>
+
+namespace {
+
+sgpu_ctx *context() {
+    static sgpu_ctx *ctx = nullptr;
+    if (!ctx) {
+        const char *dev = std::getenv("SECEDO_B200_DEVICE");
+        const int rc = sgpu_init(dev ? std::atoi(dev) : 0, &ctx);
+        if (rc != SGPU_OK) {
+            std::fprintf(stderr, "secedo_b200: %s\n", sgpu_last_error(ctx));
+            std::exit(1);
+        }
+    }
+    return ctx;
+}
+
+void check(int rc) {
+    if (rc != SGPU_OK) {
+        std::fprintf(stderr, "secedo_b200: error %d: %s\n", rc, sgpu_last_error(context()));
+        std::exit(1);
+    }
+}
+
+// vector<vector<PosData>> -> the five flat CSR arrays of the ABI
+struct Csr {
+    std::vector<uint64_t> chr_ptr, row_ptr;
+    std::vector<uint32_t> position, read_id;
+    std::vector<uint16_t> gid_base;
+
+    explicit Csr(const std::vector<std::vector<PosData>> &pds) {
+        uint64_t n_loci = 0, n_entries = 0;
+        for (const auto &chr : pds) {
+            n_loci += chr.size();
+            for (const auto &pd : chr) {
+                n_entries += pd.read_ids.size();
+            }
+        }
+        chr_ptr.reserve(pds.size() + 1);
+        row_ptr.reserve(n_loci + 1);
+        position.reserve(n_loci);
+        read_id.reserve(n_entries);
+        gid_base.reserve(n_entries);
+        chr_ptr.push_back(0);
+        row_ptr.push_back(0);
+        for (const auto &chr : pds) {
+            for (const auto &pd : chr) {
+                position.push_back(pd.position);
+                read_id.insert(read_id.end(), pd.read_ids.begin(), pd.read_ids.end());
+                gid_base.insert(gid_base.end(), pd.group_ids_bases.begin(), pd.group_ids_bases.end());
+                row_ptr.push_back(read_id.size());
+            }
+            chr_ptr.push_back(position.size());
+        }
+    }
+
+    sgpu_pileup *upload() const {
+        sgpu_pileup *p = nullptr;
+        check(sgpu_pileup_upload(context(), static_cast<uint32_t>(chr_ptr.size() - 1), chr_ptr.data(), row_ptr.data(),
+                                 position.data(), read_id.data(), gid_base.data(), &p));
+        return p;
+    }
+};
+
+int normalization_code(const std::string &normalization) {
+    if (normalization == "ADD_MIN") {
+        return SGPU_NORM_ADD_MIN;
+    }
+    if (normalization == "EXPONENTIATE") {
+        return SGPU_NORM_EXPONENTIATE;
+    }
+    if (normalization == "SCALE_MAX_1") {
+        return SGPU_NORM_SCALE_MAX_1;
+    }
+    throw std::logic_error("Invalid normalization: " + normalization);
+}
+
+} // namespace
+
+// ---- Filter -------------------------------------------------------------------------------------------
+
+Filter::Filter(double theta, uint8_t cell_proportion)
+    : theta(theta),
+      cell_proportion(cell_proportion),
+      log_theta_3(std::log(theta / 3)),
+      log_one_minus_theta(std::log(1 - theta)) {
+    // table used only by log_fact(), which is not on the hot path
+    log_factorial.reserve(171);
+    double f = 1;
+    log_factorial.push_back(std::log(f));
+    for (uint32_t i = 1; i < 171; ++i) {
+        f *= i;
+        log_factorial.push_back(std::log(f));
+    }
+}
+
+double Filter::log_fact(uint32_t n) {
+    return n > 170 ? 0.5 * std::log(2 * M_PI * n) + n * std::log(n / M_E) : log_factorial.at(n);
+}
+
+bool Filter::is_significant(std::array<uint16_t, 4> &base_count) {
+    uint8_t out = 0;
+    check(sgpu_is_significant(context(), base_count.data(), 1, theta, cell_proportion, &out));
+    std::sort(base_count.begin(), base_count.end()); // the reference sorts its argument in place
+    return out != 0;
+}
+
+bool Filter::is_significant(const PosData &pos_data, uint16_t *coverage) {
+    std::array<uint16_t, 4> base_count = { 0, 0, 0, 0 };
+    for (uint32_t i = 0; i < pos_data.size(); ++i) {
+        base_count[pos_data.base(i)]++;
+    }
+    *coverage = base_count[0] + base_count[1] + base_count[2] + base_count[3];
+    return is_significant(base_count);
+}
+
+std::pair<std::vector<std::vector<PosData>>, double> Filter::filter(const std::vector<std::vector<PosData>> &pos_data,
+                                                                    const std::vector<uint32_t> &id_to_pos,
+                                                                    const std::string &marker, uint32_t num_threads) {
+    (void)marker;      // only logged by the reference
+    (void)num_threads; // the reference parallelises over chromosomes with it; the result does not depend on it
+    sgpu_ctx *ctx = context();
+    const Csr csr(pos_data);
+    sgpu_pileup *in = csr.upload(), *kept = nullptr;
+    double avg_coverage = 0;
+    check(sgpu_filter(ctx, in, id_to_pos.data(), static_cast<uint32_t>(id_to_pos.size()), theta, cell_proportion, &kept,
+                      &avg_coverage));
+    sgpu_pileup_free(ctx, in);
+    uint32_t n_chr = 0;
+    uint64_t n_loci = 0, n_entries = 0;
+    check(sgpu_pileup_dims(kept, &n_chr, &n_loci, &n_entries));
+    std::vector<uint64_t> chr_ptr(n_chr + 1), row_ptr(n_loci + 1);
+    std::vector<uint32_t> position(n_loci), read_id(n_entries);
+    std::vector<uint16_t> gid_base(n_entries);
+    check(sgpu_pileup_download(ctx, kept, chr_ptr.data(), row_ptr.data(), position.data(), read_id.data(), gid_base.data()));
+    sgpu_pileup_free(ctx, kept);
+    std::vector<std::vector<PosData>> result(n_chr);
+    for (uint32_t c = 0; c < n_chr; ++c) {
+        result[c].reserve(chr_ptr[c + 1] - chr_ptr[c]);
+        for (uint64_t l = chr_ptr[c]; l < chr_ptr[c + 1]; ++l) {
+            result[c].emplace_back(position[l], std::vector<uint32_t>(read_id.begin() + row_ptr[l], read_id.begin() + row_ptr[l + 1]),
+                                   std::vector<uint16_t>(gid_base.begin() + row_ptr[l], gid_base.begin() + row_ptr[l + 1]));
+        }
+    }
+    return { std::move(result), avg_coverage };
+}
+
+// ---- similarity matrix ------------------------------------------------------------------------------------
+
+Matd computeSimilarityMatrix(const std::vector<std::vector<PosData>> &pos_data, uint32_t num_cells,
+                             uint32_t max_fragment_length, const std::vector<uint32_t> &group_id_to_pos,
+                             double mutation_rate, double homozygous_rate, double seq_error_rate,
+                             const uint32_t num_threads, const std::string &marker, const std::string &normalization) {
+    (void)marker;
+    const int norm = normalization_code(normalization); // throws like the reference, before any work
+    sgpu_ctx *ctx = context();
+    const Csr csr(pos_data);
+    sgpu_pileup *p = csr.upload();
+    Matd result(num_cells, num_cells);
+    check(sgpu_similarity(ctx, p, num_cells, max_fragment_length, group_id_to_pos.data(),
+                          static_cast<uint32_t>(group_id_to_pos.size()), mutation_rate, homozygous_rate, seq_error_rate,
+                          num_threads /* selects the reference's tail cutoff */, norm, SGPU_PATH_AUTO, result.data(), nullptr));
+    sgpu_pileup_free(ctx, p);
+    return result;
+}

@@ -1,0 +1,92 @@
+// Test driver for the C++ drop-in shim: reads a pileup (CSR, binary), rebuilds the reference's
+// std::vector<std::vector<PosData>>, calls Filter::filter and computeSimilarityMatrix exactly like
+// divide_cluster does (spectral_clustering.cpp:336-356) and writes the filtered pileup and the matrix.
+#include "similarity_matrix.hpp"
+#include "util/is_significant.hpp"
+
+#include <cstdio>
+#include <cstdlib>
+#include <stdexcept>
+#include <string>
+
+template <typename T>
+static std::vector<T> read_vec(FILE *f) {
+    uint64_t n = 0;
+    if (fread(&n, sizeof(n), 1, f) != 1) {
+        std::exit(2);
+    }
+    std::vector<T> v(n);
+    if (n && fread(v.data(), sizeof(T), n, f) != n) {
+        std::exit(2);
+    }
+    return v;
+}
+template <typename T>
+static void write_vec(FILE *f, const std::vector<T> &v) {
+    uint64_t n = v.size();
+    fwrite(&n, sizeof(n), 1, f);
+    fwrite(v.data(), sizeof(T), n, f);
+}
+
+int main(int argc, char **argv) {
+    if (argc < 10) {
+        return 2;
+    }
+    FILE *in = fopen(argv[1], "rb");
+    FILE *out = fopen(argv[2], "wb");
+    const uint32_t num_cells = std::atoi(argv[3]), L = std::atoi(argv[4]), threads = std::atoi(argv[5]);
+    const double eps = std::atof(argv[6]), h = std::atof(argv[7]), theta = std::atof(argv[8]);
+    const std::string normalization = argv[9];
+    auto chr_ptr = read_vec<uint64_t>(in);
+    auto row_ptr = read_vec<uint64_t>(in);
+    auto position = read_vec<uint32_t>(in);
+    auto read_id = read_vec<uint32_t>(in);
+    auto gid_base = read_vec<uint16_t>(in);
+    auto id_to_pos = read_vec<uint32_t>(in);
+    std::vector<std::vector<PosData>> pds(chr_ptr.size() - 1);
+    for (size_t c = 0; c + 1 < chr_ptr.size(); ++c) {
+        for (uint64_t l = chr_ptr[c]; l < chr_ptr[c + 1]; ++l) {
+            pds[c].emplace_back(position[l], std::vector<uint32_t>(read_id.begin() + row_ptr[l], read_id.begin() + row_ptr[l + 1]),
+                                std::vector<uint16_t>(gid_base.begin() + row_ptr[l], gid_base.begin() + row_ptr[l + 1]));
+        }
+    }
+    // known answers of tests/test_is_significant.cpp through the scalar entry point
+    Filter f001(0.001);
+    std::array<uint16_t, 4> paradox = { 1, 0, 3, 0 }; // "GGGA"
+    if (f001.is_significant(paradox) || paradox[3] != 3) {
+        return 3;
+    }
+    bool threw = false;
+    try {
+        computeSimilarityMatrix(pds, num_cells, L, id_to_pos, eps, h, theta, threads, "", "NOPE");
+    } catch (const std::logic_error &e) {
+        threw = std::string(e.what()) == "Invalid normalization: NOPE";
+    }
+    if (!threw) {
+        return 4;
+    }
+    Filter filter(theta);
+    auto [filtered, coverage] = filter.filter(pds, id_to_pos, "", threads);
+    Matd m = computeSimilarityMatrix(filtered, num_cells, L, id_to_pos, eps, h, theta, threads, "", normalization);
+    std::vector<uint64_t> f_chr{ 0 }, f_row{ 0 };
+    std::vector<uint32_t> f_pos, f_rid;
+    std::vector<uint16_t> f_gb;
+    for (const auto &chr : filtered) {
+        for (const auto &pd : chr) {
+            f_pos.push_back(pd.position);
+            f_rid.insert(f_rid.end(), pd.read_ids.begin(), pd.read_ids.end());
+            f_gb.insert(f_gb.end(), pd.group_ids_bases.begin(), pd.group_ids_bases.end());
+            f_row.push_back(f_rid.size());
+        }
+        f_chr.push_back(f_pos.size());
+    }
+    write_vec(out, f_chr);
+    write_vec(out, f_row);
+    write_vec(out, f_pos);
+    write_vec(out, f_rid);
+    write_vec(out, f_gb);
+    write_vec(out, std::vector<double>{ coverage });
+    write_vec(out, std::vector<double>(m.data(), m.data() + static_cast<size_t>(num_cells) * num_cells));
+    fclose(out);
+    return 0;
+}

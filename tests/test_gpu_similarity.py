@@ -119,8 +119,18 @@ def test_edge_cases(gpu_ctx):
     # invalid normalization -> the reference throws std::logic_error
     with pytest.raises(ValueError):
         api.compute_similarity_matrix(p, 4, 1000, ident, 0.01, 0.5, 0.01, 1, "", "NOPE", ctx=gpu_ctx)
-    # read id spanning >= L
-    p = Pileup.from_pos_data([[(100, [1, 2], [0 << 2, 1 << 2]), (1600, [1, 3], [0 << 2, 2 << 2])]])
+    # a read id that recurs >= L bp later with nothing in between is a new read (what the reference does
+    # once the first one has been retired; the oracle calls the input undefined): same result as renaming
+    loci = [(100 + 40 * i, [10 + i, 50 + i], [0 << 2, (1 << 2) | 1]) for i in range(30)]
+    far = loci + [(5000, [10, 99], [2 << 2, 3 << 2]), (5100, [98, 97], [2 << 2, 3 << 2])]
+    ren = loci + [(5000, [777, 99], [2 << 2, 3 << 2]), (5100, [98, 97], [2 << 2, 3 << 2])]
+    Ma = api.compute_similarity_matrix(Pileup.from_pos_data([far]), 4, 1000, ident, 0.01, 0.5, 0.01, 1, ctx=gpu_ctx)
+    Mb = api.compute_similarity_matrix(Pileup.from_pos_data([ren]), 4, 1000, ident, 0.01, 0.5, 0.01, 1, ctx=gpu_ctx)
+    assert np.array_equal(Ma, Mb) and Ma.any()
+    assert_matrix_close(Mb, po.similarity(Pileup.from_pos_data([ren]), 4, 1000, ident, 0.01, 0.5, 0.01, 1).M, TOL)
+    # a read id chained over >= L bp through intermediate loci: undefined in the reference -> error
+    p = Pileup.from_pos_data([[(100, [1, 2], [0 << 2, 1 << 2]), (700, [1, 3], [0 << 2, 2 << 2]),
+                               (1300, [1, 4], [0 << 2, 2 << 2])]])
     with pytest.raises(api.SgpuError):
         api.compute_similarity_matrix(p, 4, 1000, ident, 0.01, 0.5, 0.01, 1, ctx=gpu_ctx)
     # cell outside the matrix
@@ -193,3 +203,13 @@ def test_auto_path_and_stats(gpu_ctx):
     st = c.accumulate(fdev, 1000, ident, 0.01, 0.15, 0.001, 8, "auto")
     assert st["path_used"] == "gemm" and st["gemm_launches"] >= 1 and st["ms_gemm"] > 0
     assert gpu_ctx.launch_count() > n0
+
+
+def test_huge_loci_use_global_hash_linking(gpu_ctx):
+    """loci with more entries than the shared-memory window hash holds fall back to the global hash"""
+    cfg = SynthConfig(n_cells=3000, coverage=4.0, n_loci=8, n_chr=1, frac_somatic=1.0, frac_germline=0.0,
+                      p_multi=0.05, p_mate=0.02, seed=51)
+    p = make_pileup(cfg)
+    assert np.diff(p.row_ptr.astype(np.int64)).max() > 11000
+    ident = np.arange(cfg.n_cells, dtype=np.uint32)
+    check_counts(gpu_ctx, p, cfg.n_cells, 1000, ident, 0.01, 0.5, 0.01, 1, "gemm")
