@@ -118,9 +118,14 @@ def run_reference_step(p, threads):
 
 
 def reference_threads():
+    """all host cores the process may use (torchrun exports OMP_NUM_THREADS=1; the reference takes its
+    thread count as an argument, so that variable does not limit it)"""
     from oracle import pyoracle as po
     if po.have_ref():
-        return max(1, min(po.ref_omp_max_threads(), os.cpu_count() or 1))
+        try:
+            return max(1, len(os.sched_getaffinity(0)))
+        except AttributeError:
+            return max(1, os.cpu_count() or 1)
     return 1
 
 
@@ -226,7 +231,13 @@ def main_ours(args):
         st = counts.accumulate(filtered, w["L"], ident, w["eps"], w["h"], w["theta"], w["num_threads"], args.path)
         st["sig_loci"] = filtered.n_loci
         filtered.free()
+        r0, r1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        r0.record(stream)
         sdist.reduce_counts(counts, device, dst=0)
+        r1.record(stream)
+        if world > 1:
+            r1.synchronize()
+            st["ms_reduce"] = r0.elapsed_time(r1)
         if rank == 0:
             counts.finalize(*lik, w["normalization"], out=out_host, to_host=out_host is not None)
         last.update(st)
@@ -235,18 +246,18 @@ def main_ours(args):
     def timed(fn, steps, warmup):
         for _ in range(warmup):
             fn()
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         stop, lines = threading.Event(), []
         th = threading.Thread(target=clocks_sampler, args=(stop, lines, local_rank), daemon=True)
         if rank == 0:
             th.start()
-            time.sleep(0.25)
+            time.sleep(0.25)  # let nvidia-smi come up BEFORE the barrier, so that all ranks start together
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
         launches0 = ctx.launch_count()
         acc = {"ms_gemm": 0.0, "ms_stage": 0.0, "gemm_launches": 0, "ms_link": 0.0, "ms_first_order": 0.0,
-               "ms_multi": 0.0, "ms_epilogue": 0.0, "sig_loci": 0}
+               "ms_multi": 0.0, "ms_epilogue": 0.0, "ms_reduce": 0.0, "sig_loci": 0}
         e0.record(stream)
         for _ in range(steps):
             st = fn()
@@ -339,7 +350,7 @@ def main_ours(args):
             "build_time_s_per_step": ms_dev / args.steps * 1e-3,
             "prefilter_loci_per_s": P * world * args.steps / (ms_dev * 1e-3),
             "phase_ms_per_step_rank0": {k: acc[k] / args.steps for k in ("ms_link", "ms_first_order", "ms_stage", "ms_gemm",
-                                                                         "ms_multi", "ms_epilogue")},
+                                                                         "ms_multi", "ms_epilogue", "ms_reduce")},
             "roofline": roofline, "cpu_baseline": cpu,
             "e2e": {"value": e2e_value, "unit": "loci/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                     "ms_per_step": ms_e2e / e2e_steps, "steps": e2e_steps},
