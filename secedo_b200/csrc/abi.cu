@@ -2,6 +2,8 @@
 #include "common.cuh"
 
 #include <algorithm>
+#include <chrono>
+#include <cstdlib>
 #include <cstring>
 #include <vector>
 
@@ -15,6 +17,63 @@ int sgpu_fail(sgpu_ctx *ctx, int code, const char *fmt, ...) {
         ctx->error = buf;
     }
     return code;
+}
+
+void sgpu_trace_point(sgpu_ctx *ctx, const char *what) {
+    cudaStreamSynchronize(ctx->stream);
+    const double now = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count();
+    fprintf(stderr, "[sgpu trace] %-28s %8.3f ms\n", what, ctx->trace_t0 == 0.0 ? 0.0 : now - ctx->trace_t0);
+    ctx->trace_t0 = now;
+}
+
+// ---- device memory cache -------------------------------------------------------------------------
+cudaError_t sgpu_dev_alloc(sgpu_ctx *ctx, void **p, size_t bytes) {
+    bytes = (std::max<size_t>(bytes, 1) + 255) & ~static_cast<size_t>(255);
+    auto it = ctx->free_blocks.lower_bound(bytes);
+    if (it != ctx->free_blocks.end() && it->first <= bytes + bytes / 4 + (1u << 20)) {
+        *p = it->second;
+        ctx->live_blocks.emplace(it->second, it->first);
+        ctx->cached_bytes -= it->first;
+        ctx->free_blocks.erase(it);
+        return cudaSuccess;
+    }
+    cudaError_t e = cudaMalloc(p, bytes);
+    if (e == cudaErrorMemoryAllocation) { // out of memory: give the cached blocks back and retry
+        cudaGetLastError();
+        sgpu_dev_release_cache(ctx);
+        e = cudaMalloc(p, bytes);
+    }
+    if (e == cudaSuccess) {
+        ctx->live_blocks.emplace(*p, bytes);
+    }
+    return e;
+}
+
+void sgpu_dev_free(sgpu_ctx *ctx, void *p) {
+    if (!p) {
+        return;
+    }
+    if (ctx) {
+        auto it = ctx->live_blocks.find(p);
+        if (it != ctx->live_blocks.end()) {
+            // everything that uses the block is already queued on ctx->stream, and so will be its next user
+            ctx->free_blocks.emplace(it->second, p);
+            ctx->cached_bytes += it->second;
+            ctx->live_blocks.erase(it);
+            return;
+        }
+        cudaStreamSynchronize(ctx->stream);
+    }
+    cudaFree(p);
+}
+
+void sgpu_dev_release_cache(sgpu_ctx *ctx) {
+    cudaStreamSynchronize(ctx->stream);
+    for (auto &b : ctx->free_blocks) {
+        cudaFree(b.second);
+    }
+    ctx->free_blocks.clear();
+    ctx->cached_bytes = 0;
 }
 
 namespace {
@@ -72,6 +131,8 @@ int sgpu_init(int device, sgpu_ctx **out) {
         return SGPU_E_CUDA;
     }
     ctx->device = device;
+    const char *tr = getenv("SECEDO_B200_TRACE");
+    ctx->trace = tr && tr[0] == '1';
     *out = ctx;
     SGPU_CUDA(ctx, cudaSetDevice(device));
     cudaDeviceProp prop;
@@ -85,11 +146,6 @@ int sgpu_init(int device, sgpu_ctx **out) {
     ctx->stream = ctx->own_stream;
     SGPU_CUDA(ctx, cudaMallocHost(&ctx->h_scratch, 64 * sizeof(uint64_t)));
     SGPU_CUDA(ctx, cudaMalloc(&ctx->d_scratch, 64 * sizeof(uint64_t)));
-    // keep freed stream-ordered blocks cached in the pool instead of returning them to the driver
-    cudaMemPool_t pool;
-    SGPU_CUDA(ctx, cudaDeviceGetDefaultMemPool(&pool, device));
-    uint64_t threshold = UINT64_MAX;
-    SGPU_CUDA(ctx, cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &threshold));
     return SGPU_OK;
 }
 
@@ -107,6 +163,13 @@ void sgpu_shutdown(sgpu_ctx *ctx) {
     if (ctx->d_scratch) {
         cudaFree(ctx->d_scratch);
     }
+    if (ctx->tile_cache) {
+        cudaFree(ctx->tile_cache);
+    }
+    sgpu_dev_release_cache(ctx);
+    for (auto &b : ctx->live_blocks) { // objects the caller never freed
+        cudaFree(b.first);
+    }
     delete ctx;
 }
 
@@ -114,6 +177,7 @@ const char *sgpu_last_error(const sgpu_ctx *ctx) { return ctx ? ctx->error.c_str
 
 int sgpu_set_stream(sgpu_ctx *ctx, void *cuda_stream) {
     SGPU_CUDA(ctx, cudaSetDevice(ctx->device));
+    // cached blocks are only safe to reuse in the order of ONE stream: drain the old one first
     SGPU_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     ctx->stream = cuda_stream ? static_cast<cudaStream_t>(cuda_stream) : ctx->own_stream;
     return SGPU_OK;
@@ -139,11 +203,11 @@ int sgpu_pileup_upload(sgpu_ctx *ctx, uint32_t n_chr, const uint64_t *chr_ptr, c
     p->h_chr_ptr = new uint64_t[n_chr + 1];
     std::memcpy(p->h_chr_ptr, chr_ptr, (n_chr + 1) * sizeof(uint64_t));
     const uint64_t P = p->n_loci, E = p->n_entries;
-    SGPU_CUDA(ctx, cudaMallocAsync(reinterpret_cast<void **>(&p->d_chr_ptr), (n_chr + 1) * sizeof(uint64_t), ctx->stream));
-    SGPU_CUDA(ctx, cudaMallocAsync(reinterpret_cast<void **>(&p->d_row_ptr), (P + 1) * sizeof(uint64_t), ctx->stream));
-    SGPU_CUDA(ctx, cudaMallocAsync(reinterpret_cast<void **>(&p->d_position), (P ? P : 1) * sizeof(uint32_t), ctx->stream));
-    SGPU_CUDA(ctx, cudaMallocAsync(reinterpret_cast<void **>(&p->d_read_id), (E ? E : 1) * sizeof(uint32_t), ctx->stream));
-    SGPU_CUDA(ctx, cudaMallocAsync(reinterpret_cast<void **>(&p->d_gid_base), (E ? E : 1) * sizeof(uint16_t), ctx->stream));
+    SGPU_CUDA(ctx, sgpu_dev_alloc(ctx, reinterpret_cast<void **>(&p->d_chr_ptr), (n_chr + 1) * sizeof(uint64_t)));
+    SGPU_CUDA(ctx, sgpu_dev_alloc(ctx, reinterpret_cast<void **>(&p->d_row_ptr), (P + 1) * sizeof(uint64_t)));
+    SGPU_CUDA(ctx, sgpu_dev_alloc(ctx, reinterpret_cast<void **>(&p->d_position), (P ? P : 1) * sizeof(uint32_t)));
+    SGPU_CUDA(ctx, sgpu_dev_alloc(ctx, reinterpret_cast<void **>(&p->d_read_id), (E ? E : 1) * sizeof(uint32_t)));
+    SGPU_CUDA(ctx, sgpu_dev_alloc(ctx, reinterpret_cast<void **>(&p->d_gid_base), (E ? E : 1) * sizeof(uint16_t)));
     SGPU_CUDA(ctx, cudaMemcpyAsync(p->d_chr_ptr, chr_ptr, (n_chr + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, st));
     if (P) {
         SGPU_CUDA(ctx, cudaMemcpyAsync(p->d_row_ptr, row_ptr, (P + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, st));
@@ -169,7 +233,7 @@ int sgpu_pileup_wrap_device(sgpu_ctx *ctx, uint32_t n_chr, const uint64_t *host_
     p->n_loci = host_chr_ptr[n_chr];
     p->h_chr_ptr = new uint64_t[n_chr + 1];
     std::memcpy(p->h_chr_ptr, host_chr_ptr, (n_chr + 1) * sizeof(uint64_t));
-    SGPU_CUDA(ctx, cudaMallocAsync(reinterpret_cast<void **>(&p->d_chr_ptr), (n_chr + 1) * sizeof(uint64_t), ctx->stream));
+    SGPU_CUDA(ctx, sgpu_dev_alloc(ctx, reinterpret_cast<void **>(&p->d_chr_ptr), (n_chr + 1) * sizeof(uint64_t)));
     SGPU_CUDA(ctx, cudaMemcpyAsync(p->d_chr_ptr, host_chr_ptr, (n_chr + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, ctx->stream));
     p->d_row_ptr = const_cast<uint64_t *>(dev_row_ptr);
     p->d_position = const_cast<uint32_t *>(dev_position);
@@ -231,16 +295,15 @@ void sgpu_pileup_free(sgpu_ctx *ctx, sgpu_pileup *p) {
     if (!p) {
         return;
     }
-    cudaStream_t st = ctx ? ctx->stream : nullptr;
     if (ctx) {
         cudaSetDevice(ctx->device);
     }
-    cudaFreeAsync(p->d_chr_ptr, st); // stream ordered: safe after everything already queued on st
+    sgpu_dev_free(ctx, p->d_chr_ptr); // reuse is stream ordered: safe after everything already queued
     if (p->owns) {
-        cudaFreeAsync(p->d_row_ptr, st);
-        cudaFreeAsync(p->d_position, st);
-        cudaFreeAsync(p->d_read_id, st);
-        cudaFreeAsync(p->d_gid_base, st);
+        sgpu_dev_free(ctx, p->d_row_ptr);
+        sgpu_dev_free(ctx, p->d_position);
+        sgpu_dev_free(ctx, p->d_read_id);
+        sgpu_dev_free(ctx, p->d_gid_base);
     }
     delete[] p->h_chr_ptr;
     delete p;
@@ -338,6 +401,7 @@ int sgpu_counts_accumulate(sgpu_ctx *ctx, sgpu_counts *c, const sgpu_pileup *fil
     {
         EventTimer t(ctx->stream);
         if (path == SGPU_PATH_SCATTER) {
+            SGPU_TRY(sgpu_link_dense_codes(ctx, filtered, &lr));
             SGPU_TRY(sgpu_scatter_pairs(ctx, filtered, lr, c, +1, false, &s.n_pairs_first));
         } else {
             SGPU_TRY(sgpu_gemm_counts(ctx, filtered, lr, c, &s.n_pairs_first)); // incl. the tail x tail correction

@@ -6,7 +6,9 @@
 #include <cstdarg>
 #include <cstdint>
 #include <cstdio>
+#include <map>
 #include <string>
+#include <unordered_map>
 
 #include "../../include/secedo_b200.h"
 
@@ -27,7 +29,27 @@ struct sgpu_ctx {
     // recorded on ctx->stream around the launches
     float ms_syrk = 0.f, ms_stage = 0.f;
     uint64_t n_syrk = 0;
+    // gemm.cu: rasterised list of upper-triangle output tiles for tile_cache_cells cells (device memory)
+    void *tile_cache = nullptr;
+    uint32_t tile_cache_n = 0, tile_cache_cells = 0;
+    // Device memory cache (abi.cu): temporaries and pileups are re-created with identical sizes at every
+    // call, and cudaMallocAsync/cudaFreeAsync of GB-sized blocks cost milliseconds each, so freed blocks
+    // are kept and handed out again. Reuse is safe because all work of a context is ordered on ONE stream.
+    std::multimap<size_t, void *> free_blocks;
+    std::unordered_map<void *, size_t> live_blocks;
+    size_t cached_bytes = 0;
+    // SECEDO_B200_TRACE=1: synchronise and print the wall-clock time between trace points (debug aid)
+    bool trace = false;
+    double trace_t0 = 0.0;
 };
+
+void sgpu_trace_point(sgpu_ctx *ctx, const char *what);
+#define SGPU_TRACE(ctx, what)            \
+    do {                                 \
+        if ((ctx)->trace) {              \
+            sgpu_trace_point((ctx), (what)); \
+        }                                \
+    } while (0)
 
 #define SGPU_LAUNCH(ctx, call) \
     do {                       \
@@ -54,28 +76,32 @@ int sgpu_fail(sgpu_ctx *ctx, int code, const char *fmt, ...);
         }                                                                                          \
     } while (0)
 
-// stream-ordered device memory (cudaMallocAsync pool keeps freed blocks cached)
+// device memory from the context's cache (see sgpu_ctx::free_blocks)
+cudaError_t sgpu_dev_alloc(sgpu_ctx *ctx, void **p, size_t bytes);
+void sgpu_dev_free(sgpu_ctx *ctx, void *p);
+void sgpu_dev_release_cache(sgpu_ctx *ctx);
+
 template <typename T>
 struct DevBuf {
     T *p = nullptr;
     size_t n = 0;
-    cudaStream_t s = nullptr;
+    sgpu_ctx *c = nullptr;
     DevBuf() = default;
     DevBuf(const DevBuf &) = delete;
     DevBuf &operator=(const DevBuf &) = delete;
     ~DevBuf() { release(); }
-    cudaError_t alloc(size_t count, cudaStream_t stream) {
+    cudaError_t alloc(size_t count, sgpu_ctx *ctx) {
         release();
-        s = stream;
+        c = ctx;
         n = count;
         if (count == 0) {
             return cudaSuccess;
         }
-        return cudaMallocAsync(reinterpret_cast<void **>(&p), count * sizeof(T), stream);
+        return sgpu_dev_alloc(ctx, reinterpret_cast<void **>(&p), count * sizeof(T));
     }
     void release() {
         if (p) {
-            cudaFreeAsync(p, s);
+            sgpu_dev_free(c, p);
             p = nullptr;
         }
         n = 0;
@@ -102,6 +128,7 @@ struct sgpu_pileup {
     uint32_t *d_read_id = nullptr;
     uint16_t *d_gid_base = nullptr;
     bool owns = true;
+    mutable uint32_t max_row = 0;  // entries of the largest locus (0 = not known yet; cached by reads.cu)
 };
 
 // plane indices inside sgpu_counts::i32
@@ -135,17 +162,30 @@ __host__ __device__ inline bool code_tail(uint32_t c) { return (c >> 1) & 1u; }
 __host__ __device__ inline bool code_multi(uint32_t c) { return c & 1u; }
 
 struct LinkResult {
-    DevBuf<uint32_t> code;      // per entry, see above
-    DevBuf<uint32_t> eread;     // per entry: global read index
-    DevBuf<uint32_t> eloc;      // per entry: locus index
-    // multi-locus reads only (reads that keep >= 2 loci after the mate rule)
-    DevBuf<uint32_t> r_multi;   // per read: index into the multi tables or 0xFFFFFFFF
-    DevBuf<uint64_t> m_off;     // per multi read: offset into m_locus/m_base (n_multi + 1)
-    DevBuf<uint32_t> m_locus;   // stored loci, ascending
-    DevBuf<uint8_t> m_base;     // stored bases
-    uint64_t n_reads = 0, n_multi = 0, n_dropped = 0, n_tail = 0, n_multi_entries = 0;
-    DevBuf<uint32_t> tail_loci; // loci that can hold tail reads (from the cutoff locus to the chromosome end)
+    // Entries that share their read with another entry are "special"; all other entries are the
+    // only entry of their read (cell = own group, created at the own locus, never dropped).
+    DevBuf<uint32_t> sp_bits;   // bitmap over entries: bit e set = special
+    DevBuf<uint64_t> sp_rank;   // per bitmap word: number of special entries before it (dense numbering "sid")
+    DevBuf<uint32_t> sp_entry;  // per sid: entry index (ascending)
+    DevBuf<uint32_t> sp_locus;  // per sid: locus index
+    DevBuf<uint32_t> sp_head;   // per sid: sid of the first entry of the read
+    DevBuf<uint32_t> sp_code;   // per sid: code, see above
+    DevBuf<uint8_t> sp_drop;    // per sid: removed by the mate rule
+    // per read with >= 2 entries, indexed by the sid of its first entry ("head")
+    DevBuf<uint64_t> g_off;     // [n_special + 1] offsets into g_list / g_base (only heads own a range)
+    DevBuf<uint32_t> g_list;    // stored loci, ascending (first g_nst[head] elements of the range)
+    DevBuf<uint8_t> g_base;     // stored bases
+    DevBuf<uint32_t> g_nst;     // per head: number of loci the read keeps after the mate rule
+    uint64_t n_special = 0;
+    // per locus / chromosome
+    DevBuf<uint8_t> lchr;        // chromosome of every locus
+    DevBuf<uint64_t> tail_locus; // per chromosome: reads created at loci >= this one have index >= K
+    DevBuf<uint32_t> tail_loci;  // loci that can hold tail reads (from the cutoff locus to the chromosome end)
     uint64_t n_tail_loci = 0;
+    DevBuf<uint32_t> gmap;       // group_id_to_pos on the device
+    uint32_t n_groups = 0, num_cells = 0;
+    DevBuf<uint32_t> code;       // dense per-entry codes, only built for the pair-scatter path
+    uint64_t n_reads = 0, n_multi = 0, n_dropped = 0, n_tail = 0;
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -165,6 +205,7 @@ int sgpu_is_significant_impl(sgpu_ctx *ctx, const uint16_t *h_counts4, uint64_t 
 int sgpu_link_reads(sgpu_ctx *ctx, const sgpu_pileup *p, uint32_t num_cells, uint32_t L,
                     const uint32_t *h_group_id_to_pos, uint32_t n_groups, uint32_t num_threads,
                     LinkResult *out);
+int sgpu_link_dense_codes(sgpu_ctx *ctx, const sgpu_pileup *p, LinkResult *lr);
 
 // scatter.cu — first-order counts by pair enumeration; only_tail_pairs: enumerate just the pairs of
 // two tail reads (used with sign = -1 to correct the GEMM path)

@@ -263,10 +263,10 @@ int device_log_probs(sgpu_ctx *ctx, double eps, double h, double theta, uint32_t
     make_cache(&hc, eps, h, theta, L);
     DevBuf<CacheTables> dc;
     DevBuf<uint64_t> comb;
-    SGPU_CUDA(ctx, dc.alloc(1, st));
-    SGPU_CUDA(ctx, comb.alloc(TBL * TBL, st));
-    SGPU_CUDA(ctx, ls.alloc(static_cast<size_t>(n) * n, st));
-    SGPU_CUDA(ctx, ld.alloc(static_cast<size_t>(n) * n, st));
+    SGPU_CUDA(ctx, dc.alloc(1, ctx));
+    SGPU_CUDA(ctx, comb.alloc(TBL * TBL, ctx));
+    SGPU_CUDA(ctx, ls.alloc(static_cast<size_t>(n) * n, ctx));
+    SGPU_CUDA(ctx, ld.alloc(static_cast<size_t>(n) * n, ctx));
     SGPU_CUDA(ctx, cudaMemcpyAsync(dc.p, &hc, sizeof(hc), cudaMemcpyHostToDevice, st));
     SGPU_CUDA(ctx, cudaStreamSynchronize(st)); SGPU_LAUNCH(ctx, (// hc lives on this stack frame
     pascal_kernel<<<1, 128, 0, st>>>(comb.p)));
@@ -313,8 +313,8 @@ int sgpu_epilogue(sgpu_ctx *ctx, sgpu_counts *c, uint32_t L, double eps, double 
     // classes needed by the integer planes: all (s,d) with s + d <= 3
     DevBuf<double> d_G, d_F, raw;
     DevBuf<unsigned long long> d_minmax;
-    SGPU_CUDA(ctx, d_G.alloc(SGPU_MAX_CLASS * SGPU_MAX_CLASS, st));
-    SGPU_CUDA(ctx, d_F.alloc(SGPU_MAX_CLASS * SGPU_MAX_CLASS, st));
+    SGPU_CUDA(ctx, d_G.alloc(SGPU_MAX_CLASS * SGPU_MAX_CLASS, ctx));
+    SGPU_CUDA(ctx, d_F.alloc(SGPU_MAX_CLASS * SGPU_MAX_CLASS, ctx));
     SGPU_TRY(sgpu_build_gtable(ctx, eps, h, theta, L, 4, d_G.p, d_F.p));
     std::vector<double> G(SGPU_MAX_CLASS * SGPU_MAX_CLASS), F(SGPU_MAX_CLASS * SGPU_MAX_CLASS);
     SGPU_CUDA(ctx, cudaMemcpyAsync(G.data(), d_G.p, G.size() * sizeof(double), cudaMemcpyDeviceToHost, st));
@@ -347,8 +347,8 @@ int sgpu_epilogue(sgpu_ctx *ctx, sgpu_counts *c, uint32_t L, double eps, double 
             }
         }
     }
-    SGPU_CUDA(ctx, raw.alloc(c->nn, st));
-    SGPU_CUDA(ctx, d_minmax.alloc(2, st));
+    SGPU_CUDA(ctx, raw.alloc(c->nn, ctx));
+    SGPU_CUDA(ctx, d_minmax.alloc(2, ctx));
     const unsigned long long init[2] = { ~0ull, 0ull };
     SGPU_CUDA(ctx, cudaMemcpyAsync(d_minmax.p, init, sizeof(init), cudaMemcpyHostToDevice, st));
     const unsigned grid = static_cast<unsigned>(ceil_div_u64(c->nn, TR_THREADS));

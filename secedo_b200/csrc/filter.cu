@@ -244,8 +244,8 @@ int sgpu_is_significant_impl(sgpu_ctx *ctx, const uint16_t *h_counts4, uint64_t 
     cudaStream_t st = ctx->stream;
     DevBuf<uint16_t> d_in;
     DevBuf<uint8_t> d_out;
-    SGPU_CUDA(ctx, d_in.alloc(4 * n, st));
-    SGPU_CUDA(ctx, d_out.alloc(n, st));
+    SGPU_CUDA(ctx, d_in.alloc(4 * n, ctx));
+    SGPU_CUDA(ctx, d_out.alloc(n, ctx));
     SGPU_CUDA(ctx, cudaMemcpyAsync(d_in.p, h_counts4, 4 * n * sizeof(uint16_t), cudaMemcpyHostToDevice, st));
     SGPU_LAUNCH(ctx, (is_significant_kernel<<<static_cast<unsigned>(ceil_div_u64(n, 256)), 256, 0, st>>>(d_in.p, n, make_params(theta, cell_proportion), d_out.p)));
     SGPU_CUDA(ctx, cudaGetLastError());
@@ -277,12 +277,12 @@ int sgpu_filter_impl(sgpu_ctx *ctx, const sgpu_pileup *in, const uint32_t *h_id_
     DevBuf<uint8_t> d_keep;
     DevBuf<uint64_t> d_new_locus, d_new_row;
     DevBuf<int> d_err;
-    SGPU_CUDA(ctx, d_mask.alloc(h_mask.size(), st));
-    SGPU_CUDA(ctx, d_cnt.alloc(P, st));
-    SGPU_CUDA(ctx, d_keep.alloc(P, st));
-    SGPU_CUDA(ctx, d_new_locus.alloc(P + 1, st));
-    SGPU_CUDA(ctx, d_new_row.alloc(P + 1, st));
-    SGPU_CUDA(ctx, d_err.alloc(1, st));
+    SGPU_CUDA(ctx, d_mask.alloc(h_mask.size(), ctx));
+    SGPU_CUDA(ctx, d_cnt.alloc(P, ctx));
+    SGPU_CUDA(ctx, d_keep.alloc(P, ctx));
+    SGPU_CUDA(ctx, d_new_locus.alloc(P + 1, ctx));
+    SGPU_CUDA(ctx, d_new_row.alloc(P + 1, ctx));
+    SGPU_CUDA(ctx, d_err.alloc(1, ctx));
     SGPU_CUDA(ctx, cudaMemsetAsync(d_err.p, 0, sizeof(int), st));
     SGPU_CUDA(ctx, cudaMemcpyAsync(d_mask.p, h_mask.data(), smem, cudaMemcpyHostToDevice, st));
 
@@ -316,11 +316,11 @@ int sgpu_filter_impl(sgpu_ctx *ctx, const sgpu_pileup *in, const uint32_t *h_id_
     out->n_entries = Ek;
     out->owns = true;
     out->h_chr_ptr = new uint64_t[in->n_chr + 1];
-    SGPU_CUDA(ctx, cudaMallocAsync(reinterpret_cast<void **>(&out->d_chr_ptr), (in->n_chr + 1) * sizeof(uint64_t), st));
-    SGPU_CUDA(ctx, cudaMallocAsync(reinterpret_cast<void **>(&out->d_row_ptr), (Lk + 1) * sizeof(uint64_t), st));
-    SGPU_CUDA(ctx, cudaMallocAsync(reinterpret_cast<void **>(&out->d_position), (Lk ? Lk : 1) * sizeof(uint32_t), st));
-    SGPU_CUDA(ctx, cudaMallocAsync(reinterpret_cast<void **>(&out->d_read_id), (Ek ? Ek : 1) * sizeof(uint32_t), st));
-    SGPU_CUDA(ctx, cudaMallocAsync(reinterpret_cast<void **>(&out->d_gid_base), (Ek ? Ek : 1) * sizeof(uint16_t), st));
+    SGPU_CUDA(ctx, sgpu_dev_alloc(ctx, reinterpret_cast<void **>(&out->d_chr_ptr), (in->n_chr + 1) * sizeof(uint64_t)));
+    SGPU_CUDA(ctx, sgpu_dev_alloc(ctx, reinterpret_cast<void **>(&out->d_row_ptr), (Lk + 1) * sizeof(uint64_t)));
+    SGPU_CUDA(ctx, sgpu_dev_alloc(ctx, reinterpret_cast<void **>(&out->d_position), (Lk ? Lk : 1) * sizeof(uint32_t)));
+    SGPU_CUDA(ctx, sgpu_dev_alloc(ctx, reinterpret_cast<void **>(&out->d_read_id), (Ek ? Ek : 1) * sizeof(uint32_t)));
+    SGPU_CUDA(ctx, sgpu_dev_alloc(ctx, reinterpret_cast<void **>(&out->d_gid_base), (Ek ? Ek : 1) * sizeof(uint16_t)));
     if (P) {
         SGPU_LAUNCH(ctx, (filter_compact_kernel<<<grid, FILTER_THREADS, smem, st>>>(in->d_row_ptr, in->d_position, in->d_read_id, in->d_gid_base,
                                                                  P, d_mask.p, n_groups, d_keep.p, d_new_locus.p, d_new_row.p,

@@ -42,94 +42,155 @@ constexpr uint32_t TMEM_COLS = 512;
 
 // ------------------------------------------------------------------------------------------------
 // staging
+//
+// The panel buffer holds one 128-byte row per (cell, k-block of 32 loci). While the counts are being
+// accumulated, word j of the row is locus j's four base counts (4 x u8); transform_kernel then turns
+// the row IN PLACE into the K-major operand layout [plane 0..3][32 loci] of Hadamard planes, so the
+// staged counts cost one memset, one pass of atomics and one read + write of the panel.
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) stage_count_kernel(const uint32_t *__restrict__ code,
-                                                          const uint32_t *__restrict__ eloc, uint64_t e_begin,
-                                                          uint64_t e_end, uint32_t l0, uint32_t n_pad,
-                                                          uint32_t *__restrict__ cnt, int *__restrict__ err) {
-    const uint64_t e = e_begin + static_cast<uint64_t>(blockIdx.x) * 256 + threadIdx.x;
-    if (e >= e_end) {
-        return;
-    }
-    const uint32_t c = code[e];
-    if (c == CODE_DROPPED) {
-        return;
-    }
-    const uint32_t sh = 8u * code_base(c);
-    const uint32_t old = atomicAdd(&cnt[static_cast<uint64_t>(eloc[e] - l0) * n_pad + code_cell(c)], 1u << sh);
+__device__ __forceinline__ void add_count(uint32_t *__restrict__ U, uint64_t word, uint32_t base, int *__restrict__ err) {
+    const uint32_t sh = 8u * base;
+    const uint32_t old = atomicAdd(&U[word], 1u << sh);
     if (((old >> sh) & 0xFFu) >= 127u) {
         atomicExch(err, SGPU_E_COUNT_RANGE); // > 127 reads of one cell at one locus: outside int8
     }
 }
 
-// tail correction panel: column b of the panel holds ONLY the tail reads of locus tail_loci[b]
-__global__ void __launch_bounds__(256) stage_tail_kernel(const uint64_t *__restrict__ row_ptr,
-                                                         const uint32_t *__restrict__ code,
-                                                         const uint32_t *__restrict__ tail_loci, uint32_t n_pad,
-                                                         uint32_t *__restrict__ cnt, int *__restrict__ err) {
-    const uint32_t l = tail_loci[blockIdx.x];
-    const uint64_t e0 = row_ptr[l], e1 = row_ptr[l + 1];
-    for (uint64_t e = e0 + threadIdx.x; e < e1; e += 256) {
-        const uint32_t c = code[e];
-        if (c == CODE_DROPPED || !code_tail(c)) {
-            continue;
-        }
-        const uint32_t sh = 8u * code_base(c);
-        const uint32_t old = atomicAdd(&cnt[static_cast<uint64_t>(blockIdx.x) * n_pad + code_cell(c)], 1u << sh);
-        if (((old >> sh) & 0xFFu) >= 127u) {
-            atomicExch(err, SGPU_E_COUNT_RANGE);
+// entries that are the only entry of their read, loci [l0, l1): one block per locus
+__global__ void __launch_bounds__(256) stage_main_kernel(const uint64_t *__restrict__ row_ptr,
+                                                         const uint16_t *__restrict__ gid_base,
+                                                         const uint32_t *__restrict__ sp_bits,
+                                                         const uint32_t *__restrict__ gmap, uint32_t n_groups,
+                                                         uint32_t n_cells, uint32_t l0, uint32_t l1,
+                                                         uint64_t row_words, uint32_t *__restrict__ U,
+                                                         int *__restrict__ err) {
+    for (uint32_t l = l0 + blockIdx.x; l < l1; l += gridDim.x) {
+        const uint64_t e0 = row_ptr[l], e1 = row_ptr[l + 1];
+        const uint64_t col = l - l0; // k-block col / 32, word col % 32: the rows are K-contiguous
+        for (uint64_t e = e0 + threadIdx.x; e < e1; e += 256) {
+            if ((sp_bits[e >> 5] >> (e & 31)) & 1u) {
+                continue; // staged by stage_special_kernel
+            }
+            const uint32_t gb = gid_base[e];
+            const uint32_t gid = gb >> 2;
+            uint32_t cell;
+            if (gid >= n_groups || (cell = gmap[gid]) >= n_cells) {
+                atomicExch(err, SGPU_E_CELL_RANGE);
+                continue;
+            }
+            add_count(U, static_cast<uint64_t>(cell) * row_words + col, gb & 3u, err);
         }
     }
 }
 
-// one block: 32 loci (one k-block) x 64 cells
-__global__ void __launch_bounds__(256) transform_kernel(const uint32_t *__restrict__ cnt, uint32_t n_pad,
-                                                        uint32_t n_loci_panel /* valid loci */,
-                                                        uint64_t row_bytes /* k-blocks * 128 */,
-                                                        int8_t *__restrict__ U, int *__restrict__ err) {
-    __shared__ uint32_t tile[64 * 32]; // [cell][32 words = 4 planes x 8 groups of 4 loci], chunk-swizzled
-    const uint32_t kb = blockIdx.x, cell0 = blockIdx.y * 64;
+// entries of reads with several entries that survived the mate rule
+__global__ void __launch_bounds__(256) stage_special_kernel(const uint32_t *__restrict__ sp_code,
+                                                            const uint32_t *__restrict__ sp_locus, uint64_t n_special,
+                                                            uint32_t l0, uint32_t l1, uint64_t row_words,
+                                                            uint32_t *__restrict__ U, int *__restrict__ err) {
+    const uint64_t s = static_cast<uint64_t>(blockIdx.x) * 256 + threadIdx.x;
+    if (s >= n_special) {
+        return;
+    }
+    const uint32_t c = sp_code[s], l = sp_locus[s];
+    if (c == CODE_DROPPED || l < l0 || l >= l1) {
+        return;
+    }
+    add_count(U, static_cast<uint64_t>(code_cell(c)) * row_words + (l - l0), code_base(c), err);
+}
+
+// tail correction panel: column b of the panel holds ONLY the tail reads of locus tail_loci[b]. A
+// read that is the only entry... of its read was created at its own locus, i.e. behind the cutoff.
+__global__ void __launch_bounds__(256) stage_tail_kernel(const uint64_t *__restrict__ row_ptr,
+                                                         const uint16_t *__restrict__ gid_base,
+                                                         const uint32_t *__restrict__ sp_bits,
+                                                         const uint32_t *__restrict__ gmap, uint32_t n_groups,
+                                                         uint32_t n_cells, const uint32_t *__restrict__ tail_loci,
+                                                         uint64_t row_words, uint32_t *__restrict__ U,
+                                                         int *__restrict__ err) {
+    const uint32_t l = tail_loci[blockIdx.x];
+    const uint64_t e0 = row_ptr[l], e1 = row_ptr[l + 1];
+    for (uint64_t e = e0 + threadIdx.x; e < e1; e += 256) {
+        if ((sp_bits[e >> 5] >> (e & 31)) & 1u) {
+            continue;
+        }
+        const uint32_t gb = gid_base[e];
+        const uint32_t gid = gb >> 2;
+        uint32_t cell;
+        if (gid >= n_groups || (cell = gmap[gid]) >= n_cells) {
+            atomicExch(err, SGPU_E_CELL_RANGE);
+            continue;
+        }
+        add_count(U, static_cast<uint64_t>(cell) * row_words + blockIdx.x, gb & 3u, err);
+    }
+}
+
+__global__ void __launch_bounds__(256) stage_tail_special_kernel(const uint32_t *__restrict__ sp_code,
+                                                                 const uint32_t *__restrict__ sp_locus,
+                                                                 uint64_t n_special, const uint32_t *__restrict__ tail_loci,
+                                                                 uint32_t n_tail /* columns of this panel */,
+                                                                 uint64_t row_words, uint32_t *__restrict__ U,
+                                                                 int *__restrict__ err) {
+    const uint64_t s = static_cast<uint64_t>(blockIdx.x) * 256 + threadIdx.x;
+    if (s >= n_special) {
+        return;
+    }
+    const uint32_t c = sp_code[s], l = sp_locus[s];
+    if (c == CODE_DROPPED || !code_tail(c)) {
+        return;
+    }
+    uint32_t lo = 0, hi = n_tail; // tail_loci is ascending
+    while (lo < hi) {
+        const uint32_t mid = (lo + hi) >> 1;
+        if (tail_loci[mid] < l) {
+            lo = mid + 1;
+        } else {
+            hi = mid;
+        }
+    }
+    if (lo < n_tail && tail_loci[lo] == l) {
+        add_count(U, static_cast<uint64_t>(code_cell(c)) * row_words + lo, code_base(c), err);
+    }
+}
+
+// In-place Hadamard transform of the rows: 8 consecutive lanes own one 128-byte row (one cell, one
+// k-block); each loads 4 loci x 4 base counts (16 B) and, after the whole warp has loaded, stores the
+// four plane words of those loci.
+__global__ void __launch_bounds__(256) transform_kernel(uint32_t *__restrict__ U, uint32_t kbs /* valid k-blocks */,
+                                                        uint64_t row_words, uint64_t n_items /* rows * kbs * 8 */,
+                                                        int *__restrict__ err) {
+    const uint64_t t = static_cast<uint64_t>(blockIdx.x) * 256 + threadIdx.x;
+    if (t >= n_items) {
+        return; // n_items is a multiple of 8 and of the 8-lane groups: whole groups leave together
+    }
+    const uint32_t g = t & 7;
+    const uint64_t rk = t >> 3;
+    const uint64_t row = rk / kbs, kb = rk - row * kbs;
+    uint32_t *r = U + row * row_words + kb * 32;
+    const uint4 v = *reinterpret_cast<const uint4 *>(r + 4 * g);
+    const uint32_t in[4] = { v.x, v.y, v.z, v.w };
+    uint32_t w[4] = { 0, 0, 0, 0 }; // per plane, 4 loci packed
     bool bad = false;
 #pragma unroll
-    for (int it = 0; it < 2; ++it) {
-        const uint32_t item = threadIdx.x + it * 256; // 512 items: cell (0..63) x group (0..7)
-        const uint32_t tx = item & 63, g = item >> 6;
-        uint32_t w[4] = { 0, 0, 0, 0 }; // per plane, 4 loci packed
+    for (int q = 0; q < 4; ++q) {
+        const int c0 = in[q] & 0xFF, c1 = (in[q] >> 8) & 0xFF, c2 = (in[q] >> 16) & 0xFF, c3 = in[q] >> 24;
+        const int u0 = c0 + c1 + c2 + c3;
+        const int u1 = c0 - c1 + c2 - c3;
+        const int u2 = c0 + c1 - c2 - c3;
+        const int u3 = c0 - c1 - c2 + c3;
+        bad |= u0 > 127;
+        w[0] |= static_cast<uint32_t>(u0 & 0xFF) << (8 * q);
+        w[1] |= static_cast<uint32_t>(u1 & 0xFF) << (8 * q);
+        w[2] |= static_cast<uint32_t>(u2 & 0xFF) << (8 * q);
+        w[3] |= static_cast<uint32_t>(u3 & 0xFF) << (8 * q);
+    }
+    __syncwarp(); // every lane of the row has its counts in registers before any plane word is written
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
-            const uint32_t locus = kb * LOCI_PER_KB + g * 4 + q;
-            uint32_t v = 0;
-            if (locus < n_loci_panel) {
-                v = cnt[static_cast<uint64_t>(locus) * n_pad + cell0 + tx];
-            }
-            const int c0 = v & 0xFF, c1 = (v >> 8) & 0xFF, c2 = (v >> 16) & 0xFF, c3 = v >> 24;
-            const int u0 = c0 + c1 + c2 + c3;
-            const int u1 = c0 - c1 + c2 - c3;
-            const int u2 = c0 + c1 - c2 - c3;
-            const int u3 = c0 - c1 - c2 + c3;
-            bad |= u0 > 127;
-            w[0] |= static_cast<uint32_t>(u0 & 0xFF) << (8 * q);
-            w[1] |= static_cast<uint32_t>(u1 & 0xFF) << (8 * q);
-            w[2] |= static_cast<uint32_t>(u2 & 0xFF) << (8 * q);
-            w[3] |= static_cast<uint32_t>(u3 & 0xFF) << (8 * q);
-        }
-#pragma unroll
-        for (int pl = 0; pl < 4; ++pl) {
-            const uint32_t word = pl * 8 + g;
-            tile[tx * 32 + (word ^ ((tx & 7) << 2))] = w[pl];
-        }
+    for (int pl = 0; pl < 4; ++pl) {
+        r[pl * 8 + g] = w[pl];
     }
     if (bad) {
         atomicExch(err, SGPU_E_COUNT_RANGE);
-    }
-    __syncthreads();
-    // 64 rows x 8 chunks of 16 bytes
-#pragma unroll
-    for (int it = 0; it < 2; ++it) {
-        const uint32_t item = threadIdx.x + it * 256;
-        const uint32_t row = item >> 3, ch = item & 7;
-        const uint4 v = *reinterpret_cast<const uint4 *>(&tile[row * 32 + ((ch ^ (row & 7)) << 2)]);
-        *reinterpret_cast<uint4 *>(U + static_cast<uint64_t>(cell0 + row) * row_bytes + static_cast<uint64_t>(kb) * KB_BYTES + ch * 16) = v;
     }
 }
 
@@ -220,13 +281,28 @@ struct WorkItem {
     uint32_t k0, k1;   // k-block range
 };
 
+// work item w = (tile w % n_tiles, K split w / n_tiles)
+struct WorkList {
+    const uint2 *tiles; // (row block, column block), rasterised for L2 reuse
+    uint32_t n_tiles;
+    uint32_t n_work;    // n_tiles * splits
+    uint32_t kbs;       // k-blocks of the panel
+    uint32_t per;       // k-blocks per split
+};
+__device__ __forceinline__ WorkItem work_item(const WorkList &wl, uint32_t w) {
+    const uint32_t split = w / wl.n_tiles;
+    const uint2 t = wl.tiles[w - split * wl.n_tiles];
+    const uint32_t k0 = split * wl.per;
+    return WorkItem{ t.x, t.y, k0, min(wl.kbs, k0 + wl.per) };
+}
+
 // ------------------------------------------------------------------------------------------------
 // the GEMM
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(GEMM_THREADS, 1) syrk_kernel(const __grid_constant__ CUtensorMap map_u,
-                                                               const WorkItem *__restrict__ work, uint32_t n_work,
-                                                               int32_t *__restrict__ S, int32_t *__restrict__ D,
-                                                               uint32_t n_cells, int sign) {
+                                                               const WorkList wl, int32_t *__restrict__ S,
+                                                               int32_t *__restrict__ D, uint32_t n_cells, int sign) {
+    const uint32_t n_work = wl.n_work;
     extern __shared__ uint8_t smem_raw[];
     // 128B swizzle needs 1024-byte aligned tiles
     uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
@@ -262,7 +338,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) syrk_kernel(const __grid_cons
         if (elect_one()) {
             uint32_t stage = 0, phase = 0;
             for (uint32_t w = blockIdx.x; w < n_work; w += gridDim.x) {
-                const WorkItem wi = work[w];
+                const WorkItem wi = work_item(wl, w);
                 for (uint32_t kb = wi.k0; kb < wi.k1; ++kb) {
                     mbar_wait(empty0 + 8 * stage, phase ^ 1);
                     const uint32_t sa = smem_u32(smem + stage * STAGE_BYTES), sb = sa + A_BYTES;
@@ -283,7 +359,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) syrk_kernel(const __grid_cons
         if (elect_one()) {
             uint32_t stage = 0, phase = 0, acc_phase = 0;
             for (uint32_t w = blockIdx.x; w < n_work; w += gridDim.x) {
-                const WorkItem wi = work[w];
+                const WorkItem wi = work_item(wl, w);
                 mbar_wait(tmem_empty, acc_phase ^ 1); // epilogue has drained the accumulators
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 for (uint32_t kb = wi.k0; kb < wi.k1; ++kb) {
@@ -311,7 +387,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) syrk_kernel(const __grid_cons
         const uint32_t lane_base = 32 * (warp & 3);
         uint32_t acc_phase = 0;
         for (uint32_t w = blockIdx.x; w < n_work; w += gridDim.x) {
-            const WorkItem wi = work[w];
+            const WorkItem wi = work_item(wl, w);
             mbar_wait(tmem_full, acc_phase);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             const uint32_t row = wi.rb * BM + lane_base + lane;
@@ -355,6 +431,43 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) syrk_kernel(const __grid_cons
 
 } // namespace
 
+// Upper-triangle output tiles in an order that keeps the tiles in flight (one per SM) inside a block
+// of ~18 row blocks x 8 column blocks, so that a wave touches ~4 400 distinct operand rows instead of
+// ~20 000: bands of 8 column blocks, row-block-major inside a band.
+static int tile_list(sgpu_ctx *ctx, uint32_t N, uint32_t n_pad, const uint2 **d_tiles, uint32_t *n_tiles) {
+    if (ctx->tile_cache && ctx->tile_cache_cells == N) {
+        *d_tiles = static_cast<const uint2 *>(ctx->tile_cache);
+        *n_tiles = ctx->tile_cache_n;
+        return SGPU_OK;
+    }
+    constexpr uint32_t BAND = 8;
+    std::vector<uint2> tiles;
+    const uint32_t n_cb = n_pad / BN, n_rb = n_pad / BM;
+    for (uint32_t band = 0; band < n_cb; band += BAND) {
+        const uint32_t cb_end = std::min(n_cb, band + BAND);
+        for (uint32_t rb = 0; rb < n_rb; ++rb) {
+            for (uint32_t cb = band; cb < cb_end; ++cb) {
+                // the tile intersects the upper triangle: its last column > its first row
+                if (cb * BN + BN - 1 > rb * BM && rb * BM < N && cb * BN < N) {
+                    tiles.push_back(make_uint2(rb, cb));
+                }
+            }
+        }
+    }
+    if (ctx->tile_cache) {
+        SGPU_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        SGPU_CUDA(ctx, cudaFree(ctx->tile_cache));
+        ctx->tile_cache = nullptr;
+    }
+    SGPU_CUDA(ctx, cudaMalloc(&ctx->tile_cache, std::max<size_t>(1, tiles.size()) * sizeof(uint2)));
+    SGPU_CUDA(ctx, cudaMemcpy(ctx->tile_cache, tiles.data(), tiles.size() * sizeof(uint2), cudaMemcpyHostToDevice));
+    ctx->tile_cache_cells = N;
+    ctx->tile_cache_n = static_cast<uint32_t>(tiles.size());
+    *d_tiles = static_cast<const uint2 *>(ctx->tile_cache);
+    *n_tiles = ctx->tile_cache_n;
+    return SGPU_OK;
+}
+
 int sgpu_gemm_counts(sgpu_ctx *ctx, const sgpu_pileup *p, const LinkResult &lr, sgpu_counts *c, uint64_t *n_pairs) {
     cudaStream_t st = ctx->stream;
     if (n_pairs) {
@@ -366,22 +479,21 @@ int sgpu_gemm_counts(sgpu_ctx *ctx, const sgpu_pileup *p, const LinkResult &lr, 
     }
     const uint32_t N = c->n;
     const uint32_t n_pad = (N + BN - 1) / BN * BN;
-    // panel: at most ~2 GB of packed counts and as much of Hadamard planes
+    // panel: at most ~2 GB of staged counts / Hadamard planes
     uint64_t panel = (1ull << 31) / (4ull * n_pad) / LOCI_PER_KB * LOCI_PER_KB;
     panel = std::max<uint64_t>(panel, LOCI_PER_KB);
     panel = std::min<uint64_t>(panel, (P + LOCI_PER_KB - 1) / LOCI_PER_KB * LOCI_PER_KB);
     const uint64_t kbs_max = panel / LOCI_PER_KB;
-    const uint64_t row_bytes = kbs_max * KB_BYTES;
+    const uint64_t row_bytes = kbs_max * KB_BYTES, row_words = row_bytes / 4;
 
-    DevBuf<uint32_t> cnt;
-    DevBuf<int8_t> U;
+    SGPU_TRACE(ctx, "gemm: enter");
+    DevBuf<uint32_t> U;
     DevBuf<int> d_err;
-    DevBuf<WorkItem> d_work;
-    SGPU_CUDA(ctx, cnt.alloc(panel * n_pad, st));
-    SGPU_CUDA(ctx, U.alloc(static_cast<uint64_t>(n_pad) * row_bytes, st));
-    SGPU_CUDA(ctx, d_err.alloc(1, st));
-    SGPU_CUDA(ctx, cudaMemsetAsync(d_err.p, 0, sizeof(int), st));
+    SGPU_CUDA(ctx, U.alloc(static_cast<uint64_t>(n_pad) * row_words, ctx));
+    SGPU_CUDA(ctx, d_err.alloc(2, ctx));
+    SGPU_CUDA(ctx, cudaMemsetAsync(d_err.p, 0, 2 * sizeof(int), st));
 
+    SGPU_TRACE(ctx, "gemm: alloc");
     // tensor map over U: [n_pad rows][row_bytes], box = 128 rows x 128 bytes, 128B swizzle
     CUtensorMap map;
     {
@@ -408,52 +520,45 @@ int sgpu_gemm_counts(sgpu_ctx *ctx, const sgpu_pileup *p, const LinkResult &lr, 
         }
     }
     SGPU_CUDA(ctx, cudaFuncSetAttribute(syrk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+    const uint2 *d_tiles = nullptr;
+    uint32_t n_tiles = 0;
+    SGPU_TRY(tile_list(ctx, N, n_pad, &d_tiles, &n_tiles));
 
-    // output tiles that intersect the upper triangle: last column of the tile > first row of the tile
-    std::vector<std::pair<uint32_t, uint32_t>> tiles;
-    for (uint32_t cb = 0; cb < n_pad / BN; ++cb) {
-        for (uint32_t rb = 0; rb < n_pad / BM; ++rb) {
-            if (cb * BN + BN - 1 > rb * BM && rb * BM < N && cb * BN < N) {
-                tiles.emplace_back(rb, cb);
-            }
-        }
-    }
+    SGPU_TRACE(ctx, "gemm: tensor map + tiles");
     // CUDA events on the launching stream around the staging kernels and around the tcgen05 kernel
     std::vector<cudaEvent_t> evs;
     auto mark = [&]() {
         cudaEvent_t e;
-        cudaEventCreate(&e);
+        cudaEventCreateWithFlags(&e, cudaEventDefault);
         cudaEventRecord(e, st);
         evs.push_back(e);
     };
     const uint32_t sms = static_cast<uint32_t>(ctx->sm_count);
-    // transform + GEMM of the nl loci currently staged in cnt; sign -1 subtracts
+    const unsigned sp_blocks = static_cast<unsigned>(ceil_div_u64(lr.n_special ? lr.n_special : 1, 256));
+    auto clear_panel = [&](uint32_t kbs) -> int {
+        SGPU_CUDA(ctx, cudaMemset2DAsync(U.p, row_bytes, 0, static_cast<size_t>(kbs) * KB_BYTES, n_pad, st));
+        return SGPU_OK;
+    };
+    // transform + GEMM of the nl loci currently staged; sign -1 subtracts
     auto gemm_panel = [&](uint64_t nl, int sign) -> int {
         const uint32_t kbs = static_cast<uint32_t>((nl + LOCI_PER_KB - 1) / LOCI_PER_KB);
-        SGPU_LAUNCH(ctx, (transform_kernel<<<dim3(kbs, n_pad / 64), 256, 0, st>>>(cnt.p, n_pad, static_cast<uint32_t>(nl), row_bytes, U.p, d_err.p)));
-        // work list: split K so that every SM has work even when there are few tiles
+        const uint64_t items = static_cast<uint64_t>(n_pad) * kbs * 8;
+        SGPU_LAUNCH(ctx, (transform_kernel<<<static_cast<unsigned>(ceil_div_u64(items, 256)), 256, 0, st>>>(U.p, kbs, row_words, items, d_err.p)));
+        // split K so that every SM has work even when there are few tiles
         uint32_t splits = 1;
-        if (tiles.size() < 2 * sms) {
-            splits = static_cast<uint32_t>(std::min<uint64_t>(kbs, (2 * sms + tiles.size() - 1) / tiles.size()));
+        if (n_tiles < 2 * sms) {
+            splits = static_cast<uint32_t>(std::min<uint64_t>(kbs, (2 * sms + n_tiles - 1) / n_tiles));
         }
-        std::vector<WorkItem> work;
-        const uint32_t per = (kbs + splits - 1) / splits;
-        for (uint32_t s = 0; s < splits; ++s) {
-            const uint32_t k0 = s * per, k1 = std::min(kbs, k0 + per);
-            if (k0 >= k1) {
-                break;
-            }
-            for (auto &t : tiles) {
-                work.push_back(WorkItem{ t.first, t.second, k0, k1 });
-            }
-        }
-        SGPU_CUDA(ctx, d_work.alloc(work.size(), st));
-        SGPU_CUDA(ctx, cudaMemcpyAsync(d_work.p, work.data(), work.size() * sizeof(WorkItem), cudaMemcpyHostToDevice, st));
-        SGPU_CUDA(ctx, cudaStreamSynchronize(st)); // `work` is pageable host memory
-        const unsigned grid = static_cast<unsigned>(std::min<uint64_t>(work.size(), sms));
-        mark(); // [3k+1] staging done (the host sync above is inside the staging interval), GEMM begins
-        SGPU_LAUNCH(ctx, (syrk_kernel<<<grid, GEMM_THREADS, SMEM_BYTES, st>>>(map, d_work.p, static_cast<uint32_t>(work.size()),
-                                                           c->i32 + PLANE_S * c->nn, c->i32 + PLANE_D * c->nn, N, sign)));
+        WorkList wl;
+        wl.tiles = d_tiles;
+        wl.n_tiles = n_tiles;
+        wl.kbs = kbs;
+        wl.per = (kbs + splits - 1) / splits;
+        splits = (kbs + wl.per - 1) / wl.per; // no empty split
+        wl.n_work = n_tiles * splits;
+        const unsigned grid = static_cast<unsigned>(std::min<uint64_t>(wl.n_work, sms));
+        mark(); // [3k+1] staging done, GEMM begins
+        SGPU_LAUNCH(ctx, (syrk_kernel<<<grid, GEMM_THREADS, SMEM_BYTES, st>>>(map, wl, c->i32 + PLANE_S * c->nn, c->i32 + PLANE_D * c->nn, N, sign)));
         SGPU_CUDA(ctx, cudaGetLastError());
         mark(); // [3k+2] GEMM done
         ++ctx->n_syrk;
@@ -462,28 +567,35 @@ int sgpu_gemm_counts(sgpu_ctx *ctx, const sgpu_pileup *p, const LinkResult &lr, 
     for (uint64_t l0 = 0; l0 < P; l0 += panel) {
         const uint64_t l1 = std::min<uint64_t>(P, l0 + panel);
         const uint64_t nl = l1 - l0;
-        SGPU_CUDA(ctx, cudaMemcpyAsync(&ctx->h_scratch[0], p->d_row_ptr + l0, sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
-        SGPU_CUDA(ctx, cudaMemcpyAsync(&ctx->h_scratch[1], p->d_row_ptr + l1, sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
-        SGPU_CUDA(ctx, cudaStreamSynchronize(st));
-        const uint64_t e0 = ctx->h_scratch[0], e1 = ctx->h_scratch[1];
         mark(); // [3k] staging begins
-        SGPU_CUDA(ctx, cudaMemsetAsync(cnt.p, 0, nl * n_pad * sizeof(uint32_t), st));
-        if (e1 > e0) {
-            SGPU_LAUNCH(ctx, (stage_count_kernel<<<static_cast<unsigned>(ceil_div_u64(e1 - e0, 256)), 256, 0, st>>>(lr.code.p, lr.eloc.p, e0, e1,
-                                                                                               static_cast<uint32_t>(l0), n_pad, cnt.p, d_err.p)));
+        SGPU_TRY(clear_panel(static_cast<uint32_t>((nl + LOCI_PER_KB - 1) / LOCI_PER_KB)));
+        const unsigned grid = static_cast<unsigned>(std::min<uint64_t>(nl, static_cast<uint64_t>(sms) * 16));
+        SGPU_LAUNCH(ctx, (stage_main_kernel<<<grid, 256, 0, st>>>(p->d_row_ptr, p->d_gid_base, lr.sp_bits.p, lr.gmap.p, lr.n_groups, N,
+                                                                  static_cast<uint32_t>(l0), static_cast<uint32_t>(l1), row_words, U.p, d_err.p)));
+        if (lr.n_special) {
+            SGPU_LAUNCH(ctx, (stage_special_kernel<<<sp_blocks, 256, 0, st>>>(lr.sp_code.p, lr.sp_locus.p, lr.n_special, static_cast<uint32_t>(l0),
+                                                                             static_cast<uint32_t>(l1), row_words, U.p, d_err.p)));
         }
+        SGPU_TRACE(ctx, "gemm: stage main");
         SGPU_TRY(gemm_panel(nl, +1));
     }
+    SGPU_TRACE(ctx, "gemm: main panels");
     // The reference never compares two reads that both lie behind the per-chromosome cutoff K
     // (SURVEY F2). Those pairs only exist at the few loci behind the cutoff: subtract Z Z^T, Z = counts
     // of the tail reads alone at those loci, with the same kernel and sign -1.
     for (uint64_t t0 = 0; t0 < lr.n_tail_loci; t0 += panel) {
         const uint64_t nl = std::min<uint64_t>(lr.n_tail_loci - t0, panel);
         mark();
-        SGPU_CUDA(ctx, cudaMemsetAsync(cnt.p, 0, nl * n_pad * sizeof(uint32_t), st));
-        SGPU_LAUNCH(ctx, (stage_tail_kernel<<<static_cast<unsigned>(nl), 256, 0, st>>>(p->d_row_ptr, lr.code.p, lr.tail_loci.p + t0, n_pad, cnt.p, d_err.p)));
+        SGPU_TRY(clear_panel(static_cast<uint32_t>((nl + LOCI_PER_KB - 1) / LOCI_PER_KB)));
+        SGPU_LAUNCH(ctx, (stage_tail_kernel<<<static_cast<unsigned>(nl), 256, 0, st>>>(p->d_row_ptr, p->d_gid_base, lr.sp_bits.p, lr.gmap.p, lr.n_groups,
+                                                                                       N, lr.tail_loci.p + t0, row_words, U.p, d_err.p)));
+        if (lr.n_special) {
+            SGPU_LAUNCH(ctx, (stage_tail_special_kernel<<<sp_blocks, 256, 0, st>>>(lr.sp_code.p, lr.sp_locus.p, lr.n_special, lr.tail_loci.p + t0,
+                                                                                  static_cast<uint32_t>(nl), row_words, U.p, d_err.p)));
+        }
         SGPU_TRY(gemm_panel(nl, -1));
     }
+    SGPU_TRACE(ctx, "gemm: tail panels");
     SGPU_CUDA(ctx, cudaMemcpyAsync(&ctx->h_scratch[2], d_err.p, sizeof(int), cudaMemcpyDeviceToHost, st));
     SGPU_CUDA(ctx, cudaStreamSynchronize(st));
     for (size_t k = 0; k + 2 < evs.size(); k += 3) {
@@ -496,7 +608,11 @@ int sgpu_gemm_counts(sgpu_ctx *ctx, const sgpu_pileup *p, const LinkResult &lr, 
     for (cudaEvent_t e : evs) {
         cudaEventDestroy(e);
     }
-    if (static_cast<int>(ctx->h_scratch[2] & 0xFFFFFFFFu) != 0) {
+    const int err = static_cast<int>(ctx->h_scratch[2] & 0xFFFFFFFFu);
+    if (err == SGPU_E_CELL_RANGE) {
+        return sgpu_fail(ctx, err, "a group id is >= n_groups or maps to a cell >= num_cells (filter the pileup first)");
+    }
+    if (err != 0) {
         return sgpu_fail(ctx, SGPU_E_COUNT_RANGE, "more than 127 reads of one cell at one locus: outside the int8 GEMM path, use the scatter path");
     }
     return SGPU_OK;

@@ -10,43 +10,25 @@
 // plus a global class histogram. The epilogue then adds G(s,d) = F(s,d) - s F(1,0) - d F(0,1) per
 // recorded pair, which together with F(1,0) S + F(0,1) D gives exactly sum_pairs F(x_s, x_d).
 //
-// Only entries of reads that keep >= 2 loci take part (a small minority of the pileup): they are
-// compacted into a list ordered by locus, and each thread pairs one of them with the later ones of
-// the same locus, merging the two reads' stored (locus, base) lists.
+// Only entries of reads that keep >= 2 loci take part, and read linking (reads.cu) already lists
+// them: they are among the "special" entries, numbered in entry order (hence grouped by locus). Each
+// thread pairs one of them with the later ones of the same locus, merging the two reads' stored
+// (locus, base) lists.
 #include "common.cuh"
 
 namespace {
 
 constexpr int TB = 256;
 
-__global__ void __launch_bounds__(TB) multi_entry_flag_kernel(const uint32_t *__restrict__ code, uint64_t n_entries,
-                                                              uint8_t *__restrict__ flag) {
-    const uint64_t e = static_cast<uint64_t>(blockIdx.x) * TB + threadIdx.x;
-    if (e < n_entries) {
-        const uint32_t c = code[e];
-        flag[e] = (c != CODE_DROPPED && (c & 1u)) ? 1 : 0;
-    }
-}
-
-__global__ void __launch_bounds__(TB) multi_entry_compact_kernel(const uint8_t *__restrict__ flag,
-                                                                 const uint64_t *__restrict__ idx, uint64_t n_entries,
-                                                                 uint32_t *__restrict__ me) {
-    const uint64_t e = static_cast<uint64_t>(blockIdx.x) * TB + threadIdx.x;
-    if (e < n_entries && flag[e]) {
-        me[idx[e]] = static_cast<uint32_t>(e);
-    }
-}
-
 struct MultiArgs {
-    const uint32_t *me;       // entries of multi-locus reads, ascending (hence grouped by locus)
-    uint64_t n_me;
-    const uint32_t *code;
-    const uint32_t *eread;
-    const uint32_t *eloc;
-    const uint32_t *r_multi;
-    const uint64_t *m_off;
-    const uint32_t *m_locus;
-    const uint8_t *m_base;
+    uint64_t n_special;
+    const uint32_t *sp_code;  // per special entry: code (bit 0 = read keeps >= 2 loci) or CODE_DROPPED
+    const uint32_t *sp_locus;
+    const uint32_t *sp_head;  // first entry of the read: owner of the stored list
+    const uint64_t *g_off;
+    const uint32_t *g_list;   // stored loci, ascending
+    const uint8_t *g_base;    // stored bases
+    const uint32_t *g_nst;    // per head: stored length
     int32_t *H2;              // 3 planes
     int32_t *H3;              // 4 planes
     double *spill;            // may be null
@@ -64,32 +46,36 @@ struct MultiArgs {
 __global__ void __launch_bounds__(TB) multilocus_kernel(MultiArgs a) {
     const uint64_t ia = static_cast<uint64_t>(blockIdx.x) * TB + threadIdx.x;
     unsigned long long local_pairs = 0;
-    if (ia < a.n_me) {
-        const uint32_t ea = a.me[ia];
-        const uint32_t loc = a.eloc[ea];
-        const uint32_t ca = a.code[ea];
-        const uint32_t ma = a.r_multi[a.eread[ea]];
-        const uint64_t a0 = a.m_off[ma], a1 = a.m_off[ma + 1];
-        for (uint64_t ib = ia + 1; ib < a.n_me; ++ib) {
-            const uint32_t eb = a.me[ib];
-            if (a.eloc[eb] != loc) {
+    uint32_t ca = CODE_DROPPED;
+    if (ia < a.n_special) {
+        ca = a.sp_code[ia];
+    }
+    if (ca != CODE_DROPPED && (ca & 1u)) {
+        const uint32_t loc = a.sp_locus[ia];
+        const uint32_t ha = a.sp_head[ia];
+        const uint64_t a0 = a.g_off[ha], a1 = a0 + a.g_nst[ha];
+        for (uint64_t ib = ia + 1; ib < a.n_special; ++ib) {
+            if (a.sp_locus[ib] != loc) {
                 break;
             }
-            const uint32_t cb = a.code[eb];
+            const uint32_t cb = a.sp_code[ib];
+            if (cb == CODE_DROPPED || !(cb & 1u)) {
+                continue;
+            }
             if (code_cell(ca) == code_cell(cb) || (ca & cb & 2u)) {
                 continue; // same cell, or both reads behind the cutoff K
             }
-            const uint32_t mb = a.r_multi[a.eread[eb]];
-            const uint64_t b0 = a.m_off[mb], b1 = a.m_off[mb + 1];
+            const uint32_t hb = a.sp_head[ib];
+            const uint64_t b0 = a.g_off[hb], b1 = b0 + a.g_nst[hb];
             // two-pointer merge over the stored loci (similarity_matrix.cpp:221-229)
             uint32_t xs = 0, xd = 0, first_common = 0xFFFFFFFFu;
             for (uint64_t i = a0, j = b0; i < a1 && j < b1;) {
-                const uint32_t la = a.m_locus[i], lb = a.m_locus[j];
+                const uint32_t la = a.g_list[i], lb = a.g_list[j];
                 if (la == lb) {
                     if (first_common == 0xFFFFFFFFu) {
                         first_common = la;
                     }
-                    a.m_base[i] == a.m_base[j] ? ++xs : ++xd;
+                    a.g_base[i] == a.g_base[j] ? ++xs : ++xd;
                     ++i;
                     ++j;
                 } else if (la < lb) {
@@ -143,51 +129,35 @@ int sgpu_multilocus(sgpu_ctx *ctx, const sgpu_pileup *p, const LinkResult &lr, s
     if (n_pairs_multi) {
         *n_pairs_multi = 0;
     }
-    const uint64_t E = p->n_entries;
-    if (lr.n_multi == 0 || E == 0) {
+    if (lr.n_multi == 0 || p->n_entries == 0 || lr.n_special == 0) {
         return SGPU_OK;
     }
-    DevBuf<uint8_t> flag;
-    DevBuf<uint64_t> idx;
-    DevBuf<uint32_t> me;
+    const uint64_t NS = lr.n_special;
     DevBuf<unsigned long long> d_np;
     DevBuf<unsigned int> d_max;
     DevBuf<int> d_err;
     DevBuf<double> d_G;
-    SGPU_CUDA(ctx, flag.alloc(E, st));
-    SGPU_CUDA(ctx, idx.alloc(E + 1, st));
-    SGPU_LAUNCH(ctx, (multi_entry_flag_kernel<<<blocks_for(E), TB, 0, st>>>(lr.code.p, E, flag.p)));
-    SGPU_TRY(sgpu_scan_u8_u64(ctx, flag.p, idx.p, E));
-    SGPU_CUDA(ctx, cudaMemcpyAsync(&ctx->h_scratch[0], idx.p + E, sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
-    SGPU_CUDA(ctx, cudaStreamSynchronize(st));
-    const uint64_t NME = ctx->h_scratch[0];
-    if (NME == 0) {
-        return SGPU_OK;
-    }
-    SGPU_CUDA(ctx, me.alloc(NME, st));
-    SGPU_LAUNCH(ctx, (multi_entry_compact_kernel<<<blocks_for(E), TB, 0, st>>>(flag.p, idx.p, E, me.p)));
-    SGPU_CUDA(ctx, d_np.alloc(1, st));
-    SGPU_CUDA(ctx, d_max.alloc(1, st));
-    SGPU_CUDA(ctx, d_err.alloc(1, st));
+    SGPU_CUDA(ctx, d_np.alloc(1, ctx));
+    SGPU_CUDA(ctx, d_max.alloc(1, ctx));
+    SGPU_CUDA(ctx, d_err.alloc(1, ctx));
     SGPU_CUDA(ctx, cudaMemsetAsync(d_np.p, 0, sizeof(unsigned long long), st));
     SGPU_CUDA(ctx, cudaMemsetAsync(d_max.p, 0, sizeof(unsigned int), st));
     SGPU_CUDA(ctx, cudaMemsetAsync(d_err.p, 0, sizeof(int), st));
     if (c->spill != nullptr) {
-        SGPU_CUDA(ctx, d_G.alloc(SGPU_MAX_CLASS * SGPU_MAX_CLASS, st));
+        SGPU_CUDA(ctx, d_G.alloc(SGPU_MAX_CLASS * SGPU_MAX_CLASS, ctx));
         SGPU_TRY(sgpu_build_gtable(ctx, c->eps, c->h, c->theta, c->L, SGPU_MAX_CLASS, d_G.p, nullptr));
     }
     c->planes_used = N_PLANES;
 
     MultiArgs a;
-    a.me = me.p;
-    a.n_me = NME;
-    a.code = lr.code.p;
-    a.eread = lr.eread.p;
-    a.eloc = lr.eloc.p;
-    a.r_multi = lr.r_multi.p;
-    a.m_off = lr.m_off.p;
-    a.m_locus = lr.m_locus.p;
-    a.m_base = lr.m_base.p;
+    a.n_special = NS;
+    a.sp_code = lr.sp_code.p;
+    a.sp_locus = lr.sp_locus.p;
+    a.sp_head = lr.sp_head.p;
+    a.g_off = lr.g_off.p;
+    a.g_list = lr.g_list.p;
+    a.g_base = lr.g_base.p;
+    a.g_nst = lr.g_nst.p;
     a.H2 = c->i32 + PLANE_H2 * c->nn;
     a.H3 = c->i32 + PLANE_H3 * c->nn;
     a.spill = c->spill;
@@ -200,7 +170,7 @@ int sgpu_multilocus(sgpu_ctx *ctx, const sgpu_pileup *p, const LinkResult &lr, s
     a.max_order = d_max.p;
     a.n_pairs = d_np.p;
     a.err = d_err.p;
-    SGPU_LAUNCH(ctx, (multilocus_kernel<<<blocks_for(NME), TB, 0, st>>>(a)));
+    SGPU_LAUNCH(ctx, (multilocus_kernel<<<blocks_for(NS), TB, 0, st>>>(a)));
     SGPU_CUDA(ctx, cudaGetLastError());
     SGPU_CUDA(ctx, cudaMemcpyAsync(&ctx->h_scratch[0], d_np.p, sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
     SGPU_CUDA(ctx, cudaMemcpyAsync(&ctx->h_scratch[1], d_max.p, sizeof(unsigned int), cudaMemcpyDeviceToHost, st));
@@ -218,12 +188,12 @@ int sgpu_multilocus(sgpu_ctx *ctx, const sgpu_pileup *p, const LinkResult &lr, s
         // just those classes in a second pass
         SGPU_CUDA(ctx, cudaMalloc(&c->spill, c->nn * sizeof(double)));
         SGPU_CUDA(ctx, cudaMemsetAsync(c->spill, 0, c->nn * sizeof(double), st));
-        SGPU_CUDA(ctx, d_G.alloc(SGPU_MAX_CLASS * SGPU_MAX_CLASS, st));
+        SGPU_CUDA(ctx, d_G.alloc(SGPU_MAX_CLASS * SGPU_MAX_CLASS, ctx));
         SGPU_TRY(sgpu_build_gtable(ctx, c->eps, c->h, c->theta, c->L, SGPU_MAX_CLASS, d_G.p, nullptr));
         a.spill = c->spill;
         a.G = d_G.p;
         a.spill_only = 1;
-        SGPU_LAUNCH(ctx, (multilocus_kernel<<<blocks_for(NME), TB, 0, st>>>(a)));
+        SGPU_LAUNCH(ctx, (multilocus_kernel<<<blocks_for(NS), TB, 0, st>>>(a)));
         SGPU_CUDA(ctx, cudaGetLastError());
         SGPU_CUDA(ctx, cudaStreamSynchronize(st));
     }

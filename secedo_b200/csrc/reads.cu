@@ -1,28 +1,35 @@
 // K2 — read linking, paired-end mate rule and tail cutoff.
 //
 // The reference walks the filtered loci sequentially and rebuilds reads in a hash map keyed by
-// read id (similarity_matrix.cpp:342-403). What the similarity matrix needs from that walk is, per
-// pileup entry: which read it belongs to, the read's index in order of first appearance, whether
-// the entry survives the mate rule (:387-395), whether the read keeps >= 2 loci, and whether the
-// read lies behind the per-chromosome cutoff K that the batching at :354-373 + the clear() at
-// :407-408 imply. This file computes exactly that, data-parallel:
+// read id (similarity_matrix.cpp:342-403). What the counting kernels need from that walk is: which
+// entries share a read with another entry (same id twice at one locus = overlapping mates, or at
+// several loci within one fragment length), what the mate rule (:387-395) makes of those reads, and
+// the per-chromosome cutoff K implied by the batching at :354-373 + the clear() at :407-408
+// (SURVEY.md Appendix A.4). In real pileups the overwhelming majority of the entries are the only
+// entry of their read; everything about them is implicit (cell = own group, read created at the own
+// locus). So the work is split into ONE dense pass that only finds the exceptions and a chain of
+// small kernels over those exceptions ("special" entries):
 //
-//   link_insert      open-addressing hash (chromosome, read id) -> smallest entry index
-//   link_first       is this entry the first of its read?         (+ exclusive scan = read index)
-//   link_reads       read index per entry, cell/start per read, extra-entry count per read
-//   cand_fill/sort   entry lists of the reads with >= 2 entries (a small minority)
-//   mate_rule        sequential replay of the insertion rules for those reads only
-//   cutoff           one thread per chromosome, two-pointer sweep over loci
-//   make_codes       packs (cell, base, tail, multi | dropped) per entry for the counting kernels
+//   link_window_kernel   dense, one CTA per owner locus: the owner's read ids go into a shared-memory
+//                        table (plain stores for the first round, CAS only for the ~10 % displaced
+//                        ids), the loci of the following L bp are streamed against it. Output: a
+//                        compact list of links (entry x, entry y) carrying the same read id.
+//   mark / rank / list   bitmap of special entries, popcount prefix = dense numbering ("sid")
+//   link_min             first entry of every special entry's read (two atomicMin sweeps)
+//   group / mate_rule    entry lists per read, sequential replay of the insertion rules (:383-402)
+//   cutoff               K per chromosome from the per-locus number of reads created
+//   sp_finish            code (cell, base, tail, multi | dropped) per special entry
+// The bitmap is all the dense counting kernels read (1 bit per entry).
 #include "common.cuh"
 
 #include <algorithm>
+#include <cstdlib>
 #include <vector>
 
 namespace {
 
-constexpr uint64_t KEY_EMPTY = ~0ull;
 constexpr int TB = 256;
+constexpr uint64_t KEY_EMPTY = ~0ull;
 
 __device__ __forceinline__ uint64_t mix64(uint64_t x) {
     x ^= x >> 33;
@@ -46,72 +53,34 @@ __device__ __forceinline__ uint32_t chr_of_locus(const uint64_t *__restrict__ ch
     return lo;
 }
 
-// eloc[e] = locus of entry e; lchr[l] = chromosome of locus l; checks strictly increasing positions
-__global__ void __launch_bounds__(TB) locus_fill_kernel(const uint64_t *__restrict__ row_ptr,
+// locus of entry e: largest l with row_ptr[l] <= e
+__device__ __forceinline__ uint32_t locus_of_entry(const uint64_t *__restrict__ row_ptr, uint64_t n_loci, uint64_t e) {
+    uint64_t lo = 0, hi = n_loci;
+    while (hi - lo > 1) {
+        const uint64_t mid = (lo + hi) >> 1;
+        if (row_ptr[mid] <= e) {
+            lo = mid;
+        } else {
+            hi = mid;
+        }
+    }
+    return static_cast<uint32_t>(lo);
+}
+
+// lchr[l] = chromosome of locus l; checks strictly increasing positions; largest locus
+__global__ void __launch_bounds__(TB) locus_meta_kernel(const uint64_t *__restrict__ row_ptr,
                                                         const uint32_t *__restrict__ position,
                                                         const uint64_t *__restrict__ chr_ptr, uint32_t n_chr,
-                                                        uint64_t n_loci, uint32_t *__restrict__ eloc,
-                                                        uint8_t *__restrict__ lchr, int *__restrict__ err) {
-    const int lane = threadIdx.x & 31;
-    const uint64_t warps_total = static_cast<uint64_t>(gridDim.x) * (TB / 32);
-    for (uint64_t l = static_cast<uint64_t>(blockIdx.x) * (TB / 32) + (threadIdx.x >> 5); l < n_loci; l += warps_total) {
-        if (lane == 0) {
-            const uint32_t c = chr_of_locus(chr_ptr, n_chr, l);
-            lchr[l] = static_cast<uint8_t>(c);
-            if (l > chr_ptr[c] && position[l] <= position[l - 1]) {
-                atomicExch(err, SGPU_E_POSITIONS);
-            }
-        }
-        const uint64_t e0 = row_ptr[l], e1 = row_ptr[l + 1];
-        for (uint64_t e = e0 + lane; e < e1; e += 32) {
-            eloc[e] = static_cast<uint32_t>(l);
-        }
-    }
-}
-
-__global__ void __launch_bounds__(TB) link_insert_kernel(const uint32_t *__restrict__ read_id,
-                                                         const uint32_t *__restrict__ eloc,
-                                                         const uint8_t *__restrict__ lchr, uint64_t n_entries,
-                                                         uint64_t *__restrict__ keys, uint32_t *__restrict__ vals,
-                                                         uint64_t mask, uint32_t *__restrict__ eslot) {
-    const uint64_t e = static_cast<uint64_t>(blockIdx.x) * TB + threadIdx.x;
-    if (e >= n_entries) {
-        return;
-    }
-    const uint64_t key = (static_cast<uint64_t>(lchr[eloc[e]]) << 32) | read_id[e];
-    uint64_t slot = mix64(key) & mask;
-    for (;;) {
-        uint64_t cur = keys[slot];
-        if (cur == KEY_EMPTY) {
-            cur = atomicCAS(reinterpret_cast<unsigned long long *>(&keys[slot]), KEY_EMPTY, key);
-            if (cur == KEY_EMPTY) {
-                break;
-            }
-        }
-        if (cur == key) {
-            break;
-        }
-        slot = (slot + 1) & mask;
-    }
-    atomicMin(&vals[slot], static_cast<uint32_t>(e));
-    eslot[e] = static_cast<uint32_t>(slot);
-}
-
-// ---- windowed linking ----------------------------------------------------------------------------
-// A fragment spans less than L bp, so all entries of a read lie in the loci within L bp after the
-// locus of its first entry. One CTA per "owner" locus builds a hash table of that locus' read ids in
-// shared memory (value = smallest entry index carrying the id) and streams the entries of the
-// following loci inside the window against it; every entry ends up with efirst[e] = the smallest
-// entry index of its read. No global-memory hash table: reads are 4 B/entry per pass, coalesced.
-constexpr uint32_t ID_EMPTY = 0xFFFFFFFFu;
-constexpr int WIN_THREADS = 512;
-constexpr uint32_t WIN_MAX_SLOTS = 16384; // 128 KB of shared memory
-
-__global__ void __launch_bounds__(TB) max_locus_size_kernel(const uint64_t *__restrict__ row_ptr, uint64_t n_loci,
-                                                            unsigned int *__restrict__ out) {
+                                                        uint64_t n_loci, uint8_t *__restrict__ lchr,
+                                                        unsigned int *__restrict__ max_row, int *__restrict__ err) {
     const uint64_t l = static_cast<uint64_t>(blockIdx.x) * TB + threadIdx.x;
     unsigned int n = 0;
     if (l < n_loci) {
+        const uint32_t c = chr_of_locus(chr_ptr, n_chr, l);
+        lchr[l] = static_cast<uint8_t>(c);
+        if (l > chr_ptr[c] && position[l] <= position[l - 1]) {
+            atomicExch(err, SGPU_E_POSITIONS);
+        }
         n = static_cast<unsigned int>(min(row_ptr[l + 1] - row_ptr[l], static_cast<uint64_t>(0xFFFFFFFFu)));
     }
 #pragma unroll
@@ -119,77 +88,138 @@ __global__ void __launch_bounds__(TB) max_locus_size_kernel(const uint64_t *__re
         n = max(n, __shfl_xor_sync(0xffffffffu, n, o));
     }
     if ((threadIdx.x & 31) == 0 && n) {
-        atomicMax(out, n);
+        atomicMax(max_row, n);
     }
 }
 
-__global__ void __launch_bounds__(TB) iota_kernel(uint32_t *__restrict__ a, uint64_t n) {
-    const uint64_t i = static_cast<uint64_t>(blockIdx.x) * TB + threadIdx.x;
-    if (i < n) {
-        a[i] = static_cast<uint32_t>(i);
-    }
-}
+// ---- windowed linking ----------------------------------------------------------------------------
+// A fragment spans less than L bp, so all entries of a read lie in the loci within L bp after the
+// locus of its first entry. One CTA per "owner" locus puts the owner's read ids into a shared-memory
+// open-addressing table of 16-bit entry indices and streams the entries of the following loci inside
+// the window against it. Shared-memory atomics cost ~2 cycles per lane on this machine, plain
+// loads/stores 1/8 of that, so the table is built optimistically: every entry stores its index at its
+// home slot (last writer wins), reads it back, and only the losers (another id won the slot) insert
+// themselves with CAS. An id that occurs several times at the owner keeps ONE representative in the
+// table; the others are linked to it. Links go to a CTA-local buffer that is flushed with one global
+// atomic per flush.
+constexpr int WIN_THREADS = 512;
+constexpr uint32_t SLOT_EMPTY = 0xFFFFu;
+constexpr uint32_t REC_BUF = 1024;      // links staged per CTA between flushes
+constexpr uint32_t WIN_MAX_ENTRIES = 0xFFFEu;
+constexpr size_t WIN_SMEM_LIMIT = 220 * 1024;
 
-__device__ __forceinline__ uint32_t hash32(uint32_t x) {
-    x ^= x >> 16;
-    x *= 0x7feb352du;
-    x ^= x >> 15;
-    x *= 0x846ca68bu;
-    x ^= x >> 16;
-    return x;
+struct WinCounters {
+    unsigned long long n_links; // links produced (may exceed the capacity of the list: the host then retries)
+};
+
+__device__ __forceinline__ uint32_t slot_hash(uint32_t id, uint32_t shift) { return (id * 0x9E3779B1u) >> shift; }
+
+__device__ __forceinline__ void emit_link(uint2 *rbuf, uint32_t *s_cnt, uint2 *__restrict__ links, uint64_t cap,
+                                          WinCounters *__restrict__ ctr, uint32_t x, uint32_t y) {
+    const uint32_t k = atomicAdd(s_cnt, 1u);
+    if (k < REC_BUF) {
+        rbuf[k] = make_uint2(x, y);
+    } else { // staging buffer full: straight to the global list
+        const unsigned long long g = atomicAdd(&ctr->n_links, 1ull);
+        if (g < cap) {
+            links[g] = make_uint2(x, y);
+        }
+    }
 }
 
 __global__ void __launch_bounds__(WIN_THREADS) link_window_kernel(
         const uint64_t *__restrict__ row_ptr, const uint32_t *__restrict__ position, const uint32_t *__restrict__ read_id,
         const uint8_t *__restrict__ lchr, const uint64_t *__restrict__ chr_ptr, uint64_t n_loci, uint32_t L,
-        uint32_t slots /* power of two */, uint32_t *__restrict__ efirst) {
-    extern __shared__ uint32_t s_tab[]; // keys[slots], vals[slots]
-    uint32_t *keys = s_tab, *vals = s_tab + slots;
-    const uint32_t mask = slots - 1;
+        uint32_t slots /* power of two */, uint32_t id_cap, uint2 *__restrict__ links, uint64_t cap,
+        WinCounters *__restrict__ ctr) {
+    extern __shared__ uint32_t s_mem[];
+    uint32_t *ids = s_mem;                                              // [id_cap]
+    uint2 *rbuf = reinterpret_cast<uint2 *>(s_mem + id_cap);            // [REC_BUF] (id_cap is even)
+    unsigned short *tab = reinterpret_cast<unsigned short *>(rbuf + REC_BUF); // [slots]
+    __shared__ uint32_t s_cnt;
+    __shared__ unsigned long long s_base;
+    const uint32_t mask = slots - 1, shift = 32 - (31 - __clz(slots));
+    if (threadIdx.x == 0) {
+        s_cnt = 0;
+    }
     for (uint64_t lo = blockIdx.x; lo < n_loci; lo += gridDim.x) {
-        const uint64_t e0 = row_ptr[lo], e1 = row_ptr[lo + 1];
+        const uint64_t e0 = row_ptr[lo];
+        const uint32_t n = static_cast<uint32_t>(row_ptr[lo + 1] - e0);
         const uint64_t chr_end = chr_ptr[lchr[lo] + 1];
         const uint32_t p0 = position[lo];
-        __syncthreads(); // previous owner's probes are done
-        for (uint32_t i = threadIdx.x; i < slots; i += WIN_THREADS) {
-            keys[i] = ID_EMPTY;
-            vals[i] = 0xFFFFFFFFu;
+        const bool has_window = lo + 1 < chr_end && position[lo + 1] - p0 < L;
+        if (n == 0 || (n < 2 && !has_window)) {
+            continue; // nothing this owner could link (uniform over the CTA)
+        }
+        __syncthreads(); // the previous owner's probes are done
+        if (s_cnt > REC_BUF / 2) { // uniform: nobody emits before the next barrier
+            const uint32_t m = min(s_cnt, REC_BUF);
+            if (threadIdx.x == 0) {
+                s_base = atomicAdd(&ctr->n_links, static_cast<unsigned long long>(m));
+            }
+            __syncthreads();
+            for (uint32_t i = threadIdx.x; i < m; i += WIN_THREADS) {
+                if (s_base + i < cap) {
+                    links[s_base + i] = rbuf[i];
+                }
+            }
+            __syncthreads();
+            if (threadIdx.x == 0) {
+                s_cnt = 0;
+            }
+        }
+        for (uint32_t i = threadIdx.x; i < slots / 2; i += WIN_THREADS) {
+            reinterpret_cast<uint32_t *>(tab)[i] = 0xFFFFFFFFu;
+        }
+        for (uint32_t i = threadIdx.x; i < n; i += WIN_THREADS) {
+            ids[i] = read_id[e0 + i];
         }
         __syncthreads();
-        // build: id -> smallest entry index at the owner locus
-        for (uint64_t e = e0 + threadIdx.x; e < e1; e += WIN_THREADS) {
-            const uint32_t id = read_id[e];
-            uint32_t s = hash32(id) & mask;
+        // round 1: optimistic placement at the home slot
+        for (uint32_t i = threadIdx.x; i < n; i += WIN_THREADS) {
+            tab[slot_hash(ids[i], shift)] = static_cast<unsigned short>(i);
+        }
+        __syncthreads();
+        // round 2: losers either carry the winner's id (overlapping mates: link) or insert with CAS
+        for (uint32_t i = threadIdx.x; i < n; i += WIN_THREADS) {
+            const uint32_t id = ids[i];
+            uint32_t s = slot_hash(id, shift);
+            uint32_t cur = tab[s];
+            if (cur == i) {
+                continue;
+            }
             for (;;) {
-                const uint32_t prev = atomicCAS(&keys[s], ID_EMPTY, id);
-                if (prev == ID_EMPTY || prev == id) {
+                if (cur == SLOT_EMPTY) {
+                    cur = atomicCAS(&tab[s], static_cast<unsigned short>(SLOT_EMPTY), static_cast<unsigned short>(i));
+                    if (cur == SLOT_EMPTY) {
+                        break; // placed
+                    }
+                }
+                if (ids[cur] == id) {
+                    emit_link(rbuf, &s_cnt, links, cap, ctr, static_cast<uint32_t>(e0) + cur, static_cast<uint32_t>(e0) + i);
                     break;
                 }
                 s = (s + 1) & mask;
+                cur = tab[s];
             }
-            atomicMin(&vals[s], static_cast<uint32_t>(e));
         }
         __syncthreads();
-        // the owner's own entries (two entries of one read at one locus: overlapping mates), then the
-        // loci of the window
-        for (uint64_t l = lo; l < chr_end; ++l) {
-            if (l > lo && (position[l] - p0 >= L)) {
+        // the loci of the window
+        for (uint64_t l = lo + 1; l < chr_end; ++l) {
+            if (position[l] - p0 >= L) {
                 break;
             }
             const uint64_t a0 = row_ptr[l], a1 = row_ptr[l + 1];
             for (uint64_t e = a0 + threadIdx.x; e < a1; e += WIN_THREADS) {
                 const uint32_t id = read_id[e];
-                uint32_t s = hash32(id) & mask;
+                uint32_t s = slot_hash(id, shift);
                 for (;;) {
-                    const uint32_t k = keys[s];
-                    if (k == id) {
-                        const uint32_t m = vals[s];
-                        if (m < static_cast<uint32_t>(e)) {
-                            atomicMin(&efirst[e], m);
-                        }
+                    const uint32_t cur = tab[s];
+                    if (cur == SLOT_EMPTY) {
                         break;
                     }
-                    if (k == ID_EMPTY) {
+                    if (ids[cur] == id) {
+                        emit_link(rbuf, &s_cnt, links, cap, ctr, static_cast<uint32_t>(e0) + cur, static_cast<uint32_t>(e));
                         break;
                     }
                     s = (s + 1) & mask;
@@ -197,114 +227,204 @@ __global__ void __launch_bounds__(WIN_THREADS) link_window_kernel(
             }
         }
     }
-}
-
-// isfirst[e] and the check that first-entry pointers are idempotent (a chain means a read id
-// spanning >= L through intermediate loci)
-__global__ void __launch_bounds__(TB) link_finish_kernel(const uint32_t *__restrict__ efirst, uint64_t n_entries,
-                                                         uint8_t *__restrict__ isfirst, int *__restrict__ err) {
-    const uint64_t e = static_cast<uint64_t>(blockIdx.x) * TB + threadIdx.x;
-    if (e >= n_entries) {
-        return;
-    }
-    const uint32_t f = efirst[e];
-    isfirst[e] = f == static_cast<uint32_t>(e) ? 1 : 0;
-    if (efirst[f] != f) {
-        atomicExch(err, SGPU_E_FRAGMENT_SPAN);
-    }
-}
-
-// efirst[e] (in place over eslot) = first entry of e's read; isfirst[e]
-__global__ void __launch_bounds__(TB) link_first_kernel(uint32_t *__restrict__ eslot_efirst,
-                                                        const uint32_t *__restrict__ vals, uint64_t n_entries,
-                                                        uint8_t *__restrict__ isfirst) {
-    const uint64_t e = static_cast<uint64_t>(blockIdx.x) * TB + threadIdx.x;
-    if (e >= n_entries) {
-        return;
-    }
-    const uint32_t f = vals[eslot_efirst[e]];
-    eslot_efirst[e] = f;
-    isfirst[e] = f == static_cast<uint32_t>(e) ? 1 : 0;
-}
-
-__global__ void __launch_bounds__(TB) link_reads_kernel(const uint32_t *__restrict__ efirst,
-                                                        const uint64_t *__restrict__ rscan,
-                                                        const uint16_t *__restrict__ gid_base,
-                                                        const uint32_t *__restrict__ eloc,
-                                                        const uint32_t *__restrict__ gmap, uint32_t n_groups,
-                                                        uint32_t num_cells, uint64_t n_entries,
-                                                        uint32_t *__restrict__ eread, uint32_t *__restrict__ r_cell,
-                                                        uint32_t *__restrict__ r_startloc,
-                                                        uint32_t *__restrict__ r_extra, int *__restrict__ err) {
-    const uint64_t e = static_cast<uint64_t>(blockIdx.x) * TB + threadIdx.x;
-    if (e >= n_entries) {
-        return;
-    }
-    const uint32_t f = efirst[e];
-    const uint32_t r = static_cast<uint32_t>(rscan[f]);
-    eread[e] = r;
-    if (f == static_cast<uint32_t>(e)) {
-        // the read's cell is fixed by its first entry (similarity_matrix.cpp:379, :208-209)
-        const uint32_t gid = gid_base[e] >> 2;
-        uint32_t cell = 0;
-        if (gid >= n_groups || (cell = gmap[gid]) >= num_cells) {
-            atomicExch(err, SGPU_E_CELL_RANGE);
-            cell = 0;
+    __syncthreads();
+    const uint32_t m = min(s_cnt, REC_BUF);
+    if (m) {
+        if (threadIdx.x == 0) {
+            s_base = atomicAdd(&ctr->n_links, static_cast<unsigned long long>(m));
         }
-        r_cell[r] = cell;
-        r_startloc[r] = eloc[e];
-    } else {
-        atomicAdd(&r_extra[r], 1u);
+        __syncthreads();
+        for (uint32_t i = threadIdx.x; i < m; i += WIN_THREADS) {
+            if (s_base + i < cap) {
+                links[s_base + i] = rbuf[i];
+            }
+        }
     }
 }
 
-// cand[r] = read has >= 2 entries; clen[r] = its entry count (0 for non candidates)
-__global__ void __launch_bounds__(TB) cand_flag_kernel(const uint32_t *__restrict__ r_extra, uint64_t n_reads,
-                                                       uint8_t *__restrict__ cand, uint32_t *__restrict__ clen) {
-    const uint64_t r = static_cast<uint64_t>(blockIdx.x) * TB + threadIdx.x;
-    if (r >= n_reads) {
+// ---- fallback for loci too large for the shared-memory table: global (chromosome, id) hash ---------
+__global__ void __launch_bounds__(TB) ghash_insert_kernel(const uint64_t *__restrict__ row_ptr,
+                                                          const uint32_t *__restrict__ read_id,
+                                                          const uint8_t *__restrict__ lchr, uint64_t n_loci,
+                                                          uint64_t *__restrict__ keys, uint32_t *__restrict__ vals,
+                                                          uint64_t mask) {
+    for (uint64_t l = blockIdx.x; l < n_loci; l += gridDim.x) {
+        const uint64_t e0 = row_ptr[l], e1 = row_ptr[l + 1];
+        const uint64_t chr = lchr[l];
+        for (uint64_t e = e0 + threadIdx.x; e < e1; e += TB) {
+            const uint64_t key = (chr << 32) | read_id[e];
+            uint64_t slot = mix64(key) & mask;
+            for (;;) {
+                uint64_t cur = keys[slot];
+                if (cur == KEY_EMPTY) {
+                    cur = atomicCAS(reinterpret_cast<unsigned long long *>(&keys[slot]), KEY_EMPTY, key);
+                    if (cur == KEY_EMPTY) {
+                        break;
+                    }
+                }
+                if (cur == key) {
+                    break;
+                }
+                slot = (slot + 1) & mask;
+            }
+            atomicMin(&vals[slot], static_cast<uint32_t>(e));
+        }
+    }
+}
+
+__global__ void __launch_bounds__(TB) ghash_emit_kernel(const uint64_t *__restrict__ row_ptr,
+                                                        const uint32_t *__restrict__ read_id,
+                                                        const uint8_t *__restrict__ lchr, uint64_t n_loci,
+                                                        const uint64_t *__restrict__ keys, const uint32_t *__restrict__ vals,
+                                                        uint64_t mask, uint2 *__restrict__ links, uint64_t cap,
+                                                        WinCounters *__restrict__ ctr) {
+    for (uint64_t l = blockIdx.x; l < n_loci; l += gridDim.x) {
+        const uint64_t e0 = row_ptr[l], e1 = row_ptr[l + 1];
+        const uint64_t chr = lchr[l];
+        for (uint64_t base = e0; base < e1; base += TB) {
+            const uint64_t e = base + threadIdx.x;
+            uint32_t first = 0xFFFFFFFFu;
+            if (e < e1) {
+                const uint64_t key = (chr << 32) | read_id[e];
+                uint64_t slot = mix64(key) & mask;
+                while (keys[slot] != key) {
+                    slot = (slot + 1) & mask;
+                }
+                first = vals[slot];
+            }
+            const bool hit = e < e1 && first != static_cast<uint32_t>(e);
+            const uint32_t ballot = __ballot_sync(0xffffffffu, hit);
+            if (ballot) {
+                const int lane = threadIdx.x & 31, leader = __ffs(ballot) - 1;
+                unsigned long long g = 0;
+                if (lane == leader) {
+                    g = atomicAdd(&ctr->n_links, static_cast<unsigned long long>(__popc(ballot)));
+                }
+                g = __shfl_sync(0xffffffffu, g, leader);
+                if (hit) {
+                    g += __popc(ballot & ((1u << lane) - 1u));
+                    if (g < cap) {
+                        links[g] = make_uint2(first, static_cast<uint32_t>(e));
+                    }
+                }
+            }
+        }
+    }
+}
+
+// ---- special entries ------------------------------------------------------------------------------
+__global__ void __launch_bounds__(TB) mark_kernel(const uint2 *__restrict__ links, uint64_t n_links,
+                                                  uint32_t *__restrict__ bits) {
+    const uint64_t i = static_cast<uint64_t>(blockIdx.x) * TB + threadIdx.x;
+    if (i < n_links) {
+        const uint2 r = links[i];
+        atomicOr(&bits[r.x >> 5], 1u << (r.x & 31));
+        atomicOr(&bits[r.y >> 5], 1u << (r.y & 31));
+    }
+}
+
+__global__ void __launch_bounds__(TB) popc_kernel(const uint32_t *__restrict__ bits, uint64_t n_words,
+                                                  uint32_t *__restrict__ pc) {
+    const uint64_t w = static_cast<uint64_t>(blockIdx.x) * TB + threadIdx.x;
+    if (w < n_words) {
+        pc[w] = __popc(bits[w]);
+    }
+}
+
+__device__ __forceinline__ uint32_t sid_of(const uint32_t *__restrict__ bits, const uint64_t *__restrict__ rank, uint32_t e) {
+    return static_cast<uint32_t>(rank[e >> 5]) + __popc(bits[e >> 5] & ((1u << (e & 31)) - 1u));
+}
+
+__global__ void __launch_bounds__(TB) sp_list_kernel(const uint32_t *__restrict__ bits, const uint64_t *__restrict__ rank,
+                                                     uint64_t n_words, const uint64_t *__restrict__ row_ptr,
+                                                     uint64_t n_loci, uint32_t *__restrict__ sp_entry,
+                                                     uint32_t *__restrict__ sp_first, uint32_t *__restrict__ sp_locus) {
+    const uint64_t w = static_cast<uint64_t>(blockIdx.x) * TB + threadIdx.x;
+    if (w >= n_words) {
         return;
     }
-    const uint32_t x = r_extra[r];
-    cand[r] = x ? 1 : 0;
-    clen[r] = x ? x + 1 : 0;
+    uint32_t b = bits[w];
+    uint64_t k = rank[w];
+    while (b) {
+        const uint32_t bit = __ffs(b) - 1;
+        b &= b - 1;
+        const uint32_t e = static_cast<uint32_t>(w * 32 + bit);
+        sp_entry[k] = e;
+        sp_first[k] = e;
+        sp_locus[k] = locus_of_entry(row_ptr, n_loci, e);
+        ++k;
+    }
 }
 
-__global__ void __launch_bounds__(TB) cand_fill_kernel(const uint32_t *__restrict__ eread,
-                                                       const uint8_t *__restrict__ cand,
-                                                       const uint64_t *__restrict__ c_off /* per read, scan of clen */,
-                                                       uint64_t n_entries, uint32_t *__restrict__ cursor /* per read */,
-                                                       uint32_t *__restrict__ c_list) {
-    const uint64_t e = static_cast<uint64_t>(blockIdx.x) * TB + threadIdx.x;
-    if (e >= n_entries) {
+// one sweep of "first entry of my read = smallest entry linked to me"; two sweeps settle every read
+// whose entries all lie in the window of its first locus, a third one only verifies
+__global__ void __launch_bounds__(TB) link_min_kernel(const uint2 *__restrict__ links, uint64_t n_links,
+                                                      const uint32_t *__restrict__ bits, const uint64_t *__restrict__ rank,
+                                                      uint32_t *__restrict__ sp_first, int *__restrict__ changed) {
+    const uint64_t i = static_cast<uint64_t>(blockIdx.x) * TB + threadIdx.x;
+    if (i >= n_links) {
         return;
     }
-    const uint32_t r = eread[e];
-    if (cand[r]) {
-        const uint32_t k = atomicAdd(&cursor[r], 1u);
-        c_list[c_off[r] + k] = static_cast<uint32_t>(e);
+    const uint2 r = links[i];
+    const uint32_t sx = sid_of(bits, rank, r.x), sy = sid_of(bits, rank, r.y);
+    const uint32_t fx = sp_first[sx], fy = sp_first[sy];
+    const uint32_t m = min(fx, fy);
+    if (fx != m) {
+        atomicMin(&sp_first[sx], m);
+        *changed = 1;
+    }
+    if (fy != m) {
+        atomicMin(&sp_first[sy], m);
+        *changed = 1;
     }
 }
 
-// One thread per candidate read: sort its entries (entry order = the order in which the reference
-// meets them), replay the insertion rules (similarity_matrix.cpp:383-402) and leave the stored
-// (locus, base) list in place. nst[r] = number of loci the read keeps.
-__global__ void __launch_bounds__(TB) mate_rule_kernel(const uint8_t *__restrict__ cand,
-                                                       const uint64_t *__restrict__ c_off, uint64_t n_reads,
-                                                       uint32_t *__restrict__ c_list /* in: entries, out: stored loci */,
-                                                       uint8_t *__restrict__ c_base, const uint32_t *__restrict__ eloc,
-                                                       const uint16_t *__restrict__ gid_base,
-                                                       const uint32_t *__restrict__ position,
-                                                       const uint32_t *__restrict__ r_startloc, uint32_t L,
-                                                       uint8_t *__restrict__ edrop, uint32_t *__restrict__ nst,
+__global__ void __launch_bounds__(TB) group_count_kernel(const uint32_t *__restrict__ bits, const uint64_t *__restrict__ rank,
+                                                         const uint32_t *__restrict__ sp_first, uint64_t n_special,
+                                                         uint32_t *__restrict__ sp_head, uint32_t *__restrict__ g_cnt) {
+    const uint64_t s = static_cast<uint64_t>(blockIdx.x) * TB + threadIdx.x;
+    if (s < n_special) {
+        const uint32_t h = sid_of(bits, rank, sp_first[s]);
+        sp_head[s] = h;
+        atomicAdd(&g_cnt[h], 1u);
+    }
+}
+
+__global__ void __launch_bounds__(TB) group_fill_kernel(const uint32_t *__restrict__ sp_head,
+                                                        const uint32_t *__restrict__ sp_locus,
+                                                        const uint64_t *__restrict__ g_off, uint64_t n_special,
+                                                        uint32_t *__restrict__ cursor, uint32_t *__restrict__ g_list,
+                                                        uint32_t *__restrict__ nf_locus) {
+    const uint64_t s = static_cast<uint64_t>(blockIdx.x) * TB + threadIdx.x;
+    if (s < n_special) {
+        const uint32_t h = sp_head[s];
+        const uint32_t k = atomicAdd(&cursor[h], 1u);
+        g_list[g_off[h] + k] = static_cast<uint32_t>(s);
+        if (h != s) {
+            atomicAdd(&nf_locus[sp_locus[s]], 1u); // an entry that does not create a read
+        }
+    }
+}
+
+// One thread per read with >= 2 entries: sort its entries (entry order = the order in which the
+// reference meets them), replay the insertion rules (similarity_matrix.cpp:383-402) and leave the
+// stored (locus, base) list in place. g_nst[head] = number of loci the read keeps.
+__global__ void __launch_bounds__(TB) mate_rule_kernel(const uint32_t *__restrict__ sp_head,
+                                                       const uint32_t *__restrict__ sp_entry,
+                                                       const uint32_t *__restrict__ sp_locus,
+                                                       const uint64_t *__restrict__ g_off, uint64_t n_special,
+                                                       uint32_t *__restrict__ g_list /* in: sids, out: stored loci */,
+                                                       uint8_t *__restrict__ g_base, const uint16_t *__restrict__ gid_base,
+                                                       const uint32_t *__restrict__ position, uint32_t L,
+                                                       uint8_t *__restrict__ sp_drop, uint32_t *__restrict__ g_nst,
                                                        int *__restrict__ err) {
-    const uint64_t r = static_cast<uint64_t>(blockIdx.x) * TB + threadIdx.x;
-    if (r >= n_reads || !cand[r]) {
+    const uint64_t h = static_cast<uint64_t>(blockIdx.x) * TB + threadIdx.x;
+    if (h >= n_special || sp_head[h] != h) {
         return;
     }
-    const uint64_t o = c_off[r];
-    const uint32_t n = static_cast<uint32_t>(c_off[r + 1] - o);
-    uint32_t *lst = c_list + o;
+    const uint64_t o = g_off[h];
+    const uint32_t n = static_cast<uint32_t>(g_off[h + 1] - o);
+    uint32_t *lst = g_list + o;
     for (uint32_t i = 1; i < n; ++i) { // insertion sort, n is tiny
         const uint32_t v = lst[i];
         uint32_t j = i;
@@ -314,42 +434,47 @@ __global__ void __launch_bounds__(TB) mate_rule_kernel(const uint8_t *__restrict
         }
         lst[j] = v;
     }
-    const uint32_t start_pos = position[r_startloc[r]];
+    if (lst[0] != h) {
+        atomicExch(err, SGPU_E_FRAGMENT_SPAN); // the linking did not converge: a chain of windows
+        g_nst[h] = 0;
+        return;
+    }
+    const uint32_t start_pos = position[sp_locus[h]];
     uint32_t n_st = 0;
-    uint32_t last_entry = 0; // entry that produced the last stored element
+    uint32_t last_sid = 0; // special entry that produced the last stored element
     for (uint32_t i = 0; i < n; ++i) {
-        const uint32_t e = lst[i];
-        const uint32_t loc = eloc[e];
-        const uint8_t base = gid_base[e] & 3;
+        const uint32_t s = lst[i];
+        const uint32_t loc = sp_locus[s];
+        const uint8_t base = gid_base[sp_entry[s]] & 3;
         if (position[loc] - start_pos >= L) {
             atomicExch(err, SGPU_E_FRAGMENT_SPAN);
         }
         if (n_st > 0 && lst[n_st - 1] == loc) { // read.pos.back() == pd.position (:387)
-            if (c_base[o + n_st - 1] != base) { // mates disagree: remove the stored base too (:390-393)
-                edrop[last_entry] = 1;
+            if (g_base[o + n_st - 1] != base) { // mates disagree: remove the stored base too (:390-393)
+                sp_drop[last_sid] = 1;
                 --n_st;
                 // the element below (if any) was produced by an entry we no longer track; it can only
                 // be popped by a further entry at ITS locus, which cannot come (loci are increasing)
             }
-            edrop[e] = 1;
+            sp_drop[s] = 1;
             continue;
         }
         // lst[0..n_st) is overwritten with stored loci; i >= n_st always holds
         lst[n_st] = loc;
-        c_base[o + n_st] = base;
-        last_entry = e;
+        g_base[o + n_st] = base;
+        last_sid = s;
         ++n_st;
     }
-    nst[r] = n_st;
+    g_nst[h] = n_st;
 }
 
 // readbase[l] = number of reads created before locus l (l = 0..n_loci)
 __global__ void __launch_bounds__(TB) readbase_kernel(const uint64_t *__restrict__ row_ptr,
-                                                      const uint64_t *__restrict__ rscan, uint64_t n_loci,
-                                                      uint64_t *__restrict__ readbase) {
+                                                      const uint64_t *__restrict__ nf_scan /* may be null */,
+                                                      uint64_t n_loci, uint64_t *__restrict__ readbase) {
     const uint64_t l = static_cast<uint64_t>(blockIdx.x) * TB + threadIdx.x;
     if (l <= n_loci) {
-        readbase[l] = rscan[row_ptr[l]];
+        readbase[l] = row_ptr[l] - (nf_scan ? nf_scan[l] : 0);
     }
 }
 
@@ -361,7 +486,7 @@ constexpr int CUT_CHUNK = 1024;
 __global__ void __launch_bounds__(CUT_THREADS) cutoff_kernel(const uint64_t *__restrict__ chr_ptr, uint32_t n_chr,
                                                              const uint32_t *__restrict__ position,
                                                              const uint64_t *__restrict__ readbase, uint32_t L,
-                                                             uint32_t num_threads, uint64_t *__restrict__ Kglob,
+                                                             uint32_t num_threads, uint64_t *__restrict__ n_tail_reads,
                                                              uint64_t *__restrict__ tail_locus) {
     __shared__ uint64_t s_u[CUT_CHUNK];
     __shared__ uint32_t s_j[CUT_CHUNK];
@@ -404,33 +529,42 @@ __global__ void __launch_bounds__(CUT_THREADS) cutoff_kernel(const uint64_t *__r
         __syncthreads();
     }
     if (threadIdx.x == 0) {
-        Kglob[c] = rb0 + front;
-        tail_locus[c] = jk; // reads with index >= K are exactly those created at loci >= jk
+        // reads with index >= K = rb0 + front are exactly those created at loci >= jk
+        n_tail_reads[c] = readbase[l1] - (rb0 + front);
+        tail_locus[c] = jk;
     }
 }
 
-__global__ void __launch_bounds__(TB) make_codes_kernel(
-        const uint32_t *__restrict__ eread, const uint32_t *__restrict__ efirst, const uint32_t *__restrict__ eloc,
-        const uint8_t *__restrict__ lchr, const uint16_t *__restrict__ gid_base, const uint32_t *__restrict__ r_cell,
-        const uint8_t *__restrict__ cand, const uint32_t *__restrict__ nst, const uint8_t *__restrict__ edrop,
-        const uint64_t *__restrict__ Kglob, uint64_t n_entries, uint32_t *__restrict__ code,
-        unsigned long long *__restrict__ stats /* [0]=dropped [1]=multi entries */) {
-    const uint64_t e = static_cast<uint64_t>(blockIdx.x) * TB + threadIdx.x;
-    uint32_t dropped = 0, multi = 0;
-    if (e < n_entries) {
-        const uint32_t r = eread[e];
-        if (edrop[e]) {
-            code[e] = CODE_DROPPED;
+__global__ void __launch_bounds__(TB) sp_finish_kernel(
+        const uint32_t *__restrict__ sp_head, const uint32_t *__restrict__ sp_entry, const uint32_t *__restrict__ sp_locus,
+        const uint8_t *__restrict__ sp_drop, const uint32_t *__restrict__ g_nst, const uint16_t *__restrict__ gid_base,
+        const uint8_t *__restrict__ lchr, const uint64_t *__restrict__ tail_locus, const uint32_t *__restrict__ gmap,
+        uint32_t n_groups, uint32_t num_cells, uint64_t n_special, uint32_t *__restrict__ sp_code,
+        unsigned long long *__restrict__ stats /* [0]=dropped [1]=multi reads */, int *__restrict__ err) {
+    const uint64_t s = static_cast<uint64_t>(blockIdx.x) * TB + threadIdx.x;
+    uint32_t dropped = 0, multi_head = 0;
+    if (s < n_special) {
+        const uint32_t h = sp_head[s];
+        const uint32_t multi = g_nst[h] >= 2 ? 1u : 0u;
+        multi_head = (h == s) & multi;
+        if (sp_drop[s]) {
+            sp_code[s] = CODE_DROPPED;
             dropped = 1;
         } else {
-            const uint32_t cell = r_cell[r];
-            const uint32_t base = gid_base[e] & 3u;
-            const uint32_t tail = r >= Kglob[lchr[eloc[e]]] ? 1u : 0u;
-            multi = (cand[r] && nst[r] >= 2) ? 1u : 0u;
-            code[e] = (cell << 4) | (base << 2) | (tail << 1) | multi;
+            // the read's cell is fixed by its first entry (similarity_matrix.cpp:379, :208-209)
+            const uint32_t gid = gid_base[sp_entry[h]] >> 2;
+            uint32_t cell = 0;
+            if (gid >= n_groups || (cell = gmap[gid]) >= num_cells) {
+                atomicExch(err, SGPU_E_CELL_RANGE);
+                cell = 0;
+            }
+            const uint32_t base = gid_base[sp_entry[s]] & 3u;
+            const uint32_t hl = sp_locus[h];
+            const uint32_t tail = hl >= tail_locus[lchr[hl]] ? 1u : 0u; // read created behind the cutoff
+            sp_code[s] = (cell << 4) | (base << 2) | (tail << 1) | multi;
         }
     }
-    const uint32_t bd = __ballot_sync(0xffffffffu, dropped), bm = __ballot_sync(0xffffffffu, multi);
+    const uint32_t bd = __ballot_sync(0xffffffffu, dropped), bm = __ballot_sync(0xffffffffu, multi_head);
     if ((threadIdx.x & 31) == 0) {
         if (bd) {
             atomicAdd(&stats[0], static_cast<unsigned long long>(__popc(bd)));
@@ -439,48 +573,38 @@ __global__ void __launch_bounds__(TB) make_codes_kernel(
             atomicAdd(&stats[1], static_cast<unsigned long long>(__popc(bm)));
         }
     }
-    (void)efirst;
 }
 
-// multi reads: flag + stored length
-__global__ void __launch_bounds__(TB) multi_flag_kernel(const uint8_t *__restrict__ cand, const uint32_t *__restrict__ nst,
-                                                        uint64_t n_reads, uint8_t *__restrict__ mflag,
-                                                        uint32_t *__restrict__ mlen) {
-    const uint64_t r = static_cast<uint64_t>(blockIdx.x) * TB + threadIdx.x;
-    if (r >= n_reads) {
-        return;
+// ---- dense codes (scatter path only) ----------------------------------------------------------------
+__global__ void __launch_bounds__(TB) dense_codes_kernel(const uint64_t *__restrict__ row_ptr,
+                                                         const uint16_t *__restrict__ gid_base,
+                                                         const uint8_t *__restrict__ lchr,
+                                                         const uint64_t *__restrict__ tail_locus,
+                                                         const uint32_t *__restrict__ gmap, uint32_t n_groups,
+                                                         uint32_t num_cells, uint64_t n_loci, uint32_t *__restrict__ code,
+                                                         int *__restrict__ err) {
+    for (uint64_t l = blockIdx.x; l < n_loci; l += gridDim.x) {
+        const uint64_t e0 = row_ptr[l], e1 = row_ptr[l + 1];
+        const uint32_t tail = l >= tail_locus[lchr[l]] ? 2u : 0u;
+        for (uint64_t e = e0 + threadIdx.x; e < e1; e += TB) {
+            const uint32_t gb = gid_base[e];
+            const uint32_t gid = gb >> 2;
+            uint32_t cell = 0;
+            if (gid >= n_groups || (cell = gmap[gid]) >= num_cells) {
+                atomicExch(err, SGPU_E_CELL_RANGE);
+                cell = 0;
+            }
+            code[e] = (cell << 4) | ((gb & 3u) << 2) | tail; // special entries are overwritten afterwards
+        }
     }
-    const bool m = cand[r] && nst[r] >= 2;
-    mflag[r] = m ? 1 : 0;
-    mlen[r] = m ? nst[r] : 0;
 }
 
-__global__ void __launch_bounds__(TB) multi_copy_kernel(const uint8_t *__restrict__ mflag,
-                                                        const uint64_t *__restrict__ midx /* scan of mflag */,
-                                                        const uint64_t *__restrict__ moff_r /* scan of mlen, per read */,
-                                                        const uint64_t *__restrict__ c_off, const uint32_t *__restrict__ c_list,
-                                                        const uint8_t *__restrict__ c_base, const uint32_t *__restrict__ nst,
-                                                        uint64_t n_reads, uint32_t *__restrict__ r_multi,
-                                                        uint64_t *__restrict__ m_off, uint32_t *__restrict__ m_locus,
-                                                        uint8_t *__restrict__ m_base) {
-    const uint64_t r = static_cast<uint64_t>(blockIdx.x) * TB + threadIdx.x;
-    if (r > n_reads) {
-        return;
-    }
-    if (r == n_reads) {
-        m_off[midx[n_reads]] = moff_r[n_reads];
-        return;
-    }
-    if (!mflag[r]) {
-        r_multi[r] = 0xFFFFFFFFu;
-        return;
-    }
-    const uint64_t m = midx[r], dst = moff_r[r], src = c_off[r];
-    r_multi[r] = static_cast<uint32_t>(m);
-    m_off[m] = dst;
-    for (uint32_t i = 0; i < nst[r]; ++i) {
-        m_locus[dst + i] = c_list[src + i];
-        m_base[dst + i] = c_base[src + i];
+__global__ void __launch_bounds__(TB) sp_codes_kernel(const uint32_t *__restrict__ sp_entry,
+                                                      const uint32_t *__restrict__ sp_code, uint64_t n_special,
+                                                      uint32_t *__restrict__ code) {
+    const uint64_t s = static_cast<uint64_t>(blockIdx.x) * TB + threadIdx.x;
+    if (s < n_special) {
+        code[sp_entry[s]] = sp_code[s];
     }
 }
 
@@ -505,184 +629,245 @@ int sgpu_link_reads(sgpu_ctx *ctx, const sgpu_pileup *p, uint32_t num_cells, uin
     if (num_cells >= (1u << 27)) {
         return sgpu_fail(ctx, SGPU_E_ARG, "num_cells too large");
     }
-    out->n_reads = out->n_multi = out->n_dropped = out->n_tail = out->n_multi_entries = 0;
-    SGPU_CUDA(ctx, out->code.alloc(E, st));
-    SGPU_CUDA(ctx, out->eread.alloc(E, st));
-    SGPU_CUDA(ctx, out->eloc.alloc(E, st));
-    if (E == 0) {
-        SGPU_CUDA(ctx, out->m_off.alloc(1, st));
-        SGPU_CUDA(ctx, cudaMemsetAsync(out->m_off.p, 0, sizeof(uint64_t), st));
+    out->n_reads = out->n_multi = out->n_dropped = out->n_tail = out->n_special = out->n_tail_loci = 0;
+    out->n_groups = n_groups;
+    out->num_cells = num_cells;
+    SGPU_CUDA(ctx, out->gmap.alloc(n_groups ? n_groups : 1, ctx));
+    SGPU_CUDA(ctx, cudaMemcpyAsync(out->gmap.p, h_group_id_to_pos, n_groups * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
+    const uint64_t W = E / 32 + 1; // bitmap words
+    SGPU_CUDA(ctx, out->sp_bits.alloc(W, ctx));
+    SGPU_CUDA(ctx, cudaMemsetAsync(out->sp_bits.p, 0, W * sizeof(uint32_t), st));
+    SGPU_CUDA(ctx, out->lchr.alloc(P ? P : 1, ctx));
+    SGPU_CUDA(ctx, out->tail_locus.alloc(p->n_chr ? p->n_chr : 1, ctx));
+    if (E == 0 || P == 0) {
+        // nothing to link; tail_locus = end of every chromosome
+        if (p->n_chr) {
+            SGPU_CUDA(ctx, cudaMemcpyAsync(out->tail_locus.p, p->d_chr_ptr + 1, p->n_chr * sizeof(uint64_t), cudaMemcpyDeviceToDevice, st));
+        }
+        SGPU_CUDA(ctx, out->tail_loci.alloc(1, ctx));
         return SGPU_OK;
     }
 
-    DevBuf<uint8_t> lchr, isfirst, edrop;
-    DevBuf<uint32_t> gmap, efirst, vals;
-    DevBuf<uint64_t> keys, rscan, readbase, Kglob, tail_locus;
-    DevBuf<int> d_err;
-    DevBuf<unsigned long long> d_stats;
-    SGPU_CUDA(ctx, lchr.alloc(P, st));
-    SGPU_CUDA(ctx, isfirst.alloc(E, st));
-    SGPU_CUDA(ctx, edrop.alloc(E, st));
-    SGPU_CUDA(ctx, gmap.alloc(n_groups ? n_groups : 1, st));
-    SGPU_CUDA(ctx, efirst.alloc(E, st));
-    SGPU_CUDA(ctx, rscan.alloc(E + 1, st));
-    SGPU_CUDA(ctx, readbase.alloc(P + 1, st));
-    SGPU_CUDA(ctx, Kglob.alloc(p->n_chr, st));
-    SGPU_CUDA(ctx, tail_locus.alloc(p->n_chr, st));
-    SGPU_CUDA(ctx, d_err.alloc(1, st));
-    SGPU_CUDA(ctx, d_stats.alloc(2, st));
-    SGPU_CUDA(ctx, cudaMemsetAsync(d_err.p, 0, sizeof(int), st));
-    SGPU_CUDA(ctx, cudaMemsetAsync(d_stats.p, 0, 2 * sizeof(unsigned long long), st));
-    SGPU_CUDA(ctx, cudaMemsetAsync(edrop.p, 0, E, st));
-    SGPU_CUDA(ctx, cudaMemcpyAsync(gmap.p, h_group_id_to_pos, n_groups * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
-
-    const unsigned locus_grid = static_cast<unsigned>(std::min<uint64_t>(ceil_div_u64(P, TB / 32), static_cast<uint64_t>(ctx->sm_count) * 32));
-    SGPU_LAUNCH(ctx, (locus_fill_kernel<<<locus_grid, TB, 0, st>>>(p->d_row_ptr, p->d_position, p->d_chr_ptr, p->n_chr, P, out->eloc.p, lchr.p, d_err.p)));
-
-    // ---- first entry of every read: windowed shared-memory hashing, or (loci too large for shared
-    // memory) a global open-addressing hash (chromosome, read id) -> first entry
+    SGPU_TRACE(ctx, "link: enter");
+    DevBuf<int> d_err;            // [0] error code, [1] "third sweep still changed something"
     DevBuf<unsigned int> d_maxn;
-    SGPU_CUDA(ctx, d_maxn.alloc(1, st));
+    DevBuf<WinCounters> d_ctr;
+    DevBuf<unsigned long long> d_stats;
+    DevBuf<uint64_t> readbase, n_tail_reads;
+    SGPU_CUDA(ctx, d_err.alloc(2, ctx));
+    SGPU_CUDA(ctx, d_maxn.alloc(1, ctx));
+    SGPU_CUDA(ctx, d_ctr.alloc(1, ctx));
+    SGPU_CUDA(ctx, d_stats.alloc(2, ctx));
+    SGPU_CUDA(ctx, readbase.alloc(P + 1, ctx));
+    SGPU_CUDA(ctx, n_tail_reads.alloc(p->n_chr, ctx));
+    SGPU_CUDA(ctx, cudaMemsetAsync(d_err.p, 0, 2 * sizeof(int), st));
     SGPU_CUDA(ctx, cudaMemsetAsync(d_maxn.p, 0, sizeof(unsigned int), st));
-    SGPU_LAUNCH(ctx, (max_locus_size_kernel<<<blocks_for(P), TB, 0, st>>>(p->d_row_ptr, P, d_maxn.p)));
-    SGPU_CUDA(ctx, cudaMemcpyAsync(&ctx->h_scratch[0], d_maxn.p, sizeof(unsigned int), cudaMemcpyDeviceToHost, st));
-    SGPU_CUDA(ctx, cudaStreamSynchronize(st));
-    const uint32_t max_n = static_cast<uint32_t>(ctx->h_scratch[0] & 0xFFFFFFFFu);
+    SGPU_CUDA(ctx, cudaMemsetAsync(d_ctr.p, 0, sizeof(WinCounters), st));
+    SGPU_CUDA(ctx, cudaMemsetAsync(d_stats.p, 0, 2 * sizeof(unsigned long long), st));
+
+    SGPU_LAUNCH(ctx, (locus_meta_kernel<<<blocks_for(P), TB, 0, st>>>(p->d_row_ptr, p->d_position, p->d_chr_ptr, p->n_chr, P,
+                                                                       out->lchr.p, d_maxn.p, d_err.p)));
+    uint32_t max_n = p->max_row;
+    if (max_n == 0) {
+        SGPU_CUDA(ctx, cudaMemcpyAsync(&ctx->h_scratch[0], d_maxn.p, sizeof(unsigned int), cudaMemcpyDeviceToHost, st));
+        SGPU_CUDA(ctx, cudaStreamSynchronize(st));
+        max_n = static_cast<uint32_t>(ctx->h_scratch[0] & 0xFFFFFFFFu);
+        p->max_row = max_n; // cached: the pileup is immutable
+    }
+
+    SGPU_TRACE(ctx, "link: allocs+meta");
+    // ---- links between entries of one read -----------------------------------------------------------
+    // table geometry: slots >= 4 x the largest locus if shared memory allows, never below 1.25 x
+    const uint32_t id_cap = (max_n + 1) & ~1u;
     uint32_t slots = 1024;
-    while (slots < max_n + max_n / 2) {
+    while (slots < 4ull * max_n && slots < 65536) {
         slots <<= 1;
     }
-    if (slots <= WIN_MAX_SLOTS) {
-        const size_t smem = static_cast<size_t>(slots) * 2 * sizeof(uint32_t);
-        SGPU_CUDA(ctx, cudaFuncSetAttribute(link_window_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-        SGPU_LAUNCH(ctx, (iota_kernel<<<blocks_for(E), TB, 0, st>>>(efirst.p, E)));
-        const unsigned per_sm = static_cast<unsigned>(std::max<size_t>(1, std::min<size_t>(4, (200 * 1024) / smem)));
-        const unsigned wgrid = static_cast<unsigned>(std::min<uint64_t>(P, static_cast<uint64_t>(ctx->sm_count) * per_sm));
-        SGPU_LAUNCH(ctx, (link_window_kernel<<<wgrid, WIN_THREADS, smem, st>>>(p->d_row_ptr, p->d_position, p->d_read_id, lchr.p,
-                                                                              p->d_chr_ptr, P, L, slots, efirst.p)));
-        SGPU_LAUNCH(ctx, (link_finish_kernel<<<blocks_for(E), TB, 0, st>>>(efirst.p, E, isfirst.p, d_err.p)));
-    } else {
-        uint64_t cap = 1024;
-        while (cap < 2 * E) {
-            cap <<= 1;
+    auto win_smem = [&](uint32_t s) { return static_cast<size_t>(id_cap) * 4 + REC_BUF * sizeof(uint2) + static_cast<size_t>(s) * 2; };
+    while (slots > 1024 && win_smem(slots) > WIN_SMEM_LIMIT) {
+        slots >>= 1;
+    }
+    // SECEDO_B200_FORCE_GLOBAL_HASH=1 forces the large-locus path (tests)
+    const char *force_global = getenv("SECEDO_B200_FORCE_GLOBAL_HASH");
+    const bool use_window = max_n <= WIN_MAX_ENTRIES && win_smem(slots) <= WIN_SMEM_LIMIT && 4ull * slots >= 5ull * max_n
+            && !(force_global && force_global[0] == '1');
+    const unsigned locus_grid = static_cast<unsigned>(std::min<uint64_t>(P, static_cast<uint64_t>(ctx->sm_count) * 16));
+
+    DevBuf<uint2> links;
+    uint64_t cap = std::max<uint64_t>(E / 8, 4096);
+    uint64_t NL = 0;
+    for (int attempt = 0; attempt < 2; ++attempt) {
+        SGPU_CUDA(ctx, links.alloc(cap, ctx));
+        SGPU_CUDA(ctx, cudaMemsetAsync(d_ctr.p, 0, sizeof(WinCounters), st));
+        if (use_window) {
+            const size_t smem = win_smem(slots);
+            SGPU_CUDA(ctx, cudaFuncSetAttribute(link_window_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+            const unsigned per_sm = static_cast<unsigned>(std::max<size_t>(1, std::min<size_t>(4, (224 * 1024) / (smem + 1280))));
+            const unsigned wgrid = static_cast<unsigned>(std::min<uint64_t>(P, static_cast<uint64_t>(ctx->sm_count) * per_sm));
+            SGPU_LAUNCH(ctx, (link_window_kernel<<<wgrid, WIN_THREADS, smem, st>>>(p->d_row_ptr, p->d_position, p->d_read_id, out->lchr.p,
+                                                                                  p->d_chr_ptr, P, L, slots, id_cap, links.p, cap, d_ctr.p)));
+        } else {
+            DevBuf<uint64_t> keys;
+            DevBuf<uint32_t> vals;
+            uint64_t hcap = 1024;
+            while (hcap < 2 * E) {
+                hcap <<= 1;
+            }
+            SGPU_CUDA(ctx, keys.alloc(hcap, ctx));
+            SGPU_CUDA(ctx, vals.alloc(hcap, ctx));
+            SGPU_CUDA(ctx, cudaMemsetAsync(keys.p, 0xFF, hcap * sizeof(uint64_t), st));
+            SGPU_CUDA(ctx, cudaMemsetAsync(vals.p, 0xFF, hcap * sizeof(uint32_t), st));
+            SGPU_LAUNCH(ctx, (ghash_insert_kernel<<<locus_grid, TB, 0, st>>>(p->d_row_ptr, p->d_read_id, out->lchr.p, P, keys.p, vals.p, hcap - 1)));
+            SGPU_LAUNCH(ctx, (ghash_emit_kernel<<<locus_grid, TB, 0, st>>>(p->d_row_ptr, p->d_read_id, out->lchr.p, P, keys.p, vals.p, hcap - 1,
+                                                                            links.p, cap, d_ctr.p)));
         }
-        SGPU_CUDA(ctx, keys.alloc(cap, st));
-        SGPU_CUDA(ctx, vals.alloc(cap, st));
-        SGPU_CUDA(ctx, cudaMemsetAsync(keys.p, 0xFF, cap * sizeof(uint64_t), st));
-        SGPU_CUDA(ctx, cudaMemsetAsync(vals.p, 0xFF, cap * sizeof(uint32_t), st));
-        SGPU_LAUNCH(ctx, (link_insert_kernel<<<blocks_for(E), TB, 0, st>>>(p->d_read_id, out->eloc.p, lchr.p, E, keys.p, vals.p, cap - 1, efirst.p)));
-        SGPU_LAUNCH(ctx, (link_first_kernel<<<blocks_for(E), TB, 0, st>>>(efirst.p, vals.p, E, isfirst.p)));
-        keys.release();
-        vals.release();
+        SGPU_CUDA(ctx, cudaGetLastError());
+        SGPU_CUDA(ctx, cudaMemcpyAsync(&ctx->h_scratch[0], d_ctr.p, sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
+        SGPU_CUDA(ctx, cudaStreamSynchronize(st));
+        NL = ctx->h_scratch[0];
+        if (NL <= cap) {
+            break;
+        }
+        if (attempt == 1) {
+            return sgpu_fail(ctx, SGPU_E_CUDA, "link list overflow on retry (%llu > %llu)", (unsigned long long)NL, (unsigned long long)cap);
+        }
+        cap = NL; // the list was too small: the count is exact, run once more
+    }
+
+    SGPU_TRACE(ctx, "link: window kernel");
+    // ---- special entries: numbering, first entry of the read, groups, mate rule -----------------------
+    uint64_t NS = 0;
+    DevBuf<uint32_t> nf_locus;
+    DevBuf<uint64_t> nf_scan;
+    if (NL) {
+        DevBuf<uint32_t> pc;
+        SGPU_CUDA(ctx, pc.alloc(W, ctx));
+        SGPU_CUDA(ctx, out->sp_rank.alloc(W + 1, ctx));
+        SGPU_LAUNCH(ctx, (mark_kernel<<<blocks_for(NL), TB, 0, st>>>(links.p, NL, out->sp_bits.p)));
+        SGPU_LAUNCH(ctx, (popc_kernel<<<blocks_for(W), TB, 0, st>>>(out->sp_bits.p, W, pc.p)));
+        SGPU_TRY(sgpu_scan_u32_u64(ctx, pc.p, out->sp_rank.p, W));
+        SGPU_CUDA(ctx, cudaMemcpyAsync(&ctx->h_scratch[0], out->sp_rank.p + W, sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
+        SGPU_CUDA(ctx, cudaStreamSynchronize(st));
+        NS = ctx->h_scratch[0];
+    }
+    SGPU_TRACE(ctx, "link: mark+rank");
+    out->n_special = NS;
+    if (NS) {
+        DevBuf<uint32_t> sp_first, g_cnt, cursor;
+        SGPU_CUDA(ctx, out->sp_entry.alloc(NS, ctx));
+        SGPU_CUDA(ctx, out->sp_locus.alloc(NS, ctx));
+        SGPU_CUDA(ctx, out->sp_head.alloc(NS, ctx));
+        SGPU_CUDA(ctx, out->sp_code.alloc(NS, ctx));
+        SGPU_CUDA(ctx, out->sp_drop.alloc(NS, ctx));
+        SGPU_CUDA(ctx, out->g_off.alloc(NS + 1, ctx));
+        SGPU_CUDA(ctx, out->g_list.alloc(NS, ctx));
+        SGPU_CUDA(ctx, out->g_base.alloc(NS, ctx));
+        SGPU_CUDA(ctx, out->g_nst.alloc(NS, ctx));
+        SGPU_CUDA(ctx, sp_first.alloc(NS, ctx));
+        SGPU_CUDA(ctx, g_cnt.alloc(NS, ctx));
+        SGPU_CUDA(ctx, cursor.alloc(NS, ctx));
+        SGPU_CUDA(ctx, nf_locus.alloc(P, ctx));
+        SGPU_CUDA(ctx, nf_scan.alloc(P + 1, ctx));
+        SGPU_CUDA(ctx, cudaMemsetAsync(g_cnt.p, 0, NS * sizeof(uint32_t), st));
+        SGPU_CUDA(ctx, cudaMemsetAsync(cursor.p, 0, NS * sizeof(uint32_t), st));
+        SGPU_CUDA(ctx, cudaMemsetAsync(out->g_nst.p, 0, NS * sizeof(uint32_t), st));
+        SGPU_CUDA(ctx, cudaMemsetAsync(out->sp_drop.p, 0, NS, st));
+        SGPU_CUDA(ctx, cudaMemsetAsync(nf_locus.p, 0, P * sizeof(uint32_t), st));
+        SGPU_LAUNCH(ctx, (sp_list_kernel<<<blocks_for(W), TB, 0, st>>>(out->sp_bits.p, out->sp_rank.p, W, p->d_row_ptr, P, out->sp_entry.p,
+                                                                        sp_first.p, out->sp_locus.p)));
+        for (int sweep = 0; sweep < 3; ++sweep) {
+            SGPU_LAUNCH(ctx, (link_min_kernel<<<blocks_for(NL), TB, 0, st>>>(links.p, NL, out->sp_bits.p, out->sp_rank.p, sp_first.p,
+                                                                             d_err.p + 1)));
+            if (sweep == 1) {
+                SGPU_CUDA(ctx, cudaMemsetAsync(d_err.p + 1, 0, sizeof(int), st)); // only the verifying sweep counts
+            }
+        }
+        SGPU_LAUNCH(ctx, (group_count_kernel<<<blocks_for(NS), TB, 0, st>>>(out->sp_bits.p, out->sp_rank.p, sp_first.p, NS, out->sp_head.p, g_cnt.p)));
+        SGPU_TRY(sgpu_scan_u32_u64(ctx, g_cnt.p, out->g_off.p, NS));
+        SGPU_LAUNCH(ctx, (group_fill_kernel<<<blocks_for(NS), TB, 0, st>>>(out->sp_head.p, out->sp_locus.p, out->g_off.p, NS, cursor.p,
+                                                                           out->g_list.p, nf_locus.p)));
+        SGPU_LAUNCH(ctx, (mate_rule_kernel<<<blocks_for(NS), TB, 0, st>>>(out->sp_head.p, out->sp_entry.p, out->sp_locus.p, out->g_off.p, NS,
+                                                                          out->g_list.p, out->g_base.p, p->d_gid_base, p->d_position, L,
+                                                                          out->sp_drop.p, out->g_nst.p, d_err.p)));
+        SGPU_TRY(sgpu_scan_u32_u64(ctx, nf_locus.p, nf_scan.p, P));
+    }
+    links.release();
+
+    SGPU_TRACE(ctx, "link: groups+mate rule");
+    // ---- cutoff K per chromosome ----------------------------------------------------------------------
+    SGPU_LAUNCH(ctx, (readbase_kernel<<<blocks_for(P + 1), TB, 0, st>>>(p->d_row_ptr, NS ? nf_scan.p : nullptr, P, readbase.p)));
+    SGPU_LAUNCH(ctx, (cutoff_kernel<<<p->n_chr, CUT_THREADS, 0, st>>>(p->d_chr_ptr, p->n_chr, p->d_position, readbase.p, L, num_threads,
+                                                                      n_tail_reads.p, out->tail_locus.p)));
+    if (NS) {
+        SGPU_LAUNCH(ctx, (sp_finish_kernel<<<blocks_for(NS), TB, 0, st>>>(out->sp_head.p, out->sp_entry.p, out->sp_locus.p, out->sp_drop.p,
+                                                                          out->g_nst.p, p->d_gid_base, out->lchr.p, out->tail_locus.p,
+                                                                          out->gmap.p, n_groups, num_cells, NS, out->sp_code.p, d_stats.p,
+                                                                          d_err.p)));
     }
     SGPU_CUDA(ctx, cudaGetLastError());
-    SGPU_TRY(sgpu_scan_u8_u64(ctx, isfirst.p, rscan.p, E));
-    SGPU_CUDA(ctx, cudaMemcpyAsync(&ctx->h_scratch[0], rscan.p + E, sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
-    SGPU_CUDA(ctx, cudaStreamSynchronize(st));
-    const uint64_t R = ctx->h_scratch[0];
-    out->n_reads = R;
 
-    // ---- per-read tables
-    DevBuf<uint32_t> r_cell, r_startloc, r_extra, clen, nst, cursor;
-    DevBuf<uint8_t> cand;
-    DevBuf<uint64_t> c_off;
-    SGPU_CUDA(ctx, r_cell.alloc(R, st));
-    SGPU_CUDA(ctx, r_startloc.alloc(R, st));
-    SGPU_CUDA(ctx, r_extra.alloc(R, st));
-    SGPU_CUDA(ctx, clen.alloc(R, st));
-    SGPU_CUDA(ctx, nst.alloc(R, st));
-    SGPU_CUDA(ctx, cursor.alloc(R, st));
-    SGPU_CUDA(ctx, cand.alloc(R, st));
-    SGPU_CUDA(ctx, c_off.alloc(R + 1, st));
-    SGPU_CUDA(ctx, cudaMemsetAsync(r_extra.p, 0, R * sizeof(uint32_t), st));
-    SGPU_CUDA(ctx, cudaMemsetAsync(cursor.p, 0, R * sizeof(uint32_t), st));
-    SGPU_CUDA(ctx, cudaMemsetAsync(nst.p, 0, R * sizeof(uint32_t), st));
-    SGPU_LAUNCH(ctx, (link_reads_kernel<<<blocks_for(E), TB, 0, st>>>(efirst.p, rscan.p, p->d_gid_base, out->eloc.p, gmap.p, n_groups, num_cells, E,
-                                                   out->eread.p, r_cell.p, r_startloc.p, r_extra.p, d_err.p)));
-    SGPU_LAUNCH(ctx, (cand_flag_kernel<<<blocks_for(R), TB, 0, st>>>(r_extra.p, R, cand.p, clen.p)));
-    SGPU_CUDA(ctx, cudaGetLastError());
-    SGPU_TRY(sgpu_scan_u32_u64(ctx, clen.p, c_off.p, R));
-    SGPU_CUDA(ctx, cudaMemcpyAsync(&ctx->h_scratch[0], c_off.p + R, sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
-    SGPU_CUDA(ctx, cudaStreamSynchronize(st));
-    const uint64_t CE = ctx->h_scratch[0];
-
-    DevBuf<uint32_t> c_list;
-    DevBuf<uint8_t> c_base;
-    SGPU_CUDA(ctx, c_list.alloc(CE ? CE : 1, st));
-    SGPU_CUDA(ctx, c_base.alloc(CE ? CE : 1, st));
-    if (CE) {
-        SGPU_LAUNCH(ctx, (cand_fill_kernel<<<blocks_for(E), TB, 0, st>>>(out->eread.p, cand.p, c_off.p, E, cursor.p, c_list.p)));
-        SGPU_LAUNCH(ctx, (mate_rule_kernel<<<blocks_for(R), TB, 0, st>>>(cand.p, c_off.p, R, c_list.p, c_base.p, out->eloc.p, p->d_gid_base,
-                                                      p->d_position, r_startloc.p, L, edrop.p, nst.p, d_err.p)));
-    }
-    SGPU_LAUNCH(ctx, (// ---- cutoff K per chromosome
-    readbase_kernel<<<blocks_for(P + 1), TB, 0, st>>>(p->d_row_ptr, rscan.p, P, readbase.p)));
-    SGPU_LAUNCH(ctx, (cutoff_kernel<<<p->n_chr, CUT_THREADS, 0, st>>>(p->d_chr_ptr, p->n_chr, p->d_position, readbase.p, L, num_threads, Kglob.p, tail_locus.p)));
-    SGPU_LAUNCH(ctx, (// ---- codes
-    make_codes_kernel<<<blocks_for(E), TB, 0, st>>>(out->eread.p, efirst.p, out->eloc.p, lchr.p, p->d_gid_base, r_cell.p, cand.p,
-                                                   nst.p, edrop.p, Kglob.p, E, out->code.p, d_stats.p)));
-    SGPU_CUDA(ctx, cudaGetLastError());
-
-    // ---- multi-locus read tables
-    DevBuf<uint8_t> mflag;
-    DevBuf<uint32_t> mlen;
-    DevBuf<uint64_t> midx, moff_r;
-    SGPU_CUDA(ctx, mflag.alloc(R, st));
-    SGPU_CUDA(ctx, mlen.alloc(R, st));
-    SGPU_CUDA(ctx, midx.alloc(R + 1, st));
-    SGPU_CUDA(ctx, moff_r.alloc(R + 1, st));
-    SGPU_LAUNCH(ctx, (multi_flag_kernel<<<blocks_for(R), TB, 0, st>>>(cand.p, nst.p, R, mflag.p, mlen.p)));
-    SGPU_TRY(sgpu_scan_u8_u64(ctx, mflag.p, midx.p, R));
-    SGPU_TRY(sgpu_scan_u32_u64(ctx, mlen.p, moff_r.p, R));
-    // scalars to the host: n_multi, total stored, error, stats, K per chromosome, reads per chromosome
-    std::vector<uint64_t> h_K(p->n_chr), h_rb(p->n_chr + 1), h_tl(p->n_chr);
-    SGPU_CUDA(ctx, cudaMemcpyAsync(h_tl.data(), tail_locus.p, p->n_chr * sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
-    SGPU_CUDA(ctx, cudaMemcpyAsync(&ctx->h_scratch[0], midx.p + R, sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
-    SGPU_CUDA(ctx, cudaMemcpyAsync(&ctx->h_scratch[1], moff_r.p + R, sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
-    SGPU_CUDA(ctx, cudaMemcpyAsync(&ctx->h_scratch[2], d_err.p, sizeof(int), cudaMemcpyDeviceToHost, st));
+    SGPU_TRACE(ctx, "link: cutoff+finish");
+    // scalars to the host: errors, stats, reads created, tail loci per chromosome
+    std::vector<uint64_t> h_nt(p->n_chr), h_tl(p->n_chr);
+    SGPU_CUDA(ctx, cudaMemcpyAsync(h_tl.data(), out->tail_locus.p, p->n_chr * sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
+    SGPU_CUDA(ctx, cudaMemcpyAsync(h_nt.data(), n_tail_reads.p, p->n_chr * sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
+    SGPU_CUDA(ctx, cudaMemcpyAsync(&ctx->h_scratch[2], d_err.p, 2 * sizeof(int), cudaMemcpyDeviceToHost, st));
     SGPU_CUDA(ctx, cudaMemcpyAsync(&ctx->h_scratch[4], d_stats.p, 2 * sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
-    SGPU_CUDA(ctx, cudaMemcpyAsync(h_K.data(), Kglob.p, p->n_chr * sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
+    SGPU_CUDA(ctx, cudaMemcpyAsync(&ctx->h_scratch[6], readbase.p + P, sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
     SGPU_CUDA(ctx, cudaStreamSynchronize(st));
     const int err = static_cast<int>(ctx->h_scratch[2] & 0xFFFFFFFFu);
+    const int unsettled = static_cast<int>(ctx->h_scratch[2] >> 32);
     if (err == SGPU_E_CELL_RANGE) {
         return sgpu_fail(ctx, err, "a group id is >= n_groups or maps to a cell >= num_cells (filter the pileup first)");
     }
     if (err == SGPU_E_POSITIONS) {
         return sgpu_fail(ctx, err, "positions are not strictly increasing inside a chromosome");
     }
-    if (err == SGPU_E_FRAGMENT_SPAN) {
-        return sgpu_fail(ctx, err, "a read id spans >= max_fragment_length (%u): undefined in the reference", L);
+    if (err == SGPU_E_FRAGMENT_SPAN || unsettled) {
+        return sgpu_fail(ctx, SGPU_E_FRAGMENT_SPAN, "a read id spans >= max_fragment_length (%u): undefined in the reference", L);
     }
-    const uint64_t NM = ctx->h_scratch[0], MS = ctx->h_scratch[1];
-    out->n_multi = NM;
     out->n_dropped = ctx->h_scratch[4];
-    out->n_multi_entries = ctx->h_scratch[5];
-    // tail reads = reads of each chromosome with index >= K
-    for (uint32_t c = 0; c < p->n_chr; ++c) {
-        SGPU_CUDA(ctx, cudaMemcpyAsync(&h_rb[c + 1], readbase.p + p->h_chr_ptr[c + 1], sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
-    }
-    SGPU_CUDA(ctx, cudaStreamSynchronize(st));
+    out->n_multi = ctx->h_scratch[5];
+    out->n_reads = ctx->h_scratch[6];
     std::vector<uint32_t> h_tail_loci;
     for (uint32_t c = 0; c < p->n_chr; ++c) {
-        out->n_tail += h_rb[c + 1] - h_K[c];
+        out->n_tail += h_nt[c];
         for (uint64_t l = h_tl[c]; l < p->h_chr_ptr[c + 1]; ++l) {
             h_tail_loci.push_back(static_cast<uint32_t>(l));
         }
     }
+    SGPU_TRACE(ctx, "link: scalars");
     out->n_tail_loci = h_tail_loci.size();
-    SGPU_CUDA(ctx, out->tail_loci.alloc(h_tail_loci.size() ? h_tail_loci.size() : 1, st));
+    SGPU_CUDA(ctx, out->tail_loci.alloc(h_tail_loci.size() ? h_tail_loci.size() : 1, ctx));
     if (!h_tail_loci.empty()) {
         SGPU_CUDA(ctx, cudaMemcpyAsync(out->tail_loci.p, h_tail_loci.data(), h_tail_loci.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
-        SGPU_CUDA(ctx, cudaStreamSynchronize(st));
+        SGPU_CUDA(ctx, cudaStreamSynchronize(st)); // h_tail_loci is pageable
     }
+    return SGPU_OK;
+}
 
-    SGPU_CUDA(ctx, out->r_multi.alloc(R, st));
-    SGPU_CUDA(ctx, out->m_off.alloc(NM + 1, st));
-    SGPU_CUDA(ctx, out->m_locus.alloc(MS ? MS : 1, st));
-    SGPU_CUDA(ctx, out->m_base.alloc(MS ? MS : 1, st));
-    SGPU_LAUNCH(ctx, (multi_copy_kernel<<<blocks_for(R + 1), TB, 0, st>>>(mflag.p, midx.p, moff_r.p, c_off.p, c_list.p, c_base.p, nst.p, R,
-                                                       out->r_multi.p, out->m_off.p, out->m_locus.p, out->m_base.p)));
+// dense per-entry codes for the pair-scatter kernel
+int sgpu_link_dense_codes(sgpu_ctx *ctx, const sgpu_pileup *p, LinkResult *lr) {
+    cudaStream_t st = ctx->stream;
+    const uint64_t E = p->n_entries, P = p->n_loci;
+    SGPU_CUDA(ctx, lr->code.alloc(E ? E : 1, ctx));
+    if (E == 0 || P == 0) {
+        return SGPU_OK;
+    }
+    DevBuf<int> d_err;
+    SGPU_CUDA(ctx, d_err.alloc(1, ctx));
+    SGPU_CUDA(ctx, cudaMemsetAsync(d_err.p, 0, sizeof(int), st));
+    const unsigned grid = static_cast<unsigned>(std::min<uint64_t>(P, static_cast<uint64_t>(ctx->sm_count) * 16));
+    SGPU_LAUNCH(ctx, (dense_codes_kernel<<<grid, TB, 0, st>>>(p->d_row_ptr, p->d_gid_base, lr->lchr.p, lr->tail_locus.p, lr->gmap.p,
+                                                              lr->n_groups, lr->num_cells, P, lr->code.p, d_err.p)));
+    if (lr->n_special) {
+        SGPU_LAUNCH(ctx, (sp_codes_kernel<<<blocks_for(lr->n_special), TB, 0, st>>>(lr->sp_entry.p, lr->sp_code.p, lr->n_special, lr->code.p)));
+    }
     SGPU_CUDA(ctx, cudaGetLastError());
-    SGPU_CUDA(ctx, cudaStreamSynchronize(st)); // temporaries are released by the destructors below
+    SGPU_CUDA(ctx, cudaMemcpyAsync(&ctx->h_scratch[0], d_err.p, sizeof(int), cudaMemcpyDeviceToHost, st));
+    SGPU_CUDA(ctx, cudaStreamSynchronize(st));
+    if (static_cast<int>(ctx->h_scratch[0] & 0xFFFFFFFFu) != 0) {
+        return sgpu_fail(ctx, SGPU_E_CELL_RANGE, "a group id is >= n_groups or maps to a cell >= num_cells (filter the pileup first)");
+    }
     return SGPU_OK;
 }

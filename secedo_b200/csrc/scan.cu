@@ -129,7 +129,7 @@ int scan_impl(sgpu_ctx *ctx, const T *in, uint64_t *out, uint64_t n) {
     }
     const uint64_t nb = ceil_div_u64(n, SCAN_TILE);
     DevBuf<uint64_t> sums;
-    SGPU_CUDA(ctx, sums.alloc(nb, st));
+    SGPU_CUDA(ctx, sums.alloc(nb, ctx));
     SGPU_LAUNCH(ctx, (scan_reduce_kernel<T><<<static_cast<unsigned>(nb), SCAN_THREADS, 0, st>>>(in, n, sums.p)));
     SGPU_LAUNCH(ctx, (scan_sums_kernel<<<1, SCAN_THREADS, 0, st>>>(sums.p, nb, out + n)));
     SGPU_LAUNCH(ctx, (scan_apply_kernel<T><<<static_cast<unsigned>(nb), SCAN_THREADS, 0, st>>>(in, n, sums.p, out)));

@@ -113,7 +113,7 @@ int sgpu_scatter_pairs(sgpu_ctx *ctx, const sgpu_pileup *p, const LinkResult &lr
         return SGPU_OK;
     }
     DevBuf<unsigned long long> d_np;
-    SGPU_CUDA(ctx, d_np.alloc(1, st));
+    SGPU_CUDA(ctx, d_np.alloc(1, ctx));
     SGPU_CUDA(ctx, cudaMemsetAsync(d_np.p, 0, sizeof(unsigned long long), st));
     // tail x tail pairs only exist at the loci behind the cutoff of each chromosome
     const uint64_t n_loci = only_tail_pairs ? lr.n_tail_loci : p->n_loci;

@@ -169,12 +169,12 @@ extern "C" int sgpu_synth_pileup(sgpu_ctx *ctx, const sgpu_synth_params *sp, sgp
     for (uint32_t c = 0; c <= sp->n_chr; ++c) {
         pl->h_chr_ptr[c] = static_cast<uint64_t>(c) * sp->loci_per_chr;
     }
-    SGPU_CUDA(ctx, cudaMallocAsync(reinterpret_cast<void **>(&pl->d_chr_ptr), (sp->n_chr + 1) * sizeof(uint64_t), st));
+    SGPU_CUDA(ctx, sgpu_dev_alloc(ctx, reinterpret_cast<void **>(&pl->d_chr_ptr), (sp->n_chr + 1) * sizeof(uint64_t)));
     SGPU_CUDA(ctx, cudaMemcpyAsync(pl->d_chr_ptr, pl->h_chr_ptr, (sp->n_chr + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, st));
-    SGPU_CUDA(ctx, cudaMallocAsync(reinterpret_cast<void **>(&pl->d_row_ptr), (P + 1) * sizeof(uint64_t), st));
-    SGPU_CUDA(ctx, cudaMallocAsync(reinterpret_cast<void **>(&pl->d_position), std::max<uint64_t>(P, 1) * sizeof(uint32_t), st));
+    SGPU_CUDA(ctx, sgpu_dev_alloc(ctx, reinterpret_cast<void **>(&pl->d_row_ptr), (P + 1) * sizeof(uint64_t)));
+    SGPU_CUDA(ctx, sgpu_dev_alloc(ctx, reinterpret_cast<void **>(&pl->d_position), std::max<uint64_t>(P, 1) * sizeof(uint32_t)));
     DevBuf<uint32_t> cnt;
-    SGPU_CUDA(ctx, cnt.alloc(std::max<uint64_t>(P, 1), st));
+    SGPU_CUDA(ctx, cnt.alloc(std::max<uint64_t>(P, 1), ctx));
     const unsigned grid = static_cast<unsigned>(ceil_div_u64(std::max<uint64_t>(P, 1) * 32, TB));
     SGPU_LAUNCH(ctx, (synth_count_kernel<<<grid, TB, 0, st>>>(p, P, cnt.p, pl->d_position)));
     SGPU_CUDA(ctx, cudaGetLastError());
@@ -185,8 +185,8 @@ extern "C" int sgpu_synth_pileup(sgpu_ctx *ctx, const sgpu_synth_params *sp, sgp
     if (pl->n_entries >= 0xFFFFFFF0ull) {
         return sgpu_fail(ctx, SGPU_E_ARG, "synthetic pileup too large for 32-bit read ids");
     }
-    SGPU_CUDA(ctx, cudaMallocAsync(reinterpret_cast<void **>(&pl->d_read_id), std::max<uint64_t>(pl->n_entries, 1) * sizeof(uint32_t), st));
-    SGPU_CUDA(ctx, cudaMallocAsync(reinterpret_cast<void **>(&pl->d_gid_base), std::max<uint64_t>(pl->n_entries, 1) * sizeof(uint16_t), st));
+    SGPU_CUDA(ctx, sgpu_dev_alloc(ctx, reinterpret_cast<void **>(&pl->d_read_id), std::max<uint64_t>(pl->n_entries, 1) * sizeof(uint32_t)));
+    SGPU_CUDA(ctx, sgpu_dev_alloc(ctx, reinterpret_cast<void **>(&pl->d_gid_base), std::max<uint64_t>(pl->n_entries, 1) * sizeof(uint16_t)));
     SGPU_LAUNCH(ctx, (synth_fill_kernel<<<grid, TB, 0, st>>>(p, P, pl->d_row_ptr, pl->d_read_id, pl->d_gid_base)));
     SGPU_CUDA(ctx, cudaGetLastError());
     SGPU_CUDA(ctx, cudaStreamSynchronize(st));

@@ -205,11 +205,24 @@ def test_auto_path_and_stats(gpu_ctx):
     assert gpu_ctx.launch_count() > n0
 
 
-def test_huge_loci_use_global_hash_linking(gpu_ctx):
-    """loci with more entries than the shared-memory window hash holds fall back to the global hash"""
+def test_huge_loci(gpu_ctx):
+    """loci of > 11 000 entries: the shared-memory link table runs at its largest geometry"""
     cfg = SynthConfig(n_cells=3000, coverage=4.0, n_loci=8, n_chr=1, frac_somatic=1.0, frac_germline=0.0,
                       p_multi=0.05, p_mate=0.02, seed=51)
     p = make_pileup(cfg)
     assert np.diff(p.row_ptr.astype(np.int64)).max() > 11000
     ident = np.arange(cfg.n_cells, dtype=np.uint32)
     check_counts(gpu_ctx, p, cfg.n_cells, 1000, ident, 0.01, 0.5, 0.01, 1, "gemm")
+
+
+@pytest.mark.parametrize("path", PATHS)
+def test_global_hash_linking(gpu_ctx, path, monkeypatch):
+    """loci too large for the shared-memory link table (> ~26 000 entries) are linked through a global
+    (chromosome, read id) hash; forced here on a small case so that the oracle can follow"""
+    monkeypatch.setenv("SECEDO_B200_FORCE_GLOBAL_HASH", "1")
+    cfg = SynthConfig(n_cells=60, coverage=0.3, n_loci=900, n_chr=3, p_multi=0.45, p_mate=0.15, theta=0.02, seed=8)
+    p = make_pileup(cfg)
+    ident = np.arange(cfg.n_cells, dtype=np.uint32)
+    f, _ = api.Filter(0.01, 4, gpu_ctx).filter(p, ident, "", 1)
+    st, o = check_counts(gpu_ctx, f, cfg.n_cells, 1000, ident, 0.01, 0.5, 0.01, 2, path)
+    assert st["n_multi_reads"] > 0 and st["n_dropped_entries"] > 0
