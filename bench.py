@@ -210,7 +210,9 @@ def main_ours(args):
     w = WORKLOAD
     N = w["n_cells"]
     ctx = api.Context(local_rank)
-    stream = torch.cuda.current_stream()
+    # one explicit stream for everything: the library's kernels, the NCCL reduce and the timing events
+    stream = torch.cuda.Stream(device)
+    torch.cuda.set_stream(stream)
     ctx.set_stream(stream.cuda_stream)
     ident = np.arange(N, dtype=np.uint32)
 

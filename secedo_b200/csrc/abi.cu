@@ -153,22 +153,26 @@ void sgpu_shutdown(sgpu_ctx *ctx) {
     if (!ctx) {
         return;
     }
-    if (ctx->own_stream) {
+    if (ctx->own_stream) { // contexts that failed in sgpu_init carry only the error text
+        cudaSetDevice(ctx->device);
+        cudaStreamSynchronize(ctx->stream);
+        sgpu_dev_release_cache(ctx);
+        for (auto &b : ctx->live_blocks) { // objects the caller never freed
+            cudaFree(b.first);
+        }
+        ctx->live_blocks.clear();
+        if (ctx->tile_cache) {
+            cudaFree(ctx->tile_cache);
+        }
+        if (ctx->h_scratch) {
+            cudaFreeHost(ctx->h_scratch);
+        }
+        if (ctx->d_scratch) {
+            cudaFree(ctx->d_scratch);
+        }
+        ctx->stream = nullptr;
         cudaStreamSynchronize(ctx->own_stream);
         cudaStreamDestroy(ctx->own_stream);
-    }
-    if (ctx->h_scratch) {
-        cudaFreeHost(ctx->h_scratch);
-    }
-    if (ctx->d_scratch) {
-        cudaFree(ctx->d_scratch);
-    }
-    if (ctx->tile_cache) {
-        cudaFree(ctx->tile_cache);
-    }
-    sgpu_dev_release_cache(ctx);
-    for (auto &b : ctx->live_blocks) { // objects the caller never freed
-        cudaFree(b.first);
     }
     delete ctx;
 }

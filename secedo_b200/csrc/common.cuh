@@ -177,6 +177,15 @@ struct LinkResult {
     DevBuf<uint8_t> g_base;     // stored bases
     DevBuf<uint32_t> g_nst;     // per head: number of loci the read keeps after the mate rule
     uint64_t n_special = 0;
+    // candidates of the multi-locus correction: surviving entries of reads that keep >= 2 loci and keep
+    // one AFTER the entry's own locus (a pair is accounted at its first common locus, so it needs a
+    // later one). Compact, in entry order; the count stays on the device (me_idx[n_special]).
+    DevBuf<uint64_t> me_idx;    // scan of the candidate flags
+    DevBuf<uint32_t> me_code;   // cell << 4 | base << 2 | tail << 1 | 1
+    DevBuf<uint32_t> me_locus;
+    DevBuf<uint32_t> me_pos;    // index into g_list / g_base of the element stored for this locus
+    DevBuf<uint32_t> me_beg;    // stored list of the read: [me_beg, me_end)
+    DevBuf<uint32_t> me_end;
     // per locus / chromosome
     DevBuf<uint8_t> lchr;        // chromosome of every locus
     DevBuf<uint64_t> tail_locus; // per chromosome: reads created at loci >= this one have index >= K

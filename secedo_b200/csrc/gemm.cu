@@ -24,6 +24,7 @@
 #include <cuda.h>
 
 #include <algorithm>
+#include <cstdlib>
 #include <vector>
 
 namespace {
@@ -39,6 +40,24 @@ constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
 constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /* alignment slack */ + 256 /* barriers */;
 constexpr int GEMM_THREADS = 192;  // 6 warps
 constexpr uint32_t TMEM_COLS = 512;
+
+// Panel layout. One 128-byte row per (cell, k-block of 32 loci). The rows of CK consecutive k-blocks
+// form a chunk [chunk][cell][k-block in chunk]: the ~1 200 loci that are staged concurrently then touch
+// a few tens of MB of address space (2 MB pages: a handful of TLB entries) instead of one row in each of
+// the 8 192 cell stripes of a [cell][K] matrix, 128 KB apart, which made the staging atomics TLB bound.
+// The GEMM reads the same buffer through a 3-D tensor map (bytes in chunk row, cell, chunk).
+struct PanelLayout {
+    uint32_t ck_shift;    // log2(k-blocks per chunk)
+    uint32_t cell_words;  // 32-bit words between consecutive cells of a chunk: an odd number of 128-byte lines
+    uint64_t chunk_words; // words per chunk = n_pad * cell_words
+    __host__ __device__ uint64_t row(uint32_t cell, uint32_t kb) const { // first word of the row (cell, kb)
+        const uint32_t ch = kb >> ck_shift, kbi = kb - (ch << ck_shift);
+        return ch * chunk_words + static_cast<uint64_t>(cell) * cell_words + kbi * 32u;
+    }
+    __host__ __device__ uint64_t word(uint32_t cell, uint32_t col) const { // staged counts of (cell, locus col)
+        return row(cell, col >> 5) + (col & 31u);
+    }
+};
 
 // ------------------------------------------------------------------------------------------------
 // staging
@@ -56,47 +75,94 @@ __device__ __forceinline__ void add_count(uint32_t *__restrict__ U, uint64_t wor
     }
 }
 
-// entries that are the only entry of their read, loci [l0, l1): one block per locus
+// entries that are the only entry of their read, loci [l0, l1): one block per locus. Four entries per
+// thread are in flight (all loads first, then the atomics, then the range checks): the chain
+// gid_base -> group map -> atomic is three dependent memory round trips.
+template <bool RETURNING>
 __global__ void __launch_bounds__(256) stage_main_kernel(const uint64_t *__restrict__ row_ptr,
                                                          const uint16_t *__restrict__ gid_base,
                                                          const uint32_t *__restrict__ sp_bits,
                                                          const uint32_t *__restrict__ gmap, uint32_t n_groups,
-                                                         uint32_t n_cells, uint32_t l0, uint32_t l1,
-                                                         uint64_t row_words, uint32_t *__restrict__ U,
+                                                         uint32_t n_cells, uint32_t l0, uint32_t l1, uint32_t col0,
+                                                         PanelLayout pl, uint32_t *__restrict__ U,
                                                          int *__restrict__ err) {
+    constexpr int UNROLL = 4;
     for (uint32_t l = l0 + blockIdx.x; l < l1; l += gridDim.x) {
         const uint64_t e0 = row_ptr[l], e1 = row_ptr[l + 1];
-        const uint64_t col = l - l0; // k-block col / 32, word col % 32: the rows are K-contiguous
-        for (uint64_t e = e0 + threadIdx.x; e < e1; e += 256) {
-            if ((sp_bits[e >> 5] >> (e & 31)) & 1u) {
-                continue; // staged by stage_special_kernel
+        const uint64_t col = pl.word(0, l - col0); // + cell * cell_words
+        for (uint64_t eb = e0 + threadIdx.x; eb < e1; eb += 256 * UNROLL) {
+            uint32_t gb[UNROLL], cell[UNROLL], old[UNROLL];
+            bool live[UNROLL];
+#pragma unroll
+            for (int u = 0; u < UNROLL; ++u) {
+                const uint64_t e = eb + 256 * u;
+                live[u] = e < e1;
+                gb[u] = live[u] ? gid_base[e] : 0;
+                if (live[u] && ((sp_bits[e >> 5] >> (e & 31)) & 1u)) {
+                    live[u] = false; // staged by stage_special_kernel
+                }
             }
-            const uint32_t gb = gid_base[e];
-            const uint32_t gid = gb >> 2;
-            uint32_t cell;
-            if (gid >= n_groups || (cell = gmap[gid]) >= n_cells) {
-                atomicExch(err, SGPU_E_CELL_RANGE);
-                continue;
+#pragma unroll
+            for (int u = 0; u < UNROLL; ++u) {
+                const uint32_t gid = gb[u] >> 2;
+                cell[u] = 0;
+                if (live[u]) {
+                    if (gid >= n_groups || (cell[u] = gmap[gid]) >= n_cells) {
+                        atomicExch(err, SGPU_E_CELL_RANGE);
+                        live[u] = false;
+                    }
+                }
             }
-            add_count(U, static_cast<uint64_t>(cell) * row_words + col, gb & 3u, err);
+#pragma unroll
+            for (int u = 0; u < UNROLL; ++u) {
+                old[u] = 0;
+                if (live[u]) {
+                    const uint32_t inc = 1u << (8u * (gb[u] & 3u));
+                    uint32_t *w = &U[static_cast<uint64_t>(cell[u]) * pl.cell_words + col];
+                    if (RETURNING) {
+                        old[u] = atomicAdd(w, inc);
+                    } else {
+                        atomicAdd(w, inc); // RED
+                    }
+                }
+            }
+            if (RETURNING) {
+#pragma unroll
+                for (int u = 0; u < UNROLL; ++u) {
+                    if (live[u] && ((old[u] >> (8u * (gb[u] & 3u))) & 0xFFu) >= 127u) {
+                        atomicExch(err, SGPU_E_COUNT_RANGE); // > 127 reads of one cell at one locus: outside int8
+                    }
+                }
+            }
         }
     }
 }
 
-// entries of reads with several entries that survived the mate rule
+// entries of reads with several entries that survived the mate rule; sp_locus is ascending, the loci
+// [l0, l1) own a contiguous range of special entries that is found by bisection
 __global__ void __launch_bounds__(256) stage_special_kernel(const uint32_t *__restrict__ sp_code,
                                                             const uint32_t *__restrict__ sp_locus, uint64_t n_special,
-                                                            uint32_t l0, uint32_t l1, uint64_t row_words,
+                                                            uint32_t l0, uint32_t l1, uint32_t col0, PanelLayout pl,
                                                             uint32_t *__restrict__ U, int *__restrict__ err) {
-    const uint64_t s = static_cast<uint64_t>(blockIdx.x) * 256 + threadIdx.x;
-    if (s >= n_special) {
-        return;
+    uint64_t lo = 0, hi = n_special;
+    while (lo < hi) {
+        const uint64_t mid = (lo + hi) >> 1;
+        if (sp_locus[mid] < l0) {
+            lo = mid + 1;
+        } else {
+            hi = mid;
+        }
     }
-    const uint32_t c = sp_code[s], l = sp_locus[s];
-    if (c == CODE_DROPPED || l < l0 || l >= l1) {
-        return;
+    for (uint64_t s = lo + static_cast<uint64_t>(blockIdx.x) * 256 + threadIdx.x; s < n_special; s += static_cast<uint64_t>(gridDim.x) * 256) {
+        const uint32_t l = sp_locus[s];
+        if (l >= l1) {
+            break;
+        }
+        const uint32_t c = sp_code[s];
+        if (c != CODE_DROPPED) {
+            add_count(U, pl.word(code_cell(c), l - col0), code_base(c), err);
+        }
     }
-    add_count(U, static_cast<uint64_t>(code_cell(c)) * row_words + (l - l0), code_base(c), err);
 }
 
 // tail correction panel: column b of the panel holds ONLY the tail reads of locus tail_loci[b]. A
@@ -106,7 +172,7 @@ __global__ void __launch_bounds__(256) stage_tail_kernel(const uint64_t *__restr
                                                          const uint32_t *__restrict__ sp_bits,
                                                          const uint32_t *__restrict__ gmap, uint32_t n_groups,
                                                          uint32_t n_cells, const uint32_t *__restrict__ tail_loci,
-                                                         uint64_t row_words, uint32_t *__restrict__ U,
+                                                         PanelLayout pl, uint32_t *__restrict__ U,
                                                          int *__restrict__ err) {
     const uint32_t l = tail_loci[blockIdx.x];
     const uint64_t e0 = row_ptr[l], e1 = row_ptr[l + 1];
@@ -121,7 +187,7 @@ __global__ void __launch_bounds__(256) stage_tail_kernel(const uint64_t *__restr
             atomicExch(err, SGPU_E_CELL_RANGE);
             continue;
         }
-        add_count(U, static_cast<uint64_t>(cell) * row_words + blockIdx.x, gb & 3u, err);
+        add_count(U, pl.word(cell, blockIdx.x), gb & 3u, err);
     }
 }
 
@@ -129,7 +195,7 @@ __global__ void __launch_bounds__(256) stage_tail_special_kernel(const uint32_t 
                                                                  const uint32_t *__restrict__ sp_locus,
                                                                  uint64_t n_special, const uint32_t *__restrict__ tail_loci,
                                                                  uint32_t n_tail /* columns of this panel */,
-                                                                 uint64_t row_words, uint32_t *__restrict__ U,
+                                                                 PanelLayout pl, uint32_t *__restrict__ U,
                                                                  int *__restrict__ err) {
     const uint64_t s = static_cast<uint64_t>(blockIdx.x) * 256 + threadIdx.x;
     if (s >= n_special) {
@@ -149,25 +215,32 @@ __global__ void __launch_bounds__(256) stage_tail_special_kernel(const uint32_t 
         }
     }
     if (lo < n_tail && tail_loci[lo] == l) {
-        add_count(U, static_cast<uint64_t>(code_cell(c)) * row_words + lo, code_base(c), err);
+        add_count(U, pl.word(code_cell(c), lo), code_base(c), err);
     }
 }
 
 // In-place Hadamard transform of the rows: 8 consecutive lanes own one 128-byte row (one cell, one
 // k-block); each loads 4 loci x 4 base counts (16 B) and, after the whole warp has loaded, stores the
 // four plane words of those loci.
-__global__ void __launch_bounds__(256) transform_kernel(uint32_t *__restrict__ U, uint32_t kbs /* valid k-blocks */,
-                                                        uint64_t row_words, uint64_t n_items /* rows * kbs * 8 */,
-                                                        int *__restrict__ err) {
+__global__ void __launch_bounds__(256) transform_kernel(uint32_t *__restrict__ U, uint32_t kbs /* valid k-blocks */, uint32_t n_pad,
+                                                        PanelLayout pl, int *__restrict__ err) {
+    // consecutive 8-lane groups walk the k-blocks of a chunk row, then the cells of the chunk: contiguous
+    // memory. The grid covers whole chunks (a multiple of 32 threads), rows behind kbs are skipped.
     const uint64_t t = static_cast<uint64_t>(blockIdx.x) * 256 + threadIdx.x;
-    if (t >= n_items) {
-        return; // n_items is a multiple of 8 and of the 8-lane groups: whole groups leave together
-    }
     const uint32_t g = t & 7;
     const uint64_t rk = t >> 3;
-    const uint64_t row = rk / kbs, kb = rk - row * kbs;
-    uint32_t *r = U + row * row_words + kb * 32;
-    const uint4 v = *reinterpret_cast<const uint4 *>(r + 4 * g);
+    const uint32_t ck = 1u << pl.ck_shift;
+    const uint64_t per_chunk = static_cast<uint64_t>(n_pad) << pl.ck_shift; // rows of a chunk
+    const uint32_t ch = static_cast<uint32_t>(rk / per_chunk);
+    const uint64_t in_chunk = rk - ch * per_chunk;
+    const uint32_t cell = static_cast<uint32_t>(in_chunk >> pl.ck_shift);
+    const uint32_t kb = (ch << pl.ck_shift) + static_cast<uint32_t>(in_chunk & (ck - 1));
+    const bool valid = kb < kbs;
+    uint32_t *r = U + pl.row(cell, valid ? kb : 0);
+    uint4 v = make_uint4(0, 0, 0, 0);
+    if (valid) {
+        v = *reinterpret_cast<const uint4 *>(r + 4 * g);
+    }
     const uint32_t in[4] = { v.x, v.y, v.z, v.w };
     uint32_t w[4] = { 0, 0, 0, 0 }; // per plane, 4 loci packed
     bool bad = false;
@@ -185,9 +258,11 @@ __global__ void __launch_bounds__(256) transform_kernel(uint32_t *__restrict__ U
         w[3] |= static_cast<uint32_t>(u3 & 0xFF) << (8 * q);
     }
     __syncwarp(); // every lane of the row has its counts in registers before any plane word is written
+    if (valid) {
 #pragma unroll
-    for (int pl = 0; pl < 4; ++pl) {
-        r[pl * 8 + g] = w[pl];
+        for (int pl_i = 0; pl_i < 4; ++pl_i) {
+            r[pl_i * 8 + g] = w[pl_i];
+        }
     }
     if (bad) {
         atomicExch(err, SGPU_E_COUNT_RANGE);
@@ -221,10 +296,10 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
             "r"(parity)
             : "memory");
 }
-__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap *map, uint32_t bar, int32_t c0, int32_t c1) {
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap *map, uint32_t bar, int32_t c0, int32_t c1, int32_t c2) {
     asm volatile(
-            "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(dst),
-            "l"(map), "r"(bar), "r"(c0), "r"(c1)
+            "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(dst),
+            "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
             : "memory");
 }
 __device__ __forceinline__ bool elect_one() {
@@ -288,6 +363,7 @@ struct WorkList {
     uint32_t n_work;    // n_tiles * splits
     uint32_t kbs;       // k-blocks of the panel
     uint32_t per;       // k-blocks per split
+    uint32_t ck_shift;  // log2(k-blocks per chunk of the panel layout)
 };
 __device__ __forceinline__ WorkItem work_item(const WorkList &wl, uint32_t w) {
     const uint32_t split = w / wl.n_tiles;
@@ -344,9 +420,11 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) syrk_kernel(const __grid_cons
                     const uint32_t sa = smem_u32(smem + stage * STAGE_BYTES), sb = sa + A_BYTES;
                     const uint32_t bar = full0 + 8 * stage;
                     mbar_expect_tx(bar, STAGE_BYTES);
-                    tma_load_2d(sa, &map_u, bar, kb * KB_BYTES, wi.rb * BM);
-                    tma_load_2d(sb, &map_u, bar, kb * KB_BYTES, wi.cb * BN);
-                    tma_load_2d(sb + A_BYTES, &map_u, bar, kb * KB_BYTES, wi.cb * BN + 128);
+                    const int32_t ch = static_cast<int32_t>(kb >> wl.ck_shift);
+                    const int32_t kx = static_cast<int32_t>((kb - (static_cast<uint32_t>(ch) << wl.ck_shift)) * KB_BYTES);
+                    tma_load_3d(sa, &map_u, bar, kx, wi.rb * BM, ch);
+                    tma_load_3d(sb, &map_u, bar, kx, wi.cb * BN, ch);
+                    tma_load_3d(sb + A_BYTES, &map_u, bar, kx, wi.cb * BN + 128, ch);
                     if (++stage == STAGES) {
                         stage = 0;
                         phase ^= 1;
@@ -484,23 +562,30 @@ int sgpu_gemm_counts(sgpu_ctx *ctx, const sgpu_pileup *p, const LinkResult &lr, 
     panel = std::max<uint64_t>(panel, LOCI_PER_KB);
     panel = std::min<uint64_t>(panel, (P + LOCI_PER_KB - 1) / LOCI_PER_KB * LOCI_PER_KB);
     const uint64_t kbs_max = panel / LOCI_PER_KB;
-    const uint64_t row_bytes = kbs_max * KB_BYTES, row_words = row_bytes / 4;
+    PanelLayout pl;
+    pl.ck_shift = 5; // 32 k-blocks = 1 024 loci per chunk: 4 KB per cell, 33.8 MB per chunk at 8 192 cells
+    if (const char *env = getenv("SECEDO_B200_CHUNK_SHIFT")) {
+        pl.ck_shift = static_cast<uint32_t>(std::min(10, std::max(0, atoi(env))));
+    }
+    const uint32_t ck = 1u << pl.ck_shift;
+    pl.cell_words = (ck | 1u) * 32u; // odd number of lines: consecutive cells do not alias in the L2 sets
+    pl.chunk_words = static_cast<uint64_t>(n_pad) * pl.cell_words;
+    const uint64_t n_chunks_max = (kbs_max + ck - 1) / ck;
 
-    SGPU_TRACE(ctx, "gemm: enter");
     DevBuf<uint32_t> U;
     DevBuf<int> d_err;
-    SGPU_CUDA(ctx, U.alloc(static_cast<uint64_t>(n_pad) * row_words, ctx));
+    SGPU_CUDA(ctx, U.alloc(n_chunks_max * pl.chunk_words, ctx));
     SGPU_CUDA(ctx, d_err.alloc(2, ctx));
     SGPU_CUDA(ctx, cudaMemsetAsync(d_err.p, 0, 2 * sizeof(int), st));
-
     SGPU_TRACE(ctx, "gemm: alloc");
-    // tensor map over U: [n_pad rows][row_bytes], box = 128 rows x 128 bytes, 128B swizzle
+
+    // tensor map over U: [chunk][cell][ck x 128 bytes], box = 128 cells x 128 bytes, 128B swizzle
     CUtensorMap map;
     {
-        const cuuint64_t gdim[2] = { row_bytes, n_pad };
-        const cuuint64_t gstride[1] = { row_bytes };
-        const cuuint32_t box[2] = { KB_BYTES, 128 };
-        const cuuint32_t estr[2] = { 1, 1 };
+        const cuuint64_t gdim[3] = { static_cast<cuuint64_t>(ck) * KB_BYTES, n_pad, n_chunks_max };
+        const cuuint64_t gstride[2] = { static_cast<cuuint64_t>(pl.cell_words) * 4, pl.chunk_words * 4 };
+        const cuuint32_t box[3] = { KB_BYTES, 128, 1 };
+        const cuuint32_t estr[3] = { 1, 1, 1 };
         // resolved through the runtime so that the library does not link libcuda.so (it must load, and
         // fail loudly in sgpu_init, on a machine without a driver)
         typedef CUresult (*encode_fn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
@@ -512,7 +597,7 @@ int sgpu_gemm_counts(sgpu_ctx *ctx, const sgpu_pileup *p, const LinkResult &lr, 
         if (fn == nullptr || qres != cudaDriverEntryPointSuccess) {
             return sgpu_fail(ctx, SGPU_E_CUDA, "driver does not provide cuTensorMapEncodeTiled");
         }
-        CUresult r = reinterpret_cast<encode_fn>(fn)(&map, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, U.p, gdim, gstride, box, estr,
+        CUresult r = reinterpret_cast<encode_fn>(fn)(&map, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, U.p, gdim, gstride, box, estr,
                                             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
                                             CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         if (r != CUDA_SUCCESS) {
@@ -535,15 +620,20 @@ int sgpu_gemm_counts(sgpu_ctx *ctx, const sgpu_pileup *p, const LinkResult &lr, 
     };
     const uint32_t sms = static_cast<uint32_t>(ctx->sm_count);
     const unsigned sp_blocks = static_cast<unsigned>(ceil_div_u64(lr.n_special ? lr.n_special : 1, 256));
-    auto clear_panel = [&](uint32_t kbs) -> int {
-        SGPU_CUDA(ctx, cudaMemset2DAsync(U.p, row_bytes, 0, static_cast<size_t>(kbs) * KB_BYTES, n_pad, st));
+    // zero / Hadamard-transform in place the chunks that hold the first kbs k-blocks
+    auto clear_kbs = [&](uint32_t kbs) -> int {
+        const uint64_t chunks = (kbs + ck - 1) / ck;
+        SGPU_CUDA(ctx, cudaMemsetAsync(U.p, 0, chunks * pl.chunk_words * sizeof(uint32_t), st));
         return SGPU_OK;
     };
-    // transform + GEMM of the nl loci currently staged; sign -1 subtracts
+    auto transform_kbs = [&](uint32_t kbs) {
+        const uint64_t chunks = (kbs + ck - 1) / ck;
+        const uint64_t items = chunks * (static_cast<uint64_t>(n_pad) << pl.ck_shift) * 8; // a multiple of 256
+        SGPU_LAUNCH(ctx, (transform_kernel<<<static_cast<unsigned>(items / 256), 256, 0, st>>>(U.p, kbs, n_pad, pl, d_err.p)));
+    };
+    // GEMM of the nl loci currently staged; sign -1 subtracts
     auto gemm_panel = [&](uint64_t nl, int sign) -> int {
         const uint32_t kbs = static_cast<uint32_t>((nl + LOCI_PER_KB - 1) / LOCI_PER_KB);
-        const uint64_t items = static_cast<uint64_t>(n_pad) * kbs * 8;
-        SGPU_LAUNCH(ctx, (transform_kernel<<<static_cast<unsigned>(ceil_div_u64(items, 256)), 256, 0, st>>>(U.p, kbs, row_words, items, d_err.p)));
         // split K so that every SM has work even when there are few tiles
         uint32_t splits = 1;
         if (n_tiles < 2 * sms) {
@@ -553,6 +643,7 @@ int sgpu_gemm_counts(sgpu_ctx *ctx, const sgpu_pileup *p, const LinkResult &lr, 
         wl.tiles = d_tiles;
         wl.n_tiles = n_tiles;
         wl.kbs = kbs;
+        wl.ck_shift = pl.ck_shift;
         wl.per = (kbs + splits - 1) / splits;
         splits = (kbs + wl.per - 1) / wl.per; // no empty split
         wl.n_work = n_tiles * splits;
@@ -564,18 +655,29 @@ int sgpu_gemm_counts(sgpu_ctx *ctx, const sgpu_pileup *p, const LinkResult &lr, 
         ++ctx->n_syrk;
         return SGPU_OK;
     };
+    const char *env_red = getenv("SECEDO_B200_STAGE_RED"); // experiment: fire-and-forget atomics (no range check)
+    const bool stage_red = env_red && env_red[0] == '1';
     for (uint64_t l0 = 0; l0 < P; l0 += panel) {
         const uint64_t l1 = std::min<uint64_t>(P, l0 + panel);
         const uint64_t nl = l1 - l0;
+        const uint32_t kbs = static_cast<uint32_t>((nl + LOCI_PER_KB - 1) / LOCI_PER_KB);
         mark(); // [3k] staging begins
-        SGPU_TRY(clear_panel(static_cast<uint32_t>((nl + LOCI_PER_KB - 1) / LOCI_PER_KB)));
+        SGPU_TRY(clear_kbs(kbs));
         const unsigned grid = static_cast<unsigned>(std::min<uint64_t>(nl, static_cast<uint64_t>(sms) * 16));
-        SGPU_LAUNCH(ctx, (stage_main_kernel<<<grid, 256, 0, st>>>(p->d_row_ptr, p->d_gid_base, lr.sp_bits.p, lr.gmap.p, lr.n_groups, N,
-                                                                  static_cast<uint32_t>(l0), static_cast<uint32_t>(l1), row_words, U.p, d_err.p)));
+        if (stage_red) {
+            SGPU_LAUNCH(ctx, (stage_main_kernel<false><<<grid, 256, 0, st>>>(p->d_row_ptr, p->d_gid_base, lr.sp_bits.p, lr.gmap.p, lr.n_groups, N,
+                                                                             static_cast<uint32_t>(l0), static_cast<uint32_t>(l1),
+                                                                             static_cast<uint32_t>(l0), pl, U.p, d_err.p)));
+        } else {
+            SGPU_LAUNCH(ctx, (stage_main_kernel<true><<<grid, 256, 0, st>>>(p->d_row_ptr, p->d_gid_base, lr.sp_bits.p, lr.gmap.p, lr.n_groups, N,
+                                                                            static_cast<uint32_t>(l0), static_cast<uint32_t>(l1),
+                                                                            static_cast<uint32_t>(l0), pl, U.p, d_err.p)));
+        }
         if (lr.n_special) {
             SGPU_LAUNCH(ctx, (stage_special_kernel<<<sp_blocks, 256, 0, st>>>(lr.sp_code.p, lr.sp_locus.p, lr.n_special, static_cast<uint32_t>(l0),
-                                                                             static_cast<uint32_t>(l1), row_words, U.p, d_err.p)));
+                                                                             static_cast<uint32_t>(l1), static_cast<uint32_t>(l0), pl, U.p, d_err.p)));
         }
+        transform_kbs(kbs);
         SGPU_TRACE(ctx, "gemm: stage main");
         SGPU_TRY(gemm_panel(nl, +1));
     }
@@ -585,14 +687,16 @@ int sgpu_gemm_counts(sgpu_ctx *ctx, const sgpu_pileup *p, const LinkResult &lr, 
     // of the tail reads alone at those loci, with the same kernel and sign -1.
     for (uint64_t t0 = 0; t0 < lr.n_tail_loci; t0 += panel) {
         const uint64_t nl = std::min<uint64_t>(lr.n_tail_loci - t0, panel);
+        const uint32_t kbs = static_cast<uint32_t>((nl + LOCI_PER_KB - 1) / LOCI_PER_KB);
         mark();
-        SGPU_TRY(clear_panel(static_cast<uint32_t>((nl + LOCI_PER_KB - 1) / LOCI_PER_KB)));
+        SGPU_TRY(clear_kbs(kbs));
         SGPU_LAUNCH(ctx, (stage_tail_kernel<<<static_cast<unsigned>(nl), 256, 0, st>>>(p->d_row_ptr, p->d_gid_base, lr.sp_bits.p, lr.gmap.p, lr.n_groups,
-                                                                                       N, lr.tail_loci.p + t0, row_words, U.p, d_err.p)));
+                                                                                       N, lr.tail_loci.p + t0, pl, U.p, d_err.p)));
         if (lr.n_special) {
             SGPU_LAUNCH(ctx, (stage_tail_special_kernel<<<sp_blocks, 256, 0, st>>>(lr.sp_code.p, lr.sp_locus.p, lr.n_special, lr.tail_loci.p + t0,
-                                                                                  static_cast<uint32_t>(nl), row_words, U.p, d_err.p)));
+                                                                                  static_cast<uint32_t>(nl), pl, U.p, d_err.p)));
         }
+        transform_kbs(kbs);
         SGPU_TRY(gemm_panel(nl, -1));
     }
     SGPU_TRACE(ctx, "gemm: tail panels");

@@ -21,14 +21,15 @@ namespace {
 constexpr int TB = 256;
 
 struct MultiArgs {
-    uint64_t n_special;
-    const uint32_t *sp_code;  // per special entry: code (bit 0 = read keeps >= 2 loci) or CODE_DROPPED
-    const uint32_t *sp_locus;
-    const uint32_t *sp_head;  // first entry of the read: owner of the stored list
-    const uint64_t *g_off;
+    uint64_t n_special;       // upper bound of the number of candidates (launch size)
+    const uint64_t *n_me;     // device: number of candidates
+    const uint32_t *me_code;  // cell << 4 | base << 2 | tail << 1 | 1
+    const uint32_t *me_locus;
+    const uint32_t *me_pos;   // element of the read's stored list that belongs to this locus
+    const uint32_t *me_beg;   // stored list [me_beg, me_end) in g_list / g_base
+    const uint32_t *me_end;
     const uint32_t *g_list;   // stored loci, ascending
     const uint8_t *g_base;    // stored bases
-    const uint32_t *g_nst;    // per head: stored length
     int32_t *H2;              // 3 planes
     int32_t *H3;              // 4 planes
     double *spill;            // may be null
@@ -44,37 +45,37 @@ struct MultiArgs {
 };
 
 __global__ void __launch_bounds__(TB) multilocus_kernel(MultiArgs a) {
+    // the class histogram has a handful of hot bins: count per block, flush once
+    __shared__ uint32_t s_hist[SGPU_MAX_CLASS * SGPU_MAX_CLASS];
     const uint64_t ia = static_cast<uint64_t>(blockIdx.x) * TB + threadIdx.x;
-    unsigned long long local_pairs = 0;
-    uint32_t ca = CODE_DROPPED;
-    if (ia < a.n_special) {
-        ca = a.sp_code[ia];
+    const uint64_t n_me = *a.n_me;
+    if (static_cast<uint64_t>(blockIdx.x) * TB >= n_me) {
+        return; // whole block behind the last candidate
     }
-    if (ca != CODE_DROPPED && (ca & 1u)) {
-        const uint32_t loc = a.sp_locus[ia];
-        const uint32_t ha = a.sp_head[ia];
-        const uint64_t a0 = a.g_off[ha], a1 = a0 + a.g_nst[ha];
-        for (uint64_t ib = ia + 1; ib < a.n_special; ++ib) {
-            if (a.sp_locus[ib] != loc) {
+    for (uint32_t i = threadIdx.x; i < SGPU_MAX_CLASS * SGPU_MAX_CLASS; i += TB) {
+        s_hist[i] = 0;
+    }
+    __syncthreads();
+    unsigned long long local_pairs = 0;
+    if (ia < n_me) {
+        const uint32_t loc = a.me_locus[ia];
+        const uint32_t ca = a.me_code[ia];
+        const uint32_t a0 = a.me_beg[ia], ap = a.me_pos[ia], a1 = a.me_end[ia];
+        for (uint64_t ib = ia + 1; ib < n_me; ++ib) {
+            if (a.me_locus[ib] != loc) {
                 break;
             }
-            const uint32_t cb = a.sp_code[ib];
-            if (cb == CODE_DROPPED || !(cb & 1u)) {
-                continue;
-            }
+            const uint32_t cb = a.me_code[ib];
             if (code_cell(ca) == code_cell(cb) || (ca & cb & 2u)) {
                 continue; // same cell, or both reads behind the cutoff K
             }
-            const uint32_t hb = a.sp_head[ib];
-            const uint64_t b0 = a.g_off[hb], b1 = b0 + a.g_nst[hb];
-            // two-pointer merge over the stored loci (similarity_matrix.cpp:221-229)
-            uint32_t xs = 0, xd = 0, first_common = 0xFFFFFFFFu;
-            for (uint64_t i = a0, j = b0; i < a1 && j < b1;) {
+            const uint32_t b0 = a.me_beg[ib], bp = a.me_pos[ib], b1 = a.me_end[ib];
+            // two-pointer merge over the stored loci (similarity_matrix.cpp:221-229), the part behind this
+            // locus first: most pairs share nothing there and are single-locus overlaps (first order)
+            uint32_t xs = 0, xd = 0;
+            for (uint32_t i = ap + 1, j = bp + 1; i < a1 && j < b1;) {
                 const uint32_t la = a.g_list[i], lb = a.g_list[j];
                 if (la == lb) {
-                    if (first_common == 0xFFFFFFFFu) {
-                        first_common = la;
-                    }
                     a.g_base[i] == a.g_base[j] ? ++xs : ++xd;
                     ++i;
                     ++j;
@@ -84,9 +85,22 @@ __global__ void __launch_bounds__(TB) multilocus_kernel(MultiArgs a) {
                     ++j;
                 }
             }
-            if (first_common != loc || xs + xd < 2) {
-                continue; // accounted at an earlier shared locus, or a single-locus overlap
+            if (xs + xd == 0) {
+                continue;
             }
+            bool earlier = false; // a common locus before this one: the pair is accounted there
+            for (uint32_t i = a0, j = b0; i < ap && j < bp;) {
+                const uint32_t la = a.g_list[i], lb = a.g_list[j];
+                if (la == lb) {
+                    earlier = true;
+                    break;
+                }
+                la < lb ? ++i : ++j;
+            }
+            if (earlier) {
+                continue;
+            }
+            a.g_base[ap] == a.g_base[bp] ? ++xs : ++xd; // this locus
             if (xs >= SGPU_MAX_CLASS || xd >= SGPU_MAX_CLASS || xs >= a.L || xd >= a.L) {
                 atomicExch(a.err, SGPU_E_CLASS_RANGE);
                 continue;
@@ -96,7 +110,7 @@ __global__ void __launch_bounds__(TB) multilocus_kernel(MultiArgs a) {
             const uint64_t ij = static_cast<uint64_t>(lo) * a.n_cells + hi;
             if (!a.spill_only) {
                 ++local_pairs;
-                atomicAdd(&a.hist[xs * SGPU_MAX_CLASS + xd], 1ull);
+                atomicAdd(&s_hist[xs * SGPU_MAX_CLASS + xd], 1u);
                 if (order == 2) {
                     atomicAdd(&a.H2[static_cast<uint64_t>(xd) * a.nn + ij], 1);
                 } else if (order == 3) {
@@ -108,6 +122,12 @@ __global__ void __launch_bounds__(TB) multilocus_kernel(MultiArgs a) {
             if (order >= 4 && a.spill != nullptr) {
                 atomicAdd(&a.spill[ij], a.G[xs * SGPU_MAX_CLASS + xd]);
             }
+        }
+    }
+    __syncthreads();
+    for (uint32_t i = threadIdx.x; i < SGPU_MAX_CLASS * SGPU_MAX_CLASS; i += TB) {
+        if (s_hist[i]) {
+            atomicAdd(&a.hist[i], static_cast<unsigned long long>(s_hist[i]));
         }
     }
 #pragma unroll
@@ -151,13 +171,14 @@ int sgpu_multilocus(sgpu_ctx *ctx, const sgpu_pileup *p, const LinkResult &lr, s
 
     MultiArgs a;
     a.n_special = NS;
-    a.sp_code = lr.sp_code.p;
-    a.sp_locus = lr.sp_locus.p;
-    a.sp_head = lr.sp_head.p;
-    a.g_off = lr.g_off.p;
+    a.n_me = lr.me_idx.p + NS;
+    a.me_code = lr.me_code.p;
+    a.me_locus = lr.me_locus.p;
+    a.me_pos = lr.me_pos.p;
+    a.me_beg = lr.me_beg.p;
+    a.me_end = lr.me_end.p;
     a.g_list = lr.g_list.p;
     a.g_base = lr.g_base.p;
-    a.g_nst = lr.g_nst.p;
     a.H2 = c->i32 + PLANE_H2 * c->nn;
     a.H3 = c->i32 + PLANE_H3 * c->nn;
     a.spill = c->spill;

@@ -335,23 +335,46 @@ __device__ __forceinline__ uint32_t sid_of(const uint32_t *__restrict__ bits, co
     return static_cast<uint32_t>(rank[e >> 5]) + __popc(bits[e >> 5] & ((1u << (e & 31)) - 1u));
 }
 
+// word_locus[w] = locus of entry 32 w (the first entry of bitmap word w)
+__global__ void __launch_bounds__(TB) word_locus_kernel(const uint64_t *__restrict__ row_ptr, uint64_t n_loci,
+                                                        uint64_t n_words, uint32_t *__restrict__ word_locus) {
+    const int lane = threadIdx.x & 31;
+    const uint64_t warps_total = static_cast<uint64_t>(gridDim.x) * (TB / 32);
+    for (uint64_t l = static_cast<uint64_t>(blockIdx.x) * (TB / 32) + (threadIdx.x >> 5); l < n_loci; l += warps_total) {
+        const uint64_t e0 = row_ptr[l], e1 = l + 1 < n_loci ? row_ptr[l + 1] : n_words * 32;
+        // words whose first entry lies in [e0, e1)
+        for (uint64_t w = (e0 + 31) / 32 + lane; w * 32 < e1 && w < n_words; w += 32) {
+            word_locus[w] = static_cast<uint32_t>(l);
+        }
+    }
+}
+
 __global__ void __launch_bounds__(TB) sp_list_kernel(const uint32_t *__restrict__ bits, const uint64_t *__restrict__ rank,
                                                      uint64_t n_words, const uint64_t *__restrict__ row_ptr,
-                                                     uint64_t n_loci, uint32_t *__restrict__ sp_entry,
+                                                     const uint32_t *__restrict__ word_locus, uint32_t *__restrict__ sp_entry,
                                                      uint32_t *__restrict__ sp_first, uint32_t *__restrict__ sp_locus) {
     const uint64_t w = static_cast<uint64_t>(blockIdx.x) * TB + threadIdx.x;
     if (w >= n_words) {
         return;
     }
     uint32_t b = bits[w];
+    if (b == 0) {
+        return;
+    }
     uint64_t k = rank[w];
+    uint32_t l = word_locus[w];
+    uint64_t l_end = row_ptr[l + 1];
     while (b) {
         const uint32_t bit = __ffs(b) - 1;
         b &= b - 1;
         const uint32_t e = static_cast<uint32_t>(w * 32 + bit);
+        while (e >= l_end) { // entries are ascending: walk on to the locus that holds e
+            ++l;
+            l_end = row_ptr[l + 1];
+        }
         sp_entry[k] = e;
         sp_first[k] = e;
-        sp_locus[k] = locus_of_entry(row_ptr, n_loci, e);
+        sp_locus[k] = l;
         ++k;
     }
 }
@@ -575,6 +598,50 @@ __global__ void __launch_bounds__(TB) sp_finish_kernel(
     }
 }
 
+// ---- candidates of the multi-locus correction ---------------------------------------------------------
+__global__ void __launch_bounds__(TB) me_flag_kernel(const uint32_t *__restrict__ sp_code, const uint32_t *__restrict__ sp_head,
+                                                     const uint32_t *__restrict__ sp_locus, const uint64_t *__restrict__ g_off,
+                                                     const uint32_t *__restrict__ g_list, const uint32_t *__restrict__ g_nst,
+                                                     uint64_t n_special, uint32_t *__restrict__ flag, uint32_t *__restrict__ pos) {
+    const uint64_t s = static_cast<uint64_t>(blockIdx.x) * TB + threadIdx.x;
+    if (s >= n_special) {
+        return;
+    }
+    const uint32_t c = sp_code[s];
+    uint32_t f = 0;
+    if (c != CODE_DROPPED && (c & 1u)) {
+        const uint32_t h = sp_head[s], loc = sp_locus[s], n = g_nst[h];
+        const uint64_t o = g_off[h];
+        uint32_t i = 0;
+        while (i < n && g_list[o + i] != loc) { // a surviving entry's locus is stored exactly once
+            ++i;
+        }
+        f = i + 1 < n ? 1u : 0u;
+        pos[s] = static_cast<uint32_t>(o + i);
+    }
+    flag[s] = f;
+}
+
+__global__ void __launch_bounds__(TB) me_compact_kernel(const uint32_t *__restrict__ flag, const uint32_t *__restrict__ pos,
+                                                        const uint64_t *__restrict__ me_idx, const uint32_t *__restrict__ sp_code,
+                                                        const uint32_t *__restrict__ sp_head, const uint32_t *__restrict__ sp_locus,
+                                                        const uint64_t *__restrict__ g_off, const uint32_t *__restrict__ g_nst,
+                                                        uint64_t n_special, uint32_t *__restrict__ me_code,
+                                                        uint32_t *__restrict__ me_locus, uint32_t *__restrict__ me_pos,
+                                                        uint32_t *__restrict__ me_beg, uint32_t *__restrict__ me_end) {
+    const uint64_t s = static_cast<uint64_t>(blockIdx.x) * TB + threadIdx.x;
+    if (s >= n_special || !flag[s]) {
+        return;
+    }
+    const uint64_t k = me_idx[s];
+    const uint32_t h = sp_head[s];
+    me_code[k] = sp_code[s];
+    me_locus[k] = sp_locus[s];
+    me_pos[k] = pos[s];
+    me_beg[k] = static_cast<uint32_t>(g_off[h]);
+    me_end[k] = static_cast<uint32_t>(g_off[h]) + g_nst[h];
+}
+
 // ---- dense codes (scatter path only) ----------------------------------------------------------------
 __global__ void __launch_bounds__(TB) dense_codes_kernel(const uint64_t *__restrict__ row_ptr,
                                                          const uint16_t *__restrict__ gid_base,
@@ -677,10 +744,10 @@ int sgpu_link_reads(sgpu_ctx *ctx, const sgpu_pileup *p, uint32_t num_cells, uin
 
     SGPU_TRACE(ctx, "link: allocs+meta");
     // ---- links between entries of one read -----------------------------------------------------------
-    // table geometry: slots >= 4 x the largest locus if shared memory allows, never below 1.25 x
+    // table geometry: slots >= 3 x the largest locus if shared memory allows, never below 1.25 x
     const uint32_t id_cap = (max_n + 1) & ~1u;
     uint32_t slots = 1024;
-    while (slots < 4ull * max_n && slots < 65536) {
+    while (slots < 3ull * max_n && slots < 65536) {
         slots <<= 1;
     }
     auto win_smem = [&](uint32_t s) { return static_cast<size_t>(id_cap) * 4 + REC_BUF * sizeof(uint2) + static_cast<size_t>(s) * 2; };
@@ -773,8 +840,13 @@ int sgpu_link_reads(sgpu_ctx *ctx, const sgpu_pileup *p, uint32_t num_cells, uin
         SGPU_CUDA(ctx, cudaMemsetAsync(out->g_nst.p, 0, NS * sizeof(uint32_t), st));
         SGPU_CUDA(ctx, cudaMemsetAsync(out->sp_drop.p, 0, NS, st));
         SGPU_CUDA(ctx, cudaMemsetAsync(nf_locus.p, 0, P * sizeof(uint32_t), st));
-        SGPU_LAUNCH(ctx, (sp_list_kernel<<<blocks_for(W), TB, 0, st>>>(out->sp_bits.p, out->sp_rank.p, W, p->d_row_ptr, P, out->sp_entry.p,
-                                                                        sp_first.p, out->sp_locus.p)));
+        {
+            DevBuf<uint32_t> word_locus;
+            SGPU_CUDA(ctx, word_locus.alloc(W, ctx));
+            SGPU_LAUNCH(ctx, (word_locus_kernel<<<locus_grid, TB, 0, st>>>(p->d_row_ptr, P, W, word_locus.p)));
+            SGPU_LAUNCH(ctx, (sp_list_kernel<<<blocks_for(W), TB, 0, st>>>(out->sp_bits.p, out->sp_rank.p, W, p->d_row_ptr, word_locus.p,
+                                                                            out->sp_entry.p, sp_first.p, out->sp_locus.p)));
+        }
         for (int sweep = 0; sweep < 3; ++sweep) {
             SGPU_LAUNCH(ctx, (link_min_kernel<<<blocks_for(NL), TB, 0, st>>>(links.p, NL, out->sp_bits.p, out->sp_rank.p, sp_first.p,
                                                                              d_err.p + 1)));
@@ -803,6 +875,21 @@ int sgpu_link_reads(sgpu_ctx *ctx, const sgpu_pileup *p, uint32_t num_cells, uin
                                                                           out->g_nst.p, p->d_gid_base, out->lchr.p, out->tail_locus.p,
                                                                           out->gmap.p, n_groups, num_cells, NS, out->sp_code.p, d_stats.p,
                                                                           d_err.p)));
+        DevBuf<uint32_t> me_flag, me_tmp;
+        SGPU_CUDA(ctx, me_flag.alloc(NS, ctx));
+        SGPU_CUDA(ctx, me_tmp.alloc(NS, ctx));
+        SGPU_CUDA(ctx, out->me_idx.alloc(NS + 1, ctx));
+        SGPU_CUDA(ctx, out->me_code.alloc(NS, ctx));
+        SGPU_CUDA(ctx, out->me_locus.alloc(NS, ctx));
+        SGPU_CUDA(ctx, out->me_pos.alloc(NS, ctx));
+        SGPU_CUDA(ctx, out->me_beg.alloc(NS, ctx));
+        SGPU_CUDA(ctx, out->me_end.alloc(NS, ctx));
+        SGPU_LAUNCH(ctx, (me_flag_kernel<<<blocks_for(NS), TB, 0, st>>>(out->sp_code.p, out->sp_head.p, out->sp_locus.p, out->g_off.p, out->g_list.p,
+                                                                        out->g_nst.p, NS, me_flag.p, me_tmp.p)));
+        SGPU_TRY(sgpu_scan_u32_u64(ctx, me_flag.p, out->me_idx.p, NS));
+        SGPU_LAUNCH(ctx, (me_compact_kernel<<<blocks_for(NS), TB, 0, st>>>(me_flag.p, me_tmp.p, out->me_idx.p, out->sp_code.p, out->sp_head.p,
+                                                                           out->sp_locus.p, out->g_off.p, out->g_nst.p, NS, out->me_code.p,
+                                                                           out->me_locus.p, out->me_pos.p, out->me_beg.p, out->me_end.p)));
     }
     SGPU_CUDA(ctx, cudaGetLastError());
 
