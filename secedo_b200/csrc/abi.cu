@@ -347,6 +347,7 @@ int sgpu_counts_zero(sgpu_ctx *ctx, sgpu_counts *c) {
     }
     c->planes_used = 2;
     c->have_params = false;
+    c->fresh = true;
     return SGPU_OK;
 }
 
@@ -407,6 +408,7 @@ int sgpu_counts_accumulate(sgpu_ctx *ctx, sgpu_counts *c, const sgpu_pileup *fil
         if (path == SGPU_PATH_SCATTER) {
             SGPU_TRY(sgpu_link_dense_codes(ctx, filtered, &lr));
             SGPU_TRY(sgpu_scatter_pairs(ctx, filtered, lr, c, +1, false, &s.n_pairs_first));
+            c->fresh = false;
         } else {
             SGPU_TRY(sgpu_gemm_counts(ctx, filtered, lr, c, &s.n_pairs_first)); // incl. the tail x tail correction
         }

@@ -139,6 +139,7 @@ struct sgpu_counts {
     uint64_t nn = 0;            // n*n
     int32_t *i32 = nullptr;     // N_PLANES planes of n*n, only the upper triangle (i<j) is meaningful
     int planes_used = 2;        // 2, 5 or 9
+    bool fresh = false;         // S and D are all zero (nothing accumulated since sgpu_counts_zero)
     double *spill = nullptr;    // n*n doubles: sum of G(x_s,x_d) over pairs with x_s+x_d >= 4 (lazy)
     uint64_t *hist = nullptr;   // SGPU_MAX_CLASS^2 class histogram (pairs with x_s+x_d >= 2)
     // log-likelihood parameters the spill plane was accumulated with (must match at finalize)

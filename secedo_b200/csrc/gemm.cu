@@ -62,210 +62,239 @@ struct PanelLayout {
 // ------------------------------------------------------------------------------------------------
 // staging
 //
-// The panel buffer holds one 128-byte row per (cell, k-block of 32 loci). While the counts are being
-// accumulated, word j of the row is locus j's four base counts (4 x u8); transform_kernel then turns
-// the row IN PLACE into the K-major operand layout [plane 0..3][32 loci] of Hadamard planes, so the
-// staged counts cost one memset, one pass of atomics and one read + write of the panel.
+// One CTA per (k-block of 32 loci, stripe of cells) accumulates the per-(cell, locus) base counts of
+// its loci in a shared-memory tile (one word = 4 x u8 base counts, shared-memory atomics), turns the
+// tile into Hadamard planes and writes the finished 128-byte operand rows [plane 0..3][32 loci] once,
+// coalesced. Every stripe's CTA scans all entries of the 32 loci and keeps the cells of its stripe; the
+// repeated reads come from L2. Nothing is zeroed, atomically updated or re-read in HBM: counting in
+// global memory was bound by TLB reach and DRAM row activations (one 32-byte sector per atomic, each in
+// a different page), not by bytes.
+//
+// The reference never compares two reads that both lie behind the per-chromosome cutoff K (SURVEY
+// F2). Those pairs only exist at the few loci behind the cutoff; they are removed by extra k-blocks at
+// the end of the panel that hold ONLY the tail reads, Z as the A operand and -Z as the B operand of
+// the same GEMM:  S = C C^T - Z Z^T.
 // ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ void add_count(uint32_t *__restrict__ U, uint64_t word, uint32_t base, int *__restrict__ err) {
+constexpr int ST_THREADS = 1024;
+constexpr uint32_t ST_MAX_CELLS = 1728; // 216 KB tile, one CTA per SM
+constexpr uint32_t CB_SKIP = 0xFFFFu;   // cellbase of an entry the dense scan does not count
+
+// cellbase[e] = cell << 2 | base for the entries that are the only entry of their read, CB_SKIP for
+// the others (staged from the special-entry list): what every stripe's CTA scans, 2 bytes per entry,
+// with the group map and the bitmap already applied. 8 entries per thread.
+__global__ void __launch_bounds__(256) cellbase_kernel(const uint16_t *__restrict__ gid_base,
+                                                       const uint32_t *__restrict__ sp_bits,
+                                                       const uint32_t *__restrict__ gmap, uint32_t n_groups,
+                                                       uint32_t n_cells, uint64_t n_entries,
+                                                       uint16_t *__restrict__ cellbase, int *__restrict__ err) {
+    const uint64_t e0 = (static_cast<uint64_t>(blockIdx.x) * 256 + threadIdx.x) * 8;
+    if (e0 >= n_entries) {
+        return;
+    }
+    const uint32_t special = (sp_bits[e0 >> 5] >> (e0 & 31)) & 0xFFu;
+    uint16_t in[8], out[8];
+    if (e0 + 8 <= n_entries) {
+        *reinterpret_cast<uint4 *>(in) = *reinterpret_cast<const uint4 *>(gid_base + e0);
+    } else {
+        for (int k = 0; k < 8; ++k) {
+            in[k] = e0 + k < n_entries ? gid_base[e0 + k] : 0;
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        const uint32_t gid = in[k] >> 2;
+        uint32_t v = CB_SKIP;
+        if (e0 + k < n_entries && !((special >> k) & 1u)) {
+            uint32_t cell;
+            if (gid >= n_groups || (cell = gmap[gid]) >= n_cells) {
+                atomicExch(err, SGPU_E_CELL_RANGE);
+            } else {
+                v = (cell << 2) | (in[k] & 3u);
+            }
+        }
+        out[k] = static_cast<uint16_t>(v);
+    }
+    *reinterpret_cast<uint4 *>(cellbase + e0) = *reinterpret_cast<const uint4 *>(out); // the array is padded to 8 entries
+}
+
+struct StageArgs {
+    const uint64_t *row_ptr;
+    const uint16_t *cellbase;  // see cellbase_kernel; padded to a multiple of 8 entries
+    const uint32_t *sp_code;   // special entries, ascending by entry (hence by locus)
+    const uint32_t *sp_locus;
+    uint64_t n_special;
+    uint32_t n_pad;
+    uint32_t l0, nl;           // main k-blocks: loci [l0, l0 + nl), 32 per k-block
+    uint32_t kbs_main;
+    const uint32_t *tail_loci; // tail k-blocks: loci tail_loci[0 .. n_tail), ascending
+    uint32_t n_tail, kbs_tail; // Z goes to k-block kbs_main + t, -Z to kbs_main + kbs_tail + t
+    uint32_t cells_per_cta, n_stripes;
+    PanelLayout pl;
+    uint32_t *U;
+    int *err;
+};
+
+__device__ __forceinline__ void tile_add(uint32_t *tile, uint32_t r, uint32_t j, uint32_t base, int *err) {
     const uint32_t sh = 8u * base;
-    const uint32_t old = atomicAdd(&U[word], 1u << sh);
+    const uint32_t old = atomicAdd(&tile[r * 32 + ((j + r) & 31u)], 1u << sh);
     if (((old >> sh) & 0xFFu) >= 127u) {
         atomicExch(err, SGPU_E_COUNT_RANGE); // > 127 reads of one cell at one locus: outside int8
     }
 }
 
-// entries that are the only entry of their read, loci [l0, l1): one block per locus. Four entries per
-// thread are in flight (all loads first, then the atomics, then the range checks): the chain
-// gid_base -> group map -> atomic is three dependent memory round trips.
-template <bool RETURNING>
-__global__ void __launch_bounds__(256) stage_main_kernel(const uint64_t *__restrict__ row_ptr,
-                                                         const uint16_t *__restrict__ gid_base,
-                                                         const uint32_t *__restrict__ sp_bits,
-                                                         const uint32_t *__restrict__ gmap, uint32_t n_groups,
-                                                         uint32_t n_cells, uint32_t l0, uint32_t l1, uint32_t col0,
-                                                         PanelLayout pl, uint32_t *__restrict__ U,
-                                                         int *__restrict__ err) {
-    constexpr int UNROLL = 4;
-    for (uint32_t l = l0 + blockIdx.x; l < l1; l += gridDim.x) {
-        const uint64_t e0 = row_ptr[l], e1 = row_ptr[l + 1];
-        const uint64_t col = pl.word(0, l - col0); // + cell * cell_words
-        for (uint64_t eb = e0 + threadIdx.x; eb < e1; eb += 256 * UNROLL) {
-            uint32_t gb[UNROLL], cell[UNROLL], old[UNROLL];
-            bool live[UNROLL];
-#pragma unroll
-            for (int u = 0; u < UNROLL; ++u) {
-                const uint64_t e = eb + 256 * u;
-                live[u] = e < e1;
-                gb[u] = live[u] ? gid_base[e] : 0;
-                if (live[u] && ((sp_bits[e >> 5] >> (e & 31)) & 1u)) {
-                    live[u] = false; // staged by stage_special_kernel
-                }
+__global__ void __launch_bounds__(ST_THREADS, 1) stage_tile_kernel(const StageArgs a) {
+    extern __shared__ uint32_t tile[]; // [cell in stripe][32 loci], word of locus j of row r at (j + r) % 32
+    __shared__ uint64_t s_e0[32], s_e1[32];
+    __shared__ uint32_t s_loc[32];
+    __shared__ uint64_t s_sp0[32], s_sp1[32];
+    // the stripes of one k-block are neighbours in the grid: they run together and share its entries in L2
+    const uint32_t kb = blockIdx.x / a.n_stripes;
+    const uint32_t c0 = (blockIdx.x - kb * a.n_stripes) * a.cells_per_cta;
+    const uint32_t nc = min(a.cells_per_cta, a.n_pad - c0);
+    const bool tail = kb >= a.kbs_main;
+    if (threadIdx.x < 32) {
+        const uint32_t j = threadIdx.x;
+        uint32_t l = 0xFFFFFFFFu;
+        if (!tail) {
+            const uint32_t col = kb * LOCI_PER_KB + j;
+            if (col < a.nl) {
+                l = a.l0 + col;
             }
-#pragma unroll
-            for (int u = 0; u < UNROLL; ++u) {
-                const uint32_t gid = gb[u] >> 2;
-                cell[u] = 0;
-                if (live[u]) {
-                    if (gid >= n_groups || (cell[u] = gmap[gid]) >= n_cells) {
-                        atomicExch(err, SGPU_E_CELL_RANGE);
-                        live[u] = false;
-                    }
-                }
+        } else {
+            const uint32_t t = (kb - a.kbs_main) * LOCI_PER_KB + j;
+            if (t < a.n_tail) {
+                l = a.tail_loci[t];
             }
-#pragma unroll
-            for (int u = 0; u < UNROLL; ++u) {
-                old[u] = 0;
-                if (live[u]) {
-                    const uint32_t inc = 1u << (8u * (gb[u] & 3u));
-                    uint32_t *w = &U[static_cast<uint64_t>(cell[u]) * pl.cell_words + col];
-                    if (RETURNING) {
-                        old[u] = atomicAdd(w, inc);
+        }
+        s_loc[j] = l;
+        // unused slots are empty ranges at the end of the k-block's entries (main mode: contiguous loci)
+        const uint64_t e_last = __shfl_sync(0xffffffffu, l != 0xFFFFFFFFu ? a.row_ptr[l + 1] : 0, 31 - __clz(__ballot_sync(0xffffffffu, l != 0xFFFFFFFFu) | 1u));
+        s_e0[j] = l != 0xFFFFFFFFu ? a.row_ptr[l] : e_last;
+        s_e1[j] = l != 0xFFFFFFFFu ? a.row_ptr[l + 1] : e_last;
+        // the special entries of locus l: a contiguous range of the (ascending) list
+        uint64_t r0 = 0, r1 = 0;
+        if (l != 0xFFFFFFFFu) {
+#pragma unroll 1
+            for (int side = 0; side < 2; ++side) {
+                const uint32_t key = l + side; // first special entry with locus >= key
+                uint64_t lo = 0, hi = a.n_special;
+                while (lo < hi) {
+                    const uint64_t mid = (lo + hi) >> 1;
+                    if (a.sp_locus[mid] < key) {
+                        lo = mid + 1;
                     } else {
-                        atomicAdd(w, inc); // RED
+                        hi = mid;
                     }
                 }
+                (side == 0 ? r0 : r1) = lo;
             }
-            if (RETURNING) {
+        }
+        s_sp0[j] = r0;
+        s_sp1[j] = r1;
+    }
+    for (uint32_t i = threadIdx.x; i < nc * 32; i += ST_THREADS) {
+        tile[i] = 0;
+    }
+    __syncthreads();
+
+    // ---- entries that are the only entry of their read (in a tail k-block all of them are tail reads:
+    // such a read was created at its own locus, which lies behind the cutoff)
+    if (!tail) {
+        // the 32 loci are consecutive: one contiguous range of entries, 8 per 16-byte load
+        const uint64_t E0 = s_e0[0], E1 = s_e1[31];
+        for (uint64_t v = (E0 & ~7ull) + 8ull * threadIdx.x; v < E1; v += 8ull * ST_THREADS) {
+            const uint4 q = *reinterpret_cast<const uint4 *>(a.cellbase + v);
+            const uint32_t w[4] = { q.x, q.y, q.z, q.w };
+            // locus of the first entry of the vector that belongs to the k-block
+            const uint64_t ef = max(v, E0);
+            uint32_t j = 0;
 #pragma unroll
-                for (int u = 0; u < UNROLL; ++u) {
-                    if (live[u] && ((old[u] >> (8u * (gb[u] & 3u))) & 0xFFu) >= 127u) {
-                        atomicExch(err, SGPU_E_COUNT_RANGE); // > 127 reads of one cell at one locus: outside int8
-                    }
+            for (int step = 16; step > 0; step >>= 1) {
+                if (s_e1[j + step - 1] <= ef) {
+                    j += step;
+                }
+            }
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                const uint64_t e = v + k;
+                const uint32_t cb = (w[k >> 1] >> (16 * (k & 1))) & 0xFFFFu;
+                if (e < E0 || e >= E1 || cb == CB_SKIP) {
+                    continue;
+                }
+                while (e >= s_e1[j]) {
+                    ++j;
+                }
+                const uint32_t r = (cb >> 2) - c0;
+                if (r < nc) {
+                    tile_add(tile, r, j, cb & 3u, a.err);
+                }
+            }
+        }
+    } else {
+        for (uint32_t j = 0; j < 32; ++j) {
+            for (uint64_t e = s_e0[j] + threadIdx.x; e < s_e1[j]; e += ST_THREADS) {
+                const uint32_t cb = a.cellbase[e];
+                const uint32_t r = (cb >> 2) - c0;
+                if (cb != CB_SKIP && r < nc) {
+                    tile_add(tile, r, j, cb & 3u, a.err);
                 }
             }
         }
     }
-}
+    // ---- surviving entries of reads with several entries
+    for (uint32_t j = 0; j < 32; ++j) {
+        for (uint64_t s = s_sp0[j] + threadIdx.x; s < s_sp1[j]; s += ST_THREADS) {
+            const uint32_t c = a.sp_code[s];
+            if (c == CODE_DROPPED || (tail && !code_tail(c))) {
+                continue;
+            }
+            const uint32_t r = code_cell(c) - c0;
+            if (r < nc) {
+                tile_add(tile, r, j, code_base(c), a.err);
+            }
+        }
+    }
+    __syncthreads();
 
-// entries of reads with several entries that survived the mate rule; sp_locus is ascending, the loci
-// [l0, l1) own a contiguous range of special entries that is found by bisection
-__global__ void __launch_bounds__(256) stage_special_kernel(const uint32_t *__restrict__ sp_code,
-                                                            const uint32_t *__restrict__ sp_locus, uint64_t n_special,
-                                                            uint32_t l0, uint32_t l1, uint32_t col0, PanelLayout pl,
-                                                            uint32_t *__restrict__ U, int *__restrict__ err) {
-    uint64_t lo = 0, hi = n_special;
-    while (lo < hi) {
-        const uint64_t mid = (lo + hi) >> 1;
-        if (sp_locus[mid] < l0) {
-            lo = mid + 1;
-        } else {
-            hi = mid;
-        }
-    }
-    for (uint64_t s = lo + static_cast<uint64_t>(blockIdx.x) * 256 + threadIdx.x; s < n_special; s += static_cast<uint64_t>(gridDim.x) * 256) {
-        const uint32_t l = sp_locus[s];
-        if (l >= l1) {
-            break;
-        }
-        const uint32_t c = sp_code[s];
-        if (c != CODE_DROPPED) {
-            add_count(U, pl.word(code_cell(c), l - col0), code_base(c), err);
-        }
-    }
-}
-
-// tail correction panel: column b of the panel holds ONLY the tail reads of locus tail_loci[b]. A
-// read that is the only entry... of its read was created at its own locus, i.e. behind the cutoff.
-__global__ void __launch_bounds__(256) stage_tail_kernel(const uint64_t *__restrict__ row_ptr,
-                                                         const uint16_t *__restrict__ gid_base,
-                                                         const uint32_t *__restrict__ sp_bits,
-                                                         const uint32_t *__restrict__ gmap, uint32_t n_groups,
-                                                         uint32_t n_cells, const uint32_t *__restrict__ tail_loci,
-                                                         PanelLayout pl, uint32_t *__restrict__ U,
-                                                         int *__restrict__ err) {
-    const uint32_t l = tail_loci[blockIdx.x];
-    const uint64_t e0 = row_ptr[l], e1 = row_ptr[l + 1];
-    for (uint64_t e = e0 + threadIdx.x; e < e1; e += 256) {
-        if ((sp_bits[e >> 5] >> (e & 31)) & 1u) {
-            continue;
-        }
-        const uint32_t gb = gid_base[e];
-        const uint32_t gid = gb >> 2;
-        uint32_t cell;
-        if (gid >= n_groups || (cell = gmap[gid]) >= n_cells) {
-            atomicExch(err, SGPU_E_CELL_RANGE);
-            continue;
-        }
-        add_count(U, pl.word(cell, blockIdx.x), gb & 3u, err);
-    }
-}
-
-__global__ void __launch_bounds__(256) stage_tail_special_kernel(const uint32_t *__restrict__ sp_code,
-                                                                 const uint32_t *__restrict__ sp_locus,
-                                                                 uint64_t n_special, const uint32_t *__restrict__ tail_loci,
-                                                                 uint32_t n_tail /* columns of this panel */,
-                                                                 PanelLayout pl, uint32_t *__restrict__ U,
-                                                                 int *__restrict__ err) {
-    const uint64_t s = static_cast<uint64_t>(blockIdx.x) * 256 + threadIdx.x;
-    if (s >= n_special) {
-        return;
-    }
-    const uint32_t c = sp_code[s], l = sp_locus[s];
-    if (c == CODE_DROPPED || !code_tail(c)) {
-        return;
-    }
-    uint32_t lo = 0, hi = n_tail; // tail_loci is ascending
-    while (lo < hi) {
-        const uint32_t mid = (lo + hi) >> 1;
-        if (tail_loci[mid] < l) {
-            lo = mid + 1;
-        } else {
-            hi = mid;
-        }
-    }
-    if (lo < n_tail && tail_loci[lo] == l) {
-        add_count(U, pl.word(code_cell(c), lo), code_base(c), err);
-    }
-}
-
-// In-place Hadamard transform of the rows: 8 consecutive lanes own one 128-byte row (one cell, one
-// k-block); each loads 4 loci x 4 base counts (16 B) and, after the whole warp has loaded, stores the
-// four plane words of those loci.
-__global__ void __launch_bounds__(256) transform_kernel(uint32_t *__restrict__ U, uint32_t kbs /* valid k-blocks */, uint32_t n_pad,
-                                                        PanelLayout pl, int *__restrict__ err) {
-    // consecutive 8-lane groups walk the k-blocks of a chunk row, then the cells of the chunk: contiguous
-    // memory. The grid covers whole chunks (a multiple of 32 threads), rows behind kbs are skipped.
-    const uint64_t t = static_cast<uint64_t>(blockIdx.x) * 256 + threadIdx.x;
-    const uint32_t g = t & 7;
-    const uint64_t rk = t >> 3;
-    const uint32_t ck = 1u << pl.ck_shift;
-    const uint64_t per_chunk = static_cast<uint64_t>(n_pad) << pl.ck_shift; // rows of a chunk
-    const uint32_t ch = static_cast<uint32_t>(rk / per_chunk);
-    const uint64_t in_chunk = rk - ch * per_chunk;
-    const uint32_t cell = static_cast<uint32_t>(in_chunk >> pl.ck_shift);
-    const uint32_t kb = (ch << pl.ck_shift) + static_cast<uint32_t>(in_chunk & (ck - 1));
-    const bool valid = kb < kbs;
-    uint32_t *r = U + pl.row(cell, valid ? kb : 0);
-    uint4 v = make_uint4(0, 0, 0, 0);
-    if (valid) {
-        v = *reinterpret_cast<const uint4 *>(r + 4 * g);
-    }
-    const uint32_t in[4] = { v.x, v.y, v.z, v.w };
-    uint32_t w[4] = { 0, 0, 0, 0 }; // per plane, 4 loci packed
+    // ---- Hadamard planes, written as finished operand rows: 8 consecutive lanes own one 128-byte row
+    const uint32_t kb_neg = kb + a.kbs_tail;
     bool bad = false;
+    for (uint32_t item = threadIdx.x; item < nc * 8; item += ST_THREADS) {
+        const uint32_t r = item >> 3, g = item & 7;
+        uint32_t w[4] = { 0, 0, 0, 0 }, wn[4] = { 0, 0, 0, 0 }; // per plane, 4 loci packed (and negated)
 #pragma unroll
-    for (int q = 0; q < 4; ++q) {
-        const int c0 = in[q] & 0xFF, c1 = (in[q] >> 8) & 0xFF, c2 = (in[q] >> 16) & 0xFF, c3 = in[q] >> 24;
-        const int u0 = c0 + c1 + c2 + c3;
-        const int u1 = c0 - c1 + c2 - c3;
-        const int u2 = c0 + c1 - c2 - c3;
-        const int u3 = c0 - c1 - c2 + c3;
-        bad |= u0 > 127;
-        w[0] |= static_cast<uint32_t>(u0 & 0xFF) << (8 * q);
-        w[1] |= static_cast<uint32_t>(u1 & 0xFF) << (8 * q);
-        w[2] |= static_cast<uint32_t>(u2 & 0xFF) << (8 * q);
-        w[3] |= static_cast<uint32_t>(u3 & 0xFF) << (8 * q);
-    }
-    __syncwarp(); // every lane of the row has its counts in registers before any plane word is written
-    if (valid) {
+        for (int q = 0; q < 4; ++q) {
+            const uint32_t v = tile[r * 32 + ((4 * g + q + r) & 31u)];
+            const int b0 = v & 0xFF, b1 = (v >> 8) & 0xFF, b2 = (v >> 16) & 0xFF, b3 = v >> 24;
+            const int u0 = b0 + b1 + b2 + b3;
+            const int u1 = b0 - b1 + b2 - b3;
+            const int u2 = b0 + b1 - b2 - b3;
+            const int u3 = b0 - b1 - b2 + b3;
+            bad |= u0 > 127;
+            w[0] |= static_cast<uint32_t>(u0 & 0xFF) << (8 * q);
+            w[1] |= static_cast<uint32_t>(u1 & 0xFF) << (8 * q);
+            w[2] |= static_cast<uint32_t>(u2 & 0xFF) << (8 * q);
+            w[3] |= static_cast<uint32_t>(u3 & 0xFF) << (8 * q);
+            wn[0] |= static_cast<uint32_t>(-u0 & 0xFF) << (8 * q);
+            wn[1] |= static_cast<uint32_t>(-u1 & 0xFF) << (8 * q);
+            wn[2] |= static_cast<uint32_t>(-u2 & 0xFF) << (8 * q);
+            wn[3] |= static_cast<uint32_t>(-u3 & 0xFF) << (8 * q);
+        }
+        uint32_t *out = a.U + a.pl.row(c0 + r, kb);
 #pragma unroll
-        for (int pl_i = 0; pl_i < 4; ++pl_i) {
-            r[pl_i * 8 + g] = w[pl_i];
+        for (int p = 0; p < 4; ++p) {
+            out[p * 8 + g] = w[p];
+        }
+        if (tail) {
+            uint32_t *outn = a.U + a.pl.row(c0 + r, kb_neg);
+#pragma unroll
+            for (int p = 0; p < 4; ++p) {
+                outn[p * 8 + g] = wn[p];
+            }
         }
     }
     if (bad) {
-        atomicExch(err, SGPU_E_COUNT_RANGE);
+        atomicExch(a.err, SGPU_E_COUNT_RANGE);
     }
 }
 
@@ -354,30 +383,50 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
 struct WorkItem {
     uint32_t rb, cb;   // row block (x128), column block (x256)
     uint32_t k0, k1;   // k-block range
+    uint32_t partial;  // 1: the tile's K range is shared with other CTAs -> atomics only
 };
 
-// work item w = (tile w % n_tiles, K split w / n_tiles)
+// Work list of one launch: the first n_full items are whole tiles (all k-blocks), n_full a multiple of
+// the grid so that every CTA owns the same number of them; the remaining tiles are cut into `splits`
+// K ranges each, so that the last round keeps every SM busy for 1/splits of a tile instead of leaving
+// most of them idle for a whole tile (1 055 tiles on 148 SMs = 7.13 rounds).
 struct WorkList {
     const uint2 *tiles; // (row block, column block), rasterised for L2 reuse
-    uint32_t n_tiles;
-    uint32_t n_work;    // n_tiles * splits
-    uint32_t kbs;       // k-blocks of the panel
-    uint32_t per;       // k-blocks per split
+    uint32_t n_full;    // tiles processed whole
+    uint32_t n_work;    // n_full + (n_tiles - n_full) * splits
+    uint32_t splits;    // K ranges per remaining tile (>= 1)
+    uint32_t kbs;       // k-blocks of the panel (main + tail)
+    uint32_t per;       // k-blocks per K range of a remaining tile
     uint32_t ck_shift;  // log2(k-blocks per chunk of the panel layout)
+    uint32_t kb_neg0;   // k-blocks >= kb_neg0 hold tail reads only: their B operand is k-block kb + kb_negd (-Z)
+    uint32_t kb_negd;
 };
 __device__ __forceinline__ WorkItem work_item(const WorkList &wl, uint32_t w) {
-    const uint32_t split = w / wl.n_tiles;
-    const uint2 t = wl.tiles[w - split * wl.n_tiles];
+    if (w < wl.n_full) {
+        const uint2 t = wl.tiles[w];
+        return WorkItem{ t.x, t.y, 0u, wl.kbs, 0u };
+    }
+    const uint32_t j = w - wl.n_full;
+    const uint32_t tile = j / wl.splits, split = j - tile * wl.splits;
+    const uint2 t = wl.tiles[wl.n_full + tile];
     const uint32_t k0 = split * wl.per;
-    return WorkItem{ t.x, t.y, k0, min(wl.kbs, k0 + wl.per) };
+    return WorkItem{ t.x, t.y, k0, min(wl.kbs, k0 + wl.per), wl.splits > 1 ? 1u : 0u };
 }
+
+// how whole tiles reach the count planes
+enum : int {
+    EPI_RED = 0,   // atomics, zeros skipped
+    EPI_STORE = 1, // the planes are known to be zero: plain vector stores
+    EPI_RMW = 2    // vector load + add + store (the tile is owned by one CTA)
+};
 
 // ------------------------------------------------------------------------------------------------
 // the GEMM
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(GEMM_THREADS, 1) syrk_kernel(const __grid_constant__ CUtensorMap map_u,
                                                                const WorkList wl, int32_t *__restrict__ S,
-                                                               int32_t *__restrict__ D, uint32_t n_cells, int sign) {
+                                                               int32_t *__restrict__ D, uint32_t n_cells, int sign,
+                                                               int epi_mode) {
     const uint32_t n_work = wl.n_work;
     extern __shared__ uint8_t smem_raw[];
     // 128B swizzle needs 1024-byte aligned tiles
@@ -422,9 +471,12 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) syrk_kernel(const __grid_cons
                     mbar_expect_tx(bar, STAGE_BYTES);
                     const int32_t ch = static_cast<int32_t>(kb >> wl.ck_shift);
                     const int32_t kx = static_cast<int32_t>((kb - (static_cast<uint32_t>(ch) << wl.ck_shift)) * KB_BYTES);
+                    const uint32_t kbb = kb >= wl.kb_neg0 ? kb + wl.kb_negd : kb;
+                    const int32_t chb = static_cast<int32_t>(kbb >> wl.ck_shift);
+                    const int32_t kxb = static_cast<int32_t>((kbb - (static_cast<uint32_t>(chb) << wl.ck_shift)) * KB_BYTES);
                     tma_load_3d(sa, &map_u, bar, kx, wi.rb * BM, ch);
-                    tma_load_3d(sb, &map_u, bar, kx, wi.cb * BN, ch);
-                    tma_load_3d(sb + A_BYTES, &map_u, bar, kx, wi.cb * BN + 128, ch);
+                    tma_load_3d(sb, &map_u, bar, kxb, wi.cb * BN, chb);
+                    tma_load_3d(sb + A_BYTES, &map_u, bar, kxb, wi.cb * BN + 128, chb);
                     if (++stage == STAGES) {
                         stage = 0;
                         phase ^= 1;
@@ -471,6 +523,9 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) syrk_kernel(const __grid_cons
             const uint32_t row = wi.rb * BM + lane_base + lane;
             int32_t *Srow = S + static_cast<uint64_t>(row) * n_cells;
             int32_t *Drow = D + static_cast<uint64_t>(row) * n_cells;
+            // a tile strictly above the diagonal and inside the matrix needs no per-element guards
+            const bool interior = wi.cb * BN >= wi.rb * BM + BM && wi.cb * BN + BN <= n_cells && wi.rb * BM + BM <= n_cells;
+            const bool vec = interior && !wi.partial && epi_mode != EPI_RED && (n_cells & 3u) == 0;
 #pragma unroll 1
             for (uint32_t cc = 0; cc < BN / 32; ++cc) {
                 uint32_t q[32], t[32];
@@ -478,7 +533,36 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) syrk_kernel(const __grid_cons
                 tmem_ld32(tmem_T + (lane_base << 16) + cc * 32, t);
                 asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
                 const uint32_t col0 = wi.cb * BN + cc * 32;
-                if (row < n_cells && col0 + 31 > row) {
+                if (vec) {
+                    // each thread owns 128 contiguous bytes of its row in either plane
+                    int4 *ps = reinterpret_cast<int4 *>(Srow + col0), *pd = reinterpret_cast<int4 *>(Drow + col0);
+                    int4 os[8], od[8];
+                    if (epi_mode == EPI_RMW) {
+#pragma unroll
+                        for (int k = 0; k < 8; ++k) {
+                            os[k] = ps[k];
+                            od[k] = pd[k];
+                        }
+                    }
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) {
+                        int32_t sv[4], dv[4];
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) {
+                            const int32_t tv = static_cast<int32_t>(t[4 * k + e]);
+                            sv[e] = (static_cast<int32_t>(q[4 * k + e]) + tv) >> 2; // (4S - T + T) / 4
+                            dv[e] = tv - sv[e];
+                        }
+                        int4 vs = make_int4(sign * sv[0], sign * sv[1], sign * sv[2], sign * sv[3]);
+                        int4 vd = make_int4(sign * dv[0], sign * dv[1], sign * dv[2], sign * dv[3]);
+                        if (epi_mode == EPI_RMW) {
+                            vs.x += os[k].x, vs.y += os[k].y, vs.z += os[k].z, vs.w += os[k].w;
+                            vd.x += od[k].x, vd.y += od[k].y, vd.z += od[k].z, vd.w += od[k].w;
+                        }
+                        ps[k] = vs;
+                        pd[k] = vd;
+                    }
+                } else if (row < n_cells && col0 + 31 > row) {
 #pragma unroll
                     for (int k = 0; k < 32; ++k) {
                         const uint32_t col = col0 + k;
@@ -556,12 +640,17 @@ int sgpu_gemm_counts(sgpu_ctx *ctx, const sgpu_pileup *p, const LinkResult &lr, 
         return SGPU_OK;
     }
     const uint32_t N = c->n;
+    if (N > 16383) { // (cell << 2 | base) must fit 16 bits; the reference's PosData holds 14-bit group ids
+        return sgpu_fail(ctx, SGPU_E_ARG, "the GEMM path supports at most 16383 cells");
+    }
     const uint32_t n_pad = (N + BN - 1) / BN * BN;
-    // panel: at most ~2 GB of staged counts / Hadamard planes
+    // the tail k-blocks (Z and -Z) ride along with the first panel
+    const uint32_t kbs_tail = static_cast<uint32_t>((lr.n_tail_loci + LOCI_PER_KB - 1) / LOCI_PER_KB);
+    // panel: at most ~2 GB of Hadamard planes
     uint64_t panel = (1ull << 31) / (4ull * n_pad) / LOCI_PER_KB * LOCI_PER_KB;
     panel = std::max<uint64_t>(panel, LOCI_PER_KB);
     panel = std::min<uint64_t>(panel, (P + LOCI_PER_KB - 1) / LOCI_PER_KB * LOCI_PER_KB);
-    const uint64_t kbs_max = panel / LOCI_PER_KB;
+    const uint64_t kbs_max = panel / LOCI_PER_KB + 2ull * kbs_tail;
     PanelLayout pl;
     pl.ck_shift = 5; // 32 k-blocks = 1 024 loci per chunk: 4 KB per cell, 33.8 MB per chunk at 8 192 cells
     if (const char *env = getenv("SECEDO_B200_CHUNK_SHIFT")) {
@@ -571,6 +660,7 @@ int sgpu_gemm_counts(sgpu_ctx *ctx, const sgpu_pileup *p, const LinkResult &lr, 
     pl.cell_words = (ck | 1u) * 32u; // odd number of lines: consecutive cells do not alias in the L2 sets
     pl.chunk_words = static_cast<uint64_t>(n_pad) * pl.cell_words;
     const uint64_t n_chunks_max = (kbs_max + ck - 1) / ck;
+    SGPU_TRACE(ctx, "gemm: enter");
 
     DevBuf<uint32_t> U;
     DevBuf<int> d_err;
@@ -608,9 +698,9 @@ int sgpu_gemm_counts(sgpu_ctx *ctx, const sgpu_pileup *p, const LinkResult &lr, 
     const uint2 *d_tiles = nullptr;
     uint32_t n_tiles = 0;
     SGPU_TRY(tile_list(ctx, N, n_pad, &d_tiles, &n_tiles));
-
     SGPU_TRACE(ctx, "gemm: tensor map + tiles");
-    // CUDA events on the launching stream around the staging kernels and around the tcgen05 kernel
+
+    // CUDA events on the launching stream around the staging kernel and around the tcgen05 kernel
     std::vector<cudaEvent_t> evs;
     auto mark = [&]() {
         cudaEvent_t e;
@@ -619,87 +709,81 @@ int sgpu_gemm_counts(sgpu_ctx *ctx, const sgpu_pileup *p, const LinkResult &lr, 
         evs.push_back(e);
     };
     const uint32_t sms = static_cast<uint32_t>(ctx->sm_count);
-    const unsigned sp_blocks = static_cast<unsigned>(ceil_div_u64(lr.n_special ? lr.n_special : 1, 256));
-    // zero / Hadamard-transform in place the chunks that hold the first kbs k-blocks
-    auto clear_kbs = [&](uint32_t kbs) -> int {
-        const uint64_t chunks = (kbs + ck - 1) / ck;
-        SGPU_CUDA(ctx, cudaMemsetAsync(U.p, 0, chunks * pl.chunk_words * sizeof(uint32_t), st));
-        return SGPU_OK;
-    };
-    auto transform_kbs = [&](uint32_t kbs) {
-        const uint64_t chunks = (kbs + ck - 1) / ck;
-        const uint64_t items = chunks * (static_cast<uint64_t>(n_pad) << pl.ck_shift) * 8; // a multiple of 256
-        SGPU_LAUNCH(ctx, (transform_kernel<<<static_cast<unsigned>(items / 256), 256, 0, st>>>(U.p, kbs, n_pad, pl, d_err.p)));
-    };
-    // GEMM of the nl loci currently staged; sign -1 subtracts
-    auto gemm_panel = [&](uint64_t nl, int sign) -> int {
-        const uint32_t kbs = static_cast<uint32_t>((nl + LOCI_PER_KB - 1) / LOCI_PER_KB);
-        // split K so that every SM has work even when there are few tiles
-        uint32_t splits = 1;
-        if (n_tiles < 2 * sms) {
-            splits = static_cast<uint32_t>(std::min<uint64_t>(kbs, (2 * sms + n_tiles - 1) / n_tiles));
-        }
-        WorkList wl;
-        wl.tiles = d_tiles;
-        wl.n_tiles = n_tiles;
-        wl.kbs = kbs;
-        wl.ck_shift = pl.ck_shift;
-        wl.per = (kbs + splits - 1) / splits;
-        splits = (kbs + wl.per - 1) / wl.per; // no empty split
-        wl.n_work = n_tiles * splits;
-        const unsigned grid = static_cast<unsigned>(std::min<uint64_t>(wl.n_work, sms));
-        mark(); // [3k+1] staging done, GEMM begins
-        SGPU_LAUNCH(ctx, (syrk_kernel<<<grid, GEMM_THREADS, SMEM_BYTES, st>>>(map, wl, c->i32 + PLANE_S * c->nn, c->i32 + PLANE_D * c->nn, N, sign)));
-        SGPU_CUDA(ctx, cudaGetLastError());
-        mark(); // [3k+2] GEMM done
-        ++ctx->n_syrk;
-        return SGPU_OK;
-    };
-    const char *env_red = getenv("SECEDO_B200_STAGE_RED"); // experiment: fire-and-forget atomics (no range check)
-    const bool stage_red = env_red && env_red[0] == '1';
+    // stripes of cells per staging CTA: as few as a 104 KB tile allows
+    const uint32_t n_stripes = (n_pad + ST_MAX_CELLS - 1) / ST_MAX_CELLS;
+    const uint32_t cells_per_cta = ((n_pad + n_stripes - 1) / n_stripes + 3) / 4 * 4;
+    const size_t st_smem = static_cast<size_t>(cells_per_cta) * 128;
+    SGPU_CUDA(ctx, cudaFuncSetAttribute(stage_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(st_smem)));
+
+    // per-entry (cell, base) with the group map and the special bitmap applied, once per call
+    DevBuf<uint16_t> cellbase;
+    const uint64_t E = p->n_entries;
+    SGPU_CUDA(ctx, cellbase.alloc((E + 7) / 8 * 8 + 8, ctx));
+    mark(); // folded into the first panel's staging time
+    SGPU_LAUNCH(ctx, (cellbase_kernel<<<static_cast<unsigned>(ceil_div_u64(ceil_div_u64(E, 8), 256)), 256, 0, st>>>(
+                             p->d_gid_base, lr.sp_bits.p, lr.gmap.p, lr.n_groups, N, E, cellbase.p, d_err.p)));
+
+    bool first = true;
     for (uint64_t l0 = 0; l0 < P; l0 += panel) {
         const uint64_t l1 = std::min<uint64_t>(P, l0 + panel);
         const uint64_t nl = l1 - l0;
-        const uint32_t kbs = static_cast<uint32_t>((nl + LOCI_PER_KB - 1) / LOCI_PER_KB);
-        mark(); // [3k] staging begins
-        SGPU_TRY(clear_kbs(kbs));
-        const unsigned grid = static_cast<unsigned>(std::min<uint64_t>(nl, static_cast<uint64_t>(sms) * 16));
-        if (stage_red) {
-            SGPU_LAUNCH(ctx, (stage_main_kernel<false><<<grid, 256, 0, st>>>(p->d_row_ptr, p->d_gid_base, lr.sp_bits.p, lr.gmap.p, lr.n_groups, N,
-                                                                             static_cast<uint32_t>(l0), static_cast<uint32_t>(l1),
-                                                                             static_cast<uint32_t>(l0), pl, U.p, d_err.p)));
-        } else {
-            SGPU_LAUNCH(ctx, (stage_main_kernel<true><<<grid, 256, 0, st>>>(p->d_row_ptr, p->d_gid_base, lr.sp_bits.p, lr.gmap.p, lr.n_groups, N,
-                                                                            static_cast<uint32_t>(l0), static_cast<uint32_t>(l1),
-                                                                            static_cast<uint32_t>(l0), pl, U.p, d_err.p)));
+        const uint32_t kbs_main = static_cast<uint32_t>((nl + LOCI_PER_KB - 1) / LOCI_PER_KB);
+        const uint32_t kt = first ? kbs_tail : 0;
+        if (!first) {
+            mark(); // [3k] staging begins
         }
-        if (lr.n_special) {
-            SGPU_LAUNCH(ctx, (stage_special_kernel<<<sp_blocks, 256, 0, st>>>(lr.sp_code.p, lr.sp_locus.p, lr.n_special, static_cast<uint32_t>(l0),
-                                                                             static_cast<uint32_t>(l1), static_cast<uint32_t>(l0), pl, U.p, d_err.p)));
+        StageArgs sa;
+        sa.row_ptr = p->d_row_ptr;
+        sa.cellbase = cellbase.p;
+        sa.n_pad = n_pad;
+        sa.sp_code = lr.sp_code.p;
+        sa.sp_locus = lr.sp_locus.p;
+        sa.n_special = lr.n_special;
+        sa.l0 = static_cast<uint32_t>(l0);
+        sa.nl = static_cast<uint32_t>(nl);
+        sa.kbs_main = kbs_main;
+        sa.tail_loci = lr.tail_loci.p;
+        sa.n_tail = kt ? static_cast<uint32_t>(lr.n_tail_loci) : 0;
+        sa.kbs_tail = kt;
+        sa.cells_per_cta = cells_per_cta;
+        sa.n_stripes = n_stripes;
+        sa.pl = pl;
+        sa.U = U.p;
+        sa.err = d_err.p;
+        SGPU_LAUNCH(ctx, (stage_tile_kernel<<<(kbs_main + kt) * n_stripes, ST_THREADS, st_smem, st>>>(sa)));
+        SGPU_CUDA(ctx, cudaGetLastError());
+        SGPU_TRACE(ctx, "gemm: stage");
+
+        WorkList wl;
+        wl.tiles = d_tiles;
+        wl.kbs = kbs_main + kt;
+        wl.ck_shift = pl.ck_shift;
+        wl.kb_neg0 = kbs_main;
+        wl.kb_negd = kt;
+        // whole tiles in full rounds of the grid; the rest (or everything, when there are few tiles) in
+        // K ranges so that every SM has work in the last round
+        wl.n_full = n_tiles >= 2 * sms ? n_tiles / sms * sms : 0;
+        const uint32_t rest = n_tiles - wl.n_full;
+        uint32_t splits = 1;
+        if (rest) {
+            const uint32_t target = wl.n_full ? sms : 2 * sms;
+            splits = static_cast<uint32_t>(std::min<uint64_t>(wl.kbs, std::max<uint32_t>(1, target / rest)));
         }
-        transform_kbs(kbs);
-        SGPU_TRACE(ctx, "gemm: stage main");
-        SGPU_TRY(gemm_panel(nl, +1));
+        wl.per = (wl.kbs + splits - 1) / splits;
+        wl.splits = (wl.kbs + wl.per - 1) / wl.per; // no empty range
+        wl.n_work = wl.n_full + rest * wl.splits;
+        // the planes are zero right after sgpu_counts_zero: the first panel stores, later ones add in place
+        const int epi = c->fresh ? EPI_STORE : EPI_RMW;
+        const unsigned grid = static_cast<unsigned>(std::min<uint64_t>(wl.n_work, sms));
+        mark(); // [3k+1] staging done, GEMM begins
+        SGPU_LAUNCH(ctx, (syrk_kernel<<<grid, GEMM_THREADS, SMEM_BYTES, st>>>(map, wl, c->i32 + PLANE_S * c->nn, c->i32 + PLANE_D * c->nn, N, 1, epi)));
+        SGPU_CUDA(ctx, cudaGetLastError());
+        c->fresh = false;
+        mark(); // [3k+2] GEMM done
+        ++ctx->n_syrk;
+        first = false;
+        SGPU_TRACE(ctx, "gemm: syrk");
     }
-    SGPU_TRACE(ctx, "gemm: main panels");
-    // The reference never compares two reads that both lie behind the per-chromosome cutoff K
-    // (SURVEY F2). Those pairs only exist at the few loci behind the cutoff: subtract Z Z^T, Z = counts
-    // of the tail reads alone at those loci, with the same kernel and sign -1.
-    for (uint64_t t0 = 0; t0 < lr.n_tail_loci; t0 += panel) {
-        const uint64_t nl = std::min<uint64_t>(lr.n_tail_loci - t0, panel);
-        const uint32_t kbs = static_cast<uint32_t>((nl + LOCI_PER_KB - 1) / LOCI_PER_KB);
-        mark();
-        SGPU_TRY(clear_kbs(kbs));
-        SGPU_LAUNCH(ctx, (stage_tail_kernel<<<static_cast<unsigned>(nl), 256, 0, st>>>(p->d_row_ptr, p->d_gid_base, lr.sp_bits.p, lr.gmap.p, lr.n_groups,
-                                                                                       N, lr.tail_loci.p + t0, pl, U.p, d_err.p)));
-        if (lr.n_special) {
-            SGPU_LAUNCH(ctx, (stage_tail_special_kernel<<<sp_blocks, 256, 0, st>>>(lr.sp_code.p, lr.sp_locus.p, lr.n_special, lr.tail_loci.p + t0,
-                                                                                  static_cast<uint32_t>(nl), pl, U.p, d_err.p)));
-        }
-        transform_kbs(kbs);
-        SGPU_TRY(gemm_panel(nl, -1));
-    }
-    SGPU_TRACE(ctx, "gemm: tail panels");
     SGPU_CUDA(ctx, cudaMemcpyAsync(&ctx->h_scratch[2], d_err.p, sizeof(int), cudaMemcpyDeviceToHost, st));
     SGPU_CUDA(ctx, cudaStreamSynchronize(st));
     for (size_t k = 0; k + 2 < evs.size(); k += 3) {
