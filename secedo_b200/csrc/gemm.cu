@@ -134,18 +134,19 @@ struct StageArgs {
     int *err;
 };
 
-__device__ __forceinline__ void tile_add(uint32_t *tile, uint32_t r, uint32_t j, uint32_t base, int *err) {
-    const uint32_t sh = 8u * base;
-    const uint32_t old = atomicAdd(&tile[r * 32 + ((j + r) & 31u)], 1u << sh);
-    if (((old >> sh) & 0xFFu) >= 127u) {
-        atomicExch(err, SGPU_E_COUNT_RANGE); // > 127 reads of one cell at one locus: outside int8
-    }
+// One count. Range check without looking at the old value: the CTA compares the number of counts it
+// added with the sum of the tile's bytes afterwards (a byte that wrapped past 255 loses 255 or 256),
+// and a byte above 127 is seen when the planes are built.
+__device__ __forceinline__ void tile_add(uint32_t *tile, uint32_t r, uint32_t j, uint32_t base) {
+    atomicAdd(&tile[r * 32 + ((j + r) & 31u)], 1u << (8u * base));
 }
 
 __global__ void __launch_bounds__(ST_THREADS, 1) stage_tile_kernel(const StageArgs a) {
     extern __shared__ uint32_t tile[]; // [cell in stripe][32 loci], word of locus j of row r at (j + r) % 32
     __shared__ uint64_t s_e0[32], s_e1[32];
     __shared__ uint32_t s_loc[32];
+    __shared__ uint32_t s_b[32];  // end of locus j relative to the first entry of the k-block (main mode)
+    __shared__ int s_balance;     // counts added - counts found in the tile
     __shared__ uint64_t s_sp0[32], s_sp1[32];
     // the stripes of one k-block are neighbours in the grid: they run together and share its entries in L2
     const uint32_t kb = blockIdx.x / a.n_stripes;
@@ -171,6 +172,10 @@ __global__ void __launch_bounds__(ST_THREADS, 1) stage_tile_kernel(const StageAr
         const uint64_t e_last = __shfl_sync(0xffffffffu, l != 0xFFFFFFFFu ? a.row_ptr[l + 1] : 0, 31 - __clz(__ballot_sync(0xffffffffu, l != 0xFFFFFFFFu) | 1u));
         s_e0[j] = l != 0xFFFFFFFFu ? a.row_ptr[l] : e_last;
         s_e1[j] = l != 0xFFFFFFFFu ? a.row_ptr[l + 1] : e_last;
+        s_b[j] = static_cast<uint32_t>(s_e1[j] - __shfl_sync(0xffffffffu, s_e0[j], 0));
+        if (j == 0) {
+            s_balance = 0;
+        }
         // the special entries of locus l: a contiguous range of the (ascending) list
         uint64_t r0 = 0, r1 = 0;
         if (l != 0xFFFFFFFFu) {
@@ -199,34 +204,38 @@ __global__ void __launch_bounds__(ST_THREADS, 1) stage_tile_kernel(const StageAr
 
     // ---- entries that are the only entry of their read (in a tail k-block all of them are tail reads:
     // such a read was created at its own locus, which lies behind the cutoff)
+    uint32_t n_added = 0;
     if (!tail) {
-        // the 32 loci are consecutive: one contiguous range of entries, 8 per 16-byte load
-        const uint64_t E0 = s_e0[0], E1 = s_e1[31];
-        for (uint64_t v = (E0 & ~7ull) + 8ull * threadIdx.x; v < E1; v += 8ull * ST_THREADS) {
-            const uint4 q = *reinterpret_cast<const uint4 *>(a.cellbase + v);
+        // the 32 loci are consecutive: one contiguous range of entries, 8 per 16-byte load; entry
+        // indices relative to the first entry of the k-block fit 32 bits
+        const uint64_t E0 = s_e0[0];
+        const uint32_t n_e = static_cast<uint32_t>(s_e1[31] - E0), off0 = static_cast<uint32_t>(E0 & 7u);
+        const uint16_t *cbp = a.cellbase + (E0 - off0);
+        for (uint32_t vi = threadIdx.x; vi * 8 < n_e + off0; vi += ST_THREADS) {
+            const uint4 q = *reinterpret_cast<const uint4 *>(cbp + 8ull * vi);
             const uint32_t w[4] = { q.x, q.y, q.z, q.w };
+            const int32_t i0 = static_cast<int32_t>(vi * 8) - static_cast<int32_t>(off0);
             // locus of the first entry of the vector that belongs to the k-block
-            const uint64_t ef = max(v, E0);
+            const uint32_t ef = static_cast<uint32_t>(max(i0, 0));
             uint32_t j = 0;
 #pragma unroll
             for (int step = 16; step > 0; step >>= 1) {
-                if (s_e1[j + step - 1] <= ef) {
+                if (s_b[j + step - 1] <= ef) {
                     j += step;
                 }
             }
+            uint32_t nb = s_b[j]; // end of locus j
 #pragma unroll
             for (int k = 0; k < 8; ++k) {
-                const uint64_t e = v + k;
+                const uint32_t i = static_cast<uint32_t>(i0 + k); // wraps for the entries before E0
                 const uint32_t cb = (w[k >> 1] >> (16 * (k & 1))) & 0xFFFFu;
-                if (e < E0 || e >= E1 || cb == CB_SKIP) {
-                    continue;
-                }
-                while (e >= s_e1[j]) {
-                    ++j;
+                while (static_cast<int32_t>(i) >= static_cast<int32_t>(nb) && j < 31) {
+                    nb = s_b[++j];
                 }
                 const uint32_t r = (cb >> 2) - c0;
-                if (r < nc) {
-                    tile_add(tile, r, j, cb & 3u, a.err);
+                if (i < n_e && cb != CB_SKIP && r < nc) {
+                    tile_add(tile, r, j, cb & 3u);
+                    ++n_added;
                 }
             }
         }
@@ -236,7 +245,8 @@ __global__ void __launch_bounds__(ST_THREADS, 1) stage_tile_kernel(const StageAr
                 const uint32_t cb = a.cellbase[e];
                 const uint32_t r = (cb >> 2) - c0;
                 if (cb != CB_SKIP && r < nc) {
-                    tile_add(tile, r, j, cb & 3u, a.err);
+                    tile_add(tile, r, j, cb & 3u);
+                    ++n_added;
                 }
             }
         }
@@ -250,7 +260,8 @@ __global__ void __launch_bounds__(ST_THREADS, 1) stage_tile_kernel(const StageAr
             }
             const uint32_t r = code_cell(c) - c0;
             if (r < nc) {
-                tile_add(tile, r, j, code_base(c), a.err);
+                tile_add(tile, r, j, code_base(c));
+                ++n_added;
             }
         }
     }
@@ -259,6 +270,7 @@ __global__ void __launch_bounds__(ST_THREADS, 1) stage_tile_kernel(const StageAr
     // ---- Hadamard planes, written as finished operand rows: 8 consecutive lanes own one 128-byte row
     const uint32_t kb_neg = kb + a.kbs_tail;
     bool bad = false;
+    int balance = static_cast<int>(n_added);
     for (uint32_t item = threadIdx.x; item < nc * 8; item += ST_THREADS) {
         const uint32_t r = item >> 3, g = item & 7;
         uint32_t w[4] = { 0, 0, 0, 0 }, wn[4] = { 0, 0, 0, 0 }; // per plane, 4 loci packed (and negated)
@@ -271,6 +283,7 @@ __global__ void __launch_bounds__(ST_THREADS, 1) stage_tile_kernel(const StageAr
             const int u2 = b0 + b1 - b2 - b3;
             const int u3 = b0 - b1 - b2 + b3;
             bad |= u0 > 127;
+            balance -= u0;
             w[0] |= static_cast<uint32_t>(u0 & 0xFF) << (8 * q);
             w[1] |= static_cast<uint32_t>(u1 & 0xFF) << (8 * q);
             w[2] |= static_cast<uint32_t>(u2 & 0xFF) << (8 * q);
@@ -293,7 +306,16 @@ __global__ void __launch_bounds__(ST_THREADS, 1) stage_tile_kernel(const StageAr
             }
         }
     }
-    if (bad) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        balance += __shfl_xor_sync(0xffffffffu, balance, o);
+    }
+    if ((threadIdx.x & 31) == 0 && balance) {
+        atomicAdd(&s_balance, balance);
+    }
+    __syncthreads();
+    // > 127 reads of one cell at one locus: outside int8 (a wrapped byte leaves the balance positive)
+    if (bad || (threadIdx.x == 0 && s_balance != 0)) {
         atomicExch(a.err, SGPU_E_COUNT_RANGE);
     }
 }

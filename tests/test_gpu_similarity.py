@@ -205,6 +205,28 @@ def test_auto_path_and_stats(gpu_ctx):
     assert gpu_ctx.launch_count() > n0
 
 
+@pytest.mark.parametrize("reps", [127, 128, 200, 256, 300, 520])
+def test_int8_count_range(gpu_ctx, reps):
+    """the GEMM path holds per-(cell, locus) base counts in int8: up to 127 reads of one cell at a locus
+    are exact, more must be refused (also when a byte of the packed counts wraps) — the scatter path
+    takes them"""
+    rid = iter(range(1, 10 ** 6))
+    loci = []
+    for i in range(40):
+        gb = [(0 << 2) | 1] * reps + [(1 << 2) | 2, (2 << 2) | 1, (3 << 2) | (i & 3)]
+        loci.append((100 + 30 * i, [next(rid) for _ in gb], gb))
+    p = Pileup.from_pos_data([loci])
+    ident = np.arange(4, dtype=np.uint32)
+    ref = api.compute_similarity_matrix(p, 4, 1000, ident, 0.01, 0.5, 0.01, 1, ctx=gpu_ctx, path="scatter")
+    if reps <= 127:
+        M = api.compute_similarity_matrix(p, 4, 1000, ident, 0.01, 0.5, 0.01, 1, ctx=gpu_ctx, path="gemm")
+        assert_matrix_close(M, ref, TOL)
+        assert_matrix_close(M, po.similarity(p, 4, 1000, ident, 0.01, 0.5, 0.01, 1).M, TOL)
+    else:
+        with pytest.raises(api.SgpuError):
+            api.compute_similarity_matrix(p, 4, 1000, ident, 0.01, 0.5, 0.01, 1, ctx=gpu_ctx, path="gemm")
+
+
 def test_huge_loci(gpu_ctx):
     """loci of > 11 000 entries: the shared-memory link table runs at its largest geometry"""
     cfg = SynthConfig(n_cells=3000, coverage=4.0, n_loci=8, n_chr=1, frac_somatic=1.0, frac_germline=0.0,
