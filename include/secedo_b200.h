@@ -150,7 +150,7 @@ int sgpu_counts_accumulate(sgpu_ctx *ctx, sgpu_counts *c, const sgpu_pileup *fil
  * call sgpu_counts_set_layout (buffers may move), then fetch the pointers again. */
 int sgpu_counts_buffers(sgpu_counts *c, int32_t **i32, uint64_t *n_i32, double **f64, uint64_t *n_f64,
                         uint64_t **hist, uint64_t *n_hist);
-int sgpu_counts_set_layout(sgpu_ctx *ctx, sgpu_counts *c, int planes_used /* 2 or 9 */, int want_spill);
+int sgpu_counts_set_layout(sgpu_ctx *ctx, sgpu_counts *c, int planes_used /* 2, 5 or 9 */, int want_spill);
 /* Symmetric per-cell-pair integers for bit-exact checks (any pointer may be NULL):
  *   S1, D1  num_cells^2 int32: incidences (read pair, shared locus) with equal / different base
  *   H       3*num_cells^2 int32: read pairs in overlap class (2,0), (1,1), (0,2)

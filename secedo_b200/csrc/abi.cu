@@ -164,6 +164,9 @@ void sgpu_shutdown(sgpu_ctx *ctx) {
         if (ctx->tile_cache) {
             cudaFree(ctx->tile_cache);
         }
+        if (ctx->ep_tiles) {
+            cudaFree(ctx->ep_tiles);
+        }
         if (ctx->h_scratch) {
             cudaFreeHost(ctx->h_scratch);
         }
@@ -340,12 +343,14 @@ int sgpu_counts_create(sgpu_ctx *ctx, uint32_t num_cells, sgpu_counts **out) {
 
 int sgpu_counts_zero(sgpu_ctx *ctx, sgpu_counts *c) {
     SGPU_CUDA(ctx, cudaSetDevice(ctx->device));
-    SGPU_CUDA(ctx, cudaMemsetAsync(c->i32, 0, N_PLANES * c->nn * sizeof(int32_t), ctx->stream));
+    // only the planes that were used since the last zeroing can be non-zero
+    SGPU_CUDA(ctx, cudaMemsetAsync(c->i32, 0, static_cast<uint64_t>(c->planes_dirty) * c->nn * sizeof(int32_t), ctx->stream));
     SGPU_CUDA(ctx, cudaMemsetAsync(c->hist, 0, SGPU_MAX_CLASS * SGPU_MAX_CLASS * sizeof(uint64_t), ctx->stream));
     if (c->spill) {
         SGPU_CUDA(ctx, cudaMemsetAsync(c->spill, 0, c->nn * sizeof(double), ctx->stream));
     }
     c->planes_used = 2;
+    c->planes_dirty = 2;
     c->have_params = false;
     c->fresh = true;
     return SGPU_OK;
@@ -422,6 +427,7 @@ int sgpu_counts_accumulate(sgpu_ctx *ctx, sgpu_counts *c, const sgpu_pileup *fil
         SGPU_TRY(sgpu_multilocus(ctx, filtered, lr, c, max_fragment_length, &s.n_pairs_multi));
         s.ms_multi = t.stop();
     }
+    c->planes_dirty = std::max(c->planes_dirty, c->planes_used);
     if (stats) {
         *stats = s;
     }
@@ -456,10 +462,11 @@ int sgpu_counts_buffers(sgpu_counts *c, int32_t **i32, uint64_t *n_i32, double *
 
 int sgpu_counts_set_layout(sgpu_ctx *ctx, sgpu_counts *c, int planes_used, int want_spill) {
     SGPU_CUDA(ctx, cudaSetDevice(ctx->device));
-    if (planes_used != 2 && planes_used != N_PLANES) {
-        return sgpu_fail(ctx, SGPU_E_ARG, "planes_used must be 2 or %d", N_PLANES);
+    if (planes_used != 2 && planes_used != PLANE_H3 && planes_used != N_PLANES) {
+        return sgpu_fail(ctx, SGPU_E_ARG, "planes_used must be 2, %d or %d", PLANE_H3, N_PLANES);
     }
     c->planes_used = std::max(c->planes_used, planes_used);
+    c->planes_dirty = std::max(c->planes_dirty, c->planes_used);
     if (want_spill && !c->spill) {
         SGPU_CUDA(ctx, cudaMalloc(&c->spill, std::max<uint64_t>(1, c->nn) * sizeof(double)));
         SGPU_CUDA(ctx, cudaMemsetAsync(c->spill, 0, c->nn * sizeof(double), ctx->stream));

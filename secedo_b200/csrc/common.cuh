@@ -32,6 +32,12 @@ struct sgpu_ctx {
     // gemm.cu: rasterised list of upper-triangle output tiles for tile_cache_cells cells (device memory)
     void *tile_cache = nullptr;
     uint32_t tile_cache_n = 0, tile_cache_cells = 0;
+    // epilogue.cu: F / G coefficients of the last likelihood parameters, tile list of the last matrix size
+    bool ft_valid = false;
+    double ft_eps = 0, ft_h = 0, ft_theta = 0, ft_f10 = 0, ft_f01 = 0, ft_g2[3] = { 0, 0, 0 }, ft_g3[4] = { 0, 0, 0, 0 };
+    uint32_t ft_L = 0;
+    void *ep_tiles = nullptr;
+    uint32_t ep_tiles_n = 0;
     // Device memory cache (abi.cu): temporaries and pileups are re-created with identical sizes at every
     // call, and cudaMallocAsync/cudaFreeAsync of GB-sized blocks cost milliseconds each, so freed blocks
     // are kept and handed out again. Reuse is safe because all work of a context is ordered on ONE stream.
@@ -138,7 +144,8 @@ struct sgpu_counts {
     uint32_t n = 0;             // num_cells
     uint64_t nn = 0;            // n*n
     int32_t *i32 = nullptr;     // N_PLANES planes of n*n, only the upper triangle (i<j) is meaningful
-    int planes_used = 2;        // 2, 5 or 9
+    int planes_used = 2;        // 2, 5 or 9: planes that can be non-zero
+    int planes_dirty = N_PLANES; // planes to clear at the next sgpu_counts_zero
     bool fresh = false;         // S and D are all zero (nothing accumulated since sgpu_counts_zero)
     double *spill = nullptr;    // n*n doubles: sum of G(x_s,x_d) over pairs with x_s+x_d >= 4 (lazy)
     uint64_t *hist = nullptr;   // SGPU_MAX_CLASS^2 class histogram (pairs with x_s+x_d >= 2)

@@ -167,56 +167,58 @@ struct TransformArgs {
 
 constexpr int TR_THREADS = 256;
 
-__global__ void __launch_bounds__(TR_THREADS) transform_kernel(TransformArgs a, double *__restrict__ raw,
-                                                              unsigned long long *__restrict__ minmax) {
-    // one thread per element of the upper triangle incl. diagonal, addressed as (i, j) of the full
-    // matrix; elements below the diagonal are written by their mirror
-    const uint64_t idx = static_cast<uint64_t>(blockIdx.x) * TR_THREADS + threadIdx.x;
-    double v = 0.0;
-    bool valid = false;
-    if (idx < a.nn) {
-        const uint32_t i = static_cast<uint32_t>(idx / a.n), j = static_cast<uint32_t>(idx % a.n);
-        if (i < j) {
-            valid = true;
-            v = a.f10 * a.i32[PLANE_S * a.nn + idx] + a.f01 * a.i32[PLANE_D * a.nn + idx];
-            if (a.planes_used > 2) {
+// raw[i][j] = F(1,0) S + F(0,1) D + sum G(s,d) N_sd  (the upper triangle of mat_diff - mat_same)
+__device__ __forceinline__ double raw_value(const TransformArgs &a, uint64_t idx) {
+    double v = a.f10 * a.i32[PLANE_S * a.nn + idx] + a.f01 * a.i32[PLANE_D * a.nn + idx];
+    if (a.planes_used > 2) {
 #pragma unroll
-                for (int k = 0; k < 3; ++k) {
-                    const int32_t h = a.i32[(PLANE_H2 + k) * a.nn + idx];
-                    if (h) {
-                        v += a.g2[k] * h;
-                    }
-                }
-#pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                    const int32_t h = a.i32[(PLANE_H3 + k) * a.nn + idx];
-                    if (h) {
-                        v += a.g3[k] * h;
-                    }
-                }
+        for (int k = 0; k < 3; ++k) {
+            const int32_t h = a.i32[(PLANE_H2 + k) * a.nn + idx];
+            if (h) {
+                v += a.g2[k] * h;
             }
-            if (a.spill) {
-                v += a.spill[idx];
-            }
-            raw[idx] = v;
-            raw[static_cast<uint64_t>(j) * a.n + i] = v;
-        } else if (i == j) {
-            valid = true;
-            raw[idx] = 0.0; // mat_same and mat_diff have an all-zero diagonal
         }
     }
-    // block reduce of min / max over the elements this block produced (the diagonal zeros count,
-    // util/mat.hpp:35-53 scans the whole matrix)
-    double mn = valid ? v : DBL_MAX, mx = valid ? v : -DBL_MAX;
+    if (a.planes_used > PLANE_H3) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const int32_t h = a.i32[(PLANE_H3 + k) * a.nn + idx];
+            if (h) {
+                v += a.g3[k] * h;
+            }
+        }
+    }
+    if (a.spill) {
+        v += a.spill[idx];
+    }
+    return v;
+}
+
+// max (and min) of the raw matrix over the upper triangle; the zero diagonal counts, util/mat.hpp:35-53
+// scans the whole matrix. One CTA per 32 x 32 tile of the upper triangle of tiles.
+__global__ void __launch_bounds__(TR_THREADS) minmax_kernel(TransformArgs a, const uint2 *__restrict__ tiles,
+                                                           unsigned long long *__restrict__ minmax) {
+    const uint2 t = tiles[blockIdx.x];
+    const uint32_t tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    double mn = 0.0, mx = 0.0; // the diagonal
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const uint32_t i = t.x * 32 + ty + 8 * k, j = t.y * 32 + tx;
+        if (i < j && j < a.n) {
+            const double v = raw_value(a, static_cast<uint64_t>(i) * a.n + j);
+            mn = fmin(mn, v);
+            mx = fmax(mx, v);
+        }
+    }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
         mn = fmin(mn, __shfl_xor_sync(0xffffffffu, mn, o));
         mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
     }
     __shared__ double s_mn[TR_THREADS / 32], s_mx[TR_THREADS / 32];
-    if ((threadIdx.x & 31) == 0) {
-        s_mn[threadIdx.x >> 5] = mn;
-        s_mx[threadIdx.x >> 5] = mx;
+    if (tx == 0) {
+        s_mn[ty] = mn;
+        s_mx[ty] = mx;
     }
     __syncthreads();
     if (threadIdx.x == 0) {
@@ -224,27 +226,23 @@ __global__ void __launch_bounds__(TR_THREADS) transform_kernel(TransformArgs a, 
             mn = fmin(mn, s_mn[w]);
             mx = fmax(mx, s_mx[w]);
         }
-        if (mn != DBL_MAX) {
-            atomicMin(&minmax[0], enc(mn));
-            atomicMax(&minmax[1], enc(mx));
-        }
+        atomicMin(&minmax[0], enc(mn));
+        atomicMax(&minmax[1], enc(mx));
     }
 }
 
-__global__ void __launch_bounds__(TR_THREADS) normalize_kernel(double *__restrict__ m, uint32_t n, uint64_t nn,
-                                                              int normalization, double mn, double mx) {
-    const uint64_t idx = static_cast<uint64_t>(blockIdx.x) * TR_THREADS + threadIdx.x;
-    if (idx >= nn) {
-        return;
-    }
-    const uint32_t i = static_cast<uint32_t>(idx / n), j = static_cast<uint32_t>(idx % n);
-    double v = m[idx];
+__device__ __forceinline__ double dec_dev(unsigned long long u) {
+    const unsigned long long v = (u >> 63) ? (u & 0x7FFFFFFFFFFFFFFFull) : ~u;
+    return __longlong_as_double(static_cast<long long>(v));
+}
+
+// similarity_matrix.cpp:271-293 on one element
+__device__ __forceinline__ double normalized(double v, int normalization, double mx) {
     switch (normalization) {
-        case SGPU_NORM_ADD_MIN: { // M *= -1; M += |min(M)|   (min(-raw) = -max(raw))
+        case SGPU_NORM_ADD_MIN: // M *= -1; M += |min(M)|   (min(-raw) = -max(raw))
             v = v * -1;
             v += fabs(-mx);
             break;
-        }
         case SGPU_NORM_EXPONENTIATE:
             v = 1. / (exp(v) + 1);
             break;
@@ -252,8 +250,51 @@ __global__ void __launch_bounds__(TR_THREADS) normalize_kernel(double *__restric
             v = v * (1. / mx);
             break;
     }
-    (void)mn;
-    m[idx] = i == j ? 0.0 : v; // fill_diagonal(0), similarity_matrix.cpp:292
+    return v;
+}
+
+// The whole output in one pass: every 32 x 32 tile of the upper triangle is evaluated once, normalised,
+// written as rows (i, j..) and, through a shared-memory transpose, as rows (j, i..) of the mirror
+// image; the diagonal is zero (fill_diagonal(0), :292).
+__global__ void __launch_bounds__(TR_THREADS) finalize_kernel(TransformArgs a, const uint2 *__restrict__ tiles,
+                                                             const unsigned long long *__restrict__ minmax,
+                                                             int normalization, double *__restrict__ out) {
+    __shared__ double tile[32][33];
+    const uint2 t = tiles[blockIdx.x];
+    const uint32_t tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    const double mx = dec_dev(minmax[1]);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const uint32_t r = ty + 8 * k;
+        const uint32_t i = t.x * 32 + r, j = t.y * 32 + tx;
+        double v = 0.0;
+        if (i < j && j < a.n) {
+            v = normalized(raw_value(a, static_cast<uint64_t>(i) * a.n + j), normalization, mx);
+        }
+        tile[r][tx] = v;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const uint32_t r = ty + 8 * k;
+        // rows of the tile itself
+        uint32_t i = t.x * 32 + r, j = t.y * 32 + tx;
+        if (i < a.n && j < a.n) {
+            if (i < j) {
+                out[static_cast<uint64_t>(i) * a.n + j] = tile[r][tx];
+            } else if (t.x == t.y) { // diagonal tile: zero diagonal, lower half mirrored
+                out[static_cast<uint64_t>(i) * a.n + j] = i == j ? 0.0 : tile[tx][r];
+            }
+        }
+        // rows of the mirrored tile
+        if (t.x != t.y) {
+            i = t.y * 32 + r;
+            j = t.x * 32 + tx;
+            if (i < a.n && j < a.n) {
+                out[static_cast<uint64_t>(i) * a.n + j] = tile[tx][r];
+            }
+        }
+    }
 }
 
 int device_log_probs(sgpu_ctx *ctx, double eps, double h, double theta, uint32_t L, uint32_t n, DevBuf<double> &ls,
@@ -310,57 +351,81 @@ int sgpu_epilogue(sgpu_ctx *ctx, sgpu_counts *c, uint32_t L, double eps, double 
     if (c->nn == 0) {
         return SGPU_OK;
     }
-    // classes needed by the integer planes: all (s,d) with s + d <= 3
-    DevBuf<double> d_G, d_F, raw;
-    DevBuf<unsigned long long> d_minmax;
-    SGPU_CUDA(ctx, d_G.alloc(SGPU_MAX_CLASS * SGPU_MAX_CLASS, ctx));
-    SGPU_CUDA(ctx, d_F.alloc(SGPU_MAX_CLASS * SGPU_MAX_CLASS, ctx));
-    SGPU_TRY(sgpu_build_gtable(ctx, eps, h, theta, L, 4, d_G.p, d_F.p));
-    std::vector<double> G(SGPU_MAX_CLASS * SGPU_MAX_CLASS), F(SGPU_MAX_CLASS * SGPU_MAX_CLASS);
-    SGPU_CUDA(ctx, cudaMemcpyAsync(G.data(), d_G.p, G.size() * sizeof(double), cudaMemcpyDeviceToHost, st));
-    SGPU_CUDA(ctx, cudaMemcpyAsync(F.data(), d_F.p, F.size() * sizeof(double), cudaMemcpyDeviceToHost, st));
-    SGPU_CUDA(ctx, cudaStreamSynchronize(st));
-
+    // F and G for the classes of the integer planes (s + d <= 3); kept for the next call with the same
+    // likelihood parameters (divide_cluster calls with the same ones at every node of its recursion)
+    if (!(ctx->ft_valid && ctx->ft_eps == eps && ctx->ft_h == h && ctx->ft_theta == theta && ctx->ft_L == L)) {
+        DevBuf<double> d_G, d_F;
+        SGPU_CUDA(ctx, d_G.alloc(SGPU_MAX_CLASS * SGPU_MAX_CLASS, ctx));
+        SGPU_CUDA(ctx, d_F.alloc(SGPU_MAX_CLASS * SGPU_MAX_CLASS, ctx));
+        SGPU_TRY(sgpu_build_gtable(ctx, eps, h, theta, L, 4, d_G.p, d_F.p));
+        std::vector<double> G(SGPU_MAX_CLASS * SGPU_MAX_CLASS), F(SGPU_MAX_CLASS * SGPU_MAX_CLASS);
+        SGPU_CUDA(ctx, cudaMemcpyAsync(G.data(), d_G.p, G.size() * sizeof(double), cudaMemcpyDeviceToHost, st));
+        SGPU_CUDA(ctx, cudaMemcpyAsync(F.data(), d_F.p, F.size() * sizeof(double), cudaMemcpyDeviceToHost, st));
+        SGPU_CUDA(ctx, cudaStreamSynchronize(st));
+        ctx->ft_f10 = F[1 * SGPU_MAX_CLASS + 0];
+        ctx->ft_f01 = F[0 * SGPU_MAX_CLASS + 1];
+        for (int d = 0; d < 3; ++d) {
+            ctx->ft_g2[d] = G[(2 - d) * SGPU_MAX_CLASS + d];
+        }
+        for (int d = 0; d < 4; ++d) {
+            ctx->ft_g3[d] = G[(3 - d) * SGPU_MAX_CLASS + d];
+        }
+        ctx->ft_eps = eps;
+        ctx->ft_h = h;
+        ctx->ft_theta = theta;
+        ctx->ft_L = L;
+        ctx->ft_valid = true;
+    }
     TransformArgs a;
     a.i32 = c->i32;
     a.spill = c->spill;
     a.n = c->n;
     a.nn = c->nn;
     a.planes_used = c->planes_used;
-    a.f10 = F[1 * SGPU_MAX_CLASS + 0];
-    a.f01 = F[0 * SGPU_MAX_CLASS + 1];
+    a.f10 = ctx->ft_f10;
+    a.f01 = ctx->ft_f01;
     for (int d = 0; d < 3; ++d) {
-        a.g2[d] = G[(2 - d) * SGPU_MAX_CLASS + d];
+        // NaN: class impossible with this max_fragment_length; its plane is all zero
+        a.g2[d] = std::isnan(ctx->ft_g2[d]) ? 0.0 : ctx->ft_g2[d];
     }
     for (int d = 0; d < 4; ++d) {
-        a.g3[d] = G[(3 - d) * SGPU_MAX_CLASS + d];
+        a.g3[d] = std::isnan(ctx->ft_g3[d]) ? 0.0 : ctx->ft_g3[d];
     }
-    if (c->planes_used > 2) {
-        for (int d = 0; d < 3; ++d) {
-            if (std::isnan(a.g2[d])) {
-                a.g2[d] = 0.0; // class impossible with this max_fragment_length; its plane is all zero
+    // 32 x 32 tiles of the upper triangle (list kept on the device per matrix size)
+    const uint32_t nb = (c->n + 31) / 32;
+    const uint32_t n_tiles = nb * (nb + 1) / 2;
+    if (!(ctx->ep_tiles && ctx->ep_tiles_n == c->n)) {
+        std::vector<uint2> tiles;
+        tiles.reserve(n_tiles);
+        for (uint32_t bi = 0; bi < nb; ++bi) {
+            for (uint32_t bj = bi; bj < nb; ++bj) {
+                tiles.push_back(make_uint2(bi, bj));
             }
         }
-        for (int d = 0; d < 4; ++d) {
-            if (std::isnan(a.g3[d])) {
-                a.g3[d] = 0.0;
-            }
+        if (ctx->ep_tiles) {
+            SGPU_CUDA(ctx, cudaStreamSynchronize(st));
+            SGPU_CUDA(ctx, cudaFree(ctx->ep_tiles));
+            ctx->ep_tiles = nullptr;
         }
+        SGPU_CUDA(ctx, cudaMalloc(&ctx->ep_tiles, tiles.size() * sizeof(uint2)));
+        SGPU_CUDA(ctx, cudaMemcpy(ctx->ep_tiles, tiles.data(), tiles.size() * sizeof(uint2), cudaMemcpyHostToDevice));
+        ctx->ep_tiles_n = c->n;
     }
-    SGPU_CUDA(ctx, raw.alloc(c->nn, ctx));
+    const uint2 *d_tiles = static_cast<const uint2 *>(ctx->ep_tiles);
+    DevBuf<double> out;
+    DevBuf<unsigned long long> d_minmax;
+    SGPU_CUDA(ctx, out.alloc(c->nn, ctx));
     SGPU_CUDA(ctx, d_minmax.alloc(2, ctx));
-    const unsigned long long init[2] = { ~0ull, 0ull };
-    SGPU_CUDA(ctx, cudaMemcpyAsync(d_minmax.p, init, sizeof(init), cudaMemcpyHostToDevice, st));
-    const unsigned grid = static_cast<unsigned>(ceil_div_u64(c->nn, TR_THREADS));
-    SGPU_LAUNCH(ctx, (transform_kernel<<<grid, TR_THREADS, 0, st>>>(a, raw.p, d_minmax.p)));
-    SGPU_CUDA(ctx, cudaGetLastError());
-    SGPU_CUDA(ctx, cudaMemcpyAsync(&ctx->h_scratch[0], d_minmax.p, 2 * sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
-    SGPU_CUDA(ctx, cudaStreamSynchronize(st));
-    const double mn = dec(ctx->h_scratch[0]), mx = dec(ctx->h_scratch[1]);
-    SGPU_LAUNCH(ctx, (normalize_kernel<<<grid, TR_THREADS, 0, st>>>(raw.p, c->n, c->nn, normalization, mn, mx)));
+    // min starts at +inf, max at -inf in the ordered encoding; both kernels also see the zero diagonal
+    SGPU_CUDA(ctx, cudaMemsetAsync(d_minmax.p, 0xFF, sizeof(unsigned long long), st));
+    SGPU_CUDA(ctx, cudaMemsetAsync(d_minmax.p + 1, 0x00, sizeof(unsigned long long), st));
+    if (normalization != SGPU_NORM_EXPONENTIATE) { // the only normalisation that does not need max(M)
+        SGPU_LAUNCH(ctx, (minmax_kernel<<<n_tiles, TR_THREADS, 0, st>>>(a, d_tiles, d_minmax.p)));
+    }
+    SGPU_LAUNCH(ctx, (finalize_kernel<<<n_tiles, TR_THREADS, 0, st>>>(a, d_tiles, d_minmax.p, normalization, out.p)));
     SGPU_CUDA(ctx, cudaGetLastError());
     if (h_out) { // NULL: leave the result on the device (timing of the device-resident path)
-        SGPU_CUDA(ctx, cudaMemcpyAsync(h_out, raw.p, c->nn * sizeof(double), cudaMemcpyDeviceToHost, st));
+        SGPU_CUDA(ctx, cudaMemcpyAsync(h_out, out.p, c->nn * sizeof(double), cudaMemcpyDeviceToHost, st));
     }
     SGPU_CUDA(ctx, cudaStreamSynchronize(st));
     return SGPU_OK;

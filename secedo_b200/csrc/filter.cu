@@ -100,53 +100,113 @@ __device__ bool is_significant_dev(uint32_t c0, uint32_t c1, uint32_t c2, uint32
 
 constexpr int FILTER_THREADS = 256;
 
+// One CTA per locus (grid-stride); 8 entries per 16-byte load once the row is aligned.
 __global__ void __launch_bounds__(FILTER_THREADS) filter_count_kernel(
         const uint64_t *__restrict__ row_ptr, const uint16_t *__restrict__ gid_base, uint64_t n_loci,
-        const uint32_t *__restrict__ in_mask /* bit per group id */, uint32_t n_groups, FilterParams fp,
-        uint8_t *__restrict__ keep, uint32_t *__restrict__ kept_cnt, int *__restrict__ err) {
+        const uint32_t *__restrict__ in_mask /* bit per group id */, uint32_t n_groups,
+        uint4 *__restrict__ counts /* pooled A, C, G, T per locus */, int *__restrict__ err) {
     extern __shared__ uint32_t s_mask[];
+    __shared__ uint32_t s_cnt[4];
+    __shared__ int s_bad;
     const uint32_t mask_words = (n_groups + 31) / 32;
     for (uint32_t i = threadIdx.x; i < mask_words; i += blockDim.x) {
         s_mask[i] = in_mask[i];
     }
+    if (threadIdx.x < 4) {
+        s_cnt[threadIdx.x] = 0;
+    }
+    if (threadIdx.x == 0) {
+        s_bad = 0;
+    }
     __syncthreads();
     const int lane = threadIdx.x & 31;
-    const uint64_t warps_total = static_cast<uint64_t>(gridDim.x) * (FILTER_THREADS / 32);
-    for (uint64_t l = static_cast<uint64_t>(blockIdx.x) * (FILTER_THREADS / 32) + (threadIdx.x >> 5); l < n_loci;
-         l += warps_total) {
+    for (uint64_t l = blockIdx.x; l < n_loci; l += gridDim.x) {
         const uint64_t e0 = row_ptr[l], e1 = row_ptr[l + 1];
-        // per-lane counters packed 4 x 16 bit would overflow above 64k reads per lane; keep 32-bit
-        uint32_t c0 = 0, c1 = 0, c2 = 0, c3 = 0;
+        // per-thread counters packed 4 x 16 bit would overflow above 64k reads per thread; keep 32-bit
+        uint32_t c[4] = { 0, 0, 0, 0 };
         bool bad = false;
-        for (uint64_t e = e0 + lane; e < e1; e += 32) {
-            const uint32_t gb = gid_base[e];
+        auto count = [&](uint32_t gb) {
             const uint32_t gid = gb >> 2;
             if (gid >= n_groups) {
                 bad = true;
-                continue;
+                return;
             }
             const uint32_t in = (s_mask[gid >> 5] >> (gid & 31)) & 1u;
             const uint32_t b = gb & 3u;
-            c0 += in & (b == 0);
-            c1 += in & (b == 1);
-            c2 += in & (b == 2);
-            c3 += in & (b == 3);
+            c[0] += in & (b == 0);
+            c[1] += in & (b == 1);
+            c[2] += in & (b == 2);
+            c[3] += in & (b == 3);
+        };
+        // 16-byte aligned middle part (none if the caller's array itself is not aligned)
+        const bool aligned = (reinterpret_cast<uintptr_t>(gid_base) & 15u) == 0;
+        const uint64_t up = (e0 + 7) & ~static_cast<uint64_t>(7), down = e1 & ~static_cast<uint64_t>(7);
+        const uint64_t a0 = up < e1 ? up : e1, a1 = (aligned && down > a0) ? down : a0;
+        for (uint64_t e = e0 + threadIdx.x; e < a0; e += FILTER_THREADS) {
+            count(gid_base[e]);
+        }
+        for (uint64_t v = a0 + 8ull * threadIdx.x; v < a1; v += 8ull * FILTER_THREADS) {
+            const uint4 q = *reinterpret_cast<const uint4 *>(gid_base + v);
+            const uint32_t w[4] = { q.x, q.y, q.z, q.w };
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                count((w[k >> 1] >> (16 * (k & 1))) & 0xFFFFu);
+            }
+        }
+        for (uint64_t e = a1 + threadIdx.x; e < e1; e += FILTER_THREADS) {
+            count(gid_base[e]);
         }
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) {
-            c0 += __shfl_xor_sync(0xffffffffu, c0, o);
-            c1 += __shfl_xor_sync(0xffffffffu, c1, o);
-            c2 += __shfl_xor_sync(0xffffffffu, c2, o);
-            c3 += __shfl_xor_sync(0xffffffffu, c3, o);
-        }
-        if (__any_sync(0xffffffffu, bad) && lane == 0) {
-            atomicExch(err, SGPU_E_CELL_RANGE);
+#pragma unroll
+            for (int b = 0; b < 4; ++b) {
+                c[b] += __shfl_xor_sync(0xffffffffu, c[b], o);
+            }
         }
         if (lane == 0) {
-            const bool sig = is_significant_dev(c0, c1, c2, c3, fp);
-            keep[l] = sig ? 1 : 0;
-            kept_cnt[l] = sig ? (c0 + c1 + c2 + c3) : 0;
+#pragma unroll
+            for (int b = 0; b < 4; ++b) {
+                if (c[b]) {
+                    atomicAdd(&s_cnt[b], c[b]);
+                }
+            }
         }
+        if (bad) {
+            s_bad = 1;
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            if (s_bad) {
+                atomicExch(err, SGPU_E_CELL_RANGE);
+            }
+            counts[l] = make_uint4(s_cnt[0], s_cnt[1], s_cnt[2], s_cnt[3]);
+            s_cnt[0] = s_cnt[1] = s_cnt[2] = s_cnt[3] = 0;
+            s_bad = 0;
+        }
+        __syncthreads();
+    }
+}
+
+// the Bayesian test, one thread per locus (fp64 pow / log: kept out of the counting CTAs)
+__global__ void __launch_bounds__(FILTER_THREADS) filter_decide_kernel(const uint4 *__restrict__ counts, uint64_t n_loci,
+                                                                      FilterParams fp, uint8_t *__restrict__ keep,
+                                                                      uint32_t *__restrict__ kept_cnt,
+                                                                      unsigned int *__restrict__ max_kept) {
+    const uint64_t l = static_cast<uint64_t>(blockIdx.x) * FILTER_THREADS + threadIdx.x;
+    unsigned int n = 0;
+    if (l < n_loci) {
+        const uint4 c = counts[l];
+        const bool sig = is_significant_dev(c.x, c.y, c.z, c.w, fp);
+        n = sig ? c.x + c.y + c.z + c.w : 0;
+        keep[l] = sig ? 1 : 0;
+        kept_cnt[l] = n;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        n = max(n, __shfl_xor_sync(0xffffffffu, n, o));
+    }
+    if ((threadIdx.x & 31) == 0 && n) {
+        atomicMax(max_kept, n);
     }
 }
 
@@ -277,6 +337,9 @@ int sgpu_filter_impl(sgpu_ctx *ctx, const sgpu_pileup *in, const uint32_t *h_id_
     DevBuf<uint8_t> d_keep;
     DevBuf<uint64_t> d_new_locus, d_new_row;
     DevBuf<int> d_err;
+    DevBuf<unsigned int> d_maxk;
+    SGPU_CUDA(ctx, d_maxk.alloc(1, ctx));
+    SGPU_CUDA(ctx, cudaMemsetAsync(d_maxk.p, 0, sizeof(unsigned int), st));
     SGPU_CUDA(ctx, d_mask.alloc(h_mask.size(), ctx));
     SGPU_CUDA(ctx, d_cnt.alloc(P, ctx));
     SGPU_CUDA(ctx, d_keep.alloc(P, ctx));
@@ -294,8 +357,13 @@ int sgpu_filter_impl(sgpu_ctx *ctx, const sgpu_pileup *in, const uint32_t *h_id_
         SGPU_CUDA(ctx, cudaFuncSetAttribute(filter_compact_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     }
     if (P) {
-        SGPU_LAUNCH(ctx, (filter_count_kernel<<<grid, FILTER_THREADS, smem, st>>>(in->d_row_ptr, in->d_gid_base, P, d_mask.p, n_groups, fp,
-                                                               d_keep.p, d_cnt.p, d_err.p)));
+        const unsigned cgrid = static_cast<unsigned>(std::min<uint64_t>(P, static_cast<uint64_t>(ctx->sm_count) * 16));
+        DevBuf<uint4> d_counts;
+        SGPU_CUDA(ctx, d_counts.alloc(P, ctx));
+        SGPU_LAUNCH(ctx, (filter_count_kernel<<<cgrid, FILTER_THREADS, smem, st>>>(in->d_row_ptr, in->d_gid_base, P, d_mask.p, n_groups,
+                                                                                   d_counts.p, d_err.p)));
+        SGPU_LAUNCH(ctx, (filter_decide_kernel<<<static_cast<unsigned>(ceil_div_u64(P, FILTER_THREADS)), FILTER_THREADS, 0, st>>>(
+                                 d_counts.p, P, fp, d_keep.p, d_cnt.p, d_maxk.p)));
         SGPU_CUDA(ctx, cudaGetLastError());
     }
     SGPU_TRY(sgpu_scan_u8_u64(ctx, d_keep.p, d_new_locus.p, P));
@@ -304,6 +372,7 @@ int sgpu_filter_impl(sgpu_ctx *ctx, const sgpu_pileup *in, const uint32_t *h_id_
     SGPU_CUDA(ctx, cudaMemcpyAsync(&ctx->h_scratch[0], d_new_locus.p + P, sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
     SGPU_CUDA(ctx, cudaMemcpyAsync(&ctx->h_scratch[1], d_new_row.p + P, sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
     SGPU_CUDA(ctx, cudaMemcpyAsync(&ctx->h_scratch[2], d_err.p, sizeof(int), cudaMemcpyDeviceToHost, st));
+    SGPU_CUDA(ctx, cudaMemcpyAsync(&ctx->h_scratch[3], d_maxk.p, sizeof(unsigned int), cudaMemcpyDeviceToHost, st));
     SGPU_CUDA(ctx, cudaStreamSynchronize(st));
     if (static_cast<int>(ctx->h_scratch[2] & 0xFFFFFFFFu) != 0) {
         return sgpu_fail(ctx, SGPU_E_CELL_RANGE, "pileup holds a group id >= n_groups (%u)", n_groups);
@@ -314,6 +383,7 @@ int sgpu_filter_impl(sgpu_ctx *ctx, const sgpu_pileup *in, const uint32_t *h_id_
     out->n_chr = in->n_chr;
     out->n_loci = Lk;
     out->n_entries = Ek;
+    out->max_row = static_cast<uint32_t>(ctx->h_scratch[3] & 0xFFFFFFFFu); // read linking sizes its table by it
     out->owns = true;
     out->h_chr_ptr = new uint64_t[in->n_chr + 1];
     SGPU_CUDA(ctx, sgpu_dev_alloc(ctx, reinterpret_cast<void **>(&out->d_chr_ptr), (in->n_chr + 1) * sizeof(uint64_t)));

@@ -75,51 +75,127 @@ struct PanelLayout {
 // the end of the panel that hold ONLY the tail reads, Z as the A operand and -Z as the B operand of
 // the same GEMM:  S = C C^T - Z Z^T.
 // ------------------------------------------------------------------------------------------------
-constexpr int ST_THREADS = 1024;
-constexpr uint32_t ST_MAX_CELLS = 1728; // 216 KB tile, one CTA per SM
+constexpr int ST_THREADS = 512;
+constexpr uint32_t ST_MAX_CELLS = 424;  // 53 KB tile: four CTAs per SM hide each other's phases
+constexpr uint32_t ST_MAX_STRIPES = 63;
 constexpr uint32_t CB_SKIP = 0xFFFFu;   // cellbase of an entry the dense scan does not count
 
-// cellbase[e] = cell << 2 | base for the entries that are the only entry of their read, CB_SKIP for
-// the others (staged from the special-entry list): what every stripe's CTA scans, 2 bytes per entry,
-// with the group map and the bitmap already applied. 8 entries per thread.
-__global__ void __launch_bounds__(256) cellbase_kernel(const uint16_t *__restrict__ gid_base,
-                                                       const uint32_t *__restrict__ sp_bits,
-                                                       const uint32_t *__restrict__ gmap, uint32_t n_groups,
-                                                       uint32_t n_cells, uint64_t n_entries,
-                                                       uint16_t *__restrict__ cellbase, int *__restrict__ err) {
-    const uint64_t e0 = (static_cast<uint64_t>(blockIdx.x) * 256 + threadIdx.x) * 8;
-    if (e0 >= n_entries) {
-        return;
-    }
-    const uint32_t special = (sp_bits[e0 >> 5] >> (e0 & 31)) & 0xFFu;
-    uint16_t in[8], out[8];
-    if (e0 + 8 <= n_entries) {
-        *reinterpret_cast<uint4 *>(in) = *reinterpret_cast<const uint4 *>(gid_base + e0);
-    } else {
-        for (int k = 0; k < 8; ++k) {
-            in[k] = e0 + k < n_entries ? gid_base[e0 + k] : 0;
-        }
-    }
-#pragma unroll
-    for (int k = 0; k < 8; ++k) {
-        const uint32_t gid = in[k] >> 2;
+// cellbase = (cell << 2 | base) of every entry that is the only entry of its read, with the group map and
+// the bitmap of special entries applied, and PARTITIONED BY CELL STRIPE inside every locus:
+// seg[l * (n_stripes + 1) + s] = first entry (relative to the locus) of stripe s, [.. + n_stripes] = end of
+// the last stripe (the special entries, staged from their own list, are left out). A staging CTA then reads
+// exactly the entries of its stripe. One CTA per locus: count per stripe, scan, scatter (order inside a
+// stripe does not matter).
+struct PartitionArgs {
+    const uint64_t *row_ptr;
+    const uint16_t *gid_base;
+    const uint32_t *sp_bits;
+    const uint32_t *gmap;
+    uint32_t n_groups, n_cells;
+    uint64_t n_loci;
+    uint32_t n_stripes;
+    uint32_t stripe_magic; // cell / cells_per_cta = (cell * magic) >> 32, exact for 14-bit cells
+    uint16_t *cellbase;
+    uint32_t *seg;
+    int *err;
+};
+
+constexpr uint32_t PART_CACHE = 8192; // entries of a locus kept in shared memory between the two passes
+
+__global__ void __launch_bounds__(256) partition_kernel(const PartitionArgs a) {
+    __shared__ uint32_t s_cnt[ST_MAX_STRIPES + 1];
+    __shared__ uint16_t s_v[PART_CACHE];
+    const uint32_t lane = threadIdx.x & 31;
+    const uint32_t ns = a.n_stripes;
+    // value of entry i of the locus starting at e0 (CB_SKIP = left out)
+    auto classify = [&](uint64_t e0, uint32_t n, uint32_t i) -> uint32_t {
         uint32_t v = CB_SKIP;
-        if (e0 + k < n_entries && !((special >> k) & 1u)) {
-            uint32_t cell;
-            if (gid >= n_groups || (cell = gmap[gid]) >= n_cells) {
-                atomicExch(err, SGPU_E_CELL_RANGE);
-            } else {
-                v = (cell << 2) | (in[k] & 3u);
+        if (i < n) {
+            const uint64_t e = e0 + i;
+            const uint32_t gb = a.gid_base[e];
+            if (!((a.sp_bits[e >> 5] >> (e & 31)) & 1u)) {
+                const uint32_t gid = gb >> 2;
+                uint32_t cell;
+                if (gid >= a.n_groups || (cell = a.gmap[gid]) >= a.n_cells) {
+                    atomicExch(a.err, SGPU_E_CELL_RANGE);
+                } else {
+                    v = (cell << 2) | (gb & 3u);
+                }
             }
         }
-        out[k] = static_cast<uint16_t>(v);
+        return v;
+    };
+    auto stripe_of = [&](uint32_t v) -> uint32_t { return v == CB_SKIP ? ns : __umulhi(v >> 2, a.stripe_magic); };
+    // warp-aggregated: the first lane of every group of equal stripes adds the group to the stripe's counter
+    auto count = [&](uint32_t stripe) {
+        const uint32_t m = __match_any_sync(0xffffffffu, stripe);
+        if (stripe < ns && lane == static_cast<uint32_t>(__ffs(m) - 1)) {
+            atomicAdd(&s_cnt[stripe], __popc(m));
+        }
+    };
+    auto place = [&](uint64_t e0, uint32_t v, uint32_t stripe) {
+        const uint32_t m = __match_any_sync(0xffffffffu, stripe);
+        const int leader = __ffs(m) - 1;
+        uint32_t base = 0;
+        if (stripe < ns && static_cast<int>(lane) == leader) {
+            base = atomicAdd(&s_cnt[stripe], __popc(m));
+        }
+        base = __shfl_sync(0xffffffffu, base, leader);
+        if (stripe < ns) {
+            a.cellbase[e0 + base + __popc(m & ((1u << lane) - 1u))] = static_cast<uint16_t>(v);
+        }
+    };
+    for (uint64_t l = blockIdx.x; l < a.n_loci; l += gridDim.x) {
+        const uint64_t e0 = a.row_ptr[l];
+        const uint32_t n = static_cast<uint32_t>(a.row_ptr[l + 1] - e0);
+        const bool cached = n <= PART_CACHE;
+        if (threadIdx.x <= ns) {
+            s_cnt[threadIdx.x] = 0;
+        }
+        __syncthreads();
+        // pass 1: count per stripe, four entries per thread in flight
+        for (uint32_t ib = 0; ib < n; ib += 1024) {
+            uint32_t v[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                v[u] = classify(e0, n, ib + 256 * u + threadIdx.x);
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const uint32_t i = ib + 256 * u + threadIdx.x;
+                if (cached && i < n) {
+                    s_v[i] = static_cast<uint16_t>(v[u]);
+                }
+                count(stripe_of(v[u]));
+            }
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) { // exclusive scan: s_cnt[s] becomes the cursor of stripe s
+            uint32_t acc = 0;
+            uint32_t *sg = a.seg + l * (ns + 1);
+            for (uint32_t s = 0; s < ns; ++s) {
+                const uint32_t c = s_cnt[s];
+                sg[s] = acc;
+                s_cnt[s] = acc;
+                acc += c;
+            }
+            sg[ns] = acc;
+        }
+        __syncthreads();
+        // pass 2: scatter (order inside a stripe does not matter)
+        for (uint32_t ib = 0; ib < n; ib += 256) {
+            const uint32_t i = ib + threadIdx.x;
+            const uint32_t v = cached ? (i < n ? s_v[i] : CB_SKIP) : classify(e0, n, i);
+            place(e0, v, stripe_of(v));
+        }
+        __syncthreads();
     }
-    *reinterpret_cast<uint4 *>(cellbase + e0) = *reinterpret_cast<const uint4 *>(out); // the array is padded to 8 entries
 }
 
 struct StageArgs {
     const uint64_t *row_ptr;
-    const uint16_t *cellbase;  // see cellbase_kernel; padded to a multiple of 8 entries
+    const uint16_t *cellbase;  // see partition_kernel
+    const uint32_t *seg;
     const uint32_t *sp_code;   // special entries, ascending by entry (hence by locus)
     const uint32_t *sp_locus;
     uint64_t n_special;
@@ -134,6 +210,13 @@ struct StageArgs {
     int *err;
 };
 
+// dot product of four unsigned bytes with four signed bytes
+__device__ __forceinline__ int dp4a_us(uint32_t a, int b) {
+    int d;
+    asm("dp4a.u32.s32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(0));
+    return d;
+}
+
 // One count. Range check without looking at the old value: the CTA compares the number of counts it
 // added with the sum of the tile's bytes afterwards (a byte that wrapped past 255 loses 255 or 256),
 // and a byte above 127 is seen when the planes are built.
@@ -141,16 +224,16 @@ __device__ __forceinline__ void tile_add(uint32_t *tile, uint32_t r, uint32_t j,
     atomicAdd(&tile[r * 32 + ((j + r) & 31u)], 1u << (8u * base));
 }
 
-__global__ void __launch_bounds__(ST_THREADS, 1) stage_tile_kernel(const StageArgs a) {
+__global__ void __launch_bounds__(ST_THREADS, 4) stage_tile_kernel(const StageArgs a) {
     extern __shared__ uint32_t tile[]; // [cell in stripe][32 loci], word of locus j of row r at (j + r) % 32
     __shared__ uint64_t s_e0[32], s_e1[32];
     __shared__ uint32_t s_loc[32];
-    __shared__ uint32_t s_b[32];  // end of locus j relative to the first entry of the k-block (main mode)
     __shared__ int s_balance;     // counts added - counts found in the tile
     __shared__ uint64_t s_sp0[32], s_sp1[32];
     // the stripes of one k-block are neighbours in the grid: they run together and share its entries in L2
     const uint32_t kb = blockIdx.x / a.n_stripes;
-    const uint32_t c0 = (blockIdx.x - kb * a.n_stripes) * a.cells_per_cta;
+    const uint32_t stripe = blockIdx.x - kb * a.n_stripes;
+    const uint32_t c0 = stripe * a.cells_per_cta;
     const uint32_t nc = min(a.cells_per_cta, a.n_pad - c0);
     const bool tail = kb >= a.kbs_main;
     if (threadIdx.x < 32) {
@@ -168,11 +251,16 @@ __global__ void __launch_bounds__(ST_THREADS, 1) stage_tile_kernel(const StageAr
             }
         }
         s_loc[j] = l;
-        // unused slots are empty ranges at the end of the k-block's entries (main mode: contiguous loci)
-        const uint64_t e_last = __shfl_sync(0xffffffffu, l != 0xFFFFFFFFu ? a.row_ptr[l + 1] : 0, 31 - __clz(__ballot_sync(0xffffffffu, l != 0xFFFFFFFFu) | 1u));
-        s_e0[j] = l != 0xFFFFFFFFu ? a.row_ptr[l] : e_last;
-        s_e1[j] = l != 0xFFFFFFFFu ? a.row_ptr[l + 1] : e_last;
-        s_b[j] = static_cast<uint32_t>(s_e1[j] - __shfl_sync(0xffffffffu, s_e0[j], 0));
+        // this stripe's segment of the locus
+        uint64_t b0 = 0, b1 = 0;
+        if (l != 0xFFFFFFFFu) {
+            const uint64_t e0 = a.row_ptr[l];
+            const uint32_t *sg = a.seg + static_cast<uint64_t>(l) * (a.n_stripes + 1) + stripe;
+            b0 = e0 + sg[0];
+            b1 = e0 + sg[1];
+        }
+        s_e0[j] = b0;
+        s_e1[j] = b1;
         if (j == 0) {
             s_balance = 0;
         }
@@ -203,51 +291,17 @@ __global__ void __launch_bounds__(ST_THREADS, 1) stage_tile_kernel(const StageAr
     __syncthreads();
 
     // ---- entries that are the only entry of their read (in a tail k-block all of them are tail reads:
-    // such a read was created at its own locus, which lies behind the cutoff)
+    // such a read was created at its own locus, which lies behind the cutoff). Warp j takes locus j.
     uint32_t n_added = 0;
-    if (!tail) {
-        // the 32 loci are consecutive: one contiguous range of entries, 8 per 16-byte load; entry
-        // indices relative to the first entry of the k-block fit 32 bits
-        const uint64_t E0 = s_e0[0];
-        const uint32_t n_e = static_cast<uint32_t>(s_e1[31] - E0), off0 = static_cast<uint32_t>(E0 & 7u);
-        const uint16_t *cbp = a.cellbase + (E0 - off0);
-        for (uint32_t vi = threadIdx.x; vi * 8 < n_e + off0; vi += ST_THREADS) {
-            const uint4 q = *reinterpret_cast<const uint4 *>(cbp + 8ull * vi);
-            const uint32_t w[4] = { q.x, q.y, q.z, q.w };
-            const int32_t i0 = static_cast<int32_t>(vi * 8) - static_cast<int32_t>(off0);
-            // locus of the first entry of the vector that belongs to the k-block
-            const uint32_t ef = static_cast<uint32_t>(max(i0, 0));
-            uint32_t j = 0;
-#pragma unroll
-            for (int step = 16; step > 0; step >>= 1) {
-                if (s_b[j + step - 1] <= ef) {
-                    j += step;
-                }
-            }
-            uint32_t nb = s_b[j]; // end of locus j
-#pragma unroll
-            for (int k = 0; k < 8; ++k) {
-                const uint32_t i = static_cast<uint32_t>(i0 + k); // wraps for the entries before E0
-                const uint32_t cb = (w[k >> 1] >> (16 * (k & 1))) & 0xFFFFu;
-                while (static_cast<int32_t>(i) >= static_cast<int32_t>(nb) && j < 31) {
-                    nb = s_b[++j];
-                }
-                const uint32_t r = (cb >> 2) - c0;
-                if (i < n_e && cb != CB_SKIP && r < nc) {
-                    tile_add(tile, r, j, cb & 3u);
-                    ++n_added;
-                }
-            }
-        }
-    } else {
-        for (uint32_t j = 0; j < 32; ++j) {
-            for (uint64_t e = s_e0[j] + threadIdx.x; e < s_e1[j]; e += ST_THREADS) {
-                const uint32_t cb = a.cellbase[e];
-                const uint32_t r = (cb >> 2) - c0;
-                if (cb != CB_SKIP && r < nc) {
-                    tile_add(tile, r, j, cb & 3u);
-                    ++n_added;
-                }
+    for (uint32_t j = threadIdx.x >> 5; j < 32; j += ST_THREADS / 32) {
+        const uint32_t lane = threadIdx.x & 31;
+        const uint64_t b1 = s_e1[j];
+        for (uint64_t e = s_e0[j] + lane; e < b1; e += 32) {
+            const uint32_t cb = a.cellbase[e];
+            const uint32_t r = (cb >> 2) - c0;
+            if (r < nc) {
+                tile_add(tile, r, j, cb & 3u);
+                ++n_added;
             }
         }
     }
@@ -273,25 +327,28 @@ __global__ void __launch_bounds__(ST_THREADS, 1) stage_tile_kernel(const StageAr
     int balance = static_cast<int>(n_added);
     for (uint32_t item = threadIdx.x; item < nc * 8; item += ST_THREADS) {
         const uint32_t r = item >> 3, g = item & 7;
-        uint32_t w[4] = { 0, 0, 0, 0 }, wn[4] = { 0, 0, 0, 0 }; // per plane, 4 loci packed (and negated)
+        // u_p = H_p . (counts of the four bases), one dp4a per plane and locus; H rows as signed bytes
+        uint32_t w[4], wn[4]; // per plane, 4 loci packed (and negated)
+        int u[4][4];
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
             const uint32_t v = tile[r * 32 + ((4 * g + q + r) & 31u)];
-            const int b0 = v & 0xFF, b1 = (v >> 8) & 0xFF, b2 = (v >> 16) & 0xFF, b3 = v >> 24;
-            const int u0 = b0 + b1 + b2 + b3;
-            const int u1 = b0 - b1 + b2 - b3;
-            const int u2 = b0 + b1 - b2 - b3;
-            const int u3 = b0 - b1 - b2 + b3;
-            bad |= u0 > 127;
-            balance -= u0;
-            w[0] |= static_cast<uint32_t>(u0 & 0xFF) << (8 * q);
-            w[1] |= static_cast<uint32_t>(u1 & 0xFF) << (8 * q);
-            w[2] |= static_cast<uint32_t>(u2 & 0xFF) << (8 * q);
-            w[3] |= static_cast<uint32_t>(u3 & 0xFF) << (8 * q);
-            wn[0] |= static_cast<uint32_t>(-u0 & 0xFF) << (8 * q);
-            wn[1] |= static_cast<uint32_t>(-u1 & 0xFF) << (8 * q);
-            wn[2] |= static_cast<uint32_t>(-u2 & 0xFF) << (8 * q);
-            wn[3] |= static_cast<uint32_t>(-u3 & 0xFF) << (8 * q);
+            u[0][q] = dp4a_us(v, 0x01010101);
+            u[1][q] = dp4a_us(v, static_cast<int>(0xFF01FF01u)); // + - + -
+            u[2][q] = dp4a_us(v, static_cast<int>(0xFFFF0101u)); // + + - -
+            u[3][q] = dp4a_us(v, static_cast<int>(0x01FFFF01u)); // + - - +
+            balance -= u[0][q];
+        }
+        bad |= ((u[0][0] | u[0][1] | u[0][2] | u[0][3]) & ~127) != 0;
+#pragma unroll
+        for (int p = 0; p < 4; ++p) {
+            w[p] = __byte_perm(__byte_perm(u[p][0], u[p][1], 0x0040), __byte_perm(u[p][2], u[p][3], 0x0040), 0x5410);
+        }
+        if (tail) {
+#pragma unroll
+            for (int p = 0; p < 4; ++p) {
+                wn[p] = __byte_perm(__byte_perm(-u[p][0], -u[p][1], 0x0040), __byte_perm(-u[p][2], -u[p][3], 0x0040), 0x5410);
+            }
         }
         uint32_t *out = a.U + a.pl.row(c0 + r, kb);
 #pragma unroll
@@ -737,13 +794,31 @@ int sgpu_gemm_counts(sgpu_ctx *ctx, const sgpu_pileup *p, const LinkResult &lr, 
     const size_t st_smem = static_cast<size_t>(cells_per_cta) * 128;
     SGPU_CUDA(ctx, cudaFuncSetAttribute(stage_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(st_smem)));
 
-    // per-entry (cell, base) with the group map and the special bitmap applied, once per call
+    // per-entry (cell, base) with the group map and the special bitmap applied, partitioned by stripe
+    // inside every locus, once per call
     DevBuf<uint16_t> cellbase;
+    DevBuf<uint32_t> seg;
     const uint64_t E = p->n_entries;
-    SGPU_CUDA(ctx, cellbase.alloc((E + 7) / 8 * 8 + 8, ctx));
+    SGPU_CUDA(ctx, cellbase.alloc(E + 8, ctx));
+    SGPU_CUDA(ctx, seg.alloc(P * (n_stripes + 1), ctx));
     mark(); // folded into the first panel's staging time
-    SGPU_LAUNCH(ctx, (cellbase_kernel<<<static_cast<unsigned>(ceil_div_u64(ceil_div_u64(E, 8), 256)), 256, 0, st>>>(
-                             p->d_gid_base, lr.sp_bits.p, lr.gmap.p, lr.n_groups, N, E, cellbase.p, d_err.p)));
+    {
+        PartitionArgs pa;
+        pa.row_ptr = p->d_row_ptr;
+        pa.gid_base = p->d_gid_base;
+        pa.sp_bits = lr.sp_bits.p;
+        pa.gmap = lr.gmap.p;
+        pa.n_groups = lr.n_groups;
+        pa.n_cells = N;
+        pa.n_loci = P;
+        pa.n_stripes = n_stripes;
+        pa.stripe_magic = static_cast<uint32_t>(((1ull << 32) + cells_per_cta - 1) / cells_per_cta);
+        pa.cellbase = cellbase.p;
+        pa.seg = seg.p;
+        pa.err = d_err.p;
+        const unsigned grid = static_cast<unsigned>(std::min<uint64_t>(P, static_cast<uint64_t>(sms) * 16));
+        SGPU_LAUNCH(ctx, (partition_kernel<<<grid, 256, 0, st>>>(pa)));
+    }
 
     bool first = true;
     for (uint64_t l0 = 0; l0 < P; l0 += panel) {
@@ -757,6 +832,7 @@ int sgpu_gemm_counts(sgpu_ctx *ctx, const sgpu_pileup *p, const LinkResult &lr, 
         StageArgs sa;
         sa.row_ptr = p->d_row_ptr;
         sa.cellbase = cellbase.p;
+        sa.seg = seg.p;
         sa.n_pad = n_pad;
         sa.sp_code = lr.sp_code.p;
         sa.sp_locus = lr.sp_locus.p;

@@ -16,6 +16,8 @@
 // (locus, base) lists.
 #include "common.cuh"
 
+#include <algorithm>
+
 namespace {
 
 constexpr int TB = 256;
@@ -47,6 +49,7 @@ struct MultiArgs {
 __global__ void __launch_bounds__(TB) multilocus_kernel(MultiArgs a) {
     // the class histogram has a handful of hot bins: count per block, flush once
     __shared__ uint32_t s_hist[SGPU_MAX_CLASS * SGPU_MAX_CLASS];
+    __shared__ unsigned int s_max_order;
     const uint64_t ia = static_cast<uint64_t>(blockIdx.x) * TB + threadIdx.x;
     const uint64_t n_me = *a.n_me;
     if (static_cast<uint64_t>(blockIdx.x) * TB >= n_me) {
@@ -55,8 +58,12 @@ __global__ void __launch_bounds__(TB) multilocus_kernel(MultiArgs a) {
     for (uint32_t i = threadIdx.x; i < SGPU_MAX_CLASS * SGPU_MAX_CLASS; i += TB) {
         s_hist[i] = 0;
     }
+    if (threadIdx.x == 0) {
+        s_max_order = 0;
+    }
     __syncthreads();
     unsigned long long local_pairs = 0;
+    unsigned int local_max = 0;
     if (ia < n_me) {
         const uint32_t loc = a.me_locus[ia];
         const uint32_t ca = a.me_code[ia];
@@ -115,20 +122,25 @@ __global__ void __launch_bounds__(TB) multilocus_kernel(MultiArgs a) {
                     atomicAdd(&a.H2[static_cast<uint64_t>(xd) * a.nn + ij], 1);
                 } else if (order == 3) {
                     atomicAdd(&a.H3[static_cast<uint64_t>(xd) * a.nn + ij], 1);
-                } else {
-                    atomicMax(a.max_order, order);
                 }
+                local_max = max(local_max, order);
             }
             if (order >= 4 && a.spill != nullptr) {
                 atomicAdd(&a.spill[ij], a.G[xs * SGPU_MAX_CLASS + xd]);
             }
         }
     }
+    if (local_max) {
+        atomicMax(&s_max_order, local_max);
+    }
     __syncthreads();
     for (uint32_t i = threadIdx.x; i < SGPU_MAX_CLASS * SGPU_MAX_CLASS; i += TB) {
         if (s_hist[i]) {
             atomicAdd(&a.hist[i], static_cast<unsigned long long>(s_hist[i]));
         }
+    }
+    if (threadIdx.x == 0 && s_max_order) {
+        atomicMax(a.max_order, s_max_order);
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
@@ -167,8 +179,6 @@ int sgpu_multilocus(sgpu_ctx *ctx, const sgpu_pileup *p, const LinkResult &lr, s
         SGPU_CUDA(ctx, d_G.alloc(SGPU_MAX_CLASS * SGPU_MAX_CLASS, ctx));
         SGPU_TRY(sgpu_build_gtable(ctx, c->eps, c->h, c->theta, c->L, SGPU_MAX_CLASS, d_G.p, nullptr));
     }
-    c->planes_used = N_PLANES;
-
     MultiArgs a;
     a.n_special = NS;
     a.n_me = lr.me_idx.p + NS;
@@ -204,6 +214,11 @@ int sgpu_multilocus(sgpu_ctx *ctx, const sgpu_pileup *p, const LinkResult &lr, s
         *n_pairs_multi = ctx->h_scratch[0];
     }
     const unsigned int max_order = static_cast<unsigned int>(ctx->h_scratch[1] & 0xFFFFFFFFu);
+    // planes that can be non-zero from now on: (2,0) (1,1) (0,2), and (3,0) .. (0,3) once an overlap of
+    // three loci was seen (zeroing, the multi-GPU reduction and the epilogue skip the others)
+    if (max_order >= 2) {
+        c->planes_used = std::max(c->planes_used, max_order >= 3 ? static_cast<int>(N_PLANES) : static_cast<int>(PLANE_H3));
+    }
     if (max_order >= 4 && c->spill == nullptr) {
         // first pair of order >= 4 seen by this counts object: create the spill plane and record
         // just those classes in a second pass

@@ -501,18 +501,40 @@ __global__ void __launch_bounds__(TB) readbase_kernel(const uint64_t *__restrict
     }
 }
 
-// SURVEY Appendix A.4. One CTA per chromosome: for a chunk of loci all threads compute
-// u(l) = number of reads whose start + L <= position[l] (a binary search over the positions, reads are
-// created locus by locus), then one thread replays the reference's batching rule over the chunk.
+// SURVEY Appendix A.4. One CTA per chromosome. u(l) = number of reads whose start + L <= position[l]
+// (a binary search over the positions, reads are created locus by locus); the reference's batching
+// rule "if u - front >= need: front = u" is sequential, but a locus with u(l) - u(l-1) >= need fires
+// whatever happened before it (front <= u(l-1)), so the replay only has to start at the LAST such locus:
+// found by all threads scanning chunks backwards from the chromosome's end, then one thread replays
+// the few loci behind it.
 constexpr int CUT_THREADS = 256;
 constexpr int CUT_CHUNK = 1024;
+
+// number of completed reads at locus l and the first locus whose reads are not complete yet
+__device__ __forceinline__ uint64_t completed_at(const uint32_t *__restrict__ position, const uint64_t *__restrict__ readbase,
+                                                 uint64_t l0, uint64_t l, uint32_t L, uint64_t rb0, uint32_t *j_out) {
+    const uint64_t p = position[l];
+    uint64_t lo = l0, hi = l; // first locus in [l0, l] with position + L > p
+    while (lo < hi) {
+        const uint64_t mid = (lo + hi) >> 1;
+        if (static_cast<uint64_t>(position[mid]) + L > p) {
+            hi = mid;
+        } else {
+            lo = mid + 1;
+        }
+    }
+    *j_out = static_cast<uint32_t>(lo - l0);
+    return readbase[lo] - rb0; // reads with start + L <= p, all created before locus l
+}
+
 __global__ void __launch_bounds__(CUT_THREADS) cutoff_kernel(const uint64_t *__restrict__ chr_ptr, uint32_t n_chr,
                                                              const uint32_t *__restrict__ position,
                                                              const uint64_t *__restrict__ readbase, uint32_t L,
                                                              uint32_t num_threads, uint64_t *__restrict__ n_tail_reads,
                                                              uint64_t *__restrict__ tail_locus) {
-    __shared__ uint64_t s_u[CUT_CHUNK];
-    __shared__ uint32_t s_j[CUT_CHUNK];
+    __shared__ uint64_t s_u[CUT_CHUNK + 1];
+    __shared__ uint32_t s_j[CUT_CHUNK + 1];
+    __shared__ unsigned long long s_sure; // 1 + last locus that fires for sure, 0 = none found yet
     const uint32_t c = blockIdx.x;
     if (c >= n_chr) {
         return;
@@ -520,24 +542,45 @@ __global__ void __launch_bounds__(CUT_THREADS) cutoff_kernel(const uint64_t *__r
     const uint64_t l0 = chr_ptr[c], l1 = chr_ptr[c + 1];
     const uint64_t rb0 = readbase[l0];
     const uint64_t need = 4ull * num_threads; // BATCH_SIZE * num_threads (similarity_matrix.cpp:354-356)
-    uint64_t front = 0, jk = l0;              // used by thread 0 only
-    for (uint64_t base = l0; base < l1; base += CUT_CHUNK) {
-        const uint32_t n = static_cast<uint32_t>(min(static_cast<uint64_t>(CUT_CHUNK), l1 - base));
+    if (threadIdx.x == 0) {
+        s_sure = 0;
+    }
+    __syncthreads();
+    // ---- backwards: the last locus whose trigger fires whatever the history
+    for (uint64_t end = l1; end > l0; end = end > l0 + CUT_CHUNK ? end - CUT_CHUNK : l0) {
+        const uint64_t base = end > l0 + CUT_CHUNK ? end - CUT_CHUNK : l0;
+        const uint32_t n = static_cast<uint32_t>(end - base);
+        // s_u[0] belongs to locus base - 1 (0 completed reads before the first locus), s_u[1 + i] to base + i
+        for (uint32_t i = threadIdx.x; i <= n; i += CUT_THREADS) {
+            uint32_t j = 0;
+            s_u[i] = (i == 0 && base == l0) ? 0 : completed_at(position, readbase, l0, base + i - 1, L, rb0, &j);
+        }
+        __syncthreads();
         for (uint32_t i = threadIdx.x; i < n; i += CUT_THREADS) {
-            const uint64_t l = base + i;
-            const uint64_t p = position[l];
-            // j = first locus in [l0, l] whose reads are NOT complete at p: position[j] + L > p
-            uint64_t lo = l0, hi = l;
-            while (lo < hi) {
-                const uint64_t mid = (lo + hi) >> 1;
-                if (static_cast<uint64_t>(position[mid]) + L > p) {
-                    hi = mid;
-                } else {
-                    lo = mid + 1;
-                }
+            if (s_u[i + 1] - s_u[i] >= need) {
+                atomicMax(&s_sure, static_cast<unsigned long long>(base + i + 1));
             }
-            s_u[i] = readbase[lo] - rb0; // reads with start + L <= p, all created before locus l
-            s_j[i] = static_cast<uint32_t>(lo - l0);
+        }
+        __syncthreads();
+        if (s_sure) {
+            break;
+        }
+    }
+    // ---- forwards from there: one thread replays the batching rule chunk by chunk
+    uint64_t front = 0, jk = l0, start = l0; // used by thread 0 only
+    if (s_sure) {
+        start = s_sure; // the locus after the sure one
+        if (threadIdx.x == 0) {
+            uint32_t j = 0;
+            front = completed_at(position, readbase, l0, s_sure - 1, L, rb0, &j);
+            jk = l0 + j;
+        }
+    }
+    for (uint64_t base = start; base < l1; base += CUT_CHUNK) {
+        const uint32_t n = static_cast<uint32_t>(min(static_cast<uint64_t>(CUT_CHUNK), l1 - base));
+        __syncthreads();
+        for (uint32_t i = threadIdx.x; i < n; i += CUT_THREADS) {
+            s_u[i] = completed_at(position, readbase, l0, base + i, L, rb0, &s_j[i]);
         }
         __syncthreads();
         if (threadIdx.x == 0) {
@@ -549,7 +592,6 @@ __global__ void __launch_bounds__(CUT_THREADS) cutoff_kernel(const uint64_t *__r
                 }
             }
         }
-        __syncthreads();
     }
     if (threadIdx.x == 0) {
         // reads with index >= K = rb0 + front are exactly those created at loci >= jk
