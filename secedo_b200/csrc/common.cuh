@@ -176,6 +176,7 @@ struct LinkResult {
     DevBuf<uint64_t> sp_rank;   // per bitmap word: number of special entries before it (dense numbering "sid")
     DevBuf<uint32_t> sp_entry;  // per sid: entry index (ascending)
     DevBuf<uint32_t> sp_locus;  // per sid: locus index
+    DevBuf<uint32_t> sp_start;  // per locus (n_loci + 1): first sid of the locus (all zero without special entries)
     DevBuf<uint32_t> sp_head;   // per sid: sid of the first entry of the read
     DevBuf<uint32_t> sp_code;   // per sid: code, see above
     DevBuf<uint8_t> sp_drop;    // per sid: removed by the mate rule

@@ -93,6 +93,7 @@ struct PartitionArgs {
     const uint32_t *gmap;
     uint32_t n_groups, n_cells;
     uint64_t n_loci;
+    uint64_t n_entries_padded; // entries that may be read with 16-byte loads (the arrays this library allocates are padded)
     uint32_t n_stripes;
     uint32_t stripe_magic; // cell / cells_per_cta = (cell * magic) >> 32, exact for 14-bit cells
     uint16_t *cellbase;
@@ -100,95 +101,122 @@ struct PartitionArgs {
     int *err;
 };
 
-constexpr uint32_t PART_CACHE = 8192; // entries of a locus kept in shared memory between the two passes
+constexpr uint32_t PART_CACHE = 8192; // entries of a locus handled per round (values + ranks in shared memory)
 
 __global__ void __launch_bounds__(256) partition_kernel(const PartitionArgs a) {
-    __shared__ uint32_t s_cnt[ST_MAX_STRIPES + 1];
-    __shared__ uint16_t s_v[PART_CACHE];
-    const uint32_t lane = threadIdx.x & 31;
+    __shared__ uint32_t s_cnt[ST_MAX_STRIPES + 1]; // entries of the stripe seen so far / start of the stripe
+    __shared__ uint16_t s_v[PART_CACHE], s_rank[PART_CACHE];
     const uint32_t ns = a.n_stripes;
-    // value of entry i of the locus starting at e0 (CB_SKIP = left out)
-    auto classify = [&](uint64_t e0, uint32_t n, uint32_t i) -> uint32_t {
+    // value of entry e (CB_SKIP = left out)
+    auto classify = [&](uint64_t e) -> uint32_t {
         uint32_t v = CB_SKIP;
-        if (i < n) {
-            const uint64_t e = e0 + i;
-            const uint32_t gb = a.gid_base[e];
-            if (!((a.sp_bits[e >> 5] >> (e & 31)) & 1u)) {
-                const uint32_t gid = gb >> 2;
-                uint32_t cell;
-                if (gid >= a.n_groups || (cell = a.gmap[gid]) >= a.n_cells) {
-                    atomicExch(a.err, SGPU_E_CELL_RANGE);
-                } else {
-                    v = (cell << 2) | (gb & 3u);
-                }
+        const uint32_t gb = a.gid_base[e];
+        if (!((a.sp_bits[e >> 5] >> (e & 31)) & 1u)) {
+            const uint32_t gid = gb >> 2;
+            uint32_t cell;
+            if (gid >= a.n_groups || (cell = a.gmap[gid]) >= a.n_cells) {
+                atomicExch(a.err, SGPU_E_CELL_RANGE);
+            } else {
+                v = (cell << 2) | (gb & 3u);
             }
         }
         return v;
     };
-    auto stripe_of = [&](uint32_t v) -> uint32_t { return v == CB_SKIP ? ns : __umulhi(v >> 2, a.stripe_magic); };
-    // warp-aggregated: the first lane of every group of equal stripes adds the group to the stripe's counter
-    auto count = [&](uint32_t stripe) {
-        const uint32_t m = __match_any_sync(0xffffffffu, stripe);
-        if (stripe < ns && lane == static_cast<uint32_t>(__ffs(m) - 1)) {
-            atomicAdd(&s_cnt[stripe], __popc(m));
-        }
-    };
-    auto place = [&](uint64_t e0, uint32_t v, uint32_t stripe) {
-        const uint32_t m = __match_any_sync(0xffffffffu, stripe);
-        const int leader = __ffs(m) - 1;
-        uint32_t base = 0;
-        if (stripe < ns && static_cast<int>(lane) == leader) {
-            base = atomicAdd(&s_cnt[stripe], __popc(m));
-        }
-        base = __shfl_sync(0xffffffffu, base, leader);
-        if (stripe < ns) {
-            a.cellbase[e0 + base + __popc(m & ((1u << lane) - 1u))] = static_cast<uint16_t>(v);
-        }
-    };
     for (uint64_t l = blockIdx.x; l < a.n_loci; l += gridDim.x) {
         const uint64_t e0 = a.row_ptr[l];
         const uint32_t n = static_cast<uint32_t>(a.row_ptr[l + 1] - e0);
-        const bool cached = n <= PART_CACHE;
-        if (threadIdx.x <= ns) {
-            s_cnt[threadIdx.x] = 0;
-        }
-        __syncthreads();
-        // pass 1: count per stripe, four entries per thread in flight
-        for (uint32_t ib = 0; ib < n; ib += 1024) {
-            uint32_t v[4];
-#pragma unroll
-            for (int u = 0; u < 4; ++u) {
-                v[u] = classify(e0, n, ib + 256 * u + threadIdx.x);
+        uint32_t *sg = a.seg + l * (ns + 1);
+        if (n <= PART_CACHE) {
+            // one sweep: the shared-memory atomic that counts the stripe also ranks the entry inside it
+            // (~20 stripes: the lanes of a warp spread over them, few same-address conflicts)
+            if (threadIdx.x <= ns) {
+                s_cnt[threadIdx.x] = 0;
             }
+            __syncthreads();
+            for (uint32_t ib = 0; ib < n; ib += 1024) {
+                uint32_t v[4];
 #pragma unroll
-            for (int u = 0; u < 4; ++u) {
-                const uint32_t i = ib + 256 * u + threadIdx.x;
-                if (cached && i < n) {
-                    s_v[i] = static_cast<uint16_t>(v[u]);
+                for (int u = 0; u < 4; ++u) {
+                    const uint32_t i = ib + 256 * u + threadIdx.x;
+                    v[u] = i < n ? classify(e0 + i) : CB_SKIP;
                 }
-                count(stripe_of(v[u]));
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const uint32_t i = ib + 256 * u + threadIdx.x;
+                    if (i < n) {
+                        s_v[i] = static_cast<uint16_t>(v[u]);
+                        if (v[u] != CB_SKIP) {
+                            s_rank[i] = static_cast<uint16_t>(atomicAdd(&s_cnt[__umulhi(v[u] >> 2, a.stripe_magic)], 1u));
+                        }
+                    }
+                }
             }
-        }
-        __syncthreads();
-        if (threadIdx.x == 0) { // exclusive scan: s_cnt[s] becomes the cursor of stripe s
-            uint32_t acc = 0;
-            uint32_t *sg = a.seg + l * (ns + 1);
-            for (uint32_t s = 0; s < ns; ++s) {
-                const uint32_t c = s_cnt[s];
-                sg[s] = acc;
-                s_cnt[s] = acc;
-                acc += c;
+            __syncthreads();
+            if (threadIdx.x < 32) { // exclusive scan over the stripes (<= 63): s_cnt[s] becomes the start of stripe s
+                uint32_t c0 = threadIdx.x < ns ? s_cnt[threadIdx.x] : 0, c1 = threadIdx.x + 32 < ns ? s_cnt[threadIdx.x + 32] : 0;
+                uint32_t i0 = c0, i1 = c1;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    const uint32_t t0 = __shfl_up_sync(0xffffffffu, i0, o), t1 = __shfl_up_sync(0xffffffffu, i1, o);
+                    if (static_cast<int>(threadIdx.x) >= o) {
+                        i0 += t0;
+                        i1 += t1;
+                    }
+                }
+                const uint32_t total0 = __shfl_sync(0xffffffffu, i0, 31);
+                i1 += total0;
+                if (threadIdx.x < ns) {
+                    s_cnt[threadIdx.x] = i0 - c0;
+                    sg[threadIdx.x] = i0 - c0;
+                }
+                if (threadIdx.x + 32 < ns) {
+                    s_cnt[threadIdx.x + 32] = i1 - c1;
+                    sg[threadIdx.x + 32] = i1 - c1;
+                }
+                if (threadIdx.x == 31) {
+                    sg[ns] = __shfl_sync(0x80000000u, i1, 31); // end of the last stripe
+                }
             }
-            sg[ns] = acc;
+            __syncthreads();
+            for (uint32_t i = threadIdx.x; i < n; i += 256) {
+                const uint32_t v = s_v[i];
+                if (v != CB_SKIP) {
+                    a.cellbase[e0 + s_cnt[__umulhi(v >> 2, a.stripe_magic)] + s_rank[i]] = static_cast<uint16_t>(v);
+                }
+            }
+            __syncthreads();
+        } else {
+            // a locus too large for the shared-memory round: count, scan, then rank with global re-reads
+            if (threadIdx.x <= ns) {
+                s_cnt[threadIdx.x] = 0;
+            }
+            __syncthreads();
+            for (uint32_t i = threadIdx.x; i < n; i += 256) {
+                const uint32_t v = classify(e0 + i);
+                if (v != CB_SKIP) {
+                    atomicAdd(&s_cnt[__umulhi(v >> 2, a.stripe_magic)], 1u);
+                }
+            }
+            __syncthreads();
+            if (threadIdx.x == 0) {
+                uint32_t acc = 0;
+                for (uint32_t s = 0; s < ns; ++s) {
+                    const uint32_t c = s_cnt[s];
+                    sg[s] = acc;
+                    s_cnt[s] = acc;
+                    acc += c;
+                }
+                sg[ns] = acc;
+            }
+            __syncthreads();
+            for (uint32_t i = threadIdx.x; i < n; i += 256) {
+                const uint32_t v = classify(e0 + i);
+                if (v != CB_SKIP) {
+                    a.cellbase[e0 + atomicAdd(&s_cnt[__umulhi(v >> 2, a.stripe_magic)], 1u)] = static_cast<uint16_t>(v);
+                }
+            }
+            __syncthreads();
         }
-        __syncthreads();
-        // pass 2: scatter (order inside a stripe does not matter)
-        for (uint32_t ib = 0; ib < n; ib += 256) {
-            const uint32_t i = ib + threadIdx.x;
-            const uint32_t v = cached ? (i < n ? s_v[i] : CB_SKIP) : classify(e0, n, i);
-            place(e0, v, stripe_of(v));
-        }
-        __syncthreads();
     }
 }
 
@@ -197,8 +225,7 @@ struct StageArgs {
     const uint16_t *cellbase;  // see partition_kernel
     const uint32_t *seg;
     const uint32_t *sp_code;   // special entries, ascending by entry (hence by locus)
-    const uint32_t *sp_locus;
-    uint64_t n_special;
+    const uint32_t *sp_start;  // per locus: first special entry of the locus (n_loci + 1 values)
     uint32_t n_pad;
     uint32_t l0, nl;           // main k-blocks: loci [l0, l0 + nl), 32 per k-block
     uint32_t kbs_main;
@@ -229,7 +256,7 @@ __global__ void __launch_bounds__(ST_THREADS, 4) stage_tile_kernel(const StageAr
     __shared__ uint64_t s_e0[32], s_e1[32];
     __shared__ uint32_t s_loc[32];
     __shared__ int s_balance;     // counts added - counts found in the tile
-    __shared__ uint64_t s_sp0[32], s_sp1[32];
+    __shared__ uint32_t s_sp0[32], s_sp1[32];
     // the stripes of one k-block are neighbours in the grid: they run together and share its entries in L2
     const uint32_t kb = blockIdx.x / a.n_stripes;
     const uint32_t stripe = blockIdx.x - kb * a.n_stripes;
@@ -265,25 +292,8 @@ __global__ void __launch_bounds__(ST_THREADS, 4) stage_tile_kernel(const StageAr
             s_balance = 0;
         }
         // the special entries of locus l: a contiguous range of the (ascending) list
-        uint64_t r0 = 0, r1 = 0;
-        if (l != 0xFFFFFFFFu) {
-#pragma unroll 1
-            for (int side = 0; side < 2; ++side) {
-                const uint32_t key = l + side; // first special entry with locus >= key
-                uint64_t lo = 0, hi = a.n_special;
-                while (lo < hi) {
-                    const uint64_t mid = (lo + hi) >> 1;
-                    if (a.sp_locus[mid] < key) {
-                        lo = mid + 1;
-                    } else {
-                        hi = mid;
-                    }
-                }
-                (side == 0 ? r0 : r1) = lo;
-            }
-        }
-        s_sp0[j] = r0;
-        s_sp1[j] = r1;
+        s_sp0[j] = l != 0xFFFFFFFFu ? a.sp_start[l] : 0;
+        s_sp1[j] = l != 0xFFFFFFFFu ? a.sp_start[l + 1] : 0;
     }
     for (uint32_t i = threadIdx.x; i < nc * 32; i += ST_THREADS) {
         tile[i] = 0;
@@ -296,18 +306,25 @@ __global__ void __launch_bounds__(ST_THREADS, 4) stage_tile_kernel(const StageAr
     for (uint32_t j = threadIdx.x >> 5; j < 32; j += ST_THREADS / 32) {
         const uint32_t lane = threadIdx.x & 31;
         const uint64_t b1 = s_e1[j];
-        for (uint64_t e = s_e0[j] + lane; e < b1; e += 32) {
-            const uint32_t cb = a.cellbase[e];
-            const uint32_t r = (cb >> 2) - c0;
-            if (r < nc) {
-                tile_add(tile, r, j, cb & 3u);
-                ++n_added;
+        for (uint64_t eb = s_e0[j] + lane; eb < b1; eb += 128) {
+            uint32_t cb[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) { // four loads in flight
+                cb[u] = eb + 32 * u < b1 ? a.cellbase[eb + 32 * u] : CB_SKIP;
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const uint32_t r = (cb[u] >> 2) - c0;
+                if (cb[u] != CB_SKIP && r < nc) {
+                    tile_add(tile, r, j, cb[u] & 3u);
+                    ++n_added;
+                }
             }
         }
     }
     // ---- surviving entries of reads with several entries
     for (uint32_t j = 0; j < 32; ++j) {
-        for (uint64_t s = s_sp0[j] + threadIdx.x; s < s_sp1[j]; s += ST_THREADS) {
+        for (uint32_t s = s_sp0[j] + threadIdx.x; s < s_sp1[j]; s += ST_THREADS) {
             const uint32_t c = a.sp_code[s];
             if (c == CODE_DROPPED || (tail && !code_tail(c))) {
                 continue;
@@ -811,6 +828,7 @@ int sgpu_gemm_counts(sgpu_ctx *ctx, const sgpu_pileup *p, const LinkResult &lr, 
         pa.n_groups = lr.n_groups;
         pa.n_cells = N;
         pa.n_loci = P;
+        pa.n_entries_padded = E / 8 * 8; // whole 8-entry groups inside the array
         pa.n_stripes = n_stripes;
         pa.stripe_magic = static_cast<uint32_t>(((1ull << 32) + cells_per_cta - 1) / cells_per_cta);
         pa.cellbase = cellbase.p;
@@ -835,8 +853,7 @@ int sgpu_gemm_counts(sgpu_ctx *ctx, const sgpu_pileup *p, const LinkResult &lr, 
         sa.seg = seg.p;
         sa.n_pad = n_pad;
         sa.sp_code = lr.sp_code.p;
-        sa.sp_locus = lr.sp_locus.p;
-        sa.n_special = lr.n_special;
+        sa.sp_start = lr.sp_start.p;
         sa.l0 = static_cast<uint32_t>(l0);
         sa.nl = static_cast<uint32_t>(nl);
         sa.kbs_main = kbs_main;

@@ -640,6 +640,25 @@ __global__ void __launch_bounds__(TB) sp_finish_kernel(
     }
 }
 
+// sp_start[l] = first special entry with locus >= l, l = 0 .. n_loci
+__global__ void __launch_bounds__(TB) sp_start_kernel(const uint32_t *__restrict__ sp_locus, uint64_t n_special,
+                                                      uint64_t n_loci, uint32_t *__restrict__ sp_start) {
+    const uint64_t l = static_cast<uint64_t>(blockIdx.x) * TB + threadIdx.x;
+    if (l > n_loci) {
+        return;
+    }
+    uint64_t lo = 0, hi = n_special;
+    while (lo < hi) {
+        const uint64_t mid = (lo + hi) >> 1;
+        if (sp_locus[mid] < l) {
+            lo = mid + 1;
+        } else {
+            hi = mid;
+        }
+    }
+    sp_start[l] = static_cast<uint32_t>(lo);
+}
+
 // ---- candidates of the multi-locus correction ---------------------------------------------------------
 __global__ void __launch_bounds__(TB) me_flag_kernel(const uint32_t *__restrict__ sp_code, const uint32_t *__restrict__ sp_head,
                                                      const uint32_t *__restrict__ sp_locus, const uint64_t *__restrict__ g_off,
@@ -861,6 +880,10 @@ int sgpu_link_reads(sgpu_ctx *ctx, const sgpu_pileup *p, uint32_t num_cells, uin
     }
     SGPU_TRACE(ctx, "link: mark+rank");
     out->n_special = NS;
+    SGPU_CUDA(ctx, out->sp_start.alloc(P + 1, ctx));
+    if (NS == 0) {
+        SGPU_CUDA(ctx, cudaMemsetAsync(out->sp_start.p, 0, (P + 1) * sizeof(uint32_t), st));
+    }
     if (NS) {
         DevBuf<uint32_t> sp_first, g_cnt, cursor;
         SGPU_CUDA(ctx, out->sp_entry.alloc(NS, ctx));
@@ -889,6 +912,7 @@ int sgpu_link_reads(sgpu_ctx *ctx, const sgpu_pileup *p, uint32_t num_cells, uin
             SGPU_LAUNCH(ctx, (sp_list_kernel<<<blocks_for(W), TB, 0, st>>>(out->sp_bits.p, out->sp_rank.p, W, p->d_row_ptr, word_locus.p,
                                                                             out->sp_entry.p, sp_first.p, out->sp_locus.p)));
         }
+        SGPU_LAUNCH(ctx, (sp_start_kernel<<<blocks_for(P + 1), TB, 0, st>>>(out->sp_locus.p, NS, P, out->sp_start.p)));
         for (int sweep = 0; sweep < 3; ++sweep) {
             SGPU_LAUNCH(ctx, (link_min_kernel<<<blocks_for(NL), TB, 0, st>>>(links.p, NL, out->sp_bits.p, out->sp_rank.p, sp_first.p,
                                                                              d_err.p + 1)));
