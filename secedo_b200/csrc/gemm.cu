@@ -93,7 +93,6 @@ struct PartitionArgs {
     const uint32_t *gmap;
     uint32_t n_groups, n_cells;
     uint64_t n_loci;
-    uint64_t n_entries_padded; // entries that may be read with 16-byte loads (the arrays this library allocates are padded)
     uint32_t n_stripes;
     uint32_t stripe_magic; // cell / cells_per_cta = (cell * magic) >> 32, exact for 14-bit cells
     uint16_t *cellbase;
@@ -101,12 +100,22 @@ struct PartitionArgs {
     int *err;
 };
 
-constexpr uint32_t PART_CACHE = 8192; // entries of a locus handled per round (values + ranks in shared memory)
+constexpr uint32_t PART_CACHE = 4608; // entries of a locus handled in shared memory (values, ranks, output)
 
+// Gathers from the group map and scattered 2-byte stores cost one L1 wavefront per lane when they go to
+// global memory; both are done in shared memory here (the map is copied once per CTA, the partitioned
+// locus is assembled in shared memory and written out contiguously).
 __global__ void __launch_bounds__(256) partition_kernel(const PartitionArgs a) {
+    extern __shared__ uint16_t s_dyn[];
     __shared__ uint32_t s_cnt[ST_MAX_STRIPES + 1]; // entries of the stripe seen so far / start of the stripe
-    __shared__ uint16_t s_v[PART_CACHE], s_rank[PART_CACHE];
+    uint16_t *s_v = s_dyn, *s_rank = s_dyn + PART_CACHE, *s_out = s_dyn + 2 * PART_CACHE;
+    uint16_t *s_map = s_dyn + 3 * PART_CACHE;      // [n_groups] cell of the group, 0xFFFF = outside the matrix
     const uint32_t ns = a.n_stripes;
+    for (uint32_t g = threadIdx.x; g < a.n_groups; g += 256) {
+        const uint32_t c = a.gmap[g];
+        s_map[g] = static_cast<uint16_t>(c < a.n_cells ? c : 0xFFFFu);
+    }
+    __syncthreads();
     // value of entry e (CB_SKIP = left out)
     auto classify = [&](uint64_t e) -> uint32_t {
         uint32_t v = CB_SKIP;
@@ -114,7 +123,7 @@ __global__ void __launch_bounds__(256) partition_kernel(const PartitionArgs a) {
         if (!((a.sp_bits[e >> 5] >> (e & 31)) & 1u)) {
             const uint32_t gid = gb >> 2;
             uint32_t cell;
-            if (gid >= a.n_groups || (cell = a.gmap[gid]) >= a.n_cells) {
+            if (gid >= a.n_groups || (cell = s_map[gid]) == 0xFFFFu) {
                 atomicExch(a.err, SGPU_E_CELL_RANGE);
             } else {
                 v = (cell << 2) | (gb & 3u);
@@ -174,15 +183,21 @@ __global__ void __launch_bounds__(256) partition_kernel(const PartitionArgs a) {
                     sg[threadIdx.x + 32] = i1 - c1;
                 }
                 if (threadIdx.x == 31) {
-                    sg[ns] = __shfl_sync(0x80000000u, i1, 31); // end of the last stripe
+                    sg[ns] = i1; // end of the last stripe
+                    s_cnt[ns] = i1;
                 }
             }
             __syncthreads();
             for (uint32_t i = threadIdx.x; i < n; i += 256) {
                 const uint32_t v = s_v[i];
                 if (v != CB_SKIP) {
-                    a.cellbase[e0 + s_cnt[__umulhi(v >> 2, a.stripe_magic)] + s_rank[i]] = static_cast<uint16_t>(v);
+                    s_out[s_cnt[__umulhi(v >> 2, a.stripe_magic)] + s_rank[i]] = static_cast<uint16_t>(v);
                 }
+            }
+            __syncthreads();
+            const uint32_t n_out = s_cnt[ns];
+            for (uint32_t i = threadIdx.x; i < n_out; i += 256) {
+                a.cellbase[e0 + i] = s_out[i];
             }
             __syncthreads();
         } else {
@@ -828,14 +843,15 @@ int sgpu_gemm_counts(sgpu_ctx *ctx, const sgpu_pileup *p, const LinkResult &lr, 
         pa.n_groups = lr.n_groups;
         pa.n_cells = N;
         pa.n_loci = P;
-        pa.n_entries_padded = E / 8 * 8; // whole 8-entry groups inside the array
         pa.n_stripes = n_stripes;
         pa.stripe_magic = static_cast<uint32_t>(((1ull << 32) + cells_per_cta - 1) / cells_per_cta);
         pa.cellbase = cellbase.p;
         pa.seg = seg.p;
         pa.err = d_err.p;
         const unsigned grid = static_cast<unsigned>(std::min<uint64_t>(P, static_cast<uint64_t>(sms) * 16));
-        SGPU_LAUNCH(ctx, (partition_kernel<<<grid, 256, 0, st>>>(pa)));
+        const size_t psmem = (3 * static_cast<size_t>(PART_CACHE) + lr.n_groups) * sizeof(uint16_t);
+        SGPU_CUDA(ctx, cudaFuncSetAttribute(partition_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(psmem)));
+        SGPU_LAUNCH(ctx, (partition_kernel<<<grid, 256, psmem, st>>>(pa)));
     }
 
     bool first = true;
