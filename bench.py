@@ -309,19 +309,36 @@ def main_ours(args):
     ms_gemm_step = acc["ms_gemm"] / args.steps
     launches_gemm = max(1, acc["gemm_launches"] // args.steps)
     alg_ops_step = 5.0 * N * N * sig_local                      # 5 N^2 per significant locus
-    executed_ops_step = 4.0 * (((N + 255) // 256) * 256) ** 2 * sig_local  # what the Hadamard form issues (upper bound)
+    n_pad = ((N + 255) // 256) * 256
+    n_tiles = sum(1 for cb in range(n_pad // 256) for rb in range(n_pad // 128)
+                  if cb * 256 + 255 > rb * 128 and rb * 128 < N and cb * 256 < N)
+    kbs = (sig_local + 31) // 32
+    executed_ops_step = 2.0 * n_tiles * 128 * 256 * kbs * 128  # MACs x 2 the tcgen05 kernel issues: tiles x k-blocks of 128 B
     line = None
     if rank == 0:
         int8_peak, bf16_peak, how = int8_peak_tops(torch, device)
         achieved = alg_ops_step / (ms_gemm_step * 1e-3) / 1e12 if ms_gemm_step > 0 else 0.0
+        # DRAM bytes of one launch from the committed ncu --set full capture of this exact workload
+        traffic = None
+        try:
+            tr = json.load(open(os.path.join(ROOT, "profiles", "r1_syrk_traffic.json")))
+            tw = tr["workload"]
+            if (tw["n_cells"], tw["n_chr"], tw["loci_per_chr"], tw["coverage"]) == (N, w["n_chr"], w["loci_per_chr"], w["coverage"]):
+                traffic = tr["dram_bytes_read"] + tr["dram_bytes_write"]
+        except Exception:  # noqa: BLE001
+            pass
         roofline = {
             "bound": "tensor", "kernel": "syrk_kernel (tcgen05.mma.kind::i8)", "achieved": achieved, "peak": int8_peak,
-            "unit": "TFLOP/s", "frac": achieved / int8_peak if int8_peak else None, "traffic": None,
-            "op": "int8 multiply-add = 2 ops; algorithmic ops = 5*N^2 per significant locus (SURVEY 8d)",
+            "unit": "TFLOP/s", "frac": achieved / int8_peak if int8_peak else None, "traffic": traffic,
+            "op": "int8 multiply-add = 2 ops; algorithmic ops = 5*N^2 per significant locus (SURVEY 8d); the kernel "
+                  "issues 4*N_pad^2*(upper-triangle tiles) of them (Hadamard planes: 4 K-slices per 32 loci instead of 5)",
             "peak_source": how, "bf16_peak_measured": bf16_peak,
             "launches_per_step": launches_gemm, "avg_launch_ms": ms_gemm_step / launches_gemm,
             "executed_ops_frac_of_algorithmic": executed_ops_step / alg_ops_step if alg_ops_step else None,
+            "achieved_executed": achieved * executed_ops_step / alg_ops_step if alg_ops_step else None,
+            "frac_executed": (achieved * executed_ops_step / alg_ops_step / int8_peak) if alg_ops_step and int8_peak else None,
             "kernel_share_of_step": ms_gemm_step / (ms_dev / args.steps),
+            "traffic_source": "profiles/r1_syrk_traffic.json (ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum)",
         }
         # ---- CPU baseline: the unmodified reference on a bounded sample ---------------------------------
         threads = reference_threads()
@@ -345,7 +362,7 @@ def main_ours(args):
                 "theta": w["theta"], "eps": w["eps"], "h": w["h"], "max_fragment_length": w["L"],
                 "num_threads_for_cutoff": w["num_threads"], "normalization": w["normalization"],
                 "path": last.get("path_used"), "parallelism": f"loci sharded by chromosome over {world} GPU(s), "
-                "one NCCL reduce of the int32 count planes",
+                "one NCCL reduce of the int32 count planes in use",
                 "l2": "inputs larger than L2 (pileup batch %.1f GB, Hadamard panel %.1f GB per step)" % (
                     h2d / 1e9, 4.0 * N * sig_local / 1e9),
             },
