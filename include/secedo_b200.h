@@ -151,6 +151,12 @@ int sgpu_counts_accumulate(sgpu_ctx *ctx, sgpu_counts *c, const sgpu_pileup *fil
 int sgpu_counts_buffers(sgpu_counts *c, int32_t **i32, uint64_t *n_i32, double **f64, uint64_t *n_f64,
                         uint64_t **hist, uint64_t *n_hist);
 int sgpu_counts_set_layout(sgpu_ctx *ctx, sgpu_counts *c, int planes_used /* 2, 5 or 9 */, int want_spill);
+/* Half the bytes for the cross-rank reduction: the upper triangles (i < j) of the int32 planes in use,
+ * packed row by row into one contiguous device buffer owned by the counts object
+ * (n = planes * num_cells (num_cells - 1) / 2). Agree on the layout first; reduce the packed buffer;
+ * sgpu_counts_unpack on the destination rank writes the sums back into the planes. */
+int sgpu_counts_pack(sgpu_ctx *ctx, sgpu_counts *c, int32_t **packed, uint64_t *n);
+int sgpu_counts_unpack(sgpu_ctx *ctx, sgpu_counts *c);
 /* Symmetric per-cell-pair integers for bit-exact checks (any pointer may be NULL):
  *   S1, D1  num_cells^2 int32: incidences (read pair, shared locus) with equal / different base
  *   H       3*num_cells^2 int32: read pairs in overlap class (2,0), (1,1), (0,2)

@@ -80,6 +80,8 @@ SIGNATURES = {
                                          C.c_double, C.c_uint32, C.c_int, C.POINTER(Stats)]),
     "sgpu_counts_buffers": (C.c_int, [_vp, C.POINTER(_vp), _u64p, C.POINTER(_vp), _u64p, C.POINTER(_vp), _u64p]),
     "sgpu_counts_set_layout": (C.c_int, [_vp, _vp, C.c_int, C.c_int]),
+    "sgpu_counts_pack": (C.c_int, [_vp, _vp, C.POINTER(_vp), _u64p]),
+    "sgpu_counts_unpack": (C.c_int, [_vp, _vp]),
     "sgpu_counts_download": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp]),
     "sgpu_similarity_finalize": (C.c_int, [_vp, _vp, C.c_uint32, C.c_double, C.c_double, C.c_double, C.c_int, _vp,
                                            C.POINTER(Stats)]),

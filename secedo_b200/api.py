@@ -246,6 +246,16 @@ class Counts:
     def set_layout(self, planes_used: int, want_spill: bool) -> None:
         self.ctx.check(self.ctx._lib.sgpu_counts_set_layout(self.ctx._h, self._h, int(planes_used), int(want_spill)))
 
+    def pack(self):
+        """Upper triangles of the planes in use, packed into one device buffer: (pointer, n int32)."""
+        ptr, n = C.c_void_p(), C.c_uint64()
+        self.ctx.check(self.ctx._lib.sgpu_counts_pack(self.ctx._h, self._h, C.byref(ptr), C.byref(n)))
+        return ptr.value, n.value
+
+    def unpack(self) -> None:
+        """Packed buffer (after the cross-rank reduction) back into the planes."""
+        self.ctx.check(self.ctx._lib.sgpu_counts_unpack(self.ctx._h, self._h))
+
     def download(self):
         """Symmetric host copies: (S1, D1, H[3], class_hist) for bit-exact checks."""
         n = self.num_cells

@@ -78,6 +78,25 @@ void sgpu_dev_release_cache(sgpu_ctx *ctx) {
 
 namespace {
 
+// upper triangle (i < j) of `planes` N x N planes <-> rows packed back to back
+template <bool PACK>
+__global__ void __launch_bounds__(256) tri_pack_kernel(int32_t *__restrict__ planes, int32_t *__restrict__ packed, uint32_t n,
+                                                       uint32_t n_planes) {
+    const uint64_t nn = static_cast<uint64_t>(n) * n, tri = static_cast<uint64_t>(n) * (n - 1) / 2;
+    for (uint64_t row = blockIdx.x; row < static_cast<uint64_t>(n_planes) * n; row += gridDim.x) {
+        const uint32_t pl = static_cast<uint32_t>(row / n), i = static_cast<uint32_t>(row - static_cast<uint64_t>(pl) * n);
+        int32_t *src = planes + pl * nn + static_cast<uint64_t>(i) * n;
+        int32_t *dst = packed + pl * tri + (static_cast<uint64_t>(i) * n - static_cast<uint64_t>(i) * (i + 1) / 2);
+        for (uint32_t j = i + 1 + threadIdx.x; j < n; j += 256) {
+            if (PACK) {
+                dst[j - i - 1] = src[j];
+            } else {
+                src[j] = dst[j - i - 1];
+            }
+        }
+    }
+}
+
 struct EventTimer {
     cudaEvent_t a = nullptr, b = nullptr;
     cudaStream_t st;
@@ -367,6 +386,9 @@ void sgpu_counts_free(sgpu_ctx *ctx, sgpu_counts *c) {
     cudaFree(c->i32);
     cudaFree(c->hist);
     cudaFree(c->spill);
+    if (ctx) {
+        sgpu_dev_free(ctx, c->packed);
+    }
     delete c;
 }
 
@@ -471,6 +493,46 @@ int sgpu_counts_set_layout(sgpu_ctx *ctx, sgpu_counts *c, int planes_used, int w
         SGPU_CUDA(ctx, cudaMalloc(&c->spill, std::max<uint64_t>(1, c->nn) * sizeof(double)));
         SGPU_CUDA(ctx, cudaMemsetAsync(c->spill, 0, c->nn * sizeof(double), ctx->stream));
     }
+    return SGPU_OK;
+}
+
+int sgpu_counts_pack(sgpu_ctx *ctx, sgpu_counts *c, int32_t **packed, uint64_t *n) {
+    SGPU_CUDA(ctx, cudaSetDevice(ctx->device));
+    const uint64_t need = static_cast<uint64_t>(c->planes_used) * c->n * (c->n ? c->n - 1 : 0) / 2;
+    if (c->packed_n < need) {
+        sgpu_dev_free(ctx, c->packed);
+        c->packed = nullptr;
+        SGPU_CUDA(ctx, sgpu_dev_alloc(ctx, reinterpret_cast<void **>(&c->packed), std::max<uint64_t>(need, 1) * sizeof(int32_t)));
+        c->packed_n = need;
+    }
+    if (need) {
+        const unsigned grid = static_cast<unsigned>(std::min<uint64_t>(static_cast<uint64_t>(c->planes_used) * c->n,
+                                                                      static_cast<uint64_t>(ctx->sm_count) * 16));
+        SGPU_LAUNCH(ctx, (tri_pack_kernel<true><<<grid, 256, 0, ctx->stream>>>(c->i32, c->packed, c->n, c->planes_used)));
+        SGPU_CUDA(ctx, cudaGetLastError());
+    }
+    if (packed) {
+        *packed = c->packed;
+    }
+    if (n) {
+        *n = need;
+    }
+    return SGPU_OK;
+}
+
+int sgpu_counts_unpack(sgpu_ctx *ctx, sgpu_counts *c) {
+    SGPU_CUDA(ctx, cudaSetDevice(ctx->device));
+    const uint64_t need = static_cast<uint64_t>(c->planes_used) * c->n * (c->n ? c->n - 1 : 0) / 2;
+    if (c->packed == nullptr || c->packed_n < need) {
+        return sgpu_fail(ctx, SGPU_E_ARG, "sgpu_counts_unpack without a matching sgpu_counts_pack");
+    }
+    if (need) {
+        const unsigned grid = static_cast<unsigned>(std::min<uint64_t>(static_cast<uint64_t>(c->planes_used) * c->n,
+                                                                      static_cast<uint64_t>(ctx->sm_count) * 16));
+        SGPU_LAUNCH(ctx, (tri_pack_kernel<false><<<grid, 256, 0, ctx->stream>>>(c->i32, c->packed, c->n, c->planes_used)));
+        SGPU_CUDA(ctx, cudaGetLastError());
+    }
+    c->fresh = false;
     return SGPU_OK;
 }
 

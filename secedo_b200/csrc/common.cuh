@@ -147,6 +147,8 @@ struct sgpu_counts {
     int planes_used = 2;        // 2, 5 or 9: planes that can be non-zero
     int planes_dirty = N_PLANES; // planes to clear at the next sgpu_counts_zero
     bool fresh = false;         // S and D are all zero (nothing accumulated since sgpu_counts_zero)
+    int32_t *packed = nullptr;  // upper triangles of the planes in use, for the cross-rank reduction (lazy)
+    uint64_t packed_n = 0;
     double *spill = nullptr;    // n*n doubles: sum of G(x_s,x_d) over pairs with x_s+x_d >= 4 (lazy)
     uint64_t *hist = nullptr;   // SGPU_MAX_CLASS^2 class histogram (pairs with x_s+x_d >= 2)
     // log-likelihood parameters the spill plane was accumulated with (must match at finalize)

@@ -759,6 +759,9 @@ int sgpu_gemm_counts(sgpu_ctx *ctx, const sgpu_pileup *p, const LinkResult &lr, 
     const uint32_t kbs_tail = static_cast<uint32_t>((lr.n_tail_loci + LOCI_PER_KB - 1) / LOCI_PER_KB);
     // panel: at most ~2 GB of Hadamard planes
     uint64_t panel = (1ull << 31) / (4ull * n_pad) / LOCI_PER_KB * LOCI_PER_KB;
+    if (const char *env = getenv("SECEDO_B200_PANEL_LOCI")) { // tests: force several panels on small inputs
+        panel = std::max(1, atoi(env)) / LOCI_PER_KB * LOCI_PER_KB;
+    }
     panel = std::max<uint64_t>(panel, LOCI_PER_KB);
     panel = std::min<uint64_t>(panel, (P + LOCI_PER_KB - 1) / LOCI_PER_KB * LOCI_PER_KB);
     const uint64_t kbs_max = panel / LOCI_PER_KB + 2ull * kbs_tail;

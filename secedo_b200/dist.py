@@ -72,9 +72,21 @@ def counts_tensors(counts, device: torch.device) -> List[torch.Tensor]:
 
 
 def reduce_counts(counts, device: torch.device, dst: int = 0, group=None) -> None:
-    """Agree on the buffer layout, then sum the count planes of all ranks onto ``dst``."""
+    """Agree on the buffer layout, then sum the count planes of all ranks onto ``dst``. Only the upper
+    triangles of the planes in use travel: they are packed into one contiguous buffer on every rank
+    (``sgpu_counts_pack``), summed with ONE reduction, and unpacked on ``dst``."""
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+        return
     i32, n_i32, f64, n_f64, hist, n_hist = counts.buffers()
     nn = counts.num_cells * counts.num_cells
     planes, spill = agree_layout(n_i32 // nn if nn else 2, n_f64 > 0, device, group)
     counts.set_layout(planes, spill)
-    reduce_buffers(counts_tensors(counts, device), dst, group)
+    ptr, n = counts.pack()
+    counts.ctx.synchronize()  # the library's stream need not be the one the collective is ordered on
+    _, _, f64, n_f64, hist, n_hist = counts.buffers()
+    reduce_buffers([tensor_from_ptr(ptr, n, torch.int32, device), tensor_from_ptr(f64, n_f64, torch.float64, device),
+                    tensor_from_ptr(hist, n_hist, torch.int64, device)], dst, group)
+    if dist.get_rank(group) == dst:
+        if device is not None and torch.device(device).type == "cuda":
+            torch.cuda.current_stream(device).synchronize()  # the sums have arrived before they are unpacked
+        counts.unpack()

@@ -205,6 +205,27 @@ def test_auto_path_and_stats(gpu_ctx):
     assert gpu_ctx.launch_count() > n0
 
 
+@pytest.mark.parametrize("panel_loci", [32, 96, 256])
+def test_several_gemm_panels(gpu_ctx, panel_loci, monkeypatch):
+    """inputs larger than one operand panel (2 GB) are processed panel by panel: the first panel stores
+    into the fresh count planes and carries the tail k-blocks, the later ones add in place. Forced here
+    with tiny panels; also accumulates twice into the same counts object (load-add-store epilogue)."""
+    monkeypatch.setenv("SECEDO_B200_PANEL_LOCI", str(panel_loci))
+    cfg = SynthConfig(n_cells=300, coverage=0.3, n_loci=1200, n_chr=3, p_multi=0.1, p_mate=0.05, seed=61)
+    p = make_pileup(cfg)
+    ident = np.arange(cfg.n_cells, dtype=np.uint32)
+    f, _ = api.Filter(0.01, 4, gpu_ctx).filter(p, ident, "", 1)
+    assert f.n_loci > 3 * panel_loci
+    check_counts(gpu_ctx, f, cfg.n_cells, 1000, ident, 0.01, 0.5, 0.01, 4, "gemm")
+    c = api.Counts(gpu_ctx, cfg.n_cells)
+    c.accumulate(f, 1000, ident, 0.01, 0.5, 0.01, 4, "gemm")
+    c.accumulate(f, 1000, ident, 0.01, 0.5, 0.01, 4, "gemm")
+    o = po.similarity(f, cfg.n_cells, 1000, ident, 0.01, 0.5, 0.01, 4, "ADD_MIN")
+    S1, D1, H, _ = c.download()
+    assert np.array_equal(S1, 2 * o.S1) and np.array_equal(D1, 2 * o.D1) and np.array_equal(H, 2 * o.H)
+    c.free()
+
+
 @pytest.mark.parametrize("reps", [127, 128, 200, 256, 300, 520])
 def test_int8_count_range(gpu_ctx, reps):
     """the GEMM path holds per-(cell, locus) base counts in int8: up to 127 reads of one cell at a locus
