@@ -285,21 +285,74 @@ def main_ours(args):
     sig_total = int(sig.item())
 
     # ---- end to end: host (pinned) pileup in, host matrix out ------------------------------------------
+    # The reference-facing call sequence with HOST buffers: every step uploads its whole batch (one
+    # asynchronous upload per chromosome on the library's copy stream, so that the copy of the next
+    # chromosome overlaps the kernels of the current one, and the first copy of the next step overlaps the
+    # D2H of this step's matrix), filters and accumulates chromosome by chromosome into one counts object,
+    # reduces, and reads the N x N matrix back into host memory. All H2D / D2H bytes of all timed steps
+    # are inside the timed region.
     host = raw_dev.download()
     pinned = []
     def pin(a):
-        t = torch.from_numpy(a).pin_memory()
+        t = torch.from_numpy(np.ascontiguousarray(a)).pin_memory()
         pinned.append(t)
         return t.numpy()
-    host_p = Pileup.__new__(Pileup)
-    host_p.chr_ptr, host_p.row_ptr = host.chr_ptr, pin(host.row_ptr)
-    host_p.position, host_p.read_id, host_p.gid_base = pin(host.position), pin(host.read_id), pin(host.gid_base)
+    pos_p, rid_p, gb_p = pin(host.position), pin(host.read_id), pin(host.gid_base)
+    chunks = []
+    for c in range(n_chr):
+        l0, l1 = int(host.chr_ptr[c]), int(host.chr_ptr[c + 1])
+        e0, e1 = int(host.row_ptr[l0]), int(host.row_ptr[l1])
+        hp = Pileup.__new__(Pileup)  # views of the pinned arrays, no copies
+        hp.chr_ptr = np.array([0, l1 - l0], np.uint64)
+        hp.row_ptr = pin(host.row_ptr[l0:l1 + 1] - np.uint64(e0))
+        hp.position, hp.read_id, hp.gid_base = pos_p[l0:l1], rid_p[e0:e1], gb_p[e0:e1]
+        chunks.append(hp)
     out_t = torch.empty((N, N), dtype=torch.float64).pin_memory() if rank == 0 else None
     out_host = out_t.numpy() if rank == 0 else None
     e2e_steps = max(1, min(args.steps, 3))
-    ms_e2e, _, _, _ = timed(lambda: step(host_p, out_host), e2e_steps, 1)
+    E2E_WARMUP = 2
+    e2e_total = E2E_WARMUP + e2e_steps  # warm-up + timed
+    # uploads run up to LOOKAHEAD chromosomes ahead of the kernels, but never across the warm-up / timed
+    # boundary nor past the last step: every timed step's H2D bytes are copied inside the timed region
+    LOOKAHEAD = 2
+    runs = [[(s, c) for s in range(E2E_WARMUP) for c in range(n_chr)],
+            [(s, c) for s in range(E2E_WARMUP, e2e_total) for c in range(n_chr)]]
+    state = {"queue": [], "issued": 0, "run": []}
+
+    def top_up():
+        while len(state["queue"]) < LOOKAHEAD and state["issued"] < len(state["run"]):
+            state["queue"].append(ctx.upload_async(chunks[state["run"][state["issued"]][1]]))
+            state["issued"] += 1
+
+    def e2e_step():
+        if state["issued"] == len(state["run"]):  # next run (warm-up, then the timed steps)
+            state["run"], state["issued"] = runs.pop(0), 0
+        counts.zero()
+        st = {}
+        for c in range(n_chr):
+            top_up()
+            cur = state["queue"].pop(0)
+            top_up()
+            filtered, _ = flt.filter_device(cur, ident)
+            s1 = counts.accumulate(filtered, w["L"], ident, w["eps"], w["h"], w["theta"], w["num_threads"], args.path)
+            st["sig_loci"] = st.get("sig_loci", 0) + filtered.n_loci
+            for k in ("ms_gemm", "ms_stage", "ms_link", "ms_first_order", "ms_multi", "gemm_launches"):
+                st[k] = st.get(k, 0) + (s1.get(k, 0) or 0)
+            filtered.free()
+            cur.free()
+        sdist.reduce_counts(counts, device, dst=0)
+        if rank == 0:
+            counts.finalize(*lik, w["normalization"], out=out_host, to_host=True)
+        return st
+
+    ms_e2e, acc_e2e, _, _ = timed(e2e_step, e2e_steps, E2E_WARMUP)
+    ctx.synchronize()
     h2d = host.row_ptr.nbytes + host.position.nbytes + host.read_id.nbytes + host.gid_base.nbytes + host.chr_ptr.nbytes
     d2h = N * N * 8
+    sig_e2e = torch.tensor([acc_e2e["sig_loci"] // e2e_steps], device=device, dtype=torch.int64)
+    if world > 1:
+        dist.all_reduce(sig_e2e)
+    assert int(sig_e2e.item()) == sig_total, "the chromosome-wise end-to-end path must see the same significant loci"
 
     if rank == 0:
         M = out_host
@@ -372,7 +425,10 @@ def main_ours(args):
                                                                          "ms_multi", "ms_epilogue", "ms_reduce")},
             "roofline": roofline, "cpu_baseline": cpu,
             "e2e": {"value": e2e_value, "unit": "loci/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-                    "ms_per_step": ms_e2e / e2e_steps, "steps": e2e_steps},
+                    "ms_per_step": ms_e2e / e2e_steps, "steps": e2e_steps,
+                    "how": "host pinned pileup -> sgpu_pileup_upload_async per chromosome (copy stream, overlapping the "
+                           "kernels of the previous chromosome) -> filter -> accumulate -> reduce -> finalize -> N x N "
+                           "fp64 matrix in host memory, every step"},
             "gpu_launches": int(launches), "clocks": clocks,
         }
         print(json.dumps(line))

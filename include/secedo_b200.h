@@ -100,6 +100,13 @@ uint64_t sgpu_launch_count(const sgpu_ctx *ctx);
 int sgpu_pileup_upload(sgpu_ctx *ctx, uint32_t n_chr, const uint64_t *chr_ptr, const uint64_t *row_ptr,
                        const uint32_t *position, const uint32_t *read_id, const uint16_t *gid_base,
                        sgpu_pileup **out);
+/* The same without waiting for the copies: they run on the context's copy stream, so that the upload
+ * of the next batch of chromosomes overlaps the kernels of the current one (the host arrays must stay
+ * valid, and should be pinned, until the pileup is first used or sgpu_synchronize returns). Every
+ * function that takes the pileup waits for its copies on the device. */
+int sgpu_pileup_upload_async(sgpu_ctx *ctx, uint32_t n_chr, const uint64_t *chr_ptr, const uint64_t *row_ptr,
+                             const uint32_t *position, const uint32_t *read_id, const uint16_t *gid_base,
+                             sgpu_pileup **out);
 /* Adopt arrays that already live on this context's device (not copied, not freed). */
 int sgpu_pileup_wrap_device(sgpu_ctx *ctx, uint32_t n_chr, const uint64_t *host_chr_ptr,
                             const uint64_t *dev_row_ptr, const uint32_t *dev_position,

@@ -89,6 +89,16 @@ class Context:
                                                 _ptr(p.read_id), _ptr(p.gid_base), C.byref(h)))
         return DevicePileup(self, h)
 
+    def upload_async(self, p: Pileup) -> "DevicePileup":
+        """Upload on the context's copy stream without waiting: overlaps the kernels of the work issued
+        next. The host arrays must stay alive (and should be pinned) until the pileup is first used."""
+        h = C.c_void_p()
+        self.check(self._lib.sgpu_pileup_upload_async(self._h, p.n_chr, _ptr(p.chr_ptr), _ptr(p.row_ptr), _ptr(p.position),
+                                                      _ptr(p.read_id), _ptr(p.gid_base), C.byref(h)))
+        dp = DevicePileup(self, h)
+        dp._keepalive = p
+        return dp
+
     def wrap_device(self, chr_ptr: np.ndarray, d_row_ptr: int, d_position: int, d_read_id: int, d_gid_base: int,
                     keepalive=None) -> "DevicePileup":
         chr_ptr = np.ascontiguousarray(chr_ptr, np.uint64)

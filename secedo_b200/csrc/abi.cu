@@ -28,14 +28,27 @@ void sgpu_trace_point(sgpu_ctx *ctx, const char *what) {
 
 // ---- device memory cache -------------------------------------------------------------------------
 cudaError_t sgpu_dev_alloc(sgpu_ctx *ctx, void **p, size_t bytes) {
-    bytes = (std::max<size_t>(bytes, 1) + 255) & ~static_cast<size_t>(255);
+    // size classes with 3 mantissa bits (<= 12.5 % slack): the same logical buffer keeps landing in the
+    // same class although its exact size changes from call to call, so the cache stops growing after
+    // the first pass over a workload
+    bytes = std::max<size_t>(bytes, 256);
+    int top = 63;
+    while (!(bytes >> top)) {
+        --top;
+    }
+    const size_t gran = std::max<size_t>(256, static_cast<size_t>(1) << (top > 3 ? top - 3 : 0));
+    bytes = (bytes + gran - 1) / gran * gran;
     auto it = ctx->free_blocks.lower_bound(bytes);
-    if (it != ctx->free_blocks.end() && it->first <= bytes + bytes / 4 + (1u << 20)) {
+    if (it != ctx->free_blocks.end() && it->first <= 2 * bytes) {
         *p = it->second;
         ctx->live_blocks.emplace(it->second, it->first);
         ctx->cached_bytes -= it->first;
         ctx->free_blocks.erase(it);
         return cudaSuccess;
+    }
+    if (ctx->trace_alloc) {
+        fprintf(stderr, "[sgpu trace] cudaMalloc %.1f MB (cache holds %.1f MB in %zu blocks)\n", bytes / 1048576.0,
+                ctx->cached_bytes / 1048576.0, ctx->free_blocks.size());
     }
     cudaError_t e = cudaMalloc(p, bytes);
     if (e == cudaErrorMemoryAllocation) { // out of memory: give the cached blocks back and retry
@@ -152,6 +165,7 @@ int sgpu_init(int device, sgpu_ctx **out) {
     ctx->device = device;
     const char *tr = getenv("SECEDO_B200_TRACE");
     ctx->trace = tr && tr[0] == '1';
+    ctx->trace_alloc = tr && tr[0] == '2';
     *out = ctx;
     SGPU_CUDA(ctx, cudaSetDevice(device));
     cudaDeviceProp prop;
@@ -193,6 +207,10 @@ void sgpu_shutdown(sgpu_ctx *ctx) {
             cudaFree(ctx->d_scratch);
         }
         ctx->stream = nullptr;
+        if (ctx->copy_stream) {
+            cudaStreamSynchronize(ctx->copy_stream);
+            cudaStreamDestroy(ctx->copy_stream);
+        }
         cudaStreamSynchronize(ctx->own_stream);
         cudaStreamDestroy(ctx->own_stream);
     }
@@ -212,16 +230,32 @@ int sgpu_set_stream(sgpu_ctx *ctx, void *cuda_stream) {
 uint64_t sgpu_launch_count(const sgpu_ctx *ctx) { return ctx ? ctx->launches : 0; }
 
 int sgpu_synchronize(sgpu_ctx *ctx) {
+    if (ctx->copy_stream) {
+        SGPU_CUDA(ctx, cudaStreamSynchronize(ctx->copy_stream));
+    }
     SGPU_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     return SGPU_OK;
 }
 
 // ---- pileup ---------------------------------------------------------------------------------------
-int sgpu_pileup_upload(sgpu_ctx *ctx, uint32_t n_chr, const uint64_t *chr_ptr, const uint64_t *row_ptr,
-                       const uint32_t *position, const uint32_t *read_id, const uint16_t *gid_base,
-                       sgpu_pileup **out) {
+static int pileup_upload(sgpu_ctx *ctx, uint32_t n_chr, const uint64_t *chr_ptr, const uint64_t *row_ptr,
+                         const uint32_t *position, const uint32_t *read_id, const uint16_t *gid_base, bool async,
+                         sgpu_pileup **out) {
     SGPU_CUDA(ctx, cudaSetDevice(ctx->device));
     cudaStream_t st = ctx->stream;
+    if (async) {
+        if (!ctx->copy_stream) {
+            SGPU_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+        }
+        // the blocks may come from the cache with work of their previous life still queued on the
+        // compute stream: the copies start behind everything queued there so far
+        cudaEvent_t ev;
+        SGPU_CUDA(ctx, cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+        SGPU_CUDA(ctx, cudaEventRecord(ev, ctx->stream));
+        SGPU_CUDA(ctx, cudaStreamWaitEvent(ctx->copy_stream, ev, 0));
+        SGPU_CUDA(ctx, cudaEventDestroy(ev));
+        st = ctx->copy_stream;
+    }
     sgpu_pileup *p = new sgpu_pileup();
     p->n_chr = n_chr;
     p->n_loci = chr_ptr[n_chr];
@@ -234,7 +268,8 @@ int sgpu_pileup_upload(sgpu_ctx *ctx, uint32_t n_chr, const uint64_t *chr_ptr, c
     SGPU_CUDA(ctx, sgpu_dev_alloc(ctx, reinterpret_cast<void **>(&p->d_position), (P ? P : 1) * sizeof(uint32_t)));
     SGPU_CUDA(ctx, sgpu_dev_alloc(ctx, reinterpret_cast<void **>(&p->d_read_id), (E ? E : 1) * sizeof(uint32_t)));
     SGPU_CUDA(ctx, sgpu_dev_alloc(ctx, reinterpret_cast<void **>(&p->d_gid_base), (E ? E : 1) * sizeof(uint16_t)));
-    SGPU_CUDA(ctx, cudaMemcpyAsync(p->d_chr_ptr, chr_ptr, (n_chr + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, st));
+    // the copy of chr_ptr reads p->h_chr_ptr (owned by the pileup), not the caller's array
+    SGPU_CUDA(ctx, cudaMemcpyAsync(p->d_chr_ptr, p->h_chr_ptr, (n_chr + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, st));
     if (P) {
         SGPU_CUDA(ctx, cudaMemcpyAsync(p->d_row_ptr, row_ptr, (P + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, st));
         SGPU_CUDA(ctx, cudaMemcpyAsync(p->d_position, position, P * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
@@ -245,9 +280,26 @@ int sgpu_pileup_upload(sgpu_ctx *ctx, uint32_t n_chr, const uint64_t *chr_ptr, c
         SGPU_CUDA(ctx, cudaMemcpyAsync(p->d_read_id, read_id, E * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
         SGPU_CUDA(ctx, cudaMemcpyAsync(p->d_gid_base, gid_base, E * sizeof(uint16_t), cudaMemcpyHostToDevice, st));
     }
-    SGPU_CUDA(ctx, cudaStreamSynchronize(st));
+    if (async) {
+        SGPU_CUDA(ctx, cudaEventCreateWithFlags(&p->ready, cudaEventDisableTiming));
+        SGPU_CUDA(ctx, cudaEventRecord(p->ready, st));
+    } else {
+        SGPU_CUDA(ctx, cudaStreamSynchronize(st));
+    }
     *out = p;
     return SGPU_OK;
+}
+
+int sgpu_pileup_upload(sgpu_ctx *ctx, uint32_t n_chr, const uint64_t *chr_ptr, const uint64_t *row_ptr,
+                       const uint32_t *position, const uint32_t *read_id, const uint16_t *gid_base,
+                       sgpu_pileup **out) {
+    return pileup_upload(ctx, n_chr, chr_ptr, row_ptr, position, read_id, gid_base, false, out);
+}
+
+int sgpu_pileup_upload_async(sgpu_ctx *ctx, uint32_t n_chr, const uint64_t *chr_ptr, const uint64_t *row_ptr,
+                             const uint32_t *position, const uint32_t *read_id, const uint16_t *gid_base,
+                             sgpu_pileup **out) {
+    return pileup_upload(ctx, n_chr, chr_ptr, row_ptr, position, read_id, gid_base, true, out);
 }
 
 int sgpu_pileup_wrap_device(sgpu_ctx *ctx, uint32_t n_chr, const uint64_t *host_chr_ptr, const uint64_t *dev_row_ptr,
@@ -297,6 +349,7 @@ int sgpu_pileup_dims(const sgpu_pileup *p, uint32_t *n_chr, uint64_t *n_loci, ui
 int sgpu_pileup_download(sgpu_ctx *ctx, const sgpu_pileup *p, uint64_t *chr_ptr, uint64_t *row_ptr, uint32_t *position,
                          uint32_t *read_id, uint16_t *gid_base) {
     SGPU_CUDA(ctx, cudaSetDevice(ctx->device));
+    SGPU_WAIT_PILEUP(ctx, p);
     cudaStream_t st = ctx->stream;
     if (chr_ptr) {
         std::memcpy(chr_ptr, p->h_chr_ptr, (p->n_chr + 1) * sizeof(uint64_t));
@@ -324,6 +377,12 @@ void sgpu_pileup_free(sgpu_ctx *ctx, sgpu_pileup *p) {
     if (ctx) {
         cudaSetDevice(ctx->device);
     }
+    if (p->ready) {
+        if (ctx) { // the blocks go back to the cache of the compute stream: order it behind the copies
+            cudaStreamWaitEvent(ctx->stream, p->ready, 0);
+        }
+        cudaEventDestroy(p->ready);
+    }
     sgpu_dev_free(ctx, p->d_chr_ptr); // reuse is stream ordered: safe after everything already queued
     if (p->owns) {
         sgpu_dev_free(ctx, p->d_row_ptr);
@@ -345,6 +404,7 @@ int sgpu_is_significant(sgpu_ctx *ctx, const uint16_t *counts4, uint64_t n, doub
 int sgpu_filter(sgpu_ctx *ctx, const sgpu_pileup *in, const uint32_t *id_to_pos, uint32_t n_groups, double theta,
                 int cell_proportion, sgpu_pileup **filtered, double *avg_coverage) {
     SGPU_CUDA(ctx, cudaSetDevice(ctx->device));
+    SGPU_WAIT_PILEUP(ctx, in);
     return sgpu_filter_impl(ctx, in, id_to_pos, n_groups, theta, cell_proportion, filtered, avg_coverage);
 }
 
@@ -397,6 +457,7 @@ int sgpu_counts_accumulate(sgpu_ctx *ctx, sgpu_counts *c, const sgpu_pileup *fil
                            double homozygous_rate, double seq_error_rate, uint32_t num_threads, int path,
                            sgpu_stats *stats) {
     SGPU_CUDA(ctx, cudaSetDevice(ctx->device));
+    SGPU_WAIT_PILEUP(ctx, filtered);
     if (path < SGPU_PATH_AUTO || path > SGPU_PATH_GEMM) {
         return sgpu_fail(ctx, SGPU_E_ARG, "unknown path %d", path);
     }

@@ -20,6 +20,7 @@ struct sgpu_ctx {
     int sm_count = 148;
     cudaStream_t own_stream = nullptr;
     cudaStream_t stream = nullptr;
+    cudaStream_t copy_stream = nullptr; // sgpu_pileup_upload_async
     std::string error;
     // small pinned scratch for device->host scalars
     uint64_t *h_scratch = nullptr; // 64 x u64, pinned
@@ -46,6 +47,7 @@ struct sgpu_ctx {
     size_t cached_bytes = 0;
     // SECEDO_B200_TRACE=1: synchronise and print the wall-clock time between trace points (debug aid)
     bool trace = false;
+    bool trace_alloc = false; // SECEDO_B200_TRACE=2: log every real cudaMalloc
     double trace_t0 = 0.0;
 };
 
@@ -64,6 +66,13 @@ void sgpu_trace_point(sgpu_ctx *ctx, const char *what);
     } while (0)
 
 int sgpu_fail(sgpu_ctx *ctx, int code, const char *fmt, ...);
+// make the context's stream wait for an asynchronously uploaded pileup
+#define SGPU_WAIT_PILEUP(ctx, p)                                                                   \
+    do {                                                                                           \
+        if ((p) && (p)->ready) {                                                                   \
+            SGPU_CUDA((ctx), cudaStreamWaitEvent((ctx)->stream, (p)->ready, 0));                   \
+        }                                                                                          \
+    } while (0)
 
 #define SGPU_CUDA(ctx, expr)                                                                       \
     do {                                                                                           \
@@ -134,6 +143,7 @@ struct sgpu_pileup {
     uint32_t *d_read_id = nullptr;
     uint16_t *d_gid_base = nullptr;
     bool owns = true;
+    cudaEvent_t ready = nullptr;   // set by sgpu_pileup_upload_async: the copies are done
     mutable uint32_t max_row = 0;  // entries of the largest locus (0 = not known yet; cached by reads.cu)
 };
 

@@ -205,6 +205,33 @@ def test_auto_path_and_stats(gpu_ctx):
     assert gpu_ctx.launch_count() > n0
 
 
+def test_async_upload_pipeline(gpu_ctx):
+    """chromosome by chromosome with asynchronous uploads running ahead of the kernels (the end-to-end
+    path of bench.py): same counts as one synchronous call on the whole pileup"""
+    cfg = SynthConfig(n_cells=350, coverage=0.3, n_loci=2400, n_chr=4, p_multi=0.08, p_mate=0.04, seed=71)
+    p = make_pileup(cfg)
+    ident = np.arange(cfg.n_cells, dtype=np.uint32)
+    flt = api.Filter(0.01, 4, gpu_ctx)
+    args = (1000, ident, 0.01, 0.5, 0.01, 8)
+    whole = api.Counts(gpu_ctx, cfg.n_cells)
+    f_all, _ = flt.filter_device(p, ident)
+    whole.accumulate(f_all, *args, path="gemm")
+    parts = [p.loci_range(c, 0, 1 << 40) for c in range(p.n_chr)]
+    piped = api.Counts(gpu_ctx, cfg.n_cells)
+    queue = [gpu_ctx.upload_async(parts[0]), gpu_ctx.upload_async(parts[1])]
+    for c in range(p.n_chr):
+        cur = queue.pop(0)
+        if c + 2 < p.n_chr:
+            queue.append(gpu_ctx.upload_async(parts[c + 2]))
+        f, _ = flt.filter_device(cur, ident)
+        piped.accumulate(f, *args, path="gemm")
+        f.free()
+        cur.free()
+    for x, y in zip(whole.download(), piped.download()):
+        assert np.array_equal(x, y)
+    assert np.array_equal(whole.finalize(1000, 0.01, 0.5, 0.01, "ADD_MIN"), piped.finalize(1000, 0.01, 0.5, 0.01, "ADD_MIN"))
+
+
 @pytest.mark.parametrize("panel_loci", [32, 96, 256])
 def test_several_gemm_panels(gpu_ctx, panel_loci, monkeypatch):
     """inputs larger than one operand panel (2 GB) are processed panel by panel: the first panel stores
