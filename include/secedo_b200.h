@@ -107,6 +107,19 @@ int sgpu_pileup_upload(sgpu_ctx *ctx, uint32_t n_chr, const uint64_t *chr_ptr, c
 int sgpu_pileup_upload_async(sgpu_ctx *ctx, uint32_t n_chr, const uint64_t *chr_ptr, const uint64_t *row_ptr,
                              const uint32_t *position, const uint32_t *read_id, const uint16_t *gid_base,
                              sgpu_pileup **out);
+/* Direct ingestion of SECEDO's binary pileup files (replaces read_pileup_bin, util/pileup_reader.cpp:139-257,
+ * and the flattening of its vector<PosData>): one buffer per chromosome holding the bytes of the `.bin` file
+ *     u32 position | u16 coverage | u32 read_id[coverage] | u16 (cell_id << 2 | base)[coverage]   per locus.
+ * The host only walks the records; the bytes are copied to the device as they are and unpacked there with
+ * id_to_group applied (get_grouping, :273). Loci with coverage > max_coverage are skipped (:195-197); if
+ * positions is not NULL, positions[c] (ascending, n_positions[c] values, may be empty = no filter) selects the
+ * loci of chromosome c (:199-210). A cell id >= n_ids is an error (the reference exits). n_cells / n_groups
+ * receive max cell id + 1 / max group id + 1 (:232-233); max_fragment_length is 1000 as for the reference
+ * without --compute_read_stats (:256). */
+int sgpu_pileup_from_bin(sgpu_ctx *ctx, uint32_t n_chr, const void *const *file_bytes, const uint64_t *file_sizes,
+                         const uint16_t *id_to_group, uint32_t n_ids, uint32_t max_coverage,
+                         const uint32_t *const *positions, const uint64_t *n_positions, sgpu_pileup **out,
+                         uint32_t *n_cells, uint32_t *n_groups);
 /* Adopt arrays that already live on this context's device (not copied, not freed). */
 int sgpu_pileup_wrap_device(sgpu_ctx *ctx, uint32_t n_chr, const uint64_t *host_chr_ptr,
                             const uint64_t *dev_row_ptr, const uint32_t *dev_position,

@@ -221,5 +221,24 @@ def ref_read_pileup_text(path: str, max_coverage: int = 100):
     return out, int(max_len)
 
 
+def ref_read_pileup(path: str, id_to_group, max_coverage: int = 100, positions=()):
+    """The reference's read_pileup (.bin or text by suffix) with a grouping and an optional position list;
+    returns (arrays namespace, n_cells, max_fragment_length)."""
+    nl, ne, ml = C.c_uint64(), C.c_uint64(), C.c_uint32()
+    lib = ref_lib()
+    g = np.ascontiguousarray(id_to_group, np.uint16)
+    pos = np.ascontiguousarray(positions, np.uint32)
+    lib.ref_read_pileup.restype = C.c_uint32
+    n_cells = lib.ref_read_pileup(path.encode(), _p(g, C.POINTER(C.c_uint16)), C.c_uint32(g.size), C.c_uint32(max_coverage),
+                                  _p(pos, _u32p), C.c_uint64(pos.size), C.byref(nl), C.byref(ne), C.byref(ml))
+    out = SimpleNamespace(chr_ptr=np.zeros(2, np.uint64), row_ptr=np.zeros(nl.value + 1, np.uint64),
+                          position=np.zeros(nl.value, np.uint32), read_id=np.zeros(ne.value, np.uint32),
+                          gid_base=np.zeros(ne.value, np.uint16))
+    lib.ref_filter_fetch(_p(out.chr_ptr, _u64p), _p(out.row_ptr, _u64p), _p(out.position, _u32p),
+                         _p(out.read_id, _u32p), _p(out.gid_base, _u16p))
+    out.n_chr, out.n_loci, out.n_entries = 1, int(nl.value), int(ne.value)
+    return out, int(n_cells), int(ml.value)
+
+
 def ref_omp_max_threads() -> int:
     return ref_lib().ref_omp_max_threads()

@@ -199,6 +199,34 @@ uint32_t ref_read_pileup_text(const char *fname,
     return max_len;
 }
 
+/**
+ * read_pileup (text or .bin by suffix) with an explicit grouping, max_coverage and an optional list of
+ * positions (util/pileup_reader.cpp:259-271); same two-call protocol. Returns n_cells (max cell id + 1).
+ */
+uint32_t ref_read_pileup(const char *fname,
+                         const uint16_t *id_to_group,
+                         uint32_t n_ids,
+                         uint32_t max_coverage,
+                         const uint32_t *positions,
+                         uint64_t n_positions,
+                         uint64_t *n_loci_out,
+                         uint64_t *n_entries_out,
+                         uint32_t *max_len_out) {
+    std::vector<uint16_t> grouping(id_to_group, id_to_group + n_ids);
+    std::vector<uint32_t> pos(positions, positions + n_positions);
+    auto [pds, n_cells, max_len] = read_pileup(fname, grouping, [](uint64_t) {}, max_coverage, pos, false);
+    uint64_t ne = 0;
+    for (const auto &pd : pds) {
+        ne += pd.size();
+    }
+    *n_loci_out = pds.size();
+    *n_entries_out = ne;
+    *max_len_out = max_len;
+    g_filtered.clear();
+    g_filtered.push_back(std::move(pds));
+    return n_cells;
+}
+
 int ref_omp_max_threads() {
     return omp_get_max_threads();
 }

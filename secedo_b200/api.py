@@ -16,6 +16,7 @@ this shim, which defines the reference's own symbols, lives in ``secedo_b200/hos
 from __future__ import annotations
 
 import ctypes as C
+import os
 from typing import Optional, Sequence, Tuple, Union
 
 import numpy as np
@@ -98,6 +99,32 @@ class Context:
         dp = DevicePileup(self, h)
         dp._keepalive = p
         return dp
+
+    def pileup_from_bin(self, files: Sequence, id_to_group: Sequence[int], max_coverage: int = 100,
+                        positions: Optional[Sequence[Sequence[int]]] = None):
+        """Direct ingestion of the reference's binary pileup files (``read_pileup_bin``,
+        util/pileup_reader.cpp:139-257), one per chromosome: ``files`` holds paths or bytes-like objects.
+        Returns ``(DevicePileup, n_cells, n_groups, max_fragment_length)``; the last is 1000 like the
+        reference without ``--compute_read_stats``."""
+        bufs = []
+        for f in files:
+            if isinstance(f, (str, os.PathLike)):
+                f = np.fromfile(f, dtype=np.uint8)
+            bufs.append(np.frombuffer(f, dtype=np.uint8) if not isinstance(f, np.ndarray) else np.ascontiguousarray(f, np.uint8))
+        n = len(bufs)
+        ptrs = (C.c_void_p * max(n, 1))(*[b.ctypes.data if b.size else None for b in bufs])
+        sizes = np.array([b.size for b in bufs], np.uint64)
+        g = np.ascontiguousarray(id_to_group, np.uint16)
+        pos_ptrs, pos_n, keep = None, None, []
+        if positions is not None:
+            keep = [np.ascontiguousarray(x, np.uint32) for x in positions]
+            assert len(keep) == n
+            pos_ptrs = (C.c_void_p * max(n, 1))(*[x.ctypes.data if x.size else None for x in keep])
+            pos_n = np.array([x.size for x in keep], np.uint64)
+        h, nc, ng = C.c_void_p(), C.c_uint32(), C.c_uint32()
+        self.check(self._lib.sgpu_pileup_from_bin(self._h, n, ptrs, _ptr(sizes), _ptr(g), g.size, int(max_coverage), pos_ptrs,
+                                                  _ptr(pos_n), C.byref(h), C.byref(nc), C.byref(ng)))
+        return DevicePileup(self, h), nc.value, ng.value, 1000
 
     def wrap_device(self, chr_ptr: np.ndarray, d_row_ptr: int, d_position: int, d_read_id: int, d_gid_base: int,
                     keepalive=None) -> "DevicePileup":

@@ -143,6 +143,60 @@ class Pileup:
         chr_ptr = cum_loci[self.chr_ptr.astype(np.int64)]
         return Pileup(chr_ptr, row_ptr, self.position[keep_locus], self.read_id[keep_entry], self.gid_base[keep_entry])
 
+    def to_bin(self, chrom: int) -> bytes:
+        """One chromosome in the reference's binary pileup format (written by pileup.cpp:327-332, read by
+        util/pileup_reader.cpp:165-179): per locus ``u32 position, u16 coverage, u32 read_id[coverage],
+        u16 (cell_id << 2 | base)[coverage]``."""
+        out = bytearray()
+        for l in range(int(self.chr_ptr[chrom]), int(self.chr_ptr[chrom + 1])):
+            a, b = int(self.row_ptr[l]), int(self.row_ptr[l + 1])
+            assert b - a < 65536, "coverage is a uint16 in the binary format"
+            out += np.uint32(self.position[l]).tobytes() + np.uint16(b - a).tobytes()
+            out += self.read_id[a:b].astype("<u4").tobytes() + self.gid_base[a:b].astype("<u2").tobytes()
+        return bytes(out)
+
+    @staticmethod
+    def from_bin(files: Sequence[bytes], id_to_group: Sequence[int], max_coverage: int = 100,
+                 positions: Sequence[Sequence[int]] = None) -> Tuple["Pileup", int, int]:
+        """Host-side restatement of ``read_pileup_bin`` (util/pileup_reader.cpp:139-257) over one buffer per
+        chromosome, used to check ``sgpu_pileup_from_bin``: returns (pileup, n_cells, n_groups)."""
+        g = np.asarray(id_to_group, np.uint16)
+        chr_ptr, row_ptr, pos, rid, gb = [0], [0], [], [], []
+        max_cell = max_group = 0
+        for c, buf in enumerate(files):
+            buf = bytes(buf)
+            plist = None if positions is None or len(positions[c]) == 0 else list(positions[c])
+            pidx, off = 0, 0
+            while off + 6 <= len(buf):
+                p = int(np.frombuffer(buf, "<u4", 1, off)[0])
+                cov = int(np.frombuffer(buf, "<u2", 1, off + 4)[0])
+                ids = np.frombuffer(buf, "<u4", cov, off + 6)
+                cb = np.frombuffer(buf, "<u2", cov, off + 6 + 4 * cov)
+                off += 6 + 6 * cov
+                if cov > max_coverage:
+                    continue
+                if plist is not None:
+                    while pidx < len(plist) and plist[pidx] < p:
+                        pidx += 1
+                    if pidx == len(plist):
+                        break
+                    if plist[pidx] > p:
+                        continue
+                cells = cb >> 2
+                if cells.size and int(cells.max()) >= g.size:
+                    raise ValueError("Cell id is too large")
+                groups = g[cells]
+                if cells.size:
+                    max_cell, max_group = max(max_cell, int(cells.max())), max(max_group, int(groups.max()))
+                pos.append(p)
+                rid.append(ids)
+                gb.append((groups.astype(np.uint16) << 2) | (cb & 3))
+                row_ptr.append(row_ptr[-1] + cov)
+            chr_ptr.append(len(pos))
+        cat = lambda xs, dt: np.concatenate(xs).astype(dt) if xs else np.zeros(0, dt)  # noqa: E731
+        return (Pileup(np.array(chr_ptr, np.uint64), np.array(row_ptr, np.uint64), np.array(pos, np.uint32),
+                       cat(rid, np.uint32), cat(gb, np.uint16)), max_cell + 1, max_group + 1)
+
     def loci_range(self, chrom: int, lo: int, hi: int) -> "Pileup":
         """Loci [lo, hi) of one chromosome as a single-chromosome pileup."""
         base = int(self.chr_ptr[chrom])

@@ -147,6 +147,36 @@ def main():
         tabs[f"ls{i}"] = ls
         tabs[f"ld{i}"] = ld
     np.savez_compressed(os.path.join(OUT, "log_probs.npz"), **tabs)
+
+    # ---- binary pileup ingestion: read_pileup_bin of the reference on files in its own format -----------
+    bins = {}
+    # (a) the reference's own text fixture, converted with its grouping file (tests/data/six_cells.pileup.group)
+    cfg = SynthConfig(n_cells=300, coverage=0.15, n_loci=400, n_chr=2, p_multi=0.1, p_mate=0.05, seed=81)
+    p = make_pileup(cfg)
+    rng = np.random.default_rng(3)
+    grouping = (np.arange(10000) // 3).astype(np.uint16)           # --merge_count 3
+    scrambled = rng.permutation(10000).astype(np.uint16) % 117      # a --merge_file style mapping
+    for c in range(p.n_chr):
+        path = os.path.join(tmp, f"chr{c}.bin")
+        raw = p.to_bin(c)
+        open(path, "wb").write(raw)
+        bins[f"file{c}"] = np.frombuffer(raw, np.uint8)
+        chrom = p.loci_range(c, 0, 1 << 40)
+        some = np.sort(rng.choice(chrom.position, chrom.position.size // 3, replace=False)).astype(np.uint32)
+        some = np.unique(np.concatenate([some, some[:5] + 1]))     # a few positions that are not in the file
+        cases = {"ident": (np.arange(10000, dtype=np.uint16), 100, np.zeros(0, np.uint32)),
+                 "merge3_cov40": (grouping, 40, np.zeros(0, np.uint32)),
+                 "mapfile_pos": (scrambled, 100, some),
+                 "pos_early_stop": (np.arange(10000, dtype=np.uint16), 100, some[: some.size // 4])}
+        for name, (g, maxcov, pos) in cases.items():
+            r, n_cells, max_len = po.ref_read_pileup(path, g, maxcov, pos)
+            k = f"c{c}_{name}_"
+            bins[k + "grouping"], bins[k + "max_coverage"], bins[k + "positions"] = g, np.int64(maxcov), pos
+            bins[k + "n_cells"], bins[k + "max_len"] = np.int64(n_cells), np.int64(max_len)
+            for f in ("row_ptr", "position", "read_id", "gid_base"):
+                bins[k + f] = getattr(r, f)
+            print("bin", c, name, r.n_loci, r.n_entries, n_cells, max_len)
+    np.savez_compressed(os.path.join(OUT, "pileup_bin.npz"), **bins)
     shutil.rmtree(tmp)
 
 
