@@ -40,6 +40,10 @@ constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
 constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /* alignment slack */ + 256 /* barriers */;
 constexpr int GEMM_THREADS = 192;  // 6 warps
 constexpr uint32_t TMEM_COLS = 512;
+#ifndef SGPU_PREFETCH_KB
+#define SGPU_PREFETCH_KB 0
+#endif
+constexpr uint32_t PREFETCH_KB = SGPU_PREFETCH_KB; // k-blocks an L2 prefetch runs ahead of the TMA loads; 0 = off (measured: 12 ahead doubles the kernel time, the TMA unit serialises the prefetches with the loads)
 
 // Panel layout. One 128-byte row per (cell, k-block of 32 loci). The rows of CK consecutive k-blocks
 // form a chunk [chunk][cell][k-block in chunk]: the ~1 200 loci that are staged concurrently then touch
@@ -442,6 +446,11 @@ __device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap *map
             "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
             : "memory");
 }
+// bring a box into L2 without touching shared memory (hides DRAM latency the 4-stage ring cannot cover)
+__device__ __forceinline__ void tma_prefetch_3d(const CUtensorMap *map, int32_t c0, int32_t c1, int32_t c2) {
+    asm volatile("cp.async.bulk.prefetch.tensor.3d.L2.global.tile [%0, {%1, %2, %3}];" ::"l"(map), "r"(c0), "r"(c1), "r"(c2)
+                 : "memory");
+}
 __device__ __forceinline__ bool elect_one() {
     uint32_t pred;
     asm volatile(
@@ -576,6 +585,14 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) syrk_kernel(const __grid_cons
             for (uint32_t w = blockIdx.x; w < n_work; w += gridDim.x) {
                 const WorkItem wi = work_item(wl, w);
                 for (uint32_t kb = wi.k0; kb < wi.k1; ++kb) {
+                    if (PREFETCH_KB && kb + PREFETCH_KB < wi.k1 && kb + PREFETCH_KB < wl.kb_neg0) {
+                        const uint32_t kp = kb + PREFETCH_KB;
+                        const int32_t chp = static_cast<int32_t>(kp >> wl.ck_shift);
+                        const int32_t kxp = static_cast<int32_t>((kp - (static_cast<uint32_t>(chp) << wl.ck_shift)) * KB_BYTES);
+                        tma_prefetch_3d(&map_u, kxp, wi.rb * BM, chp);
+                        tma_prefetch_3d(&map_u, kxp, wi.cb * BN, chp);
+                        tma_prefetch_3d(&map_u, kxp, wi.cb * BN + 128, chp);
+                    }
                     mbar_wait(empty0 + 8 * stage, phase ^ 1);
                     const uint32_t sa = smem_u32(smem + stage * STAGE_BYTES), sb = sa + A_BYTES;
                     const uint32_t bar = full0 + 8 * stage;

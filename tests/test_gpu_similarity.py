@@ -205,6 +205,41 @@ def test_auto_path_and_stats(gpu_ctx):
     assert gpu_ctx.launch_count() > n0
 
 
+@pytest.mark.parametrize("n_cells,coverage,loci_per_chr", [(8000, 0.5, 384), (10000, 0.05, 4096), (16000, 0.25, 96)])
+def test_full_size_paths_agree(gpu_ctx, n_cells, coverage, loci_per_chr):
+    """BASELINE.json's cell counts (cfg3: 8 000 cells at 0.5x, cfg4: 10 000 cells at 0.05x, and the largest
+    matrix the 14-bit group id allows) on device-generated pileups, too large for the oracle: the tcgen05
+    GEMM path and the pair-scatter path — two independent implementations of the first-order counts — must
+    agree bit for bit, counts must add up over disjoint chromosome sets, and the matrix is symmetric with
+    a zero diagonal and minimum 0 (ADD_MIN)."""
+    dev = gpu_ctx.synth_pileup(n_cells, coverage, 2, loci_per_chr, n_clones=4, theta=0.001, p_multi=0.01, p_mate=0.01, seed=13)
+    ident = np.arange(n_cells, dtype=np.uint32)
+    fdev, _ = api.Filter(0.001, 4, gpu_ctx).filter_device(dev, ident)
+    assert fdev.n_loci > loci_per_chr // 4
+    args = (1000, ident, 0.01, 0.5, 0.001, 8)
+    res = {}
+    for path in ("gemm", "scatter"):
+        c = api.Counts(gpu_ctx, n_cells)
+        st = c.accumulate(fdev, *args, path=path)
+        res[path] = c.download()
+        if path == "gemm":
+            M = c.finalize(1000, 0.01, 0.5, 0.001, "ADD_MIN")
+            assert np.array_equal(M, M.T) and not np.diag(M).any() and M.min() == 0.0 and np.isfinite(M).all()
+            assert st["n_multi_reads"] > 0 and st["n_dropped_entries"] > 0 and st["n_tail_reads"] > 0
+        c.free()
+    for a, b, name in zip(res["gemm"], res["scatter"], ("S", "D", "H", "hist")):
+        assert np.array_equal(a, b), f"{name} differs between the GEMM and the scatter path"
+    assert res["gemm"][0].sum() > 0 and res["gemm"][1].sum() > 0
+    # linearity over chromosomes: the two chromosomes one after the other == both at once
+    f = fdev.download()
+    two = api.Counts(gpu_ctx, n_cells)
+    for c_ in range(2):
+        two.accumulate(f.loci_range(c_, 0, 1 << 40), *args, path="gemm")
+    for a, b in zip(res["gemm"], two.download()):
+        assert np.array_equal(a, b)
+    two.free()
+
+
 def test_async_upload_pipeline(gpu_ctx):
     """chromosome by chromosome with asynchronous uploads running ahead of the kernels (the end-to-end
     path of bench.py): same counts as one synchronous call on the whole pileup"""
