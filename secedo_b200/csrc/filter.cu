@@ -105,12 +105,12 @@ __global__ void __launch_bounds__(FILTER_THREADS) filter_count_kernel(
         const uint64_t *__restrict__ row_ptr, const uint16_t *__restrict__ gid_base, uint64_t n_loci,
         const uint32_t *__restrict__ in_mask /* bit per group id */, uint32_t n_groups,
         uint4 *__restrict__ counts /* pooled A, C, G, T per locus */, int *__restrict__ err) {
-    extern __shared__ uint32_t s_mask[];
+    __shared__ uint32_t s_mask[512]; // one bit per 14-bit group id
     __shared__ uint32_t s_cnt[4];
     __shared__ int s_bad;
     const uint32_t mask_words = (n_groups + 31) / 32;
-    for (uint32_t i = threadIdx.x; i < mask_words; i += blockDim.x) {
-        s_mask[i] = in_mask[i];
+    for (uint32_t i = threadIdx.x; i < 512; i += blockDim.x) {
+        s_mask[i] = i < mask_words ? in_mask[i] : 0;
     }
     if (threadIdx.x < 4) {
         s_cnt[threadIdx.x] = 0;
@@ -122,21 +122,24 @@ __global__ void __launch_bounds__(FILTER_THREADS) filter_count_kernel(
     const int lane = threadIdx.x & 31;
     for (uint64_t l = blockIdx.x; l < n_loci; l += gridDim.x) {
         const uint64_t e0 = row_ptr[l], e1 = row_ptr[l + 1];
-        // per-thread counters packed 4 x 16 bit would overflow above 64k reads per thread; keep 32-bit
+        // per-thread counters: one byte per base packed in a word (one shift + add per entry), spilled
+        // into 32-bit counters before a byte can overflow
         uint32_t c[4] = { 0, 0, 0, 0 };
-        bool bad = false;
+        uint32_t packed = 0, since_flush = 0, max_gid = 0;
+        auto flush = [&]() {
+            c[0] += packed & 0xFFu;
+            c[1] += (packed >> 8) & 0xFFu;
+            c[2] += (packed >> 16) & 0xFFu;
+            c[3] += packed >> 24;
+            packed = 0;
+            since_flush = 0;
+        };
         auto count = [&](uint32_t gb) {
             const uint32_t gid = gb >> 2;
-            if (gid >= n_groups) {
-                bad = true;
-                return;
-            }
+            max_gid = max(max_gid, gid);
+            // gid is 14 bits and the shared-memory mask covers all 16 384 of them (bits behind n_groups are 0)
             const uint32_t in = (s_mask[gid >> 5] >> (gid & 31)) & 1u;
-            const uint32_t b = gb & 3u;
-            c[0] += in & (b == 0);
-            c[1] += in & (b == 1);
-            c[2] += in & (b == 2);
-            c[3] += in & (b == 3);
+            packed += in << (8u * (gb & 3u));
         };
         // 16-byte aligned middle part (none if the caller's array itself is not aligned)
         const bool aligned = (reinterpret_cast<uintptr_t>(gid_base) & 15u) == 0;
@@ -152,10 +155,19 @@ __global__ void __launch_bounds__(FILTER_THREADS) filter_count_kernel(
             for (int k = 0; k < 8; ++k) {
                 count((w[k >> 1] >> (16 * (k & 1))) & 0xFFFFu);
             }
+            since_flush += 8;
+            if (since_flush > 240) {
+                flush();
+            }
         }
-        for (uint64_t e = a1 + threadIdx.x; e < e1; e += FILTER_THREADS) {
+        for (uint64_t e = a1 + threadIdx.x; e < e1; e += FILTER_THREADS) { // < 8 entries, or all of an unaligned array
             count(gid_base[e]);
+            if (++since_flush > 240) {
+                flush();
+            }
         }
+        flush();
+        const bool bad = max_gid >= n_groups;
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) {
 #pragma unroll
@@ -238,23 +250,28 @@ __global__ void __launch_bounds__(FILTER_THREADS) filter_compact_kernel(
             out_position[nl] = position[l];
         }
         const uint64_t e0 = row_ptr[l], e1 = row_ptr[l + 1];
-        for (uint64_t base = e0; base < e1; base += 32) {
-            const uint64_t e = base + lane;
-            uint32_t gb = 0, rid = 0;
-            bool in = false;
-            if (e < e1) {
-                gb = gid_base[e];
-                rid = read_id[e];
-                const uint32_t gid = gb >> 2;
-                in = gid < n_groups && ((s_mask[gid >> 5] >> (gid & 31)) & 1u);
+        for (uint64_t base = e0; base < e1; base += 128) { // four independent 32-entry groups in flight
+            uint32_t gb[4], rid[4];
+            bool in[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const uint64_t e = base + 32 * u + lane;
+                gb[u] = e < e1 ? gid_base[e] : 0;
+                rid[u] = e < e1 ? read_id[e] : 0;
+                in[u] = e < e1;
             }
-            const uint32_t ballot = __ballot_sync(0xffffffffu, in);
-            if (in) {
-                const uint64_t dst = w + __popc(ballot & ((1u << lane) - 1u));
-                out_read_id[dst] = rid;
-                out_gid_base[dst] = static_cast<uint16_t>(gb);
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const uint32_t gid = gb[u] >> 2;
+                in[u] = in[u] && gid < n_groups && ((s_mask[gid >> 5] >> (gid & 31)) & 1u);
+                const uint32_t ballot = __ballot_sync(0xffffffffu, in[u]);
+                if (in[u]) {
+                    const uint64_t dst = w + __popc(ballot & ((1u << lane) - 1u));
+                    out_read_id[dst] = rid[u];
+                    out_gid_base[dst] = static_cast<uint16_t>(gb[u]);
+                }
+                w += __popc(ballot);
             }
-            w += __popc(ballot);
         }
     }
 }

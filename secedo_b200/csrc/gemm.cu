@@ -146,15 +146,16 @@ __global__ void __launch_bounds__(256) partition_kernel(const PartitionArgs a) {
                 s_cnt[threadIdx.x] = 0;
             }
             __syncthreads();
-            for (uint32_t ib = 0; ib < n; ib += 1024) {
-                uint32_t v[4];
+            constexpr int PU = 8; // entries per thread in flight
+            for (uint32_t ib = 0; ib < n; ib += 256 * PU) {
+                uint32_t v[PU];
 #pragma unroll
-                for (int u = 0; u < 4; ++u) {
+                for (int u = 0; u < PU; ++u) {
                     const uint32_t i = ib + 256 * u + threadIdx.x;
                     v[u] = i < n ? classify(e0 + i) : CB_SKIP;
                 }
 #pragma unroll
-                for (int u = 0; u < 4; ++u) {
+                for (int u = 0; u < PU; ++u) {
                     const uint32_t i = ib + 256 * u + threadIdx.x;
                     if (i < n) {
                         s_v[i] = static_cast<uint16_t>(v[u]);

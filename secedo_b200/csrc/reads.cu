@@ -210,19 +210,32 @@ __global__ void __launch_bounds__(WIN_THREADS) link_window_kernel(
                 break;
             }
             const uint64_t a0 = row_ptr[l], a1 = row_ptr[l + 1];
-            for (uint64_t e = a0 + threadIdx.x; e < a1; e += WIN_THREADS) {
-                const uint32_t id = read_id[e];
-                uint32_t s = slot_hash(id, shift);
-                for (;;) {
-                    const uint32_t cur = tab[s];
-                    if (cur == SLOT_EMPTY) {
+            for (uint64_t eb = a0 + threadIdx.x; eb < a1; eb += 4 * WIN_THREADS) {
+                uint32_t id4[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) { // four loads in flight
+                    const uint64_t e = eb + u * WIN_THREADS;
+                    id4[u] = e < a1 ? read_id[e] : 0;
+                }
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const uint64_t e = eb + u * WIN_THREADS;
+                    if (e >= a1) {
                         break;
                     }
-                    if (ids[cur] == id) {
-                        emit_link(rbuf, &s_cnt, links, cap, ctr, static_cast<uint32_t>(e0) + cur, static_cast<uint32_t>(e));
-                        break;
+                    const uint32_t id = id4[u];
+                    uint32_t s = slot_hash(id, shift);
+                    for (;;) {
+                        const uint32_t cur = tab[s];
+                        if (cur == SLOT_EMPTY) {
+                            break;
+                        }
+                        if (ids[cur] == id) {
+                            emit_link(rbuf, &s_cnt, links, cap, ctr, static_cast<uint32_t>(e0) + cur, static_cast<uint32_t>(e));
+                            break;
+                        }
+                        s = (s + 1) & mask;
                     }
-                    s = (s + 1) & mask;
                 }
             }
         }
