@@ -146,22 +146,41 @@ __global__ void __launch_bounds__(256) partition_kernel(const PartitionArgs a) {
                 s_cnt[threadIdx.x] = 0;
             }
             __syncthreads();
-            constexpr int PU = 8; // entries per thread in flight
-            for (uint32_t ib = 0; ib < n; ib += 256 * PU) {
-                uint32_t v[PU];
+            // eight consecutive entries per thread: one 16-byte load and one byte of the bitmap (an aligned
+            // window covers the locus; entries outside it are masked)
+            const uint64_t e1 = e0 + n, base = e0 & ~7ull;
+            const bool vec_ok = (reinterpret_cast<uintptr_t>(a.gid_base) & 15u) == 0;
+            for (uint64_t v0 = base + 8ull * threadIdx.x; v0 < e1; v0 += 8ull * 256) {
+                __align__(16) uint16_t gb[8];
+                if (vec_ok && v0 >= e0 && v0 + 8 <= e1) {
+                    *reinterpret_cast<uint4 *>(gb) = *reinterpret_cast<const uint4 *>(a.gid_base + v0);
+                } else {
 #pragma unroll
-                for (int u = 0; u < PU; ++u) {
-                    const uint32_t i = ib + 256 * u + threadIdx.x;
-                    v[u] = i < n ? classify(e0 + i) : CB_SKIP;
+                    for (int k = 0; k < 8; ++k) {
+                        gb[k] = (v0 + k >= e0 && v0 + k < e1) ? a.gid_base[v0 + k] : 0;
+                    }
                 }
+                const uint32_t special = (a.sp_bits[v0 >> 5] >> (v0 & 31)) & 0xFFu;
 #pragma unroll
-                for (int u = 0; u < PU; ++u) {
-                    const uint32_t i = ib + 256 * u + threadIdx.x;
-                    if (i < n) {
-                        s_v[i] = static_cast<uint16_t>(v[u]);
-                        if (v[u] != CB_SKIP) {
-                            s_rank[i] = static_cast<uint16_t>(atomicAdd(&s_cnt[__umulhi(v[u] >> 2, a.stripe_magic)], 1u));
+                for (int k = 0; k < 8; ++k) {
+                    const uint64_t e = v0 + k;
+                    if (e < e0 || e >= e1) {
+                        continue;
+                    }
+                    uint32_t v = CB_SKIP;
+                    if (!((special >> k) & 1u)) {
+                        const uint32_t gid = gb[k] >> 2;
+                        uint32_t cell;
+                        if (gid >= a.n_groups || (cell = s_map[gid]) == 0xFFFFu) {
+                            atomicExch(a.err, SGPU_E_CELL_RANGE);
+                        } else {
+                            v = (cell << 2) | (gb[k] & 3u);
                         }
+                    }
+                    const uint32_t i = static_cast<uint32_t>(e - e0);
+                    s_v[i] = static_cast<uint16_t>(v);
+                    if (v != CB_SKIP) {
+                        s_rank[i] = static_cast<uint16_t>(atomicAdd(&s_cnt[__umulhi(v >> 2, a.stripe_magic)], 1u));
                     }
                 }
             }
@@ -245,6 +264,7 @@ struct StageArgs {
     const uint16_t *cellbase;  // see partition_kernel
     const uint32_t *seg;
     const uint32_t *sp_code;   // special entries, ascending by entry (hence by locus)
+    const uint32_t *sp_locus;
     const uint32_t *sp_start;  // per locus: first special entry of the locus (n_loci + 1 values)
     uint32_t n_pad;
     uint32_t l0, nl;           // main k-blocks: loci [l0, l0 + nl), 32 per k-block
@@ -326,14 +346,14 @@ __global__ void __launch_bounds__(ST_THREADS, 4) stage_tile_kernel(const StageAr
     for (uint32_t j = threadIdx.x >> 5; j < 32; j += ST_THREADS / 32) {
         const uint32_t lane = threadIdx.x & 31;
         const uint64_t b1 = s_e1[j];
-        for (uint64_t eb = s_e0[j] + lane; eb < b1; eb += 128) {
-            uint32_t cb[4];
+        for (uint64_t eb = s_e0[j] + lane; eb < b1; eb += 256) {
+            uint32_t cb[8];
 #pragma unroll
-            for (int u = 0; u < 4; ++u) { // four loads in flight
+            for (int u = 0; u < 8; ++u) { // eight loads in flight: a whole locus segment in one round
                 cb[u] = eb + 32 * u < b1 ? a.cellbase[eb + 32 * u] : CB_SKIP;
             }
 #pragma unroll
-            for (int u = 0; u < 4; ++u) {
+            for (int u = 0; u < 8; ++u) {
                 const uint32_t r = (cb[u] >> 2) - c0;
                 if (cb[u] != CB_SKIP && r < nc) {
                     tile_add(tile, r, j, cb[u] & 3u);
@@ -343,16 +363,33 @@ __global__ void __launch_bounds__(ST_THREADS, 4) stage_tile_kernel(const StageAr
         }
     }
     // ---- surviving entries of reads with several entries
-    for (uint32_t j = 0; j < 32; ++j) {
-        for (uint32_t s = s_sp0[j] + threadIdx.x; s < s_sp1[j]; s += ST_THREADS) {
-            const uint32_t c = a.sp_code[s];
-            if (c == CODE_DROPPED || (tail && !code_tail(c))) {
-                continue;
+    if (!tail) {
+        // consecutive loci: their special entries are one contiguous range of the (ascending) list
+        const uint32_t l_first = s_loc[0];
+        if (l_first != 0xFFFFFFFFu) {
+            const uint32_t n_valid = min(32u, a.nl - kb * LOCI_PER_KB);
+            const uint32_t sp1 = s_sp1[n_valid - 1];
+            for (uint32_t s = s_sp0[0] + threadIdx.x; s < sp1; s += ST_THREADS) {
+                const uint32_t c = a.sp_code[s];
+                const uint32_t r = code_cell(c) - c0;
+                if (c != CODE_DROPPED && r < nc) {
+                    tile_add(tile, r, a.sp_locus[s] - l_first, code_base(c));
+                    ++n_added;
+                }
             }
-            const uint32_t r = code_cell(c) - c0;
-            if (r < nc) {
-                tile_add(tile, r, j, code_base(c));
-                ++n_added;
+        }
+    } else {
+        for (uint32_t j = 0; j < 32; ++j) {
+            for (uint32_t s = s_sp0[j] + threadIdx.x; s < s_sp1[j]; s += ST_THREADS) {
+                const uint32_t c = a.sp_code[s];
+                if (c == CODE_DROPPED || !code_tail(c)) {
+                    continue;
+                }
+                const uint32_t r = code_cell(c) - c0;
+                if (r < nc) {
+                    tile_add(tile, r, j, code_base(c));
+                    ++n_added;
+                }
             }
         }
     }
@@ -890,6 +927,7 @@ int sgpu_gemm_counts(sgpu_ctx *ctx, const sgpu_pileup *p, const LinkResult &lr, 
         sa.seg = seg.p;
         sa.n_pad = n_pad;
         sa.sp_code = lr.sp_code.p;
+        sa.sp_locus = lr.sp_locus.p;
         sa.sp_start = lr.sp_start.p;
         sa.l0 = static_cast<uint32_t>(l0);
         sa.nl = static_cast<uint32_t>(nl);
