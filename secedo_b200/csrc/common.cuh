@@ -32,7 +32,7 @@ struct sgpu_ctx {
     uint64_t n_syrk = 0;
     // gemm.cu: rasterised list of upper-triangle output tiles for tile_cache_cells cells (device memory)
     void *tile_cache = nullptr;
-    uint32_t tile_cache_n = 0, tile_cache_cells = 0;
+    uint32_t tile_cache_n = 0, tile_cache_cells = 0, tile_cache_bm = 0;
     // epilogue.cu: F / G coefficients of the last likelihood parameters, tile list of the last matrix size
     bool ft_valid = false;
     double ft_eps = 0, ft_h = 0, ft_theta = 0, ft_f10 = 0, ft_f01 = 0, ft_g2[3] = { 0, 0, 0 }, ft_g3[4] = { 0, 0, 0, 0 };

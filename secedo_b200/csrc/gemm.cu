@@ -757,26 +757,257 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) syrk_kernel(const __grid_cons
     }
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// the same GEMM on CTA pairs (tcgen05 cta_group::2): a cluster of two CTAs owns a 256 x 256 output tile,
+// each CTA 128 of its rows (its own TMEM) and HALF of the B operand (128 of the 256 columns' rows), which
+// the tensor cores of both SMs read across the pair. Per CTA and k-block that is 32 KB of operands
+// instead of 48 KB (6 pipeline stages instead of 4, a third less L2->SM traffic and shared-memory
+// bandwidth). Only the leader CTA issues MMAs; both CTAs' TMA loads report to the leader's barrier; the
+// leader's commits release the stage / publish the accumulators in both CTAs (multicast).
+// ------------------------------------------------------------------------------------------------
+constexpr int STAGES2 = 6;
+constexpr int HALF_B_BYTES = 128 * KB_BYTES;             // 16 KB
+constexpr int STAGE2_BYTES = A_BYTES + HALF_B_BYTES;     // 32 KB per CTA
+constexpr int SMEM2_BYTES = STAGES2 * STAGE2_BYTES + 1024 + 256;
+constexpr uint32_t IDESC2 = (2u << 4) | (1u << 7) | (1u << 10) | ((256u >> 3) << 17) | ((256u >> 4) << 24); // M = 256, N = 256
+
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t mapa_u32(uint32_t addr, uint32_t rank) { // same offset in CTA `rank` of the cluster
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+    return r;
+}
+__device__ __forceinline__ void mbar_arrive_remote(uint32_t cluster_addr) {
+    asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx_remote(uint32_t cluster_addr, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cluster.b64 _, [%0], %1;" ::"r"(cluster_addr), "r"(bytes)
+                 : "memory");
+}
+// TMA load of one CTA of a pair; the completion is reported to a barrier of the LEADER CTA
+__device__ __forceinline__ void tma_load_3d_2sm(uint32_t dst, const CUtensorMap *map, uint32_t leader_bar, int32_t c0, int32_t c1,
+                                                int32_t c2) {
+    asm volatile(
+            "cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(dst),
+            "l"(map), "r"(leader_bar), "r"(c0), "r"(c1), "r"(c2)
+            : "memory");
+}
+__device__ __forceinline__ void umma_i8_2sm(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t accumulate) {
+    asm volatile(
+            "{\n\t"
+            ".reg .pred p;\n\t"
+            "setp.ne.b32 p, %4, 0;\n\t"
+            "tcgen05.mma.cta_group::2.kind::i8 [%0], %1, %2, %3, p;\n\t"
+            "}" ::"r"(d_tmem),
+            "l"(a_desc), "l"(b_desc), "r"(IDESC2), "r"(accumulate)
+            : "memory");
+}
+__device__ __forceinline__ void umma_commit_2sm(uint32_t bar) { // arrives on `bar` in BOTH CTAs of the pair
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),
+                 "h"(static_cast<uint16_t>(3))
+                 : "memory");
+}
+
+// work item of a pair: tiles are (row block of 256, column block of 256)
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 1)
+        syrk2_kernel(const __grid_constant__ CUtensorMap map_u, const WorkList wl, int32_t *__restrict__ S, int32_t *__restrict__ D,
+                     uint32_t n_cells, int epi_mode) {
+    const uint32_t n_work = wl.n_work;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+    uint64_t *bars = reinterpret_cast<uint64_t *>(smem + STAGES2 * STAGE2_BYTES);
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 2 * STAGES2 + 2);
+    const uint32_t full0 = smem_u32(bars), empty0 = smem_u32(bars + STAGES2);
+    const uint32_t tmem_full = smem_u32(bars + 2 * STAGES2), tmem_empty = smem_u32(bars + 2 * STAGES2 + 1);
+    const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t rank = cluster_ctarank();
+    const uint32_t pair = blockIdx.x >> 1, n_pairs = gridDim.x >> 1;
+    const bool leader = rank == 0;
+
+    if (warp == 0 && lane == 0) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_u) : "memory");
+        for (int s = 0; s < STAGES2; ++s) {
+            mbar_init(full0 + 8 * s, 2);  // one arrive.expect_tx per CTA of the pair (only the leader's is used)
+            mbar_init(empty0 + 8 * s, 1); // the leader's commit, multicast
+        }
+        mbar_init(tmem_full, 1);          // the leader's commit, multicast
+        mbar_init(tmem_empty, 256);       // the epilogue threads of both CTAs (only the leader's is used)
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(TMEM_COLS));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    cluster_sync_all(); // barriers and TMEM of both CTAs exist before anything is sent across the pair
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_base = *tmem_slot;
+    const uint32_t tmem_Q = tmem_base, tmem_T = tmem_base + BN;
+
+    if (warp == 0) {
+        // ===== TMA producer (both CTAs): own 128 rows of A, own half of B =====
+        if (elect_one()) {
+            uint32_t stage = 0, phase = 0;
+            for (uint32_t w = pair; w < n_work; w += n_pairs) {
+                const WorkItem wi = work_item(wl, w);
+                for (uint32_t kb = wi.k0; kb < wi.k1; ++kb) {
+                    mbar_wait(empty0 + 8 * stage, phase ^ 1);
+                    const uint32_t sa = smem_u32(smem + stage * STAGE2_BYTES), sb = sa + A_BYTES;
+                    const uint32_t bar = mapa_u32(full0 + 8 * stage, 0); // the leader's barrier
+                    mbar_expect_tx_remote(bar, STAGE2_BYTES);
+                    const int32_t ch = static_cast<int32_t>(kb >> wl.ck_shift);
+                    const int32_t kx = static_cast<int32_t>((kb - (static_cast<uint32_t>(ch) << wl.ck_shift)) * KB_BYTES);
+                    const uint32_t kbb = kb >= wl.kb_neg0 ? kb + wl.kb_negd : kb;
+                    const int32_t chb = static_cast<int32_t>(kbb >> wl.ck_shift);
+                    const int32_t kxb = static_cast<int32_t>((kbb - (static_cast<uint32_t>(chb) << wl.ck_shift)) * KB_BYTES);
+                    tma_load_3d_2sm(sa, &map_u, bar, kx, wi.rb * 256 + rank * 128, ch);
+                    tma_load_3d_2sm(sb, &map_u, bar, kxb, wi.cb * 256 + rank * 128, chb);
+                    if (++stage == STAGES2) {
+                        stage = 0;
+                        phase ^= 1;
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===== MMA issuer (leader CTA only) =====
+        if (leader && elect_one()) {
+            uint32_t stage = 0, phase = 0, acc_phase = 0;
+            for (uint32_t w = pair; w < n_work; w += n_pairs) {
+                const WorkItem wi = work_item(wl, w);
+                mbar_wait(tmem_empty, acc_phase ^ 1); // both CTAs' epilogues have drained the accumulators
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                for (uint32_t kb = wi.k0; kb < wi.k1; ++kb) {
+                    mbar_wait(full0 + 8 * stage, phase);
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                    const uint32_t sa = smem_u32(smem + stage * STAGE2_BYTES), sb = sa + A_BYTES;
+                    const uint32_t first = kb == wi.k0 ? 0u : 1u;
+                    umma_i8_2sm(tmem_T, make_desc(sa), make_desc(sb), first);
+                    umma_i8_2sm(tmem_Q, make_desc(sa + 32), make_desc(sb + 32), first);
+                    umma_i8_2sm(tmem_Q, make_desc(sa + 64), make_desc(sb + 64), 1u);
+                    umma_i8_2sm(tmem_Q, make_desc(sa + 96), make_desc(sb + 96), 1u);
+                    umma_commit_2sm(empty0 + 8 * stage); // frees the slot in both CTAs once these MMAs retire
+                    if (++stage == STAGES2) {
+                        stage = 0;
+                        phase ^= 1;
+                    }
+                }
+                umma_commit_2sm(tmem_full); // accumulators complete, in both CTAs
+                acc_phase ^= 1;
+            }
+        }
+    } else {
+        // ===== epilogue (both CTAs): warps 2..5, TMEM lanes 32*(warp%4) .. +31 = this CTA's 128 rows =====
+        const uint32_t lane_base = 32 * (warp & 3);
+        const uint32_t leader_tmem_empty = mapa_u32(tmem_empty, 0);
+        uint32_t acc_phase = 0;
+        for (uint32_t w = pair; w < n_work; w += n_pairs) {
+            const WorkItem wi = work_item(wl, w);
+            mbar_wait(tmem_full, acc_phase);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const uint32_t row0 = wi.rb * 256 + rank * 128;
+            const uint32_t row = row0 + lane_base + lane;
+            int32_t *Srow = S + static_cast<uint64_t>(row) * n_cells;
+            int32_t *Drow = D + static_cast<uint64_t>(row) * n_cells;
+            // this CTA's 128 x 256 part lies strictly above the diagonal and inside the matrix
+            const bool interior = wi.cb * 256 >= row0 + 128 && wi.cb * 256 + 256 <= n_cells && row0 + 128 <= n_cells;
+            const bool vec = interior && !wi.partial && epi_mode != EPI_RED && (n_cells & 3u) == 0;
+#pragma unroll 1
+            for (uint32_t cc = 0; cc < 256 / 32; ++cc) {
+                uint32_t q[32], t[32];
+                tmem_ld32(tmem_Q + (lane_base << 16) + cc * 32, q);
+                tmem_ld32(tmem_T + (lane_base << 16) + cc * 32, t);
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                const uint32_t col0 = wi.cb * 256 + cc * 32;
+                if (vec) {
+                    int4 *ps = reinterpret_cast<int4 *>(Srow + col0), *pd = reinterpret_cast<int4 *>(Drow + col0);
+                    int4 os[8], od[8];
+                    if (epi_mode == EPI_RMW) {
+#pragma unroll
+                        for (int k = 0; k < 8; ++k) {
+                            os[k] = ps[k];
+                            od[k] = pd[k];
+                        }
+                    }
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) {
+                        int32_t sv[4], dv[4];
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) {
+                            const int32_t tv = static_cast<int32_t>(t[4 * k + e]);
+                            sv[e] = (static_cast<int32_t>(q[4 * k + e]) + tv) >> 2; // (4S - T + T) / 4
+                            dv[e] = tv - sv[e];
+                        }
+                        int4 vs = make_int4(sv[0], sv[1], sv[2], sv[3]);
+                        int4 vd = make_int4(dv[0], dv[1], dv[2], dv[3]);
+                        if (epi_mode == EPI_RMW) {
+                            vs.x += os[k].x, vs.y += os[k].y, vs.z += os[k].z, vs.w += os[k].w;
+                            vd.x += od[k].x, vd.y += od[k].y, vd.z += od[k].z, vd.w += od[k].w;
+                        }
+                        ps[k] = vs;
+                        pd[k] = vd;
+                    }
+                } else if (row < n_cells && col0 + 31 > row) {
+#pragma unroll
+                    for (int k = 0; k < 32; ++k) {
+                        const uint32_t col = col0 + k;
+                        const int32_t tv = static_cast<int32_t>(t[k]);
+                        const int32_t sv = (static_cast<int32_t>(q[k]) + tv) >> 2;
+                        const int32_t dv = tv - sv;
+                        if (col > row && col < n_cells) {
+                            if (sv) {
+                                atomicAdd(Srow + col, sv);
+                            }
+                            if (dv) {
+                                atomicAdd(Drow + col, dv);
+                            }
+                        }
+                    }
+                }
+            }
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            mbar_arrive_remote(leader_tmem_empty);
+            acc_phase ^= 1;
+        }
+    }
+    __syncthreads();
+    cluster_sync_all(); // nobody frees TMEM or exits while the other CTA may still be using the pair
+    if (warp == 1) {
+        asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TMEM_COLS));
+    }
+}
+
 } // namespace
 
 // Upper-triangle output tiles in an order that keeps the tiles in flight (one per SM) inside a block
 // of ~18 row blocks x 8 column blocks, so that a wave touches ~4 400 distinct operand rows instead of
 // ~20 000: bands of 8 column blocks, row-block-major inside a band.
-static int tile_list(sgpu_ctx *ctx, uint32_t N, uint32_t n_pad, const uint2 **d_tiles, uint32_t *n_tiles) {
-    if (ctx->tile_cache && ctx->tile_cache_cells == N) {
+static int tile_list(sgpu_ctx *ctx, uint32_t N, uint32_t n_pad, uint32_t bm /* tile height: 128, or 256 for CTA pairs */,
+                     const uint2 **d_tiles, uint32_t *n_tiles) {
+    if (ctx->tile_cache && ctx->tile_cache_cells == N && ctx->tile_cache_bm == bm) {
         *d_tiles = static_cast<const uint2 *>(ctx->tile_cache);
         *n_tiles = ctx->tile_cache_n;
         return SGPU_OK;
     }
     constexpr uint32_t BAND = 8;
     std::vector<uint2> tiles;
-    const uint32_t n_cb = n_pad / BN, n_rb = n_pad / BM;
+    const uint32_t n_cb = n_pad / BN, n_rb = n_pad / bm;
     for (uint32_t band = 0; band < n_cb; band += BAND) {
         const uint32_t cb_end = std::min(n_cb, band + BAND);
         for (uint32_t rb = 0; rb < n_rb; ++rb) {
             for (uint32_t cb = band; cb < cb_end; ++cb) {
                 // the tile intersects the upper triangle: its last column > its first row
-                if (cb * BN + BN - 1 > rb * BM && rb * BM < N && cb * BN < N) {
+                if (cb * BN + BN - 1 > rb * bm && rb * bm < N && cb * BN < N) {
                     tiles.push_back(make_uint2(rb, cb));
                 }
             }
@@ -790,6 +1021,7 @@ static int tile_list(sgpu_ctx *ctx, uint32_t N, uint32_t n_pad, const uint2 **d_
     SGPU_CUDA(ctx, cudaMalloc(&ctx->tile_cache, std::max<size_t>(1, tiles.size()) * sizeof(uint2)));
     SGPU_CUDA(ctx, cudaMemcpy(ctx->tile_cache, tiles.data(), tiles.size() * sizeof(uint2), cudaMemcpyHostToDevice));
     ctx->tile_cache_cells = N;
+    ctx->tile_cache_bm = bm;
     ctx->tile_cache_n = static_cast<uint32_t>(tiles.size());
     *d_tiles = static_cast<const uint2 *>(ctx->tile_cache);
     *n_tiles = ctx->tile_cache_n;
@@ -863,10 +1095,14 @@ int sgpu_gemm_counts(sgpu_ctx *ctx, const sgpu_pileup *p, const LinkResult &lr, 
             return sgpu_fail(ctx, SGPU_E_CUDA, "cuTensorMapEncodeTiled failed (%d)", static_cast<int>(r));
         }
     }
+    // CTA pairs (tcgen05 cta_group::2, 256 x 256 tiles) or single CTAs (128 x 256 tiles)
+    const char *env_pair = getenv("SECEDO_B200_GEMM_PAIRS");
+    const bool pairs = env_pair ? env_pair[0] == '1' : (ctx->sm_count % 2 == 0); // default; SECEDO_B200_GEMM_PAIRS=0 for single CTAs
     SGPU_CUDA(ctx, cudaFuncSetAttribute(syrk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+    SGPU_CUDA(ctx, cudaFuncSetAttribute(syrk2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM2_BYTES));
     const uint2 *d_tiles = nullptr;
     uint32_t n_tiles = 0;
-    SGPU_TRY(tile_list(ctx, N, n_pad, &d_tiles, &n_tiles));
+    SGPU_TRY(tile_list(ctx, N, n_pad, pairs ? 256 : BM, &d_tiles, &n_tiles));
     SGPU_TRACE(ctx, "gemm: tensor map + tiles");
 
     // CUDA events on the launching stream around the staging kernel and around the tcgen05 kernel
@@ -952,11 +1188,12 @@ int sgpu_gemm_counts(sgpu_ctx *ctx, const sgpu_pileup *p, const LinkResult &lr, 
         wl.kb_negd = kt;
         // whole tiles in full rounds of the grid; the rest (or everything, when there are few tiles) in
         // K ranges so that every SM has work in the last round
-        wl.n_full = n_tiles >= 2 * sms ? n_tiles / sms * sms : 0;
+        const uint32_t units = pairs ? sms / 2 : sms; // CTAs or CTA pairs that take work items
+        wl.n_full = n_tiles >= 2 * units ? n_tiles / units * units : 0;
         const uint32_t rest = n_tiles - wl.n_full;
         uint32_t splits = 1;
         if (rest) {
-            const uint32_t target = wl.n_full ? sms : 2 * sms;
+            const uint32_t target = wl.n_full ? units : 2 * units;
             splits = static_cast<uint32_t>(std::min<uint64_t>(wl.kbs, std::max<uint32_t>(1, target / rest)));
         }
         wl.per = (wl.kbs + splits - 1) / splits;
@@ -964,9 +1201,13 @@ int sgpu_gemm_counts(sgpu_ctx *ctx, const sgpu_pileup *p, const LinkResult &lr, 
         wl.n_work = wl.n_full + rest * wl.splits;
         // the planes are zero right after sgpu_counts_zero: the first panel stores, later ones add in place
         const int epi = c->fresh ? EPI_STORE : EPI_RMW;
-        const unsigned grid = static_cast<unsigned>(std::min<uint64_t>(wl.n_work, sms));
+        const unsigned grid = static_cast<unsigned>(std::min<uint64_t>(wl.n_work, units));
         mark(); // [3k+1] staging done, GEMM begins
-        SGPU_LAUNCH(ctx, (syrk_kernel<<<grid, GEMM_THREADS, SMEM_BYTES, st>>>(map, wl, c->i32 + PLANE_S * c->nn, c->i32 + PLANE_D * c->nn, N, 1, epi)));
+        if (pairs) {
+            SGPU_LAUNCH(ctx, (syrk2_kernel<<<2 * grid, GEMM_THREADS, SMEM2_BYTES, st>>>(map, wl, c->i32 + PLANE_S * c->nn, c->i32 + PLANE_D * c->nn, N, epi)));
+        } else {
+            SGPU_LAUNCH(ctx, (syrk_kernel<<<grid, GEMM_THREADS, SMEM_BYTES, st>>>(map, wl, c->i32 + PLANE_S * c->nn, c->i32 + PLANE_D * c->nn, N, 1, epi)));
+        }
         SGPU_CUDA(ctx, cudaGetLastError());
         c->fresh = false;
         mark(); // [3k+2] GEMM done
