@@ -9,6 +9,7 @@
 #include <map>
 #include <string>
 #include <unordered_map>
+#include <vector>
 
 #include "../../include/secedo_b200.h"
 
@@ -192,6 +193,7 @@ struct LinkResult {
     DevBuf<uint32_t> sp_head;   // per sid: sid of the first entry of the read
     DevBuf<uint32_t> sp_code;   // per sid: code, see above
     DevBuf<uint8_t> sp_drop;    // per sid: removed by the mate rule
+    DevBuf<uint32_t> sp_rcode;  // per head: cell << 4 | tail << 1 | multi of the READ (set even if the head entry is dropped)
     // per read with >= 2 entries, indexed by the sid of its first entry ("head")
     DevBuf<uint64_t> g_off;     // [n_special + 1] offsets into g_list / g_base (only heads own a range)
     DevBuf<uint32_t> g_list;    // stored loci, ascending (first g_nst[head] elements of the range)
@@ -210,6 +212,7 @@ struct LinkResult {
     // per locus / chromosome
     DevBuf<uint8_t> lchr;        // chromosome of every locus
     DevBuf<uint64_t> tail_locus; // per chromosome: reads created at loci >= this one have index >= K
+    std::vector<uint64_t> h_tail_locus; // host copy
     DevBuf<uint32_t> tail_loci;  // loci that can hold tail reads (from the cutoff locus to the chromosome end)
     uint64_t n_tail_loci = 0;
     DevBuf<uint32_t> gmap;       // group_id_to_pos on the device
@@ -236,6 +239,8 @@ int sgpu_link_reads(sgpu_ctx *ctx, const sgpu_pileup *p, uint32_t num_cells, uin
                     const uint32_t *h_group_id_to_pos, uint32_t n_groups, uint32_t num_threads,
                     LinkResult *out);
 int sgpu_link_dense_codes(sgpu_ctx *ctx, const sgpu_pileup *p, LinkResult *lr);
+// (re)build the compact candidate list of the multi-locus correction from the reads that keep >= min_nst loci
+int sgpu_link_candidates(sgpu_ctx *ctx, LinkResult *lr, uint32_t min_nst);
 
 // scatter.cu — first-order counts by pair enumeration; only_tail_pairs: enumerate just the pairs of
 // two tail reads (used with sign = -1 to correct the GEMM path)
@@ -243,7 +248,7 @@ int sgpu_scatter_pairs(sgpu_ctx *ctx, const sgpu_pileup *p, const LinkResult &lr
                        int sign, bool only_tail_pairs, uint64_t *n_pairs);
 
 // multilocus.cu
-int sgpu_multilocus(sgpu_ctx *ctx, const sgpu_pileup *p, const LinkResult &lr, sgpu_counts *c,
+int sgpu_multilocus(sgpu_ctx *ctx, const sgpu_pileup *p, LinkResult &lr, sgpu_counts *c,
                     uint32_t L, uint64_t *n_pairs_multi);
 
 // epilogue.cu
@@ -259,6 +264,20 @@ int sgpu_build_gtable(sgpu_ctx *ctx, double eps, double h, double theta, uint32_
                       double *d_G /* device, SGPU_MAX_CLASS^2 */, double *d_F /* device, optional */);
 
 // gemm.cu — int8 tcgen05 path
+struct GemmInput {
+    const uint64_t *row_ptr;   // CSR over n_loci loci
+    const uint16_t *gid_base;  // group << 2 | letter per entry
+    uint64_t n_loci, n_main;   // loci [0, n_main) are counted; loci >= n_main only through tail_loci
+    uint64_t n_entries;
+    const uint32_t *sp_bits;   // entries to leave out (staged from the special list instead)
+    const uint32_t *gmap;      // group -> cell
+    uint32_t n_groups;
+    const uint32_t *sp_code, *sp_locus, *sp_start; // special entries (may be empty: n_special = 0, sp_start all zero)
+    uint64_t n_special;
+    const uint32_t *tail_loci; // loci whose entries are subtracted as Z Z^T (ascending)
+    uint64_t n_tail_loci;
+};
+int sgpu_gemm_run(sgpu_ctx *ctx, const GemmInput &in, uint32_t num_cells, int32_t *S_plane, int32_t *D_plane, bool *fresh);
 int sgpu_gemm_counts(sgpu_ctx *ctx, const sgpu_pileup *p, const LinkResult &lr, sgpu_counts *c,
                      uint64_t *n_pairs);
 

@@ -1029,21 +1029,42 @@ static int tile_list(sgpu_ctx *ctx, uint32_t N, uint32_t n_pad, uint32_t bm /* t
 }
 
 int sgpu_gemm_counts(sgpu_ctx *ctx, const sgpu_pileup *p, const LinkResult &lr, sgpu_counts *c, uint64_t *n_pairs) {
-    cudaStream_t st = ctx->stream;
     if (n_pairs) {
         *n_pairs = 0; // not enumerated on this path
     }
-    const uint64_t P = p->n_loci;
-    if (P == 0 || p->n_entries == 0 || c->n < 2) {
+    GemmInput in;
+    in.row_ptr = p->d_row_ptr;
+    in.gid_base = p->d_gid_base;
+    in.n_loci = p->n_loci;
+    in.n_main = p->n_loci;
+    in.n_entries = p->n_entries;
+    in.sp_bits = lr.sp_bits.p;
+    in.gmap = lr.gmap.p;
+    in.n_groups = lr.n_groups;
+    in.sp_code = lr.sp_code.p;
+    in.sp_locus = lr.sp_locus.p;
+    in.sp_start = lr.sp_start.p;
+    in.n_special = lr.n_special;
+    in.tail_loci = lr.tail_loci.p;
+    in.n_tail_loci = lr.n_tail_loci;
+    return sgpu_gemm_run(ctx, in, c->n, c->i32 + PLANE_S * c->nn, c->i32 + PLANE_D * c->nn, &c->fresh);
+}
+
+// The GEMM path on any CSR of (cell group, letter) entries: loci [0, n_main) are counted, the loci listed
+// in tail_loci are subtracted as Z Z^T. Used for the pileup itself and for the derived pileup of locus
+// pairs of the second-order correction (multilocus.cu).
+int sgpu_gemm_run(sgpu_ctx *ctx, const GemmInput &in, uint32_t N, int32_t *S_plane, int32_t *D_plane, bool *fresh) {
+    cudaStream_t st = ctx->stream;
+    const uint64_t P = in.n_main;
+    if (P == 0 || in.n_entries == 0 || N < 2) {
         return SGPU_OK;
     }
-    const uint32_t N = c->n;
     if (N > 16383) { // (cell << 2 | base) must fit 16 bits; the reference's PosData holds 14-bit group ids
         return sgpu_fail(ctx, SGPU_E_ARG, "the GEMM path supports at most 16383 cells");
     }
     const uint32_t n_pad = (N + BN - 1) / BN * BN;
     // the tail k-blocks (Z and -Z) ride along with the first panel
-    const uint32_t kbs_tail = static_cast<uint32_t>((lr.n_tail_loci + LOCI_PER_KB - 1) / LOCI_PER_KB);
+    const uint32_t kbs_tail = static_cast<uint32_t>((in.n_tail_loci + LOCI_PER_KB - 1) / LOCI_PER_KB);
     // panel: at most ~2 GB of Hadamard planes
     uint64_t panel = (1ull << 31) / (4ull * n_pad) / LOCI_PER_KB * LOCI_PER_KB;
     if (const char *env = getenv("SECEDO_B200_PANEL_LOCI")) { // tests: force several panels on small inputs
@@ -1124,26 +1145,26 @@ int sgpu_gemm_counts(sgpu_ctx *ctx, const sgpu_pileup *p, const LinkResult &lr, 
     // inside every locus, once per call
     DevBuf<uint16_t> cellbase;
     DevBuf<uint32_t> seg;
-    const uint64_t E = p->n_entries;
+    const uint64_t E = in.n_entries;
     SGPU_CUDA(ctx, cellbase.alloc(E + 8, ctx));
-    SGPU_CUDA(ctx, seg.alloc(P * (n_stripes + 1), ctx));
+    SGPU_CUDA(ctx, seg.alloc(in.n_loci * (n_stripes + 1), ctx));
     mark(); // folded into the first panel's staging time
     {
         PartitionArgs pa;
-        pa.row_ptr = p->d_row_ptr;
-        pa.gid_base = p->d_gid_base;
-        pa.sp_bits = lr.sp_bits.p;
-        pa.gmap = lr.gmap.p;
-        pa.n_groups = lr.n_groups;
+        pa.row_ptr = in.row_ptr;
+        pa.gid_base = in.gid_base;
+        pa.sp_bits = in.sp_bits;
+        pa.gmap = in.gmap;
+        pa.n_groups = in.n_groups;
         pa.n_cells = N;
-        pa.n_loci = P;
+        pa.n_loci = in.n_loci;
         pa.n_stripes = n_stripes;
         pa.stripe_magic = static_cast<uint32_t>(((1ull << 32) + cells_per_cta - 1) / cells_per_cta);
         pa.cellbase = cellbase.p;
         pa.seg = seg.p;
         pa.err = d_err.p;
-        const unsigned grid = static_cast<unsigned>(std::min<uint64_t>(P, static_cast<uint64_t>(sms) * 16));
-        const size_t psmem = (3 * static_cast<size_t>(PART_CACHE) + lr.n_groups) * sizeof(uint16_t);
+        const unsigned grid = static_cast<unsigned>(std::min<uint64_t>(in.n_loci, static_cast<uint64_t>(sms) * 16));
+        const size_t psmem = (3 * static_cast<size_t>(PART_CACHE) + in.n_groups) * sizeof(uint16_t);
         SGPU_CUDA(ctx, cudaFuncSetAttribute(partition_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(psmem)));
         SGPU_LAUNCH(ctx, (partition_kernel<<<grid, 256, psmem, st>>>(pa)));
     }
@@ -1158,18 +1179,18 @@ int sgpu_gemm_counts(sgpu_ctx *ctx, const sgpu_pileup *p, const LinkResult &lr, 
             mark(); // [3k] staging begins
         }
         StageArgs sa;
-        sa.row_ptr = p->d_row_ptr;
+        sa.row_ptr = in.row_ptr;
         sa.cellbase = cellbase.p;
         sa.seg = seg.p;
         sa.n_pad = n_pad;
-        sa.sp_code = lr.sp_code.p;
-        sa.sp_locus = lr.sp_locus.p;
-        sa.sp_start = lr.sp_start.p;
+        sa.sp_code = in.sp_code;
+        sa.sp_locus = in.sp_locus;
+        sa.sp_start = in.sp_start;
         sa.l0 = static_cast<uint32_t>(l0);
         sa.nl = static_cast<uint32_t>(nl);
         sa.kbs_main = kbs_main;
-        sa.tail_loci = lr.tail_loci.p;
-        sa.n_tail = kt ? static_cast<uint32_t>(lr.n_tail_loci) : 0;
+        sa.tail_loci = in.tail_loci;
+        sa.n_tail = kt ? static_cast<uint32_t>(in.n_tail_loci) : 0;
         sa.kbs_tail = kt;
         sa.cells_per_cta = cells_per_cta;
         sa.n_stripes = n_stripes;
@@ -1200,16 +1221,16 @@ int sgpu_gemm_counts(sgpu_ctx *ctx, const sgpu_pileup *p, const LinkResult &lr, 
         wl.splits = (wl.kbs + wl.per - 1) / wl.per; // no empty range
         wl.n_work = wl.n_full + rest * wl.splits;
         // the planes are zero right after sgpu_counts_zero: the first panel stores, later ones add in place
-        const int epi = c->fresh ? EPI_STORE : EPI_RMW;
+        const int epi = *fresh ? EPI_STORE : EPI_RMW;
         const unsigned grid = static_cast<unsigned>(std::min<uint64_t>(wl.n_work, units));
         mark(); // [3k+1] staging done, GEMM begins
         if (pairs) {
-            SGPU_LAUNCH(ctx, (syrk2_kernel<<<2 * grid, GEMM_THREADS, SMEM2_BYTES, st>>>(map, wl, c->i32 + PLANE_S * c->nn, c->i32 + PLANE_D * c->nn, N, epi)));
+            SGPU_LAUNCH(ctx, (syrk2_kernel<<<2 * grid, GEMM_THREADS, SMEM2_BYTES, st>>>(map, wl, S_plane, D_plane, N, epi)));
         } else {
-            SGPU_LAUNCH(ctx, (syrk_kernel<<<grid, GEMM_THREADS, SMEM_BYTES, st>>>(map, wl, c->i32 + PLANE_S * c->nn, c->i32 + PLANE_D * c->nn, N, 1, epi)));
+            SGPU_LAUNCH(ctx, (syrk_kernel<<<grid, GEMM_THREADS, SMEM_BYTES, st>>>(map, wl, S_plane, D_plane, N, 1, epi)));
         }
         SGPU_CUDA(ctx, cudaGetLastError());
-        c->fresh = false;
+        *fresh = false;
         mark(); // [3k+2] GEMM done
         ++ctx->n_syrk;
         first = false;

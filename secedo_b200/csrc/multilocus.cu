@@ -17,6 +17,9 @@
 #include "common.cuh"
 
 #include <algorithm>
+#include <cstdlib>
+#include <cstring>
+#include <vector>
 
 namespace {
 
@@ -41,6 +44,9 @@ struct MultiArgs {
     uint64_t nn;
     uint32_t L;
     int spill_only;           // second pass: record only the classes with x_s + x_d >= 4
+    uint32_t min_order;       // 2: every multi-locus pair is enumerated here; 3: the pairs of order 2 come from
+                              // the second-order GEMM, which counts every pair of order >= 3 C(x_s,2) / x_s x_d /
+                              // C(x_d,2) times too much in the (2,0) / (1,1) / (0,2) planes: taken back here
     unsigned int *max_order;
     unsigned long long *n_pairs;
     int *err;
@@ -108,6 +114,9 @@ __global__ void __launch_bounds__(TB) multilocus_kernel(MultiArgs a) {
                 continue;
             }
             a.g_base[ap] == a.g_base[bp] ? ++xs : ++xd; // this locus
+            if (xs + xd < a.min_order) {
+                continue;
+            }
             if (xs >= SGPU_MAX_CLASS || xd >= SGPU_MAX_CLASS || xs >= a.L || xd >= a.L) {
                 atomicExch(a.err, SGPU_E_CLASS_RANGE);
                 continue;
@@ -117,6 +126,21 @@ __global__ void __launch_bounds__(TB) multilocus_kernel(MultiArgs a) {
             const uint64_t ij = static_cast<uint64_t>(lo) * a.n_cells + hi;
             if (!a.spill_only) {
                 ++local_pairs;
+                if (a.min_order > 2) {
+                    const int c20 = static_cast<int>(xs * (xs - 1) / 2), c11 = static_cast<int>(xs * xd), c02 = static_cast<int>(xd * (xd - 1) / 2);
+                    if (c20) {
+                        atomicAdd(&a.H2[0 * a.nn + ij], -c20);
+                        atomicAdd(&a.hist[2 * SGPU_MAX_CLASS + 0], static_cast<unsigned long long>(-static_cast<long long>(c20)));
+                    }
+                    if (c11) {
+                        atomicAdd(&a.H2[1 * a.nn + ij], -c11);
+                        atomicAdd(&a.hist[1 * SGPU_MAX_CLASS + 1], static_cast<unsigned long long>(-static_cast<long long>(c11)));
+                    }
+                    if (c02) {
+                        atomicAdd(&a.H2[2 * a.nn + ij], -c02);
+                        atomicAdd(&a.hist[0 * SGPU_MAX_CLASS + 2], static_cast<unsigned long long>(-static_cast<long long>(c02)));
+                    }
+                }
                 atomicAdd(&s_hist[xs * SGPU_MAX_CLASS + xd], 1u);
                 if (order == 2) {
                     atomicAdd(&a.H2[static_cast<uint64_t>(xd) * a.nn + ij], 1);
@@ -151,11 +175,316 @@ __global__ void __launch_bounds__(TB) multilocus_kernel(MultiArgs a) {
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Second order as a GEMM. When many reads cover two loci (real data: ~16 % of the
+// reads), enumerating the read pairs that share both costs one atomic per pair — hundreds of ms at
+// 8 000 cells. The number of read pairs of cells (i, j) that cover a given PAIR of loci with a given base
+// pattern is again a sum of outer products, so the first-order machinery (stripe partition, tile staging,
+// tcgen05 GEMM) is reused on a derived pileup whose "loci" are locus pairs:
+//   run A: 4 pseudo-loci per locus pair (l1, l2), one per base b1 at l1, holding the reads that cover both
+//          with that b1, letter = base at l2:        same-letter count S_A = H20 (same at both loci),
+//                                                    all-pairs count  T_A = P_s* (same at l1)
+//   run B: 1 pseudo-locus per locus pair, letter = base at l2:  S_B = P_*s (same at l2), T_B = P_** (all)
+// and with D = T - S of either run
+//   N(2,0) += S_A        N(1,1) += D_A + S_B - S_A        N(0,2) += D_B - D_A.
+// These are SUBSET counts (every pair of order >= 3 is seen at each of its locus pairs); the enumeration
+// kernel, restricted to reads with >= 3 loci, records those pairs and takes the surplus back. Pairs of two
+// tail reads are removed by the Z Z^T k-blocks of the GEMM path (pseudo-loci that hold only tail reads).
+// ------------------------------------------------------------------------------------------------
+struct PairArgs {
+    uint64_t n_special;
+    const uint32_t *sp_head;
+    const uint32_t *sp_rcode; // per head: cell << 4 | tail << 1 | multi
+    const uint64_t *g_off;
+    const uint32_t *g_list;   // stored loci
+    const uint8_t *g_base;
+    const uint32_t *g_nst;
+    unsigned long long *occ;  // per locus l1: bit d set = some read covers (l1, l1 + d + 1)
+    const uint64_t *pair_base; // per locus: number of locus pairs before it (scan of popc(occ))
+    uint64_t n_pairs;         // locus pairs
+    // tail pairs: per chromosome the pair ids [z_first[c], z_first[c] + z_count[c]) get tail-only pseudo-loci z_off[c] ...
+    const uint8_t *lchr;
+    const uint64_t *z_first, *z_off;
+    const uint32_t *z_count;
+    uint64_t n_z;
+    uint32_t *cntA, *cntB;     // entries per pseudo-locus
+    const uint64_t *rowA, *rowB;
+    uint16_t *gbA, *gbB;       // cell << 2 | letter
+    int *err;
+};
+
+__device__ __forceinline__ bool pair_head(const PairArgs &a, uint64_t h) {
+    return h < a.n_special && a.sp_head[h] == h && a.g_nst[h] >= 2;
+}
+
+__global__ void __launch_bounds__(TB) pair_occ_kernel(PairArgs a) {
+    const uint64_t h = static_cast<uint64_t>(blockIdx.x) * TB + threadIdx.x;
+    if (!pair_head(a, h)) {
+        return;
+    }
+    const uint64_t o = a.g_off[h];
+    const uint32_t n = a.g_nst[h];
+    for (uint32_t p = 0; p + 1 < n; ++p) {
+        for (uint32_t q = p + 1; q < n; ++q) {
+            const uint32_t d = a.g_list[o + q] - a.g_list[o + p] - 1;
+            if (d >= 64) {
+                atomicExch(a.err, 1); // loci of one read more than 64 apart: the caller falls back to enumeration
+                return;
+            }
+            atomicOr(&a.occ[a.g_list[o + p]], 1ull << d);
+        }
+    }
+}
+
+__global__ void __launch_bounds__(TB) pair_popc_kernel(const unsigned long long *__restrict__ occ, uint64_t n_loci,
+                                                       uint32_t *__restrict__ pc) {
+    const uint64_t l = static_cast<uint64_t>(blockIdx.x) * TB + threadIdx.x;
+    if (l < n_loci) {
+        pc[l] = __popcll(occ[l]);
+    }
+}
+
+// FILL = false: count the entries of every pseudo-locus; FILL = true: write them
+template <bool FILL>
+__global__ void __launch_bounds__(TB) pair_emit_kernel(PairArgs a) {
+    const uint64_t h = static_cast<uint64_t>(blockIdx.x) * TB + threadIdx.x;
+    if (!pair_head(a, h)) {
+        return;
+    }
+    const uint64_t o = a.g_off[h];
+    const uint32_t n = a.g_nst[h];
+    const uint32_t rc = a.sp_rcode[h];
+    const uint32_t cell = rc >> 4;
+    const bool tail = (rc >> 1) & 1u;
+    for (uint32_t p = 0; p + 1 < n; ++p) {
+        const uint32_t l1 = a.g_list[o + p], b1 = a.g_base[o + p];
+        const unsigned long long occ = a.occ[l1];
+        for (uint32_t q = p + 1; q < n; ++q) {
+            const uint32_t d = a.g_list[o + q] - l1 - 1, b2 = a.g_base[o + q];
+            const uint64_t pid = a.pair_base[l1] + __popcll(occ & ((1ull << d) - 1ull));
+            uint64_t plA[2] = { pid * 4 + b1, 0 }, plB[2] = { pid, 0 };
+            int n_out = 1;
+            if (tail) { // a tail read: all its loci lie behind the cutoff of its chromosome
+                const uint32_t c = a.lchr[l1];
+                const uint64_t z = a.z_off[c] + (pid - a.z_first[c]);
+                plA[1] = a.n_pairs * 4 + z * 4 + b1;
+                plB[1] = a.n_pairs + z;
+                n_out = 2;
+            }
+            for (int k = 0; k < n_out; ++k) {
+                const uint32_t ka = atomicAdd(&a.cntA[plA[k]], 1u), kb = atomicAdd(&a.cntB[plB[k]], 1u);
+                if (FILL) {
+                    a.gbA[a.rowA[plA[k]] + ka] = static_cast<uint16_t>((cell << 2) | b2);
+                    a.gbB[a.rowB[plB[k]] + kb] = static_cast<uint16_t>((cell << 2) | b2);
+                }
+            }
+        }
+    }
+}
+
+// one of the two combinations above, elementwise over the upper triangle; sums of the increments per plane
+// go to the class histogram (the classes of order 2 are not enumerated on this path)
+__global__ void __launch_bounds__(TB) pair_combine_kernel(const int32_t *__restrict__ S, const int32_t *__restrict__ D,
+                                                          int32_t *__restrict__ H2, uint32_t n, uint64_t nn, int run_b,
+                                                          unsigned long long *__restrict__ hist) {
+    const uint64_t idx = static_cast<uint64_t>(blockIdx.x) * TB + threadIdx.x;
+    long long d20 = 0, d11 = 0, d02 = 0;
+    if (idx < nn) {
+        const uint32_t i = static_cast<uint32_t>(idx / n), j = static_cast<uint32_t>(idx - static_cast<uint64_t>(i) * n);
+        if (i < j) {
+            const int32_t s = S[idx], d = D[idx];
+            if (!run_b) {
+                d20 = s;
+                d11 = d - s;
+                d02 = -d;
+            } else {
+                d11 = s;
+                d02 = d;
+            }
+            if (d20) {
+                H2[0 * nn + idx] += static_cast<int32_t>(d20);
+            }
+            if (d11) {
+                H2[1 * nn + idx] += static_cast<int32_t>(d11);
+            }
+            if (d02) {
+                H2[2 * nn + idx] += static_cast<int32_t>(d02);
+            }
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        d20 += __shfl_xor_sync(0xffffffffu, d20, o);
+        d11 += __shfl_xor_sync(0xffffffffu, d11, o);
+        d02 += __shfl_xor_sync(0xffffffffu, d02, o);
+    }
+    if ((threadIdx.x & 31) == 0) {
+        if (d20) {
+            atomicAdd(&hist[2 * SGPU_MAX_CLASS + 0], static_cast<unsigned long long>(d20));
+        }
+        if (d11) {
+            atomicAdd(&hist[1 * SGPU_MAX_CLASS + 1], static_cast<unsigned long long>(d11));
+        }
+        if (d02) {
+            atomicAdd(&hist[0 * SGPU_MAX_CLASS + 2], static_cast<unsigned long long>(d02));
+        }
+    }
+}
+
+__global__ void __launch_bounds__(TB) iota_u32_kernel(uint32_t *__restrict__ a, uint32_t n, uint32_t first) {
+    const uint32_t i = blockIdx.x * TB + threadIdx.x;
+    if (i < n) {
+        a[i] = first + i;
+    }
+}
+
 unsigned blocks_for(uint64_t n) { return static_cast<unsigned>(ceil_div_u64(n ? n : 1, TB)); }
 
 } // namespace
 
-int sgpu_multilocus(sgpu_ctx *ctx, const sgpu_pileup *p, const LinkResult &lr, sgpu_counts *c,
+// second order through the GEMM path; returns 1 if the input does not fit the scheme (fall back to enumeration)
+static int second_order_gemm(sgpu_ctx *ctx, const sgpu_pileup *p, LinkResult &lr, sgpu_counts *c, long long *class2_pairs) {
+    cudaStream_t st = ctx->stream;
+    const uint64_t NS = lr.n_special, P = p->n_loci, nn = c->nn;
+    const uint32_t N = c->n, n_chr = p->n_chr;
+    *class2_pairs = 0;
+    DevBuf<unsigned long long> occ;
+    DevBuf<uint32_t> pc;
+    DevBuf<uint64_t> pair_base;
+    DevBuf<int> d_err;
+    SGPU_CUDA(ctx, occ.alloc(P, ctx));
+    SGPU_CUDA(ctx, pc.alloc(P, ctx));
+    SGPU_CUDA(ctx, pair_base.alloc(P + 1, ctx));
+    SGPU_CUDA(ctx, d_err.alloc(1, ctx));
+    SGPU_CUDA(ctx, cudaMemsetAsync(occ.p, 0, P * sizeof(unsigned long long), st));
+    SGPU_CUDA(ctx, cudaMemsetAsync(d_err.p, 0, sizeof(int), st));
+    PairArgs a;
+    memset(&a, 0, sizeof(a));
+    a.n_special = NS;
+    a.sp_head = lr.sp_head.p;
+    a.sp_rcode = lr.sp_rcode.p;
+    a.g_off = lr.g_off.p;
+    a.g_list = lr.g_list.p;
+    a.g_base = lr.g_base.p;
+    a.g_nst = lr.g_nst.p;
+    a.occ = occ.p;
+    a.lchr = lr.lchr.p;
+    a.err = d_err.p;
+    SGPU_LAUNCH(ctx, (pair_occ_kernel<<<blocks_for(NS), TB, 0, st>>>(a)));
+    SGPU_LAUNCH(ctx, (pair_popc_kernel<<<blocks_for(P), TB, 0, st>>>(occ.p, P, pc.p)));
+    SGPU_TRY(sgpu_scan_u32_u64(ctx, pc.p, pair_base.p, P));
+    // locus pairs in total and in front of the cutoff locus / the end of every chromosome
+    std::vector<uint64_t> h_first(n_chr), h_last(n_chr), h_zoff(n_chr + 1, 0);
+    std::vector<uint32_t> h_zcnt(n_chr);
+    SGPU_CUDA(ctx, cudaMemcpyAsync(&ctx->h_scratch[0], pair_base.p + P, sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
+    SGPU_CUDA(ctx, cudaMemcpyAsync(&ctx->h_scratch[1], d_err.p, sizeof(int), cudaMemcpyDeviceToHost, st));
+    for (uint32_t ch = 0; ch < n_chr; ++ch) {
+        SGPU_CUDA(ctx, cudaMemcpyAsync(&h_first[ch], pair_base.p + lr.h_tail_locus[ch], sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
+        SGPU_CUDA(ctx, cudaMemcpyAsync(&h_last[ch], pair_base.p + p->h_chr_ptr[ch + 1], sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
+    }
+    SGPU_CUDA(ctx, cudaStreamSynchronize(st));
+    if (static_cast<int>(ctx->h_scratch[1] & 0xFFFFFFFFu) != 0) {
+        return 1;
+    }
+    const uint64_t NP = ctx->h_scratch[0];
+    if (NP == 0) {
+        return SGPU_OK;
+    }
+    for (uint32_t ch = 0; ch < n_chr; ++ch) {
+        h_zcnt[ch] = static_cast<uint32_t>(h_last[ch] - h_first[ch]);
+        h_zoff[ch + 1] = h_zoff[ch] + h_zcnt[ch];
+    }
+    const uint64_t NZ = h_zoff[n_chr];
+    const uint64_t RA = 4 * (NP + NZ), RB = NP + NZ;
+    if (RA >= 0x7FFFFFF0ull) {
+        return 1;
+    }
+    DevBuf<uint64_t> z_first, z_off, rowA, rowB;
+    DevBuf<uint32_t> z_count, cntA, cntB;
+    SGPU_CUDA(ctx, z_first.alloc(n_chr, ctx));
+    SGPU_CUDA(ctx, z_off.alloc(n_chr + 1, ctx));
+    SGPU_CUDA(ctx, z_count.alloc(n_chr, ctx));
+    SGPU_CUDA(ctx, cntA.alloc(RA, ctx));
+    SGPU_CUDA(ctx, cntB.alloc(RB, ctx));
+    SGPU_CUDA(ctx, rowA.alloc(RA + 1, ctx));
+    SGPU_CUDA(ctx, rowB.alloc(RB + 1, ctx));
+    SGPU_CUDA(ctx, cudaMemcpyAsync(z_first.p, h_first.data(), n_chr * sizeof(uint64_t), cudaMemcpyHostToDevice, st));
+    SGPU_CUDA(ctx, cudaMemcpyAsync(z_off.p, h_zoff.data(), (n_chr + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, st));
+    SGPU_CUDA(ctx, cudaMemcpyAsync(z_count.p, h_zcnt.data(), n_chr * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
+    SGPU_CUDA(ctx, cudaMemsetAsync(cntA.p, 0, RA * sizeof(uint32_t), st));
+    SGPU_CUDA(ctx, cudaMemsetAsync(cntB.p, 0, RB * sizeof(uint32_t), st));
+    a.pair_base = pair_base.p;
+    a.n_pairs = NP;
+    a.z_first = z_first.p;
+    a.z_off = z_off.p;
+    a.z_count = z_count.p;
+    a.n_z = NZ;
+    a.cntA = cntA.p;
+    a.cntB = cntB.p;
+    SGPU_LAUNCH(ctx, (pair_emit_kernel<false><<<blocks_for(NS), TB, 0, st>>>(a)));
+    SGPU_TRY(sgpu_scan_u32_u64(ctx, cntA.p, rowA.p, RA));
+    SGPU_TRY(sgpu_scan_u32_u64(ctx, cntB.p, rowB.p, RB));
+    SGPU_CUDA(ctx, cudaMemcpyAsync(&ctx->h_scratch[0], rowA.p + RA, sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
+    SGPU_CUDA(ctx, cudaStreamSynchronize(st)); // also: the host vectors above have been copied
+    const uint64_t EA = ctx->h_scratch[0]; // = entries of run B as well
+    if (EA >= 0x7FFFFFF0ull) {
+        return 1;
+    }
+    DevBuf<uint16_t> gbA, gbB;
+    DevBuf<uint32_t> zero_bits, zero_start, ident, tailA, tailB;
+    DevBuf<int32_t> tmp;
+    SGPU_CUDA(ctx, gbA.alloc(EA + 8, ctx));
+    SGPU_CUDA(ctx, gbB.alloc(EA + 8, ctx));
+    SGPU_CUDA(ctx, zero_bits.alloc(EA / 32 + 2, ctx));
+    SGPU_CUDA(ctx, zero_start.alloc(RA + 2, ctx));
+    SGPU_CUDA(ctx, ident.alloc(N, ctx));
+    SGPU_CUDA(ctx, tailA.alloc(4 * NZ + 1, ctx));
+    SGPU_CUDA(ctx, tailB.alloc(NZ + 1, ctx));
+    SGPU_CUDA(ctx, tmp.alloc(2 * nn, ctx));
+    SGPU_CUDA(ctx, cudaMemsetAsync(cntA.p, 0, RA * sizeof(uint32_t), st));
+    SGPU_CUDA(ctx, cudaMemsetAsync(cntB.p, 0, RB * sizeof(uint32_t), st));
+    SGPU_CUDA(ctx, cudaMemsetAsync(zero_bits.p, 0, (EA / 32 + 2) * sizeof(uint32_t), st));
+    SGPU_CUDA(ctx, cudaMemsetAsync(zero_start.p, 0, (RA + 2) * sizeof(uint32_t), st));
+    a.rowA = rowA.p;
+    a.rowB = rowB.p;
+    a.gbA = gbA.p;
+    a.gbB = gbB.p;
+    SGPU_LAUNCH(ctx, (pair_emit_kernel<true><<<blocks_for(NS), TB, 0, st>>>(a)));
+    SGPU_LAUNCH(ctx, (iota_u32_kernel<<<blocks_for(N), TB, 0, st>>>(ident.p, N, 0)));
+    if (NZ) {
+        SGPU_LAUNCH(ctx, (iota_u32_kernel<<<blocks_for(4 * NZ), TB, 0, st>>>(tailA.p, static_cast<uint32_t>(4 * NZ), static_cast<uint32_t>(4 * NP))));
+        SGPU_LAUNCH(ctx, (iota_u32_kernel<<<blocks_for(NZ), TB, 0, st>>>(tailB.p, static_cast<uint32_t>(NZ), static_cast<uint32_t>(NP))));
+    }
+    SGPU_CUDA(ctx, cudaGetLastError());
+    for (int run = 0; run < 2; ++run) {
+        GemmInput in;
+        in.row_ptr = run ? rowB.p : rowA.p;
+        in.gid_base = run ? gbB.p : gbA.p;
+        in.n_loci = run ? RB : RA;
+        in.n_main = run ? NP : 4 * NP;
+        in.n_entries = EA;
+        in.sp_bits = zero_bits.p;
+        in.gmap = ident.p;
+        in.n_groups = N;
+        in.sp_code = nullptr;
+        in.sp_locus = nullptr;
+        in.sp_start = zero_start.p;
+        in.n_special = 0;
+        in.tail_loci = run ? tailB.p : tailA.p;
+        in.n_tail_loci = run ? NZ : 4 * NZ;
+        SGPU_CUDA(ctx, cudaMemsetAsync(tmp.p, 0, 2 * nn * sizeof(int32_t), st));
+        bool fresh = true;
+        SGPU_TRY(sgpu_gemm_run(ctx, in, N, tmp.p, tmp.p + nn, &fresh));
+        SGPU_LAUNCH(ctx, (pair_combine_kernel<<<blocks_for(nn), TB, 0, st>>>(tmp.p, tmp.p + nn, c->i32 + PLANE_H2 * nn, N, nn, run,
+                                                                          reinterpret_cast<unsigned long long *>(c->hist))));
+        SGPU_CUDA(ctx, cudaGetLastError());
+    }
+    SGPU_CUDA(ctx, cudaStreamSynchronize(st));
+    (void)class2_pairs;
+    return SGPU_OK;
+}
+
+int sgpu_multilocus(sgpu_ctx *ctx, const sgpu_pileup *p, LinkResult &lr, sgpu_counts *c,
                     uint32_t L, uint64_t *n_pairs_multi) {
     cudaStream_t st = ctx->stream;
     if (n_pairs_multi) {
@@ -165,6 +494,30 @@ int sgpu_multilocus(sgpu_ctx *ctx, const sgpu_pileup *p, const LinkResult &lr, s
         return SGPU_OK;
     }
     const uint64_t NS = lr.n_special;
+    // Pairs of order 2: enumeration costs ~m^2 / 2 atomics per locus (m multi-locus reads there), the
+    // second-order GEMM ~5 pseudo-loci per locus pair whatever m is: the GEMM wins from a few hundred
+    // reads per locus. SECEDO_B200_SECOND_ORDER=gemm|enum overrides (tests).
+    const char *env = getenv("SECEDO_B200_SECOND_ORDER");
+    bool use_gemm = env ? env[0] == 'g' : (c->n >= 1024 && lr.n_multi > 150 * p->n_loci);
+    uint64_t hist2_before[3] = { 0, 0, 0 };
+    if (use_gemm) {
+        // the order-2 classes are not enumerated: their number is read off the class histogram afterwards
+        const size_t off[3] = { 2 * SGPU_MAX_CLASS + 0, 1 * SGPU_MAX_CLASS + 1, 0 * SGPU_MAX_CLASS + 2 };
+        for (int k = 0; k < 3; ++k) {
+            SGPU_CUDA(ctx, cudaMemcpyAsync(&hist2_before[k], c->hist + off[k], sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
+        }
+        SGPU_CUDA(ctx, cudaStreamSynchronize(st));
+        long long unused = 0;
+        const int rc = second_order_gemm(ctx, p, lr, c, &unused);
+        if (rc == 1) {
+            use_gemm = false; // loci of one read too far apart for the pair numbering
+        } else if (rc != SGPU_OK) {
+            return rc;
+        } else {
+            c->planes_used = std::max(c->planes_used, static_cast<int>(PLANE_H3));
+            SGPU_TRY(sgpu_link_candidates(ctx, &lr, 3)); // only reads with >= 3 loci can form pairs of order >= 3
+        }
+    }
     DevBuf<unsigned long long> d_np;
     DevBuf<unsigned int> d_max;
     DevBuf<int> d_err;
@@ -198,6 +551,7 @@ int sgpu_multilocus(sgpu_ctx *ctx, const sgpu_pileup *p, const LinkResult &lr, s
     a.nn = c->nn;
     a.L = L;
     a.spill_only = 0;
+    a.min_order = use_gemm ? 3 : 2;
     a.max_order = d_max.p;
     a.n_pairs = d_np.p;
     a.err = d_err.p;
@@ -212,6 +566,19 @@ int sgpu_multilocus(sgpu_ctx *ctx, const sgpu_pileup *p, const LinkResult &lr, s
     }
     if (n_pairs_multi) {
         *n_pairs_multi = ctx->h_scratch[0];
+    }
+    if (use_gemm) { // + the pairs of order 2 (GEMM counts minus what the enumeration took back)
+        const size_t off[3] = { 2 * SGPU_MAX_CLASS + 0, 1 * SGPU_MAX_CLASS + 1, 0 * SGPU_MAX_CLASS + 2 };
+        uint64_t after[3];
+        for (int k = 0; k < 3; ++k) {
+            SGPU_CUDA(ctx, cudaMemcpyAsync(&after[k], c->hist + off[k], sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
+        }
+        SGPU_CUDA(ctx, cudaStreamSynchronize(st));
+        if (n_pairs_multi) {
+            for (int k = 0; k < 3; ++k) {
+                *n_pairs_multi += after[k] - hist2_before[k];
+            }
+        }
     }
     const unsigned int max_order = static_cast<unsigned int>(ctx->h_scratch[1] & 0xFFFFFFFFu);
     // planes that can be non-zero from now on: (2,0) (1,1) (0,2), and (3,0) .. (0,3) once an overlap of

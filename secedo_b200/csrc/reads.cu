@@ -618,6 +618,7 @@ __global__ void __launch_bounds__(TB) sp_finish_kernel(
         const uint8_t *__restrict__ sp_drop, const uint32_t *__restrict__ g_nst, const uint16_t *__restrict__ gid_base,
         const uint8_t *__restrict__ lchr, const uint64_t *__restrict__ tail_locus, const uint32_t *__restrict__ gmap,
         uint32_t n_groups, uint32_t num_cells, uint64_t n_special, uint32_t *__restrict__ sp_code,
+        uint32_t *__restrict__ sp_rcode,
         unsigned long long *__restrict__ stats /* [0]=dropped [1]=multi reads */, int *__restrict__ err) {
     const uint64_t s = static_cast<uint64_t>(blockIdx.x) * TB + threadIdx.x;
     uint32_t dropped = 0, multi_head = 0;
@@ -625,10 +626,12 @@ __global__ void __launch_bounds__(TB) sp_finish_kernel(
         const uint32_t h = sp_head[s];
         const uint32_t multi = g_nst[h] >= 2 ? 1u : 0u;
         multi_head = (h == s) & multi;
-        if (sp_drop[s]) {
+        const bool drop = sp_drop[s] != 0;
+        if (drop) {
             sp_code[s] = CODE_DROPPED;
             dropped = 1;
-        } else {
+        }
+        if (!drop || h == s) {
             // the read's cell is fixed by its first entry (similarity_matrix.cpp:379, :208-209)
             const uint32_t gid = gid_base[sp_entry[h]] >> 2;
             uint32_t cell = 0;
@@ -639,7 +642,12 @@ __global__ void __launch_bounds__(TB) sp_finish_kernel(
             const uint32_t base = gid_base[sp_entry[s]] & 3u;
             const uint32_t hl = sp_locus[h];
             const uint32_t tail = hl >= tail_locus[lchr[hl]] ? 1u : 0u; // read created behind the cutoff
-            sp_code[s] = (cell << 4) | (base << 2) | (tail << 1) | multi;
+            if (!drop) {
+                sp_code[s] = (cell << 4) | (base << 2) | (tail << 1) | multi;
+            }
+            if (h == s) { // the read as a whole (its first entry may itself have been removed by the mate rule)
+                sp_rcode[s] = (cell << 4) | (tail << 1) | multi;
+            }
         }
     }
     const uint32_t bd = __ballot_sync(0xffffffffu, dropped), bm = __ballot_sync(0xffffffffu, multi_head);
@@ -676,14 +684,15 @@ __global__ void __launch_bounds__(TB) sp_start_kernel(const uint32_t *__restrict
 __global__ void __launch_bounds__(TB) me_flag_kernel(const uint32_t *__restrict__ sp_code, const uint32_t *__restrict__ sp_head,
                                                      const uint32_t *__restrict__ sp_locus, const uint64_t *__restrict__ g_off,
                                                      const uint32_t *__restrict__ g_list, const uint32_t *__restrict__ g_nst,
-                                                     uint64_t n_special, uint32_t *__restrict__ flag, uint32_t *__restrict__ pos) {
+                                                     uint64_t n_special, uint32_t min_nst, uint32_t *__restrict__ flag,
+                                                     uint32_t *__restrict__ pos) {
     const uint64_t s = static_cast<uint64_t>(blockIdx.x) * TB + threadIdx.x;
     if (s >= n_special) {
         return;
     }
     const uint32_t c = sp_code[s];
     uint32_t f = 0;
-    if (c != CODE_DROPPED && (c & 1u)) {
+    if (c != CODE_DROPPED && (c & 1u) && g_nst[sp_head[s]] >= min_nst) {
         const uint32_t h = sp_head[s], loc = sp_locus[s], n = g_nst[h];
         const uint64_t o = g_off[h];
         uint32_t i = 0;
@@ -904,6 +913,7 @@ int sgpu_link_reads(sgpu_ctx *ctx, const sgpu_pileup *p, uint32_t num_cells, uin
         SGPU_CUDA(ctx, out->sp_head.alloc(NS, ctx));
         SGPU_CUDA(ctx, out->sp_code.alloc(NS, ctx));
         SGPU_CUDA(ctx, out->sp_drop.alloc(NS, ctx));
+        SGPU_CUDA(ctx, out->sp_rcode.alloc(NS, ctx));
         SGPU_CUDA(ctx, out->g_off.alloc(NS + 1, ctx));
         SGPU_CUDA(ctx, out->g_list.alloc(NS, ctx));
         SGPU_CUDA(ctx, out->g_base.alloc(NS, ctx));
@@ -952,23 +962,9 @@ int sgpu_link_reads(sgpu_ctx *ctx, const sgpu_pileup *p, uint32_t num_cells, uin
     if (NS) {
         SGPU_LAUNCH(ctx, (sp_finish_kernel<<<blocks_for(NS), TB, 0, st>>>(out->sp_head.p, out->sp_entry.p, out->sp_locus.p, out->sp_drop.p,
                                                                           out->g_nst.p, p->d_gid_base, out->lchr.p, out->tail_locus.p,
-                                                                          out->gmap.p, n_groups, num_cells, NS, out->sp_code.p, d_stats.p,
-                                                                          d_err.p)));
-        DevBuf<uint32_t> me_flag, me_tmp;
-        SGPU_CUDA(ctx, me_flag.alloc(NS, ctx));
-        SGPU_CUDA(ctx, me_tmp.alloc(NS, ctx));
-        SGPU_CUDA(ctx, out->me_idx.alloc(NS + 1, ctx));
-        SGPU_CUDA(ctx, out->me_code.alloc(NS, ctx));
-        SGPU_CUDA(ctx, out->me_locus.alloc(NS, ctx));
-        SGPU_CUDA(ctx, out->me_pos.alloc(NS, ctx));
-        SGPU_CUDA(ctx, out->me_beg.alloc(NS, ctx));
-        SGPU_CUDA(ctx, out->me_end.alloc(NS, ctx));
-        SGPU_LAUNCH(ctx, (me_flag_kernel<<<blocks_for(NS), TB, 0, st>>>(out->sp_code.p, out->sp_head.p, out->sp_locus.p, out->g_off.p, out->g_list.p,
-                                                                        out->g_nst.p, NS, me_flag.p, me_tmp.p)));
-        SGPU_TRY(sgpu_scan_u32_u64(ctx, me_flag.p, out->me_idx.p, NS));
-        SGPU_LAUNCH(ctx, (me_compact_kernel<<<blocks_for(NS), TB, 0, st>>>(me_flag.p, me_tmp.p, out->me_idx.p, out->sp_code.p, out->sp_head.p,
-                                                                           out->sp_locus.p, out->g_off.p, out->g_nst.p, NS, out->me_code.p,
-                                                                           out->me_locus.p, out->me_pos.p, out->me_beg.p, out->me_end.p)));
+                                                                          out->gmap.p, n_groups, num_cells, NS, out->sp_code.p,
+                                                                          out->sp_rcode.p, d_stats.p, d_err.p)));
+        SGPU_TRY(sgpu_link_candidates(ctx, out, 2));
     }
     SGPU_CUDA(ctx, cudaGetLastError());
 
@@ -996,6 +992,7 @@ int sgpu_link_reads(sgpu_ctx *ctx, const sgpu_pileup *p, uint32_t num_cells, uin
     out->n_multi = ctx->h_scratch[5];
     out->n_reads = ctx->h_scratch[6];
     std::vector<uint32_t> h_tail_loci;
+    out->h_tail_locus = h_tl;
     for (uint32_t c = 0; c < p->n_chr; ++c) {
         out->n_tail += h_nt[c];
         for (uint64_t l = h_tl[c]; l < p->h_chr_ptr[c + 1]; ++l) {
@@ -1009,6 +1006,33 @@ int sgpu_link_reads(sgpu_ctx *ctx, const sgpu_pileup *p, uint32_t num_cells, uin
         SGPU_CUDA(ctx, cudaMemcpyAsync(out->tail_loci.p, h_tail_loci.data(), h_tail_loci.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
         SGPU_CUDA(ctx, cudaStreamSynchronize(st)); // h_tail_loci is pageable
     }
+    return SGPU_OK;
+}
+
+int sgpu_link_candidates(sgpu_ctx *ctx, LinkResult *out, uint32_t min_nst) {
+    cudaStream_t st = ctx->stream;
+    const uint64_t NS = out->n_special;
+    if (NS == 0) {
+        return SGPU_OK;
+    }
+    DevBuf<uint32_t> me_flag, me_tmp;
+    SGPU_CUDA(ctx, me_flag.alloc(NS, ctx));
+    SGPU_CUDA(ctx, me_tmp.alloc(NS, ctx));
+    if (out->me_idx.p == nullptr) {
+        SGPU_CUDA(ctx, out->me_idx.alloc(NS + 1, ctx));
+        SGPU_CUDA(ctx, out->me_code.alloc(NS, ctx));
+        SGPU_CUDA(ctx, out->me_locus.alloc(NS, ctx));
+        SGPU_CUDA(ctx, out->me_pos.alloc(NS, ctx));
+        SGPU_CUDA(ctx, out->me_beg.alloc(NS, ctx));
+        SGPU_CUDA(ctx, out->me_end.alloc(NS, ctx));
+    }
+    SGPU_LAUNCH(ctx, (me_flag_kernel<<<blocks_for(NS), TB, 0, st>>>(out->sp_code.p, out->sp_head.p, out->sp_locus.p, out->g_off.p, out->g_list.p,
+                                                                    out->g_nst.p, NS, min_nst, me_flag.p, me_tmp.p)));
+    SGPU_TRY(sgpu_scan_u32_u64(ctx, me_flag.p, out->me_idx.p, NS));
+    SGPU_LAUNCH(ctx, (me_compact_kernel<<<blocks_for(NS), TB, 0, st>>>(me_flag.p, me_tmp.p, out->me_idx.p, out->sp_code.p, out->sp_head.p,
+                                                                       out->sp_locus.p, out->g_off.p, out->g_nst.p, NS, out->me_code.p,
+                                                                       out->me_locus.p, out->me_pos.p, out->me_beg.p, out->me_end.p)));
+    SGPU_CUDA(ctx, cudaGetLastError());
     return SGPU_OK;
 }
 
