@@ -248,7 +248,7 @@ __global__ void __launch_bounds__(TB) pair_popc_kernel(const unsigned long long 
 template <bool FILL>
 __global__ void __launch_bounds__(TB) pair_emit_kernel(PairArgs a) {
     const uint64_t h = static_cast<uint64_t>(blockIdx.x) * TB + threadIdx.x;
-    if (!pair_head(a, h)) {
+    if (!pair_head(a, h) || a.g_nst[h] == 2) { // reads with two loci: pair_emit2_kernel
         return;
     }
     const uint64_t o = a.g_off[h];
@@ -278,6 +278,54 @@ __global__ void __launch_bounds__(TB) pair_emit_kernel(PairArgs a) {
                     a.gbB[a.rowB[plB[k]] + kb] = static_cast<uint16_t>((cell << 2) | b2);
                 }
             }
+        }
+    }
+}
+
+// The same for the reads that keep exactly two loci (nearly all multi-locus reads): one thread per read,
+// no loops, and the lanes of a warp that hit the same pseudo-locus (reads are ordered by first locus, so
+// most of a warp does) share one atomic.
+template <bool FILL>
+__global__ void __launch_bounds__(TB) pair_emit2_kernel(PairArgs a) {
+    const uint64_t h = static_cast<uint64_t>(blockIdx.x) * TB + threadIdx.x;
+    const uint32_t lane = threadIdx.x & 31;
+    const bool on = pair_head(a, h) && a.g_nst[h] == 2;
+    uint64_t plA = ~0ull, plB = ~0ull, zA = ~0ull, zB = ~0ull;
+    uint32_t val = 0;
+    if (on) {
+        const uint64_t o = a.g_off[h];
+        const uint32_t rc = a.sp_rcode[h];
+        const uint32_t l1 = a.g_list[o], b1 = a.g_base[o], d = a.g_list[o + 1] - l1 - 1, b2 = a.g_base[o + 1];
+        const uint64_t pid = a.pair_base[l1] + __popcll(a.occ[l1] & ((1ull << d) - 1ull));
+        plA = pid * 4 + b1;
+        plB = pid;
+        val = ((rc >> 4) << 2) | b2;
+        if ((rc >> 1) & 1u) { // tail read
+            const uint32_t c = a.lchr[l1];
+            const uint64_t z = a.z_off[c] + (pid - a.z_first[c]);
+            zA = a.n_pairs * 4 + z * 4 + b1;
+            zB = a.n_pairs + z;
+        }
+    }
+    // one aggregated atomic per distinct key in the warp; returns this lane's position
+    auto reserve = [&](uint32_t *cnt, uint64_t key) -> uint32_t {
+        const uint32_t m = __match_any_sync(0xffffffffu, key);
+        const int leader = __ffs(m) - 1;
+        uint32_t base = 0;
+        if (key != ~0ull && static_cast<int>(lane) == leader) {
+            base = atomicAdd(&cnt[key], static_cast<uint32_t>(__popc(m)));
+        }
+        base = __shfl_sync(0xffffffffu, base, leader);
+        return base + __popc(m & ((1u << lane) - 1u));
+    };
+    const uint32_t ka = reserve(a.cntA, plA), kb = reserve(a.cntB, plB);
+    const uint32_t kza = reserve(a.cntA, zA), kzb = reserve(a.cntB, zB);
+    if (FILL && on) {
+        a.gbA[a.rowA[plA] + ka] = static_cast<uint16_t>(val);
+        a.gbB[a.rowB[plB] + kb] = static_cast<uint16_t>(val);
+        if (zA != ~0ull) {
+            a.gbA[a.rowA[zA] + kza] = static_cast<uint16_t>(val);
+            a.gbB[a.rowB[zB] + kzb] = static_cast<uint16_t>(val);
         }
     }
 }
@@ -370,6 +418,7 @@ static int second_order_gemm(sgpu_ctx *ctx, const sgpu_pileup *p, LinkResult &lr
     a.occ = occ.p;
     a.lchr = lr.lchr.p;
     a.err = d_err.p;
+    SGPU_TRACE(ctx, "pairs: enter");
     SGPU_LAUNCH(ctx, (pair_occ_kernel<<<blocks_for(NS), TB, 0, st>>>(a)));
     SGPU_LAUNCH(ctx, (pair_popc_kernel<<<blocks_for(P), TB, 0, st>>>(occ.p, P, pc.p)));
     SGPU_TRY(sgpu_scan_u32_u64(ctx, pc.p, pair_base.p, P));
@@ -386,6 +435,7 @@ static int second_order_gemm(sgpu_ctx *ctx, const sgpu_pileup *p, LinkResult &lr
     if (static_cast<int>(ctx->h_scratch[1] & 0xFFFFFFFFu) != 0) {
         return 1;
     }
+    SGPU_TRACE(ctx, "pairs: occupancy + numbering");
     const uint64_t NP = ctx->h_scratch[0];
     if (NP == 0) {
         return SGPU_OK;
@@ -421,11 +471,13 @@ static int second_order_gemm(sgpu_ctx *ctx, const sgpu_pileup *p, LinkResult &lr
     a.n_z = NZ;
     a.cntA = cntA.p;
     a.cntB = cntB.p;
+    SGPU_LAUNCH(ctx, (pair_emit2_kernel<false><<<blocks_for(NS), TB, 0, st>>>(a)));
     SGPU_LAUNCH(ctx, (pair_emit_kernel<false><<<blocks_for(NS), TB, 0, st>>>(a)));
     SGPU_TRY(sgpu_scan_u32_u64(ctx, cntA.p, rowA.p, RA));
     SGPU_TRY(sgpu_scan_u32_u64(ctx, cntB.p, rowB.p, RB));
     SGPU_CUDA(ctx, cudaMemcpyAsync(&ctx->h_scratch[0], rowA.p + RA, sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
     SGPU_CUDA(ctx, cudaStreamSynchronize(st)); // also: the host vectors above have been copied
+    SGPU_TRACE(ctx, "pairs: count entries");
     const uint64_t EA = ctx->h_scratch[0]; // = entries of run B as well
     if (EA >= 0x7FFFFFF0ull) {
         return 1;
@@ -449,6 +501,7 @@ static int second_order_gemm(sgpu_ctx *ctx, const sgpu_pileup *p, LinkResult &lr
     a.rowB = rowB.p;
     a.gbA = gbA.p;
     a.gbB = gbB.p;
+    SGPU_LAUNCH(ctx, (pair_emit2_kernel<true><<<blocks_for(NS), TB, 0, st>>>(a)));
     SGPU_LAUNCH(ctx, (pair_emit_kernel<true><<<blocks_for(NS), TB, 0, st>>>(a)));
     SGPU_LAUNCH(ctx, (iota_u32_kernel<<<blocks_for(N), TB, 0, st>>>(ident.p, N, 0)));
     if (NZ) {
@@ -456,6 +509,7 @@ static int second_order_gemm(sgpu_ctx *ctx, const sgpu_pileup *p, LinkResult &lr
         SGPU_LAUNCH(ctx, (iota_u32_kernel<<<blocks_for(NZ), TB, 0, st>>>(tailB.p, static_cast<uint32_t>(NZ), static_cast<uint32_t>(NP))));
     }
     SGPU_CUDA(ctx, cudaGetLastError());
+    SGPU_TRACE(ctx, "pairs: fill");
     for (int run = 0; run < 2; ++run) {
         GemmInput in;
         in.row_ptr = run ? rowB.p : rowA.p;
@@ -480,6 +534,7 @@ static int second_order_gemm(sgpu_ctx *ctx, const sgpu_pileup *p, LinkResult &lr
         SGPU_CUDA(ctx, cudaGetLastError());
     }
     SGPU_CUDA(ctx, cudaStreamSynchronize(st));
+    SGPU_TRACE(ctx, "pairs: GEMM runs + combine");
     (void)class2_pairs;
     return SGPU_OK;
 }
@@ -494,11 +549,14 @@ int sgpu_multilocus(sgpu_ctx *ctx, const sgpu_pileup *p, LinkResult &lr, sgpu_co
         return SGPU_OK;
     }
     const uint64_t NS = lr.n_special;
-    // Pairs of order 2: enumeration costs ~m^2 / 2 atomics per locus (m multi-locus reads there), the
-    // second-order GEMM ~5 pseudo-loci per locus pair whatever m is: the GEMM wins from a few hundred
-    // reads per locus. SECEDO_B200_SECOND_ORDER=gemm|enum overrides (tests).
+    // Pairs of order 2: enumeration costs m^2 / 2 atomics per locus (m multi-locus reads there; measured
+    // 36 ps per pair), the second-order GEMM 5 pseudo-loci per locus pair whatever m is (measured 0.9 us per
+    // locus pair at 8 192 padded cells, ~ N^2): the GEMM wins from m ~ 224 N_pad / 8192 reads per locus.
+    // SECEDO_B200_SECOND_ORDER=gemm|enum overrides (tests).
     const char *env = getenv("SECEDO_B200_SECOND_ORDER");
-    bool use_gemm = env ? env[0] == 'g' : (c->n >= 1024 && lr.n_multi > 150 * p->n_loci);
+    const double n_pad = (c->n + 255) / 256 * 256.0;
+    bool use_gemm = env ? env[0] == 'g'
+                        : (c->n >= 512 && static_cast<double>(lr.n_multi) > 224.0 * n_pad / 8192.0 * static_cast<double>(p->n_loci));
     uint64_t hist2_before[3] = { 0, 0, 0 };
     if (use_gemm) {
         // the order-2 classes are not enumerated: their number is read off the class histogram afterwards
@@ -555,8 +613,10 @@ int sgpu_multilocus(sgpu_ctx *ctx, const sgpu_pileup *p, LinkResult &lr, sgpu_co
     a.max_order = d_max.p;
     a.n_pairs = d_np.p;
     a.err = d_err.p;
+    SGPU_TRACE(ctx, "multi: before enumeration");
     SGPU_LAUNCH(ctx, (multilocus_kernel<<<blocks_for(NS), TB, 0, st>>>(a)));
     SGPU_CUDA(ctx, cudaGetLastError());
+    SGPU_TRACE(ctx, "multi: enumeration");
     SGPU_CUDA(ctx, cudaMemcpyAsync(&ctx->h_scratch[0], d_np.p, sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
     SGPU_CUDA(ctx, cudaMemcpyAsync(&ctx->h_scratch[1], d_max.p, sizeof(unsigned int), cudaMemcpyDeviceToHost, st));
     SGPU_CUDA(ctx, cudaMemcpyAsync(&ctx->h_scratch[2], d_err.p, sizeof(int), cudaMemcpyDeviceToHost, st));

@@ -429,15 +429,34 @@ __global__ void __launch_bounds__(TB) group_count_kernel(const uint32_t *__restr
 __global__ void __launch_bounds__(TB) group_fill_kernel(const uint32_t *__restrict__ sp_head,
                                                         const uint32_t *__restrict__ sp_locus,
                                                         const uint64_t *__restrict__ g_off, uint64_t n_special,
-                                                        uint32_t *__restrict__ cursor, uint32_t *__restrict__ g_list,
-                                                        uint32_t *__restrict__ nf_locus) {
+                                                        uint32_t *__restrict__ cursor, uint32_t *__restrict__ g_list) {
     const uint64_t s = static_cast<uint64_t>(blockIdx.x) * TB + threadIdx.x;
     if (s < n_special) {
         const uint32_t h = sp_head[s];
         const uint32_t k = atomicAdd(&cursor[h], 1u);
         g_list[g_off[h] + k] = static_cast<uint32_t>(s);
-        if (h != s) {
-            atomicAdd(&nf_locus[sp_locus[s]], 1u); // an entry that does not create a read
+    }
+    (void)sp_locus;
+}
+
+// nf_locus[l] = entries of locus l that do not create a read (special entries that are not the first of
+// their read); the special entries of a locus are contiguous: one warp per locus, no atomics
+__global__ void __launch_bounds__(TB) nonfirst_kernel(const uint32_t *__restrict__ sp_head, const uint32_t *__restrict__ sp_start,
+                                                      uint64_t n_loci, uint32_t *__restrict__ nf_locus) {
+    const int lane = threadIdx.x & 31;
+    const uint64_t warps_total = static_cast<uint64_t>(gridDim.x) * (TB / 32);
+    for (uint64_t l = static_cast<uint64_t>(blockIdx.x) * (TB / 32) + (threadIdx.x >> 5); l < n_loci; l += warps_total) {
+        const uint32_t s0 = sp_start[l], s1 = sp_start[l + 1];
+        uint32_t n = 0;
+        for (uint32_t s = s0 + lane; s < s1; s += 32) {
+            n += sp_head[s] != s;
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            n += __shfl_xor_sync(0xffffffffu, n, o);
+        }
+        if (lane == 0) {
+            nf_locus[l] = n;
         }
     }
 }
@@ -927,7 +946,6 @@ int sgpu_link_reads(sgpu_ctx *ctx, const sgpu_pileup *p, uint32_t num_cells, uin
         SGPU_CUDA(ctx, cudaMemsetAsync(cursor.p, 0, NS * sizeof(uint32_t), st));
         SGPU_CUDA(ctx, cudaMemsetAsync(out->g_nst.p, 0, NS * sizeof(uint32_t), st));
         SGPU_CUDA(ctx, cudaMemsetAsync(out->sp_drop.p, 0, NS, st));
-        SGPU_CUDA(ctx, cudaMemsetAsync(nf_locus.p, 0, P * sizeof(uint32_t), st));
         {
             DevBuf<uint32_t> word_locus;
             SGPU_CUDA(ctx, word_locus.alloc(W, ctx));
@@ -946,7 +964,8 @@ int sgpu_link_reads(sgpu_ctx *ctx, const sgpu_pileup *p, uint32_t num_cells, uin
         SGPU_LAUNCH(ctx, (group_count_kernel<<<blocks_for(NS), TB, 0, st>>>(out->sp_bits.p, out->sp_rank.p, sp_first.p, NS, out->sp_head.p, g_cnt.p)));
         SGPU_TRY(sgpu_scan_u32_u64(ctx, g_cnt.p, out->g_off.p, NS));
         SGPU_LAUNCH(ctx, (group_fill_kernel<<<blocks_for(NS), TB, 0, st>>>(out->sp_head.p, out->sp_locus.p, out->g_off.p, NS, cursor.p,
-                                                                           out->g_list.p, nf_locus.p)));
+                                                                           out->g_list.p)));
+        SGPU_LAUNCH(ctx, (nonfirst_kernel<<<locus_grid, TB, 0, st>>>(out->sp_head.p, out->sp_start.p, P, nf_locus.p)));
         SGPU_LAUNCH(ctx, (mate_rule_kernel<<<blocks_for(NS), TB, 0, st>>>(out->sp_head.p, out->sp_entry.p, out->sp_locus.p, out->g_off.p, NS,
                                                                           out->g_list.p, out->g_base.p, p->d_gid_base, p->d_position, L,
                                                                           out->sp_drop.p, out->g_nst.p, d_err.p)));
