@@ -240,6 +240,44 @@ def test_full_size_paths_agree(gpu_ctx, n_cells, coverage, loci_per_chr):
     two.free()
 
 
+@pytest.mark.parametrize("threads", [1, 2, 8])
+def test_second_order_gemm_vs_oracle(gpu_ctx, threads, monkeypatch):
+    """the pairs that overlap at two loci counted by the tcgen05 path on the derived pileup of locus pairs
+    (forced; by default it only takes over from a few hundred multi-locus reads per locus): exact against
+    the oracle incl. mate duplicates, the tail rule and fragments of up to 6 loci, whose pairs of order >= 3
+    are enumerated and taken back out of the second-order planes"""
+    monkeypatch.setenv("SECEDO_B200_SECOND_ORDER", "gemm")
+    ident = np.arange(60, dtype=np.uint32)
+    cfg = SynthConfig(n_cells=60, coverage=0.3, n_loci=900, n_chr=3, p_multi=0.45, p_mate=0.15, theta=0.02, seed=7)
+    f, _ = api.Filter(0.01, 4, gpu_ctx).filter(make_pileup(cfg), ident, "", 1)
+    st, o = check_counts(gpu_ctx, f, 60, 1000, ident, 0.01, 0.5, 0.01, threads, "gemm")
+    assert st["n_multi_reads"] > 0 and st["n_tail_reads"] > 0 and st["n_pairs_multi"] > 0
+    cfg = SynthConfig(n_cells=25, coverage=1.5, n_loci=300, n_chr=1, spacing=40, p_multi=0.9, p_mate=0.1, seed=31)
+    ident = np.arange(25, dtype=np.uint32)
+    st, o = check_counts(gpu_ctx, make_pileup(cfg), 25, 1000, ident, 0.01, 0.5, 0.01, threads, "gemm")
+    hi = o.class_hist.copy()
+    hi[:3, :3][np.add.outer(np.arange(3), np.arange(3)) < 3] = 0
+    assert hi.sum() > 0, "the case must contain overlaps of order >= 3"
+
+
+def test_second_order_gemm_vs_enumeration_full_size(gpu_ctx, monkeypatch):
+    """8 000 cells, 20 % two-locus fragments (the share seen in real pileups): both ways of counting the
+    second-order pairs agree bit for bit, on both first-order paths' worth of planes"""
+    dev = gpu_ctx.synth_pileup(8000, 0.5, 2, 192, n_clones=4, theta=0.001, p_multi=0.2, p_mate=0.05, seed=17)
+    ident = np.arange(8000, dtype=np.uint32)
+    fdev, _ = api.Filter(0.001, 4, gpu_ctx).filter_device(dev, ident)
+    res = {}
+    for mode in ("enum", "gemm"):
+        monkeypatch.setenv("SECEDO_B200_SECOND_ORDER", mode)
+        c = api.Counts(gpu_ctx, 8000)
+        st = c.accumulate(fdev, 1000, ident, 0.01, 0.5, 0.001, 8, "gemm")
+        res[mode] = c.download() + (st["n_pairs_multi"],)
+        c.free()
+    for a, b, name in zip(res["enum"], res["gemm"], ("S", "D", "H", "hist", "n_pairs_multi")):
+        assert np.array_equal(a, b), name
+    assert res["gemm"][2].sum() > 0 and res["gemm"][4] > 10 ** 6
+
+
 def test_async_upload_pipeline(gpu_ctx):
     """chromosome by chromosome with asynchronous uploads running ahead of the kernels (the end-to-end
     path of bench.py): same counts as one synchronous call on the whole pileup"""
