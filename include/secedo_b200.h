@@ -41,7 +41,8 @@ enum {
     SGPU_E_FRAGMENT_SPAN = -4, /* a read id spans >= max_fragment_length: undefined in the reference */
     SGPU_E_CLASS_RANGE = -5,   /* a read pair overlaps at >= SGPU_MAX_CLASS (or >= L) loci */
     SGPU_E_POSITIONS = -6,     /* loci not strictly increasing inside a chromosome */
-    SGPU_E_COUNT_RANGE = -7    /* internal int8/int32 range exceeded */
+    SGPU_E_COUNT_RANGE = -7,   /* internal int8/int32 range exceeded */
+    SGPU_E_CONVERGENCE = -8    /* eigen-solver did not reach the tolerance (sgpu_spectral_embedding) */
 };
 
 /* similarity_matrix.hpp:9-17 */
@@ -189,6 +190,41 @@ int sgpu_similarity_finalize(sgpu_ctx *ctx, sgpu_counts *c, uint32_t max_fragmen
 /* LS / LD tables as evaluated on the device, n*n row-major (parity with similarity_matrix.cpp:117-170). */
 int sgpu_log_probs(sgpu_ctx *ctx, double mutation_rate, double homozygous_rate, double seq_error_rate,
                    uint32_t max_fragment_length, uint32_t n, double *ls, double *ld);
+
+/* ---- Laplacian and its leading eigenpairs (spectral_clustering.cpp) ------------------------------- */
+typedef struct sgpu_spectral_stats {
+    uint32_t outer_iterations; /* Rayleigh-Ritz steps */
+    uint32_t block;            /* vectors iterated together */
+    uint64_t matvec_columns;   /* columns multiplied by the N x N matrix in total */
+    uint64_t matvec_launches;  /* launches of the block product kernel */
+    uint64_t launches;         /* all kernels of the call */
+    double max_residual;       /* largest |M x - theta x| of the returned pairs */
+    double lower_bound;        /* Lanczos bound of the spectrum that the filter damps */
+    float ms_laplacian;        /* degrees + scaling */
+    float ms_solver;           /* subspace iteration */
+    float ms_matvec;           /* the block product kernel alone (sum over launches) */
+    uint32_t reserved;
+} sgpu_spectral_stats;
+/* laplacian() (spectral_clustering.cpp:33-52): out = I - D^-1/2 A D^-1/2, n x n row-major host matrices. */
+int sgpu_laplacian(sgpu_ctx *ctx, const double *similarity, uint32_t n, double *out);
+/* What spectral_clustering() takes from arma::eig_sym(laplacian(similarity)) (spectral_clustering.cpp:127-138,
+ * :166-171, :218, :236): the k smallest eigenvalues (ascending) and their eigenvectors, eigenvectors[i * n + r] =
+ * component r of eigenvector i (Armadillo's column-major layout), unit norm, the component of largest magnitude
+ * positive (LAPACK's sign is arbitrary). Residuals |L v - lambda v| <= tol (0 selects 1e-10). 1 <= k <= 32,
+ * n >= 2 * block (block = 16 for k <= 8, 32 for k <= 16, else 64); similarities must be non-negative. The full
+ * decomposition of the reference is not computed: nothing else of it is used. */
+int sgpu_spectral_embedding(sgpu_ctx *ctx, const double *similarity, uint32_t n, uint32_t k, double tol,
+                            double *eigenvalues, double *eigenvectors, sgpu_spectral_stats *stats);
+/* sgpu_similarity_finalize followed by sgpu_spectral_embedding without the matrix leaving the device
+ * (out may be NULL: the n x n matrix is then not downloaded at all). */
+int sgpu_similarity_finalize_spectral(sgpu_ctx *ctx, sgpu_counts *c, uint32_t max_fragment_length,
+                                      double mutation_rate, double homozygous_rate, double seq_error_rate,
+                                      int normalization, double *out, uint32_t k, double tol, double *eigenvalues,
+                                      double *eigenvectors, sgpu_stats *stats, sgpu_spectral_stats *spectral_stats);
+/* test hook of the block product kernel: out = alpha M X + beta X + gamma W, M n x n symmetric, blocks n x width
+ * row-major (width 8, 16, 32 or 64), all on the host */
+int sgpu_spectral_matvec(sgpu_ctx *ctx, const double *M, uint32_t n, int width, const double *X, const double *W,
+                         double alpha, double beta, double gamma, double *out);
 
 #ifdef __cplusplus
 }

@@ -68,6 +68,7 @@ def oracle_lib():
         _oracle.orc_filter.restype = C.c_int
         _oracle.orc_log_probs.restype = C.c_int
         _oracle.orc_normalize.restype = C.c_int
+        _oracle.orc_laplacian.restype = C.c_int
         _oracle.orc_is_significant.restype = C.c_int
     return _oracle
 
@@ -160,6 +161,25 @@ def normalize(m, normalization: str) -> np.ndarray:
     if rc:
         raise ValueError("invalid normalization")
     return m
+
+
+def laplacian(a) -> np.ndarray:
+    """laplacian() of the reference (spectral_clustering.cpp:33-52), restated in oracle/secedo_oracle.c."""
+    a = np.ascontiguousarray(a, np.float64)
+    out = np.zeros_like(a)
+    rc = oracle_lib().orc_laplacian(C.c_uint32(a.shape[0]), _p(a, _f64p), _p(out, _f64p))
+    assert rc == 0
+    return out
+
+
+def spectral_embedding(similarity, k: int):
+    """What spectral_clustering() takes from ``arma::eig_sym(eigenvalues, eigenvectors, lap)``
+    (spectral_clustering.cpp:127-138): all eigenpairs of the Laplacian, ascending; the first k are returned.
+    Armadillo 10.3.0 (third_party/armadillo-10.3.0) forwards eig_sym to LAPACK ``dsyev``/``dsyevd``; LAPACK is not
+    vendored by the reference, so the same published routine is reached here through numpy.linalg.eigh (``dsyevd``
+    of the OpenBLAS bundled with numpy). Eigenvector signs are arbitrary in both."""
+    w, v = np.linalg.eigh(laplacian(similarity))
+    return w[:k].copy(), np.ascontiguousarray(v[:, :k])
 
 
 # --------------------------------------------------------------------- compiled reference

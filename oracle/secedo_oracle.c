@@ -709,3 +709,33 @@ int orc_similarity(uint32_t n_chr,
     free(cache);
     return rc;
 }
+
+/* ------------------------------------------------------------------------------------------ */
+/* Graph Laplacian                                                         */
+/* ------------------------------------------------------------------------------------------ */
+
+int orc_laplacian(uint32_t n, const double *a, double *out) {
+    /* spectral_clustering.cpp:33-52: degrees summed along the row in index order, 1/sqrt (0 stays 0),
+     * result(r,c) = (r == c) - diag[r] * diag[c] * a(r,c), lower triangle mirrored */
+    double *diag = (double *)calloc(n ? n : 1, sizeof(double));
+    if (!diag) {
+        return -1;
+    }
+    for (uint32_t r = 0; r < n; ++r) {
+        for (uint32_t c = 0; c < n; ++c) {
+            diag[r] += a[(uint64_t)r * n + c];
+        }
+    }
+    for (uint32_t r = 0; r < n; ++r) {
+        diag[r] = diag[r] == 0 ? 0 : 1 / sqrt(diag[r]);
+    }
+    for (uint32_t r = 0; r < n; ++r) {
+        for (uint32_t c = 0; c <= r; ++c) {
+            double v = (r == c ? 1 : 0) - diag[r] * diag[c] * a[(uint64_t)r * n + c];
+            out[(uint64_t)r * n + c] = v;
+            out[(uint64_t)c * n + r] = v;
+        }
+    }
+    free(diag);
+    return 0;
+}

@@ -99,6 +99,9 @@ int orc_similarity(uint32_t n_chr,
 /* similarity_matrix.cpp:271-293 on a row-major n*n matrix, in place. */
 int orc_normalize(int normalization, uint32_t n, double *m);
 
+/* laplacian(), spectral_clustering.cpp:33-52, on row-major n*n matrices. */
+int orc_laplacian(uint32_t n, const double *a, double *out);
+
 #ifdef __cplusplus
 }
 #endif

@@ -41,6 +41,18 @@ class Stats(C.Structure):
         return d
 
 
+class SpectralStats(C.Structure):
+    _fields_ = [
+        ("outer_iterations", C.c_uint32), ("block", C.c_uint32), ("matvec_columns", C.c_uint64),
+        ("matvec_launches", C.c_uint64), ("launches", C.c_uint64), ("max_residual", C.c_double),
+        ("lower_bound", C.c_double), ("ms_laplacian", C.c_float), ("ms_solver", C.c_float), ("ms_matvec", C.c_float),
+        ("reserved", C.c_uint32),
+    ]
+
+    def as_dict(self):
+        return {k: getattr(self, k) for k, _ in self._fields_ if k != "reserved"}
+
+
 class SynthParams(C.Structure):
     _fields_ = [
         ("n_cells", C.c_uint32), ("n_chr", C.c_uint32), ("loci_per_chr", C.c_uint32), ("n_clones", C.c_uint32),
@@ -89,6 +101,12 @@ SIGNATURES = {
     "sgpu_similarity_finalize": (C.c_int, [_vp, _vp, C.c_uint32, C.c_double, C.c_double, C.c_double, C.c_int, _vp,
                                            C.POINTER(Stats)]),
     "sgpu_log_probs": (C.c_int, [_vp, C.c_double, C.c_double, C.c_double, C.c_uint32, C.c_uint32, _vp, _vp]),
+    "sgpu_laplacian": (C.c_int, [_vp, _vp, C.c_uint32, _vp]),
+    "sgpu_spectral_embedding": (C.c_int, [_vp, _vp, C.c_uint32, C.c_uint32, C.c_double, _vp, _vp, C.POINTER(SpectralStats)]),
+    "sgpu_similarity_finalize_spectral": (C.c_int, [_vp, _vp, C.c_uint32, C.c_double, C.c_double, C.c_double, C.c_int, _vp,
+                                                    C.c_uint32, C.c_double, _vp, _vp, C.POINTER(Stats),
+                                                    C.POINTER(SpectralStats)]),
+    "sgpu_spectral_matvec": (C.c_int, [_vp, _vp, C.c_uint32, C.c_int, _vp, _vp, C.c_double, C.c_double, C.c_double, _vp]),
 }
 
 _lib = None

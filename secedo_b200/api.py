@@ -22,7 +22,7 @@ from typing import Optional, Sequence, Tuple, Union
 import numpy as np
 
 from . import _lib
-from ._lib import NORMALIZATIONS, PATHS, SgpuError, Stats
+from ._lib import NORMALIZATIONS, PATHS, SgpuError, SpectralStats, Stats
 from .pileup import NO_POS, Pileup
 
 
@@ -324,6 +324,26 @@ class Counts:
             self.last_stats["ms_epilogue"] = st.ms_epilogue
         return out
 
+    def finalize_spectral(self, max_fragment_length: int, mutation_rate: float, homozygous_rate: float,
+                          seq_error_rate: float, normalization: str, k: int = 7, tol: float = 0.0,
+                          want_matrix: bool = False):
+        """Epilogue + Laplacian + the ``k`` smallest eigenpairs without the matrix leaving HBM
+        (what ``spectral_clustering`` takes from ``arma::eig_sym``, spectral_clustering.cpp:127-138).
+        Returns (eigenvalues[k], eigenvectors[n, k], stats, matrix or None)."""
+        if normalization not in NORMALIZATIONS:
+            raise ValueError("Invalid normalization: " + str(normalization))
+        n = self.num_cells
+        out = np.zeros((n, n), np.float64) if want_matrix else None
+        ev, vec = np.zeros(k, np.float64), np.zeros((k, n), np.float64)
+        st, sp = Stats(), SpectralStats()
+        self.ctx.check(self.ctx._lib.sgpu_similarity_finalize_spectral(
+            self.ctx._h, self._h, int(max_fragment_length), float(mutation_rate), float(homozygous_rate),
+            float(seq_error_rate), NORMALIZATIONS[normalization], _ptr(out), int(k), float(tol), _ptr(ev), _ptr(vec),
+            C.byref(st), C.byref(sp)))
+        d = sp.as_dict()
+        d["ms_epilogue"] = st.ms_epilogue
+        return ev, np.ascontiguousarray(vec.T), d, out
+
     def free(self) -> None:
         if self._h and self.ctx._h:
             self.ctx._lib.sgpu_counts_free(self.ctx._h, self._h)
@@ -375,5 +395,44 @@ def log_probs(mutation_rate: float, homozygous_rate: float, seq_error_rate: floa
     return ls, ld
 
 
-__all__ = ["Context", "DevicePileup", "Filter", "Counts", "compute_similarity_matrix", "log_probs", "default_context",
+def laplacian(a: np.ndarray, ctx: Optional[Context] = None) -> np.ndarray:
+    """``laplacian`` (spectral_clustering.cpp:33-52): I - D^-1/2 A D^-1/2 of a symmetric matrix with zero diagonal."""
+    ctx = ctx or default_context()
+    a = np.ascontiguousarray(a, np.float64)
+    assert a.ndim == 2 and a.shape[0] == a.shape[1]
+    out = np.zeros_like(a)
+    ctx.check(ctx._lib.sgpu_laplacian(ctx._h, _ptr(a), a.shape[0], _ptr(out)))
+    return out
+
+
+def spectral_embedding(similarity: np.ndarray, k: int = 7, tol: float = 0.0, ctx: Optional[Context] = None,
+                       return_stats: bool = False):
+    """The part of ``arma::eig_sym(eigenvalues, eigenvectors, laplacian(similarity))`` that
+    ``spectral_clustering`` uses (spectral_clustering.cpp:127-138, :166-171, :218, :236): the ``k`` smallest
+    eigenvalues (ascending) and their eigenvectors as the columns of an (n, k) array."""
+    ctx = ctx or default_context()
+    a = np.ascontiguousarray(similarity, np.float64)
+    assert a.ndim == 2 and a.shape[0] == a.shape[1]
+    n = a.shape[0]
+    ev, vec = np.zeros(k, np.float64), np.zeros((k, n), np.float64)
+    sp = SpectralStats()
+    ctx.check(ctx._lib.sgpu_spectral_embedding(ctx._h, _ptr(a), n, int(k), float(tol), _ptr(ev), _ptr(vec), C.byref(sp)))
+    vec = np.ascontiguousarray(vec.T)
+    return (ev, vec, sp.as_dict()) if return_stats else (ev, vec)
+
+
+def spectral_matvec(m: np.ndarray, x: np.ndarray, w: Optional[np.ndarray] = None, alpha: float = 1.0, beta: float = 0.0,
+                    gamma: float = 0.0, ctx: Optional[Context] = None) -> np.ndarray:
+    """Test hook of the block product kernel of the eigen-solver: alpha M X + beta X + gamma W."""
+    ctx = ctx or default_context()
+    m = np.ascontiguousarray(m, np.float64)
+    x = np.ascontiguousarray(x, np.float64)
+    w = None if w is None else np.ascontiguousarray(w, np.float64)
+    out = np.zeros_like(x)
+    ctx.check(ctx._lib.sgpu_spectral_matvec(ctx._h, _ptr(m), m.shape[0], x.shape[1], _ptr(x), _ptr(w), float(alpha),
+                                            float(beta), float(gamma), _ptr(out)))
+    return out
+
+
+__all__ = ["Context", "DevicePileup", "Filter", "Counts", "compute_similarity_matrix", "log_probs", "default_context", "laplacian", "spectral_embedding",
            "NO_POS", "SgpuError"]

@@ -679,4 +679,59 @@ int sgpu_log_probs(sgpu_ctx *ctx, double mutation_rate, double homozygous_rate, 
     return sgpu_log_probs_impl(ctx, mutation_rate, homozygous_rate, seq_error_rate, max_fragment_length, n, ls, ld);
 }
 
+// ---- Laplacian + leading eigenpairs (spectral.cu) ----
+static int upload_matrix(sgpu_ctx *ctx, const double *h, uint32_t n, DevBuf<double> &d) {
+    if (!h || n == 0) {
+        return sgpu_fail(ctx, SGPU_E_ARG, "similarity matrix missing");
+    }
+    SGPU_CUDA(ctx, d.alloc(static_cast<size_t>(n) * n, ctx));
+    SGPU_CUDA(ctx, cudaMemcpyAsync(d.p, h, static_cast<size_t>(n) * n * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    return SGPU_OK;
+}
+
+int sgpu_laplacian(sgpu_ctx *ctx, const double *similarity, uint32_t n, double *out) {
+    SGPU_CUDA(ctx, cudaSetDevice(ctx->device));
+    DevBuf<double> d;
+    SGPU_TRY(upload_matrix(ctx, similarity, n, d));
+    return sgpu_laplacian_device(ctx, d.p, n, out);
+}
+
+int sgpu_spectral_embedding(sgpu_ctx *ctx, const double *similarity, uint32_t n, uint32_t k, double tol,
+                            double *eigenvalues, double *eigenvectors, sgpu_spectral_stats *stats) {
+    SGPU_CUDA(ctx, cudaSetDevice(ctx->device));
+    DevBuf<double> d;
+    SGPU_TRY(upload_matrix(ctx, similarity, n, d));
+    return sgpu_spectral_device(ctx, d.p, n, k, tol, eigenvalues, eigenvectors, stats);
+}
+
+int sgpu_similarity_finalize_spectral(sgpu_ctx *ctx, sgpu_counts *c, uint32_t max_fragment_length, double mutation_rate,
+                                      double homozygous_rate, double seq_error_rate, int normalization, double *out,
+                                      uint32_t k, double tol, double *eigenvalues, double *eigenvectors, sgpu_stats *stats,
+                                      sgpu_spectral_stats *spectral_stats) {
+    SGPU_CUDA(ctx, cudaSetDevice(ctx->device));
+    if (c->have_params && c->spill
+        && (c->eps != mutation_rate || c->h != homozygous_rate || c->theta != seq_error_rate || c->L != max_fragment_length)) {
+        return sgpu_fail(ctx, SGPU_E_ARG, "finalize called with likelihood parameters different from accumulate");
+    }
+    double *d_mat = nullptr;
+    EventTimer t(ctx->stream);
+    SGPU_TRY(sgpu_epilogue(ctx, c, max_fragment_length, mutation_rate, homozygous_rate, seq_error_rate, normalization, out, &d_mat));
+    const float ms = t.stop();
+    if (stats) {
+        stats->ms_epilogue = ms;
+    }
+    if (!d_mat) {
+        return sgpu_fail(ctx, SGPU_E_ARG, "spectral: empty similarity matrix");
+    }
+    const int rc = sgpu_spectral_device(ctx, d_mat, c->n, k, tol, eigenvalues, eigenvectors, spectral_stats);
+    sgpu_dev_free(ctx, d_mat);
+    return rc;
+}
+
+int sgpu_spectral_matvec(sgpu_ctx *ctx, const double *M, uint32_t n, int width, const double *X, const double *W, double alpha,
+                         double beta, double gamma, double *out) {
+    SGPU_CUDA(ctx, cudaSetDevice(ctx->device));
+    return sgpu_spectral_matvec_host(ctx, M, n, width, X, W, alpha, beta, gamma, out);
+}
+
 } // extern "C"

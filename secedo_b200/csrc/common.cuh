@@ -257,8 +257,16 @@ struct FTable {
 };
 int sgpu_log_probs_impl(sgpu_ctx *ctx, double eps, double h, double theta, uint32_t L, uint32_t n,
                         double *h_ls, double *h_ld);
+// d_keep != NULL: the device matrix is handed to the caller (free with sgpu_dev_free)
 int sgpu_epilogue(sgpu_ctx *ctx, sgpu_counts *c, uint32_t L, double eps, double h, double theta,
-                  int normalization, double *h_out);
+                  int normalization, double *h_out, double **d_keep = nullptr);
+
+// spectral.cu
+int sgpu_spectral_device(sgpu_ctx *ctx, const double *d_A, uint32_t n, uint32_t k, double tol, double *h_evals,
+                         double *h_evecs, sgpu_spectral_stats *stats);
+int sgpu_laplacian_device(sgpu_ctx *ctx, const double *d_A, uint32_t n, double *h_out);
+int sgpu_spectral_matvec_host(sgpu_ctx *ctx, const double *h_M, uint32_t n, int width, const double *h_X, const double *h_W,
+                              double alpha, double beta, double gamma, double *h_out);
 // device table of G(s,d) = F(s,d) - s F(1,0) - d F(0,1) for the spill plane (SGPU_MAX_CLASS^2 doubles)
 int sgpu_build_gtable(sgpu_ctx *ctx, double eps, double h, double theta, uint32_t L, uint32_t n,
                       double *d_G /* device, SGPU_MAX_CLASS^2 */, double *d_F /* device, optional */);

@@ -343,7 +343,7 @@ int sgpu_build_gtable(sgpu_ctx *ctx, double eps, double h, double theta, uint32_
 }
 
 int sgpu_epilogue(sgpu_ctx *ctx, sgpu_counts *c, uint32_t L, double eps, double h, double theta, int normalization,
-                  double *h_out) {
+                  double *h_out, double **d_keep) {
     cudaStream_t st = ctx->stream;
     if (normalization < 0 || normalization > 2) {
         return sgpu_fail(ctx, SGPU_E_ARG, "Invalid normalization: %d", normalization); // similarity_matrix.cpp:264
@@ -428,5 +428,8 @@ int sgpu_epilogue(sgpu_ctx *ctx, sgpu_counts *c, uint32_t L, double eps, double 
         SGPU_CUDA(ctx, cudaMemcpyAsync(h_out, out.p, c->nn * sizeof(double), cudaMemcpyDeviceToHost, st));
     }
     SGPU_CUDA(ctx, cudaStreamSynchronize(st));
+    if (d_keep) {
+        *d_keep = out.take();
+    }
     return SGPU_OK;
 }
