@@ -25,7 +25,7 @@ def _stale(target: str, deps) -> bool:
 
 def build(verbose: bool = False, force: bool = False) -> str:
     os.makedirs(OBJ, exist_ok=True)
-    headers = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cuh", ".h"))]
+    headers = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cuh", ".h", ".hpp"))]
     headers.append(os.path.join(HERE, "..", "include", "secedo_b200.h"))
     srcs = [s for s in SOURCES if os.path.exists(os.path.join(CSRC, s))]
 

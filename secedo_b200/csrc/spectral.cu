@@ -374,7 +374,8 @@ struct Solver {
     int setup(int width) {
         const int rg = 8 / (width / 8);
         const uint32_t tiles = (ld + rg * 32 * mv_r(width) - 1) / (rg * 32 * mv_r(width));
-        uint32_t want = std::max(1u, (2u * ctx->sm_count + tiles - 1) / tiles);
+        // two CTAs per SM, ONE wave: splits rounded down so that no second, nearly empty wave is started
+        uint32_t want = std::max(1u, 2u * ctx->sm_count / tiles);
         uint32_t kps = ((ld + want - 1) / want + MV_KC - 1) / MV_KC * MV_KC;
         k_per_split = kps;
         n_split = (ld + kps - 1) / kps;
