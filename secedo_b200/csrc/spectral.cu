@@ -25,7 +25,9 @@ namespace {
 
 
 constexpr int MV_THREADS = 256;
-constexpr int MV_KC = 32; // rows of X staged per shared-memory chunk
+constexpr int MV_PAD = 64; // matrices and blocks are padded to a multiple of this many rows
+// rows of X staged per shared-memory chunk (double buffered with cp.async)
+__host__ __device__ constexpr int mv_kc(int width) { return width <= 16 ? 64 : 32; }
 // rows of the output per thread / rows of M per pipeline stage: narrow blocks are HBM bound (more bytes in
 // flight: 2 x 8 rows of 16 bytes per thread), wide ones FP64 bound (4 x 8 register tile, half the shared-memory reads)
 constexpr int mv_r(int width) { return width <= 16 ? 2 : 4; }
@@ -41,13 +43,15 @@ symm_block_kernel(const double *__restrict__ M, uint32_t ld, const double *__res
     constexpr int CG = B / 8;     // column groups (one warp each)
     constexpr int RG = 8 / CG;    // row groups of 32 * R rows per CTA
     constexpr int H = R / 2;      // 16-byte loads per row of M and thread
-    __shared__ double2 xs[MV_KC * B / 2];
+    constexpr int KC = mv_kc(B);  // rows of X per shared-memory chunk
+    constexpr int CHUNK2 = KC * B / 2;
+    __shared__ double2 xs[2][CHUNK2];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int cg = warp % CG, rg = warp / CG;
     const uint32_t r0 = (blockIdx.x * RG + rg) * (32u * R) + lane * R;
     const bool active = r0 < ld;
     const uint32_t kbeg = blockIdx.y * k_per_split;
-    const uint32_t kend = min(ld, kbeg + k_per_split); // ld == padded row count, multiple of MV_KC
+    const uint32_t kend = min(ld, kbeg + k_per_split); // ld and k_per_split are multiples of KC
     double acc[R][8];
 #pragma unroll
     for (int i = 0; i < R; ++i) {
@@ -69,10 +73,10 @@ symm_block_kernel(const double *__restrict__ M, uint32_t ld, const double *__res
             }
         }
     };
-    auto fmaU = [&](const double2 (&m)[U][H], int kk) {
+    auto fmaU = [&](const double2 (&m)[U][H], const double2 *xc, int kk) {
 #pragma unroll
         for (int u = 0; u < U; ++u) {
-            const double2 *xr = xs + ((kk + u) * B + cg * 8) / 2;
+            const double2 *xr = xc + ((kk + u) * B + cg * 8) / 2;
             const double2 x01 = xr[0], x23 = xr[1], x45 = xr[2], x67 = xr[3];
             const double x[8] = { x01.x, x01.y, x23.x, x23.y, x45.x, x45.y, x67.x, x67.y };
 #pragma unroll
@@ -85,25 +89,38 @@ symm_block_kernel(const double *__restrict__ M, uint32_t ld, const double *__res
             }
         }
     };
-    if (active && kbeg < kend) {
-        loadU(m0, kbeg);
-    }
-    for (uint32_t k0 = kbeg; k0 < kend; k0 += MV_KC) {
-        __syncthreads();
+    // rows [k0, k0 + KC) of X -> xs[buf] with cp.async (16 bytes per copy), one commit group per chunk
+    auto stage_x = [&](uint32_t k0, int buf) {
         const double2 *xg = reinterpret_cast<const double2 *>(X + static_cast<size_t>(k0) * B);
-        for (int i = threadIdx.x; i < MV_KC * B / 2; i += MV_THREADS) {
-            xs[i] = xg[i];
+        for (int i = threadIdx.x; i < CHUNK2; i += MV_THREADS) {
+            const uint32_t dst = static_cast<uint32_t>(__cvta_generic_to_shared(&xs[buf][i]));
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(xg + i) : "memory");
         }
-        __syncthreads();
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+    if (kbeg < kend) {
+        stage_x(kbeg, 0);
         if (active) {
+            loadU(m0, kbeg);
+        }
+    }
+    int buf = 0;
+    for (uint32_t k0 = kbeg; k0 < kend; k0 += KC, buf ^= 1) {
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+        __syncthreads(); // chunk k0 has landed for every thread, and everybody is done with the other buffer
+        if (k0 + KC < kend) {
+            stage_x(k0 + KC, buf ^ 1); // overlaps the arithmetic on this chunk
+        }
+        if (active) {
+            const double2 *xc = xs[buf];
 #pragma unroll
-            for (int kk = 0; kk < MV_KC; kk += 2 * U) {
+            for (int kk = 0; kk < KC; kk += 2 * U) {
                 loadU(m1, k0 + kk + U);
-                fmaU(m0, kk);
+                fmaU(m0, xc, kk);
                 if (k0 + kk + 2 * U < kend) {
                     loadU(m0, k0 + kk + 2 * U);
                 }
-                fmaU(m1, kk + U);
+                fmaU(m1, xc, kk + U);
             }
         }
     }
@@ -357,6 +374,54 @@ __global__ void __launch_bounds__(256) rank_update_kernel(double *__restrict__ M
     }
 }
 
+// One Lanczos step after w = M v, on column 0 of blocks of `width` columns, by ONE CTA (n is a few thousand):
+// alpha = v.w; w -= alpha v + beta_prev v_prev; beta = |w|; w /= beta. ab[2j] = alpha, ab[2j + 1] = beta.
+__device__ double block_sum_1024(double v, double *red) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        v += __shfl_xor_sync(0xFFFFFFFFu, v, o);
+    }
+    __syncthreads(); // red may still be read from the previous reduction
+    if ((threadIdx.x & 31) == 0) {
+        red[threadIdx.x >> 5] = v;
+    }
+    __syncthreads();
+    double s = 0.0;
+    for (int i = 0; i < 32; ++i) {
+        s += red[i];
+    }
+    return s;
+}
+
+__global__ void __launch_bounds__(1024) lanczos_tail_kernel(const double *__restrict__ v, const double *__restrict__ vp,
+                                                            double *__restrict__ w, int width, uint32_t rows, int j,
+                                                            double *__restrict__ ab) {
+    __shared__ double red[32];
+    double a = 0.0;
+    for (uint32_t r = threadIdx.x; r < rows; r += 1024) {
+        a = fma(v[static_cast<size_t>(r) * width], w[static_cast<size_t>(r) * width], a);
+    }
+    a = block_sum_1024(a, red);
+    const double bp = j > 0 ? ab[2 * (j - 1) + 1] : 0.0;
+    double nn = 0.0;
+    for (uint32_t r = threadIdx.x; r < rows; r += 1024) {
+        const size_t i = static_cast<size_t>(r) * width;
+        const double x = w[i] - a * v[i] - bp * vp[i];
+        w[i] = x;
+        nn = fma(x, x, nn);
+    }
+    nn = block_sum_1024(nn, red);
+    const double b = sqrt(nn);
+    const double inv = b > 1e-14 ? 1.0 / b : 0.0;
+    for (uint32_t r = threadIdx.x; r < rows; r += 1024) {
+        w[static_cast<size_t>(r) * width] *= inv;
+    }
+    if (threadIdx.x == 0) {
+        ab[2 * j] = a;
+        ab[2 * j + 1] = b;
+    }
+}
+
 // ------------------------------------------------------------------------------------------------------------
 struct Solver {
     sgpu_ctx *ctx;
@@ -376,7 +441,8 @@ struct Solver {
         const uint32_t tiles = (ld + rg * 32 * mv_r(width) - 1) / (rg * 32 * mv_r(width));
         // two CTAs per SM, ONE wave: splits rounded down so that no second, nearly empty wave is started
         uint32_t want = std::max(1u, 2u * ctx->sm_count / tiles);
-        uint32_t kps = ((ld + want - 1) / want + MV_KC - 1) / MV_KC * MV_KC;
+        const uint32_t kc = mv_kc(width);
+        uint32_t kps = ((ld + want - 1) / want + kc - 1) / kc * kc;
         k_per_split = kps;
         n_split = (ld + kps - 1) / kps;
         return SGPU_OK;
@@ -467,6 +533,30 @@ struct Solver {
                                          cudaMemcpyDeviceToDevice, st));
         return SGPU_OK;
     }
+    DevBuf<double> d_ab;
+    int lanczos_tail(const double *v, const double *vp, double *w, int width, int j) {
+        if (d_ab.n < 128) {
+            SGPU_CUDA(ctx, d_ab.alloc(128, ctx));
+        }
+        if (j >= 64) {
+            return sgpu_fail(ctx, SGPU_E_ARG, "spectral: too many Lanczos steps");
+        }
+        SGPU_LAUNCH(ctx, (lanczos_tail_kernel<<<1, 1024, 0, st>>>(v, vp, w, width, ld, j, d_ab.p)));
+        SGPU_CUDA(ctx, cudaGetLastError());
+        return SGPU_OK;
+    }
+    int lanczos_fetch(int steps, std::vector<double> &al, std::vector<double> &be) {
+        std::vector<double> ab(2 * static_cast<size_t>(steps));
+        SGPU_CUDA(ctx, cudaMemcpyAsync(ab.data(), d_ab.p, ab.size() * sizeof(double), cudaMemcpyDeviceToHost, st));
+        SGPU_CUDA(ctx, cudaStreamSynchronize(st));
+        al.resize(steps);
+        be.resize(steps);
+        for (int j = 0; j < steps; ++j) {
+            al[j] = ab[2 * j];
+            be[j] = ab[2 * j + 1];
+        }
+        return collect_times();
+    }
     int rank_update(const double *Q, int q_width, int off, int nl, const double *lam) {
         if (d_lam.n < 64) {
             SGPU_CUDA(ctx, d_lam.alloc(64, ctx));
@@ -554,9 +644,9 @@ int sgpu_spectral_device(sgpu_ctx *ctx, const double *d_A, uint32_t n, uint32_t 
     S.ctx = ctx;
     S.st = st;
     S.n = n;
-    S.ld = (n + 31) / 32 * 32;
+    S.ld = (n + MV_PAD - 1) / MV_PAD * MV_PAD;
     const uint32_t ld = S.ld;
-    const int b = std::min<int>(block_width_for(k), static_cast<int>(ld)); // ld >= 32
+    const int b = std::min<int>(block_width_for(k), static_cast<int>(ld)); // ld >= 64
     const int kq = static_cast<int>((k + 7) / 8 * 8);
     if (k > 1 && n < 2u * b) {
         return sgpu_fail(ctx, SGPU_E_ARG, "spectral: %u cells are too few for a block of %d vectors (k = %u)", n, b, k);
@@ -704,7 +794,7 @@ int sgpu_spectral_matvec_host(sgpu_ctx *ctx, const double *h_M, uint32_t n, int 
     S.ctx = ctx;
     S.st = st;
     S.n = n;
-    S.ld = (n + 31) / 32 * 32;
+    S.ld = (n + MV_PAD - 1) / MV_PAD * MV_PAD;
     const uint32_t ld = S.ld;
     std::vector<double> pm(static_cast<size_t>(ld) * ld, 0.0), px(static_cast<size_t>(ld) * width, 0.0), pw(px.size(), 0.0);
     for (uint32_t r = 0; r < n; ++r) {

@@ -145,6 +145,8 @@ struct Rng {
 //   bk.mv(width, out, in, alpha, beta, gamma, w)      out = alpha M in + beta in + gamma w
 //   bk.gram(X, p, Y, q, host)                         host = X^T Y (p x q)
 //   bk.xr(Z, X1, p1, R1, X2, p2, R2, q)               Z = X1 R1 + X2 R2 (X2 may be null)
+//   bk.lanczos_tail(v, v_prev, w, width, j)           one Lanczos step after w = M v, on column 0 (see below)
+//   bk.lanczos_fetch(steps, alpha, beta)              the recurrence coefficients of all steps
 //   bk.rank_update(Q, kq, off, nl, coef)              M -= sum_i coef[i] q_(off+i) q_(off+i)^T
 // Every call returns 0 or an error code that is passed up unchanged.
 struct SolveResult {
@@ -200,27 +202,24 @@ int subspace_iteration(BK &bk, uint32_t n, uint32_t ld, uint32_t k, int b, int k
         SGPU_SP_TRY(bk.gram(V, lw, V, lw, gm));
         SGPU_SP_TRY(bk.xr(Wv, V, lw, scaled_identity(lw, 1.0 / std::sqrt(gm[0])), nullptr, 0, none, lw));
         std::swap(V, Wv);
-        std::vector<double> al, be;
-        double beta_prev = 0.0;
+        // three-term recurrence without host round trips: the backend keeps alpha_j, beta_j
         for (int j = 0; j < steps; ++j) {
-            SGPU_SP_TRY(bk.mv(lw, Wv, V, 1.0, 0.0, -beta_prev, Vp)); // w = M v - beta v_prev
-            SGPU_SP_TRY(bk.gram(V, lw, Wv, lw, gm));
-            const double a = gm[0];
-            // w - a v, into Vp (v_prev is no longer needed)
-            SGPU_SP_TRY(bk.xr(Vp, Wv, lw, scaled_identity(lw), V, lw, scaled_identity(lw, -a), lw));
-            SGPU_SP_TRY(bk.gram(Vp, lw, Vp, lw, gm));
-            const double bn = std::sqrt(std::max(gm[0], 0.0));
-            al.push_back(a);
-            be.push_back(bn);
-            if (bn <= 1e-14) {
-                break;
-            }
-            SGPU_SP_TRY(bk.xr(Wv, Vp, lw, scaled_identity(lw, 1.0 / bn), nullptr, 0, none, lw)); // v_next
-            double *old_v = V; // rotate: v_prev <- v, v <- v_next
+            SGPU_SP_TRY(bk.mv(lw, Wv, V, 1.0, 0.0, 0.0, nullptr)); // w = M v
+            // alpha_j = v.w; w -= alpha_j v + beta_(j-1) v_prev; beta_j = |w|; w /= beta_j   (column 0)
+            SGPU_SP_TRY(bk.lanczos_tail(V, Vp, Wv, lw, j));
+            double *old_v = V; // rotate: v_prev <- v, v <- w, w <- scratch
             V = Wv;
             Wv = Vp;
             Vp = old_v;
-            beta_prev = bn;
+        }
+        std::vector<double> al, be;
+        SGPU_SP_TRY(bk.lanczos_fetch(steps, al, be));
+        for (size_t j = 0; j < be.size(); ++j) { // breakdown: an invariant subspace was found
+            if (!(be[j] > 1e-14)) {
+                al.resize(j + 1);
+                be.resize(j + 1);
+                break;
+            }
         }
         lanczos_bounds(al, be, &res->lo, &res->hi);
     }

@@ -64,6 +64,30 @@ struct HostBackend {
             }
         return 0;
     }
+    std::vector<double> lz_alpha, lz_beta;
+    int lanczos_tail(const double *v, const double *vp, double *w, int width, int j) {
+        double a = 0.0;
+        for (uint32_t r = 0; r < ld; ++r) a += v[(size_t)r * width] * w[(size_t)r * width];
+        const double bp = j > 0 ? lz_beta[j - 1] : 0.0;
+        double nn = 0.0;
+        for (uint32_t r = 0; r < ld; ++r) {
+            double &x = w[(size_t)r * width];
+            x = x - a * v[(size_t)r * width] - bp * vp[(size_t)r * width];
+            nn += x * x;
+        }
+        const double b = std::sqrt(nn);
+        for (uint32_t r = 0; r < ld; ++r) w[(size_t)r * width] = b > 1e-14 ? w[(size_t)r * width] / b : 0.0;
+        lz_alpha.resize(j + 1);
+        lz_beta.resize(j + 1);
+        lz_alpha[j] = a;
+        lz_beta[j] = b;
+        return 0;
+    }
+    int lanczos_fetch(int steps, std::vector<double> &al, std::vector<double> &be) {
+        al.assign(lz_alpha.begin(), lz_alpha.begin() + steps);
+        be.assign(lz_beta.begin(), lz_beta.begin() + steps);
+        return 0;
+    }
     int rank_update(const double *Q, int kq, int off, int nl, const double *lam) {
         for (uint32_t r = 0; r < ld; ++r)
             for (uint32_t c = 0; c < ld; ++c) {
