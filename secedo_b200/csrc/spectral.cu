@@ -19,6 +19,7 @@
 #include "spectral_host.hpp"
 
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 
 namespace {
@@ -135,6 +136,137 @@ symm_block_kernel(const double *__restrict__ M, uint32_t ld, const double *__res
             }
         }
     }
+}
+
+// ---- the same product with the matrix streamed by the TMA engine (widths <= 32) ---------------------------------
+// The register-prefetch kernel above is latency bound at two CTAs per SM (ncu: 23 % warps active, the first DFMA
+// after every group of loads waits on the long scoreboard, 3.5 TB/s). Here ONE thread per CTA issues bulk copies
+// (cp.async.bulk, 4 KB per row of M) into a ring of TS_STAGES shared-memory stages of TS_K rows, completion through
+// mbarriers, so that ~160 KB per SM are in flight without holding a single register; the 8 compute warps read their
+// 64 rows x B columns from shared memory (conflict-free 16-byte reads for M, broadcasts for X). One CTA per SM,
+// grid = (column tiles of 512) x (splits over K) <= number of SMs.
+constexpr int TS_COLS = 512;  // rows of the output (= columns of the stored rows of M) per CTA
+constexpr int TS_K = 8;       // rows of M per stage
+constexpr int TS_STAGES = 6;
+constexpr int TS_THREADS = 288; // 8 compute warps + 1 producer warp
+
+__device__ __forceinline__ uint32_t sp_smem_u32(const void *p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
+__device__ __forceinline__ void sp_mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void sp_mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void sp_mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void sp_mbar_wait(uint32_t bar, uint32_t parity) {
+    asm volatile(
+            "{\n\t"
+            ".reg .pred p;\n\t"
+            "SP_WAIT_LOOP:\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+            "@p bra SP_WAIT_DONE;\n\t"
+            "bra SP_WAIT_LOOP;\n\t"
+            "SP_WAIT_DONE:\n\t"
+            "}" ::"r"(bar),
+            "r"(parity)
+            : "memory");
+}
+__device__ __forceinline__ void sp_bulk_load(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src),
+                 "r"(bytes), "r"(bar)
+                 : "memory");
+}
+
+template <int B>
+__global__ void __launch_bounds__(TS_THREADS, 1)
+symm_block_tma_kernel(const double *__restrict__ M, uint32_t ld, const double *__restrict__ X, double *__restrict__ partial,
+                      uint32_t k_per_split) {
+    constexpr uint32_t M_BYTES = TS_K * TS_COLS * 8, X_BYTES = TS_K * B * 8, STAGE_BYTES = M_BYTES + X_BYTES;
+    extern __shared__ __align__(128) unsigned char ts_smem[];
+    __shared__ __align__(8) uint64_t bars[2 * TS_STAGES];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t c0 = blockIdx.x * TS_COLS;
+    const uint32_t ncols = min(static_cast<uint32_t>(TS_COLS), ld - c0); // multiple of 64
+    const uint32_t kbeg = blockIdx.y * k_per_split;
+    const uint32_t kend = min(ld, kbeg + k_per_split);
+    const uint32_t n_it = kend > kbeg ? (kend - kbeg) / TS_K : 0;       // ld and k_per_split are multiples of TS_K
+    const uint32_t full0 = sp_smem_u32(bars), empty0 = sp_smem_u32(bars + TS_STAGES), stage0 = sp_smem_u32(ts_smem);
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < TS_STAGES; ++s) {
+            sp_mbar_init(full0 + 8 * s, 1);  // the producer's arrive.expect_tx
+            sp_mbar_init(empty0 + 8 * s, 8); // one arrival per compute warp
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    if (warp == 8) {
+        if (lane == 0) {
+            for (uint32_t it = 0; it < n_it; ++it) {
+                const uint32_t s = it % TS_STAGES, ph = (it / TS_STAGES) & 1u;
+                sp_mbar_wait(empty0 + 8 * s, ph ^ 1u); // passes at once on the first round
+                const uint32_t dst = stage0 + s * STAGE_BYTES, bar = full0 + 8 * s;
+                const uint32_t k0 = kbeg + it * TS_K;
+                sp_mbar_expect_tx(bar, TS_K * ncols * 8 + X_BYTES);
+#pragma unroll
+                for (int u = 0; u < TS_K; ++u) {
+                    sp_bulk_load(dst + u * TS_COLS * 8, M + static_cast<size_t>(k0 + u) * ld + c0, ncols * 8, bar);
+                }
+                sp_bulk_load(dst + M_BYTES, X + static_cast<size_t>(k0) * B, X_BYTES, bar);
+            }
+        }
+        return;
+    }
+    // ---- compute warps: rows c0 + warp * 64 + lane * 2 (+1), all B columns ----
+    const uint32_t rl = warp * 64u + lane * 2u;
+    const bool active = rl < ncols;
+    double acc[2][B];
+#pragma unroll
+    for (int j = 0; j < B; ++j) {
+        acc[0][j] = 0.0;
+        acc[1][j] = 0.0;
+    }
+    for (uint32_t it = 0; it < n_it; ++it) {
+        const uint32_t s = it % TS_STAGES, ph = (it / TS_STAGES) & 1u;
+        sp_mbar_wait(full0 + 8 * s, ph);
+        if (active) {
+            const double *ms = reinterpret_cast<const double *>(ts_smem + s * STAGE_BYTES);
+            const double2 *xs = reinterpret_cast<const double2 *>(ts_smem + s * STAGE_BYTES + M_BYTES);
+#pragma unroll
+            for (int u = 0; u < TS_K; ++u) {
+                const double2 m = *reinterpret_cast<const double2 *>(ms + u * TS_COLS + rl);
+#pragma unroll
+                for (int j = 0; j < B / 2; ++j) {
+                    const double2 x = xs[u * (B / 2) + j];
+                    acc[0][2 * j] = fma(m.x, x.x, acc[0][2 * j]);
+                    acc[0][2 * j + 1] = fma(m.x, x.y, acc[0][2 * j + 1]);
+                    acc[1][2 * j] = fma(m.y, x.x, acc[1][2 * j]);
+                    acc[1][2 * j + 1] = fma(m.y, x.y, acc[1][2 * j + 1]);
+                }
+            }
+        }
+        __syncwarp();
+        if (lane == 0) {
+            sp_mbar_arrive(empty0 + 8 * s);
+        }
+    }
+    if (active) {
+        double *out = partial + (static_cast<size_t>(blockIdx.y) * ld + c0 + rl) * B;
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+            double2 *o = reinterpret_cast<double2 *>(out + static_cast<size_t>(i) * B);
+#pragma unroll
+            for (int j = 0; j < B / 2; ++j) {
+                o[j] = make_double2(acc[i][2 * j], acc[i][2 * j + 1]);
+            }
+        }
+    }
+}
+
+template <int B>
+constexpr size_t ts_smem_bytes() {
+    return static_cast<size_t>(TS_STAGES) * (TS_K * TS_COLS * 8 + TS_K * B * 8);
 }
 
 // out = alpha * sum_s partial[s] + beta * Xin + gamma * W   (element-wise over ld x B, two doubles per thread)
@@ -436,15 +568,24 @@ struct Solver {
     bool time_mv = true;
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> pending;
 
+    bool use_tma(int width) const { return width <= 32 && !no_tma; }
+    bool no_tma = std::getenv("SECEDO_B200_SPECTRAL_NO_TMA") != nullptr;
+    uint32_t grid_x = 1;
+
     int setup(int width) {
-        const int rg = 8 / (width / 8);
-        const uint32_t tiles = (ld + rg * 32 * mv_r(width) - 1) / (rg * 32 * mv_r(width));
-        // two CTAs per SM, ONE wave: splits rounded down so that no second, nearly empty wave is started
-        uint32_t want = std::max(1u, 2u * ctx->sm_count / tiles);
-        const uint32_t kc = mv_kc(width);
-        uint32_t kps = ((ld + want - 1) / want + kc - 1) / kc * kc;
-        k_per_split = kps;
-        n_split = (ld + kps - 1) / kps;
+        if (use_tma(width)) { // one CTA per SM, one wave
+            grid_x = (ld + TS_COLS - 1) / TS_COLS;
+            const uint32_t want = std::max(1u, static_cast<uint32_t>(ctx->sm_count) / grid_x);
+            k_per_split = ((ld + want - 1) / want + TS_K - 1) / TS_K * TS_K;
+        } else {
+            const int rg = 8 / (width / 8);
+            grid_x = (ld + rg * 32 * mv_r(width) - 1) / (rg * 32 * mv_r(width));
+            // two CTAs per SM, ONE wave: splits rounded down so that no second, nearly empty wave is started
+            const uint32_t want = std::max(1u, 2u * ctx->sm_count / grid_x);
+            const uint32_t kc = mv_kc(width);
+            k_per_split = ((ld + want - 1) / want + kc - 1) / kc * kc;
+        }
+        n_split = (ld + k_per_split - 1) / k_per_split;
         return SGPU_OK;
     }
 
@@ -455,20 +596,28 @@ struct Solver {
         if (partial.n < need) {
             SGPU_CUDA(ctx, partial.alloc(need, ctx));
         }
-        const int rg = 8 / (width / 8);
-        dim3 grid((ld + rg * 32 * mv_r(width) - 1) / (rg * 32 * mv_r(width)), n_split);
+        dim3 grid(grid_x, n_split);
         cudaEvent_t e0 = nullptr, e1 = nullptr;
         if (time_mv) {
             SGPU_CUDA(ctx, cudaEventCreate(&e0));
             SGPU_CUDA(ctx, cudaEventCreate(&e1));
             SGPU_CUDA(ctx, cudaEventRecord(e0, st));
         }
-        switch (width) {
-        case 8: SGPU_LAUNCH(ctx, (symm_block_kernel<8, mv_r(8), mv_u(8)><<<grid, MV_THREADS, 0, st>>>(M.p, ld, in, partial.p, k_per_split))); break;
-        case 16: SGPU_LAUNCH(ctx, (symm_block_kernel<16, mv_r(16), mv_u(16)><<<grid, MV_THREADS, 0, st>>>(M.p, ld, in, partial.p, k_per_split))); break;
-        case 32: SGPU_LAUNCH(ctx, (symm_block_kernel<32, mv_r(32), mv_u(32)><<<grid, MV_THREADS, 0, st>>>(M.p, ld, in, partial.p, k_per_split))); break;
-        case 64: SGPU_LAUNCH(ctx, (symm_block_kernel<64, mv_r(64), mv_u(64)><<<grid, MV_THREADS, 0, st>>>(M.p, ld, in, partial.p, k_per_split))); break;
-        default: return sgpu_fail(ctx, SGPU_E_ARG, "block width %d", width);
+        if (use_tma(width)) {
+            switch (width) {
+            case 8: SGPU_LAUNCH(ctx, (symm_block_tma_kernel<8><<<grid, TS_THREADS, ts_smem_bytes<8>(), st>>>(M.p, ld, in, partial.p, k_per_split))); break;
+            case 16: SGPU_LAUNCH(ctx, (symm_block_tma_kernel<16><<<grid, TS_THREADS, ts_smem_bytes<16>(), st>>>(M.p, ld, in, partial.p, k_per_split))); break;
+            case 32: SGPU_LAUNCH(ctx, (symm_block_tma_kernel<32><<<grid, TS_THREADS, ts_smem_bytes<32>(), st>>>(M.p, ld, in, partial.p, k_per_split))); break;
+            default: return sgpu_fail(ctx, SGPU_E_ARG, "block width %d", width);
+            }
+        } else {
+            switch (width) {
+            case 8: SGPU_LAUNCH(ctx, (symm_block_kernel<8, mv_r(8), mv_u(8)><<<grid, MV_THREADS, 0, st>>>(M.p, ld, in, partial.p, k_per_split))); break;
+            case 16: SGPU_LAUNCH(ctx, (symm_block_kernel<16, mv_r(16), mv_u(16)><<<grid, MV_THREADS, 0, st>>>(M.p, ld, in, partial.p, k_per_split))); break;
+            case 32: SGPU_LAUNCH(ctx, (symm_block_kernel<32, mv_r(32), mv_u(32)><<<grid, MV_THREADS, 0, st>>>(M.p, ld, in, partial.p, k_per_split))); break;
+            case 64: SGPU_LAUNCH(ctx, (symm_block_kernel<64, mv_r(64), mv_u(64)><<<grid, MV_THREADS, 0, st>>>(M.p, ld, in, partial.p, k_per_split))); break;
+            default: return sgpu_fail(ctx, SGPU_E_ARG, "block width %d", width);
+            }
         }
         if (time_mv) {
             SGPU_CUDA(ctx, cudaEventRecord(e1, st));
@@ -611,6 +760,17 @@ struct Solver {
 };
 
 
+int sgpu_spectral_attributes(sgpu_ctx *ctx) {
+    static bool done = false;
+    if (!done) {
+        SGPU_CUDA(ctx, cudaFuncSetAttribute(symm_block_tma_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(ts_smem_bytes<8>())));
+        SGPU_CUDA(ctx, cudaFuncSetAttribute(symm_block_tma_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(ts_smem_bytes<16>())));
+        SGPU_CUDA(ctx, cudaFuncSetAttribute(symm_block_tma_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(ts_smem_bytes<32>())));
+        done = true;
+    }
+    return SGPU_OK;
+}
+
 int block_width_for(uint32_t k) {
     const uint32_t want = std::max(2 * k, k + 8);
     return want <= 8 ? 8 : want <= 16 ? 16 : want <= 32 ? 32 : 64;
@@ -629,6 +789,7 @@ int sgpu_spectral_device(sgpu_ctx *ctx, const double *d_A, uint32_t n, uint32_t 
     tol = std::max(tol > 0 ? tol : 1e-10, 1e-13);
     static bool attr_done = false;
     if (!attr_done) {
+        SGPU_TRY(sgpu_spectral_attributes(ctx));
         SGPU_CUDA(ctx, cudaFuncSetAttribute(xr_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * 64 * 64 * 8));
         SGPU_CUDA(ctx, cudaFuncSetAttribute(rank_update_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (32 * 64 + 128 * 65) * 8));
         attr_done = true;
@@ -812,6 +973,7 @@ int sgpu_spectral_matvec_host(sgpu_ctx *ctx, const double *h_M, uint32_t n, int 
     SGPU_CUDA(ctx, cudaMemcpyAsync(S.M.p, pm.data(), pm.size() * sizeof(double), cudaMemcpyHostToDevice, st));
     SGPU_CUDA(ctx, cudaMemcpyAsync(X.p, px.data(), px.size() * sizeof(double), cudaMemcpyHostToDevice, st));
     SGPU_CUDA(ctx, cudaMemcpyAsync(W.p, pw.data(), pw.size() * sizeof(double), cudaMemcpyHostToDevice, st));
+    SGPU_TRY(sgpu_spectral_attributes(ctx));
     SGPU_TRY(S.mv(width, O.p, X.p, alpha, beta, gamma, W.p));
     SGPU_CUDA(ctx, cudaMemcpyAsync(px.data(), O.p, px.size() * sizeof(double), cudaMemcpyDeviceToHost, st));
     SGPU_CUDA(ctx, cudaStreamSynchronize(st));

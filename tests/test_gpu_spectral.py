@@ -14,10 +14,14 @@ pytestmark = pytest.mark.gpu
 TOL = 1e-10
 
 
+@pytest.mark.parametrize("kernel", ["tma", "registers"])
 @pytest.mark.parametrize("width", [8, 16, 32, 64])
-@pytest.mark.parametrize("n", [70, 257, 1000])
-def test_block_product_kernel(gpu_ctx, n, width):
-    """alpha M X + beta X + gamma W of the solver's only O(N^2) kernel (split over K, fixed summation order)"""
+@pytest.mark.parametrize("n", [70, 257, 1000, 2100])
+def test_block_product_kernel(gpu_ctx, n, width, kernel, monkeypatch):
+    """alpha M X + beta X + gamma W of the solver's only O(N^2) kernel (split over K, fixed summation order): the
+    TMA-streamed kernel (widths <= 32) and the register-prefetch kernel (width 64, or all widths on request)"""
+    if kernel == "registers":
+        monkeypatch.setenv("SECEDO_B200_SPECTRAL_NO_TMA", "1")
     rng = np.random.default_rng(n + width)
     m = rng.normal(size=(n, n))
     m = m + m.T
