@@ -191,6 +191,20 @@ int sgpu_similarity_finalize(sgpu_ctx *ctx, sgpu_counts *c, uint32_t max_fragmen
 int sgpu_log_probs(sgpu_ctx *ctx, double mutation_rate, double homozygous_rate, double seq_error_rate,
                    uint32_t max_fragment_length, uint32_t n, double *ls, double *ld);
 
+/* ---- expectation maximisation (expectation_maximization.cpp) --------------------------------------- */
+/* expectation_maximization() (expectation_maximization.hpp:27-31, body expectation_maximization.cpp:131-160) on a
+ * filtered pileup that already lives on the device: prob_cluster_b (n_cells doubles on the host) holds the probability
+ * of every cell to belong to the second cluster and is refined in place until no entry moves by 1e-2 or more
+ * (max_iterations = 0) or for at most max_iterations rounds. As in the reference the probability of an entry's cell is
+ * looked up with the group id itself and the log likelihood is accumulated at id_to_pos[group id]
+ * (expectation_maximization.cpp:24 vs :88-89) and the log likelihoods keep accumulating over the iterations
+ * (:136-137). A group id or id_to_pos[group id] >= n_cells (out-of-range read / std::out_of_range in the reference)
+ * is SGPU_E_CELL_RANGE. The sums over a cell's entries are formed in 2^-36 fixed point (order independent:
+ * results are bit-reproducible); against the reference's sequential fp64 sums the probabilities agree to 1e-6. */
+int sgpu_expectation_maximization(sgpu_ctx *ctx, const sgpu_pileup *filtered, const uint32_t *id_to_pos, uint32_t n_groups,
+                                  double theta, double *prob_cluster_b, uint32_t n_cells, uint32_t max_iterations,
+                                  uint32_t *iterations, float *ms);
+
 /* ---- Laplacian and its leading eigenpairs (spectral_clustering.cpp) ------------------------------- */
 typedef struct sgpu_spectral_stats {
     uint32_t outer_iterations; /* Rayleigh-Ritz steps */

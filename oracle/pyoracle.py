@@ -69,6 +69,7 @@ def oracle_lib():
         _oracle.orc_log_probs.restype = C.c_int
         _oracle.orc_normalize.restype = C.c_int
         _oracle.orc_laplacian.restype = C.c_int
+        _oracle.orc_expectation_maximization.restype = C.c_int
         _oracle.orc_is_significant.restype = C.c_int
     return _oracle
 
@@ -85,6 +86,8 @@ def ref_lib():
         _ref.ref_similarity.restype = C.c_double
         _ref.ref_read_pileup_text.restype = C.c_uint32
         _ref.ref_omp_max_threads.restype = C.c_int
+        if hasattr(_ref, "ref_expectation_maximization"):
+            _ref.ref_expectation_maximization.restype = C.c_double
     return _ref
 
 
@@ -161,6 +164,31 @@ def normalize(m, normalization: str) -> np.ndarray:
     if rc:
         raise ValueError("invalid normalization")
     return m
+
+
+def expectation_maximization(p, id_to_pos, theta: float, prob_cluster_b, max_iterations: int = 0):
+    """expectation_maximization() restated (oracle/secedo_oracle.c). Returns (prob_cluster_b, iterations)."""
+    prob = np.array(prob_cluster_b, dtype=np.float64, order="C")
+    m = np.ascontiguousarray(id_to_pos, np.uint32)
+    it = C.c_uint32(0)
+    rc = oracle_lib().orc_expectation_maximization(
+        C.c_uint32(len(p.chr_ptr) - 1), _p(p.chr_ptr, _u64p), _p(p.row_ptr, _u64p), _p(p.gid_base, _u16p), _p(m, _u32p),
+        C.c_uint32(m.size), C.c_double(theta), C.c_uint32(prob.size), _p(prob, _f64p), C.c_uint32(max_iterations), C.byref(it))
+    if rc:
+        raise ValueError("group id outside prob_cluster_b / id_to_pos")
+    return prob, int(it.value)
+
+
+def ref_expectation_maximization(p, id_to_pos, theta: float, prob_cluster_b):
+    """the compiled reference's expectation_maximization; returns (prob_cluster_b, seconds)"""
+    prob = np.array(prob_cluster_b, dtype=np.float64, order="C")
+    m = np.ascontiguousarray(id_to_pos, np.uint32)
+    with _quiet_stdout():
+        secs = ref_lib().ref_expectation_maximization(
+            C.c_uint32(len(p.chr_ptr) - 1), _p(p.chr_ptr, _u64p), _p(p.row_ptr, _u64p), _p(p.position, _u32p),
+            _p(p.read_id, _u32p), _p(p.gid_base, _u16p), _p(m, _u32p), C.c_uint32(m.size), C.c_double(theta),
+            C.c_uint32(prob.size), _p(prob, _f64p))
+    return prob, float(secs)
 
 
 def laplacian(a) -> np.ndarray:

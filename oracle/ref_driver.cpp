@@ -18,6 +18,7 @@
 
 #include "similarity_matrix.cpp" // the reference TU itself (path given with -I$SECEDO_REF)
 
+#include "expectation_maximization.hpp"
 #include "util/is_significant.hpp"
 #include "util/pileup_reader.hpp"
 
@@ -225,6 +226,28 @@ uint32_t ref_read_pileup(const char *fname,
     g_filtered.clear();
     g_filtered.push_back(std::move(pds));
     return n_cells;
+}
+
+/** expectation_maximization (expectation_maximization.cpp:131-160); prob_cluster_b updated in place. Seconds. */
+double ref_expectation_maximization(uint32_t n_chr,
+                                    const uint64_t *chr_ptr,
+                                    const uint64_t *row_ptr,
+                                    const uint32_t *position,
+                                    const uint32_t *read_id,
+                                    const uint16_t *gid_base,
+                                    const uint32_t *id_to_pos,
+                                    uint32_t n_groups,
+                                    double theta,
+                                    uint32_t n_cells,
+                                    double *prob_cluster_b) {
+    auto pds = from_csr(n_chr, chr_ptr, row_ptr, position, read_id, gid_base);
+    std::vector<uint32_t> map(id_to_pos, id_to_pos + n_groups);
+    std::vector<double> prob(prob_cluster_b, prob_cluster_b + n_cells);
+    auto t0 = std::chrono::steady_clock::now();
+    expectation_maximization(pds, map, 1, theta, &prob);
+    auto t1 = std::chrono::steady_clock::now();
+    std::memcpy(prob_cluster_b, prob.data(), n_cells * sizeof(double));
+    return std::chrono::duration<double>(t1 - t0).count();
 }
 
 int ref_omp_max_threads() {

@@ -739,3 +739,105 @@ int orc_laplacian(uint32_t n, const double *a, double *out) {
     free(diag);
     return 0;
 }
+
+/* ------------------------------------------------------------------------------------------ */
+/* Expectation maximisation                                                */
+/* ------------------------------------------------------------------------------------------ */
+
+static void orc_cluster_center(const uint16_t *gb, uint64_t n, const double *prob, double theta, double *center) {
+    /* expectation_maximization.cpp:19-40; prob is indexed by the GROUP id (:24), not by id_to_pos */
+    center[0] = center[1] = center[2] = center[3] = 0;
+    for (uint64_t i = 0; i < n; ++i) {
+        center[gb[i] & 3] += prob[gb[i] >> 2];
+    }
+    double s = center[0] + center[1] + center[2] + center[3];
+    if (s == 0) {
+        center[0] = center[1] = center[2] = center[3] = log(0.25);
+        return;
+    }
+    for (int b = 0; b < 4; ++b) {
+        center[b] = center[b] / s > theta ? center[b] / s : theta;
+    }
+    s = center[0] + center[1] + center[2] + center[3];
+    for (int b = 0; b < 4; ++b) {
+        center[b] = log(center[b] / s);
+    }
+}
+
+int orc_expectation_maximization(uint32_t n_chr, const uint64_t *chr_ptr, const uint64_t *row_ptr, const uint16_t *gid_base,
+                                 const uint32_t *id_to_pos, uint32_t n_groups, double theta, uint32_t n_cells,
+                                 double *prob_cluster_b, uint32_t max_iterations, uint32_t *iterations) {
+    /* expectation_maximization.cpp:131-160: the log likelihoods are NOT reset between iterations (:136-137 are
+     * outside the loop), per-chromosome sums are added chromosome by chromosome (:146-151) */
+    double *lla = (double *)calloc(n_cells ? n_cells : 1, sizeof(double));
+    double *llb = (double *)calloc(n_cells ? n_cells : 1, sizeof(double));
+    double *ca = (double *)calloc(n_cells ? n_cells : 1, sizeof(double));
+    double *cb = (double *)calloc(n_cells ? n_cells : 1, sizeof(double));
+    double *pa = (double *)calloc(n_cells ? n_cells : 1, sizeof(double));
+    uint32_t it = 0;
+    int rc = 0, done = 0;
+    while (!done && rc == 0) {
+        for (uint32_t c = 0; c < n_chr && rc == 0; ++c) {
+            for (uint32_t i = 0; i < n_cells; ++i) { /* maximization_step :59-92 */
+                pa[i] = 1 - prob_cluster_b[i];
+                ca[i] = cb[i] = 0;
+            }
+            for (uint64_t l = chr_ptr[c]; l < chr_ptr[c + 1] && rc == 0; ++l) {
+                const uint16_t *gb = gid_base + row_ptr[l];
+                uint64_t n = row_ptr[l + 1] - row_ptr[l];
+                for (uint64_t i = 0; i < n; ++i) {
+                    uint32_t g = gb[i] >> 2;
+                    if (g >= n_cells || g >= n_groups || id_to_pos[g] >= n_cells) {
+                        rc = -1; /* out-of-range read / std::out_of_range in the reference */
+                        break;
+                    }
+                }
+                if (rc) {
+                    break;
+                }
+                double center_a[4], center_b[4];
+                orc_cluster_center(gb, n, pa, theta, center_a);
+                orc_cluster_center(gb, n, prob_cluster_b, theta, center_b);
+                for (uint64_t i = 0; i < n; ++i) {
+                    ca[id_to_pos[gb[i] >> 2]] += center_a[gb[i] & 3];
+                    cb[id_to_pos[gb[i] >> 2]] += center_b[gb[i] & 3];
+                }
+            }
+            for (uint32_t i = 0; i < n_cells; ++i) {
+                lla[i] += ca[i];
+                llb[i] += cb[i];
+            }
+        }
+        if (rc) {
+            break;
+        }
+        /* expectation_step :109-129 */
+        double sum = 0;
+        for (uint32_t i = 0; i < n_cells; ++i) {
+            sum += prob_cluster_b[i];
+        }
+        double prior_b = sum / n_cells, prior_a = 1 - prior_b;
+        done = 1;
+        for (uint32_t i = 0; i < n_cells; ++i) {
+            double d = llb[i] - lla[i];
+            d = d < -100. ? -100. : (d > 100. ? 100. : d);
+            double odds = exp(d);
+            double prob = 1 - 1 / (1 + odds * prior_b / prior_a);
+            done &= fabs(prob - prob_cluster_b[i]) < 1e-2;
+            prob_cluster_b[i] = prob;
+        }
+        ++it;
+        if (max_iterations && it >= max_iterations) {
+            break;
+        }
+    }
+    if (iterations) {
+        *iterations = it;
+    }
+    free(lla);
+    free(llb);
+    free(ca);
+    free(cb);
+    free(pa);
+    return rc;
+}

@@ -99,6 +99,13 @@ int orc_similarity(uint32_t n_chr,
 /* similarity_matrix.cpp:271-293 on a row-major n*n matrix, in place. */
 int orc_normalize(int normalization, uint32_t n, double *m);
 
+/* expectation_maximization(), expectation_maximization.cpp:131-160 (with cluster_center :19-40, maximization_step
+ * :59-92, expectation_step :109-129), on the CSR form of the filtered pileup. prob_cluster_b (n_cells) is updated in
+ * place. max_iterations = 0: until convergence like the reference. Returns -1 where the reference reads out of range. */
+int orc_expectation_maximization(uint32_t n_chr, const uint64_t *chr_ptr, const uint64_t *row_ptr, const uint16_t *gid_base,
+                                 const uint32_t *id_to_pos, uint32_t n_groups, double theta, uint32_t n_cells,
+                                 double *prob_cluster_b, uint32_t max_iterations, uint32_t *iterations);
+
 /* laplacian(), spectral_clustering.cpp:33-52, on row-major n*n matrices. */
 int orc_laplacian(uint32_t n, const double *a, double *out);
 

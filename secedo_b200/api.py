@@ -395,6 +395,27 @@ def log_probs(mutation_rate: float, homozygous_rate: float, seq_error_rate: floa
     return ls, ld
 
 
+def expectation_maximization(pos_data: PosDataLike, cell_id_to_cell_pos: Sequence[int], num_threads: int, theta: float,
+                             prob_cluster_b: Sequence[float], *, ctx: Optional[Context] = None, max_iterations: int = 0,
+                             return_stats: bool = False):
+    """``expectation_maximization`` (expectation_maximization.hpp:27-31): refines the probability of every cell to
+    belong to the second cluster. The reference updates ``prob_cluster_b`` in place; here the refined vector is
+    returned. ``num_threads`` is unused, as in the reference (expectation_maximization.cpp:133)."""
+    del num_threads
+    ctx = ctx or default_context()
+    m = np.ascontiguousarray(cell_id_to_cell_pos, np.uint32)
+    prob = np.array(prob_cluster_b, dtype=np.float64, order="C")
+    dp, owned = _staged(ctx, pos_data)
+    it, ms = C.c_uint32(0), C.c_float(0)
+    try:
+        ctx.check(ctx._lib.sgpu_expectation_maximization(ctx._h, dp._h, _ptr(m) if m.size else None, m.size, float(theta),
+                                                         _ptr(prob), prob.size, int(max_iterations), C.byref(it), C.byref(ms)))
+    finally:
+        if owned:
+            dp.free()
+    return (prob, {"iterations": int(it.value), "ms": float(ms.value)}) if return_stats else prob
+
+
 def laplacian(a: np.ndarray, ctx: Optional[Context] = None) -> np.ndarray:
     """``laplacian`` (spectral_clustering.cpp:33-52): I - D^-1/2 A D^-1/2 of a symmetric matrix with zero diagonal."""
     ctx = ctx or default_context()
@@ -434,5 +455,5 @@ def spectral_matvec(m: np.ndarray, x: np.ndarray, w: Optional[np.ndarray] = None
     return out
 
 
-__all__ = ["Context", "DevicePileup", "Filter", "Counts", "compute_similarity_matrix", "log_probs", "default_context", "laplacian", "spectral_embedding",
+__all__ = ["Context", "DevicePileup", "Filter", "Counts", "compute_similarity_matrix", "log_probs", "default_context", "expectation_maximization", "laplacian", "spectral_embedding",
            "NO_POS", "SgpuError"]

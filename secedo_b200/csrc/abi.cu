@@ -679,6 +679,16 @@ int sgpu_log_probs(sgpu_ctx *ctx, double mutation_rate, double homozygous_rate, 
     return sgpu_log_probs_impl(ctx, mutation_rate, homozygous_rate, seq_error_rate, max_fragment_length, n, ls, ld);
 }
 
+int sgpu_expectation_maximization(sgpu_ctx *ctx, const sgpu_pileup *filtered, const uint32_t *id_to_pos, uint32_t n_groups,
+                                  double theta, double *prob_cluster_b, uint32_t n_cells, uint32_t max_iterations,
+                                  uint32_t *iterations, float *ms) {
+    SGPU_CUDA(ctx, cudaSetDevice(ctx->device));
+    if (!filtered) {
+        return sgpu_fail(ctx, SGPU_E_ARG, "expectation_maximization: no pileup");
+    }
+    return sgpu_em_impl(ctx, filtered, id_to_pos, n_groups, theta, prob_cluster_b, n_cells, max_iterations, iterations, ms);
+}
+
 // ---- Laplacian + leading eigenpairs (spectral.cu) ----
 static int upload_matrix(sgpu_ctx *ctx, const double *h, uint32_t n, DevBuf<double> &d) {
     if (!h || n == 0) {

@@ -261,6 +261,10 @@ int sgpu_log_probs_impl(sgpu_ctx *ctx, double eps, double h, double theta, uint3
 int sgpu_epilogue(sgpu_ctx *ctx, sgpu_counts *c, uint32_t L, double eps, double h, double theta,
                   int normalization, double *h_out, double **d_keep = nullptr);
 
+// em.cu
+int sgpu_em_impl(sgpu_ctx *ctx, const sgpu_pileup *p, const uint32_t *h_id_to_pos, uint32_t n_groups, double theta,
+                 double *h_prob_b, uint32_t n_cells, uint32_t max_iterations, uint32_t *iterations, float *ms_total);
+
 // spectral.cu
 int sgpu_spectral_device(sgpu_ctx *ctx, const double *d_A, uint32_t n, uint32_t k, double tol, double *h_evals,
                          double *h_evecs, sgpu_spectral_stats *stats);

@@ -5,15 +5,17 @@
 //   Filter::Filter, Filter::is_significant (x2), Filter::filter, Filter::log_fact
 //                                   replaces util/is_significant.cpp:48-193
 //   computeSimilarityMatrix         replaces similarity_matrix.cpp:295-433
+//   expectation_maximization        replaces expectation_maximization.cpp:131-160
 //
 // Build inside SECEDO:  add this file INSTEAD OF util/is_significant.cpp and similarity_matrix.cpp to
-// the `util` / `similarity_matrix` targets, add <repo>/include to the include path and link
+// the `util` / `similarity_matrix` targets (and INSTEAD OF expectation_maximization.cpp), add <repo>/include to the include path and link
 // libsecedo_b200.so. Build stand-alone (tests): -Isecedo_b200/host/compat.
 //
 // Same argument meaning and error behaviour as the reference: an unknown normalization throws
 // std::logic_error("Invalid normalization: ...") (similarity_matrix.cpp:264); every other failure
 // prints the message and exits with status 1 (the reference logs through spdlog and calls
 // std::exit(1)). There is no CPU fallback: without a B200 the first call fails.
+#include "expectation_maximization.hpp"
 #include "similarity_matrix.hpp"
 #include "util/is_significant.hpp"
 
@@ -187,4 +189,17 @@ Matd computeSimilarityMatrix(const std::vector<std::vector<PosData>> &pos_data, 
                           num_threads /* selects the reference's tail cutoff */, norm, SGPU_PATH_AUTO, result.data(), nullptr));
     sgpu_pileup_free(ctx, p);
     return result;
+}
+
+// ---- expectation maximisation -------------------------------------------------------------------------------
+
+void expectation_maximization(const std::vector<std::vector<PosData>> &pos_data, const std::vector<uint32_t> &cell_id_to_cell_pos,
+                              uint32_t num_threads, double theta, std::vector<double> *prob_cluster_b) {
+    (void)num_threads; // unused by the reference as well (expectation_maximization.cpp:133)
+    sgpu_ctx *ctx = context();
+    const Csr csr(pos_data);
+    sgpu_pileup *p = csr.upload();
+    check(sgpu_expectation_maximization(ctx, p, cell_id_to_cell_pos.data(), static_cast<uint32_t>(cell_id_to_cell_pos.size()), theta,
+                                        prob_cluster_b->data(), static_cast<uint32_t>(prob_cluster_b->size()), 0, nullptr, nullptr));
+    sgpu_pileup_free(ctx, p);
 }

@@ -69,8 +69,52 @@ def save_similarity_case(name, p, num_cells, L, gmap, eps, h, theta, threads, no
     print(name, "loci", p.n_loci, "entries", p.n_entries, "cells", num_cells)
 
 
+def em_cases():
+    """(name, filtered pileup, id_to_pos, theta, initial prob_cluster_b) for the EM refinement"""
+    cases = []
+    cfg = SynthConfig(n_cells=120, coverage=0.5, n_loci=700, n_chr=3, n_clones=2, p_multi=0.1, p_mate=0.05, theta=0.01, seed=41)
+    p = make_pileup(cfg)
+    ident = np.arange(cfg.n_cells, dtype=np.uint32)
+    rf, _, _ = po.ref_filter(p, ident, 0.01, 4, 1)
+    f = Pileup(rf.chr_ptr, rf.row_ptr, rf.position, rf.read_id, rf.gid_base)
+    rng = np.random.default_rng(9)
+    # a spectral-clustering-like start: hard 0/1 labels along the first half / second half, 15 % of them wrong
+    start = (np.arange(cfg.n_cells) >= cfg.n_cells // 2).astype(np.float64)
+    flip = rng.random(cfg.n_cells) < 0.15
+    start[flip] = 1 - start[flip]
+    cases.append(("hard_labels", f, ident, 0.01, start))
+    cases.append(("soft_labels", f, ident, 0.001, np.clip(start * 0.6 + 0.2 + rng.normal(0, 0.05, cfg.n_cells), 0.01, 0.99)))
+    # the group-id / id_to_pos asymmetry of the reference (expectation_maximization.cpp:24 vs :88-89): cells 0..59
+    # only, the likelihoods accumulated at a permuted position
+    sub = np.full(cfg.n_cells, NO_POS, np.uint32)
+    sub[:60] = rng.permutation(60).astype(np.uint32)
+    rf, _, _ = po.ref_filter(p, sub, 0.01, 4, 1)
+    fs = Pileup(rf.chr_ptr, rf.row_ptr, rf.position, rf.read_id, rf.gid_base)
+    cases.append(("permuted_subcluster", fs, sub, 0.01, rng.uniform(0.3, 0.7, 60)))
+    return cases
+
+
+def make_em():
+    out = {"names": []}
+    for name, f, m, theta, start in em_cases():
+        final, _ = po.ref_expectation_maximization(f, m, theta, start)
+        mine, it = po.expectation_maximization(f, m, theta, start)
+        assert np.array_equal(final, mine), name  # the restatement follows the reference's summation order exactly
+        out["names"].append(name)
+        for k, v in dict(chr_ptr=f.chr_ptr, row_ptr=f.row_ptr, position=f.position, read_id=f.read_id, gid_base=f.gid_base,
+                         id_to_pos=m, theta=theta, start=start, final=final, iterations=it).items():
+            out[f"{name}_{k}"] = v
+        print("em", name, "loci", f.n_loci, "entries", f.n_entries, "iterations", it, "in b:", int((final > 0.5).sum()),
+              "undecided:", int(((final > 0.05) & (final < 0.95)).sum()))
+    out["names"] = np.array(out["names"])
+    np.savez_compressed(os.path.join(OUT, "em.npz"), **out)
+
+
 def main():
     assert po.have_ref(), "build oracle/_ref first: make -C oracle ref"
+    if "--only-em" in sys.argv:
+        return make_em()
+    make_em()
     tmp = tempfile.mkdtemp()
 
     # ---- the reference's text fixtures, read by the reference's own reader ------------------------
