@@ -199,7 +199,7 @@ int sgpu_log_probs(sgpu_ctx *ctx, double mutation_rate, double homozygous_rate, 
  * looked up with the group id itself and the log likelihood is accumulated at id_to_pos[group id]
  * (expectation_maximization.cpp:24 vs :88-89) and the log likelihoods keep accumulating over the iterations
  * (:136-137). A group id or id_to_pos[group id] >= n_cells (out-of-range read / std::out_of_range in the reference)
- * is SGPU_E_CELL_RANGE. The sums over a cell's entries are formed in 2^-36 fixed point (order independent:
+ * is SGPU_E_CELL_RANGE. The sums over a cell's entries are formed in 2^-32 fixed point (order independent:
  * results are bit-reproducible); against the reference's sequential fp64 sums the probabilities agree to 1e-6. */
 int sgpu_expectation_maximization(sgpu_ctx *ctx, const sgpu_pileup *filtered, const uint32_t *id_to_pos, uint32_t n_groups,
                                   double theta, double *prob_cluster_b, uint32_t n_cells, uint32_t max_iterations,

@@ -7,11 +7,16 @@
 // entry's cell), its clamped / renormalised logarithm, and then per entry ll_a[cell] += centre_a[base],
 // ll_b[cell] += centre_b[base]; the E step is O(cells).
 //
-// Here: one WARP per locus (loci of the path have ~10^2..10^4 entries), 8 warps per CTA, each CTA owns a contiguous
-// chunk of loci and accumulates the per-cell log likelihoods in SHARED memory as 64-bit fixed point (scale 2^36,
-// native integer shared-memory atomics, order independent -> the result is deterministic), converted and added to a
-// per-CTA global partial row after every chunk; the E-step kernel adds the partial rows in fixed order. The pass over
-// the entries is read twice by the same warp (second time from L1/L2).
+// Here: one WARP per locus (loci of the path have ~10^2..10^4 entries), 8 warps per CTA, grid-stride over the loci.
+// The per-cell log likelihoods of one iteration are accumulated as 64-bit FIXED POINT (scale 2^32) with global
+// integer reductions (RED.ADD.64, resolved in L2: 16 bytes per cell, always resident): integer addition is order
+// independent, so the result is bit-reproducible, and no shared memory is needed, which leaves room for 40 warps per
+// SM to hide the two dependent gathers per entry (probability of the entry's cell, position of its cell). A first
+// version with per-CTA shared-memory accumulators was 10 x slower: 64-bit shared-memory atomics compile to a
+// compare-and-swap loop (ATOMS.CAST.SPIN) and 128 KB of accumulators allow only 8 warps per SM. Quantisation 2^-33 per
+// term, i.e. below the rounding of the reference's own running fp64 sums (ulp of ~10^7 is 2 10^-9); |term| < 2^6 and
+// up to 2^25 entries of one cell per iteration fit in 63 bits. The E-step kernel converts and adds to the running
+// log likelihoods. Every entry is read twice by the same warp (second time from L1/L2).
 // Quirks kept: the probability is looked up with the GROUP id, the likelihood is accumulated at id_to_pos[group]
 // (:24 vs :88-89); the log likelihoods are not reset between iterations (:136-137); sum == 0 -> log(1/4) (:29-31).
 #include "common.cuh"
@@ -23,9 +28,7 @@ namespace {
 
 constexpr int EM_WARPS = 8;
 constexpr int EM_THREADS = EM_WARPS * 32;
-constexpr uint32_t EM_CHUNK_LOCI = 4096;  // most loci per CTA between two flushes (bounds the fixed-point sums: 2^20 entries
-                                          // of one cell if a cell has up to 256 reads at a locus)
-constexpr double EM_FIX = 68719476736.0;  // 2^36: |term| < 2^6 -> < 2^42 per entry, < 2^62 after 2^20 entries of one cell
+constexpr double EM_FIX = 4294967296.0; // 2^32
 
 __device__ __forceinline__ double warp_sum(double v) {
 #pragma unroll
@@ -35,103 +38,84 @@ __device__ __forceinline__ double warp_sum(double v) {
     return v;
 }
 
-// acc: [2][n_cells] int64 in shared memory (USE_SMEM) or global memory (cells do not fit)
-template <bool USE_SMEM>
+// acc: [2][n_cells] int64, zero at launch
 __global__ void __launch_bounds__(EM_THREADS)
 em_mstep_kernel(const uint64_t *__restrict__ row_ptr, const uint16_t *__restrict__ gid_base, uint64_t n_loci,
                 const double *__restrict__ prob_b, const uint32_t *__restrict__ id_to_pos, uint32_t n_cells, double theta,
-                uint32_t n_chunks, uint32_t chunk_loci, double *__restrict__ partial /* [gridDim.x][2][n_cells] */,
-                unsigned long long *__restrict__ gacc /* [gridDim.x][2][n_cells], !USE_SMEM */) {
-    extern __shared__ unsigned long long em_smem[];
-    unsigned long long *acc = USE_SMEM ? em_smem : gacc + static_cast<size_t>(blockIdx.x) * 2 * n_cells;
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    double *mine = partial + static_cast<size_t>(blockIdx.x) * 2 * n_cells;
-    for (uint32_t i = threadIdx.x; i < 2 * n_cells; i += EM_THREADS) {
-        mine[i] = 0.0;
-        acc[i] = 0ull;
-    }
-    __syncthreads();
-    for (uint32_t chunk = blockIdx.x; chunk < n_chunks; chunk += gridDim.x) {
-        const uint64_t l0 = static_cast<uint64_t>(chunk) * chunk_loci;
-        const uint64_t l1 = min(n_loci, l0 + chunk_loci);
-        for (uint64_t l = l0 + warp; l < l1; l += EM_WARPS) {
-            const uint64_t e0 = row_ptr[l], e1 = row_ptr[l + 1];
-            // weighted base counts of cluster b and of all cells: centre_a = total - centre_b would lose accuracy
-            // when a cluster is tiny, so both are summed (a with 1 - p like the reference, :66-69)
-            double sa[4] = { 0, 0, 0, 0 }, sb[4] = { 0, 0, 0, 0 };
-            for (uint64_t e = e0 + lane; e < e1; e += 32) {
-                const uint32_t gb = gid_base[e];
-                const double pb = prob_b[gb >> 2];
-                const double pa = 1.0 - pb;
-#pragma unroll
-                for (int b = 0; b < 4; ++b) {
-                    const bool hit = (gb & 3u) == static_cast<uint32_t>(b);
-                    sa[b] += hit ? pa : 0.0;
-                    sb[b] += hit ? pb : 0.0;
-                }
-            }
-            double ca[4], cb[4];
+                unsigned long long *__restrict__ acc) {
+    const int lane = threadIdx.x & 31;
+    const uint64_t warp0 = (static_cast<uint64_t>(blockIdx.x) * EM_THREADS + threadIdx.x) >> 5;
+    const uint64_t n_warps = (static_cast<uint64_t>(gridDim.x) * EM_THREADS) >> 5;
+    for (uint64_t l = warp0; l < n_loci; l += n_warps) {
+        const uint64_t e0 = row_ptr[l], e1 = row_ptr[l + 1];
+        // weighted base counts of both clusters (a with 1 - p like the reference, :66-69)
+        double sa[4] = { 0, 0, 0, 0 }, sb[4] = { 0, 0, 0, 0 };
+#pragma unroll 4
+        for (uint64_t e = e0 + lane; e < e1; e += 32) {
+            const uint32_t gb = gid_base[e];
+            const double pb = prob_b[gb >> 2];
+            const double pa = 1.0 - pb;
 #pragma unroll
             for (int b = 0; b < 4; ++b) {
-                ca[b] = warp_sum(sa[b]);
-                cb[b] = warp_sum(sb[b]);
+                const bool hit = (gb & 3u) == static_cast<uint32_t>(b);
+                sa[b] += hit ? pa : 0.0;
+                sb[b] += hit ? pb : 0.0;
             }
-            // lanes 0..3: centre a of base `lane`; lanes 4..7: centre b (cluster_center :27-38)
-            const bool is_b = (lane & 4) != 0;
-            const double c0 = is_b ? cb[0] : ca[0], c1 = is_b ? cb[1] : ca[1], c2 = is_b ? cb[2] : ca[2], c3 = is_b ? cb[3] : ca[3];
-            const double s = c0 + c1 + c2 + c3;
-            double lg;
-            if (s == 0.0) {
-                lg = log(0.25);
-            } else {
-                const double n0 = c0 / s > theta ? c0 / s : theta, n1 = c1 / s > theta ? c1 / s : theta;
-                const double n2 = c2 / s > theta ? c2 / s : theta, n3 = c3 / s > theta ? c3 / s : theta;
-                const double s2 = n0 + n1 + n2 + n3;
-                const int bsel = lane & 3;
-                const double v = bsel == 0 ? n0 : bsel == 1 ? n1 : bsel == 2 ? n2 : n3;
-                lg = log(v / s2);
-            }
-            const long long fx = __double2ll_rn(lg * EM_FIX);
-            long long ta[4], tb[4];
+        }
+        double ca[4], cb[4];
 #pragma unroll
-            for (int b = 0; b < 4; ++b) {
-                ta[b] = __shfl_sync(0xFFFFFFFFu, fx, b);
-                tb[b] = __shfl_sync(0xFFFFFFFFu, fx, 4 + b);
-            }
-            for (uint64_t e = e0 + lane; e < e1; e += 32) {
-                const uint32_t gb = gid_base[e];
-                const uint32_t cell = id_to_pos[gb >> 2];
-                const int b = gb & 3;
-                const long long va = b == 0 ? ta[0] : b == 1 ? ta[1] : b == 2 ? ta[2] : ta[3];
-                const long long vb = b == 0 ? tb[0] : b == 1 ? tb[1] : b == 2 ? tb[2] : tb[3];
-                atomicAdd(acc + cell, static_cast<unsigned long long>(va));
-                atomicAdd(acc + n_cells + cell, static_cast<unsigned long long>(vb));
-            }
+        for (int b = 0; b < 4; ++b) {
+            ca[b] = warp_sum(sa[b]);
+            cb[b] = warp_sum(sb[b]);
         }
-        __syncthreads();
-        for (uint32_t i = threadIdx.x; i < 2 * n_cells; i += EM_THREADS) {
-            mine[i] += static_cast<double>(static_cast<long long>(acc[i])) * (1.0 / EM_FIX);
-            acc[i] = 0ull;
+        // lanes 0..3: centre a of base `lane`; lanes 4..7: centre b (cluster_center :27-38)
+        const bool is_b = (lane & 4) != 0;
+        const double c0 = is_b ? cb[0] : ca[0], c1 = is_b ? cb[1] : ca[1], c2 = is_b ? cb[2] : ca[2], c3 = is_b ? cb[3] : ca[3];
+        const double s = c0 + c1 + c2 + c3;
+        double lg;
+        if (s == 0.0) {
+            lg = log(0.25);
+        } else {
+            const double n0 = c0 / s > theta ? c0 / s : theta, n1 = c1 / s > theta ? c1 / s : theta;
+            const double n2 = c2 / s > theta ? c2 / s : theta, n3 = c3 / s > theta ? c3 / s : theta;
+            const double s2 = n0 + n1 + n2 + n3;
+            const int bsel = lane & 3;
+            const double v = bsel == 0 ? n0 : bsel == 1 ? n1 : bsel == 2 ? n2 : n3;
+            lg = log(v / s2);
         }
-        __syncthreads();
+        const long long fx = __double2ll_rn(lg * EM_FIX);
+        long long ta[4], tb[4];
+#pragma unroll
+        for (int b = 0; b < 4; ++b) {
+            ta[b] = __shfl_sync(0xFFFFFFFFu, fx, b);
+            tb[b] = __shfl_sync(0xFFFFFFFFu, fx, 4 + b);
+        }
+#pragma unroll 4
+        for (uint64_t e = e0 + lane; e < e1; e += 32) {
+            const uint32_t gb = gid_base[e];
+            const uint32_t cell = id_to_pos[gb >> 2];
+            const int b = gb & 3;
+            const long long va = b == 0 ? ta[0] : b == 1 ? ta[1] : b == 2 ? ta[2] : ta[3];
+            const long long vb = b == 0 ? tb[0] : b == 1 ? tb[1] : b == 2 ? tb[2] : tb[3];
+            atomicAdd(acc + cell, static_cast<unsigned long long>(va));
+            atomicAdd(acc + n_cells + cell, static_cast<unsigned long long>(vb));
+        }
     }
 }
 
-// ll += sum over CTAs of the partial rows (fixed order); expectation_step (:109-129) by ONE CTA of 1024 threads
-__global__ void __launch_bounds__(1024) em_estep_kernel(const double *__restrict__ partial, uint32_t n_cta, uint32_t n_cells,
+// ll += this iteration's fixed-point sums (which are cleared for the next one); expectation_step (:109-129) by ONE
+// CTA of 1024 threads
+__global__ void __launch_bounds__(1024) em_estep_kernel(unsigned long long *__restrict__ acc, uint32_t n_cells,
                                                         double *__restrict__ ll /* [2][n_cells] */, double *__restrict__ prob_b,
                                                         uint32_t *__restrict__ done_flag) {
     __shared__ double red[32];
     __shared__ int all_done;
     double psum = 0.0;
     for (uint32_t i = threadIdx.x; i < n_cells; i += 1024) {
-        double a = ll[i], b = ll[n_cells + i];
-        for (uint32_t c = 0; c < n_cta; ++c) {
-            a += partial[static_cast<size_t>(c) * 2 * n_cells + i];
-            b += partial[static_cast<size_t>(c) * 2 * n_cells + n_cells + i];
-        }
-        ll[i] = a;
-        ll[n_cells + i] = b;
+        ll[i] += static_cast<double>(static_cast<long long>(acc[i])) * (1.0 / EM_FIX);
+        ll[n_cells + i] += static_cast<double>(static_cast<long long>(acc[n_cells + i])) * (1.0 / EM_FIX);
+        acc[i] = 0ull;
+        acc[n_cells + i] = 0ull;
         psum += prob_b[i];
     }
     psum = warp_sum(psum);
@@ -192,9 +176,8 @@ int sgpu_em_impl(sgpu_ctx *ctx, const sgpu_pileup *p, const uint32_t *h_id_to_po
     SGPU_CUDA(ctx, cudaEventCreate(&t0));
     SGPU_CUDA(ctx, cudaEventCreate(&t1));
     SGPU_CUDA(ctx, cudaEventRecord(t0, st));
-    DevBuf<double> d_prob, d_ll, d_partial;
+    DevBuf<double> d_prob, d_ll;
     DevBuf<uint32_t> d_map, d_flags;
-    DevBuf<unsigned long long> d_gacc;
     const uint32_t map_n = std::max(n_groups, 1u);
     SGPU_CUDA(ctx, d_prob.alloc(n_cells, ctx));
     SGPU_CUDA(ctx, d_ll.alloc(2 * static_cast<size_t>(n_cells), ctx));
@@ -217,34 +200,17 @@ int sgpu_em_impl(sgpu_ctx *ctx, const sgpu_pileup *p, const uint32_t *h_id_to_po
             return sgpu_fail(ctx, SGPU_E_CELL_RANGE, "expectation_maximization: a group id or id_to_pos[group id] is >= %u cells", n_cells);
         }
     }
-    // ~4 chunks per CTA for balance, never more than EM_CHUNK_LOCI loci between two flushes
-    const uint32_t chunk_loci = static_cast<uint32_t>(std::min<uint64_t>(EM_CHUNK_LOCI, std::max<uint64_t>(32, (p->n_loci + 8ull * ctx->sm_count - 1) / (8ull * ctx->sm_count))));
-    const uint32_t n_chunks = static_cast<uint32_t>((p->n_loci + chunk_loci - 1) / chunk_loci);
-    const size_t smem = 2 * static_cast<size_t>(n_cells) * sizeof(unsigned long long);
-    const bool use_smem = smem <= 200 * 1024;
-    const uint32_t n_cta = std::max(1u, std::min<uint32_t>(n_chunks, static_cast<uint32_t>(ctx->sm_count) * (use_smem && smem <= 100 * 1024 ? 2 : 1)));
-    SGPU_CUDA(ctx, d_partial.alloc(static_cast<size_t>(n_cta) * 2 * n_cells, ctx));
-    if (use_smem) {
-        static bool attr_done = false;
-        if (!attr_done) {
-            SGPU_CUDA(ctx, cudaFuncSetAttribute(em_mstep_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-            attr_done = true;
-        }
-    } else {
-        SGPU_CUDA(ctx, d_gacc.alloc(static_cast<size_t>(n_cta) * 2 * n_cells, ctx));
-    }
+    DevBuf<unsigned long long> d_acc;
+    SGPU_CUDA(ctx, d_acc.alloc(2 * static_cast<size_t>(n_cells), ctx));
+    SGPU_CUDA(ctx, cudaMemsetAsync(d_acc.p, 0, 2 * static_cast<size_t>(n_cells) * sizeof(unsigned long long), st));
+    const uint32_t n_cta = static_cast<uint32_t>(std::min<uint64_t>(5ull * ctx->sm_count, (p->n_loci + EM_WARPS - 1) / EM_WARPS));
     uint32_t it = 0;
     for (;;) {
-        if (n_chunks) {
-            if (use_smem) {
-                SGPU_LAUNCH(ctx, (em_mstep_kernel<true><<<n_cta, EM_THREADS, smem, st>>>(p->d_row_ptr, p->d_gid_base, p->n_loci, d_prob.p, d_map.p,
-                                                                                         n_cells, theta, n_chunks, chunk_loci, d_partial.p, nullptr)));
-            } else {
-                SGPU_LAUNCH(ctx, (em_mstep_kernel<false><<<n_cta, EM_THREADS, 0, st>>>(p->d_row_ptr, p->d_gid_base, p->n_loci, d_prob.p, d_map.p,
-                                                                                       n_cells, theta, n_chunks, chunk_loci, d_partial.p, d_gacc.p)));
-            }
+        if (n_cta) {
+            SGPU_LAUNCH(ctx, (em_mstep_kernel<<<n_cta, EM_THREADS, 0, st>>>(p->d_row_ptr, p->d_gid_base, p->n_loci, d_prob.p, d_map.p, n_cells,
+                                                                           theta, d_acc.p)));
         }
-        SGPU_LAUNCH(ctx, (em_estep_kernel<<<1, 1024, 0, st>>>(d_partial.p, n_chunks ? n_cta : 0, n_cells, d_ll.p, d_prob.p, d_flags.p)));
+        SGPU_LAUNCH(ctx, (em_estep_kernel<<<1, 1024, 0, st>>>(d_acc.p, n_cells, d_ll.p, d_prob.p, d_flags.p)));
         SGPU_CUDA(ctx, cudaGetLastError());
         SGPU_CUDA(ctx, cudaMemcpyAsync(h_flags, d_flags.p, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
         SGPU_CUDA(ctx, cudaStreamSynchronize(st));

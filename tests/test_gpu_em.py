@@ -1,6 +1,6 @@
 """expectation_maximization on the GPU (expectation_maximization.cpp:131-160) through the C ABI:
 the reference's own known-answer tests, the golden vectors of the compiled reference and the oracle on synthetic
-pileups. The per-cell sums are formed in 2^-36 fixed point instead of the reference's sequential fp64 order, so the
+pileups. The per-cell sums are formed in 2^-32 fixed point instead of the reference's sequential fp64 order, so the
 probabilities are compared within 1e-6 (absolute; they are probabilities) and the iteration counts must agree."""
 import numpy as np
 import pytest
@@ -35,8 +35,8 @@ def test_golden_vectors(gpu_ctx):
 
 @pytest.mark.parametrize("n_cells,coverage", [(300, 0.3), (2000, 0.1), (7000, 0.05)])
 def test_against_oracle_on_filtered_device_pileup(gpu_ctx, n_cells, coverage):
-    """filter on the device, then EM on the device-resident result (the way divide_cluster chains them); 7000 cells:
-    112 KB of shared-memory accumulators, one CTA per SM; every iteration compared"""
+    """filter on the device, then EM on the device-resident result (the way divide_cluster chains them); the
+    intermediate states after 1 and 2 iterations are compared as well"""
     cfg = SynthConfig(n_cells=n_cells, coverage=coverage, n_loci=1500, n_chr=2, n_clones=2, p_multi=0.05, p_mate=0.02, theta=0.01,
                       seed=n_cells)
     ident = np.arange(n_cells, dtype=np.uint32)
@@ -54,8 +54,8 @@ def test_against_oracle_on_filtered_device_pileup(gpu_ctx, n_cells, coverage):
     fdev.free()
 
 
-def test_many_cells_global_accumulators(gpu_ctx):
-    """14 000 cells: the per-cell accumulators (224 KB) no longer fit in shared memory"""
+def test_many_cells(gpu_ctx):
+    """14 000 cells, close to the 14-bit group id limit of PosData"""
     n = 14000
     cfg = SynthConfig(n_cells=n, coverage=0.02, n_loci=600, n_chr=1, n_clones=2, theta=0.01, seed=5)
     p = make_pileup(cfg)
