@@ -9,7 +9,7 @@
 //
 // Here: one WARP per locus (loci of the path have ~10^2..10^4 entries), 8 warps per CTA, grid-stride over the loci.
 // The per-cell log likelihoods of one iteration are accumulated as 64-bit FIXED POINT (scale 2^32) with global
-// integer reductions (RED.ADD.64, resolved in L2: 16 bytes per cell, always resident): integer addition is order
+// integer reductions (RED.ADD.64, resolved in L2: 8 bytes per cell, always resident; only ll_b - ll_a is needed): integer addition is order
 // independent, so the result is bit-reproducible, and no shared memory is needed, which leaves room for 40 warps per
 // SM to hide the two dependent gathers per entry (probability of the entry's cell, position of its cell). A first
 // version with per-CTA shared-memory accumulators was 10 x slower: 64-bit shared-memory atomics compile to a
@@ -38,7 +38,8 @@ __device__ __forceinline__ double warp_sum(double v) {
     return v;
 }
 
-// acc: [2][n_cells] int64, zero at launch
+// acc: [n_cells] int64, zero at launch: sum over the cell's entries of centre_b[base] - centre_a[base]. The E step
+// only ever uses ll_b - ll_a (:120), so ONE reduction per entry carries everything
 __global__ void __launch_bounds__(EM_THREADS)
 em_mstep_kernel(const uint64_t *__restrict__ row_ptr, const uint16_t *__restrict__ gid_base, uint64_t n_loci,
                 const double *__restrict__ prob_b, const uint32_t *__restrict__ id_to_pos, uint32_t n_cells, double theta,
@@ -84,21 +85,18 @@ em_mstep_kernel(const uint64_t *__restrict__ row_ptr, const uint16_t *__restrict
             lg = log(v / s2);
         }
         const long long fx = __double2ll_rn(lg * EM_FIX);
-        long long ta[4], tb[4];
+        long long td[4];
 #pragma unroll
         for (int b = 0; b < 4; ++b) {
-            ta[b] = __shfl_sync(0xFFFFFFFFu, fx, b);
-            tb[b] = __shfl_sync(0xFFFFFFFFu, fx, 4 + b);
+            td[b] = __shfl_sync(0xFFFFFFFFu, fx, 4 + b) - __shfl_sync(0xFFFFFFFFu, fx, b);
         }
 #pragma unroll 4
         for (uint64_t e = e0 + lane; e < e1; e += 32) {
             const uint32_t gb = gid_base[e];
             const uint32_t cell = id_to_pos[gb >> 2];
             const int b = gb & 3;
-            const long long va = b == 0 ? ta[0] : b == 1 ? ta[1] : b == 2 ? ta[2] : ta[3];
-            const long long vb = b == 0 ? tb[0] : b == 1 ? tb[1] : b == 2 ? tb[2] : tb[3];
-            atomicAdd(acc + cell, static_cast<unsigned long long>(va));
-            atomicAdd(acc + n_cells + cell, static_cast<unsigned long long>(vb));
+            const long long v = b == 0 ? td[0] : b == 1 ? td[1] : b == 2 ? td[2] : td[3];
+            atomicAdd(acc + cell, static_cast<unsigned long long>(v));
         }
     }
 }
@@ -106,16 +104,14 @@ em_mstep_kernel(const uint64_t *__restrict__ row_ptr, const uint16_t *__restrict
 // ll += this iteration's fixed-point sums (which are cleared for the next one); expectation_step (:109-129) by ONE
 // CTA of 1024 threads
 __global__ void __launch_bounds__(1024) em_estep_kernel(unsigned long long *__restrict__ acc, uint32_t n_cells,
-                                                        double *__restrict__ ll /* [2][n_cells] */, double *__restrict__ prob_b,
+                                                        double *__restrict__ ll /* [n_cells]: ll_b - ll_a */, double *__restrict__ prob_b,
                                                         uint32_t *__restrict__ done_flag) {
     __shared__ double red[32];
     __shared__ int all_done;
     double psum = 0.0;
     for (uint32_t i = threadIdx.x; i < n_cells; i += 1024) {
         ll[i] += static_cast<double>(static_cast<long long>(acc[i])) * (1.0 / EM_FIX);
-        ll[n_cells + i] += static_cast<double>(static_cast<long long>(acc[n_cells + i])) * (1.0 / EM_FIX);
         acc[i] = 0ull;
-        acc[n_cells + i] = 0ull;
         psum += prob_b[i];
     }
     psum = warp_sum(psum);
@@ -133,7 +129,7 @@ __global__ void __launch_bounds__(1024) em_estep_kernel(unsigned long long *__re
     const double prior_b = total / n_cells, prior_a = 1.0 - prior_b;
     bool done = true;
     for (uint32_t i = threadIdx.x; i < n_cells; i += 1024) {
-        double d = ll[n_cells + i] - ll[i];
+        double d = ll[i];
         d = d < -100.0 ? -100.0 : (d > 100.0 ? 100.0 : d);
         const double odds = exp(d);
         const double p = 1.0 - 1.0 / (1.0 + odds * prior_b / prior_a);
@@ -180,14 +176,14 @@ int sgpu_em_impl(sgpu_ctx *ctx, const sgpu_pileup *p, const uint32_t *h_id_to_po
     DevBuf<uint32_t> d_map, d_flags;
     const uint32_t map_n = std::max(n_groups, 1u);
     SGPU_CUDA(ctx, d_prob.alloc(n_cells, ctx));
-    SGPU_CUDA(ctx, d_ll.alloc(2 * static_cast<size_t>(n_cells), ctx));
+    SGPU_CUDA(ctx, d_ll.alloc(n_cells, ctx));
     SGPU_CUDA(ctx, d_map.alloc(map_n, ctx));
     SGPU_CUDA(ctx, d_flags.alloc(2, ctx));
     SGPU_CUDA(ctx, cudaMemcpyAsync(d_prob.p, h_prob_b, n_cells * sizeof(double), cudaMemcpyHostToDevice, st));
     if (n_groups) {
         SGPU_CUDA(ctx, cudaMemcpyAsync(d_map.p, h_id_to_pos, n_groups * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
     }
-    SGPU_CUDA(ctx, cudaMemsetAsync(d_ll.p, 0, 2 * static_cast<size_t>(n_cells) * sizeof(double), st));
+    SGPU_CUDA(ctx, cudaMemsetAsync(d_ll.p, 0, n_cells * sizeof(double), st));
     SGPU_CUDA(ctx, cudaMemsetAsync(d_flags.p, 0, 2 * sizeof(uint32_t), st));
     uint32_t h_flags[2] = { 0, 0 };
     if (p->n_entries) {
@@ -201,8 +197,8 @@ int sgpu_em_impl(sgpu_ctx *ctx, const sgpu_pileup *p, const uint32_t *h_id_to_po
         }
     }
     DevBuf<unsigned long long> d_acc;
-    SGPU_CUDA(ctx, d_acc.alloc(2 * static_cast<size_t>(n_cells), ctx));
-    SGPU_CUDA(ctx, cudaMemsetAsync(d_acc.p, 0, 2 * static_cast<size_t>(n_cells) * sizeof(unsigned long long), st));
+    SGPU_CUDA(ctx, d_acc.alloc(n_cells, ctx));
+    SGPU_CUDA(ctx, cudaMemsetAsync(d_acc.p, 0, n_cells * sizeof(unsigned long long), st));
     const uint32_t n_cta = static_cast<uint32_t>(std::min<uint64_t>(5ull * ctx->sm_count, (p->n_loci + EM_WARPS - 1) / EM_WARPS));
     uint32_t it = 0;
     for (;;) {
