@@ -131,16 +131,22 @@ struct EventTimer {
     }
 };
 
-// measured crossover: the dense int8 GEMM wins unless the pileup is ultra sparse
+// Cost model fitted to profiles/r1_path_crossover.txt (16 384 loci, 500 .. 16 000 cells, 0.002x .. 0.5x), in ms:
+//   scatter: 0.03 + pairs / rate, pairs = L c^2 / 2 (c = entries per locus); rate 150 pairs/ns while the two N^2 int32
+//            planes stay in L2 (N <= 2800), 35 pairs/ns beyond (HBM atomics)
+//   GEMM:    0.15 + L * 4 N_pad^2 / 4.0e12 (the tcgen05 kernel at ~4 POP/s issued) + 4.4e-9 per entry (staging)
+// The dense path wins for every BASELINE config except the 500-cell one; scatter wins where fewer than ~50 reads
+// cover a locus of several thousand cells.
 int choose_path(const sgpu_pileup *p, uint32_t num_cells) {
     if (p->n_loci == 0 || num_cells < 256) {
         return SGPU_PATH_SCATTER;
     }
-    const double c = static_cast<double>(p->n_entries) / static_cast<double>(p->n_loci); // reads per locus
-    const double pairs = 0.5 * c * c;                            // atomics per locus on the scatter path
-    const double macs = 2.0 * num_cells * static_cast<double>(num_cells); // 4 planes x N^2 / 2
-    // scatter ~ 5e10 atomics/s, GEMM ~ 1e15 MAC/s + staging; see DESIGN.md for the measurements
-    return pairs * 2.0e4 < macs ? SGPU_PATH_SCATTER : SGPU_PATH_GEMM;
+    const double L = static_cast<double>(p->n_loci), E = static_cast<double>(p->n_entries);
+    const double c = E / L; // reads per locus
+    const double n_pad = (num_cells + 255) / 256 * 256.0;
+    const double t_scatter = 0.03 + 0.5 * c * c * L / (num_cells <= 2800 ? 150e6 : 35e6);
+    const double t_gemm = 0.15 + L * 4.0 * n_pad * n_pad / 4.0e12 + E * 4.4e-9;
+    return t_scatter < t_gemm ? SGPU_PATH_SCATTER : SGPU_PATH_GEMM;
 }
 
 } // namespace

@@ -195,7 +195,7 @@ def test_device_generated_pileup(gpu_ctx, path):
 
 
 def test_auto_path_and_stats(gpu_ctx):
-    dev = gpu_ctx.synth_pileup(1024, 0.5, 1, 400, theta=0.001, p_multi=0.01, seed=4)
+    dev = gpu_ctx.synth_pileup(1024, 0.5, 1, 4000, theta=0.001, p_multi=0.01, seed=4)
     ident = np.arange(1024, dtype=np.uint32)
     fdev, _ = api.Filter(0.001, 4, gpu_ctx).filter_device(dev, ident)
     c = api.Counts(gpu_ctx, 1024)
@@ -203,6 +203,12 @@ def test_auto_path_and_stats(gpu_ctx):
     st = c.accumulate(fdev, 1000, ident, 0.01, 0.15, 0.001, 8, "auto")
     assert st["path_used"] == "gemm" and st["gemm_launches"] >= 1 and st["ms_gemm"] > 0
     assert gpu_ctx.launch_count() > n0
+    # the ultra-sparse end of the cost model (profiles/r1_path_crossover.txt): ~40 reads over 8000 cells per locus
+    sparse = gpu_ctx.synth_pileup(8000, 0.005, 1, 2048, theta=0.001, seed=4)
+    c2 = api.Counts(gpu_ctx, 8000)
+    st2 = c2.accumulate(sparse, 1000, np.arange(8000, dtype=np.uint32), 0.01, 0.15, 0.001, 8, "auto")
+    assert st2["path_used"] == "scatter"
+    c2.free()
 
 
 @pytest.mark.parametrize("n_cells,coverage,loci_per_chr", [(8000, 0.5, 384), (10000, 0.05, 4096), (16000, 0.25, 96)])
