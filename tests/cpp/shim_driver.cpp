@@ -1,6 +1,7 @@
 // Test driver for the C++ drop-in shim: reads a pileup (CSR, binary), rebuilds the reference's
 // std::vector<std::vector<PosData>>, calls Filter::filter and computeSimilarityMatrix exactly like
 // divide_cluster does (spectral_clustering.cpp:336-356) and writes the filtered pileup and the matrix.
+#include "expectation_maximization.hpp"
 #include "similarity_matrix.hpp"
 #include "util/is_significant.hpp"
 
@@ -87,6 +88,20 @@ int main(int argc, char **argv) {
     write_vec(out, f_gb);
     write_vec(out, std::vector<double>{ coverage });
     write_vec(out, std::vector<double>(m.data(), m.data() + static_cast<size_t>(num_cells) * num_cells));
+    // expectation_maximization the way divide_cluster calls it at the root of the recursion
+    // (spectral_clustering.cpp:375-377): all cells, identity map, a two-way split as the start
+    std::vector<uint32_t> all(id_to_pos.size());
+    for (uint32_t i = 0; i < all.size(); ++i) {
+        all[i] = i;
+    }
+    auto [root, root_cov] = filter.filter(pds, all, "", threads);
+    (void)root_cov;
+    std::vector<double> prob(all.size());
+    for (uint32_t i = 0; i < prob.size(); ++i) {
+        prob[i] = (i * 7 % 10 < 5) ? 0.3 : 0.7;
+    }
+    expectation_maximization(root, all, threads, theta, &prob);
+    write_vec(out, prob);
     fclose(out);
     return 0;
 }

@@ -65,9 +65,14 @@ def test_shim_end_to_end(tmp_path):
                      _read_vec(f, np.uint16))
         cov = _read_vec(f, np.float64)[0]
         M = _read_vec(f, np.float64).reshape(keep.size, keep.size)
+        prob = _read_vec(f, np.float64)
     kl, ke, _, cov64 = po.filter_flags(p, id_to_pos, theta)
     want = p.select(kl, ke)
     assert got == want and cov == cov64
     o = po.similarity(want, keep.size, L, id_to_pos, eps, h, theta, T, "ADD_MIN")
     assert_matrix_close(M, o.M, 1e-6)
-    del members
+    # expectation_maximization through the shim's symbol (root cluster: identity map)
+    kl, ke, _, _ = po.filter_flags(p, members, theta)
+    start = np.where(np.arange(120) * 7 % 10 < 5, 0.3, 0.7)
+    want_prob, _ = po.expectation_maximization(p.select(kl, ke), members, theta, start)
+    assert np.abs(prob - want_prob).max() <= 1e-6
