@@ -108,6 +108,14 @@ int sgpu_pileup_upload(sgpu_ctx *ctx, uint32_t n_chr, const uint64_t *chr_ptr, c
 int sgpu_pileup_upload_async(sgpu_ctx *ctx, uint32_t n_chr, const uint64_t *chr_ptr, const uint64_t *row_ptr,
                              const uint32_t *position, const uint32_t *read_id, const uint16_t *gid_base,
                              sgpu_pileup **out);
+/* The same, but the read ids (4 of the 6 bytes per entry) are NOT copied: they stay in the caller's page-locked,
+ * mapped host memory (cudaHostAlloc / cudaHostRegister; must stay valid while the pileup lives). sgpu_filter then
+ * pulls the read ids of the loci it KEEPS straight over PCIe while compacting, so the read ids of rejected loci never
+ * travel (Filter::filter only looks at the bases, util/is_significant.cpp:163-175). Any other consumer of the read
+ * ids (sgpu_counts_accumulate or sgpu_pileup_download on the unfiltered pileup) copies them all first. */
+int sgpu_pileup_upload_lazy_async(sgpu_ctx *ctx, uint32_t n_chr, const uint64_t *chr_ptr, const uint64_t *row_ptr,
+                                  const uint32_t *position, const uint32_t *read_id, const uint16_t *gid_base,
+                                  sgpu_pileup **out);
 /* Direct ingestion of SECEDO's binary pileup files (replaces read_pileup_bin, util/pileup_reader.cpp:139-257,
  * and the flattening of its vector<PosData>): one buffer per chromosome holding the bytes of the `.bin` file
  *     u32 position | u16 coverage | u32 read_id[coverage] | u16 (cell_id << 2 | base)[coverage]   per locus.

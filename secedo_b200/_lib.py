@@ -78,6 +78,7 @@ SIGNATURES = {
     "sgpu_synth_pileup": (C.c_int, [_vp, C.POINTER(SynthParams), C.POINTER(_vp)]),
     "sgpu_pileup_upload": (C.c_int, [_vp, C.c_uint32, _vp, _vp, _vp, _vp, _vp, C.POINTER(_vp)]),
     "sgpu_pileup_upload_async": (C.c_int, [_vp, C.c_uint32, _vp, _vp, _vp, _vp, _vp, C.POINTER(_vp)]),
+    "sgpu_pileup_upload_lazy_async": (C.c_int, [_vp, C.c_uint32, _vp, _vp, _vp, _vp, _vp, C.POINTER(_vp)]),
     "sgpu_pileup_from_bin": (C.c_int, [_vp, C.c_uint32, _vp, _vp, _vp, C.c_uint32, C.c_uint32, _vp, _vp, C.POINTER(_vp),
                                        _u32p, _u32p]),
     "sgpu_pileup_wrap_device": (C.c_int, [_vp, C.c_uint32, _vp, _vp, _vp, _vp, _vp, C.POINTER(_vp)]),

@@ -100,6 +100,16 @@ class Context:
         dp._keepalive = p
         return dp
 
+    def upload_lazy_async(self, p: Pileup) -> "DevicePileup":
+        """Like :meth:`upload_async`, but the read ids stay in (pinned, mapped) host memory: the filter pulls the
+        read ids of the loci it keeps over PCIe, the rejected loci's never travel."""
+        h = C.c_void_p()
+        self.check(self._lib.sgpu_pileup_upload_lazy_async(self._h, p.n_chr, _ptr(p.chr_ptr), _ptr(p.row_ptr),
+                                                           _ptr(p.position), _ptr(p.read_id), _ptr(p.gid_base), C.byref(h)))
+        dp = DevicePileup(self, h)
+        dp._keepalive = p
+        return dp
+
     def pileup_from_bin(self, files: Sequence, id_to_group: Sequence[int], max_coverage: int = 100,
                         positions: Optional[Sequence[Sequence[int]]] = None):
         """Direct ingestion of the reference's binary pileup files (``read_pileup_bin``,

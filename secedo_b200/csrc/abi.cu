@@ -246,7 +246,7 @@ int sgpu_synchronize(sgpu_ctx *ctx) {
 // ---- pileup ---------------------------------------------------------------------------------------
 static int pileup_upload(sgpu_ctx *ctx, uint32_t n_chr, const uint64_t *chr_ptr, const uint64_t *row_ptr,
                          const uint32_t *position, const uint32_t *read_id, const uint16_t *gid_base, bool async,
-                         sgpu_pileup **out) {
+                         sgpu_pileup **out, bool lazy_read_id = false) {
     SGPU_CUDA(ctx, cudaSetDevice(ctx->device));
     cudaStream_t st = ctx->stream;
     if (async) {
@@ -272,7 +272,21 @@ static int pileup_upload(sgpu_ctx *ctx, uint32_t n_chr, const uint64_t *chr_ptr,
     SGPU_CUDA(ctx, sgpu_dev_alloc(ctx, reinterpret_cast<void **>(&p->d_chr_ptr), (n_chr + 1) * sizeof(uint64_t)));
     SGPU_CUDA(ctx, sgpu_dev_alloc(ctx, reinterpret_cast<void **>(&p->d_row_ptr), (P + 1) * sizeof(uint64_t)));
     SGPU_CUDA(ctx, sgpu_dev_alloc(ctx, reinterpret_cast<void **>(&p->d_position), (P ? P : 1) * sizeof(uint32_t)));
-    SGPU_CUDA(ctx, sgpu_dev_alloc(ctx, reinterpret_cast<void **>(&p->d_read_id), (E ? E : 1) * sizeof(uint32_t)));
+    if (lazy_read_id && E) {
+        void *alias = nullptr;
+        if (cudaHostGetDevicePointer(&alias, const_cast<uint32_t *>(read_id), 0) != cudaSuccess) {
+            cudaGetLastError();
+            sgpu_dev_free(ctx, p->d_chr_ptr);
+            sgpu_dev_free(ctx, p->d_row_ptr);
+            sgpu_dev_free(ctx, p->d_position);
+            delete[] p->h_chr_ptr;
+            delete p;
+            return sgpu_fail(ctx, SGPU_E_ARG, "lazy upload: read_id must be page-locked, mapped host memory (cudaHostAlloc / cudaHostRegister)");
+        }
+        p->zc_read_id = static_cast<const uint32_t *>(alias);
+    } else {
+        SGPU_CUDA(ctx, sgpu_dev_alloc(ctx, reinterpret_cast<void **>(&p->d_read_id), (E ? E : 1) * sizeof(uint32_t)));
+    }
     SGPU_CUDA(ctx, sgpu_dev_alloc(ctx, reinterpret_cast<void **>(&p->d_gid_base), (E ? E : 1) * sizeof(uint16_t)));
     // the copy of chr_ptr reads p->h_chr_ptr (owned by the pileup), not the caller's array
     SGPU_CUDA(ctx, cudaMemcpyAsync(p->d_chr_ptr, p->h_chr_ptr, (n_chr + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, st));
@@ -283,7 +297,9 @@ static int pileup_upload(sgpu_ctx *ctx, uint32_t n_chr, const uint64_t *chr_ptr,
         SGPU_CUDA(ctx, cudaMemsetAsync(p->d_row_ptr, 0, sizeof(uint64_t), st));
     }
     if (E) {
-        SGPU_CUDA(ctx, cudaMemcpyAsync(p->d_read_id, read_id, E * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
+        if (p->d_read_id) {
+            SGPU_CUDA(ctx, cudaMemcpyAsync(p->d_read_id, read_id, E * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
+        }
         SGPU_CUDA(ctx, cudaMemcpyAsync(p->d_gid_base, gid_base, E * sizeof(uint16_t), cudaMemcpyHostToDevice, st));
     }
     if (async) {
@@ -307,6 +323,27 @@ int sgpu_pileup_upload_async(sgpu_ctx *ctx, uint32_t n_chr, const uint64_t *chr_
                              sgpu_pileup **out) {
     return pileup_upload(ctx, n_chr, chr_ptr, row_ptr, position, read_id, gid_base, true, out);
 }
+
+int sgpu_pileup_upload_lazy_async(sgpu_ctx *ctx, uint32_t n_chr, const uint64_t *chr_ptr, const uint64_t *row_ptr,
+                                  const uint32_t *position, const uint32_t *read_id, const uint16_t *gid_base,
+                                  sgpu_pileup **out) {
+    return pileup_upload(ctx, n_chr, chr_ptr, row_ptr, position, read_id, gid_base, true, out, true);
+}
+
+} // extern "C"
+
+int sgpu_pileup_materialize(sgpu_ctx *ctx, const sgpu_pileup *cp) {
+    sgpu_pileup *p = const_cast<sgpu_pileup *>(cp);
+    if (!p || p->d_read_id || !p->zc_read_id) {
+        return SGPU_OK;
+    }
+    const uint64_t E = p->n_entries;
+    SGPU_CUDA(ctx, sgpu_dev_alloc(ctx, reinterpret_cast<void **>(&p->d_read_id), (E ? E : 1) * sizeof(uint32_t)));
+    SGPU_CUDA(ctx, cudaMemcpyAsync(p->d_read_id, p->zc_read_id, E * sizeof(uint32_t), cudaMemcpyDefault, ctx->stream));
+    return SGPU_OK;
+}
+
+extern "C" {
 
 int sgpu_pileup_wrap_device(sgpu_ctx *ctx, uint32_t n_chr, const uint64_t *host_chr_ptr, const uint64_t *dev_row_ptr,
                             const uint32_t *dev_position, const uint32_t *dev_read_id, const uint16_t *dev_gid_base,
@@ -356,6 +393,9 @@ int sgpu_pileup_download(sgpu_ctx *ctx, const sgpu_pileup *p, uint64_t *chr_ptr,
                          uint32_t *read_id, uint16_t *gid_base) {
     SGPU_CUDA(ctx, cudaSetDevice(ctx->device));
     SGPU_WAIT_PILEUP(ctx, p);
+    if (read_id) {
+        SGPU_TRY(sgpu_pileup_materialize(ctx, p));
+    }
     cudaStream_t st = ctx->stream;
     if (chr_ptr) {
         std::memcpy(chr_ptr, p->h_chr_ptr, (p->n_chr + 1) * sizeof(uint64_t));
@@ -464,6 +504,7 @@ int sgpu_counts_accumulate(sgpu_ctx *ctx, sgpu_counts *c, const sgpu_pileup *fil
                            sgpu_stats *stats) {
     SGPU_CUDA(ctx, cudaSetDevice(ctx->device));
     SGPU_WAIT_PILEUP(ctx, filtered);
+    SGPU_TRY(sgpu_pileup_materialize(ctx, filtered));
     if (path < SGPU_PATH_AUTO || path > SGPU_PATH_GEMM) {
         return sgpu_fail(ctx, SGPU_E_ARG, "unknown path %d", path);
     }

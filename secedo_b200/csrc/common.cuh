@@ -92,6 +92,10 @@ int sgpu_fail(sgpu_ctx *ctx, int code, const char *fmt, ...);
         }                                                                                          \
     } while (0)
 
+struct sgpu_pileup;
+// copy lazily uploaded read ids to the device (no-op otherwise); stream ordered on ctx->stream
+int sgpu_pileup_materialize(sgpu_ctx *ctx, const sgpu_pileup *p);
+
 // device memory from the context's cache (see sgpu_ctx::free_blocks)
 cudaError_t sgpu_dev_alloc(sgpu_ctx *ctx, void **p, size_t bytes);
 void sgpu_dev_free(sgpu_ctx *ctx, void *p);
@@ -144,6 +148,9 @@ struct sgpu_pileup {
     uint32_t *d_read_id = nullptr;
     uint16_t *d_gid_base = nullptr;
     bool owns = true;
+    // sgpu_pileup_upload_lazy_async: the read ids stay in the caller's pinned host memory (zc_read_id is its device
+    // alias) and d_read_id is null until somebody other than the filter needs them (sgpu_pileup_materialize)
+    const uint32_t *zc_read_id = nullptr;
     cudaEvent_t ready = nullptr;   // set by sgpu_pileup_upload_async: the copies are done
     mutable uint32_t max_row = 0;  // entries of the largest locus (0 = not known yet; cached by reads.cu)
 };

@@ -409,7 +409,10 @@ int sgpu_filter_impl(sgpu_ctx *ctx, const sgpu_pileup *in, const uint32_t *h_id_
     SGPU_CUDA(ctx, sgpu_dev_alloc(ctx, reinterpret_cast<void **>(&out->d_read_id), (Ek ? Ek : 1) * sizeof(uint32_t)));
     SGPU_CUDA(ctx, sgpu_dev_alloc(ctx, reinterpret_cast<void **>(&out->d_gid_base), (Ek ? Ek : 1) * sizeof(uint16_t)));
     if (P) {
-        SGPU_LAUNCH(ctx, (filter_compact_kernel<<<grid, FILTER_THREADS, smem, st>>>(in->d_row_ptr, in->d_position, in->d_read_id, in->d_gid_base,
+        // lazily uploaded pileup: the read ids of the KEPT loci are pulled straight from pinned host memory (the
+        // rejected loci's never cross PCIe)
+        const uint32_t *rid_src = in->d_read_id ? in->d_read_id : in->zc_read_id;
+        SGPU_LAUNCH(ctx, (filter_compact_kernel<<<grid, FILTER_THREADS, smem, st>>>(in->d_row_ptr, in->d_position, rid_src, in->d_gid_base,
                                                                  P, d_mask.p, n_groups, d_keep.p, d_new_locus.p, d_new_row.p,
                                                                  out->d_row_ptr, out->d_position, out->d_read_id,
                                                                  out->d_gid_base)));

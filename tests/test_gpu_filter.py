@@ -4,6 +4,7 @@ import pytest
 
 from conftest import golden_pileup, load_golden
 from oracle import pyoracle as po
+from secedo_b200 import api
 from secedo_b200.api import Filter
 from secedo_b200.pileup import NO_POS, Pileup
 from secedo_b200.synth import SynthConfig, make_pileup
@@ -101,3 +102,37 @@ def test_filter_rejects_bad_group(gpu_ctx):
     p = Pileup.from_pos_data([[(1, [1, 2], [(7 << 2) | 1, (2 << 2) | 1])]])
     with pytest.raises(SgpuError):
         Filter(0.01, 4, gpu_ctx).filter(p, np.arange(4), "", 1)
+
+
+def test_lazy_upload_pulls_read_ids_of_kept_loci(gpu_ctx):
+    """sgpu_pileup_upload_lazy_async: the read ids stay in pinned host memory and the filter's compaction reads those
+    of the kept loci through the mapped pointer - same filtered pileup bit for bit; other consumers copy them first"""
+    import torch
+    cfg = SynthConfig(n_cells=300, coverage=0.3, n_loci=2500, n_chr=3, p_multi=0.2, p_mate=0.05, theta=0.01, seed=12)
+    p = make_pileup(cfg)
+    pinned = {k: torch.from_numpy(np.ascontiguousarray(getattr(p, k))).pin_memory() for k in ("row_ptr", "position", "read_id", "gid_base")}
+    hp = Pileup(p.chr_ptr, *(pinned[k].numpy() for k in ("row_ptr", "position", "read_id", "gid_base")))
+    ident = np.arange(cfg.n_cells, dtype=np.uint32)
+    flt = api.Filter(0.01, 4, gpu_ctx)
+    want, cov = flt.filter(p, ident, "", 1)
+    lazy = gpu_ctx.upload_lazy_async(hp)
+    fdev, cov2 = flt.filter_device(lazy, ident)
+    assert fdev.download() == want and cov2 == cov
+    # sub-cluster: entries of other cells are dropped while compacting
+    sub = np.full(cfg.n_cells, NO_POS, np.uint32)
+    sub[40:200] = np.arange(160)
+    want_sub, _ = flt.filter(p, sub, "", 1)
+    fsub, _ = flt.filter_device(lazy, sub)
+    assert fsub.download() == want_sub
+    # any other consumer materialises the read ids: similarity counts straight from the lazy pileup, and its download
+    c1, c2 = api.Counts(gpu_ctx, cfg.n_cells), api.Counts(gpu_ctx, cfg.n_cells)
+    lazy2 = gpu_ctx.upload_lazy_async(hp)
+    c1.accumulate(lazy2, 1000, ident, 0.01, 0.5, 0.01, 8, "gemm")
+    c2.accumulate(p, 1000, ident, 0.01, 0.5, 0.01, 8, "gemm")
+    for a, b in zip(c1.download(), c2.download()):
+        assert np.array_equal(a, b)
+    assert lazy2.download() == p and gpu_ctx.upload_lazy_async(hp).download() == p
+    with pytest.raises(api.SgpuError):
+        gpu_ctx.upload_lazy_async(p)  # pageable memory cannot be read by the device
+    for o in (fdev, fsub, lazy, lazy2, c1, c2):
+        o.free()
