@@ -222,6 +222,54 @@ __global__ void __launch_bounds__(FILTER_THREADS) filter_decide_kernel(const uin
     }
 }
 
+// Lazily uploaded pileup: the read ids of the KEPT loci are pulled from the caller's mapped host memory into a device
+// array with the same indexing. One warp per kept locus, 16 bytes per lane and four loads in flight (2 KB per warp):
+// narrow 4-byte-per-lane reads of host memory reached only 27 GB/s over PCIe.
+__global__ void __launch_bounds__(FILTER_THREADS) pull_read_ids_kernel(const uint64_t *__restrict__ row_ptr, uint64_t n_loci,
+                                                                       const uint8_t *__restrict__ keep,
+                                                                       const uint32_t *__restrict__ src, uint32_t *__restrict__ dst) {
+    const int lane = threadIdx.x & 31;
+    const uint64_t warps_total = static_cast<uint64_t>(gridDim.x) * (FILTER_THREADS / 32);
+    for (uint64_t l = static_cast<uint64_t>(blockIdx.x) * (FILTER_THREADS / 32) + (threadIdx.x >> 5); l < n_loci; l += warps_total) {
+        if (!keep[l]) {
+            continue;
+        }
+        const uint64_t e0 = row_ptr[l], e1 = row_ptr[l + 1];
+        // elements up to the first 16-byte boundary of BOTH arrays (they share the alignment if the bases do; if not,
+        // everything goes through the scalar loop)
+        const uint64_t mis_s = (reinterpret_cast<uintptr_t>(src + e0) >> 2) & 3u, mis_d = (reinterpret_cast<uintptr_t>(dst + e0) >> 2) & 3u;
+        uint64_t b0 = e0 + ((4 - mis_s) & 3u);
+        uint64_t b1 = b0 + ((e1 > b0 ? e1 - b0 : 0) & ~3ull);
+        if (mis_s != mis_d || b0 > e1) {
+            b0 = b1 = e1;
+        }
+        for (uint64_t e = e0 + lane; e < min(b0, e1); e += 32) {
+            dst[e] = src[e];
+        }
+        const uint4 *s4 = reinterpret_cast<const uint4 *>(src + b0);
+        uint4 *d4 = reinterpret_cast<uint4 *>(dst + b0);
+        const uint64_t n4 = (b1 - b0) / 4;
+        for (uint64_t i = lane; i < n4; i += 128) {
+            uint4 v[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                if (i + 32 * u < n4) {
+                    v[u] = s4[i + 32 * u];
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                if (i + 32 * u < n4) {
+                    d4[i + 32 * u] = v[u];
+                }
+            }
+        }
+        for (uint64_t e = b1 + lane; e < e1; e += 32) {
+            dst[e] = src[e];
+        }
+    }
+}
+
 __global__ void __launch_bounds__(FILTER_THREADS) filter_compact_kernel(
         const uint64_t *__restrict__ row_ptr, const uint32_t *__restrict__ position,
         const uint32_t *__restrict__ read_id, const uint16_t *__restrict__ gid_base, uint64_t n_loci,
@@ -411,7 +459,13 @@ int sgpu_filter_impl(sgpu_ctx *ctx, const sgpu_pileup *in, const uint32_t *h_id_
     if (P) {
         // lazily uploaded pileup: the read ids of the KEPT loci are pulled straight from pinned host memory (the
         // rejected loci's never cross PCIe)
-        const uint32_t *rid_src = in->d_read_id ? in->d_read_id : in->zc_read_id;
+        const uint32_t *rid_src = in->d_read_id;
+        DevBuf<uint32_t> pulled;
+        if (!rid_src) {
+            SGPU_CUDA(ctx, pulled.alloc(in->n_entries ? in->n_entries : 1, ctx));
+            SGPU_LAUNCH(ctx, (pull_read_ids_kernel<<<grid, FILTER_THREADS, 0, st>>>(in->d_row_ptr, P, d_keep.p, in->zc_read_id, pulled.p)));
+            rid_src = pulled.p;
+        }
         SGPU_LAUNCH(ctx, (filter_compact_kernel<<<grid, FILTER_THREADS, smem, st>>>(in->d_row_ptr, in->d_position, rid_src, in->d_gid_base,
                                                                  P, d_mask.p, n_groups, d_keep.p, d_new_locus.p, d_new_row.p,
                                                                  out->d_row_ptr, out->d_position, out->d_read_id,
