@@ -319,7 +319,9 @@ def main_ours(args):
     e2e_total = E2E_WARMUP + e2e_steps  # warm-up + timed
     # uploads run up to LOOKAHEAD chromosomes ahead of the kernels, but never across the warm-up / timed
     # boundary nor past the last step: every timed step's H2D bytes are copied inside the timed region
-    LOOKAHEAD = 2
+    # (a whole step ahead: the DMA engine then works through accumulate and the D2H of the matrix, when the kernels
+    # leave the H2D direction of the bus idle, and the filter's zero-copy pull has the bus to itself)
+    LOOKAHEAD = 4
     runs = [[(s, c) for s in range(E2E_WARMUP) for c in range(n_chr)],
             [(s, c) for s in range(E2E_WARMUP, e2e_total) for c in range(n_chr)]]
     state = {"queue": [], "issued": 0, "run": []}
