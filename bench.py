@@ -333,7 +333,7 @@ def main_ours(args):
             state["issued"] += 1
 
     def e2e_step():
-        if state["issued"] == len(state["run"]):  # next run (warm-up, then the timed steps)
+        if state["issued"] == len(state["run"]) and not state["queue"]:  # next run (warm-up, then the timed steps)
             state["run"], state["issued"] = runs.pop(0), 0
         counts.zero()
         st = {}
