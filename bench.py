@@ -326,8 +326,8 @@ def main_ours(args):
             [(s, c) for s in range(E2E_WARMUP, e2e_total) for c in range(n_chr)]]
     state = {"queue": [], "issued": 0, "run": []}
 
-    def top_up():
-        while len(state["queue"]) < LOOKAHEAD and state["issued"] < len(state["run"]):
+    def top_up(target):
+        while len(state["queue"]) < target and state["issued"] < len(state["run"]):
             # read ids stay in pinned host memory: the filter pulls those of the loci it keeps (zero copy)
             state["queue"].append(ctx.upload_lazy_async(chunks[state["run"][state["issued"]][1]]))
             state["issued"] += 1
@@ -338,10 +338,12 @@ def main_ours(args):
         counts.zero()
         st = {}
         for c in range(n_chr):
-            top_up()
+            top_up(1)
             cur = state["queue"].pop(0)
-            top_up()
             filtered, _ = flt.filter_device(cur, ident)
+            # DMA of the coming chromosomes is queued where the kernels leave the H2D direction of the bus idle
+            # (accumulate, and the D2H of the matrix below), not next to the filter's zero-copy pull
+            top_up(2)
             s1 = counts.accumulate(filtered, w["L"], ident, w["eps"], w["h"], w["theta"], w["num_threads"], args.path)
             st["sig_loci"] = st.get("sig_loci", 0) + filtered.n_loci
             state["pulled_entries"] = state.get("pulled_entries", 0) + filtered.n_entries
@@ -350,6 +352,7 @@ def main_ours(args):
             filtered.free()
             cur.free()
         sdist.reduce_counts(counts, device, dst=0)
+        top_up(LOOKAHEAD)
         if rank == 0:
             counts.finalize(*lik, w["normalization"], out=out_host, to_host=True)
         return st
