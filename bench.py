@@ -314,6 +314,9 @@ def main_ours(args):
         chunks.append(hp)
     out_t = torch.empty((N, N), dtype=torch.float64).pin_memory() if rank == 0 else None
     out_host = out_t.numpy() if rank == 0 else None
+    # second result buffer: the matrix of step s travels to the host (own stream) while step s + 1 is computed
+    out_t2 = torch.empty((N, N), dtype=torch.float64).pin_memory() if rank == 0 else None
+    out_bufs = [out_host, out_t2.numpy()] if rank == 0 else [None, None]
     e2e_steps = max(1, min(args.steps, 3))
     E2E_WARMUP = 2
     e2e_total = E2E_WARMUP + e2e_steps  # warm-up + timed
@@ -354,11 +357,19 @@ def main_ours(args):
         sdist.reduce_counts(counts, device, dst=0)
         top_up(LOOKAHEAD)
         if rank == 0:
-            counts.finalize(*lik, w["normalization"], out=out_host, to_host=True)
+            # the previous step's matrix has to be complete before its buffer's turn comes again; every matrix of
+            # the timed steps is complete before the timed region ends (output_wait below, inside `timed`'s last step)
+            state["n_out"] = state.get("n_out", 0) + 1
+            counts.finalize_async(*lik, w["normalization"], out_bufs[state["n_out"] % 2])
+            if state["n_out"] in (E2E_WARMUP, e2e_total):  # last step of a run: nothing left to overlap with
+                ctx.output_wait()
         return st
 
     ms_e2e, acc_e2e, _, _ = timed(e2e_step, e2e_steps, E2E_WARMUP)
     ctx.synchronize()
+    if rank == 0:
+        ctx.output_wait()
+        out_host = out_bufs[state["n_out"] % 2]
     # bytes that crossed PCIe host -> device per step: the CSR without the read ids, plus the read ids of the
     # entries of the loci the filter kept (all cells take part: every entry of a kept locus is pulled once)
     pulled = state.get("pulled_entries", 0) // e2e_total

@@ -195,6 +195,13 @@ int sgpu_counts_download(sgpu_ctx *ctx, sgpu_counts *c, int32_t *S1, int32_t *D1
 int sgpu_similarity_finalize(sgpu_ctx *ctx, sgpu_counts *c, uint32_t max_fragment_length,
                              double mutation_rate, double homozygous_rate, double seq_error_rate,
                              int normalization, double *out, sgpu_stats *stats);
+/* The same without waiting for the download: the matrix is copied to `out` (page-locked host memory) on a stream of
+ * its own, so that the kernels of the next batch start at once; sgpu_output_wait returns when `out` is complete. At
+ * most one download is in flight per context (a second call first waits for the first). */
+int sgpu_similarity_finalize_async(sgpu_ctx *ctx, sgpu_counts *c, uint32_t max_fragment_length,
+                                   double mutation_rate, double homozygous_rate, double seq_error_rate,
+                                   int normalization, double *out);
+int sgpu_output_wait(sgpu_ctx *ctx);
 /* LS / LD tables as evaluated on the device, n*n row-major (parity with similarity_matrix.cpp:117-170). */
 int sgpu_log_probs(sgpu_ctx *ctx, double mutation_rate, double homozygous_rate, double seq_error_rate,
                    uint32_t max_fragment_length, uint32_t n, double *ls, double *ld);

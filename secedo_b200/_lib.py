@@ -101,6 +101,8 @@ SIGNATURES = {
     "sgpu_counts_download": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp]),
     "sgpu_similarity_finalize": (C.c_int, [_vp, _vp, C.c_uint32, C.c_double, C.c_double, C.c_double, C.c_int, _vp,
                                            C.POINTER(Stats)]),
+    "sgpu_similarity_finalize_async": (C.c_int, [_vp, _vp, C.c_uint32, C.c_double, C.c_double, C.c_double, C.c_int, _vp]),
+    "sgpu_output_wait": (C.c_int, [_vp]),
     "sgpu_log_probs": (C.c_int, [_vp, C.c_double, C.c_double, C.c_double, C.c_uint32, C.c_uint32, _vp, _vp]),
     "sgpu_expectation_maximization": (C.c_int, [_vp, _vp, _vp, C.c_uint32, C.c_double, _vp, C.c_uint32, C.c_uint32, _u32p,
                                                 C.POINTER(C.c_float)]),

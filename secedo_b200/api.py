@@ -55,6 +55,10 @@ class Context:
     def synchronize(self) -> None:
         self.check(self._lib.sgpu_synchronize(self._h))
 
+    def output_wait(self) -> None:
+        """Wait for the download started by :meth:`Counts.finalize_async`."""
+        self.check(self._lib.sgpu_output_wait(self._h))
+
     def launch_count(self) -> int:
         """CUDA kernels launched by this context so far."""
         return int(self._lib.sgpu_launch_count(self._h))
@@ -333,6 +337,19 @@ class Counts:
         if self.last_stats is not None:
             self.last_stats["ms_epilogue"] = st.ms_epilogue
         return out
+
+    def finalize_async(self, max_fragment_length: int, mutation_rate: float, homozygous_rate: float,
+                       seq_error_rate: float, normalization: str, out: np.ndarray) -> None:
+        """Epilogue now, download of the matrix into ``out`` (pinned host memory) on a stream of its own;
+        :meth:`Context.output_wait` returns when ``out`` is complete."""
+        if normalization not in NORMALIZATIONS:
+            raise ValueError("Invalid normalization: " + str(normalization))
+        n = self.num_cells
+        assert out.dtype == np.float64 and out.flags.c_contiguous and out.size == n * n
+        self.ctx.check(self.ctx._lib.sgpu_similarity_finalize_async(self.ctx._h, self._h, int(max_fragment_length),
+                                                                    float(mutation_rate), float(homozygous_rate),
+                                                                    float(seq_error_rate), NORMALIZATIONS[normalization],
+                                                                    _ptr(out)))
 
     def finalize_spectral(self, max_fragment_length: int, mutation_rate: float, homozygous_rate: float,
                           seq_error_rate: float, normalization: str, k: int = 7, tol: float = 0.0,

@@ -195,6 +195,11 @@ void sgpu_shutdown(sgpu_ctx *ctx) {
     if (ctx->own_stream) { // contexts that failed in sgpu_init carry only the error text
         cudaSetDevice(ctx->device);
         cudaStreamSynchronize(ctx->stream);
+        if (ctx->d2h_stream) {
+            cudaStreamSynchronize(ctx->d2h_stream);
+            cudaStreamDestroy(ctx->d2h_stream);
+            cudaEventDestroy(ctx->out_done);
+        }
         sgpu_dev_release_cache(ctx);
         for (auto &b : ctx->live_blocks) { // objects the caller never freed
             cudaFree(b.first);
@@ -693,6 +698,24 @@ int sgpu_similarity_finalize(sgpu_ctx *ctx, sgpu_counts *c, uint32_t max_fragmen
         stats->ms_epilogue = ms;
     }
     return SGPU_OK;
+}
+
+int sgpu_similarity_finalize_async(sgpu_ctx *ctx, sgpu_counts *c, uint32_t max_fragment_length, double mutation_rate,
+                                   double homozygous_rate, double seq_error_rate, int normalization, double *out) {
+    SGPU_CUDA(ctx, cudaSetDevice(ctx->device));
+    if (!out) {
+        return sgpu_fail(ctx, SGPU_E_ARG, "finalize_async needs a (page-locked) host buffer");
+    }
+    if (c->have_params && c->spill
+        && (c->eps != mutation_rate || c->h != homozygous_rate || c->theta != seq_error_rate || c->L != max_fragment_length)) {
+        return sgpu_fail(ctx, SGPU_E_ARG, "finalize called with likelihood parameters different from accumulate");
+    }
+    return sgpu_epilogue(ctx, c, max_fragment_length, mutation_rate, homozygous_rate, seq_error_rate, normalization, out, nullptr, true);
+}
+
+int sgpu_output_wait(sgpu_ctx *ctx) {
+    SGPU_CUDA(ctx, cudaSetDevice(ctx->device));
+    return sgpu_output_wait_impl(ctx);
 }
 
 int sgpu_similarity(sgpu_ctx *ctx, const sgpu_pileup *filtered, uint32_t num_cells, uint32_t max_fragment_length,

@@ -22,6 +22,10 @@ struct sgpu_ctx {
     cudaStream_t own_stream = nullptr;
     cudaStream_t stream = nullptr;
     cudaStream_t copy_stream = nullptr; // sgpu_pileup_upload_async
+    // sgpu_similarity_finalize_async: the matrix goes to the host on its own stream while the next batch is computed
+    cudaStream_t d2h_stream = nullptr;
+    cudaEvent_t out_done = nullptr;
+    void *pending_out = nullptr; // device matrix of the download in flight (returned to the cache by sgpu_output_wait)
     std::string error;
     // small pinned scratch for device->host scalars
     uint64_t *h_scratch = nullptr; // 64 x u64, pinned
@@ -266,7 +270,8 @@ int sgpu_log_probs_impl(sgpu_ctx *ctx, double eps, double h, double theta, uint3
                         double *h_ls, double *h_ld);
 // d_keep != NULL: the device matrix is handed to the caller (free with sgpu_dev_free)
 int sgpu_epilogue(sgpu_ctx *ctx, sgpu_counts *c, uint32_t L, double eps, double h, double theta,
-                  int normalization, double *h_out, double **d_keep = nullptr);
+                  int normalization, double *h_out, double **d_keep = nullptr, bool async_out = false);
+int sgpu_output_wait_impl(sgpu_ctx *ctx);
 
 // em.cu
 int sgpu_em_impl(sgpu_ctx *ctx, const sgpu_pileup *p, const uint32_t *h_id_to_pos, uint32_t n_groups, double theta,

@@ -342,8 +342,18 @@ int sgpu_build_gtable(sgpu_ctx *ctx, double eps, double h, double theta, uint32_
     return SGPU_OK;
 }
 
+int sgpu_output_wait_impl(sgpu_ctx *ctx) {
+    if (ctx->pending_out) {
+        SGPU_CUDA(ctx, cudaEventSynchronize(ctx->out_done));
+        // the block's last user ran on the download stream and has finished: safe to hand out again
+        sgpu_dev_free(ctx, ctx->pending_out);
+        ctx->pending_out = nullptr;
+    }
+    return SGPU_OK;
+}
+
 int sgpu_epilogue(sgpu_ctx *ctx, sgpu_counts *c, uint32_t L, double eps, double h, double theta, int normalization,
-                  double *h_out, double **d_keep) {
+                  double *h_out, double **d_keep, bool async_out) {
     cudaStream_t st = ctx->stream;
     if (normalization < 0 || normalization > 2) {
         return sgpu_fail(ctx, SGPU_E_ARG, "Invalid normalization: %d", normalization); // similarity_matrix.cpp:264
@@ -424,6 +434,23 @@ int sgpu_epilogue(sgpu_ctx *ctx, sgpu_counts *c, uint32_t L, double eps, double 
     }
     SGPU_LAUNCH(ctx, (finalize_kernel<<<n_tiles, TR_THREADS, 0, st>>>(a, d_tiles, d_minmax.p, normalization, out.p)));
     SGPU_CUDA(ctx, cudaGetLastError());
+    if (h_out && async_out) {
+        // download on a stream of its own, behind the kernels above; the caller collects it with sgpu_output_wait
+        SGPU_TRY(sgpu_output_wait_impl(ctx));
+        if (!ctx->d2h_stream) {
+            SGPU_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->d2h_stream, cudaStreamNonBlocking));
+            SGPU_CUDA(ctx, cudaEventCreateWithFlags(&ctx->out_done, cudaEventDisableTiming));
+        }
+        cudaEvent_t ev;
+        SGPU_CUDA(ctx, cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+        SGPU_CUDA(ctx, cudaEventRecord(ev, st));
+        SGPU_CUDA(ctx, cudaStreamWaitEvent(ctx->d2h_stream, ev, 0));
+        SGPU_CUDA(ctx, cudaEventDestroy(ev));
+        SGPU_CUDA(ctx, cudaMemcpyAsync(h_out, out.p, c->nn * sizeof(double), cudaMemcpyDeviceToHost, ctx->d2h_stream));
+        SGPU_CUDA(ctx, cudaEventRecord(ctx->out_done, ctx->d2h_stream));
+        ctx->pending_out = out.take();
+        return SGPU_OK;
+    }
     if (h_out) { // NULL: leave the result on the device (timing of the device-resident path)
         SGPU_CUDA(ctx, cudaMemcpyAsync(h_out, out.p, c->nn * sizeof(double), cudaMemcpyDeviceToHost, st));
     }

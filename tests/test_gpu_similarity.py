@@ -375,3 +375,24 @@ def test_global_hash_linking(gpu_ctx, path, monkeypatch):
     f, _ = api.Filter(0.01, 4, gpu_ctx).filter(p, ident, "", 1)
     st, o = check_counts(gpu_ctx, f, cfg.n_cells, 1000, ident, 0.01, 0.5, 0.01, 2, path)
     assert st["n_multi_reads"] > 0 and st["n_dropped_entries"] > 0
+
+
+def test_finalize_async_matches_finalize(gpu_ctx):
+    """the matrix downloaded on its own stream (sgpu_similarity_finalize_async + sgpu_output_wait) while the next batch is
+    already being accumulated equals the synchronous result; a second download first waits for the first"""
+    import torch
+    cfg = SynthConfig(n_cells=500, coverage=0.3, n_loci=1500, n_chr=2, p_multi=0.1, p_mate=0.05, theta=0.01, seed=19)
+    ident = np.arange(cfg.n_cells, dtype=np.uint32)
+    f, _ = api.Filter(0.01, 4, gpu_ctx).filter(make_pileup(cfg), ident, "", 1)
+    c = api.Counts(gpu_ctx, cfg.n_cells)
+    c.accumulate(f, 1000, ident, 0.01, 0.5, 0.01, 8, "gemm")
+    want = c.finalize(1000, 0.01, 0.5, 0.01, "ADD_MIN")
+    bufs = [torch.zeros((cfg.n_cells, cfg.n_cells), dtype=torch.float64).pin_memory().numpy() for _ in range(2)]
+    c.finalize_async(1000, 0.01, 0.5, 0.01, "ADD_MIN", bufs[0])
+    c.accumulate(f, 1000, ident, 0.01, 0.5, 0.01, 8, "gemm")  # twice the counts, while the first matrix travels
+    c.finalize_async(1000, 0.01, 0.5, 0.01, "EXPONENTIATE", bufs[1])
+    gpu_ctx.output_wait()
+    assert np.array_equal(bufs[0], want)
+    assert np.array_equal(bufs[1], c.finalize(1000, 0.01, 0.5, 0.01, "EXPONENTIATE"))
+    gpu_ctx.output_wait()  # nothing in flight: returns at once
+    c.free()
