@@ -340,22 +340,37 @@ def main_ours(args):
             state["run"], state["issued"] = runs.pop(0), 0
         counts.zero()
         st = {}
+        tr = state.setdefault("trace", {}) if os.environ.get("SECEDO_BENCH_E2E_TRACE") else None
+        t_prev = time.perf_counter()
+
+        def lap(name):
+            nonlocal t_prev
+            if tr is not None:
+                now = time.perf_counter()
+                tr[name] = tr.get(name, 0.0) + (now - t_prev) * 1e3
+                t_prev = now
         for c in range(n_chr):
             top_up(1)
             cur = state["queue"].pop(0)
+            lap("issue")
             filtered, _ = flt.filter_device(cur, ident)
+            lap("filter")
             # DMA of the coming chromosomes is queued where the kernels leave the H2D direction of the bus idle
             # (accumulate, and the D2H of the matrix below), not next to the filter's zero-copy pull
             top_up(2)
+            lap("issue")
             s1 = counts.accumulate(filtered, w["L"], ident, w["eps"], w["h"], w["theta"], w["num_threads"], args.path)
             st["sig_loci"] = st.get("sig_loci", 0) + filtered.n_loci
             state["pulled_entries"] = state.get("pulled_entries", 0) + filtered.n_entries
             for k in ("ms_gemm", "ms_stage", "ms_link", "ms_first_order", "ms_multi", "gemm_launches"):
                 st[k] = st.get(k, 0) + (s1.get(k, 0) or 0)
+            lap("accumulate")
             filtered.free()
             cur.free()
+            lap("free")
         sdist.reduce_counts(counts, device, dst=0)
         top_up(LOOKAHEAD)
+        lap("issue")
         if rank == 0:
             # the previous step's matrix has to be complete before its buffer's turn comes again; every matrix of
             # the timed steps is complete before the timed region ends (output_wait below, inside `timed`'s last step)
@@ -363,6 +378,9 @@ def main_ours(args):
             counts.finalize_async(*lik, w["normalization"], out_bufs[state["n_out"] % 2])
             if state["n_out"] in (E2E_WARMUP, e2e_total):  # last step of a run: nothing left to overlap with
                 ctx.output_wait()
+        lap("finalize")
+        if tr is not None:
+            sys.stderr.write("e2e trace (ms, cumulative): " + json.dumps({k: round(v, 2) for k, v in tr.items()}) + "\n")
         return st
 
     ms_e2e, acc_e2e, _, _ = timed(e2e_step, e2e_steps, E2E_WARMUP)
