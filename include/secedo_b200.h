@@ -186,6 +186,17 @@ int sgpu_counts_set_layout(sgpu_ctx *ctx, sgpu_counts *c, int planes_used /* 2, 
  * sgpu_counts_unpack on the destination rank writes the sums back into the planes. */
 int sgpu_counts_pack(sgpu_ctx *ctx, sgpu_counts *c, int32_t **packed, uint64_t *n);
 int sgpu_counts_unpack(sgpu_ctx *ctx, sgpu_counts *c);
+/* The same for planes [first_plane, first_plane + n_planes) only. */
+int sgpu_counts_pack_range(sgpu_ctx *ctx, sgpu_counts *c, int first_plane, int n_planes, int32_t **packed, uint64_t *n);
+int sgpu_counts_unpack_range(sgpu_ctx *ctx, sgpu_counts *c, int first_plane, int n_planes);
+/* The planes beyond S and D count read pairs that overlap at >= 2 loci and are almost empty on real pileups: their
+ * non-zeros (upper triangle) as a list of (idx, val), idx = position relative to plane `first_plane`
+ * (plane * num_cells^2 + i * num_cells + j, 32 bits), in device buffers owned by the counts object. The order of the
+ * list is not defined. sgpu_counts_sparse_add adds such a list (e.g. another rank's) into the planes; indices of one
+ * list must be distinct. With these the cross-rank reduction sends S and D densely and the rest as lists. */
+int sgpu_counts_sparse_pack(sgpu_ctx *ctx, sgpu_counts *c, int first_plane, uint32_t **idx, int32_t **val, uint64_t *nnz);
+int sgpu_counts_sparse_add(sgpu_ctx *ctx, sgpu_counts *c, int first_plane, const uint32_t *idx, const int32_t *val,
+                           uint64_t nnz);
 /* Symmetric per-cell-pair integers for bit-exact checks (any pointer may be NULL):
  *   S1, D1  num_cells^2 int32: incidences (read pair, shared locus) with equal / different base
  *   H       3*num_cells^2 int32: read pairs in overlap class (2,0), (1,1), (0,2)

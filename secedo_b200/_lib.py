@@ -98,6 +98,10 @@ SIGNATURES = {
     "sgpu_counts_set_layout": (C.c_int, [_vp, _vp, C.c_int, C.c_int]),
     "sgpu_counts_pack": (C.c_int, [_vp, _vp, C.POINTER(_vp), _u64p]),
     "sgpu_counts_unpack": (C.c_int, [_vp, _vp]),
+    "sgpu_counts_pack_range": (C.c_int, [_vp, _vp, C.c_int, C.c_int, C.POINTER(_vp), _u64p]),
+    "sgpu_counts_unpack_range": (C.c_int, [_vp, _vp, C.c_int, C.c_int]),
+    "sgpu_counts_sparse_pack": (C.c_int, [_vp, _vp, C.c_int, C.POINTER(_vp), C.POINTER(_vp), _u64p]),
+    "sgpu_counts_sparse_add": (C.c_int, [_vp, _vp, C.c_int, _vp, _vp, C.c_uint64]),
     "sgpu_counts_download": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp]),
     "sgpu_similarity_finalize": (C.c_int, [_vp, _vp, C.c_uint32, C.c_double, C.c_double, C.c_double, C.c_int, _vp,
                                            C.POINTER(Stats)]),

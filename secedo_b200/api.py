@@ -307,6 +307,26 @@ class Counts:
         """Packed buffer (after the cross-rank reduction) back into the planes."""
         self.ctx.check(self.ctx._lib.sgpu_counts_unpack(self.ctx._h, self._h))
 
+    def pack_range(self, first_plane: int, n_planes: int):
+        ptr, n = C.c_void_p(), C.c_uint64()
+        self.ctx.check(self.ctx._lib.sgpu_counts_pack_range(self.ctx._h, self._h, int(first_plane), int(n_planes), C.byref(ptr),
+                                                            C.byref(n)))
+        return ptr.value, n.value
+
+    def unpack_range(self, first_plane: int, n_planes: int) -> None:
+        self.ctx.check(self.ctx._lib.sgpu_counts_unpack_range(self.ctx._h, self._h, int(first_plane), int(n_planes)))
+
+    def sparse_pack(self, first_plane: int = 2):
+        """Non-zeros of the planes from ``first_plane`` on as device lists: (idx pointer, val pointer, nnz)."""
+        idx, val, nnz = C.c_void_p(), C.c_void_p(), C.c_uint64()
+        self.ctx.check(self.ctx._lib.sgpu_counts_sparse_pack(self.ctx._h, self._h, int(first_plane), C.byref(idx), C.byref(val),
+                                                             C.byref(nnz)))
+        return idx.value, val.value, nnz.value
+
+    def sparse_add(self, first_plane: int, idx_ptr: int, val_ptr: int, nnz: int) -> None:
+        self.ctx.check(self.ctx._lib.sgpu_counts_sparse_add(self.ctx._h, self._h, int(first_plane), C.c_void_p(idx_ptr),
+                                                            C.c_void_p(val_ptr), int(nnz)))
+
     def download(self):
         """Symmetric host copies: (S1, D1, H[3], class_hist) for bit-exact checks."""
         n = self.num_cells

@@ -110,6 +110,60 @@ __global__ void __launch_bounds__(256) tri_pack_kernel(int32_t *__restrict__ pla
     }
 }
 
+// non-zeros of the upper triangles (i < j) of `n_planes` planes: count, then append (index relative to the first of the
+// planes = plane * n^2 + i * n + j, value). Warp-aggregated append: the ORDER of the list varies from run to run, its
+// content does not, and it is only ever added into planes (commutative).
+template <bool WRITE>
+__global__ void __launch_bounds__(256) sparse_scan_kernel(const int32_t *__restrict__ planes, uint32_t n, uint32_t n_planes,
+                                                          unsigned long long *__restrict__ cursor, uint32_t *__restrict__ idx,
+                                                          int32_t *__restrict__ val) {
+    const uint64_t nn = static_cast<uint64_t>(n) * n;
+    const int lane = threadIdx.x & 31;
+    unsigned long long mine = 0;
+    for (uint64_t row = blockIdx.x; row < static_cast<uint64_t>(n_planes) * n; row += gridDim.x) {
+        const uint32_t pl = static_cast<uint32_t>(row / n), i = static_cast<uint32_t>(row - static_cast<uint64_t>(pl) * n);
+        const int32_t *src = planes + pl * nn + static_cast<uint64_t>(i) * n;
+        for (uint32_t j0 = i + 1; j0 < n; j0 += 256) {
+            const uint32_t j = j0 + threadIdx.x;
+            const int32_t v = j < n ? src[j] : 0;
+            if (!WRITE) {
+                mine += v != 0;
+            } else {
+                const unsigned m = __ballot_sync(0xFFFFFFFFu, v != 0);
+                if (m) {
+                    unsigned long long base = 0;
+                    if (lane == 0) {
+                        base = atomicAdd(cursor, static_cast<unsigned long long>(__popc(m)));
+                    }
+                    base = __shfl_sync(0xFFFFFFFFu, base, 0);
+                    if (v != 0) {
+                        const unsigned long long o = base + __popc(m & ((1u << lane) - 1u));
+                        idx[o] = static_cast<uint32_t>(pl * nn + static_cast<uint64_t>(i) * n + j);
+                        val[o] = v;
+                    }
+                }
+            }
+        }
+    }
+    if (!WRITE) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            mine += __shfl_xor_sync(0xFFFFFFFFu, mine, o);
+        }
+        if (lane == 0 && mine) {
+            atomicAdd(cursor, mine);
+        }
+    }
+}
+
+__global__ void sparse_add_kernel(int32_t *__restrict__ planes, const uint32_t *__restrict__ idx, const int32_t *__restrict__ val,
+                                  uint64_t nnz) {
+    const uint64_t k = static_cast<uint64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (k < nnz && val[k] != 0) {
+        planes[idx[k]] += val[k]; // the indices of one list are distinct
+    }
+}
+
 struct EventTimer {
     cudaEvent_t a = nullptr, b = nullptr;
     cudaStream_t st;
@@ -499,6 +553,8 @@ void sgpu_counts_free(sgpu_ctx *ctx, sgpu_counts *c) {
     cudaFree(c->spill);
     if (ctx) {
         sgpu_dev_free(ctx, c->packed);
+        sgpu_dev_free(ctx, c->sp_idx);
+        sgpu_dev_free(ctx, c->sp_val);
     }
     delete c;
 }
@@ -609,9 +665,12 @@ int sgpu_counts_set_layout(sgpu_ctx *ctx, sgpu_counts *c, int planes_used, int w
     return SGPU_OK;
 }
 
-int sgpu_counts_pack(sgpu_ctx *ctx, sgpu_counts *c, int32_t **packed, uint64_t *n) {
+int sgpu_counts_pack_range(sgpu_ctx *ctx, sgpu_counts *c, int first_plane, int n_planes, int32_t **packed, uint64_t *n) {
     SGPU_CUDA(ctx, cudaSetDevice(ctx->device));
-    const uint64_t need = static_cast<uint64_t>(c->planes_used) * c->n * (c->n ? c->n - 1 : 0) / 2;
+    if (first_plane < 0 || n_planes < 0 || first_plane + n_planes > c->planes_used) {
+        return sgpu_fail(ctx, SGPU_E_ARG, "plane range [%d, %d) outside the %d planes in use", first_plane, first_plane + n_planes, c->planes_used);
+    }
+    const uint64_t need = static_cast<uint64_t>(n_planes) * c->n * (c->n ? c->n - 1 : 0) / 2;
     if (c->packed_n < need) {
         sgpu_dev_free(ctx, c->packed);
         c->packed = nullptr;
@@ -619,9 +678,10 @@ int sgpu_counts_pack(sgpu_ctx *ctx, sgpu_counts *c, int32_t **packed, uint64_t *
         c->packed_n = need;
     }
     if (need) {
-        const unsigned grid = static_cast<unsigned>(std::min<uint64_t>(static_cast<uint64_t>(c->planes_used) * c->n,
+        const unsigned grid = static_cast<unsigned>(std::min<uint64_t>(static_cast<uint64_t>(n_planes) * c->n,
                                                                       static_cast<uint64_t>(ctx->sm_count) * 16));
-        SGPU_LAUNCH(ctx, (tri_pack_kernel<true><<<grid, 256, 0, ctx->stream>>>(c->i32, c->packed, c->n, c->planes_used)));
+        SGPU_LAUNCH(ctx, (tri_pack_kernel<true><<<grid, 256, 0, ctx->stream>>>(c->i32 + static_cast<uint64_t>(first_plane) * c->nn, c->packed,
+                                                                              c->n, n_planes)));
         SGPU_CUDA(ctx, cudaGetLastError());
     }
     if (packed) {
@@ -633,19 +693,94 @@ int sgpu_counts_pack(sgpu_ctx *ctx, sgpu_counts *c, int32_t **packed, uint64_t *
     return SGPU_OK;
 }
 
-int sgpu_counts_unpack(sgpu_ctx *ctx, sgpu_counts *c) {
+int sgpu_counts_unpack_range(sgpu_ctx *ctx, sgpu_counts *c, int first_plane, int n_planes) {
     SGPU_CUDA(ctx, cudaSetDevice(ctx->device));
-    const uint64_t need = static_cast<uint64_t>(c->planes_used) * c->n * (c->n ? c->n - 1 : 0) / 2;
+    if (first_plane < 0 || n_planes < 0 || first_plane + n_planes > c->planes_used) {
+        return sgpu_fail(ctx, SGPU_E_ARG, "plane range [%d, %d) outside the %d planes in use", first_plane, first_plane + n_planes, c->planes_used);
+    }
+    const uint64_t need = static_cast<uint64_t>(n_planes) * c->n * (c->n ? c->n - 1 : 0) / 2;
     if (c->packed == nullptr || c->packed_n < need) {
         return sgpu_fail(ctx, SGPU_E_ARG, "sgpu_counts_unpack without a matching sgpu_counts_pack");
     }
     if (need) {
-        const unsigned grid = static_cast<unsigned>(std::min<uint64_t>(static_cast<uint64_t>(c->planes_used) * c->n,
+        const unsigned grid = static_cast<unsigned>(std::min<uint64_t>(static_cast<uint64_t>(n_planes) * c->n,
                                                                       static_cast<uint64_t>(ctx->sm_count) * 16));
-        SGPU_LAUNCH(ctx, (tri_pack_kernel<false><<<grid, 256, 0, ctx->stream>>>(c->i32, c->packed, c->n, c->planes_used)));
+        SGPU_LAUNCH(ctx, (tri_pack_kernel<false><<<grid, 256, 0, ctx->stream>>>(c->i32 + static_cast<uint64_t>(first_plane) * c->nn, c->packed,
+                                                                               c->n, n_planes)));
         SGPU_CUDA(ctx, cudaGetLastError());
     }
     c->fresh = false;
+    return SGPU_OK;
+}
+
+int sgpu_counts_pack(sgpu_ctx *ctx, sgpu_counts *c, int32_t **packed, uint64_t *n) {
+    return sgpu_counts_pack_range(ctx, c, 0, c->planes_used, packed, n);
+}
+
+int sgpu_counts_unpack(sgpu_ctx *ctx, sgpu_counts *c) {
+    return sgpu_counts_unpack_range(ctx, c, 0, c->planes_used);
+}
+
+int sgpu_counts_sparse_pack(sgpu_ctx *ctx, sgpu_counts *c, int first_plane, uint32_t **idx, int32_t **val, uint64_t *nnz) {
+    SGPU_CUDA(ctx, cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    const int n_planes = c->planes_used - first_plane;
+    if (first_plane < 0 || n_planes < 0) {
+        return sgpu_fail(ctx, SGPU_E_ARG, "first plane %d outside the %d planes in use", first_plane, c->planes_used);
+    }
+    if (static_cast<uint64_t>(n_planes) * c->nn > 0xFFFFFFFFull) {
+        return sgpu_fail(ctx, SGPU_E_ARG, "sparse lists index with 32 bits: %d planes of %u^2 do not fit", n_planes, c->n);
+    }
+    uint64_t count = 0;
+    if (n_planes && c->n > 1) {
+        const int32_t *planes = c->i32 + static_cast<uint64_t>(first_plane) * c->nn;
+        const unsigned grid = static_cast<unsigned>(std::min<uint64_t>(static_cast<uint64_t>(n_planes) * c->n, static_cast<uint64_t>(ctx->sm_count) * 16));
+        unsigned long long *cursor = reinterpret_cast<unsigned long long *>(ctx->d_scratch);
+        SGPU_CUDA(ctx, cudaMemsetAsync(cursor, 0, sizeof(unsigned long long), st));
+        SGPU_LAUNCH(ctx, (sparse_scan_kernel<false><<<grid, 256, 0, st>>>(planes, c->n, n_planes, cursor, nullptr, nullptr)));
+        SGPU_CUDA(ctx, cudaMemcpyAsync(&ctx->h_scratch[0], cursor, sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
+        SGPU_CUDA(ctx, cudaStreamSynchronize(st));
+        count = ctx->h_scratch[0];
+        if (c->sp_cap < count) {
+            sgpu_dev_free(ctx, c->sp_idx);
+            sgpu_dev_free(ctx, c->sp_val);
+            c->sp_idx = nullptr;
+            c->sp_val = nullptr;
+            c->sp_cap = 0;
+            const uint64_t cap = count + count / 4 + 1024;
+            SGPU_CUDA(ctx, sgpu_dev_alloc(ctx, reinterpret_cast<void **>(&c->sp_idx), cap * sizeof(uint32_t)));
+            SGPU_CUDA(ctx, sgpu_dev_alloc(ctx, reinterpret_cast<void **>(&c->sp_val), cap * sizeof(int32_t)));
+            c->sp_cap = cap;
+        }
+        if (count) {
+            SGPU_CUDA(ctx, cudaMemsetAsync(cursor, 0, sizeof(unsigned long long), st));
+            SGPU_LAUNCH(ctx, (sparse_scan_kernel<true><<<grid, 256, 0, st>>>(planes, c->n, n_planes, cursor, c->sp_idx, c->sp_val)));
+        }
+        SGPU_CUDA(ctx, cudaGetLastError());
+    }
+    if (idx) {
+        *idx = c->sp_idx;
+    }
+    if (val) {
+        *val = c->sp_val;
+    }
+    if (nnz) {
+        *nnz = count;
+    }
+    return SGPU_OK;
+}
+
+int sgpu_counts_sparse_add(sgpu_ctx *ctx, sgpu_counts *c, int first_plane, const uint32_t *idx, const int32_t *val, uint64_t nnz) {
+    SGPU_CUDA(ctx, cudaSetDevice(ctx->device));
+    if (first_plane < 0 || first_plane > c->planes_used) {
+        return sgpu_fail(ctx, SGPU_E_ARG, "first plane %d outside the %d planes in use", first_plane, c->planes_used);
+    }
+    if (nnz) {
+        SGPU_LAUNCH(ctx, (sparse_add_kernel<<<static_cast<unsigned>((nnz + 255) / 256), 256, 0, ctx->stream>>>(
+                              c->i32 + static_cast<uint64_t>(first_plane) * c->nn, idx, val, nnz)));
+        SGPU_CUDA(ctx, cudaGetLastError());
+        c->fresh = false;
+    }
     return SGPU_OK;
 }
 

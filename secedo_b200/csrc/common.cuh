@@ -171,6 +171,9 @@ struct sgpu_counts {
     bool fresh = false;         // S and D are all zero (nothing accumulated since sgpu_counts_zero)
     int32_t *packed = nullptr;  // upper triangles of the planes in use, for the cross-rank reduction (lazy)
     uint64_t packed_n = 0;
+    uint32_t *sp_idx = nullptr; // non-zeros of the sparse (second / third order) planes as (index, value) lists (lazy)
+    int32_t *sp_val = nullptr;
+    uint64_t sp_cap = 0;
     double *spill = nullptr;    // n*n doubles: sum of G(x_s,x_d) over pairs with x_s+x_d >= 4 (lazy)
     uint64_t *hist = nullptr;   // SGPU_MAX_CLASS^2 class histogram (pairs with x_s+x_d >= 2)
     // log-likelihood parameters the spill plane was accumulated with (must match at finalize)

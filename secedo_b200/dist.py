@@ -12,6 +12,7 @@ Everything here is backend agnostic (the CPU tests run it with gloo and world_si
 """
 from __future__ import annotations
 
+import os
 from typing import List, Optional, Sequence
 
 import numpy as np
@@ -71,22 +72,75 @@ def counts_tensors(counts, device: torch.device) -> List[torch.Tensor]:
             tensor_from_ptr(hist, n_hist, torch.int64, device)]
 
 
+def exchange_sparse(idx: torch.Tensor, val: torch.Tensor, dst: int = 0, group=None):
+    """Variable-length (index, value) lists of all ranks -> rank ``dst``: returns, on ``dst``, the lists of the OTHER
+    ranks as [(idx, val), ...] (int32 tensors; idx carries the bits of a uint32) and an empty list elsewhere. One
+    all_gather of the lengths, one gather of the lists padded to the longest."""
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    n = torch.tensor([idx.numel()], dtype=torch.int64, device=idx.device)
+    lens = [torch.zeros_like(n) for _ in range(world)]
+    dist.all_gather(lens, n, group=group)
+    lens = [int(x.item()) for x in lens]
+    longest = max(lens)
+    if longest == 0:
+        return []
+    mine = torch.zeros(2 * longest, dtype=torch.int32, device=idx.device)
+    mine[: idx.numel()] = idx
+    mine[longest: longest + val.numel()] = val
+    if rank == dst:
+        got = [torch.empty_like(mine) for _ in range(world)]
+        dist.gather(mine, got, dst=dst, group=group)
+        return [(g[: lens[r]], g[longest: longest + lens[r]]) for r, g in enumerate(got) if r != dst and lens[r]]
+    dist.gather(mine, None, dst=dst, group=group)
+    return []
+
+
+def sparse_pays(nnz_per_rank: Sequence[int], dst: int, n_sparse_planes: int, num_cells: int) -> bool:
+    """The lists of the other ranks (8 bytes per non-zero into ``dst``) against a dense reduction of the packed planes."""
+    others = sum(nnz_per_rank) - nnz_per_rank[dst]
+    dense = 4 * n_sparse_planes * num_cells * (num_cells - 1) // 2
+    return n_sparse_planes > 0 and 8 * others < dense // 2
+
+
 def reduce_counts(counts, device: torch.device, dst: int = 0, group=None) -> None:
-    """Agree on the buffer layout, then sum the count planes of all ranks onto ``dst``. Only the upper
-    triangles of the planes in use travel: they are packed into one contiguous buffer on every rank
-    (``sgpu_counts_pack``), summed with ONE reduction, and unpacked on ``dst``."""
+    """Agree on the buffer layout, then sum the count planes of all ranks onto ``dst``. Only upper triangles travel.
+    S and D are packed into one contiguous buffer on every rank (``sgpu_counts_pack_range``), summed with ONE reduction
+    and unpacked on ``dst``. The planes of the read pairs that overlap at >= 2 loci hold few non-zeros on real
+    pileups: where that pays (:func:`sparse_pays`) every rank sends their non-zeros as a list
+    (``sgpu_counts_sparse_pack``) and ``dst`` adds the lists into its own planes - 8 bytes per non-zero instead of
+    4 bytes per cell pair and plane."""
     if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
         return
+    world = dist.get_world_size(group)
     i32, n_i32, f64, n_f64, hist, n_hist = counts.buffers()
-    nn = counts.num_cells * counts.num_cells
+    nc = counts.num_cells
+    nn = nc * nc
     planes, spill = agree_layout(n_i32 // nn if nn else 2, n_f64 > 0, device, group)
     counts.set_layout(planes, spill)
-    ptr, n = counts.pack()
+    use_sparse, idx_t, val_t = False, None, None
+    if planes > 2 and (planes - 2) * nn <= 0xFFFFFFFF:
+        ip, vp, nnz = counts.sparse_pack(2)
+        t = torch.tensor([nnz], dtype=torch.int64, device=device)
+        all_nnz = [torch.zeros_like(t) for _ in range(world)]
+        dist.all_gather(all_nnz, t, group=group)
+        use_sparse = sparse_pays([int(x.item()) for x in all_nnz], dst, planes - 2, nc)
+        force = os.environ.get("SECEDO_B200_SPARSE_REDUCE")  # tests: "1" / "0" force one route on every rank
+        if force in ("0", "1"):
+            use_sparse = force == "1"
+        if use_sparse:
+            idx_t, val_t = tensor_from_ptr(ip, nnz, torch.int32, device), tensor_from_ptr(vp, nnz, torch.int32, device)
+    dense_planes = 2 if use_sparse else planes
+    ptr, n = counts.pack_range(0, dense_planes)
     counts.ctx.synchronize()  # the library's stream need not be the one the collective is ordered on
     _, _, f64, n_f64, hist, n_hist = counts.buffers()
     reduce_buffers([tensor_from_ptr(ptr, n, torch.int32, device), tensor_from_ptr(f64, n_f64, torch.float64, device),
                     tensor_from_ptr(hist, n_hist, torch.int64, device)], dst, group)
+    lists = exchange_sparse(idx_t, val_t, dst, group) if use_sparse else []
     if dist.get_rank(group) == dst:
         if device is not None and torch.device(device).type == "cuda":
             torch.cuda.current_stream(device).synchronize()  # the sums have arrived before they are unpacked
-        counts.unpack()
+        counts.unpack_range(0, dense_planes)
+        for li, lv in lists:
+            counts.sparse_add(2, li.data_ptr(), lv.data_ptr(), li.numel())
+        if lists:
+            counts.ctx.synchronize()  # the gathered lists may be released

@@ -38,7 +38,12 @@ def main():
     mine = sdist.partition_chromosomes(weights, world)[rank]
     local_p = Pileup.concat([p.loci_range(c, 0, 1 << 40) for c in mine]) if mine else Pileup.empty(0)
     flt = api.Filter(theta, 4, ctx)
-    for path in ("gemm", "scatter"):
+    for path, sparse in (("gemm", "1"), ("gemm", "0"), ("scatter", None)):
+        # second-order planes as lists of non-zeros, as dense planes, and whichever the size estimate picks
+        if sparse is None:
+            os.environ.pop("SECEDO_B200_SPARSE_REDUCE", None)
+        else:
+            os.environ["SECEDO_B200_SPARSE_REDUCE"] = sparse
         f_local, _ = flt.filter_device(local_p, ident)
         counts = api.Counts(ctx, cfg.n_cells)
         # rank 1 accumulates without multi-locus reads knowledge of the others: layouts get reconciled
@@ -61,7 +66,7 @@ def main():
             o = po.similarity(f_all.download(), cfg.n_cells, L, ident, eps, h, theta, T, "ADD_MIN")
             assert np.array_equal(S1, o.S1) and np.array_equal(D1, o.D1) and np.array_equal(H, o.H)
             assert np.abs(M - o.M).max() <= 1e-6 * np.abs(o.M).max()
-            print(f"multi_gpu_check[{path}] world={world}: counts bit-identical to 1 GPU and to the oracle, "
+            print(f"multi_gpu_check[{path}, sparse={sparse}] world={world}: counts bit-identical to 1 GPU and to the oracle, "
                   f"reduce {t_red * 1e3:.2f} ms OK", flush=True)
         dist.barrier()
     dist.destroy_process_group()

@@ -11,7 +11,7 @@ import torch.distributed as dist
 import torch.multiprocessing as mp
 
 from conftest import ROOT
-from secedo_b200.dist import agree_layout, partition_chromosomes, reduce_buffers
+from secedo_b200.dist import agree_layout, exchange_sparse, partition_chromosomes, reduce_buffers, sparse_pays
 
 
 def test_partition_is_balanced_and_complete():
@@ -21,6 +21,14 @@ def test_partition_is_balanced_and_complete():
         assert sorted(sum(parts, [])) == list(range(len(w)))
         loads = [sum(w[i] for i in p) for p in parts]
         assert max(loads) <= 1.25 * sum(w) / world + 1
+
+
+def test_sparse_route_decision():
+    n, tri = 8000, 8000 * 7999 // 2
+    assert sparse_pays([3_000_000] * 8, 0, 3, n)            # 7 x 24 MB of lists against 384 MB of packed planes
+    assert not sparse_pays([tri] * 2, 0, 3, n)              # dense planes: lists would be larger
+    assert not sparse_pays([0, 0], 0, 0, n)                 # no sparse planes at all
+    assert sparse_pays([10 ** 9, 5], 0, 3, n)               # only the OTHER ranks' lists travel
 
 
 def _worker(rank, world, port, q):
@@ -53,7 +61,24 @@ def _worker(rank, world, port, q):
         ok = (np.array_equal(bufs[0][0].numpy(), whole.S1) and np.array_equal(bufs[0][1].numpy(), whole.D1)
               and np.array_equal(bufs[0][2:].numpy(), whole.H)
               and np.array_equal(bufs[1].numpy().astype(np.uint64), whole.class_hist))
+    # the sparse route for the second-order planes: every rank's non-zeros (upper triangle) as (index, value) lists,
+    # gathered on rank 0 and added there - what sgpu_counts_sparse_pack / sgpu_counts_sparse_add do on the device
+    n = cfg.n_cells
+    up = np.triu(np.ones((n, n), bool), 1)
+    H = r.H.astype(np.int32) * up
+    flat = H.reshape(-1)
+    nz = np.flatnonzero(flat)
+    idx = torch.from_numpy(nz.astype(np.uint32).view(np.int32).copy())
+    val = torch.from_numpy(flat[nz].copy())
+    lists = exchange_sparse(idx, val, dst=0)
+    if rank == 0:
+        acc = flat.copy()
+        for li, lv in lists:
+            acc[li.numpy().view(np.uint32)] += lv.numpy()
+        ok = ok and len(lists) == world - 1 and np.array_equal(acc.reshape(3, n, n), whole.H * up)
         q.put(bool(ok))
+    else:
+        assert lists == []
     dist.barrier()
     dist.destroy_process_group()
 

@@ -17,4 +17,4 @@ def test_two_gpus_match_one_gpu():
                         "--master-addr", "127.0.0.1", "--master-port", "29533",
                         os.path.join(ROOT, "tests", "multi_gpu_check.py")], capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-4000:]
-    assert r.stdout.count("OK") == 2
+    assert r.stdout.count("OK") == 3

@@ -396,3 +396,37 @@ def test_finalize_async_matches_finalize(gpu_ctx):
     assert np.array_equal(bufs[1], c.finalize(1000, 0.01, 0.5, 0.01, "EXPONENTIATE"))
     gpu_ctx.output_wait()  # nothing in flight: returns at once
     c.free()
+
+
+def test_sparse_plane_lists(gpu_ctx):
+    """sgpu_counts_sparse_pack / sgpu_counts_sparse_add and the plane-range pack: the non-zeros of the second-order
+    planes of one counts object added into another equal the sum of the planes (what the cross-rank reduction does
+    with them), and S, D survive a pack / unpack round trip of their range alone"""
+    cfg = SynthConfig(n_cells=300, coverage=0.4, n_loci=1200, n_chr=2, p_multi=0.3, p_mate=0.05, theta=0.01, seed=23)
+    p = make_pileup(cfg)
+    ident = np.arange(cfg.n_cells, dtype=np.uint32)
+    f, _ = api.Filter(0.01, 4, gpu_ctx).filter(p, ident, "", 1)
+    halves = [f.loci_range(0, 0, 1 << 40), f.loci_range(1, 0, 1 << 40)]
+    a, b, whole = (api.Counts(gpu_ctx, cfg.n_cells) for _ in range(3))
+    a.accumulate(halves[0], 1000, ident, 0.01, 0.5, 0.01, 8, "gemm")
+    b.accumulate(halves[1], 1000, ident, 0.01, 0.5, 0.01, 8, "gemm")
+    whole.accumulate(f, 1000, ident, 0.01, 0.5, 0.01, 8, "gemm")
+    planes = max(a.buffers()[1], b.buffers()[1]) // (cfg.n_cells ** 2)
+    assert planes >= 5
+    a.set_layout(planes, False)
+    b.set_layout(planes, False)
+    ha, hb, hw = a.download()[2], b.download()[2], whole.download()[2]
+    assert np.array_equal(ha + hb, hw) and hw.sum() > 0
+    idx, val, nnz = a.sparse_pack(2)
+    assert nnz >= np.count_nonzero(np.triu(ha, 1).reshape(3, -1).any(0)) and nnz > 0
+    b.sparse_add(2, idx, val, nnz)
+    assert np.array_equal(b.download()[2], hw)
+    s_before = a.download()[:2]
+    a.pack_range(0, 2)
+    a.unpack_range(0, 2)
+    for x, y in zip(a.download()[:2], s_before):
+        assert np.array_equal(x, y)
+    with pytest.raises(api.SgpuError):
+        a.pack_range(1, planes)  # beyond the planes in use
+    for c in (a, b, whole):
+        c.free()
