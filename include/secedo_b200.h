@@ -192,7 +192,7 @@ int sgpu_counts_unpack_range(sgpu_ctx *ctx, sgpu_counts *c, int first_plane, int
 /* The planes beyond S and D count read pairs that overlap at >= 2 loci and are almost empty on real pileups: their
  * non-zeros (upper triangle) as a list of (idx, val), idx = position relative to plane `first_plane`
  * (plane * num_cells^2 + i * num_cells + j, 32 bits), in device buffers owned by the counts object. The order of the
- * list is not defined. sgpu_counts_sparse_add adds such a list (e.g. another rank's) into the planes; indices of one
+ * list is row by row (plane, i, j ascending). sgpu_counts_sparse_add adds such a list (e.g. another rank's) into the planes; indices of one
  * list must be distinct. With these the cross-rank reduction sends S and D densely and the rest as lists. */
 int sgpu_counts_sparse_pack(sgpu_ctx *ctx, sgpu_counts *c, int first_plane, uint32_t **idx, int32_t **val, uint64_t *nnz);
 int sgpu_counts_sparse_add(sgpu_ctx *ctx, sgpu_counts *c, int first_plane, const uint32_t *idx, const int32_t *val,

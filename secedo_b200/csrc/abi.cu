@@ -110,48 +110,62 @@ __global__ void __launch_bounds__(256) tri_pack_kernel(int32_t *__restrict__ pla
     }
 }
 
-// non-zeros of the upper triangles (i < j) of `n_planes` planes: count, then append (index relative to the first of the
-// planes = plane * n^2 + i * n + j, value). Warp-aggregated append: the ORDER of the list varies from run to run, its
-// content does not, and it is only ever added into planes (commutative).
+// non-zeros of the upper triangles (i < j) of `n_planes` planes as a list (index relative to the first of the planes =
+// plane * n^2 + i * n + j, value), row by row: pass 1 counts per row, an exclusive scan gives every row its place,
+// pass 2 writes with a block-wide prefix sum per 256 columns. No global atomics (a first version appended through one
+// global cursor: 1.8 M same-address atomics made it 1.7 ms at 8 000 cells) and a deterministic order.
 template <bool WRITE>
-__global__ void __launch_bounds__(256) sparse_scan_kernel(const int32_t *__restrict__ planes, uint32_t n, uint32_t n_planes,
-                                                          unsigned long long *__restrict__ cursor, uint32_t *__restrict__ idx,
-                                                          int32_t *__restrict__ val) {
+__global__ void __launch_bounds__(256) sparse_rows_kernel(const int32_t *__restrict__ planes, uint32_t n, uint32_t n_planes,
+                                                          uint32_t *__restrict__ row_cnt, const uint64_t *__restrict__ row_off,
+                                                          uint32_t *__restrict__ idx, int32_t *__restrict__ val) {
+    __shared__ uint32_t warp_tot[8];
     const uint64_t nn = static_cast<uint64_t>(n) * n;
-    const int lane = threadIdx.x & 31;
-    unsigned long long mine = 0;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     for (uint64_t row = blockIdx.x; row < static_cast<uint64_t>(n_planes) * n; row += gridDim.x) {
         const uint32_t pl = static_cast<uint32_t>(row / n), i = static_cast<uint32_t>(row - static_cast<uint64_t>(pl) * n);
         const int32_t *src = planes + pl * nn + static_cast<uint64_t>(i) * n;
+        uint64_t base = WRITE ? row_off[row] : 0;
+        uint32_t mine = 0;
         for (uint32_t j0 = i + 1; j0 < n; j0 += 256) {
             const uint32_t j = j0 + threadIdx.x;
             const int32_t v = j < n ? src[j] : 0;
+            const unsigned m = __ballot_sync(0xFFFFFFFFu, v != 0);
             if (!WRITE) {
-                mine += v != 0;
+                mine += lane == 0 ? __popc(m) : 0;
             } else {
-                const unsigned m = __ballot_sync(0xFFFFFFFFu, v != 0);
-                if (m) {
-                    unsigned long long base = 0;
-                    if (lane == 0) {
-                        base = atomicAdd(cursor, static_cast<unsigned long long>(__popc(m)));
-                    }
-                    base = __shfl_sync(0xFFFFFFFFu, base, 0);
-                    if (v != 0) {
-                        const unsigned long long o = base + __popc(m & ((1u << lane) - 1u));
-                        idx[o] = static_cast<uint32_t>(pl * nn + static_cast<uint64_t>(i) * n + j);
-                        val[o] = v;
-                    }
+                if (lane == 0) {
+                    warp_tot[warp] = __popc(m);
                 }
+                __syncthreads();
+                uint32_t before = 0, total = 0;
+#pragma unroll
+                for (int w = 0; w < 8; ++w) {
+                    const uint32_t t = warp_tot[w];
+                    before += w < warp ? t : 0;
+                    total += t;
+                }
+                if (v != 0) {
+                    const uint64_t o = base + before + __popc(m & ((1u << lane) - 1u));
+                    idx[o] = static_cast<uint32_t>(pl * nn + static_cast<uint64_t>(i) * n + j);
+                    val[o] = v;
+                }
+                base += total;
+                __syncthreads();
             }
         }
-    }
-    if (!WRITE) {
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-            mine += __shfl_xor_sync(0xFFFFFFFFu, mine, o);
-        }
-        if (lane == 0 && mine) {
-            atomicAdd(cursor, mine);
+        if (!WRITE) {
+            if (lane == 0) {
+                warp_tot[warp] = mine;
+            }
+            __syncthreads();
+            if (threadIdx.x == 0) {
+                uint32_t t = 0;
+                for (int w = 0; w < 8; ++w) {
+                    t += warp_tot[w];
+                }
+                row_cnt[row] = t;
+            }
+            __syncthreads();
         }
     }
 }
@@ -734,11 +748,15 @@ int sgpu_counts_sparse_pack(sgpu_ctx *ctx, sgpu_counts *c, int first_plane, uint
     uint64_t count = 0;
     if (n_planes && c->n > 1) {
         const int32_t *planes = c->i32 + static_cast<uint64_t>(first_plane) * c->nn;
-        const unsigned grid = static_cast<unsigned>(std::min<uint64_t>(static_cast<uint64_t>(n_planes) * c->n, static_cast<uint64_t>(ctx->sm_count) * 16));
-        unsigned long long *cursor = reinterpret_cast<unsigned long long *>(ctx->d_scratch);
-        SGPU_CUDA(ctx, cudaMemsetAsync(cursor, 0, sizeof(unsigned long long), st));
-        SGPU_LAUNCH(ctx, (sparse_scan_kernel<false><<<grid, 256, 0, st>>>(planes, c->n, n_planes, cursor, nullptr, nullptr)));
-        SGPU_CUDA(ctx, cudaMemcpyAsync(&ctx->h_scratch[0], cursor, sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
+        const uint64_t rows = static_cast<uint64_t>(n_planes) * c->n;
+        const unsigned grid = static_cast<unsigned>(std::min<uint64_t>(rows, static_cast<uint64_t>(ctx->sm_count) * 16));
+        DevBuf<uint32_t> row_cnt;
+        DevBuf<uint64_t> row_off;
+        SGPU_CUDA(ctx, row_cnt.alloc(rows, ctx));
+        SGPU_CUDA(ctx, row_off.alloc(rows + 1, ctx));
+        SGPU_LAUNCH(ctx, (sparse_rows_kernel<false><<<grid, 256, 0, st>>>(planes, c->n, n_planes, row_cnt.p, nullptr, nullptr, nullptr)));
+        SGPU_TRY(sgpu_scan_u32_u64(ctx, row_cnt.p, row_off.p, rows));
+        SGPU_CUDA(ctx, cudaMemcpyAsync(&ctx->h_scratch[0], row_off.p + rows, sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
         SGPU_CUDA(ctx, cudaStreamSynchronize(st));
         count = ctx->h_scratch[0];
         if (c->sp_cap < count) {
@@ -753,8 +771,7 @@ int sgpu_counts_sparse_pack(sgpu_ctx *ctx, sgpu_counts *c, int first_plane, uint
             c->sp_cap = cap;
         }
         if (count) {
-            SGPU_CUDA(ctx, cudaMemsetAsync(cursor, 0, sizeof(unsigned long long), st));
-            SGPU_LAUNCH(ctx, (sparse_scan_kernel<true><<<grid, 256, 0, st>>>(planes, c->n, n_planes, cursor, c->sp_idx, c->sp_val)));
+            SGPU_LAUNCH(ctx, (sparse_rows_kernel<true><<<grid, 256, 0, st>>>(planes, c->n, n_planes, nullptr, row_off.p, c->sp_idx, c->sp_val)));
         }
         SGPU_CUDA(ctx, cudaGetLastError());
     }

@@ -72,15 +72,16 @@ def counts_tensors(counts, device: torch.device) -> List[torch.Tensor]:
             tensor_from_ptr(hist, n_hist, torch.int64, device)]
 
 
-def exchange_sparse(idx: torch.Tensor, val: torch.Tensor, dst: int = 0, group=None):
+def exchange_sparse(idx: torch.Tensor, val: torch.Tensor, dst: int = 0, group=None, lens: Optional[Sequence[int]] = None):
     """Variable-length (index, value) lists of all ranks -> rank ``dst``: returns, on ``dst``, the lists of the OTHER
     ranks as [(idx, val), ...] (int32 tensors; idx carries the bits of a uint32) and an empty list elsewhere. One
-    all_gather of the lengths, one gather of the lists padded to the longest."""
+    all_gather of the lengths (unless the caller already knows them), one gather of the lists padded to the longest."""
     world, rank = dist.get_world_size(group), dist.get_rank(group)
-    n = torch.tensor([idx.numel()], dtype=torch.int64, device=idx.device)
-    lens = [torch.zeros_like(n) for _ in range(world)]
-    dist.all_gather(lens, n, group=group)
-    lens = [int(x.item()) for x in lens]
+    if lens is None:
+        n = torch.tensor([idx.numel()], dtype=torch.int64, device=idx.device)
+        got_n = [torch.zeros_like(n) for _ in range(world)]
+        dist.all_gather(got_n, n, group=group)
+        lens = [int(x.item()) for x in got_n]
     longest = max(lens)
     if longest == 0:
         return []
@@ -115,27 +116,34 @@ def reduce_counts(counts, device: torch.device, dst: int = 0, group=None) -> Non
     i32, n_i32, f64, n_f64, hist, n_hist = counts.buffers()
     nc = counts.num_cells
     nn = nc * nc
-    planes, spill = agree_layout(n_i32 // nn if nn else 2, n_f64 > 0, device, group)
-    counts.set_layout(planes, spill)
-    use_sparse, idx_t, val_t = False, None, None
-    if planes > 2 and (planes - 2) * nn <= 0xFFFFFFFF:
+    local_planes = n_i32 // nn if nn else 2
+    # non-zeros of this rank's second / third order planes (cheap: two passes over planes that are mostly zero)
+    ip = vp = None
+    nnz = 0
+    if local_planes > 2 and 7 * nn <= 0xFFFFFFFF:
         ip, vp, nnz = counts.sparse_pack(2)
-        t = torch.tensor([nnz], dtype=torch.int64, device=device)
-        all_nnz = [torch.zeros_like(t) for _ in range(world)]
-        dist.all_gather(all_nnz, t, group=group)
-        use_sparse = sparse_pays([int(x.item()) for x in all_nnz], dst, planes - 2, nc)
-        force = os.environ.get("SECEDO_B200_SPARSE_REDUCE")  # tests: "1" / "0" force one route on every rank
-        if force in ("0", "1"):
-            use_sparse = force == "1"
-        if use_sparse:
-            idx_t, val_t = tensor_from_ptr(ip, nnz, torch.int32, device), tensor_from_ptr(vp, nnz, torch.int32, device)
+    # ONE small collective: planes in use, spill plane, list length of every rank
+    info = torch.tensor([local_planes, int(n_f64 > 0), nnz], dtype=torch.int64, device=device)
+    infos = [torch.zeros_like(info) for _ in range(world)]
+    dist.all_gather(infos, info, group=group)
+    infos = [[int(v) for v in t.tolist()] for t in infos]
+    planes, spill = max(i[0] for i in infos), any(i[1] for i in infos)
+    all_nnz = [i[2] for i in infos]
+    counts.set_layout(planes, spill)
+    use_sparse = planes > 2 and 7 * nn <= 0xFFFFFFFF and sparse_pays(all_nnz, dst, planes - 2, nc)
+    force = os.environ.get("SECEDO_B200_SPARSE_REDUCE")  # tests: "1" / "0" force one route on every rank
+    if force in ("0", "1") and planes > 2 and 7 * nn <= 0xFFFFFFFF:
+        use_sparse = force == "1"
+    idx_t = val_t = None
+    if use_sparse:
+        idx_t, val_t = tensor_from_ptr(ip, nnz, torch.int32, device), tensor_from_ptr(vp, nnz, torch.int32, device)
     dense_planes = 2 if use_sparse else planes
     ptr, n = counts.pack_range(0, dense_planes)
     counts.ctx.synchronize()  # the library's stream need not be the one the collective is ordered on
     _, _, f64, n_f64, hist, n_hist = counts.buffers()
     reduce_buffers([tensor_from_ptr(ptr, n, torch.int32, device), tensor_from_ptr(f64, n_f64, torch.float64, device),
                     tensor_from_ptr(hist, n_hist, torch.int64, device)], dst, group)
-    lists = exchange_sparse(idx_t, val_t, dst, group) if use_sparse else []
+    lists = exchange_sparse(idx_t, val_t, dst, group, lens=all_nnz) if use_sparse else []
     if dist.get_rank(group) == dst:
         if device is not None and torch.device(device).type == "cuda":
             torch.cuda.current_stream(device).synchronize()  # the sums have arrived before they are unpacked
