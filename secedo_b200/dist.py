@@ -96,6 +96,9 @@ def exchange_sparse(idx: torch.Tensor, val: torch.Tensor, dst: int = 0, group=No
     return []
 
 
+MAX_WORLD_SPARSE = 4  # largest world size at which the sparse route is tried (see reduce_counts)
+
+
 def sparse_pays(nnz_per_rank: Sequence[int], dst: int, n_sparse_planes: int, num_cells: int) -> bool:
     """The lists of the other ranks (8 bytes per non-zero into ``dst``) against a dense reduction of the packed planes."""
     others = sum(nnz_per_rank) - nnz_per_rank[dst]
@@ -120,7 +123,12 @@ def reduce_counts(counts, device: torch.device, dst: int = 0, group=None) -> Non
     # non-zeros of this rank's second / third order planes (cheap: two passes over planes that are mostly zero)
     ip = vp = None
     nnz = 0
-    if local_planes > 2 and 7 * nn <= 0xFFFFFFFF:
+    force = os.environ.get("SECEDO_B200_SPARSE_REDUCE")  # tests: "1" / "0" force one route on every rank
+    # The lists of all other ranks converge on ``dst`` while a dense NCCL reduce costs the same at any world size:
+    # measured at 8 000 cells, 5.6 M non-zeros per rank - 1.7 ms (lists) vs 1.9 ms (dense) at 2 ranks, no gain at 8
+    # (profiles/r1_reduce_probe_2gpu.txt). Beyond 4 ranks the lists are not even built.
+    try_sparse = (world <= MAX_WORLD_SPARSE or force == "1") and force != "0"
+    if try_sparse and local_planes > 2 and 7 * nn <= 0xFFFFFFFF:
         ip, vp, nnz = counts.sparse_pack(2)
     # ONE small collective: planes in use, spill plane, list length of every rank
     info = torch.tensor([local_planes, int(n_f64 > 0), nnz], dtype=torch.int64, device=device)
@@ -130,10 +138,9 @@ def reduce_counts(counts, device: torch.device, dst: int = 0, group=None) -> Non
     planes, spill = max(i[0] for i in infos), any(i[1] for i in infos)
     all_nnz = [i[2] for i in infos]
     counts.set_layout(planes, spill)
-    use_sparse = planes > 2 and 7 * nn <= 0xFFFFFFFF and sparse_pays(all_nnz, dst, planes - 2, nc)
-    force = os.environ.get("SECEDO_B200_SPARSE_REDUCE")  # tests: "1" / "0" force one route on every rank
-    if force in ("0", "1") and planes > 2 and 7 * nn <= 0xFFFFFFFF:
-        use_sparse = force == "1"
+    use_sparse = try_sparse and planes > 2 and 7 * nn <= 0xFFFFFFFF and sparse_pays(all_nnz, dst, planes - 2, nc)
+    if force == "1" and planes > 2 and 7 * nn <= 0xFFFFFFFF:
+        use_sparse = True
     idx_t = val_t = None
     if use_sparse:
         idx_t, val_t = tensor_from_ptr(ip, nnz, torch.int32, device), tensor_from_ptr(vp, nnz, torch.int32, device)
