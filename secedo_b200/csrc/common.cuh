@@ -44,6 +44,7 @@ struct sgpu_ctx {
     uint32_t ft_L = 0;
     void *ep_tiles = nullptr;
     uint32_t ep_tiles_n = 0;
+    bool spectral_attr_done = false; // spectral.cu: shared-memory attributes of its kernels set on this device
     // Device memory cache (abi.cu): temporaries and pileups are re-created with identical sizes at every
     // call, and cudaMallocAsync/cudaFreeAsync of GB-sized blocks cost milliseconds each, so freed blocks
     // are kept and handed out again. Reuse is safe because all work of a context is ordered on ONE stream.

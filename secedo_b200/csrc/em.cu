@@ -168,9 +168,20 @@ int sgpu_em_impl(sgpu_ctx *ctx, const sgpu_pileup *p, const uint32_t *h_id_to_po
         return sgpu_fail(ctx, SGPU_E_ARG, "expectation_maximization: empty probability vector");
     }
     SGPU_WAIT_PILEUP(ctx, p);
-    cudaEvent_t t0, t1;
-    SGPU_CUDA(ctx, cudaEventCreate(&t0));
-    SGPU_CUDA(ctx, cudaEventCreate(&t1));
+    struct Events { // destroyed on every return path
+        cudaEvent_t a = nullptr, b = nullptr;
+        ~Events() {
+            if (a) {
+                cudaEventDestroy(a);
+            }
+            if (b) {
+                cudaEventDestroy(b);
+            }
+        }
+    } evs;
+    SGPU_CUDA(ctx, cudaEventCreate(&evs.a));
+    SGPU_CUDA(ctx, cudaEventCreate(&evs.b));
+    const cudaEvent_t t0 = evs.a, t1 = evs.b;
     SGPU_CUDA(ctx, cudaEventRecord(t0, st));
     DevBuf<double> d_prob, d_ll;
     DevBuf<uint32_t> d_map, d_flags;
@@ -224,7 +235,5 @@ int sgpu_em_impl(sgpu_ctx *ctx, const sgpu_pileup *p, const uint32_t *h_id_to_po
     if (ms_total) {
         SGPU_CUDA(ctx, cudaEventElapsedTime(ms_total, t0, t1));
     }
-    cudaEventDestroy(t0);
-    cudaEventDestroy(t1);
     return SGPU_OK;
 }

@@ -599,8 +599,8 @@ struct Solver {
         dim3 grid(grid_x, n_split);
         cudaEvent_t e0 = nullptr, e1 = nullptr;
         if (time_mv) {
-            SGPU_CUDA(ctx, cudaEventCreate(&e0));
-            SGPU_CUDA(ctx, cudaEventCreate(&e1));
+            SGPU_TRY(get_event(&e0));
+            SGPU_TRY(get_event(&e1));
             SGPU_CUDA(ctx, cudaEventRecord(e0, st));
         }
         if (use_tma(width)) {
@@ -633,13 +633,23 @@ struct Solver {
         return SGPU_OK;
     }
 
+    std::vector<cudaEvent_t> spare_events; // recycled: hundreds of products per solve
+    int get_event(cudaEvent_t *e) {
+        if (!spare_events.empty()) {
+            *e = spare_events.back();
+            spare_events.pop_back();
+            return SGPU_OK;
+        }
+        SGPU_CUDA(ctx, cudaEventCreate(e));
+        return SGPU_OK;
+    }
     int collect_times() { // after a stream synchronisation
         for (auto &pr : pending) {
             float ms = 0.f;
             SGPU_CUDA(ctx, cudaEventElapsedTime(&ms, pr.first, pr.second));
             ms_mv += ms;
-            cudaEventDestroy(pr.first);
-            cudaEventDestroy(pr.second);
+            spare_events.push_back(pr.first);
+            spare_events.push_back(pr.second);
         }
         pending.clear();
         return SGPU_OK;
@@ -655,6 +665,9 @@ struct Solver {
         for (auto &pr : pending) {
             cudaEventDestroy(pr.first);
             cudaEventDestroy(pr.second);
+        }
+        for (cudaEvent_t e : spare_events) {
+            cudaEventDestroy(e);
         }
     }
     double *alloc(size_t count) {
@@ -760,13 +773,15 @@ struct Solver {
 };
 
 
+// kernels with more than 48 KB of dynamic shared memory; function attributes are per device, so per context
 int sgpu_spectral_attributes(sgpu_ctx *ctx) {
-    static bool done = false;
-    if (!done) {
+    if (!ctx->spectral_attr_done) {
         SGPU_CUDA(ctx, cudaFuncSetAttribute(symm_block_tma_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(ts_smem_bytes<8>())));
         SGPU_CUDA(ctx, cudaFuncSetAttribute(symm_block_tma_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(ts_smem_bytes<16>())));
         SGPU_CUDA(ctx, cudaFuncSetAttribute(symm_block_tma_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(ts_smem_bytes<32>())));
-        done = true;
+        SGPU_CUDA(ctx, cudaFuncSetAttribute(xr_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * 64 * 64 * 8));
+        SGPU_CUDA(ctx, cudaFuncSetAttribute(rank_update_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (32 * 64 + 128 * 65) * 8));
+        ctx->spectral_attr_done = true;
     }
     return SGPU_OK;
 }
@@ -787,17 +802,21 @@ int sgpu_spectral_device(sgpu_ctx *ctx, const double *d_A, uint32_t n, uint32_t 
         return sgpu_fail(ctx, SGPU_E_ARG, "spectral: need 2 <= n and 1 <= k <= min(32, n) (n = %u, k = %u)", n, k);
     }
     tol = std::max(tol > 0 ? tol : 1e-10, 1e-13);
-    static bool attr_done = false;
-    if (!attr_done) {
-        SGPU_TRY(sgpu_spectral_attributes(ctx));
-        SGPU_CUDA(ctx, cudaFuncSetAttribute(xr_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * 64 * 64 * 8));
-        SGPU_CUDA(ctx, cudaFuncSetAttribute(rank_update_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (32 * 64 + 128 * 65) * 8));
-        attr_done = true;
+    SGPU_TRY(sgpu_spectral_attributes(ctx));
+    struct Events { // destroyed on every return path
+        cudaEvent_t e[3] = { nullptr, nullptr, nullptr };
+        ~Events() {
+            for (cudaEvent_t x : e) {
+                if (x) {
+                    cudaEventDestroy(x);
+                }
+            }
+        }
+    } evs;
+    for (auto &x : evs.e) {
+        SGPU_CUDA(ctx, cudaEventCreate(&x));
     }
-    cudaEvent_t t0, t1, t2;
-    SGPU_CUDA(ctx, cudaEventCreate(&t0));
-    SGPU_CUDA(ctx, cudaEventCreate(&t1));
-    SGPU_CUDA(ctx, cudaEventCreate(&t2));
+    const cudaEvent_t t0 = evs.e[0], t1 = evs.e[1], t2 = evs.e[2];
     SGPU_CUDA(ctx, cudaEventRecord(t0, st));
     const uint64_t launches0 = ctx->launches;
 
@@ -919,9 +938,6 @@ int sgpu_spectral_device(sgpu_ctx *ctx, const double *d_A, uint32_t n, uint32_t 
         SGPU_CUDA(ctx, cudaEventElapsedTime(&stats->ms_solver, t1, t2));
         stats->ms_matvec = S.ms_mv;
     }
-    cudaEventDestroy(t0);
-    cudaEventDestroy(t1);
-    cudaEventDestroy(t2);
     return SGPU_OK;
 }
 
