@@ -383,70 +383,7 @@ def main_ours(args):
             sys.stderr.write("e2e trace (ms, cumulative): " + json.dumps({k: round(v, 2) for k, v in tr.items()}) + "\n")
         return st
 
-    # ---- the same with TWO host threads: a producer context uploads and filters chromosome c + 1 (DMA + zero-copy
-    # pull, both bus bound) while this thread accumulates chromosome c on the main context. The filtered pileup is
-    # handed over once the producer's stream has finished with it, and goes back to the producer for freeing once
-    # this context's kernels have finished reading it (the per-context memory caches are single threaded).
-    import queue
-    threaded = os.environ.get("SECEDO_BENCH_E2E_THREADS", "1") != "0"
-    tstate = {"consumed": 0, "run": [], "q": None, "done": None, "thread": None}
-    if threaded:
-        ctx2 = api.Context(local_rank)
-        flt2 = api.Filter(w["theta"], 4, ctx2)
-
-        def producer(items, q, done):
-            produced = freed = 0
-            try:
-                for _s, c in items:
-                    while not done.empty():
-                        done.get().free()
-                        freed += 1
-                    raw = ctx2.upload_lazy_async(chunks[c])
-                    filtered, _ = flt2.filter_device(raw, ident)
-                    ctx2.synchronize()  # compaction (and the pull) finished: the other context may read it
-                    raw.free()
-                    q.put(filtered)
-                    produced += 1
-                while freed < produced:
-                    done.get().free()
-                    freed += 1
-            except Exception as ex:  # noqa: BLE001
-                q.put(ex)
-
-    def e2e_step_threaded():
-        if tstate["consumed"] == len(tstate["run"]):  # next run (warm-up, then the timed steps)
-            if tstate["thread"] is not None:
-                tstate["thread"].join()
-            tstate["run"], tstate["consumed"] = runs_t.pop(0), 0
-            tstate["q"], tstate["done"] = queue.Queue(maxsize=2), queue.Queue()
-            tstate["thread"] = threading.Thread(target=producer, args=(tstate["run"], tstate["q"], tstate["done"]), daemon=True)
-            tstate["thread"].start()
-        counts.zero()
-        st = {}
-        for c in range(n_chr):
-            filtered = tstate["q"].get()
-            if isinstance(filtered, Exception):
-                raise filtered
-            tstate["consumed"] += 1
-            s1 = counts.accumulate(filtered, w["L"], ident, w["eps"], w["h"], w["theta"], w["num_threads"], args.path)
-            st["sig_loci"] = st.get("sig_loci", 0) + filtered.n_loci
-            state["pulled_entries"] = state.get("pulled_entries", 0) + filtered.n_entries
-            for k in ("ms_gemm", "ms_stage", "ms_link", "ms_first_order", "ms_multi", "gemm_launches"):
-                st[k] = st.get(k, 0) + (s1.get(k, 0) or 0)
-            ctx.synchronize()  # this context's kernels are done with the pileup
-            tstate["done"].put(filtered)
-        sdist.reduce_counts(counts, device, dst=0)
-        if rank == 0:
-            state["n_out"] = state.get("n_out", 0) + 1
-            counts.finalize_async(*lik, w["normalization"], out_bufs[state["n_out"] % 2])
-            if state["n_out"] in (E2E_WARMUP, e2e_total):
-                ctx.output_wait()
-        return st
-
-    runs_t = [list(r) for r in runs]
-    ms_e2e, acc_e2e, _, _ = timed(e2e_step_threaded if threaded else e2e_step, e2e_steps, E2E_WARMUP)
-    if threaded and tstate["thread"] is not None:
-        tstate["thread"].join()
+    ms_e2e, acc_e2e, _, _ = timed(e2e_step, e2e_steps, E2E_WARMUP)
     ctx.synchronize()
     if rank == 0:
         ctx.output_wait()
@@ -605,7 +542,6 @@ def main_ours(args):
             "e2e": {"value": e2e_value, "unit": "loci/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                     "ms_per_step": ms_e2e / e2e_steps, "steps": e2e_steps,
                     "host_pileup_bytes_per_step": int(h2d_full),
-                    "host_threads": 2 if threaded else 1,
                     "how": "host pinned pileup -> sgpu_pileup_upload_lazy_async per chromosome (copy stream, overlapping the "
                            "kernels of the previous chromosome; the read ids stay in pinned host memory) -> filter (pulls the "
                            "read ids of the loci it keeps straight over PCIe: h2d_bytes_per_step counts what crossed the "
