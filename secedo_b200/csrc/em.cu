@@ -29,6 +29,7 @@ namespace {
 constexpr int EM_WARPS = 8;
 constexpr int EM_THREADS = EM_WARPS * 32;
 constexpr double EM_FIX = 4294967296.0; // 2^32
+constexpr int EM_ILP = 4;               // entries per lane in flight
 
 __device__ __forceinline__ double warp_sum(double v) {
 #pragma unroll
@@ -51,16 +52,30 @@ em_mstep_kernel(const uint64_t *__restrict__ row_ptr, const uint16_t *__restrict
         const uint64_t e0 = row_ptr[l], e1 = row_ptr[l + 1];
         // weighted base counts of both clusters (a with 1 - p like the reference, :66-69)
         double sa[4] = { 0, 0, 0, 0 }, sb[4] = { 0, 0, 0, 0 };
-#pragma unroll 4
-        for (uint64_t e = e0 + lane; e < e1; e += 32) {
-            const uint32_t gb = gid_base[e];
-            const double pb = prob_b[gb >> 2];
-            const double pa = 1.0 - pb;
+        // four entries per lane in flight: the kernel is bound by the latency of the two dependent loads per entry
+        // (ncu: 50 long-scoreboard stall cycles per issue with one entry per lane), not by bandwidth
+        for (uint64_t e = e0 + lane; e < e1; e += 32 * EM_ILP) {
+            uint32_t gb[EM_ILP];
+            double pb[EM_ILP];
 #pragma unroll
-            for (int b = 0; b < 4; ++b) {
-                const bool hit = (gb & 3u) == static_cast<uint32_t>(b);
-                sa[b] += hit ? pa : 0.0;
-                sb[b] += hit ? pb : 0.0;
+            for (int u = 0; u < EM_ILP; ++u) {
+                gb[u] = e + 32 * u < e1 ? gid_base[e + 32 * u] : 0xFFFFFFFFu;
+            }
+#pragma unroll
+            for (int u = 0; u < EM_ILP; ++u) {
+                pb[u] = gb[u] != 0xFFFFFFFFu ? prob_b[gb[u] >> 2] : 0.0;
+            }
+#pragma unroll
+            for (int u = 0; u < EM_ILP; ++u) { // same per-lane order of additions as one entry at a time
+                if (gb[u] != 0xFFFFFFFFu) {
+                    const double pa = 1.0 - pb[u];
+#pragma unroll
+                    for (int b = 0; b < 4; ++b) {
+                        const bool hit = (gb[u] & 3u) == static_cast<uint32_t>(b);
+                        sa[b] += hit ? pa : 0.0;
+                        sb[b] += hit ? pb[u] : 0.0;
+                    }
+                }
             }
         }
         double ca[4], cb[4];
@@ -90,13 +105,24 @@ em_mstep_kernel(const uint64_t *__restrict__ row_ptr, const uint16_t *__restrict
         for (int b = 0; b < 4; ++b) {
             td[b] = __shfl_sync(0xFFFFFFFFu, fx, 4 + b) - __shfl_sync(0xFFFFFFFFu, fx, b);
         }
-#pragma unroll 4
-        for (uint64_t e = e0 + lane; e < e1; e += 32) {
-            const uint32_t gb = gid_base[e];
-            const uint32_t cell = id_to_pos[gb >> 2];
-            const int b = gb & 3;
-            const long long v = b == 0 ? td[0] : b == 1 ? td[1] : b == 2 ? td[2] : td[3];
-            atomicAdd(acc + cell, static_cast<unsigned long long>(v));
+        for (uint64_t e = e0 + lane; e < e1; e += 32 * EM_ILP) {
+            uint32_t gb[EM_ILP], cell[EM_ILP];
+#pragma unroll
+            for (int u = 0; u < EM_ILP; ++u) {
+                gb[u] = e + 32 * u < e1 ? gid_base[e + 32 * u] : 0xFFFFFFFFu;
+            }
+#pragma unroll
+            for (int u = 0; u < EM_ILP; ++u) {
+                cell[u] = gb[u] != 0xFFFFFFFFu ? id_to_pos[gb[u] >> 2] : 0u;
+            }
+#pragma unroll
+            for (int u = 0; u < EM_ILP; ++u) {
+                if (gb[u] != 0xFFFFFFFFu) {
+                    const int b = gb[u] & 3;
+                    const long long v = b == 0 ? td[0] : b == 1 ? td[1] : b == 2 ? td[2] : td[3];
+                    atomicAdd(acc + cell[u], static_cast<unsigned long long>(v));
+                }
+            }
         }
     }
 }
