@@ -30,6 +30,8 @@ constexpr int EM_WARPS = 8;
 constexpr int EM_THREADS = EM_WARPS * 32;
 constexpr double EM_FIX = 4294967296.0; // 2^32
 constexpr int EM_ILP = 4;               // entries per lane in flight
+constexpr int EM_REPLICAS = 32;         // copies of the per-cell accumulators: 8000 cells are only 500 L2 lines, and every
+                                        // line serialises its reductions (integer sums: any split gives the same total)
 
 __device__ __forceinline__ double warp_sum(double v) {
 #pragma unroll
@@ -39,7 +41,7 @@ __device__ __forceinline__ double warp_sum(double v) {
     return v;
 }
 
-// acc: [n_cells] int64, zero at launch: sum over the cell's entries of centre_b[base] - centre_a[base]. The E step
+// acc: [EM_REPLICAS][n_cells] int64, zero at launch: sum over the cell's entries of centre_b[base] - centre_a[base]. The E step
 // only ever uses ll_b - ll_a (:120), so ONE reduction per entry carries everything
 __global__ void __launch_bounds__(EM_THREADS)
 em_mstep_kernel(const uint64_t *__restrict__ row_ptr, const uint16_t *__restrict__ gid_base, uint64_t n_loci,
@@ -47,6 +49,7 @@ em_mstep_kernel(const uint64_t *__restrict__ row_ptr, const uint16_t *__restrict
                 unsigned long long *__restrict__ acc) {
     const int lane = threadIdx.x & 31;
     const uint64_t warp0 = (static_cast<uint64_t>(blockIdx.x) * EM_THREADS + threadIdx.x) >> 5;
+    acc += (warp0 % EM_REPLICAS) * n_cells;
     const uint64_t n_warps = (static_cast<uint64_t>(gridDim.x) * EM_THREADS) >> 5;
     for (uint64_t l = warp0; l < n_loci; l += n_warps) {
         const uint64_t e0 = row_ptr[l], e1 = row_ptr[l + 1];
@@ -136,8 +139,12 @@ __global__ void __launch_bounds__(1024) em_estep_kernel(unsigned long long *__re
     __shared__ int all_done;
     double psum = 0.0;
     for (uint32_t i = threadIdx.x; i < n_cells; i += 1024) {
-        ll[i] += static_cast<double>(static_cast<long long>(acc[i])) * (1.0 / EM_FIX);
-        acc[i] = 0ull;
+        long long sum = 0;
+        for (int r = 0; r < EM_REPLICAS; ++r) {
+            sum += static_cast<long long>(acc[static_cast<size_t>(r) * n_cells + i]);
+            acc[static_cast<size_t>(r) * n_cells + i] = 0ull;
+        }
+        ll[i] += static_cast<double>(sum) * (1.0 / EM_FIX);
         psum += prob_b[i];
     }
     psum = warp_sum(psum);
@@ -234,8 +241,8 @@ int sgpu_em_impl(sgpu_ctx *ctx, const sgpu_pileup *p, const uint32_t *h_id_to_po
         }
     }
     DevBuf<unsigned long long> d_acc;
-    SGPU_CUDA(ctx, d_acc.alloc(n_cells, ctx));
-    SGPU_CUDA(ctx, cudaMemsetAsync(d_acc.p, 0, n_cells * sizeof(unsigned long long), st));
+    SGPU_CUDA(ctx, d_acc.alloc(static_cast<size_t>(EM_REPLICAS) * n_cells, ctx));
+    SGPU_CUDA(ctx, cudaMemsetAsync(d_acc.p, 0, static_cast<size_t>(EM_REPLICAS) * n_cells * sizeof(unsigned long long), st));
     const uint32_t n_cta = static_cast<uint32_t>(std::min<uint64_t>(5ull * ctx->sm_count, (p->n_loci + EM_WARPS - 1) / EM_WARPS));
     uint32_t it = 0;
     for (;;) {
