@@ -8,6 +8,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <memory>
+#include <string>
 
 struct HostBackend {
     uint32_t ld;
@@ -99,7 +100,33 @@ struct HostBackend {
     }
 };
 
+// --jacobi in.bin out.bin: in = u32 n, f64 A[n*n] (symmetric); out = f64 w[n] ascending, f64 V[n*n] (columns)
+// --degree a c top kth mmax: prints the Chebyshev degree
+static int small_problems(int argc, char **argv) {
+    if (std::string(argv[1]) == "--degree" && argc == 7) {
+        std::printf("%d\n", sgpu_spectral::chebyshev_degree(std::atof(argv[2]), std::atof(argv[3]), std::atof(argv[4]),
+                                                            std::atof(argv[5]), std::atoi(argv[6])));
+        return 0;
+    }
+    if (std::string(argv[1]) == "--jacobi" && argc == 4) {
+        FILE *f = std::fopen(argv[2], "rb");
+        uint32_t n = 0;
+        if (!f || std::fread(&n, 4, 1, f) != 1) return 2;
+        std::vector<double> A((size_t)n * n), w, V;
+        if (std::fread(A.data(), 8, A.size(), f) != A.size()) return 2;
+        std::fclose(f);
+        sgpu_spectral::jacobi_eigh((int)n, A, w, V);
+        f = std::fopen(argv[3], "wb");
+        std::fwrite(w.data(), 8, n, f);
+        std::fwrite(V.data(), 8, V.size(), f);
+        std::fclose(f);
+        return 0;
+    }
+    return 2;
+}
+
 int main(int argc, char **argv) {
+    if (argc >= 2 && argv[1][0] == '-') return small_problems(argc, argv);
     if (argc < 3) return 2;
     FILE *f = std::fopen(argv[1], "rb");
     if (!f) return 2;

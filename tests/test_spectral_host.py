@@ -70,3 +70,39 @@ def test_subspace_iteration_host_backend(host_check, tmp_path, case):
     conv, outer, ev, vec = run_host(host_check, tmp_path, a, k)
     assert conv and outer < 50
     check_against_oracle(a, ev, vec, 1e-10)
+
+
+@pytest.mark.parametrize("n", [1, 2, 7, 16, 33, 64])
+def test_jacobi_against_lapack(host_check, tmp_path, n):
+    """the b x b eigenproblems of the Rayleigh-Ritz steps (cyclic Jacobi on the host) against LAPACK, incl. clustered
+    and repeated eigenvalues"""
+    rng = np.random.default_rng(n)
+    q, _ = np.linalg.qr(rng.normal(size=(n, n)))
+    lam = np.sort(np.concatenate([rng.normal(size=n - n // 2), np.full(n // 2, 0.25) + 1e-9 * np.arange(n // 2)]))
+    a = (q * lam) @ q.T
+    a = (a + a.T) / 2
+    fin, fout = str(tmp_path / "j.bin"), str(tmp_path / "jo.bin")
+    with open(fin, "wb") as f:
+        f.write(struct.pack("<I", n))
+        f.write(a.tobytes())
+    subprocess.run([host_check, "--jacobi", fin, fout], check=True)
+    raw = np.frombuffer(open(fout, "rb").read())
+    w, v = raw[:n], raw[n:].reshape(n, n)
+    assert np.abs(w - np.linalg.eigvalsh(a)).max() <= 1e-13 * max(1.0, np.abs(lam).max())
+    assert np.abs(v.T @ v - np.eye(n)).max() <= 1e-13
+    assert np.abs(a @ v - v * w).max() <= 1e-13 * max(1.0, np.abs(lam).max())
+
+
+def test_chebyshev_degree_limits(host_check):
+    def degree(a, c, top, kth, mmax=100):
+        return int(subprocess.run([host_check, "--degree", *map(repr, (a, c, top, kth)), str(mmax)], check=True,
+                                  capture_output=True, text=True).stdout)
+    # bulk edge: wanted values barely outside the damped interval -> the cap
+    assert degree(-0.02, 0.0050, 0.0052, 0.0051) == 100
+    # a signal eigenvalue far outside: few steps, so that it cannot swamp the block (growth ratio <= 2e6)
+    m = degree(-0.02, 0.005, 0.5, 0.0051)
+    assert 2 <= m <= 6
+    e, ctr = 0.0125, -0.0075
+    growth = np.cosh(m * np.arccosh((0.5 - ctr) / e)) / np.cosh(m * np.arccosh((0.0051 - ctr) / e))
+    assert growth <= 2e6 * 1.01
+    assert degree(0.0, 0.0, 1.0, 0.5) == 2  # degenerate interval
