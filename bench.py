@@ -96,9 +96,9 @@ def cpu_sample(seed=77):
     return make_pileup(cfg)
 
 
-def run_reference_step(p, threads):
+def run_reference_step(p, threads, want_matrix=False):
     """Filter::filter + computeSimilarityMatrix of the reference on pileup p. Returns (seconds,
-    significant loci, kind)."""
+    significant loci, kind[, matrix])."""
     from oracle import pyoracle as po
     from secedo_b200.pileup import Pileup
     w = WORKLOAD
@@ -107,14 +107,16 @@ def run_reference_step(p, threads):
         t0 = time.perf_counter()
         rf, _, _ = po.ref_filter(p, ident, w["theta"], 4, threads)
         f = Pileup(rf.chr_ptr, rf.row_ptr, rf.position, rf.read_id, rf.gid_base)
-        po.ref_similarity(f, w["n_cells"], w["L"], ident, w["eps"], w["h"], w["theta"], threads, w["normalization"])
-        return time.perf_counter() - t0, f.n_loci, "reference"
+        M, _ = po.ref_similarity(f, w["n_cells"], w["L"], ident, w["eps"], w["h"], w["theta"], threads, w["normalization"])
+        secs = time.perf_counter() - t0
+        return (secs, f.n_loci, "reference", M) if want_matrix else (secs, f.n_loci, "reference")
     t0 = time.perf_counter()
     kl, ke, _, _ = po.filter_flags(p, ident, w["theta"])
     f = p.select(kl, ke)
-    po.similarity(f, w["n_cells"], w["L"], ident, w["eps"], w["h"], w["theta"], threads, w["normalization"],
-                  instrument=False)
-    return time.perf_counter() - t0, f.n_loci, "port"
+    o = po.similarity(f, w["n_cells"], w["L"], ident, w["eps"], w["h"], w["theta"], threads, w["normalization"],
+                      instrument=False)
+    secs = time.perf_counter() - t0
+    return (secs, f.n_loci, "port", o.M) if want_matrix else (secs, f.n_loci, "port")
 
 
 def reference_threads():

@@ -181,6 +181,13 @@ struct sgpu_counts {
     bool have_params = false;
     double eps = 0, h = 0, theta = 0;
     uint32_t L = 0;
+    // multi-GPU epilogue over peer memory (sgpu_slab_raw / sgpu_slab_finalize): this GPU's share of the 32 x 32 tiles of
+    // the upper triangle, their raw (summed, transformed, not yet normalised) values, local extrema
+    uint64_t slab_t0 = 0, slab_t1 = 0, slab_raw_tiles = 0;
+    uint32_t slab_nb = 0;
+    double *slab_raw = nullptr;               // context cache
+    unsigned long long *slab_minmax = nullptr; // cudaMalloc: encoded {min, max}, then {-min, max} as doubles
+    double *slab_out = nullptr;               // cudaMalloc, n x n, only when the result stays on the device
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -276,6 +283,9 @@ int sgpu_log_probs_impl(sgpu_ctx *ctx, double eps, double h, double theta, uint3
 int sgpu_epilogue(sgpu_ctx *ctx, sgpu_counts *c, uint32_t L, double eps, double h, double theta,
                   int normalization, double *h_out, double **d_keep = nullptr, bool async_out = false);
 int sgpu_output_wait_impl(sgpu_ctx *ctx);
+int sgpu_slab_raw_impl(sgpu_ctx *ctx, sgpu_counts *c, const int32_t *const *peer_planes, uint32_t n_peers, uint32_t slab,
+                       uint32_t n_slabs, uint32_t L, double eps, double h, double theta, double **d_extrema);
+int sgpu_slab_finalize_impl(sgpu_ctx *ctx, sgpu_counts *c, int normalization, double *out, double **d_out);
 
 // em.cu
 int sgpu_em_impl(sgpu_ctx *ctx, const sgpu_pileup *p, const uint32_t *h_id_to_pos, uint32_t n_groups, double theta,

@@ -297,6 +297,166 @@ __global__ void __launch_bounds__(TR_THREADS) finalize_kernel(TransformArgs a, c
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Multi-GPU epilogue over peer memory: reduce-scatter and log-likelihood transform in ONE kernel.
+// Every GPU owns a contiguous share of the 32 x 32 tiles of the upper triangle. For its tiles it reads the
+// count planes of ALL GPUs (its own and, through NVLink peer mappings, the others'), adds them and applies the
+// transform: the summed integers never exist in memory and nothing travels but the operands themselves
+// (each element of every GPU's planes crosses NVLink at most once). The raw values stay in a local buffer;
+// after the ranks have exchanged max(raw) (one scalar) the second kernel normalises and writes each tile and
+// its mirror image to the output, which may be mapped host memory (every GPU writes its share of the matrix
+// over its own PCIe link).
+// ------------------------------------------------------------------------------------------------
+struct SlabArgs {
+    const int32_t *peer[SGPU_MAX_PEERS];
+    uint32_t n_peers;
+    uint32_t n;
+    uint64_t nn;
+    int planes_used;
+    double f10, f01;
+    double g2[3], g3[4];
+};
+
+// tile number t of the upper triangle of nb x nb tiles (row-major over bj >= bi) -> (bi, bj)
+__device__ __forceinline__ uint2 tri_tile(uint64_t t, uint32_t nb) {
+    // rows before bi hold bi * nb - bi (bi - 1) / 2 tiles; solve by the quadratic formula, then fix up
+    const double b = 2.0 * nb + 1.0;
+    uint32_t bi = static_cast<uint32_t>((b - sqrt(b * b - 8.0 * static_cast<double>(t))) * 0.5);
+    auto before = [nb](uint32_t r) { return static_cast<uint64_t>(r) * nb - static_cast<uint64_t>(r) * (r - 1) / 2; };
+    while (bi > 0 && before(bi) > t) {
+        --bi;
+    }
+    while (before(bi + 1) <= t) {
+        ++bi;
+    }
+    return make_uint2(bi, bi + static_cast<uint32_t>(t - before(bi)));
+}
+
+__global__ void __launch_bounds__(TR_THREADS) slab_raw_kernel(SlabArgs a, uint64_t t0, uint32_t nb, double *__restrict__ raw,
+                                                             unsigned long long *__restrict__ minmax) {
+    const uint2 t = tri_tile(t0 + blockIdx.x, nb);
+    const uint32_t tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    double mn = 0.0, mx = 0.0; // the diagonal
+    double *dst = raw + static_cast<uint64_t>(blockIdx.x) * 1024;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const uint32_t r = ty + 8 * k;
+        const uint32_t i = t.x * 32 + r, j = t.y * 32 + tx;
+        double v = 0.0;
+        if (i < j && j < a.n) {
+            const uint64_t idx = static_cast<uint64_t>(i) * a.n + j;
+            int32_t acc[N_PLANES];
+#pragma unroll
+            for (int pl = 0; pl < N_PLANES; ++pl) {
+                acc[pl] = 0;
+            }
+            for (uint32_t q = 0; q < a.n_peers; ++q) { // integer sums: the order of the GPUs does not matter
+                const int32_t *pp = a.peer[q] + idx;
+                acc[PLANE_S] += pp[PLANE_S * a.nn];
+                acc[PLANE_D] += pp[PLANE_D * a.nn];
+                if (a.planes_used > 2) {
+#pragma unroll
+                    for (int pl = PLANE_H2; pl < PLANE_H3; ++pl) {
+                        acc[pl] += pp[pl * a.nn];
+                    }
+                }
+                if (a.planes_used > PLANE_H3) {
+#pragma unroll
+                    for (int pl = PLANE_H3; pl < N_PLANES; ++pl) {
+                        acc[pl] += pp[pl * a.nn];
+                    }
+                }
+            }
+            // same expression, in the same order, as raw_value() of the single-GPU epilogue: identical bits
+            v = a.f10 * acc[PLANE_S] + a.f01 * acc[PLANE_D];
+            if (a.planes_used > 2) {
+#pragma unroll
+                for (int kk = 0; kk < 3; ++kk) {
+                    if (acc[PLANE_H2 + kk]) {
+                        v += a.g2[kk] * acc[PLANE_H2 + kk];
+                    }
+                }
+            }
+            if (a.planes_used > PLANE_H3) {
+#pragma unroll
+                for (int kk = 0; kk < 4; ++kk) {
+                    if (acc[PLANE_H3 + kk]) {
+                        v += a.g3[kk] * acc[PLANE_H3 + kk];
+                    }
+                }
+            }
+            mn = fmin(mn, v);
+            mx = fmax(mx, v);
+        }
+        dst[r * 32 + tx] = v;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        mn = fmin(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+        mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    }
+    __shared__ double s_mn[TR_THREADS / 32], s_mx[TR_THREADS / 32];
+    if (tx == 0) {
+        s_mn[ty] = mn;
+        s_mx[ty] = mx;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int w = 1; w < TR_THREADS / 32; ++w) {
+            mn = fmin(mn, s_mn[w]);
+            mx = fmax(mx, s_mx[w]);
+        }
+        atomicMin(&minmax[0], enc(mn));
+        atomicMax(&minmax[1], enc(mx));
+    }
+}
+
+// {-min, max} of this GPU's share as doubles: ONE all-reduce with MAX over the ranks gives both global extrema
+__global__ void slab_extrema_kernel(const unsigned long long *__restrict__ minmax, double *__restrict__ ext) {
+    ext[0] = -dec_dev(minmax[0]);
+    ext[1] = dec_dev(minmax[1]);
+}
+
+__global__ void __launch_bounds__(TR_THREADS) slab_finalize_kernel(const double *__restrict__ raw, uint64_t t0, uint32_t nb, uint32_t n,
+                                                                  const double *__restrict__ ext, int normalization,
+                                                                  double *__restrict__ out) {
+    __shared__ double tile[32][33];
+    const uint2 t = tri_tile(t0 + blockIdx.x, nb);
+    const uint32_t tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    const double mx = ext[1];
+    const double *src = raw + static_cast<uint64_t>(blockIdx.x) * 1024;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const uint32_t r = ty + 8 * k;
+        const uint32_t i = t.x * 32 + r, j = t.y * 32 + tx;
+        double v = 0.0;
+        if (i < j && j < n) {
+            v = normalized(src[r * 32 + tx], normalization, mx);
+        }
+        tile[r][tx] = v;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const uint32_t r = ty + 8 * k;
+        uint32_t i = t.x * 32 + r, j = t.y * 32 + tx;
+        if (i < n && j < n) {
+            if (i < j) {
+                out[static_cast<uint64_t>(i) * n + j] = tile[r][tx];
+            } else if (t.x == t.y) { // diagonal tile: zero diagonal, lower half mirrored
+                out[static_cast<uint64_t>(i) * n + j] = i == j ? 0.0 : tile[tx][r];
+            }
+        }
+        if (t.x != t.y) { // rows of the mirrored tile
+            i = t.y * 32 + r;
+            j = t.x * 32 + tx;
+            if (i < n && j < n) {
+                out[static_cast<uint64_t>(i) * n + j] = tile[tx][r];
+            }
+        }
+    }
+}
+
 int device_log_probs(sgpu_ctx *ctx, double eps, double h, double theta, uint32_t L, uint32_t n, DevBuf<double> &ls,
                      DevBuf<double> &ld) {
     cudaStream_t st = ctx->stream;
@@ -352,17 +512,10 @@ int sgpu_output_wait_impl(sgpu_ctx *ctx) {
     return SGPU_OK;
 }
 
-int sgpu_epilogue(sgpu_ctx *ctx, sgpu_counts *c, uint32_t L, double eps, double h, double theta, int normalization,
-                  double *h_out, double **d_keep, bool async_out) {
+// F and G for the classes of the integer planes (s + d <= 3); kept for the next call with the same
+// likelihood parameters (divide_cluster calls with the same ones at every node of its recursion)
+static int ensure_ftable(sgpu_ctx *ctx, uint32_t L, double eps, double h, double theta) {
     cudaStream_t st = ctx->stream;
-    if (normalization < 0 || normalization > 2) {
-        return sgpu_fail(ctx, SGPU_E_ARG, "Invalid normalization: %d", normalization); // similarity_matrix.cpp:264
-    }
-    if (c->nn == 0) {
-        return SGPU_OK;
-    }
-    // F and G for the classes of the integer planes (s + d <= 3); kept for the next call with the same
-    // likelihood parameters (divide_cluster calls with the same ones at every node of its recursion)
     if (!(ctx->ft_valid && ctx->ft_eps == eps && ctx->ft_h == h && ctx->ft_theta == theta && ctx->ft_L == L)) {
         DevBuf<double> d_G, d_F;
         SGPU_CUDA(ctx, d_G.alloc(SGPU_MAX_CLASS * SGPU_MAX_CLASS, ctx));
@@ -386,6 +539,19 @@ int sgpu_epilogue(sgpu_ctx *ctx, sgpu_counts *c, uint32_t L, double eps, double 
         ctx->ft_L = L;
         ctx->ft_valid = true;
     }
+    return SGPU_OK;
+}
+
+int sgpu_epilogue(sgpu_ctx *ctx, sgpu_counts *c, uint32_t L, double eps, double h, double theta, int normalization,
+                  double *h_out, double **d_keep, bool async_out) {
+    cudaStream_t st = ctx->stream;
+    if (normalization < 0 || normalization > 2) {
+        return sgpu_fail(ctx, SGPU_E_ARG, "Invalid normalization: %d", normalization); // similarity_matrix.cpp:264
+    }
+    if (c->nn == 0) {
+        return SGPU_OK;
+    }
+    SGPU_TRY(ensure_ftable(ctx, L, eps, h, theta));
     TransformArgs a;
     a.i32 = c->i32;
     a.spill = c->spill;
@@ -457,6 +623,94 @@ int sgpu_epilogue(sgpu_ctx *ctx, sgpu_counts *c, uint32_t L, double eps, double 
     SGPU_CUDA(ctx, cudaStreamSynchronize(st));
     if (d_keep) {
         *d_keep = out.take();
+    }
+    return SGPU_OK;
+}
+
+// ---- multi-GPU epilogue over peer memory (see slab_raw_kernel) ---------------------------------------------------
+int sgpu_slab_raw_impl(sgpu_ctx *ctx, sgpu_counts *c, const int32_t *const *peer_planes, uint32_t n_peers, uint32_t slab,
+                       uint32_t n_slabs, uint32_t L, double eps, double h, double theta, double **d_extrema) {
+    cudaStream_t st = ctx->stream;
+    if (n_peers == 0 || n_peers > SGPU_MAX_PEERS || n_slabs == 0 || slab >= n_slabs) {
+        return sgpu_fail(ctx, SGPU_E_ARG, "slab epilogue: %u peers (1..%d), slab %u of %u", n_peers, SGPU_MAX_PEERS, slab, n_slabs);
+    }
+    if (c->spill) {
+        return sgpu_fail(ctx, SGPU_E_ARG, "slab epilogue: read pairs overlapping at >= 4 loci (fp64 spill plane) need the reduce-to-one-rank route");
+    }
+    SGPU_TRY(ensure_ftable(ctx, L, eps, h, theta));
+    SlabArgs a;
+    for (uint32_t q = 0; q < SGPU_MAX_PEERS; ++q) {
+        a.peer[q] = q < n_peers ? peer_planes[q] : nullptr;
+    }
+    a.n_peers = n_peers;
+    a.n = c->n;
+    a.nn = c->nn;
+    a.planes_used = c->planes_used;
+    a.f10 = ctx->ft_f10;
+    a.f01 = ctx->ft_f01;
+    for (int d = 0; d < 3; ++d) {
+        a.g2[d] = std::isnan(ctx->ft_g2[d]) ? 0.0 : ctx->ft_g2[d];
+    }
+    for (int d = 0; d < 4; ++d) {
+        a.g3[d] = std::isnan(ctx->ft_g3[d]) ? 0.0 : ctx->ft_g3[d];
+    }
+    const uint32_t nb = (c->n + 31) / 32;
+    const uint64_t n_tiles = static_cast<uint64_t>(nb) * (nb + 1) / 2;
+    // equal numbers of tiles per slab: equal work and equal NVLink traffic for every GPU
+    c->slab_t0 = n_tiles * slab / n_slabs;
+    c->slab_t1 = n_tiles * (slab + 1) / n_slabs;
+    c->slab_nb = nb;
+    const uint64_t mine = c->slab_t1 - c->slab_t0;
+    if (c->slab_raw_tiles < mine) {
+        sgpu_dev_free(ctx, c->slab_raw);
+        c->slab_raw = nullptr;
+        SGPU_CUDA(ctx, sgpu_dev_alloc(ctx, reinterpret_cast<void **>(&c->slab_raw), std::max<uint64_t>(mine, 1) * 1024 * sizeof(double)));
+        c->slab_raw_tiles = mine;
+    }
+    if (!c->slab_minmax) {
+        SGPU_CUDA(ctx, cudaMalloc(&c->slab_minmax, 2 * sizeof(unsigned long long) + 2 * sizeof(double)));
+    }
+    double *ext = reinterpret_cast<double *>(c->slab_minmax + 2);
+    SGPU_CUDA(ctx, cudaMemsetAsync(c->slab_minmax, 0xFF, sizeof(unsigned long long), st));
+    SGPU_CUDA(ctx, cudaMemsetAsync(c->slab_minmax + 1, 0x00, sizeof(unsigned long long), st));
+    if (mine) {
+        SGPU_LAUNCH(ctx, (slab_raw_kernel<<<static_cast<unsigned>(mine), TR_THREADS, 0, st>>>(a, c->slab_t0, nb, c->slab_raw, c->slab_minmax)));
+    } else { // a GPU without tiles still contributes the zero diagonal
+        const unsigned long long z = 0x8000000000000000ull;
+        SGPU_CUDA(ctx, cudaMemcpyAsync(c->slab_minmax, &z, sizeof(z), cudaMemcpyHostToDevice, st));
+        SGPU_CUDA(ctx, cudaMemcpyAsync(c->slab_minmax + 1, &z, sizeof(z), cudaMemcpyHostToDevice, st));
+        SGPU_CUDA(ctx, cudaStreamSynchronize(st));
+    }
+    SGPU_LAUNCH(ctx, (slab_extrema_kernel<<<1, 1, 0, st>>>(c->slab_minmax, ext)));
+    SGPU_CUDA(ctx, cudaGetLastError());
+    if (d_extrema) {
+        *d_extrema = ext;
+    }
+    return SGPU_OK;
+}
+
+int sgpu_slab_finalize_impl(sgpu_ctx *ctx, sgpu_counts *c, int normalization, double *out, double **d_out) {
+    cudaStream_t st = ctx->stream;
+    if (normalization < 0 || normalization > 2) {
+        return sgpu_fail(ctx, SGPU_E_ARG, "Invalid normalization: %d", normalization);
+    }
+    if (!c->slab_minmax) {
+        return sgpu_fail(ctx, SGPU_E_ARG, "sgpu_slab_finalize without sgpu_slab_raw");
+    }
+    if (!out) { // keep this GPU's share on the device, in an n x n matrix of which only its tiles (and their mirror images) are written
+        if (!c->slab_out) {
+            SGPU_CUDA(ctx, cudaMalloc(&c->slab_out, std::max<uint64_t>(1, c->nn) * sizeof(double)));
+        }
+        out = c->slab_out;
+    }
+    const uint64_t mine = c->slab_t1 - c->slab_t0;
+    if (mine) {
+        SGPU_LAUNCH(ctx, (slab_finalize_kernel<<<static_cast<unsigned>(mine), TR_THREADS, 0, st>>>(
+                                 c->slab_raw, c->slab_t0, c->slab_nb, c->n, reinterpret_cast<const double *>(c->slab_minmax + 2), normalization, out)));
+        SGPU_CUDA(ctx, cudaGetLastError());
+    }
+    if (d_out) {
+        *d_out = out;
     }
     return SGPU_OK;
 }

@@ -100,32 +100,29 @@ __device__ bool is_significant_dev(uint32_t c0, uint32_t c1, uint32_t c2, uint32
 
 constexpr int FILTER_THREADS = 256;
 
-// One CTA per locus (grid-stride); 8 entries per 16-byte load once the row is aligned.
+// One WARP per locus (grid-stride over warps), 8 entries per 16-byte load and four loads in flight per lane (2 KB per
+// warp, 128 KB per SM): no CTA-wide barrier per locus, so the load latency of one locus is hidden by the other warps
+// (the CTA-per-locus version paid a barrier pair and an exposed load round trip per locus: 30 % of HBM).
 __global__ void __launch_bounds__(FILTER_THREADS) filter_count_kernel(
         const uint64_t *__restrict__ row_ptr, const uint16_t *__restrict__ gid_base, uint64_t n_loci,
         const uint32_t *__restrict__ in_mask /* bit per group id */, uint32_t n_groups,
         uint4 *__restrict__ counts /* pooled A, C, G, T per locus */, int *__restrict__ err) {
     __shared__ uint32_t s_mask[512]; // one bit per 14-bit group id
-    __shared__ uint32_t s_cnt[4];
-    __shared__ int s_bad;
     const uint32_t mask_words = (n_groups + 31) / 32;
     for (uint32_t i = threadIdx.x; i < 512; i += blockDim.x) {
         s_mask[i] = i < mask_words ? in_mask[i] : 0;
     }
-    if (threadIdx.x < 4) {
-        s_cnt[threadIdx.x] = 0;
-    }
-    if (threadIdx.x == 0) {
-        s_bad = 0;
-    }
     __syncthreads();
     const int lane = threadIdx.x & 31;
-    for (uint64_t l = blockIdx.x; l < n_loci; l += gridDim.x) {
+    const bool aligned = (reinterpret_cast<uintptr_t>(gid_base) & 15u) == 0;
+    const uint64_t warps_total = static_cast<uint64_t>(gridDim.x) * (FILTER_THREADS / 32);
+    uint32_t max_gid = 0;
+    for (uint64_t l = static_cast<uint64_t>(blockIdx.x) * (FILTER_THREADS / 32) + (threadIdx.x >> 5); l < n_loci; l += warps_total) {
         const uint64_t e0 = row_ptr[l], e1 = row_ptr[l + 1];
-        // per-thread counters: one byte per base packed in a word (one shift + add per entry), spilled
-        // into 32-bit counters before a byte can overflow
+        // per-lane counters: one byte per base packed in a word (one shift + add per entry), spilled into 32-bit
+        // counters before a byte can overflow
         uint32_t c[4] = { 0, 0, 0, 0 };
-        uint32_t packed = 0, since_flush = 0, max_gid = 0;
+        uint32_t packed = 0, since_flush = 0;
         auto flush = [&]() {
             c[0] += packed & 0xFFu;
             c[1] += (packed >> 8) & 0xFFu;
@@ -141,33 +138,45 @@ __global__ void __launch_bounds__(FILTER_THREADS) filter_count_kernel(
             const uint32_t in = (s_mask[gid >> 5] >> (gid & 31)) & 1u;
             packed += in << (8u * (gb & 3u));
         };
-        // 16-byte aligned middle part (none if the caller's array itself is not aligned)
-        const bool aligned = (reinterpret_cast<uintptr_t>(gid_base) & 15u) == 0;
-        const uint64_t up = (e0 + 7) & ~static_cast<uint64_t>(7), down = e1 & ~static_cast<uint64_t>(7);
-        const uint64_t a0 = up < e1 ? up : e1, a1 = (aligned && down > a0) ? down : a0;
-        for (uint64_t e = e0 + threadIdx.x; e < a0; e += FILTER_THREADS) {
-            count(gid_base[e]);
-        }
-        for (uint64_t v = a0 + 8ull * threadIdx.x; v < a1; v += 8ull * FILTER_THREADS) {
-            const uint4 q = *reinterpret_cast<const uint4 *>(gid_base + v);
+        auto count8 = [&](const uint4 &q) {
             const uint32_t w[4] = { q.x, q.y, q.z, q.w };
 #pragma unroll
             for (int k = 0; k < 8; ++k) {
                 count((w[k >> 1] >> (16 * (k & 1))) & 0xFFFFu);
             }
-            since_flush += 8;
-            if (since_flush > 240) {
+        };
+        // 16-byte aligned middle part (none if the caller's array itself is not aligned)
+        const uint64_t up = (e0 + 7) & ~static_cast<uint64_t>(7), down = e1 & ~static_cast<uint64_t>(7);
+        const uint64_t a0 = up < e1 ? up : e1, a1 = (aligned && down > a0) ? down : a0;
+        for (uint64_t e = e0 + lane; e < a0; e += 32) { // < 8 entries
+            count(gid_base[e]);
+        }
+        const uint4 *vec = reinterpret_cast<const uint4 *>(gid_base + a0);
+        const uint64_t nv = (a1 - a0) >> 3;
+        for (uint64_t v = lane; v < nv; v += 128) {
+            uint4 q[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                q[u] = v + 32 * u < nv ? vec[v + 32 * u] : make_uint4(0, 0, 0, 0);
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                if (v + 32 * u < nv) {
+                    count8(q[u]);
+                }
+            }
+            since_flush += 32;
+            if (since_flush > 200) {
                 flush();
             }
         }
-        for (uint64_t e = a1 + threadIdx.x; e < e1; e += FILTER_THREADS) { // < 8 entries, or all of an unaligned array
+        for (uint64_t e = a1 + lane; e < e1; e += 32) { // < 8 entries, or all of an unaligned array
             count(gid_base[e]);
-            if (++since_flush > 240) {
+            if (++since_flush > 200) {
                 flush();
             }
         }
         flush();
-        const bool bad = max_gid >= n_groups;
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) {
 #pragma unroll
@@ -176,26 +185,11 @@ __global__ void __launch_bounds__(FILTER_THREADS) filter_count_kernel(
             }
         }
         if (lane == 0) {
-#pragma unroll
-            for (int b = 0; b < 4; ++b) {
-                if (c[b]) {
-                    atomicAdd(&s_cnt[b], c[b]);
-                }
-            }
+            counts[l] = make_uint4(c[0], c[1], c[2], c[3]);
         }
-        if (bad) {
-            s_bad = 1;
-        }
-        __syncthreads();
-        if (threadIdx.x == 0) {
-            if (s_bad) {
-                atomicExch(err, SGPU_E_CELL_RANGE);
-            }
-            counts[l] = make_uint4(s_cnt[0], s_cnt[1], s_cnt[2], s_cnt[3]);
-            s_cnt[0] = s_cnt[1] = s_cnt[2] = s_cnt[3] = 0;
-            s_bad = 0;
-        }
-        __syncthreads();
+    }
+    if (max_gid >= n_groups) {
+        atomicExch(err, SGPU_E_CELL_RANGE);
     }
 }
 
@@ -422,7 +416,7 @@ int sgpu_filter_impl(sgpu_ctx *ctx, const sgpu_pileup *in, const uint32_t *h_id_
         SGPU_CUDA(ctx, cudaFuncSetAttribute(filter_compact_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     }
     if (P) {
-        const unsigned cgrid = static_cast<unsigned>(std::min<uint64_t>(P, static_cast<uint64_t>(ctx->sm_count) * 16));
+        const unsigned cgrid = static_cast<unsigned>(std::min<uint64_t>(ceil_div_u64(P, FILTER_THREADS / 32), static_cast<uint64_t>(ctx->sm_count) * 8));
         DevBuf<uint4> d_counts;
         SGPU_CUDA(ctx, d_counts.alloc(P, ctx));
         SGPU_LAUNCH(ctx, (filter_count_kernel<<<cgrid, FILTER_THREADS, smem, st>>>(in->d_row_ptr, in->d_gid_base, P, d_mask.p, n_groups,

@@ -104,16 +104,18 @@ struct PartitionArgs {
     int *err;
 };
 
-constexpr uint32_t PART_CACHE = 4608; // entries of a locus handled in shared memory (values, ranks, output)
+constexpr uint32_t PART_OUT = 3 * 2048 + 8;               // shared-memory elements of the assembled locus
+constexpr int PART_ROUNDS = 3;                            // rounds of 256 threads x 8 entries
+constexpr uint32_t PART_CACHE = PART_ROUNDS * 2048 - 8;  // entries of a locus handled in registers + shared memory
 
 // Gathers from the group map and scattered 2-byte stores cost one L1 wavefront per lane when they go to
 // global memory; both are done in shared memory here (the map is copied once per CTA, the partitioned
 // locus is assembled in shared memory and written out contiguously).
 __global__ void __launch_bounds__(256) partition_kernel(const PartitionArgs a) {
-    extern __shared__ uint16_t s_dyn[];
+    extern __shared__ __align__(16) uint16_t s_dyn[];
     __shared__ uint32_t s_cnt[ST_MAX_STRIPES + 1]; // entries of the stripe seen so far / start of the stripe
-    uint16_t *s_v = s_dyn, *s_rank = s_dyn + PART_CACHE, *s_out = s_dyn + 2 * PART_CACHE;
-    uint16_t *s_map = s_dyn + 3 * PART_CACHE;      // [n_groups] cell of the group, 0xFFFF = outside the matrix
+    uint16_t *s_out = s_dyn;                       // [PART_OUT] the partitioned locus
+    uint16_t *s_map = s_dyn + PART_OUT;            // [n_groups] cell of the group, 0xFFFF = outside the matrix
     const uint32_t ns = a.n_stripes;
     for (uint32_t g = threadIdx.x; g < a.n_groups; g += 256) {
         const uint32_t c = a.gmap[g];
@@ -141,46 +143,49 @@ __global__ void __launch_bounds__(256) partition_kernel(const PartitionArgs a) {
         uint32_t *sg = a.seg + l * (ns + 1);
         if (n <= PART_CACHE) {
             // one sweep: the shared-memory atomic that counts the stripe also ranks the entry inside it
-            // (~20 stripes: the lanes of a warp spread over them, few same-address conflicts)
+            // (~20 stripes: the lanes of a warp spread over them, few same-address conflicts). Values and ranks stay
+            // in registers between the sweep and the scatter (every thread meets the same entries in both).
             if (threadIdx.x <= ns) {
                 s_cnt[threadIdx.x] = 0;
             }
             __syncthreads();
-            // eight consecutive entries per thread: one 16-byte load and one byte of the bitmap (an aligned
+            // eight consecutive entries per thread and round: one 16-byte load and one byte of the bitmap (an aligned
             // window covers the locus; entries outside it are masked)
             const uint64_t e1 = e0 + n, base = e0 & ~7ull;
             const bool vec_ok = (reinterpret_cast<uintptr_t>(a.gid_base) & 15u) == 0;
-            for (uint64_t v0 = base + 8ull * threadIdx.x; v0 < e1; v0 += 8ull * 256) {
-                __align__(16) uint16_t gb[8];
-                if (vec_ok && v0 >= e0 && v0 + 8 <= e1) {
-                    *reinterpret_cast<uint4 *>(gb) = *reinterpret_cast<const uint4 *>(a.gid_base + v0);
-                } else {
+            uint32_t vr[PART_ROUNDS][8]; // value << 16 | rank inside the stripe; CB_SKIP << 16 = left out
 #pragma unroll
-                    for (int k = 0; k < 8; ++k) {
-                        gb[k] = (v0 + k >= e0 && v0 + k < e1) ? a.gid_base[v0 + k] : 0;
-                    }
-                }
-                const uint32_t special = (a.sp_bits[v0 >> 5] >> (v0 & 31)) & 0xFFu;
+            for (int it = 0; it < PART_ROUNDS; ++it) {
+                const uint64_t v0 = base + 8ull * threadIdx.x + static_cast<uint64_t>(it) * (8 * 256);
 #pragma unroll
                 for (int k = 0; k < 8; ++k) {
-                    const uint64_t e = v0 + k;
-                    if (e < e0 || e >= e1) {
-                        continue;
+                    vr[it][k] = CB_SKIP << 16;
+                }
+                if (v0 < e1) {
+                    __align__(16) uint16_t gb[8];
+                    if (vec_ok && v0 >= e0 && v0 + 8 <= e1) {
+                        *reinterpret_cast<uint4 *>(gb) = *reinterpret_cast<const uint4 *>(a.gid_base + v0);
+                    } else {
+#pragma unroll
+                        for (int k = 0; k < 8; ++k) {
+                            gb[k] = (v0 + k >= e0 && v0 + k < e1) ? a.gid_base[v0 + k] : 0;
+                        }
                     }
-                    uint32_t v = CB_SKIP;
-                    if (!((special >> k) & 1u)) {
+                    const uint32_t special = (a.sp_bits[v0 >> 5] >> (v0 & 31)) & 0xFFu;
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) {
+                        const uint64_t e = v0 + k;
+                        if (e < e0 || e >= e1 || ((special >> k) & 1u)) {
+                            continue;
+                        }
                         const uint32_t gid = gb[k] >> 2;
                         uint32_t cell;
                         if (gid >= a.n_groups || (cell = s_map[gid]) == 0xFFFFu) {
                             atomicExch(a.err, SGPU_E_CELL_RANGE);
                         } else {
-                            v = (cell << 2) | (gb[k] & 3u);
+                            const uint32_t v = (cell << 2) | (gb[k] & 3u);
+                            vr[it][k] = (v << 16) | atomicAdd(&s_cnt[__umulhi(cell, a.stripe_magic)], 1u);
                         }
-                    }
-                    const uint32_t i = static_cast<uint32_t>(e - e0);
-                    s_v[i] = static_cast<uint16_t>(v);
-                    if (v != CB_SKIP) {
-                        s_rank[i] = static_cast<uint16_t>(atomicAdd(&s_cnt[__umulhi(v >> 2, a.stripe_magic)], 1u));
                     }
                 }
             }
@@ -212,16 +217,40 @@ __global__ void __launch_bounds__(256) partition_kernel(const PartitionArgs a) {
                 }
             }
             __syncthreads();
-            for (uint32_t i = threadIdx.x; i < n; i += 256) {
-                const uint32_t v = s_v[i];
-                if (v != CB_SKIP) {
-                    s_out[s_cnt[__umulhi(v >> 2, a.stripe_magic)] + s_rank[i]] = static_cast<uint16_t>(v);
+            // the partitioned locus is assembled in shared memory at the offset (e0 mod 8), so that its 16-byte chunks
+            // line up with those of the output array
+            const uint32_t shift = static_cast<uint32_t>(e0 & 7u);
+#pragma unroll
+            for (int it = 0; it < PART_ROUNDS; ++it) {
+#pragma unroll
+                for (int k = 0; k < 8; ++k) {
+                    const uint32_t v = vr[it][k] >> 16;
+                    if (v != CB_SKIP) {
+                        s_out[shift + s_cnt[__umulhi(v >> 2, a.stripe_magic)] + (vr[it][k] & 0xFFFFu)] = static_cast<uint16_t>(v);
+                    }
                 }
             }
             __syncthreads();
             const uint32_t n_out = s_cnt[ns];
-            for (uint32_t i = threadIdx.x; i < n_out; i += 256) {
-                a.cellbase[e0 + i] = s_out[i];
+            const bool out_vec = (reinterpret_cast<uintptr_t>(a.cellbase) & 15u) == 0;
+            // [shift, shift + n_out) of s_out -> cellbase[e0 ...]: whole 16-byte chunks where they are complete
+            const uint32_t c_lo = out_vec ? (shift + 7) / 8 : 0, c_hi = out_vec ? (shift + n_out) / 8 : 0; // chunks [c_lo, c_hi)
+            if (c_hi > c_lo) {
+                for (uint32_t i = shift + threadIdx.x; i < c_lo * 8; i += 256) {
+                    a.cellbase[base + i] = s_out[i];
+                }
+                uint4 *dst = reinterpret_cast<uint4 *>(a.cellbase + base);
+                const uint4 *src = reinterpret_cast<const uint4 *>(s_out);
+                for (uint32_t c = c_lo + threadIdx.x; c < c_hi; c += 256) {
+                    dst[c] = src[c];
+                }
+                for (uint32_t i = c_hi * 8 + threadIdx.x; i < shift + n_out; i += 256) {
+                    a.cellbase[base + i] = s_out[i];
+                }
+            } else {
+                for (uint32_t i = shift + threadIdx.x; i < shift + n_out; i += 256) {
+                    a.cellbase[base + i] = s_out[i];
+                }
             }
             __syncthreads();
         } else {
@@ -558,6 +587,7 @@ struct WorkList {
     uint32_t ck_shift;  // log2(k-blocks per chunk of the panel layout)
     uint32_t kb_neg0;   // k-blocks >= kb_neg0 hold tail reads only: their B operand is k-block kb + kb_negd (-Z)
     uint32_t kb_negd;
+    unsigned int *wave_ctr; // CTA-pair kernel: pairs that have issued all loads of their n-th work item (null = no wave sync)
 };
 __device__ __forceinline__ WorkItem work_item(const WorkList &wl, uint32_t w) {
     if (w < wl.n_full) {
@@ -857,9 +887,25 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 1)
     if (warp == 0) {
         // ===== TMA producer (both CTAs): own 128 rows of A, own half of B =====
         if (elect_one()) {
-            uint32_t stage = 0, phase = 0;
-            for (uint32_t w = pair; w < n_work; w += n_pairs) {
+            uint32_t stage = 0, phase = 0, wave = 0;
+            for (uint32_t w = pair; w < n_work; w += n_pairs, ++wave) {
                 const WorkItem wi = work_item(wl, w);
+                // Wave sync: the pairs start the loads of their n-th tile together. The tiles of a wave share operand
+                // slabs through L2, but L2 only holds what was fetched during the last ~30 us; without this the pairs
+                // drift apart (diagonal tiles have slower epilogues) and every pair streams its slabs from HBM again.
+                // All pairs are resident (grid <= SM count, one CTA per SM), every wave before the last one is full.
+                if (wl.wave_ctr != nullptr && leader && wave > 0) {
+                    atomicAdd(wl.wave_ctr, 1u);
+                    // arrivals so far: n_pairs per earlier wave, and the pairs that have an item in this (maybe last, partial) wave
+                    const uint32_t want = (wave - 1) * n_pairs + min(n_pairs, n_work - wave * n_pairs);
+                    uint32_t seen;
+                    do {
+                        asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(wl.wave_ctr) : "memory");
+                        if (seen < want) {
+                            __nanosleep(64);
+                        }
+                    } while (seen < want);
+                }
                 for (uint32_t kb = wi.k0; kb < wi.k1; ++kb) {
                     mbar_wait(empty0 + 8 * stage, phase ^ 1);
                     const uint32_t sa = smem_u32(smem + stage * STAGE2_BYTES), sb = sa + A_BYTES;
@@ -994,12 +1040,15 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 1)
 // ~20 000: bands of 8 column blocks, row-block-major inside a band.
 static int tile_list(sgpu_ctx *ctx, uint32_t N, uint32_t n_pad, uint32_t bm /* tile height: 128, or 256 for CTA pairs */,
                      const uint2 **d_tiles, uint32_t *n_tiles) {
-    if (ctx->tile_cache && ctx->tile_cache_cells == N && ctx->tile_cache_bm == bm) {
+    uint32_t BAND = 8;
+    if (const char *env = getenv("SECEDO_B200_TILE_BAND")) { // raster experiments (profiles/)
+        BAND = static_cast<uint32_t>(std::max(1, atoi(env)));
+    }
+    if (ctx->tile_cache && ctx->tile_cache_cells == N && ctx->tile_cache_bm == (bm | (BAND << 16))) {
         *d_tiles = static_cast<const uint2 *>(ctx->tile_cache);
         *n_tiles = ctx->tile_cache_n;
         return SGPU_OK;
     }
-    constexpr uint32_t BAND = 8;
     std::vector<uint2> tiles;
     const uint32_t n_cb = n_pad / BN, n_rb = n_pad / bm;
     for (uint32_t band = 0; band < n_cb; band += BAND) {
@@ -1021,7 +1070,7 @@ static int tile_list(sgpu_ctx *ctx, uint32_t N, uint32_t n_pad, uint32_t bm /* t
     SGPU_CUDA(ctx, cudaMalloc(&ctx->tile_cache, std::max<size_t>(1, tiles.size()) * sizeof(uint2)));
     SGPU_CUDA(ctx, cudaMemcpy(ctx->tile_cache, tiles.data(), tiles.size() * sizeof(uint2), cudaMemcpyHostToDevice));
     ctx->tile_cache_cells = N;
-    ctx->tile_cache_bm = bm;
+    ctx->tile_cache_bm = bm | (BAND << 16);
     ctx->tile_cache_n = static_cast<uint32_t>(tiles.size());
     *d_tiles = static_cast<const uint2 *>(ctx->tile_cache);
     *n_tiles = ctx->tile_cache_n;
@@ -1109,9 +1158,15 @@ int sgpu_gemm_run(sgpu_ctx *ctx, const GemmInput &in, uint32_t N, int32_t *S_pla
         if (fn == nullptr || qres != cudaDriverEntryPointSuccess) {
             return sgpu_fail(ctx, SGPU_E_CUDA, "driver does not provide cuTensorMapEncodeTiled");
         }
+        CUtensorMapL2promotion promo = CU_TENSOR_MAP_L2_PROMOTION_L2_256B;
+        if (const char *env = getenv("SECEDO_B200_L2_PROMO")) { // 0 / 64 / 128 / 256 (profiles/)
+            const int v = atoi(env);
+            promo = v == 0 ? CU_TENSOR_MAP_L2_PROMOTION_NONE : v == 64 ? CU_TENSOR_MAP_L2_PROMOTION_L2_64B
+                    : v == 128 ? CU_TENSOR_MAP_L2_PROMOTION_L2_128B : CU_TENSOR_MAP_L2_PROMOTION_L2_256B;
+        }
         CUresult r = reinterpret_cast<encode_fn>(fn)(&map, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, U.p, gdim, gstride, box, estr,
                                             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
-                                            CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                                            promo, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         if (r != CUDA_SUCCESS) {
             return sgpu_fail(ctx, SGPU_E_CUDA, "cuTensorMapEncodeTiled failed (%d)", static_cast<int>(r));
         }
@@ -1119,6 +1174,8 @@ int sgpu_gemm_run(sgpu_ctx *ctx, const GemmInput &in, uint32_t N, int32_t *S_pla
     // CTA pairs (tcgen05 cta_group::2, 256 x 256 tiles) or single CTAs (128 x 256 tiles)
     const char *env_pair = getenv("SECEDO_B200_GEMM_PAIRS");
     const bool pairs = env_pair ? env_pair[0] == '1' : (ctx->sm_count % 2 == 0); // default; SECEDO_B200_GEMM_PAIRS=0 for single CTAs
+    const char *env_ws = getenv("SECEDO_B200_WAVE_SYNC");
+    const bool wave_sync = env_ws ? env_ws[0] == '1' : true;
     SGPU_CUDA(ctx, cudaFuncSetAttribute(syrk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
     SGPU_CUDA(ctx, cudaFuncSetAttribute(syrk2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM2_BYTES));
     const uint2 *d_tiles = nullptr;
@@ -1164,7 +1221,7 @@ int sgpu_gemm_run(sgpu_ctx *ctx, const GemmInput &in, uint32_t N, int32_t *S_pla
         pa.seg = seg.p;
         pa.err = d_err.p;
         const unsigned grid = static_cast<unsigned>(std::min<uint64_t>(in.n_loci, static_cast<uint64_t>(sms) * 16));
-        const size_t psmem = (3 * static_cast<size_t>(PART_CACHE) + in.n_groups) * sizeof(uint16_t);
+        const size_t psmem = (static_cast<size_t>(PART_OUT) + in.n_groups) * sizeof(uint16_t);
         SGPU_CUDA(ctx, cudaFuncSetAttribute(partition_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(psmem)));
         SGPU_LAUNCH(ctx, (partition_kernel<<<grid, 256, psmem, st>>>(pa)));
     }
@@ -1207,6 +1264,7 @@ int sgpu_gemm_run(sgpu_ctx *ctx, const GemmInput &in, uint32_t N, int32_t *S_pla
         wl.ck_shift = pl.ck_shift;
         wl.kb_neg0 = kbs_main;
         wl.kb_negd = kt;
+        wl.wave_ctr = nullptr;
         // whole tiles in full rounds of the grid; the rest (or everything, when there are few tiles) in
         // K ranges so that every SM has work in the last round
         const uint32_t units = pairs ? sms / 2 : sms; // CTAs or CTA pairs that take work items
@@ -1223,6 +1281,10 @@ int sgpu_gemm_run(sgpu_ctx *ctx, const GemmInput &in, uint32_t N, int32_t *S_pla
         // the planes are zero right after sgpu_counts_zero: the first panel stores, later ones add in place
         const int epi = *fresh ? EPI_STORE : EPI_RMW;
         const unsigned grid = static_cast<unsigned>(std::min<uint64_t>(wl.n_work, units));
+        if (pairs && wave_sync) {
+            wl.wave_ctr = reinterpret_cast<unsigned int *>(d_err.p + 1);
+            SGPU_CUDA(ctx, cudaMemsetAsync(d_err.p + 1, 0, sizeof(int), st));
+        }
         mark(); // [3k+1] staging done, GEMM begins
         if (pairs) {
             SGPU_LAUNCH(ctx, (syrk2_kernel<<<2 * grid, GEMM_THREADS, SMEM2_BYTES, st>>>(map, wl, S_plane, D_plane, N, epi)));

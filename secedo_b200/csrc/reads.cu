@@ -127,32 +127,108 @@ __device__ __forceinline__ void emit_link(uint2 *rbuf, uint32_t *s_cnt, uint2 *_
     }
 }
 
-__global__ void __launch_bounds__(WIN_THREADS) link_window_kernel(
+// cp.async helpers: global -> shared without staging registers
+__device__ __forceinline__ void cp_async4(void *dst, const void *src) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(static_cast<uint32_t>(__cvta_generic_to_shared(dst))), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async16(void *dst, const void *src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(static_cast<uint32_t>(__cvta_generic_to_shared(dst))), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+    asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+
+constexpr uint32_t WIN_RING = 3;   // loci whose read ids are resident in shared memory: the owner and the two after it
+constexpr uint32_t WIN_META = 64;  // owners per block of locus metadata kept in shared memory
+constexpr uint32_t WIN_META_N = WIN_META + WIN_RING + 1;
+
+// Every CTA owns a CONTIGUOUS range of owner loci, so the loci of an owner's window are the next owners: the read ids of
+// a locus are fetched from global memory once per CTA (cp.async into a ring of WIN_RING slots, two loci ahead of the
+// owner being processed) and serve first as window entries of the preceding owners, then as the owner's own table.
+// Neither the window probes nor the table build wait for global memory any more (the version that took the owners in
+// a grid-stride loop read every entry 1 + (loci per window) times and exposed four dependent global round trips per
+// owner: 14 % of HBM, barrier stalls). Window loci beyond the ring (dense loci: more than two within L bp) are still
+// streamed from global memory.
+__global__ void __launch_bounds__(WIN_THREADS, 2) link_window_kernel(
         const uint64_t *__restrict__ row_ptr, const uint32_t *__restrict__ position, const uint32_t *__restrict__ read_id,
-        const uint8_t *__restrict__ lchr, const uint64_t *__restrict__ chr_ptr, uint64_t n_loci, uint32_t L,
-        uint32_t slots /* power of two */, uint32_t id_cap, uint2 *__restrict__ links, uint64_t cap,
-        WinCounters *__restrict__ ctr) {
-    extern __shared__ uint32_t s_mem[];
-    uint32_t *ids = s_mem;                                              // [id_cap]
-    uint2 *rbuf = reinterpret_cast<uint2 *>(s_mem + id_cap);            // [REC_BUF] (id_cap is even)
-    unsigned short *tab = reinterpret_cast<unsigned short *>(rbuf + REC_BUF); // [slots]
+        const uint8_t *__restrict__ lchr, uint64_t n_loci, uint32_t L, uint32_t loci_per_cta,
+        uint32_t slots /* power of two */, uint32_t id_cap /* multiple of 4, >= largest locus + 4 */, uint2 *__restrict__ links,
+        uint64_t cap, WinCounters *__restrict__ ctr) {
+    extern __shared__ __align__(16) uint32_t s_mem[];
+    uint32_t *ring = s_mem;                                                          // [WIN_RING][id_cap]
+    uint2 *rbuf = reinterpret_cast<uint2 *>(s_mem + WIN_RING * id_cap);              // [REC_BUF]
+    unsigned short *tab = reinterpret_cast<unsigned short *>(rbuf + REC_BUF);       // [slots]
+    __shared__ uint64_t s_row[WIN_META_N + 1];
+    __shared__ uint32_t s_pos[WIN_META_N];
+    __shared__ uint8_t s_chr[WIN_META_N];
     __shared__ uint32_t s_cnt;
     __shared__ unsigned long long s_base;
     const uint32_t mask = slots - 1, shift = 32 - (31 - __clz(slots));
+    const uint64_t la = static_cast<uint64_t>(blockIdx.x) * loci_per_cta;
+    const uint64_t lb = min(n_loci, la + loci_per_cta);
     if (threadIdx.x == 0) {
         s_cnt = 0;
     }
-    for (uint64_t lo = blockIdx.x; lo < n_loci; lo += gridDim.x) {
-        const uint64_t e0 = row_ptr[lo];
-        const uint32_t n = static_cast<uint32_t>(row_ptr[lo + 1] - e0);
-        const uint64_t chr_end = chr_ptr[lchr[lo] + 1];
-        const uint32_t p0 = position[lo];
-        const bool has_window = lo + 1 < chr_end && position[lo + 1] - p0 < L;
-        if (n == 0 || (n < 2 && !has_window)) {
-            continue; // nothing this owner could link (uniform over the CTA)
+    if (la >= lb) {
+        return;
+    }
+    const bool aligned16 = (reinterpret_cast<uintptr_t>(read_id) & 15u) == 0; // else everything goes in 4-byte copies
+    uint64_t meta0 = la; // first locus of the metadata block in shared memory
+    auto load_meta = [&](uint64_t base) {
+        for (uint32_t i = threadIdx.x; i <= WIN_META_N; i += WIN_THREADS) {
+            const uint64_t l = base + i;
+            s_row[i] = row_ptr[min(l, n_loci)];
+            if (i < WIN_META_N) {
+                s_pos[i] = l < n_loci ? position[l] : 0;
+                s_chr[i] = l < n_loci ? lchr[l] : 0xFF;
+            }
         }
-        __syncthreads(); // the previous owner's probes are done
-        if (s_cnt > REC_BUF / 2) { // uniform: nobody emits before the next barrier
+    };
+    // the ids of locus l start at ring slot (l % WIN_RING) at element (first entry & 3): source and destination are
+    // congruent modulo 16 bytes, so the body goes in 16-byte copies
+    auto prefetch = [&](uint64_t l) {
+        if (l < n_loci && l - meta0 < WIN_META_N) {
+            const uint64_t e0 = s_row[l - meta0], e1 = s_row[l - meta0 + 1];
+            uint32_t *dst = ring + (l % WIN_RING) * id_cap + (e0 & 3u);
+            const uint32_t *src = read_id + e0;
+            const uint32_t n = static_cast<uint32_t>(e1 - e0);
+            const uint32_t head = aligned16 ? min(n, static_cast<uint32_t>((4 - (e0 & 3u)) & 3u)) : n;
+            const uint32_t body = (n - head) >> 2;
+            for (uint32_t i = threadIdx.x; i < head; i += WIN_THREADS) {
+                cp_async4(dst + i, src + i);
+            }
+            for (uint32_t i = threadIdx.x; i < body; i += WIN_THREADS) {
+                cp_async16(dst + head + 4 * i, src + head + 4 * i);
+            }
+            const uint32_t done = head + 4 * body;
+            if (threadIdx.x < n - done) {
+                cp_async4(dst + done + threadIdx.x, src + done + threadIdx.x);
+            }
+        }
+        cp_async_commit(); // one group per call, also when nothing was copied: the group arithmetic below stays uniform
+    };
+    load_meta(meta0);
+    __syncthreads();
+    prefetch(la);
+    prefetch(la + 1);
+    for (uint64_t lo = la; lo < lb; ++lo) {
+        if (lo - meta0 >= WIN_META) { // next block of metadata (nothing is in flight that reads the old one: see the barrier below)
+            cp_async_wait<0>();
+            __syncthreads();
+            meta0 = lo;
+            load_meta(meta0);
+            __syncthreads();
+        }
+        const uint32_t mi = static_cast<uint32_t>(lo - meta0);
+        const uint64_t e0 = s_row[mi];
+        const uint32_t n = static_cast<uint32_t>(s_row[mi + 1] - e0);
+        const uint32_t p0 = s_pos[mi];
+        const uint32_t chr = s_chr[mi];
+        const uint32_t *ids = ring + (lo % WIN_RING) * id_cap + (e0 & 3u);
+        // flush the staged links while nobody emits (uniform: s_cnt is read after the barrier that ended the last owner)
+        if (s_cnt > REC_BUF / 2) {
             const uint32_t m = min(s_cnt, REC_BUF);
             if (threadIdx.x == 0) {
                 s_base = atomicAdd(&ctr->n_links, static_cast<unsigned long long>(m));
@@ -168,12 +244,11 @@ __global__ void __launch_bounds__(WIN_THREADS) link_window_kernel(
                 s_cnt = 0;
             }
         }
+        prefetch(lo + 2); // into the slot of owner lo - 1, which the barrier at the end of its turn released
         for (uint32_t i = threadIdx.x; i < slots / 2; i += WIN_THREADS) {
             reinterpret_cast<uint32_t *>(tab)[i] = 0xFFFFFFFFu;
         }
-        for (uint32_t i = threadIdx.x; i < n; i += WIN_THREADS) {
-            ids[i] = read_id[e0 + i];
-        }
+        cp_async_wait<1>(); // loci lo and lo + 1 have arrived (issued at least one owner ago)
         __syncthreads();
         // round 1: optimistic placement at the home slot
         for (uint32_t i = threadIdx.x; i < n; i += WIN_THREADS) {
@@ -204,43 +279,80 @@ __global__ void __launch_bounds__(WIN_THREADS) link_window_kernel(
             }
         }
         __syncthreads();
-        // the loci of the window
-        for (uint64_t l = lo + 1; l < chr_end; ++l) {
-            if (position[l] - p0 >= L) {
+        // the loci of the window: same chromosome, less than L bp after the owner
+        for (uint64_t l = lo + 1; l < n_loci; ++l) {
+            const bool meta_here = l - meta0 < WIN_META_N;
+            const uint32_t pl = meta_here ? s_pos[l - meta0] : position[l];
+            const uint32_t cl = meta_here ? s_chr[l - meta0] : lchr[l];
+            if (cl != chr || pl - p0 >= L) {
                 break;
             }
-            const uint64_t a0 = row_ptr[l], a1 = row_ptr[l + 1];
-            for (uint64_t eb = a0 + threadIdx.x; eb < a1; eb += 4 * WIN_THREADS) {
-                uint32_t id4[4];
-#pragma unroll
-                for (int u = 0; u < 4; ++u) { // four loads in flight
-                    const uint64_t e = eb + u * WIN_THREADS;
-                    id4[u] = e < a1 ? read_id[e] : 0;
+            const uint64_t a0 = meta_here ? s_row[l - meta0] : row_ptr[l];
+            const uint64_t a1 = meta_here ? s_row[l - meta0 + 1] : row_ptr[l + 1];
+            const uint32_t nl = static_cast<uint32_t>(a1 - a0);
+            if (l <= lo + 2 && meta_here) {
+                if (l == lo + 2) { // the locus prefetched in this turn
+                    cp_async_wait<0>();
+                    __syncthreads();
                 }
+                const uint32_t *wid = ring + (l % WIN_RING) * id_cap + (a0 & 3u);
+                for (uint32_t ib = threadIdx.x; ib < nl; ib += 4 * WIN_THREADS) {
+                    uint32_t id4[4], cur4[4], s4[4];
 #pragma unroll
-                for (int u = 0; u < 4; ++u) {
-                    const uint64_t e = eb + u * WIN_THREADS;
-                    if (e >= a1) {
-                        break;
+                    for (int u = 0; u < 4; ++u) { // four independent table look-ups in flight
+                        const uint32_t i = ib + u * WIN_THREADS;
+                        id4[u] = i < nl ? wid[i] : 0;
+                        s4[u] = slot_hash(id4[u], shift);
+                        cur4[u] = i < nl ? tab[s4[u]] : SLOT_EMPTY;
                     }
-                    const uint32_t id = id4[u];
-                    uint32_t s = slot_hash(id, shift);
-                    for (;;) {
-                        const uint32_t cur = tab[s];
-                        if (cur == SLOT_EMPTY) {
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        uint32_t cur = cur4[u], sl = s4[u];
+                        while (cur != SLOT_EMPTY) {
+                            if (ids[cur] == id4[u]) {
+                                emit_link(rbuf, &s_cnt, links, cap, ctr, static_cast<uint32_t>(e0) + cur,
+                                          static_cast<uint32_t>(a0) + ib + u * WIN_THREADS);
+                                break;
+                            }
+                            sl = (sl + 1) & mask;
+                            cur = tab[sl];
+                        }
+                    }
+                }
+            } else {
+                for (uint64_t eb = a0 + threadIdx.x; eb < a1; eb += 4 * WIN_THREADS) {
+                    uint32_t id4[4];
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) { // four loads in flight
+                        const uint64_t e = eb + u * WIN_THREADS;
+                        id4[u] = e < a1 ? read_id[e] : 0;
+                    }
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        const uint64_t e = eb + u * WIN_THREADS;
+                        if (e >= a1) {
                             break;
                         }
-                        if (ids[cur] == id) {
-                            emit_link(rbuf, &s_cnt, links, cap, ctr, static_cast<uint32_t>(e0) + cur, static_cast<uint32_t>(e));
-                            break;
+                        const uint32_t id = id4[u];
+                        uint32_t sl = slot_hash(id, shift);
+                        for (;;) {
+                            const uint32_t cur = tab[sl];
+                            if (cur == SLOT_EMPTY) {
+                                break;
+                            }
+                            if (ids[cur] == id) {
+                                emit_link(rbuf, &s_cnt, links, cap, ctr, static_cast<uint32_t>(e0) + cur, static_cast<uint32_t>(e));
+                                break;
+                            }
+                            sl = (sl + 1) & mask;
                         }
-                        s = (s + 1) & mask;
                     }
                 }
             }
         }
+        __syncthreads(); // the probes of this owner are done: its table and its ring slot may be reused
     }
-    __syncthreads();
+    cp_async_wait<0>();
     const uint32_t m = min(s_cnt, REC_BUF);
     if (m) {
         if (threadIdx.x == 0) {
@@ -846,13 +958,16 @@ int sgpu_link_reads(sgpu_ctx *ctx, const sgpu_pileup *p, uint32_t num_cells, uin
 
     SGPU_TRACE(ctx, "link: allocs+meta");
     // ---- links between entries of one read -----------------------------------------------------------
-    // table geometry: slots >= 3 x the largest locus if shared memory allows, never below 1.25 x
-    const uint32_t id_cap = (max_n + 1) & ~1u;
+    // table geometry: slots >= 3 x the largest locus if shared memory allows, never below 1.25 x; the ring holds the
+    // read ids of WIN_RING loci (each slot: the largest locus + up to 3 elements of alignment offset)
+    const uint32_t id_cap = (max_n + 3 + 3) & ~3u;
     uint32_t slots = 1024;
     while (slots < 3ull * max_n && slots < 65536) {
         slots <<= 1;
     }
-    auto win_smem = [&](uint32_t s) { return static_cast<size_t>(id_cap) * 4 + REC_BUF * sizeof(uint2) + static_cast<size_t>(s) * 2; };
+    auto win_smem = [&](uint32_t s) {
+        return static_cast<size_t>(WIN_RING) * id_cap * 4 + REC_BUF * sizeof(uint2) + static_cast<size_t>(s) * 2;
+    };
     while (slots > 1024 && win_smem(slots) > WIN_SMEM_LIMIT) {
         slots >>= 1;
     }
@@ -871,10 +986,13 @@ int sgpu_link_reads(sgpu_ctx *ctx, const sgpu_pileup *p, uint32_t num_cells, uin
         if (use_window) {
             const size_t smem = win_smem(slots);
             SGPU_CUDA(ctx, cudaFuncSetAttribute(link_window_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-            const unsigned per_sm = static_cast<unsigned>(std::max<size_t>(1, std::min<size_t>(4, (224 * 1024) / (smem + 1280))));
-            const unsigned wgrid = static_cast<unsigned>(std::min<uint64_t>(P, static_cast<uint64_t>(ctx->sm_count) * per_sm));
-            SGPU_LAUNCH(ctx, (link_window_kernel<<<wgrid, WIN_THREADS, smem, st>>>(p->d_row_ptr, p->d_position, p->d_read_id, out->lchr.p,
-                                                                                  p->d_chr_ptr, P, L, slots, id_cap, links.p, cap, d_ctr.p)));
+            const unsigned per_sm = static_cast<unsigned>(std::max<size_t>(1, std::min<size_t>(4, (224 * 1024) / (smem + 2560))));
+            // contiguous ranges of owner loci, one per CTA, all CTAs resident at once
+            const uint64_t want = std::min<uint64_t>(P, static_cast<uint64_t>(ctx->sm_count) * per_sm);
+            const uint32_t loci_per_cta = static_cast<uint32_t>(ceil_div_u64(P, want));
+            const unsigned wgrid = static_cast<unsigned>(ceil_div_u64(P, loci_per_cta));
+            SGPU_LAUNCH(ctx, (link_window_kernel<<<wgrid, WIN_THREADS, smem, st>>>(p->d_row_ptr, p->d_position, p->d_read_id, out->lchr.p, P, L,
+                                                                                  loci_per_cta, slots, id_cap, links.p, cap, d_ctr.p)));
         } else {
             DevBuf<uint64_t> keys;
             DevBuf<uint32_t> vals;

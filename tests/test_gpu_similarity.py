@@ -246,6 +246,35 @@ def test_full_size_paths_agree(gpu_ctx, n_cells, coverage, loci_per_chr):
     two.free()
 
 
+@pytest.mark.parametrize("path", PATHS)
+def test_cfg3_full_cell_count_vs_oracle(gpu_ctx, path):
+    """BASELINE.json configs[2] at its REAL cell count: 8 000 cells at 0.5x (about 4 000 reads per locus, 8 M cross-cell
+    pairs per locus) with the multi-locus share SURVEY F1 measured on the reference's own fixture (16 % of reads cover
+    >= 2 loci) and the reference's flags_sim likelihood parameters, on a locus prefix the enumerating oracle finishes in
+    ~20 s: integer counts bit-exact, matrix within 1e-6 * max|M| for all three normalisations."""
+    cfg = SynthConfig(n_cells=8000, coverage=0.5, n_loci=30, n_chr=1, p_multi=0.16, p_mate=0.02, theta=0.001, seed=5)
+    p = make_pileup(cfg)
+    ident = np.arange(cfg.n_cells, dtype=np.uint32)
+    f, _ = api.Filter(0.001, 4, gpu_ctx).filter(p, ident, "", 1)
+    assert f.n_loci >= 10
+    st, o = check_counts(gpu_ctx, f, cfg.n_cells, 1000, ident, 0.01, 0.15, 0.001, 8, path)
+    assert st["n_multi_reads"] > 1000 and st["n_tail_reads"] > 0 and o.H.sum() > 0
+
+
+@pytest.mark.parametrize("path", PATHS)
+def test_cfg4_full_cell_count_vs_oracle(gpu_ctx, path):
+    """configs[3] at its real cell count: 10 000 cells at 0.05x, 4 clones, flags_breast parameters (h = 0.5,
+    theta = 0.001, eps = 0.01), ~600 pre-filter loci: counts bit-exact against the oracle, matrix within tolerance."""
+    cfg = SynthConfig(n_cells=10000, coverage=0.05, n_loci=600, n_chr=2, n_clones=4, p_multi=0.16, p_mate=0.02,
+                      theta=0.001, seed=6)
+    p = make_pileup(cfg)
+    ident = np.arange(cfg.n_cells, dtype=np.uint32)
+    f, _ = api.Filter(0.001, 4, gpu_ctx).filter(p, ident, "", 1)
+    assert f.n_loci >= 300
+    st, o = check_counts(gpu_ctx, f, cfg.n_cells, 1000, ident, 0.01, 0.5, 0.001, 8, path)
+    assert st["n_multi_reads"] > 1000 and o.H.sum() > 0
+
+
 @pytest.mark.parametrize("threads", [1, 2, 8])
 def test_second_order_gemm_vs_oracle(gpu_ctx, threads, monkeypatch):
     """the pairs that overlap at two loci counted by the tcgen05 path on the derived pileup of locus pairs
