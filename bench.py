@@ -4,19 +4,23 @@ loci/s at 8K cells, 0.5x, on 1/2/4/8 B200, next to the reference's OpenMP CPU pa
 
     python bench.py --gpus N --steps K --warmup W            (N > 1: launched with torchrun)
     python bench.py --impl reference --steps K --warmup W    (the reference's own CPU path)
+    python bench.py --workload cfg3-genome --gpus N          (whole genome, 23 chromosomes, strong scaling, absolute seconds)
 
-A step = one pass of the hot path over one batch of synthetic pileup per GPU:
-    Filter::filter -> read linking / mate rule / cutoff -> first-order counts (int8 tcgen05 GEMM)
-    -> multi-locus correction -> [NCCL reduce of the count planes] -> log-likelihood epilogue.
-Weak scaling: every rank owns its own chromosomes (its own seed); rank 0 produces the N x N matrix.
-`value` times the steps with the batch already resident in HBM; `e2e` times the same call sequence
-with HOST (pinned) buffers: the H2D copy of the whole batch and the D2H copy of the matrix are inside
-the timed region. The CPU baseline / reference arm run the UNMODIFIED reference compiled into
-oracle/_ref (or, if that .so is absent, the oracle port) on a bounded sample of the same workload.
+A step = one pass of the hot path over this GPU's share of the pileup and ONE similarity matrix:
+    for each of SUB sub-batches of chromosomes: Filter::filter -> read linking / mate rule / cutoff
+        -> first-order counts (int8 tcgen05 GEMM) -> multi-locus correction, accumulated into one set of count planes
+    -> the multi-GPU epilogue over peer memory (every GPU sums the planes of all GPUs over its share of the matrix through
+       NVLink and applies the log-likelihood transform in the same kernel; one scalar all-reduce) -> N x N matrix.
+Weak scaling: every rank owns its own chromosomes (its own seeds). `value` times the steps with the pileup already
+resident in HBM; `e2e` times the same call sequence with HOST (pinned) buffers: the H2D copy of the whole pileup and
+the transfer of the matrix into host memory are inside the timed region. The CPU baseline / reference arm run the
+UNMODIFIED reference compiled into oracle/_ref (or, if that .so is absent, the oracle port) on a bounded sample of the
+same workload, and the GPU path is checked against that very run (`parity_vs_reference`).
 """
 from __future__ import annotations
 
 import argparse
+import ctypes
 import json
 import os
 import subprocess
@@ -29,21 +33,27 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-# ---- workload: BASELINE.json configs[2] (headline; one batch of it fits one GPU) ----------------------
+# ---- workload: BASELINE.json configs[2] (headline) ---------------------------------------------------------------
 WORKLOAD = dict(
-    name="cfg3: 8000 cells x 0.5x, batch of whole-genome-style pileup (4 chromosomes x %d pre-filter loci per GPU and step)",
+    name="cfg3: 8000 cells x 0.5x, whole-genome-style pileup: %d sub-batches of 4 chromosomes x %d pre-filter loci per GPU "
+         "and step, one similarity matrix per step",
     n_cells=int(os.environ.get("SECEDO_BENCH_CELLS", 8000)),
     coverage=float(os.environ.get("SECEDO_BENCH_COVERAGE", 0.5)),
     n_chr=4,
     loci_per_chr=int(os.environ.get("SECEDO_BENCH_LOCI_PER_CHR", 32768)),
+    sub_batches=int(os.environ.get("SECEDO_BENCH_SUB_BATCHES", 4)),
     n_clones=2, frac_somatic=0.5, frac_germline=0.1, spacing=400,
     p_multi=float(os.environ.get("SECEDO_BENCH_P_MULTI", 0.005)),
     p_mate=float(os.environ.get("SECEDO_BENCH_P_MATE", 0.01)), p_mate_mismatch=0.2,
     # flags_sim of the reference: h = 0.15, theta = 0.001, eps = 0.01; with theta = 0.01 the reference's
     # filter accepts pure noise at this pooled coverage
-    theta=0.001, eps=0.01, h=0.15, L=1000, num_threads=8, normalization="ADD_MIN",
+    theta=0.001, eps=0.01, h=0.15, L=1000, normalization="ADD_MIN",
 )
 CPU_SAMPLE_LOCI = int(os.environ.get("SECEDO_BENCH_CPU_LOCI", 28))  # pre-filter loci of the CPU sample
+# human chromosome lengths (the reference's own table, pileup.cpp:30-34): proportions of the whole-genome workload
+CHROMOSOME_LENGTHS = [248956422, 242193529, 198295559, 190214555, 181538259, 170805979, 159345973, 145138636, 138394717,
+                      133797422, 135086622, 133275309, 114364328, 107043718, 101991189, 90338345, 83257441, 80373285,
+                      58617616, 64444167, 46709983, 50818468, 156040895]
 
 
 def clocks_sampler(stop, out, device_index):
@@ -84,6 +94,46 @@ def summarize_clocks(lines):
             "samples": len(sm)}
 
 
+ALL_CPUS = None  # the cores this process was given, before bind_to_gpu_numa narrowed them
+
+
+def bind_to_gpu_numa(torch, local_rank):
+    """Run this rank, and allocate its pinned buffers, on the NUMA node its GPU hangs off (best effort: the container's
+    cpuset may forbid it). Returns what was done, for the JSON line."""
+    global ALL_CPUS
+    info = {"numa_node": None, "cpus": None, "affinity_set": False, "mempolicy_set": False}
+    try:
+        ALL_CPUS = os.sched_getaffinity(0)
+        pr = torch.cuda.get_device_properties(local_rank)
+        bus = f"{pr.pci_domain_id:04x}:{pr.pci_bus_id:02x}:{pr.pci_device_id:02x}.0"
+        base = f"/sys/bus/pci/devices/{bus}"
+        node = int(open(base + "/numa_node").read().strip())
+        cpulist = open(base + "/local_cpulist").read().strip()
+        cpus = set()
+        for part in cpulist.split(","):
+            if "-" in part:
+                a, b = part.split("-")
+                cpus.update(range(int(a), int(b) + 1))
+            elif part:
+                cpus.add(int(part))
+        info["numa_node"], info["pci"] = node, bus
+        allowed = os.sched_getaffinity(0)
+        use = cpus & allowed
+        info["cpus"] = len(use)
+        if use and use != allowed:
+            os.sched_setaffinity(0, use)
+            info["affinity_set"] = True
+        if node >= 0:
+            libc = ctypes.CDLL(None, use_errno=True)
+            mask = ctypes.c_ulong(1 << node)
+            MPOL_PREFERRED, SYS_set_mempolicy = 1, 238  # x86_64
+            if libc.syscall(SYS_set_mempolicy, MPOL_PREFERRED, ctypes.byref(mask), ctypes.c_ulong(64)) == 0:
+                info["mempolicy_set"] = True
+    except Exception as ex:  # noqa: BLE001
+        info["error"] = f"{type(ex).__name__}: {ex}"
+    return info
+
+
 # ---------------------------------------------------------------------------------------- reference arm
 def cpu_sample(seed=77):
     """A bounded sample of the workload, generated on the host (same model as the device generator)."""
@@ -121,14 +171,22 @@ def run_reference_step(p, threads, want_matrix=False):
 
 def reference_threads():
     """all host cores the process may use (torchrun exports OMP_NUM_THREADS=1; the reference takes its
-    thread count as an argument, so that variable does not limit it)"""
-    from oracle import pyoracle as po
-    if po.have_ref():
-        try:
-            return max(1, len(os.sched_getaffinity(0)))
-        except AttributeError:
-            return max(1, os.cpu_count() or 1)
-    return 1
+    thread count as an argument, so that variable does not limit it). Also the `num_threads` BOTH arms pass to the
+    path: it selects the reference's tail cutoff, so parity is defined at this value."""
+    env = os.environ.get("SECEDO_BENCH_THREADS")
+    if env:
+        return max(1, int(env))
+    if ALL_CPUS:
+        return len(ALL_CPUS)
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except AttributeError:
+        return max(1, os.cpu_count() or 1)
+
+
+def workload_name():
+    w = WORKLOAD
+    return w["name"] % (w["sub_batches"], w["loci_per_chr"])
 
 
 def main_reference(args):
@@ -151,8 +209,8 @@ def main_reference(args):
         "unit": "loci/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": 1e3 * total / len(times), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f64 log-likelihoods over integer read-pair counts", "data": "synthetic",
-        "config": {"workload": WORKLOAD["name"] % WORKLOAD["loci_per_chr"], "sample": sample,
-                   "n_cells": WORKLOAD["n_cells"], "coverage": WORKLOAD["coverage"]},
+        "config": {"workload": workload_name(), "sample": sample,
+                   "n_cells": WORKLOAD["n_cells"], "coverage": WORKLOAD["coverage"], "num_threads": threads},
         "cpu_baseline": {"value": value, "unit": "loci/s", "cores": threads, "kind": kind, "sample": sample},
         "e2e": {"value": value, "unit": "loci/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -196,140 +254,205 @@ def int8_peak_tops(torch, device):
         return 2 * bf16, bf16, f"2 x {src_bf16} (torch._int_mm unavailable: {type(ex).__name__})"
 
 
-def main_ours(args):
-    import torch
-    import torch.distributed as dist
+class Rig:
+    """torch / distributed / library set-up shared by the bench modes"""
 
-    from secedo_b200 import api
+    def __init__(self):
+        import torch
+        import torch.distributed as dist
+        from secedo_b200 import api
+        self.torch, self.dist, self.api = torch, dist, api
+        self.world = int(os.environ.get("WORLD_SIZE", 1))
+        self.rank = int(os.environ.get("RANK", 0))
+        self.local_rank = int(os.environ.get("LOCAL_RANK", 0))
+        if not torch.cuda.is_available():
+            raise SystemExit("bench.py needs a CUDA device: secedo_b200 has no CPU fallback")
+        torch.cuda.set_device(self.local_rank)
+        self.device = torch.device("cuda", self.local_rank)
+        self.numa = bind_to_gpu_numa(torch, self.local_rank)
+        if self.world > 1:
+            os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+            dist.init_process_group("nccl", device_id=self.device)
+        self.ctx = api.Context(self.local_rank)
+        # one explicit stream for everything: the library's kernels, the collectives and the timing events
+        self.stream = torch.cuda.Stream(self.device)
+        torch.cuda.set_stream(self.stream)
+        self.ctx.set_stream(self.stream.cuda_stream)
+
+    def barrier(self):
+        if self.world > 1:
+            self.dist.barrier()
+
+    def max_over_ranks(self, x):
+        t = self.torch.tensor([x], device=self.device, dtype=self.torch.float64)
+        if self.world > 1:
+            self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def sum_over_ranks(self, x):
+        t = self.torch.tensor([x], device=self.device, dtype=self.torch.int64)
+        if self.world > 1:
+            self.dist.all_reduce(t)
+        return int(t.item())
+
+    def timed(self, fn, steps, warmup, finish=None):
+        """W untimed + K timed steps bracketed by barrier + synchronize on both sides; CUDA events on the stream all
+        work is ordered on; the MAX over ranks. finish() (e.g. waiting for the last matrix) runs inside the region."""
+        torch = self.torch
+        for _ in range(warmup):
+            fn()
+        if finish:
+            finish()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        stop, lines = threading.Event(), []
+        th = threading.Thread(target=clocks_sampler, args=(stop, lines, self.local_rank), daemon=True)
+        if self.rank == 0:
+            th.start()
+            time.sleep(0.25)  # let nvidia-smi come up BEFORE the barrier, so that all ranks start together
+        self.barrier()
+        torch.cuda.synchronize()
+        launches0 = self.ctx.launch_count()
+        acc = {}
+        e0.record(self.stream)
+        for _ in range(steps):
+            st = fn()
+            for k, v in st.items():
+                if isinstance(v, (int, float)):
+                    acc[k] = acc.get(k, 0) + v
+        if finish:
+            finish()
+        e1.record(self.stream)
+        self.barrier()
+        torch.cuda.synchronize()
+        ms = self.max_over_ranks(e0.elapsed_time(e1))
+        stop.set()
+        return ms, acc, self.ctx.launch_count() - launches0, summarize_clocks(lines)
+
+
+PHASES = ("ms_link", "ms_first_order", "ms_stage", "ms_gemm", "ms_multi", "gemm_launches")
+
+
+def main_ours(args):
     from secedo_b200 import dist as sdist
     from secedo_b200.pileup import Pileup
 
-    world = int(os.environ.get("WORLD_SIZE", 1))
-    rank = int(os.environ.get("RANK", 0))
-    local_rank = int(os.environ.get("LOCAL_RANK", 0))
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py needs a CUDA device: secedo_b200 has no CPU fallback")
-    torch.cuda.set_device(local_rank)
-    device = torch.device("cuda", local_rank)
-    if world > 1:
-        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        dist.init_process_group("nccl", device_id=device)
+    rig = Rig()
+    torch, dist, api, ctx = rig.torch, rig.dist, rig.api, rig.ctx
+    world, rank, device, stream = rig.world, rig.rank, rig.device, rig.stream
     w = WORKLOAD
-    N = w["n_cells"]
-    ctx = api.Context(local_rank)
-    # one explicit stream for everything: the library's kernels, the NCCL reduce and the timing events
-    stream = torch.cuda.Stream(device)
-    torch.cuda.set_stream(stream)
-    ctx.set_stream(stream.cuda_stream)
+    N, SUB = w["n_cells"], w["sub_batches"]
+    threads = reference_threads()  # the num_threads of BOTH arms (selects the reference's tail cutoff)
     ident = np.arange(N, dtype=np.uint32)
+    lik = (w["L"], w["eps"], w["h"], w["theta"])
 
-    raw_dev = ctx.synth_pileup(N, w["coverage"], w["n_chr"], w["loci_per_chr"], n_clones=w["n_clones"],
-                               frac_somatic=w["frac_somatic"], frac_germline=w["frac_germline"], theta=w["theta"],
-                               spacing=w["spacing"], p_multi=w["p_multi"], p_mate=w["p_mate"],
-                               p_mate_mismatch=w["p_mate_mismatch"], seed=1000 + rank)
-    n_chr, P, E = raw_dev.dims()
+    def synth(seed):
+        return ctx.synth_pileup(N, w["coverage"], w["n_chr"], w["loci_per_chr"], n_clones=w["n_clones"],
+                                frac_somatic=w["frac_somatic"], frac_germline=w["frac_germline"], theta=w["theta"],
+                                spacing=w["spacing"], p_multi=w["p_multi"], p_mate=w["p_mate"],
+                                p_mate_mismatch=w["p_mate_mismatch"], seed=seed)
+
+    raw_dev = [synth(1000 + 64 * rank + b) for b in range(SUB)]
+    dims = [r.dims() for r in raw_dev]
+    n_chr = dims[0][0]
+    P, E = sum(d[1] for d in dims), sum(d[2] for d in dims)
     flt = api.Filter(w["theta"], 4, ctx)
     counts = api.Counts(ctx, N)
-    lik = (w["L"], w["eps"], w["h"], w["theta"])
+    epi = sdist.SlabEpilogue(counts, device) if world > 1 else None
     last = {}
 
-    def step(src, out_host):
-        """one pass of the hot path; src is a DevicePileup (resident) or a host Pileup (e2e)"""
-        filtered, cov = flt.filter_device(src, ident)
-        counts.zero()
-        st = counts.accumulate(filtered, w["L"], ident, w["eps"], w["h"], w["theta"], w["num_threads"], args.path)
-        st["sig_loci"] = filtered.n_loci
-        filtered.free()
+    def accumulate_all(sources, st, free_sources=False, top_up=None):
+        for src in sources:
+            filtered, _ = flt.filter_device(src, ident)
+            if top_up:
+                top_up()
+            s1 = counts.accumulate(filtered, w["L"], ident, w["eps"], w["h"], w["theta"], threads, args.path)
+            st["sig_loci"] = st.get("sig_loci", 0) + filtered.n_loci
+            st["kept_entries"] = st.get("kept_entries", 0) + filtered.n_entries
+            for k in PHASES:
+                st[k] = st.get(k, 0) + (s1.get(k, 0) or 0)
+            st["path_used"] = s1.get("path_used")
+            filtered.free()
+            if free_sources:
+                src.free()
+
+    def epilogue(st, out_ptr=None, out_host=None, async_out=False):
+        """N x N matrix from the planes of all ranks. One GPU: the single-GPU epilogue. Several: the peer-memory epilogue
+        (every rank its share; into the shared host matrix at out_ptr, or left in the ranks' HBM)."""
         r0, r1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         r0.record(stream)
-        sdist.reduce_counts(counts, device, dst=0)
-        r1.record(stream)
         if world > 1:
-            r1.synchronize()
-            st["ms_reduce"] = r0.elapsed_time(r1)
-        if rank == 0:
+            epi.run(*lik, w["normalization"], out_ptr=out_ptr, same_stream=True)
+        elif async_out:
+            counts.finalize_async(*lik, w["normalization"], out_host)
+        else:
             counts.finalize(*lik, w["normalization"], out=out_host, to_host=out_host is not None)
+        r1.record(stream)
+        st["_ev"] = (r0, r1)
+
+    def step_resident():
+        st = {}
+        counts.zero()
+        accumulate_all(raw_dev, st)
+        epilogue(st)
+        r0, r1 = st.pop("_ev")
+        r1.synchronize()
+        st["ms_epilogue_total"] = r0.elapsed_time(r1)
         last.update(st)
         return st
 
-    def timed(fn, steps, warmup):
-        for _ in range(warmup):
-            fn()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        stop, lines = threading.Event(), []
-        th = threading.Thread(target=clocks_sampler, args=(stop, lines, local_rank), daemon=True)
-        if rank == 0:
-            th.start()
-            time.sleep(0.25)  # let nvidia-smi come up BEFORE the barrier, so that all ranks start together
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-        launches0 = ctx.launch_count()
-        acc = {"ms_gemm": 0.0, "ms_stage": 0.0, "gemm_launches": 0, "ms_link": 0.0, "ms_first_order": 0.0,
-               "ms_multi": 0.0, "ms_epilogue": 0.0, "ms_reduce": 0.0, "sig_loci": 0}
-        e0.record(stream)
-        for _ in range(steps):
-            st = fn()
-            for k in acc:
-                acc[k] += st.get(k, 0) or 0
-        e1.record(stream)
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-        ms = torch.tensor([e0.elapsed_time(e1)], device=device, dtype=torch.float64)
-        if world > 1:
-            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-        stop.set()
-        launches = ctx.launch_count() - launches0
-        return float(ms.item()), acc, launches, summarize_clocks(lines)
-
     # ---- device-resident input ------------------------------------------------------------------------
-    ms_dev, acc, launches, clocks = timed(lambda: step(raw_dev, None), args.steps, args.warmup)
+    ms_dev, acc, launches, clocks = rig.timed(step_resident, args.steps, args.warmup)
     sig_local = acc["sig_loci"] // args.steps
-    sig = torch.tensor([sig_local], device=device, dtype=torch.int64)
+    sig_total = rig.sum_over_ranks(sig_local)
+
+    # ---- verification of the multi-GPU result (untimed): the ranks' planes, summed through the peer mappings over the
+    # shares the epilogue uses, carry the checksum of the planes the ranks accumulated
+    reduce_checksum_ok = None
     if world > 1:
-        dist.all_reduce(sig)
-    sig_total = int(sig.item())
+        own_sum, peer_sum = epi.checksums()
+        reduce_checksum_ok = bool(own_sum == peer_sum)
 
     # ---- end to end: host (pinned) pileup in, host matrix out ------------------------------------------
-    # The reference-facing call sequence with HOST buffers: every step uploads its whole batch (one
-    # asynchronous upload per chromosome on the library's copy stream, so that the copy of the next
-    # chromosome overlaps the kernels of the current one, and the first copy of the next step overlaps the
-    # D2H of this step's matrix), filters and accumulates chromosome by chromosome into one counts object,
-    # reduces, and reads the N x N matrix back into host memory. All H2D / D2H bytes of all timed steps
-    # are inside the timed region.
-    host = raw_dev.download()
+    # The reference-facing call sequence with HOST buffers: every step uploads its whole pileup (one asynchronous upload
+    # per chromosome on the library's copy stream, running ahead of the kernels; the read ids stay in pinned host memory
+    # and the filter pulls those of the loci it keeps), filters and accumulates chromosome by chromosome into one counts
+    # object, and delivers the N x N matrix into host memory: one GPU -> D2H on a stream of its own while the next step
+    # starts; several GPUs -> every GPU writes its share of the matrix straight into a host matrix shared by the ranks.
+    # All H2D / D2H bytes of all timed steps are inside the timed region.
     pinned = []
     def pin(a):
         t = torch.from_numpy(np.ascontiguousarray(a)).pin_memory()
         pinned.append(t)
         return t.numpy()
-    pos_p, rid_p, gb_p = pin(host.position), pin(host.read_id), pin(host.gid_base)
-    chunks = []
-    for c in range(n_chr):
-        l0, l1 = int(host.chr_ptr[c]), int(host.chr_ptr[c + 1])
-        e0, e1 = int(host.row_ptr[l0]), int(host.row_ptr[l1])
-        hp = Pileup.__new__(Pileup)  # views of the pinned arrays, no copies
-        hp.chr_ptr = np.array([0, l1 - l0], np.uint64)
-        hp.row_ptr = pin(host.row_ptr[l0:l1 + 1] - np.uint64(e0))
-        hp.position, hp.read_id, hp.gid_base = pos_p[l0:l1], rid_p[e0:e1], gb_p[e0:e1]
-        chunks.append(hp)
-    out_t = torch.empty((N, N), dtype=torch.float64).pin_memory() if rank == 0 else None
-    out_host = out_t.numpy() if rank == 0 else None
-    # second result buffer: the matrix of step s travels to the host (own stream) while step s + 1 is computed
-    out_t2 = torch.empty((N, N), dtype=torch.float64).pin_memory() if rank == 0 else None
-    out_bufs = [out_host, out_t2.numpy()] if rank == 0 else [None, None]
-    e2e_steps = max(1, min(args.steps, 3))
+    chunks, h2d_fixed, h2d_full = [], 0, 0
+    for rd in raw_dev:
+        host = rd.download()
+        pos_p, rid_p, gb_p = pin(host.position), pin(host.read_id), pin(host.gid_base)
+        h2d_full += host.row_ptr.nbytes + host.position.nbytes + host.read_id.nbytes + host.gid_base.nbytes + host.chr_ptr.nbytes
+        h2d_fixed += host.row_ptr.nbytes + host.position.nbytes + host.gid_base.nbytes + host.chr_ptr.nbytes
+        for c in range(n_chr):
+            l0, l1 = int(host.chr_ptr[c]), int(host.chr_ptr[c + 1])
+            e0, e1 = int(host.row_ptr[l0]), int(host.row_ptr[l1])
+            hp = Pileup.__new__(Pileup)  # views of the pinned arrays, no copies
+            hp.chr_ptr = np.array([0, l1 - l0], np.uint64)
+            hp.row_ptr = pin(host.row_ptr[l0:l1 + 1] - np.uint64(e0))
+            hp.position, hp.read_id, hp.gid_base = pos_p[l0:l1], rid_p[e0:e1], gb_p[e0:e1]
+            chunks.append(hp)
+        del host
+    n_chunks = len(chunks)
+    shared = sdist.SharedHostMatrix(ctx, N) if world > 1 else None
+    out_bufs = [None, None]
+    if world == 1:
+        # second result buffer: the matrix of step s travels to the host (own stream) while step s + 1 is computed
+        out_bufs = [torch.empty((N, N), dtype=torch.float64).pin_memory().numpy() for _ in range(2)]
+    e2e_steps = max(1, min(args.steps, int(os.environ.get("SECEDO_BENCH_E2E_STEPS", 10))))
     E2E_WARMUP = 2
-    e2e_total = E2E_WARMUP + e2e_steps  # warm-up + timed
-    # uploads run up to LOOKAHEAD chromosomes ahead of the kernels, but never across the warm-up / timed
-    # boundary nor past the last step: every timed step's H2D bytes are copied inside the timed region
-    # (a whole step ahead: the DMA engine then works through accumulate and the D2H of the matrix, when the kernels
-    # leave the H2D direction of the bus idle, and the filter's zero-copy pull has the bus to itself)
+    # uploads run up to LOOKAHEAD chromosomes ahead of the kernels, but never across the warm-up / timed boundary nor past
+    # the last step: every timed step's H2D bytes are copied inside the timed region
     LOOKAHEAD = 4
-    runs = [[(s, c) for s in range(E2E_WARMUP) for c in range(n_chr)],
-            [(s, c) for s in range(E2E_WARMUP, e2e_total) for c in range(n_chr)]]
-    state = {"queue": [], "issued": 0, "run": []}
+    runs = [[(s, c) for s in range(E2E_WARMUP) for c in range(n_chunks)],
+            [(s, c) for s in range(e2e_steps) for c in range(n_chunks)]]
+    state = {"queue": [], "issued": 0, "run": [], "n_out": 0}
 
     def top_up(target):
         while len(state["queue"]) < target and state["issued"] < len(state["run"]):
@@ -342,72 +465,43 @@ def main_ours(args):
             state["run"], state["issued"] = runs.pop(0), 0
         counts.zero()
         st = {}
-        tr = state.setdefault("trace", {}) if os.environ.get("SECEDO_BENCH_E2E_TRACE") else None
-        t_prev = time.perf_counter()
-
-        def lap(name):
-            nonlocal t_prev
-            if tr is not None:
-                now = time.perf_counter()
-                tr[name] = tr.get(name, 0.0) + (now - t_prev) * 1e3
-                t_prev = now
-        for c in range(n_chr):
+        for _ in range(n_chunks):
             top_up(1)
             cur = state["queue"].pop(0)
-            lap("issue")
-            filtered, _ = flt.filter_device(cur, ident)
-            lap("filter")
             # DMA of the coming chromosomes is queued where the kernels leave the H2D direction of the bus idle
-            # (accumulate, and the D2H of the matrix below), not next to the filter's zero-copy pull
-            top_up(2)
-            lap("issue")
-            s1 = counts.accumulate(filtered, w["L"], ident, w["eps"], w["h"], w["theta"], w["num_threads"], args.path)
-            st["sig_loci"] = st.get("sig_loci", 0) + filtered.n_loci
-            state["pulled_entries"] = state.get("pulled_entries", 0) + filtered.n_entries
-            for k in ("ms_gemm", "ms_stage", "ms_link", "ms_first_order", "ms_multi", "gemm_launches"):
-                st[k] = st.get(k, 0) + (s1.get(k, 0) or 0)
-            lap("accumulate")
-            filtered.free()
-            cur.free()
-            lap("free")
-        sdist.reduce_counts(counts, device, dst=0)
+            # (accumulate, and the transfer of the matrix below), not next to the filter's zero-copy pull
+            accumulate_all([cur], st, free_sources=True, top_up=lambda: top_up(2))
+        state["n_out"] += 1
         top_up(LOOKAHEAD)
-        lap("issue")
-        if rank == 0:
-            # the previous step's matrix has to be complete before its buffer's turn comes again; every matrix of
-            # the timed steps is complete before the timed region ends (output_wait below, inside `timed`'s last step)
-            state["n_out"] = state.get("n_out", 0) + 1
-            counts.finalize_async(*lik, w["normalization"], out_bufs[state["n_out"] % 2])
-            if state["n_out"] in (E2E_WARMUP, e2e_total):  # last step of a run: nothing left to overlap with
-                ctx.output_wait()
-        lap("finalize")
-        if tr is not None:
-            sys.stderr.write("e2e trace (ms, cumulative): " + json.dumps({k: round(v, 2) for k, v in tr.items()}) + "\n")
+        epilogue(st, out_ptr=shared.dev_ptr if shared else None, out_host=out_bufs[state["n_out"] % 2], async_out=True)
+        st.pop("_ev")
+        state["pulled_entries"] = state.get("pulled_entries", 0) + st["kept_entries"]
         return st
 
-    ms_e2e, acc_e2e, _, _ = timed(e2e_step, e2e_steps, E2E_WARMUP)
+    def e2e_finish():
+        if world == 1:
+            ctx.output_wait()  # the last matrix is complete in host memory
+        else:
+            ctx.synchronize()  # this rank's share has been written (the barrier of `timed` covers the other ranks)
+
+    ms_e2e, acc_e2e, _, _ = rig.timed(e2e_step, e2e_steps, E2E_WARMUP, finish=e2e_finish)
     ctx.synchronize()
-    if rank == 0:
-        ctx.output_wait()
-        out_host = out_bufs[state["n_out"] % 2]
     # bytes that crossed PCIe host -> device per step: the CSR without the read ids, plus the read ids of the
     # entries of the loci the filter kept (all cells take part: every entry of a kept locus is pulled once)
-    pulled = state.get("pulled_entries", 0) // e2e_total
-    h2d_full = host.row_ptr.nbytes + host.position.nbytes + host.read_id.nbytes + host.gid_base.nbytes + host.chr_ptr.nbytes
-    h2d = host.row_ptr.nbytes + host.position.nbytes + host.gid_base.nbytes + host.chr_ptr.nbytes + 4 * pulled
-    d2h = N * N * 8
-    sig_e2e = torch.tensor([acc_e2e["sig_loci"] // e2e_steps], device=device, dtype=torch.int64)
-    if world > 1:
-        dist.all_reduce(sig_e2e)
-    assert int(sig_e2e.item()) == sig_total, "the chromosome-wise end-to-end path must see the same significant loci"
-
+    pulled = state.get("pulled_entries", 0) // (E2E_WARMUP + e2e_steps)
+    h2d = h2d_fixed + 4 * pulled
+    d2h = N * N * 8 // world
+    sig_e2e = rig.sum_over_ranks(acc_e2e["sig_loci"] // e2e_steps)
+    assert sig_e2e == sig_total, "the chromosome-wise end-to-end path must see the same significant loci"
     if rank == 0:
-        M = out_host
-        assert np.array_equal(M, M.T) and not np.diag(M).any(), "result must be symmetric with a zero diagonal"
+        M = shared.array if shared else out_bufs[state["n_out"] % 2]
+        assert np.array_equal(M, M.T) and not np.diag(M).any() and np.isfinite(M).all(), \
+            "result must be symmetric with a zero diagonal"
+        assert M.min() == 0.0 and M.max() > 0.0, "ADD_MIN: the smallest entry is exactly 0"
 
-    # ---- roofline of the dominant kernel (syrk_kernel, tensor bound) ---------------------------------------
+    # ---- roofline of the dominant kernel (syrk2_kernel, tensor bound) ---------------------------------------
     ms_gemm_step = acc["ms_gemm"] / args.steps
-    launches_gemm = max(1, acc["gemm_launches"] // args.steps)
+    launches_gemm = max(1, int(acc["gemm_launches"]) // args.steps)
     alg_ops_step = 5.0 * N * N * sig_local                      # 5 N^2 per significant locus
     n_pad = ((N + 255) // 256) * 256
     n_tiles = sum(1 for cb in range(n_pad // 256) for rb in range(n_pad // 128)
@@ -418,16 +512,19 @@ def main_ours(args):
     if rank == 0:
         int8_peak, bf16_peak, how = int8_peak_tops(torch, device)
         achieved = alg_ops_step / (ms_gemm_step * 1e-3) / 1e12 if ms_gemm_step > 0 else 0.0
-        # DRAM bytes of one launch from the committed ncu --set full capture of this exact workload
-        traffic, tensor_active = None, None
-        try:
-            tr = json.load(open(os.path.join(ROOT, "profiles", "r1_syrk_traffic.json")))
-            tw = tr["workload"]
-            if (tw["n_cells"], tw["n_chr"], tw["loci_per_chr"], tw["coverage"]) == (N, w["n_chr"], w["loci_per_chr"], w["coverage"]):
-                traffic = tr["dram_bytes_read"] + tr["dram_bytes_write"]
-                tensor_active = tr.get("tensor_pipe_active_pct")
-        except Exception:  # noqa: BLE001
-            pass
+        # DRAM bytes of one launch from the committed ncu capture of this exact per-launch workload
+        traffic, tensor_active, traffic_src = None, None, None
+        for name in ("r2_syrk_traffic.json", "r1_syrk_traffic.json"):
+            try:
+                tr = json.load(open(os.path.join(ROOT, "profiles", name)))
+                tw = tr["workload"]
+                if (tw["n_cells"], tw["n_chr"], tw["loci_per_chr"], tw["coverage"]) == (N, w["n_chr"], w["loci_per_chr"], w["coverage"]):
+                    traffic = tr["dram_bytes_read"] + tr["dram_bytes_write"]
+                    tensor_active = tr.get("tensor_pipe_active_pct")
+                    traffic_src = f"profiles/{name} (ncu, dram__bytes_read.sum + dram__bytes_write.sum of one launch)"
+                    break
+            except Exception:  # noqa: BLE001
+                pass
         NOMINAL_INT8 = 4500.0  # dense int8 TOP/s of a B200 (B200_PROFILING.md: 2 x the 2.25 PFLOP/s bf16 figure)
         roofline = {
             "bound": "tensor", "kernel": "syrk2_kernel (tcgen05.mma.cta_group::2.kind::i8)", "achieved": achieved, "peak": int8_peak,
@@ -436,6 +533,7 @@ def main_ours(args):
                   "issues 4*N_pad^2*(upper-triangle tiles) of them (Hadamard planes: 4 K-slices per 32 loci instead of 5)",
             "peak_source": how, "bf16_peak_measured": bf16_peak,
             "launches_per_step": launches_gemm, "avg_launch_ms": ms_gemm_step / launches_gemm,
+            "algorithmic_ops_per_launch": alg_ops_step / launches_gemm,
             "executed_ops_frac_of_algorithmic": executed_ops_step / alg_ops_step if alg_ops_step else None,
             "achieved_executed": achieved * executed_ops_step / alg_ops_step if alg_ops_step else None,
             "frac_executed": (achieved * executed_ops_step / alg_ops_step / int8_peak) if alg_ops_step and int8_peak else None,
@@ -446,78 +544,82 @@ def main_ours(args):
             "note": "frac > 1: `achieved` counts SURVEY's algorithmic ops, the Hadamard form issues 0.86 of them; and the "
                     "measured cuBLASLt int8 peak (like the bf16 one in MEASURED_PEAKS.json, 74 % of nominal) is a long "
                     "power-capped GEMM loop, while this kernel runs for a few ms between memory-bound kernels. In issued "
-                    "ops it reaches frac_executed_of_nominal of the 4.5 POP/s dense int8 rate, tensor pipe active as "
-                    "measured by ncu in tensor_pipe_active_pct_ncu",
-            "traffic_source": "profiles/r1_syrk_traffic.json (ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum)",
+                    "ops it reaches frac_executed_of_nominal of the 4.5 POP/s dense int8 rate",
+            "traffic_source": traffic_src,
         }
-        # ---- Laplacian + the 7 leading eigenpairs of this step's matrix, matrix resident in HBM --
-        spectral = None
-        try:
-            runs = []
-            for _ in range(3):
-                t0 = time.perf_counter()
-                ev, _, sst, _ = counts.finalize_spectral(*lik, w["normalization"], k=7, tol=1e-10)
-                sst["wall_ms"] = (time.perf_counter() - t0) * 1e3
-                runs.append(sst)
-            best = min(runs[1:], key=lambda r: r["wall_ms"])
-            hbm = 6650.0
+        # ---- Laplacian + the 7 leading eigenpairs of a matrix of this workload, resident in HBM ----
+        spectral, em = None, None
+        if not args.skip_extras:
             try:
-                hbm = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"])
-            except Exception:  # noqa: BLE001
-                pass
-            gbs = 8.0 * N * N * best["matvec_launches"] / (best["ms_matvec"] * 1e-3) / 1e9
-            spectral = {"what": "epilogue + laplacian() + the 7 smallest eigenpairs (spectral_clustering.cpp:33-52,127-138), "
-                                "similarity matrix never leaves HBM; residuals <= 1e-10", "k": 7,
-                        "ms": best["wall_ms"], "ms_solver": best["ms_solver"], "ms_laplacian": best["ms_laplacian"],
-                        "outer_iterations": best["outer_iterations"], "block": best["block"],
-                        "block_products": best["matvec_launches"], "max_residual": best["max_residual"],
-                        "eigenvalues": [float(x) for x in ev],
-                        "roofline": {"bound": "hbm", "kernel": "symm_block_kernel (fp64, M read once per product)",
-                                     "achieved": gbs, "peak": hbm, "unit": "GB/s", "frac": gbs / hbm,
-                                     "avg_launch_ms": best["ms_matvec"] / best["matvec_launches"],
-                                     "algorithmic_bytes_per_launch": 8.0 * N * N}}
-        except Exception as ex:  # noqa: BLE001
-            spectral = {"error": f"{type(ex).__name__}: {ex}"}
-        # ---- EM refinement on this rank's filtered batch (device resident) -------------------
-        em = None
-        try:
-            from oracle import pyoracle as po
-            filtered, _ = flt.filter_device(raw_dev, ident)
-            start = np.random.default_rng(1).uniform(0.3, 0.7, N)
-            EM_IT = 4
-            api.expectation_maximization(filtered, ident, 1, w["theta"], start, ctx=ctx, max_iterations=1)  # warm
-            _, est = api.expectation_maximization(filtered, ident, 1, w["theta"], start, ctx=ctx, max_iterations=EM_IT,
-                                                  return_stats=True)
-            n_ent = filtered.n_entries
-            filtered.free()
-            gpu_eps = n_ent * est["iterations"] / (est["ms"] * 1e-3)
-            em = {"what": "expectation_maximization (expectation_maximization.cpp:131-160) on the filtered batch in HBM, "
-                          f"{EM_IT} iterations incl. H2D/D2H of the probabilities", "entries": int(n_ent),
-                  "ms_per_iteration": est["ms"] / est["iterations"], "entries_per_s": gpu_eps,
-                  "algorithmic_bytes_per_entry": 4, "achieved_GBps": 4.0 * gpu_eps / 1e9,
-                  "bound": "L2 reductions (one RED.ADD.64 per entry) + two dependent gathers per entry"}
-            sp_cfg_loci = 256
-            from secedo_b200.synth import SynthConfig, make_pileup
-            scfg = SynthConfig(n_cells=N, coverage=w["coverage"], n_loci=sp_cfg_loci, n_chr=1, n_clones=w["n_clones"],
-                               frac_somatic=0.5, frac_germline=0.0, theta=w["theta"], spacing=w["spacing"], seed=5)
-            sp = make_pileup(scfg)
-            if po.have_ref():
-                _, it_ref = po.expectation_maximization(sp, ident, w["theta"], start)
-                _, secs = po.ref_expectation_maximization(sp, ident, w["theta"], start)
-                em["cpu_reference"] = {"entries": int(sp.n_entries), "iterations": it_ref, "seconds": secs, "cores": 1,
-                                       "entries_per_s": sp.n_entries * it_ref / secs,
-                                       "note": "the reference's EM is serial (its omp pragma is commented out, "
-                                               "expectation_maximization.cpp:140)"}
-        except Exception as ex:  # noqa: BLE001
-            em = {"error": f"{type(ex).__name__}: {ex}"}
-        # ---- CPU baseline: the unmodified reference on a bounded sample ---------------------------------
-        threads = reference_threads()
+                one = api.Counts(ctx, N)
+                f1, _ = flt.filter_device(raw_dev[0], ident)
+                one.accumulate(f1, w["L"], ident, w["eps"], w["h"], w["theta"], threads, args.path)
+                runs_ = []
+                for _ in range(3):
+                    t0 = time.perf_counter()
+                    ev, _, sst, _ = one.finalize_spectral(*lik, w["normalization"], k=7, tol=1e-10)
+                    sst["wall_ms"] = (time.perf_counter() - t0) * 1e3
+                    runs_.append(sst)
+                one.free()
+                best = min(runs_[1:], key=lambda r: r["wall_ms"])
+                hbm = 6650.0
+                try:
+                    hbm = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"])
+                except Exception:  # noqa: BLE001
+                    pass
+                gbs = 8.0 * N * N * best["matvec_launches"] / (best["ms_matvec"] * 1e-3) / 1e9
+                spectral = {"what": "epilogue + laplacian() + the 7 smallest eigenpairs (spectral_clustering.cpp:33-52,127-138), "
+                                    "similarity matrix never leaves HBM; residuals <= 1e-10", "k": 7,
+                            "ms": best["wall_ms"], "ms_solver": best["ms_solver"], "ms_laplacian": best["ms_laplacian"],
+                            "outer_iterations": best["outer_iterations"], "block": best["block"],
+                            "block_products": best["matvec_launches"], "max_residual": best["max_residual"],
+                            "eigenvalues": [float(x) for x in ev],
+                            "roofline": {"bound": "hbm", "kernel": "symm_block_kernel (fp64, M read once per product)",
+                                         "achieved": gbs, "peak": hbm, "unit": "GB/s", "frac": gbs / hbm,
+                                         "avg_launch_ms": best["ms_matvec"] / best["matvec_launches"],
+                                         "algorithmic_bytes_per_launch": 8.0 * N * N}}
+                # ---- EM refinement on a filtered sub-batch (device resident) -------------------
+                start = np.random.default_rng(1).uniform(0.3, 0.7, N)
+                EM_IT = 4
+                api.expectation_maximization(f1, ident, 1, w["theta"], start, ctx=ctx, max_iterations=1)  # warm
+                _, est = api.expectation_maximization(f1, ident, 1, w["theta"], start, ctx=ctx, max_iterations=EM_IT,
+                                                      return_stats=True)
+                n_ent = f1.n_entries
+                f1.free()
+                gpu_eps = n_ent * est["iterations"] / (est["ms"] * 1e-3)
+                em = {"what": "expectation_maximization (expectation_maximization.cpp:131-160) on a filtered sub-batch in HBM, "
+                              f"{EM_IT} iterations incl. H2D/D2H of the probabilities", "entries": int(n_ent),
+                      "ms_per_iteration": est["ms"] / est["iterations"], "entries_per_s": gpu_eps,
+                      "algorithmic_bytes_per_entry": 4, "achieved_GBps": 4.0 * gpu_eps / 1e9,
+                      "bound": "L2 reductions (one RED.ADD.64 per entry) + two dependent gathers per entry"}
+            except Exception as ex:  # noqa: BLE001
+                spectral = spectral or {"error": f"{type(ex).__name__}: {ex}"}
+                em = em or {"error": f"{type(ex).__name__}: {ex}"}
+        # ---- CPU baseline: the unmodified reference on a bounded sample, all cores and one core; and the GPU path on
+        # the SAME sample at the SAME num_threads, compared with the matrix of that very reference run ---------------
+        if ALL_CPUS:
+            os.sched_setaffinity(0, ALL_CPUS)  # the reference gets every core this process was given
         sample_p = cpu_sample()
-        secs, cpu_loci, kind = run_reference_step(sample_p, threads)
+        secs, cpu_loci, kind, M_ref = run_reference_step(sample_p, threads, want_matrix=True)
         cpu_value = cpu_loci / secs
-        cpu = {"value": cpu_value, "unit": "loci/s", "cores": threads, "kind": kind,
-               "sample": f"{CPU_SAMPLE_LOCI} pre-filter loci ({cpu_loci} significant, {sample_p.n_entries} entries) of the "
-                         f"same workload, Filter::filter + computeSimilarityMatrix, {secs:.1f} s"}
+        what = f"{CPU_SAMPLE_LOCI} pre-filter loci ({cpu_loci} significant, {sample_p.n_entries} entries) of the same workload, " \
+               f"Filter::filter + computeSimilarityMatrix"
+        cpu = {"value": cpu_value, "unit": "loci/s", "cores": threads, "kind": kind, "sample": f"{what}, {secs:.1f} s"}
+        secs1, _, _ = run_reference_step(sample_p, 1)
+        cpu["single_thread"] = {"value": cpu_loci / secs1, "unit": "loci/s", "cores": 1, "seconds": secs1,
+                                "note": "num_threads = 1 (SURVEY 8d: the reference often slows down with threads); its tail "
+                                        "cutoff differs from the all-cores run, the significant loci are the same"}
+        f_s, _ = flt.filter(sample_p, ident, "", threads)
+        M_gpu = api.compute_similarity_matrix(f_s, N, w["L"], ident, w["eps"], w["h"], w["theta"], threads, "",
+                                              w["normalization"], ctx=ctx, path=args.path)
+        scale = float(np.abs(M_ref).max())
+        diff = float(np.abs(M_gpu - M_ref).max())
+        parity = {"ok": bool(f_s.n_loci == cpu_loci and diff <= 1e-6 * max(scale, 1e-300)), "max_abs_diff": diff,
+                  "max_abs_reference": scale, "tolerance": "1e-6 * max|M_reference|", "num_threads": threads,
+                  "significant_loci": int(f_s.n_loci), "reference_kind": kind,
+                  "what": "Filter::filter + computeSimilarityMatrix through the C ABI on the CPU baseline's sample (8 000 "
+                          "cells), against the matrix of that reference run"}
+        assert parity["ok"], f"GPU path differs from the reference on the baseline sample: {parity}"
         value = sig_total * args.steps / (ms_dev * 1e-3)
         e2e_value = sig_total * e2e_steps / (ms_e2e * 1e-3)
         line = {
@@ -526,34 +628,131 @@ def main_ours(args):
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "int8 tensor-core counts (int32 accumulate) + f64 log-likelihood epilogue", "data": "synthetic",
             "config": {
-                "workload": w["name"] % w["loci_per_chr"], "n_cells": N, "coverage": w["coverage"],
+                "workload": workload_name(), "n_cells": N, "coverage": w["coverage"],
                 "prefilter_loci_per_gpu_step": P, "significant_loci_per_step_all_gpus": sig_total,
-                "pileup_entries_per_gpu_step": E, "p_multi": w["p_multi"], "p_mate": w["p_mate"],
+                "pileup_entries_per_gpu_step": E, "sub_batches_per_step": SUB, "p_multi": w["p_multi"], "p_mate": w["p_mate"],
                 "theta": w["theta"], "eps": w["eps"], "h": w["h"], "max_fragment_length": w["L"],
-                "num_threads_for_cutoff": w["num_threads"], "normalization": w["normalization"],
-                "path": last.get("path_used"), "parallelism": f"loci sharded by chromosome over {world} GPU(s), "
-                "one NCCL reduce of the int32 count planes in use",
-                "l2": "inputs larger than L2 (pileup batch %.1f GB, Hadamard panel %.1f GB per step)" % (
-                    h2d_full / 1e9, 4.0 * N * sig_local / 1e9),
+                "num_threads_for_cutoff": threads, "normalization": w["normalization"],
+                "path": last.get("path_used"),
+                "parallelism": f"loci sharded by chromosome over {world} GPU(s); per step every GPU accumulates its "
+                               f"{SUB} sub-batches into its own int32 count planes" + (
+                    ", then the peer-memory epilogue: each GPU sums the planes of all GPUs over 1/%d of the matrix through "
+                    "NVLink (CUDA IPC mappings) and transforms them in the same kernel; one all-reduce of two doubles" % world
+                    if world > 1 else ", single-GPU epilogue"),
+                "result": ("each rank's share of the N x N matrix in its own HBM (value) / one N x N matrix in host memory "
+                           "shared by the ranks (e2e)" if world > 1 else "N x N matrix in HBM (value) / in host memory (e2e)"),
+                "l2": "inputs larger than L2 (pileup %.1f GB, Hadamard panel %.1f GB per sub-batch)" % (
+                    h2d_full / 1e9, 4.0 * N * sig_local / SUB / 1e9),
+                "host_topology": rig.numa,
             },
             "build_time_s_per_step": ms_dev / args.steps * 1e-3,
             "prefilter_loci_per_s": P * world * args.steps / (ms_dev * 1e-3),
-            "phase_ms_per_step_rank0": {k: acc[k] / args.steps for k in ("ms_link", "ms_first_order", "ms_stage", "ms_gemm",
-                                                                         "ms_multi", "ms_epilogue", "ms_reduce")},
-            "roofline": roofline, "cpu_baseline": cpu,
+            "phase_ms_per_step_rank0": dict({k: acc[k] / args.steps for k in ("ms_link", "ms_first_order", "ms_stage", "ms_gemm",
+                                                                               "ms_multi")},
+                                            ms_epilogue=acc["ms_epilogue_total"] / args.steps),
+            "roofline": roofline, "cpu_baseline": cpu, "parity_vs_reference": parity,
+            "reduce_checksum_ok": reduce_checksum_ok,
             "e2e": {"value": e2e_value, "unit": "loci/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                     "ms_per_step": ms_e2e / e2e_steps, "steps": e2e_steps,
                     "host_pileup_bytes_per_step": int(h2d_full),
-                    "how": "host pinned pileup -> sgpu_pileup_upload_lazy_async per chromosome (copy stream, overlapping the "
-                           "kernels of the previous chromosome; the read ids stay in pinned host memory) -> filter (pulls the "
-                           "read ids of the loci it keeps straight over PCIe: h2d_bytes_per_step counts what crossed the "
-                           "bus, host_pileup_bytes_per_step the whole input) -> accumulate -> reduce -> finalize -> N x N "
-                           "fp64 matrix in host memory, every step"},
+                    "how": "host pinned pileup -> sgpu_pileup_upload_lazy_async per chromosome (copy stream, running ahead of "
+                           "the kernels; the read ids stay in pinned host memory) -> filter (pulls the read ids of the loci it "
+                           "keeps straight over PCIe: h2d_bytes_per_step counts what crossed the bus, "
+                           "host_pileup_bytes_per_step the whole input) -> accumulate -> epilogue -> N x N fp64 matrix in host "
+                           "memory, every step (per rank: d2h_bytes_per_step = its share)"},
             "gpu_launches": int(launches), "clocks": clocks, "spectral": spectral, "em": em,
         }
         print(json.dumps(line))
+    rig.barrier()
+    if shared:
+        shared.close()
+    if epi:
+        epi.close()
     if world > 1:
-        dist.barrier()
+        dist.destroy_process_group()
+    return 0
+
+
+# --------------------------------------------------------------------------------------- whole genome, strong scaling
+def main_genome(args):
+    """BASELINE.json configs[2] as ONE job: 23 chromosomes with the human length ratios (pileup.cpp:30-34), 8 000 cells at
+    0.5x, sharded over the GPUs, accumulated into one set of count planes per GPU, ONE epilogue at the end. Strong
+    scaling: the same genome at every N; `value` = significant loci of the whole genome / seconds for the whole matrix.
+    SECEDO_BENCH_GENOME_LOCI sets the pre-filter loci of the genome (default: chromosome 1 = 131 072 loci, the whole
+    genome 1.63 M pre-filter loci = 40 GB of pileup, resident in HBM at every N)."""
+    from secedo_b200 import dist as sdist
+    rig = Rig()
+    torch, dist, api, ctx = rig.torch, rig.dist, rig.api, rig.ctx
+    world, rank, device, stream = rig.world, rig.rank, rig.device, rig.stream
+    w = WORKLOAD
+    N = w["n_cells"]
+    threads = reference_threads()
+    ident = np.arange(N, dtype=np.uint32)
+    lik = (w["L"], w["eps"], w["h"], w["theta"])
+    total_len = float(sum(CHROMOSOME_LENGTHS))
+    G = int(os.environ.get("SECEDO_BENCH_GENOME_LOCI", round(131072 * total_len / CHROMOSOME_LENGTHS[0])))
+    sizes = [max(1024, int(round(G * x / total_len))) for x in CHROMOSOME_LENGTHS]
+    MAX_CALL = 131072  # pre-filter loci per accumulate call (one operand panel of the GEMM)
+    if max(sizes) > MAX_CALL:
+        raise SystemExit(f"chromosome 1 would hold {max(sizes)} pre-filter loci: more than one accumulate call ({MAX_CALL}); "
+                         "lower SECEDO_BENCH_GENOME_LOCI")
+    parts = sdist.partition_chromosomes(sizes, world)  # longest-processing-time assignment, same on every rank
+    mine = parts[rank]
+    raw = [ctx.synth_pileup(N, w["coverage"], 1, sizes[c], n_clones=w["n_clones"], frac_somatic=w["frac_somatic"],
+                            frac_germline=w["frac_germline"], theta=w["theta"], spacing=w["spacing"], p_multi=w["p_multi"],
+                            p_mate=w["p_mate"], p_mate_mismatch=w["p_mate_mismatch"], seed=5000 + c) for c in mine]
+    flt = api.Filter(w["theta"], 4, ctx)
+    counts = api.Counts(ctx, N)
+    epi = sdist.SlabEpilogue(counts, device) if world > 1 else None
+
+    def genome():
+        st = {"sig_loci": 0, "ms_gemm": 0.0, "gemm_launches": 0}
+        counts.zero()
+        for src in raw:
+            filtered, _ = flt.filter_device(src, ident)
+            s1 = counts.accumulate(filtered, w["L"], ident, w["eps"], w["h"], w["theta"], threads, args.path)
+            st["sig_loci"] += filtered.n_loci
+            st["ms_gemm"] += s1["ms_gemm"]
+            st["gemm_launches"] += s1["gemm_launches"]
+            filtered.free()
+        if world > 1:
+            epi.run(*lik, w["normalization"], same_stream=True)
+        else:
+            counts.finalize(*lik, w["normalization"], to_host=False)
+        return st
+
+    steps, warmup = max(1, min(args.steps, 5)), max(1, min(args.warmup, 2))
+    ms, acc, launches, clocks = rig.timed(genome, steps, warmup)
+    sig_local = acc["sig_loci"] // steps
+    sig_total = rig.sum_over_ranks(sig_local)
+    load = rig.max_over_ranks(float(sum(sizes[c] for c in mine))) / (sum(sizes) / world)
+    ok = None
+    if world > 1:
+        a, b = epi.checksums()
+        ok = bool(a == b)
+    if rank == 0:
+        secs = ms / steps * 1e-3
+        line = {
+            "metric": "similarity-matrix significant loci/s (8K cells, 0.5x, whole genome)", "value": sig_total / secs,
+            "unit": "loci/s", "n_gpus": world, "steps": steps, "warmup": warmup, "ms_per_step": ms / steps,
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "int8 tensor-core counts (int32 accumulate) + f64 log-likelihood epilogue", "data": "synthetic",
+            "whole_genome_matrix_seconds": secs,
+            "config": {"workload": f"cfg3-genome: 8000 cells x 0.5x, 23 chromosomes with the human length ratios, {sum(sizes)} "
+                                   f"pre-filter loci ({sig_total} significant), resident in HBM; one step = the whole matrix",
+                       "n_cells": N, "coverage": w["coverage"], "chromosome_loci": sizes, "assignment": parts,
+                       "largest_share_over_mean": load, "num_threads_for_cutoff": threads, "p_multi": w["p_multi"],
+                       "parallelism": f"whole chromosomes over {world} GPU(s) (longest-processing-time assignment), one "
+                                      "epilogue over peer memory at the end",
+                       "host_topology": rig.numa},
+            "gemm_ms_per_genome_rank0": acc["ms_gemm"] / steps, "reduce_checksum_ok": ok,
+            "gpu_launches": int(launches), "clocks": clocks,
+        }
+        print(json.dumps(line))
+    rig.barrier()
+    if epi:
+        epi.close()
+    if world > 1:
         dist.destroy_process_group()
     return 0
 
@@ -565,5 +764,11 @@ if __name__ == "__main__":
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--path", default="auto", choices=["auto", "scatter", "gemm"])
+    ap.add_argument("--workload", default="cfg3", choices=["cfg3", "cfg3-genome"])
+    ap.add_argument("--skip-extras", action="store_true", help="skip the spectral / EM side measurements")
     a = ap.parse_args()
-    sys.exit(main_reference(a) if a.impl == "reference" else main_ours(a))
+    if a.impl == "reference":
+        sys.exit(main_reference(a))
+    if a.workload == "cfg3-genome":
+        sys.exit(main_genome(a))
+    sys.exit(main_ours(a))

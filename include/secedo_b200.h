@@ -31,6 +31,8 @@ extern "C" {
 
 #define SGPU_NO_POS 16383u   /* util/is_significant.hpp:11 */
 #define SGPU_MAX_CLASS 64    /* overlap classes x_s, x_d < 64 are supported */
+#define SGPU_MAX_PEERS 16    /* GPUs whose count planes one epilogue kernel can sum (sgpu_slab_raw) */
+#define SGPU_IPC_HANDLE_BYTES 64
 
 enum {
     SGPU_OK = 0,
@@ -38,7 +40,8 @@ enum {
     SGPU_E_ARG = -2,           /* invalid argument (e.g. unknown normalization: the reference throws
                                   std::logic_error, similarity_matrix.cpp:264) */
     SGPU_E_CELL_RANGE = -3,    /* group id >= n_groups or mapped cell >= num_cells (mat.hpp:119 assert) */
-    SGPU_E_FRAGMENT_SPAN = -4, /* a read id spans >= max_fragment_length: undefined in the reference */
+    SGPU_E_FRAGMENT_SPAN = -4, /* a read id chained over >= max_fragment_length, only with SECEDO_B200_STRICT_SPAN=1 (by
+                                  default such a chain is split into reads the way the reference's retirement does) */
     SGPU_E_CLASS_RANGE = -5,   /* a read pair overlaps at >= SGPU_MAX_CLASS (or >= L) loci */
     SGPU_E_POSITIONS = -6,     /* loci not strictly increasing inside a chromosome */
     SGPU_E_COUNT_RANGE = -7,   /* internal int8/int32 range exceeded */
@@ -69,7 +72,9 @@ typedef struct sgpu_stats {
     uint64_t n_pairs_first;     /* cross-cell (read pair, shared locus) incidences counted */
     uint64_t n_pairs_multi;     /* read pairs overlapping at >= 2 loci */
     int32_t path_used;          /* SGPU_PATH_SCATTER or SGPU_PATH_GEMM */
-    int32_t reserved;
+    int32_t n_span_splits;      /* reads opened because a read id was chained over >= max_fragment_length (the reference
+                                   retires a read once start + L <= position and starts a new one at the next entry with its
+                                   id, similarity_matrix.cpp:348-372,379-382; 0 on ordinary pileups) */
     float ms_link;              /* device time: read linking + mate rule + cutoff K */
     float ms_first_order;       /* device time: scatter or staging + GEMM */
     float ms_multi;             /* device time: multi-locus correction */
@@ -129,6 +134,21 @@ int sgpu_pileup_from_bin(sgpu_ctx *ctx, uint32_t n_chr, const void *const *file_
                          const uint16_t *id_to_group, uint32_t n_ids, uint32_t max_coverage,
                          const uint32_t *const *positions, const uint64_t *n_positions, sgpu_pileup **out,
                          uint32_t *n_cells, uint32_t *n_groups);
+/* Wide pileups: group ids beyond the reference's 14 bits (sequenced_data.hpp:29-36 packs the id into 14 bits of a
+ * uint16; 20 000 cells, BASELINE config 5, do not fit). gid_base32[e] = group id << 2 | base with 30-bit ids; in
+ * id_to_pos / group_id_to_pos "not in the cluster" is 0xFFFFFFFF instead of SGPU_NO_POS. sgpu_filter,
+ * sgpu_counts_accumulate(_range), sgpu_chromosome_cutoff, sgpu_similarity and the epilogues accept them (the kernels
+ * that read the entries are templates over the entry width); the .bin ingestion, lazy uploads and
+ * sgpu_expectation_maximization stay 14-bit like the reference's file format and return SGPU_E_ARG. The GEMM path
+ * takes up to 26 360 cells (the scatter path has no such limit). sgpu_synth_pileup produces a wide pileup when
+ * n_cells > 16 383. */
+#define SGPU_NO_POS_WIDE 0xFFFFFFFFu
+int sgpu_pileup_upload_wide(sgpu_ctx *ctx, uint32_t n_chr, const uint64_t *chr_ptr, const uint64_t *row_ptr,
+                            const uint32_t *position, const uint32_t *read_id, const uint32_t *gid_base32,
+                            sgpu_pileup **out);
+int sgpu_pileup_download_wide(sgpu_ctx *ctx, const sgpu_pileup *p, uint64_t *chr_ptr, uint64_t *row_ptr,
+                              uint32_t *position, uint32_t *read_id, uint32_t *gid_base32);
+int sgpu_pileup_is_wide(const sgpu_pileup *p);
 /* Adopt arrays that already live on this context's device (not copied, not freed). */
 int sgpu_pileup_wrap_device(sgpu_ctx *ctx, uint32_t n_chr, const uint64_t *host_chr_ptr,
                             const uint64_t *dev_row_ptr, const uint32_t *dev_position,
@@ -168,6 +188,30 @@ int sgpu_counts_accumulate(sgpu_ctx *ctx, sgpu_counts *c, const sgpu_pileup *fil
                            uint32_t max_fragment_length, const uint32_t *group_id_to_pos,
                            uint32_t n_groups, double mutation_rate, double homozygous_rate,
                            double seq_error_rate, uint32_t num_threads, int path, sgpu_stats *stats);
+/* ---- pieces of chromosomes: locus ranges with a halo -----------------------------------------------
+ * A chromosome may be accumulated in pieces — by different GPUs, or one after the other on the same GPU. A piece is a
+ * filtered pileup that holds, for each of its chromosomes, the loci it OWNS (positions in [own_pos_begin[c],
+ * own_pos_end[c])) and a read-only halo: every filtered locus of that chromosome less than max_fragment_length bp
+ * before the first owned position and less than max_fragment_length bp after the last one (more does no harm). The
+ * owned ranges of the pieces must tile the chromosome. Each piece then adds exactly its share: first-order counts of
+ * its owned loci, and the read pairs that overlap at >= 2 loci whose FIRST common locus it owns; the halo only serves
+ * to see the reads of the owned loci completely (cell of the first entry, mate rule, all loci). The sums over the
+ * pieces equal the counts of the whole chromosome bit for bit.
+ * The reference's tail cutoff K is a property of the whole chromosome; it is decided from the chromosome's
+ * END by sgpu_chromosome_cutoff and handed to every piece as tail_position[c]: reads created at positions >=
+ * tail_position[c] are never the first read of a pair (0xFFFFFFFF: none).
+ *
+ * sgpu_chromosome_cutoff: `ends` holds, per chromosome, either the whole filtered chromosome (whole[c] != 0) or its
+ * last loci (a suffix). resolved[c] = 1: tail_position[c] is the cutoff of the whole chromosome; 0: the suffix was
+ * too short to decide (no batch trigger that fires whatever happened before it lies inside its exact part, i.e. more
+ * than max_fragment_length bp behind its first locus): call again with a longer suffix. On dense pileups (>= 4 *
+ * num_threads new reads per locus) a suffix of a few max_fragment_length always suffices. */
+int sgpu_chromosome_cutoff(sgpu_ctx *ctx, const sgpu_pileup *ends, uint32_t max_fragment_length, uint32_t num_threads,
+                           const uint8_t *whole, uint32_t *tail_position, uint8_t *resolved);
+int sgpu_counts_accumulate_range(sgpu_ctx *ctx, sgpu_counts *c, const sgpu_pileup *piece, uint32_t max_fragment_length,
+                                 const uint32_t *group_id_to_pos, uint32_t n_groups, double mutation_rate,
+                                 double homozygous_rate, double seq_error_rate, const uint32_t *own_pos_begin,
+                                 const uint32_t *own_pos_end, const uint32_t *tail_position, int path, sgpu_stats *stats);
 /* Device buffers to be summed element-wise across ranks before finalize:
  *   i32     int32 [n_i32]  planes of num_cells^2: S, D (first order), then, when read pairs that
  *                          overlap at >= 2 loci occurred, the class planes (2,0) (1,1) (0,2)
@@ -213,6 +257,46 @@ int sgpu_similarity_finalize_async(sgpu_ctx *ctx, sgpu_counts *c, uint32_t max_f
                                    double mutation_rate, double homozygous_rate, double seq_error_rate,
                                    int normalization, double *out);
 int sgpu_output_wait(sgpu_ctx *ctx);
+/* ---- multi-GPU epilogue over peer memory: reduce-scatter + transform in one kernel --------------------------------
+ * The count planes of the GPUs are NOT summed into one of them. The 32 x 32 tiles of the upper triangle are dealt out
+ * in n_slabs equal contiguous shares; the GPU that owns share `slab` reads, for its tiles, the planes of ALL GPUs
+ * (peer_planes[0 .. n_peers): device pointers valid on this GPU — its own planes, peers of the same process after
+ * cudaDeviceEnablePeerAccess, or other processes' planes mapped with sgpu_ipc_open), adds the integers and applies
+ * the log-likelihood transform in the same kernel (sgpu_slab_raw). The order of the peers does not matter (integer
+ * sums) and the floating-point expression is the single-GPU epilogue's, so the values are bit-identical to a
+ * reduction onto one GPU followed by sgpu_similarity_finalize. extrema receives a device pointer to two doubles
+ * {-min, max} of this share's raw values: the caller takes the element-wise MAX over the GPUs in place (one tiny
+ * all-reduce, which is also the barrier after which no GPU reads another's planes any more), then sgpu_slab_finalize
+ * normalises this share and writes its tiles and their mirror images into `out`: an n x n row-major matrix in device
+ * memory or in mapped page-locked host memory (sgpu_host_register; every GPU then writes its share of the matrix over
+ * its own PCIe link), or, with out = NULL, into an n x n device matrix owned by the counts object of which only this
+ * share is written (returned in *device_out). All ranks must have agreed on the layout (sgpu_counts_set_layout) and
+ * finished accumulating before any of them calls sgpu_slab_raw. peer_spill: the fp64 spill planes of the GPUs (read
+ * pairs that overlap at >= 4 loci; sgpu_counts_set_layout with want_spill on every rank once one of them has one), or
+ * NULL when no GPU holds one; they are added in the order of the array (fp64: agrees with one GPU to rounding). */
+int sgpu_slab_raw(sgpu_ctx *ctx, sgpu_counts *c, const int32_t *const *peer_planes, const double *const *peer_spill,
+                  uint32_t n_peers, uint32_t slab, uint32_t n_slabs, uint32_t max_fragment_length, double mutation_rate,
+                  double homozygous_rate, double seq_error_rate, double **extrema);
+int sgpu_slab_finalize(sgpu_ctx *ctx, sgpu_counts *c, int normalization, double *out, double **device_out);
+/* first and one-past-last tile of the share of the last sgpu_slab_raw call (tiles numbered row by row over bj >= bi) */
+int sgpu_slab_range(const sgpu_counts *c, uint64_t *tile0, uint64_t *tile1);
+/* CUDA IPC: handle (SGPU_IPC_HANDLE_BYTES bytes) of this counts object's int32 planes for another PROCESS on the same
+ * node; sgpu_ipc_open maps such a handle (the returned pointer is valid on ctx's device, peer access over NVLink is
+ * enabled by the driver), sgpu_ipc_close unmaps it. */
+int sgpu_counts_ipc_handle(sgpu_ctx *ctx, sgpu_counts *c, int which /* 0: int32 planes, 1: fp64 spill plane */, void *handle);
+int sgpu_ipc_open(sgpu_ctx *ctx, const void *handle, void **device_ptr);
+int sgpu_ipc_close(sgpu_ctx *ctx, void *device_ptr);
+/* Page-lock and map existing host memory (e.g. a shared-memory segment that several processes write their shares of
+ * the matrix into); *device_alias is the pointer kernels of ctx's device use. */
+int sgpu_host_register(sgpu_ctx *ctx, void *host, uint64_t bytes, void **device_alias);
+int sgpu_host_unregister(sgpu_ctx *ctx, void *host);
+/* order-independent 64-bit checksum of the upper triangles (i < j) of the int32 planes in use: sum over elements of
+ * value * weight(position), wrapping; linear, so the checksums of the ranks add up to the checksum of the summed planes.
+ * n_peers > 1: checksum of the element-wise sum of the peers' planes restricted to tiles [tile0, tile1) of share
+ * `slab`; the shares of all GPUs add up to the checksum of the whole sum. */
+int sgpu_counts_checksum(sgpu_ctx *ctx, sgpu_counts *c, const int32_t *const *peer_planes, uint32_t n_peers, uint32_t slab,
+                         uint32_t n_slabs, uint64_t *checksum);
+
 /* LS / LD tables as evaluated on the device, n*n row-major (parity with similarity_matrix.cpp:117-170). */
 int sgpu_log_probs(sgpu_ctx *ctx, double mutation_rate, double homozygous_rate, double seq_error_rate,
                    uint32_t max_fragment_length, uint32_t n, double *ls, double *ld);

@@ -66,6 +66,8 @@ def oracle_lib():
         _oracle = C.CDLL(ORACLE_SO)
         _oracle.orc_similarity.restype = C.c_int
         _oracle.orc_filter.restype = C.c_int
+        _oracle.orc_similarity_wide.restype = C.c_int
+        _oracle.orc_filter_wide.restype = C.c_int
         _oracle.orc_log_probs.restype = C.c_int
         _oracle.orc_normalize.restype = C.c_int
         _oracle.orc_laplacian.restype = C.c_int
@@ -112,8 +114,10 @@ def filter_flags(p, id_to_pos, theta: float, cell_proportion: int = 4):
     kl, ke = np.zeros(p.n_loci, np.uint8), np.zeros(p.n_entries, np.uint8)
     nl, ne = C.c_uint64(), C.c_uint64()
     cov, cov64 = C.c_double(), C.c_double()
-    rc = oracle_lib().orc_filter(C.c_uint32(p.n_chr), _p(p.chr_ptr, _u64p), _p(p.row_ptr, _u64p),
-                                 _p(p.read_id, _u32p), _p(p.gid_base, _u16p), _p(id_to_pos, _u32p),
+    wide = p.gid_base.dtype == np.uint32  # group ids beyond the reference's 14 bits: NO_POS is 0xFFFFFFFF there
+    fn = oracle_lib().orc_filter_wide if wide else oracle_lib().orc_filter
+    rc = fn(C.c_uint32(p.n_chr), _p(p.chr_ptr, _u64p), _p(p.row_ptr, _u64p),
+                                 _p(p.read_id, _u32p), _p(p.gid_base, _u32p if wide else _u16p), _p(id_to_pos, _u32p),
                                  C.c_uint32(id_to_pos.size), C.c_double(theta), C.c_int(cell_proportion),
                                  _p(kl, _u8p), _p(ke, _u8p), C.byref(nl), C.byref(ne), C.byref(cov),
                                  C.byref(cov64))
@@ -146,8 +150,11 @@ def similarity(p, num_cells, max_fragment_length, group_id_to_pos, mutation_rate
         r.class_hist = np.zeros((MAX_CLASS, MAX_CLASS), np.uint64)
         r.K = np.zeros(max(p.n_chr, 1), np.uint64)
         r.raw = np.zeros((n, n))
-    rc = oracle_lib().orc_similarity(
-        *_csr(p), C.c_uint32(n), C.c_uint32(max_fragment_length), _p(g, _u32p), C.c_uint32(g.size),
+    wide = p.gid_base.dtype == np.uint32
+    fn = oracle_lib().orc_similarity_wide if wide else oracle_lib().orc_similarity
+    csr = _csr(p)[:5] + (_p(p.gid_base, _u32p),) if wide else _csr(p)
+    rc = fn(
+        *csr, C.c_uint32(n), C.c_uint32(max_fragment_length), _p(g, _u32p), C.c_uint32(g.size),
         C.c_double(mutation_rate), C.c_double(homozygous_rate), C.c_double(seq_error_rate),
         C.c_uint32(num_threads), C.c_int(NORMALIZATIONS[normalization]), _p(M, _f64p), _p(r.S1, _i32p),
         _p(r.D1, _i32p), _p(r.H, _i32p), _p(r.class_hist, _u64p), _p(r.K, _u64p), _p(r.raw, _f64p))

@@ -116,11 +116,19 @@ int orc_is_significant(const uint16_t counts[4], double theta, int cell_proporti
     return log_prob_homozygous - log_evidence < Ks[cell_proportion][threshold_idx];
 }
 
-int orc_filter(uint32_t n_chr,
+/* group id << 2 | base of entry e: 16-bit entries (the reference's PosData) or, for pileups beyond its 14-bit group
+ * ids (BASELINE config 5), 32-bit ones; exactly one of the two arrays is given */
+static inline uint32_t entry_at(const uint16_t *gb16, const uint32_t *gb32, uint64_t e) {
+    return gb32 ? gb32[e] : gb16[e];
+}
+
+static int filter_impl(uint32_t n_chr,
                const uint64_t *chr_ptr,
                const uint64_t *row_ptr,
                const uint32_t *read_id,
-               const uint16_t *gid_base,
+               const uint16_t *gid_base16,
+               const uint32_t *gid_base32,
+               uint32_t no_pos,
                const uint32_t *id_to_pos,
                uint32_t n_groups,
                double theta,
@@ -143,16 +151,16 @@ int orc_filter(uint32_t n_chr,
             uint16_t bc[4] = { 0, 0, 0, 0 };
             uint64_t n_in = 0;
             for (uint64_t e = row_ptr[l]; e < row_ptr[l + 1]; ++e) {
-                uint32_t gid = gid_base[e] >> 2;
+                uint32_t gid = entry_at(gid_base16, gid_base32, e) >> 2;
                 if (gid >= n_groups) {
                     return -1;
                 }
-                if (id_to_pos[gid] == ORC_NO_POS) { /* :169 */
+                if (id_to_pos[gid] == no_pos) { /* :169 */
                     keep_entry[e] = 0;
                     continue;
                 }
                 keep_entry[e] = 1;
-                bc[gid_base[e] & 3]++;
+                bc[entry_at(gid_base16, gid_base32, e) & 3]++;
                 n_in++;
             }
             int sig = orc_is_significant(bc, theta, cell_proportion);
@@ -177,6 +185,22 @@ int orc_filter(uint32_t n_chr,
     *avg_coverage = total_positions == 0 ? 0 : (double)total_coverage / total_positions; /* :188 */
     *avg_coverage64 = loci64 == 0 ? 0 : (double)entries64 / (double)loci64;
     return 0;
+}
+
+int orc_filter(uint32_t n_chr, const uint64_t *chr_ptr, const uint64_t *row_ptr, const uint32_t *read_id,
+               const uint16_t *gid_base, const uint32_t *id_to_pos, uint32_t n_groups, double theta, int cell_proportion,
+               uint8_t *keep_locus, uint8_t *keep_entry, uint64_t *n_kept_loci, uint64_t *n_kept_entries,
+               double *avg_coverage, double *avg_coverage64) {
+    return filter_impl(n_chr, chr_ptr, row_ptr, read_id, gid_base, NULL, ORC_NO_POS, id_to_pos, n_groups, theta, cell_proportion,
+                       keep_locus, keep_entry, n_kept_loci, n_kept_entries, avg_coverage, avg_coverage64);
+}
+
+int orc_filter_wide(uint32_t n_chr, const uint64_t *chr_ptr, const uint64_t *row_ptr, const uint32_t *read_id,
+                    const uint32_t *gid_base32, const uint32_t *id_to_pos, uint32_t n_groups, double theta, int cell_proportion,
+                    uint8_t *keep_locus, uint8_t *keep_entry, uint64_t *n_kept_loci, uint64_t *n_kept_entries,
+                    double *avg_coverage, double *avg_coverage64) {
+    return filter_impl(n_chr, chr_ptr, row_ptr, read_id, NULL, gid_base32, ORC_NO_POS_WIDE, id_to_pos, n_groups, theta,
+                       cell_proportion, keep_locus, keep_entry, n_kept_loci, n_kept_entries, avg_coverage, avg_coverage64);
 }
 
 /* ------------------------------------------------------------------------------------------ */
@@ -430,12 +454,13 @@ typedef struct {
     uint32_t n;     /* number of currently stored (pos, base) */
 } read_t;
 
-int orc_similarity(uint32_t n_chr,
+static int similarity_impl(uint32_t n_chr,
                    const uint64_t *chr_ptr,
                    const uint64_t *row_ptr,
                    const uint32_t *position,
                    const uint32_t *read_id,
-                   const uint16_t *gid_base,
+                   const uint16_t *gid_base16,
+                   const uint32_t *gid_base32,
                    uint32_t num_cells,
                    uint32_t max_fragment_length,
                    const uint32_t *group_id_to_pos,
@@ -503,7 +528,7 @@ int orc_similarity(uint32_t n_chr,
                 }
                 uint64_t s = map_slot(&map, read_id[e]);
                 if (map.vals[s] == UINT32_MAX) {
-                    uint32_t gid = gid_base[e] >> 2;
+                    uint32_t gid = entry_at(gid_base16, gid_base32, e) >> 2;
                     if (gid >= n_groups || group_id_to_pos[gid] >= num_cells) {
                         rc = -2; /* the reference would index out of bounds (mat.hpp:119) */
                         break;
@@ -536,7 +561,7 @@ int orc_similarity(uint32_t n_chr,
         for (uint64_t l = l0; l < l1 && rc == 0; ++l) {
             for (uint64_t e = row_ptr[l]; e < row_ptr[l + 1]; ++e) {
                 read_t *rd = &reads[eread[e - e0]];
-                uint8_t base = gid_base[e] & 3;
+                uint8_t base = entry_at(gid_base16, gid_base32, e) & 3;
                 if (position[l] - rd->start >= L) {
                     rc = -3; /* fragment longer than max_fragment_length: the reference would
                                 have retired the read and the outcome depends on batch timing */
@@ -708,6 +733,27 @@ int orc_similarity(uint32_t n_chr,
     free(mat_diff);
     free(cache);
     return rc;
+}
+
+int orc_similarity(uint32_t n_chr, const uint64_t *chr_ptr, const uint64_t *row_ptr, const uint32_t *position,
+                   const uint32_t *read_id, const uint16_t *gid_base, uint32_t num_cells, uint32_t max_fragment_length,
+                   const uint32_t *group_id_to_pos, uint32_t n_groups, double mutation_rate, double homozygous_rate,
+                   double seq_error_rate, uint32_t num_threads, int normalization, double *out_M, int32_t *S1, int32_t *D1,
+                   int32_t *H, uint64_t *class_hist, uint64_t *K_out, double *raw_M) {
+    return similarity_impl(n_chr, chr_ptr, row_ptr, position, read_id, gid_base, NULL, num_cells, max_fragment_length,
+                           group_id_to_pos, n_groups, mutation_rate, homozygous_rate, seq_error_rate, num_threads, normalization,
+                           out_M, S1, D1, H, class_hist, K_out, raw_M);
+}
+
+/* the same restatement on a pileup with 30-bit group ids (beyond what the reference's PosData can hold) */
+int orc_similarity_wide(uint32_t n_chr, const uint64_t *chr_ptr, const uint64_t *row_ptr, const uint32_t *position,
+                        const uint32_t *read_id, const uint32_t *gid_base32, uint32_t num_cells, uint32_t max_fragment_length,
+                        const uint32_t *group_id_to_pos, uint32_t n_groups, double mutation_rate, double homozygous_rate,
+                        double seq_error_rate, uint32_t num_threads, int normalization, double *out_M, int32_t *S1, int32_t *D1,
+                        int32_t *H, uint64_t *class_hist, uint64_t *K_out, double *raw_M) {
+    return similarity_impl(n_chr, chr_ptr, row_ptr, position, read_id, NULL, gid_base32, num_cells, max_fragment_length,
+                           group_id_to_pos, n_groups, mutation_rate, homozygous_rate, seq_error_rate, num_threads, normalization,
+                           out_M, S1, D1, H, class_hist, K_out, raw_M);
 }
 
 /* ------------------------------------------------------------------------------------------ */

@@ -96,6 +96,21 @@ int orc_similarity(uint32_t n_chr,
                    uint64_t *K_out,
                    double *raw_M);
 
+/* The same two restatements on WIDE pileups: 32-bit entries (group id << 2 | base, 30-bit group ids) and 0xFFFFFFFF as
+ * "not in the cluster". The reference itself cannot hold more than 16 383 groups (sequenced_data.hpp:29-36), so for
+ * BASELINE config 5 (20 000 cells) the oracle is this restatement; below 16 384 groups it is checked to agree with the
+ * 16-bit entry points, which are pinned against the compiled reference (tests/test_oracle_similarity.py). */
+#define ORC_NO_POS_WIDE 0xFFFFFFFFu
+int orc_filter_wide(uint32_t n_chr, const uint64_t *chr_ptr, const uint64_t *row_ptr, const uint32_t *read_id,
+                    const uint32_t *gid_base32, const uint32_t *id_to_pos, uint32_t n_groups, double theta, int cell_proportion,
+                    uint8_t *keep_locus, uint8_t *keep_entry, uint64_t *n_kept_loci, uint64_t *n_kept_entries,
+                    double *avg_coverage, double *avg_coverage64);
+int orc_similarity_wide(uint32_t n_chr, const uint64_t *chr_ptr, const uint64_t *row_ptr, const uint32_t *position,
+                        const uint32_t *read_id, const uint32_t *gid_base32, uint32_t num_cells, uint32_t max_fragment_length,
+                        const uint32_t *group_id_to_pos, uint32_t n_groups, double mutation_rate, double homozygous_rate,
+                        double seq_error_rate, uint32_t num_threads, int normalization, double *out_M, int32_t *S1, int32_t *D1,
+                        int32_t *H, uint64_t *class_hist, uint64_t *K_out, double *raw_M);
+
 /* similarity_matrix.cpp:271-293 on a row-major n*n matrix, in place. */
 int orc_normalize(int normalization, uint32_t n, double *m);
 

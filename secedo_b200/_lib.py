@@ -14,6 +14,7 @@ LIB_PATH = os.path.join(HERE, "libsecedo_b200.so")
 MAX_CLASS = 64
 N_PLANES = 9
 NO_POS = 16383
+NO_POS_WIDE = 0xFFFFFFFF
 NORMALIZATIONS = {"ADD_MIN": 0, "EXPONENTIATE": 1, "SCALE_MAX_1": 2}
 PATHS = {"auto": 0, "scatter": 1, "gemm": 2}
 PATH_NAMES = {v: k for k, v in PATHS.items()}
@@ -30,7 +31,7 @@ class Stats(C.Structure):
         ("n_loci", C.c_uint64), ("n_entries", C.c_uint64), ("n_reads", C.c_uint64),
         ("n_dropped_entries", C.c_uint64), ("n_multi_reads", C.c_uint64), ("n_tail_reads", C.c_uint64),
         ("n_pairs_first", C.c_uint64), ("n_pairs_multi", C.c_uint64),
-        ("path_used", C.c_int32), ("reserved", C.c_int32),
+        ("path_used", C.c_int32), ("n_span_splits", C.c_int32),
         ("ms_link", C.c_float), ("ms_first_order", C.c_float), ("ms_multi", C.c_float), ("ms_epilogue", C.c_float),
         ("ms_stage", C.c_float), ("ms_gemm", C.c_float), ("gemm_launches", C.c_uint64),
     ]
@@ -81,6 +82,9 @@ SIGNATURES = {
     "sgpu_pileup_upload_lazy_async": (C.c_int, [_vp, C.c_uint32, _vp, _vp, _vp, _vp, _vp, C.POINTER(_vp)]),
     "sgpu_pileup_from_bin": (C.c_int, [_vp, C.c_uint32, _vp, _vp, _vp, C.c_uint32, C.c_uint32, _vp, _vp, C.POINTER(_vp),
                                        _u32p, _u32p]),
+    "sgpu_pileup_upload_wide": (C.c_int, [_vp, C.c_uint32, _vp, _vp, _vp, _vp, _vp, C.POINTER(_vp)]),
+    "sgpu_pileup_download_wide": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "sgpu_pileup_is_wide": (C.c_int, [_vp]),
     "sgpu_pileup_wrap_device": (C.c_int, [_vp, C.c_uint32, _vp, _vp, _vp, _vp, _vp, C.POINTER(_vp)]),
     "sgpu_pileup_dims": (C.c_int, [_vp, _u32p, _u64p, _u64p]),
     "sgpu_pileup_download": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp]),
@@ -94,6 +98,9 @@ SIGNATURES = {
     "sgpu_counts_free": (None, [_vp, _vp]),
     "sgpu_counts_accumulate": (C.c_int, [_vp, _vp, _vp, C.c_uint32, _vp, C.c_uint32, C.c_double, C.c_double,
                                          C.c_double, C.c_uint32, C.c_int, C.POINTER(Stats)]),
+    "sgpu_counts_accumulate_range": (C.c_int, [_vp, _vp, _vp, C.c_uint32, _vp, C.c_uint32, C.c_double, C.c_double,
+                                               C.c_double, _vp, _vp, _vp, C.c_int, C.POINTER(Stats)]),
+    "sgpu_chromosome_cutoff": (C.c_int, [_vp, _vp, C.c_uint32, C.c_uint32, _vp, _vp, _vp]),
     "sgpu_counts_buffers": (C.c_int, [_vp, C.POINTER(_vp), _u64p, C.POINTER(_vp), _u64p, C.POINTER(_vp), _u64p]),
     "sgpu_counts_set_layout": (C.c_int, [_vp, _vp, C.c_int, C.c_int]),
     "sgpu_counts_pack": (C.c_int, [_vp, _vp, C.POINTER(_vp), _u64p]),
@@ -107,6 +114,16 @@ SIGNATURES = {
                                            C.POINTER(Stats)]),
     "sgpu_similarity_finalize_async": (C.c_int, [_vp, _vp, C.c_uint32, C.c_double, C.c_double, C.c_double, C.c_int, _vp]),
     "sgpu_output_wait": (C.c_int, [_vp]),
+    "sgpu_slab_raw": (C.c_int, [_vp, _vp, _vp, _vp, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_double, C.c_double,
+                                C.c_double, C.POINTER(_vp)]),
+    "sgpu_slab_finalize": (C.c_int, [_vp, _vp, C.c_int, _vp, C.POINTER(_vp)]),
+    "sgpu_slab_range": (C.c_int, [_vp, _u64p, _u64p]),
+    "sgpu_counts_ipc_handle": (C.c_int, [_vp, _vp, C.c_int, _vp]),
+    "sgpu_ipc_open": (C.c_int, [_vp, _vp, C.POINTER(_vp)]),
+    "sgpu_ipc_close": (C.c_int, [_vp, _vp]),
+    "sgpu_host_register": (C.c_int, [_vp, _vp, C.c_uint64, C.POINTER(_vp)]),
+    "sgpu_host_unregister": (C.c_int, [_vp, _vp]),
+    "sgpu_counts_checksum": (C.c_int, [_vp, _vp, _vp, C.c_uint32, C.c_uint32, C.c_uint32, _u64p]),
     "sgpu_log_probs": (C.c_int, [_vp, C.c_double, C.c_double, C.c_double, C.c_uint32, C.c_uint32, _vp, _vp]),
     "sgpu_expectation_maximization": (C.c_int, [_vp, _vp, _vp, C.c_uint32, C.c_double, _vp, C.c_uint32, C.c_uint32, _u32p,
                                                 C.POINTER(C.c_float)]),

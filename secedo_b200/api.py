@@ -76,6 +76,24 @@ class Context:
         self.check(self._lib.sgpu_synth_pileup(self._h, C.byref(sp), C.byref(h)))
         return DevicePileup(self, h)
 
+    def ipc_open(self, handle: bytes) -> int:
+        """Map another process's count planes (:meth:`Counts.ipc_handle`) into this process; device pointer."""
+        ptr = C.c_void_p()
+        self.check(self._lib.sgpu_ipc_open(self._h, C.create_string_buffer(handle, 64), C.byref(ptr)))
+        return ptr.value
+
+    def ipc_close(self, ptr: int) -> None:
+        self.check(self._lib.sgpu_ipc_close(self._h, C.c_void_p(ptr)))
+
+    def host_register(self, host_ptr: int, nbytes: int) -> int:
+        """Page-lock + map host memory (e.g. a shared-memory segment); returns the device alias."""
+        dev = C.c_void_p()
+        self.check(self._lib.sgpu_host_register(self._h, C.c_void_p(host_ptr), int(nbytes), C.byref(dev)))
+        return dev.value
+
+    def host_unregister(self, host_ptr: int) -> None:
+        self.check(self._lib.sgpu_host_unregister(self._h, C.c_void_p(host_ptr)))
+
     def close(self) -> None:
         if self._h:
             self._lib.sgpu_shutdown(self._h)
@@ -90,8 +108,9 @@ class Context:
     # ------------------------------------------------------------------ staging
     def upload(self, p: Pileup) -> "DevicePileup":
         h = C.c_void_p()
-        self.check(self._lib.sgpu_pileup_upload(self._h, p.n_chr, _ptr(p.chr_ptr), _ptr(p.row_ptr), _ptr(p.position),
-                                                _ptr(p.read_id), _ptr(p.gid_base), C.byref(h)))
+        fn = self._lib.sgpu_pileup_upload_wide if p.wide else self._lib.sgpu_pileup_upload
+        self.check(fn(self._h, p.n_chr, _ptr(p.chr_ptr), _ptr(p.row_ptr), _ptr(p.position), _ptr(p.read_id), _ptr(p.gid_base),
+                      C.byref(h)))
         return DevicePileup(self, h)
 
     def upload_async(self, p: Pileup) -> "DevicePileup":
@@ -185,12 +204,18 @@ class DevicePileup:
     def n_entries(self) -> int:
         return self.dims()[2]
 
+    @property
+    def wide(self) -> bool:
+        return bool(self.ctx._lib.sgpu_pileup_is_wide(self._h))
+
     def download(self) -> Pileup:
         n_chr, n_loci, n_entries = self.dims()
+        wide = self.wide
         chr_ptr, row_ptr = np.zeros(n_chr + 1, np.uint64), np.zeros(n_loci + 1, np.uint64)
-        pos, rid, gb = np.zeros(n_loci, np.uint32), np.zeros(n_entries, np.uint32), np.zeros(n_entries, np.uint16)
-        self.ctx.check(self.ctx._lib.sgpu_pileup_download(self.ctx._h, self._h, _ptr(chr_ptr), _ptr(row_ptr), _ptr(pos),
-                                                          _ptr(rid), _ptr(gb)))
+        pos, rid = np.zeros(n_loci, np.uint32), np.zeros(n_entries, np.uint32)
+        gb = np.zeros(n_entries, np.uint32 if wide else np.uint16)
+        fn = self.ctx._lib.sgpu_pileup_download_wide if wide else self.ctx._lib.sgpu_pileup_download
+        self.ctx.check(fn(self.ctx._h, self._h, _ptr(chr_ptr), _ptr(row_ptr), _ptr(pos), _ptr(rid), _ptr(gb)))
         return Pileup(chr_ptr, row_ptr, pos, rid, gb)
 
     def free(self) -> None:
@@ -286,6 +311,29 @@ class Counts:
         self.last_stats = st.as_dict()
         return self.last_stats
 
+    def accumulate_range(self, piece: PosDataLike, max_fragment_length: int, group_id_to_pos: Sequence[int],
+                         mutation_rate: float, homozygous_rate: float, seq_error_rate: float,
+                         own_pos_begin: Sequence[int], own_pos_end: Sequence[int], tail_position: Sequence[int],
+                         path: str = "auto") -> dict:
+        """A piece of its chromosomes (owned loci by position range + halos of max_fragment_length bp): adds the piece's
+        share of the counts. ``tail_position`` comes from :func:`chromosome_cutoff`. See include/secedo_b200.h."""
+        ctx = self.ctx
+        g = np.ascontiguousarray(group_id_to_pos, np.uint32)
+        lo, hi = np.ascontiguousarray(own_pos_begin, np.uint32), np.ascontiguousarray(own_pos_end, np.uint32)
+        tp = np.ascontiguousarray(tail_position, np.uint32)
+        dp, owned = _staged(ctx, piece)
+        assert lo.size == hi.size == tp.size == dp.n_chr, "one value per chromosome of the piece"
+        st = Stats()
+        try:
+            ctx.check(ctx._lib.sgpu_counts_accumulate_range(ctx._h, self._h, dp._h, int(max_fragment_length), _ptr(g), g.size,
+                                                            float(mutation_rate), float(homozygous_rate), float(seq_error_rate),
+                                                            _ptr(lo), _ptr(hi), _ptr(tp), PATHS[path], C.byref(st)))
+        finally:
+            if owned:
+                dp.free()
+        self.last_stats = st.as_dict()
+        return self.last_stats
+
     def buffers(self):
         """(i32 device pointer, n_i32, f64 device pointer or None, n_f64, hist device pointer, n_hist)."""
         i32, f64, hist = C.c_void_p(), C.c_void_p(), C.c_void_p()
@@ -315,6 +363,51 @@ class Counts:
 
     def unpack_range(self, first_plane: int, n_planes: int) -> None:
         self.ctx.check(self.ctx._lib.sgpu_counts_unpack_range(self.ctx._h, self._h, int(first_plane), int(n_planes)))
+
+    # ---- multi-GPU epilogue over peer memory (include/secedo_b200.h: sgpu_slab_raw / sgpu_slab_finalize) ----
+    def ipc_handle(self, spill: bool = False) -> bytes:
+        """CUDA IPC handle (64 bytes) of the int32 planes (or of the fp64 spill plane), for the other ranks of the node."""
+        buf = C.create_string_buffer(64)
+        self.ctx.check(self.ctx._lib.sgpu_counts_ipc_handle(self.ctx._h, self._h, 1 if spill else 0, buf))
+        return buf.raw
+
+    def _peer_array(self, peer_planes: Sequence[int]):
+        return (C.c_void_p * len(peer_planes))(*[C.c_void_p(int(p)) for p in peer_planes])
+
+    def slab_raw(self, peer_planes: Sequence[int], slab: int, n_slabs: int, max_fragment_length: int, mutation_rate: float,
+                 homozygous_rate: float, seq_error_rate: float, peer_spill: Optional[Sequence[int]] = None) -> int:
+        """Sum the planes of all GPUs (device pointers valid on this GPU, own planes included) over this GPU's share of
+        the tiles and transform them; returns the device pointer of {-min, max} (2 doubles) of the share."""
+        ext = C.c_void_p()
+        self.ctx.check(self.ctx._lib.sgpu_slab_raw(self.ctx._h, self._h, self._peer_array(peer_planes),
+                                                   self._peer_array(peer_spill) if peer_spill else None, len(peer_planes),
+                                                   int(slab), int(n_slabs), int(max_fragment_length), float(mutation_rate),
+                                                   float(homozygous_rate), float(seq_error_rate), C.byref(ext)))
+        return ext.value
+
+    def slab_finalize(self, normalization: str, out_ptr: Optional[int] = None) -> int:
+        """Normalise this GPU's share and write it (and its mirror image) into the n x n matrix at ``out_ptr`` (device
+        memory or mapped host memory), or into a device matrix owned by this object; returns the pointer written to."""
+        if normalization not in NORMALIZATIONS:
+            raise ValueError(f"Invalid normalization: {normalization}")
+        dev = C.c_void_p()
+        self.ctx.check(self.ctx._lib.sgpu_slab_finalize(self.ctx._h, self._h, NORMALIZATIONS[normalization],
+                                                        C.c_void_p(out_ptr) if out_ptr else None, C.byref(dev)))
+        return dev.value
+
+    def slab_range(self) -> Tuple[int, int]:
+        a, b = C.c_uint64(), C.c_uint64()
+        self.ctx.check(self.ctx._lib.sgpu_slab_range(self._h, C.byref(a), C.byref(b)))
+        return a.value, b.value
+
+    def checksum(self, peer_planes: Optional[Sequence[int]] = None, slab: int = 0, n_slabs: int = 1) -> int:
+        """64-bit linear checksum of the upper triangles of the planes in use (of the element-wise sum of the peers'
+        planes over share ``slab`` when ``peer_planes`` is given)."""
+        out = C.c_uint64()
+        arr = self._peer_array(peer_planes) if peer_planes else None
+        self.ctx.check(self.ctx._lib.sgpu_counts_checksum(self.ctx._h, self._h, arr, len(peer_planes) if peer_planes else 0,
+                                                          int(slab), int(n_slabs), C.byref(out)))
+        return out.value
 
     def sparse_pack(self, first_plane: int = 2):
         """Non-zeros of the planes from ``first_plane`` on as device lists: (idx pointer, val pointer, nnz)."""
@@ -430,6 +523,25 @@ def compute_similarity_matrix(pos_data: PosDataLike, num_cells: int, max_fragmen
         if owned:
             dp.free()
     return (out, st.as_dict()) if return_stats else out
+
+
+def chromosome_cutoff(ends: PosDataLike, max_fragment_length: int, num_threads: int, whole: Sequence[bool],
+                      ctx: Optional[Context] = None):
+    """The reference's tail cutoff of whole chromosomes decided from their ENDS (``sgpu_chromosome_cutoff``): returns
+    (tail_position uint32[n_chr], resolved bool[n_chr])."""
+    ctx = ctx or default_context()
+    dp, owned = _staged(ctx, ends)
+    w = np.ascontiguousarray(whole, np.uint8)
+    n_chr = dp.n_chr
+    assert w.size == n_chr
+    tp, rs = np.zeros(n_chr, np.uint32), np.zeros(n_chr, np.uint8)
+    try:
+        ctx.check(ctx._lib.sgpu_chromosome_cutoff(ctx._h, dp._h, int(max_fragment_length), int(num_threads), _ptr(w), _ptr(tp),
+                                                  _ptr(rs)))
+    finally:
+        if owned:
+            dp.free()
+    return tp, rs.astype(bool)
 
 
 def log_probs(mutation_rate: float, homozygous_rate: float, seq_error_rate: float, max_fragment_length: int, n: int,

@@ -178,6 +178,55 @@ __global__ void sparse_add_kernel(int32_t *__restrict__ planes, const uint32_t *
     }
 }
 
+// order-independent checksum of (sums of) upper triangles, see sgpu_counts_checksum
+struct ChecksumArgs {
+    const int32_t *peer[SGPU_MAX_PEERS];
+    uint32_t n_peers, n, planes, nb;
+    uint64_t nn, t0, t1;
+};
+__device__ __forceinline__ uint64_t mix_weight(uint64_t x) { // splitmix64 finaliser: weight of a (plane, i, j) position
+    x += 0x9E3779B97F4A7C15ull;
+    x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ull;
+    x = (x ^ (x >> 27)) * 0x94D049BB133111EBull;
+    return x ^ (x >> 31);
+}
+__global__ void __launch_bounds__(256) checksum_kernel(ChecksumArgs a, unsigned long long *__restrict__ sum) {
+    unsigned long long acc = 0;
+    const uint32_t tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    for (uint64_t t = a.t0 + blockIdx.x; t < a.t1; t += gridDim.x) {
+        // tile number -> (bi, bj), row-major over bj >= bi (same numbering as the slab epilogue)
+        const double b = 2.0 * a.nb + 1.0;
+        uint32_t bi = static_cast<uint32_t>((b - sqrt(b * b - 8.0 * static_cast<double>(t))) * 0.5);
+        auto before = [&](uint32_t r) { return static_cast<uint64_t>(r) * a.nb - static_cast<uint64_t>(r) * (r - 1) / 2; };
+        while (bi > 0 && before(bi) > t) {
+            --bi;
+        }
+        while (before(bi + 1) <= t) {
+            ++bi;
+        }
+        const uint32_t bj = bi + static_cast<uint32_t>(t - before(bi));
+        for (int k = 0; k < 4; ++k) {
+            const uint32_t i = bi * 32 + ty + 8 * k, j = bj * 32 + tx;
+            if (i < j && j < a.n) {
+                const uint64_t idx = static_cast<uint64_t>(i) * a.n + j;
+                for (uint32_t pl = 0; pl < a.planes; ++pl) {
+                    long long v = 0;
+                    for (uint32_t q = 0; q < a.n_peers; ++q) {
+                        v += a.peer[q][pl * a.nn + idx];
+                    }
+                    acc += static_cast<unsigned long long>(v) * mix_weight(pl * a.nn + idx);
+                }
+            }
+        }
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+        acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    }
+    if (tx == 0 && acc) {
+        atomicAdd(sum, acc);
+    }
+}
+
 struct EventTimer {
     cudaEvent_t a = nullptr, b = nullptr;
     cudaStream_t st;
@@ -319,7 +368,7 @@ int sgpu_synchronize(sgpu_ctx *ctx) {
 // ---- pileup ---------------------------------------------------------------------------------------
 static int pileup_upload(sgpu_ctx *ctx, uint32_t n_chr, const uint64_t *chr_ptr, const uint64_t *row_ptr,
                          const uint32_t *position, const uint32_t *read_id, const uint16_t *gid_base, bool async,
-                         sgpu_pileup **out, bool lazy_read_id = false) {
+                         sgpu_pileup **out, bool lazy_read_id = false, const uint32_t *gid_base32 = nullptr) {
     SGPU_CUDA(ctx, cudaSetDevice(ctx->device));
     cudaStream_t st = ctx->stream;
     if (async) {
@@ -339,6 +388,7 @@ static int pileup_upload(sgpu_ctx *ctx, uint32_t n_chr, const uint64_t *chr_ptr,
     p->n_chr = n_chr;
     p->n_loci = chr_ptr[n_chr];
     p->n_entries = p->n_loci ? row_ptr[p->n_loci] : 0;
+    p->wide = gid_base32 != nullptr;
     p->h_chr_ptr = new uint64_t[n_chr + 1];
     std::memcpy(p->h_chr_ptr, chr_ptr, (n_chr + 1) * sizeof(uint64_t));
     const uint64_t P = p->n_loci, E = p->n_entries;
@@ -360,7 +410,11 @@ static int pileup_upload(sgpu_ctx *ctx, uint32_t n_chr, const uint64_t *chr_ptr,
     } else {
         SGPU_CUDA(ctx, sgpu_dev_alloc(ctx, reinterpret_cast<void **>(&p->d_read_id), (E ? E : 1) * sizeof(uint32_t)));
     }
-    SGPU_CUDA(ctx, sgpu_dev_alloc(ctx, reinterpret_cast<void **>(&p->d_gid_base), (E ? E : 1) * sizeof(uint16_t)));
+    if (p->wide) {
+        SGPU_CUDA(ctx, sgpu_dev_alloc(ctx, reinterpret_cast<void **>(&p->d_gid_base32), (E ? E : 1) * sizeof(uint32_t)));
+    } else {
+        SGPU_CUDA(ctx, sgpu_dev_alloc(ctx, reinterpret_cast<void **>(&p->d_gid_base), (E ? E : 1) * sizeof(uint16_t)));
+    }
     // the copy of chr_ptr reads p->h_chr_ptr (owned by the pileup), not the caller's array
     SGPU_CUDA(ctx, cudaMemcpyAsync(p->d_chr_ptr, p->h_chr_ptr, (n_chr + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, st));
     if (P) {
@@ -373,7 +427,11 @@ static int pileup_upload(sgpu_ctx *ctx, uint32_t n_chr, const uint64_t *chr_ptr,
         if (p->d_read_id) {
             SGPU_CUDA(ctx, cudaMemcpyAsync(p->d_read_id, read_id, E * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
         }
-        SGPU_CUDA(ctx, cudaMemcpyAsync(p->d_gid_base, gid_base, E * sizeof(uint16_t), cudaMemcpyHostToDevice, st));
+        if (p->wide) {
+            SGPU_CUDA(ctx, cudaMemcpyAsync(p->d_gid_base32, gid_base32, E * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
+        } else {
+            SGPU_CUDA(ctx, cudaMemcpyAsync(p->d_gid_base, gid_base, E * sizeof(uint16_t), cudaMemcpyHostToDevice, st));
+        }
     }
     if (async) {
         SGPU_CUDA(ctx, cudaEventCreateWithFlags(&p->ready, cudaEventDisableTiming));
@@ -390,6 +448,16 @@ int sgpu_pileup_upload(sgpu_ctx *ctx, uint32_t n_chr, const uint64_t *chr_ptr, c
                        sgpu_pileup **out) {
     return pileup_upload(ctx, n_chr, chr_ptr, row_ptr, position, read_id, gid_base, false, out);
 }
+
+int sgpu_pileup_upload_wide(sgpu_ctx *ctx, uint32_t n_chr, const uint64_t *chr_ptr, const uint64_t *row_ptr,
+                            const uint32_t *position, const uint32_t *read_id, const uint32_t *gid_base32, sgpu_pileup **out) {
+    if (!gid_base32) {
+        return sgpu_fail(ctx, SGPU_E_ARG, "upload_wide: gid_base32 missing");
+    }
+    return pileup_upload(ctx, n_chr, chr_ptr, row_ptr, position, read_id, nullptr, false, out, false, gid_base32);
+}
+
+int sgpu_pileup_is_wide(const sgpu_pileup *p) { return p && p->wide ? 1 : 0; }
 
 int sgpu_pileup_upload_async(sgpu_ctx *ctx, uint32_t n_chr, const uint64_t *chr_ptr, const uint64_t *row_ptr,
                              const uint32_t *position, const uint32_t *read_id, const uint16_t *gid_base,
@@ -462,8 +530,27 @@ int sgpu_pileup_dims(const sgpu_pileup *p, uint32_t *n_chr, uint64_t *n_loci, ui
     return SGPU_OK;
 }
 
+static int pileup_download(sgpu_ctx *ctx, const sgpu_pileup *p, uint64_t *chr_ptr, uint64_t *row_ptr, uint32_t *position,
+                           uint32_t *read_id, uint16_t *gid_base, uint32_t *gid_base32);
+
 int sgpu_pileup_download(sgpu_ctx *ctx, const sgpu_pileup *p, uint64_t *chr_ptr, uint64_t *row_ptr, uint32_t *position,
                          uint32_t *read_id, uint16_t *gid_base) {
+    if (p->wide && gid_base) {
+        return sgpu_fail(ctx, SGPU_E_ARG, "wide pileup: use sgpu_pileup_download_wide");
+    }
+    return pileup_download(ctx, p, chr_ptr, row_ptr, position, read_id, gid_base, nullptr);
+}
+
+int sgpu_pileup_download_wide(sgpu_ctx *ctx, const sgpu_pileup *p, uint64_t *chr_ptr, uint64_t *row_ptr, uint32_t *position,
+                              uint32_t *read_id, uint32_t *gid_base32) {
+    if (!p->wide && gid_base32) {
+        return sgpu_fail(ctx, SGPU_E_ARG, "not a wide pileup: use sgpu_pileup_download");
+    }
+    return pileup_download(ctx, p, chr_ptr, row_ptr, position, read_id, nullptr, gid_base32);
+}
+
+static int pileup_download(sgpu_ctx *ctx, const sgpu_pileup *p, uint64_t *chr_ptr, uint64_t *row_ptr, uint32_t *position,
+                           uint32_t *read_id, uint16_t *gid_base, uint32_t *gid_base32) {
     SGPU_CUDA(ctx, cudaSetDevice(ctx->device));
     SGPU_WAIT_PILEUP(ctx, p);
     if (read_id) {
@@ -484,6 +571,9 @@ int sgpu_pileup_download(sgpu_ctx *ctx, const sgpu_pileup *p, uint64_t *chr_ptr,
     }
     if (gid_base && p->n_entries) {
         SGPU_CUDA(ctx, cudaMemcpyAsync(gid_base, p->d_gid_base, p->n_entries * sizeof(uint16_t), cudaMemcpyDeviceToHost, st));
+    }
+    if (gid_base32 && p->n_entries) {
+        SGPU_CUDA(ctx, cudaMemcpyAsync(gid_base32, p->d_gid_base32, p->n_entries * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
     }
     SGPU_CUDA(ctx, cudaStreamSynchronize(st));
     return SGPU_OK;
@@ -508,6 +598,7 @@ void sgpu_pileup_free(sgpu_ctx *ctx, sgpu_pileup *p) {
         sgpu_dev_free(ctx, p->d_position);
         sgpu_dev_free(ctx, p->d_read_id);
         sgpu_dev_free(ctx, p->d_gid_base);
+        sgpu_dev_free(ctx, p->d_gid_base32);
     }
     delete[] p->h_chr_ptr;
     delete p;
@@ -565,6 +656,11 @@ void sgpu_counts_free(sgpu_ctx *ctx, sgpu_counts *c) {
     cudaFree(c->i32);
     cudaFree(c->hist);
     cudaFree(c->spill);
+    cudaFree(c->slab_minmax);
+    cudaFree(c->slab_out);
+    if (ctx) {
+        sgpu_dev_free(ctx, c->slab_raw);
+    }
     if (ctx) {
         sgpu_dev_free(ctx, c->packed);
         sgpu_dev_free(ctx, c->sp_idx);
@@ -573,10 +669,12 @@ void sgpu_counts_free(sgpu_ctx *ctx, sgpu_counts *c) {
     delete c;
 }
 
-int sgpu_counts_accumulate(sgpu_ctx *ctx, sgpu_counts *c, const sgpu_pileup *filtered, uint32_t max_fragment_length,
+} // extern "C"
+
+static int accumulate_impl(sgpu_ctx *ctx, sgpu_counts *c, const sgpu_pileup *filtered, uint32_t max_fragment_length,
                            const uint32_t *group_id_to_pos, uint32_t n_groups, double mutation_rate,
                            double homozygous_rate, double seq_error_rate, uint32_t num_threads, int path,
-                           sgpu_stats *stats) {
+                           sgpu_stats *stats, const RangeSpec *range) {
     SGPU_CUDA(ctx, cudaSetDevice(ctx->device));
     SGPU_WAIT_PILEUP(ctx, filtered);
     SGPU_TRY(sgpu_pileup_materialize(ctx, filtered));
@@ -604,13 +702,14 @@ int sgpu_counts_accumulate(sgpu_ctx *ctx, sgpu_counts *c, const sgpu_pileup *fil
     LinkResult lr;
     {
         EventTimer t(ctx->stream);
-        SGPU_TRY(sgpu_link_reads(ctx, filtered, c->n, max_fragment_length, group_id_to_pos, n_groups, num_threads, &lr));
+        SGPU_TRY(sgpu_link_reads(ctx, filtered, c->n, max_fragment_length, group_id_to_pos, n_groups, num_threads, &lr, range));
         s.ms_link = t.stop();
     }
     s.n_reads = lr.n_reads;
     s.n_dropped_entries = lr.n_dropped;
     s.n_multi_reads = lr.n_multi;
     s.n_tail_reads = lr.n_tail;
+    s.n_span_splits = static_cast<int32_t>(std::min<uint64_t>(lr.n_span_splits, 0x7FFFFFFF));
     ctx->ms_syrk = ctx->ms_stage = 0.f;
     ctx->n_syrk = 0;
     {
@@ -637,6 +736,46 @@ int sgpu_counts_accumulate(sgpu_ctx *ctx, sgpu_counts *c, const sgpu_pileup *fil
         *stats = s;
     }
     return SGPU_OK;
+}
+
+extern "C" {
+
+int sgpu_counts_accumulate(sgpu_ctx *ctx, sgpu_counts *c, const sgpu_pileup *filtered, uint32_t max_fragment_length,
+                           const uint32_t *group_id_to_pos, uint32_t n_groups, double mutation_rate,
+                           double homozygous_rate, double seq_error_rate, uint32_t num_threads, int path,
+                           sgpu_stats *stats) {
+    return accumulate_impl(ctx, c, filtered, max_fragment_length, group_id_to_pos, n_groups, mutation_rate, homozygous_rate,
+                           seq_error_rate, num_threads, path, stats, nullptr);
+}
+
+int sgpu_counts_accumulate_range(sgpu_ctx *ctx, sgpu_counts *c, const sgpu_pileup *piece, uint32_t max_fragment_length,
+                                 const uint32_t *group_id_to_pos, uint32_t n_groups, double mutation_rate,
+                                 double homozygous_rate, double seq_error_rate, const uint32_t *own_pos_begin,
+                                 const uint32_t *own_pos_end, const uint32_t *tail_position, int path, sgpu_stats *stats) {
+    if (!own_pos_begin || !own_pos_end || !tail_position) {
+        return sgpu_fail(ctx, SGPU_E_ARG, "accumulate_range: own_pos_begin, own_pos_end and tail_position are required (one value per chromosome)");
+    }
+    RangeSpec rs;
+    rs.own_pos_begin = own_pos_begin;
+    rs.own_pos_end = own_pos_end;
+    rs.tail_position = tail_position;
+    // num_threads is not needed: the cutoff it selects arrives as tail_position
+    return accumulate_impl(ctx, c, piece, max_fragment_length, group_id_to_pos, n_groups, mutation_rate, homozygous_rate,
+                           seq_error_rate, 1, path, stats, &rs);
+}
+
+int sgpu_chromosome_cutoff(sgpu_ctx *ctx, const sgpu_pileup *ends, uint32_t max_fragment_length, uint32_t num_threads,
+                           const uint8_t *whole, uint32_t *tail_position, uint8_t *resolved) {
+    SGPU_CUDA(ctx, cudaSetDevice(ctx->device));
+    if (!ends || !whole || !tail_position || !resolved) {
+        return sgpu_fail(ctx, SGPU_E_ARG, "chromosome_cutoff: null argument");
+    }
+    if (num_threads == 0) {
+        return sgpu_fail(ctx, SGPU_E_ARG, "num_threads must be >= 1");
+    }
+    SGPU_WAIT_PILEUP(ctx, ends);
+    SGPU_TRY(sgpu_pileup_materialize(ctx, ends));
+    return sgpu_cutoff_from_suffix(ctx, ends, max_fragment_length, num_threads, whole, tail_position, resolved);
 }
 
 int sgpu_counts_buffers(sgpu_counts *c, int32_t **i32, uint64_t *n_i32, double **f64, uint64_t *n_f64, uint64_t **hist,
@@ -895,6 +1034,111 @@ int sgpu_similarity(sgpu_ctx *ctx, const sgpu_pileup *filtered, uint32_t num_cel
     return rc;
 }
 
+// ---- multi-GPU epilogue over peer memory ----------------------------------------------------------
+int sgpu_slab_raw(sgpu_ctx *ctx, sgpu_counts *c, const int32_t *const *peer_planes, const double *const *peer_spill,
+                  uint32_t n_peers, uint32_t slab, uint32_t n_slabs, uint32_t max_fragment_length, double mutation_rate,
+                  double homozygous_rate, double seq_error_rate, double **extrema) {
+    SGPU_CUDA(ctx, cudaSetDevice(ctx->device));
+    return sgpu_slab_raw_impl(ctx, c, peer_planes, peer_spill, n_peers, slab, n_slabs, max_fragment_length, mutation_rate,
+                              homozygous_rate, seq_error_rate, extrema);
+}
+
+int sgpu_slab_finalize(sgpu_ctx *ctx, sgpu_counts *c, int normalization, double *out, double **device_out) {
+    SGPU_CUDA(ctx, cudaSetDevice(ctx->device));
+    return sgpu_slab_finalize_impl(ctx, c, normalization, out, device_out);
+}
+
+int sgpu_slab_range(const sgpu_counts *c, uint64_t *tile0, uint64_t *tile1) {
+    if (!c) {
+        return SGPU_E_ARG;
+    }
+    if (tile0) {
+        *tile0 = c->slab_t0;
+    }
+    if (tile1) {
+        *tile1 = c->slab_t1;
+    }
+    return SGPU_OK;
+}
+
+int sgpu_counts_ipc_handle(sgpu_ctx *ctx, sgpu_counts *c, int which, void *handle) {
+    SGPU_CUDA(ctx, cudaSetDevice(ctx->device));
+    static_assert(sizeof(cudaIpcMemHandle_t) == SGPU_IPC_HANDLE_BYTES, "IPC handle size");
+    if (which == 1 && !c->spill) {
+        return sgpu_fail(ctx, SGPU_E_ARG, "no spill plane (sgpu_counts_set_layout with want_spill creates it)");
+    }
+    cudaIpcMemHandle_t h;
+    SGPU_CUDA(ctx, cudaIpcGetMemHandle(&h, which == 1 ? static_cast<void *>(c->spill) : static_cast<void *>(c->i32)));
+    std::memcpy(handle, &h, sizeof(h));
+    return SGPU_OK;
+}
+
+int sgpu_ipc_open(sgpu_ctx *ctx, const void *handle, void **device_ptr) {
+    SGPU_CUDA(ctx, cudaSetDevice(ctx->device));
+    cudaIpcMemHandle_t h;
+    std::memcpy(&h, handle, sizeof(h));
+    SGPU_CUDA(ctx, cudaIpcOpenMemHandle(device_ptr, h, cudaIpcMemLazyEnablePeerAccess));
+    return SGPU_OK;
+}
+
+int sgpu_ipc_close(sgpu_ctx *ctx, void *device_ptr) {
+    SGPU_CUDA(ctx, cudaSetDevice(ctx->device));
+    SGPU_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    SGPU_CUDA(ctx, cudaIpcCloseMemHandle(device_ptr));
+    return SGPU_OK;
+}
+
+int sgpu_host_register(sgpu_ctx *ctx, void *host, uint64_t bytes, void **device_alias) {
+    SGPU_CUDA(ctx, cudaSetDevice(ctx->device));
+    SGPU_CUDA(ctx, cudaHostRegister(host, bytes, cudaHostRegisterPortable | cudaHostRegisterMapped));
+    SGPU_CUDA(ctx, cudaHostGetDevicePointer(device_alias, host, 0));
+    return SGPU_OK;
+}
+
+int sgpu_host_unregister(sgpu_ctx *ctx, void *host) {
+    SGPU_CUDA(ctx, cudaSetDevice(ctx->device));
+    SGPU_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    SGPU_CUDA(ctx, cudaHostUnregister(host));
+    return SGPU_OK;
+}
+
+int sgpu_counts_checksum(sgpu_ctx *ctx, sgpu_counts *c, const int32_t *const *peer_planes, uint32_t n_peers, uint32_t slab,
+                         uint32_t n_slabs, uint64_t *checksum) {
+    SGPU_CUDA(ctx, cudaSetDevice(ctx->device));
+    if (n_peers > SGPU_MAX_PEERS || n_slabs == 0 || slab >= n_slabs) {
+        return sgpu_fail(ctx, SGPU_E_ARG, "checksum: %u peers, slab %u of %u", n_peers, slab, n_slabs);
+    }
+    ChecksumArgs a;
+    for (uint32_t q = 0; q < SGPU_MAX_PEERS; ++q) {
+        a.peer[q] = (peer_planes && q < n_peers) ? peer_planes[q] : nullptr;
+    }
+    if (!peer_planes || n_peers == 0) {
+        a.peer[0] = c->i32;
+        n_peers = 1;
+    }
+    a.n_peers = n_peers;
+    a.n = c->n;
+    a.nn = c->nn;
+    a.planes = c->planes_used;
+    const uint32_t nb = (c->n + 31) / 32;
+    const uint64_t n_tiles = static_cast<uint64_t>(nb) * (nb + 1) / 2;
+    a.t0 = n_tiles * slab / n_slabs;
+    a.t1 = n_tiles * (slab + 1) / n_slabs;
+    a.nb = nb;
+    DevBuf<unsigned long long> d_sum;
+    SGPU_CUDA(ctx, d_sum.alloc(1, ctx));
+    SGPU_CUDA(ctx, cudaMemsetAsync(d_sum.p, 0, sizeof(unsigned long long), ctx->stream));
+    if (a.t1 > a.t0) {
+        const unsigned grid = static_cast<unsigned>(std::min<uint64_t>(a.t1 - a.t0, static_cast<uint64_t>(ctx->sm_count) * 16));
+        SGPU_LAUNCH(ctx, (checksum_kernel<<<grid, 256, 0, ctx->stream>>>(a, d_sum.p)));
+        SGPU_CUDA(ctx, cudaGetLastError());
+    }
+    SGPU_CUDA(ctx, cudaMemcpyAsync(&ctx->h_scratch[0], d_sum.p, sizeof(uint64_t), cudaMemcpyDeviceToHost, ctx->stream));
+    SGPU_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    *checksum = ctx->h_scratch[0];
+    return SGPU_OK;
+}
+
 int sgpu_log_probs(sgpu_ctx *ctx, double mutation_rate, double homozygous_rate, double seq_error_rate,
                    uint32_t max_fragment_length, uint32_t n, double *ls, double *ld) {
     SGPU_CUDA(ctx, cudaSetDevice(ctx->device));
@@ -907,6 +1151,9 @@ int sgpu_expectation_maximization(sgpu_ctx *ctx, const sgpu_pileup *filtered, co
     SGPU_CUDA(ctx, cudaSetDevice(ctx->device));
     if (!filtered) {
         return sgpu_fail(ctx, SGPU_E_ARG, "expectation_maximization: no pileup");
+    }
+    if (filtered->wide) {
+        return sgpu_fail(ctx, SGPU_E_ARG, "expectation_maximization: wide pileups (> 16 383 groups) are not supported");
     }
     return sgpu_em_impl(ctx, filtered, id_to_pos, n_groups, theta, prob_cluster_b, n_cells, max_iterations, iterations, ms);
 }

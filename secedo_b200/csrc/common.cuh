@@ -97,6 +97,21 @@ int sgpu_fail(sgpu_ctx *ctx, int code, const char *fmt, ...);
         }                                                                                          \
     } while (0)
 
+// Kernels that read (group << 2 | base) entries are templates over the entry type; SGPU_GB runs CALL with GB = uint16_t or
+// uint32_t and gid_base_ pointing to the array the pileup holds.
+#define SGPU_GB(p, CALL)                                      \
+    do {                                                      \
+        if ((p)->wide) {                                      \
+            using GB = uint32_t;                              \
+            const GB *gid_base_ = (p)->d_gid_base32;          \
+            CALL;                                             \
+        } else {                                              \
+            using GB = uint16_t;                              \
+            const GB *gid_base_ = (p)->d_gid_base;            \
+            CALL;                                             \
+        }                                                     \
+    } while (0)
+
 struct sgpu_pileup;
 // copy lazily uploaded read ids to the device (no-op otherwise); stream ordered on ctx->stream
 int sgpu_pileup_materialize(sgpu_ctx *ctx, const sgpu_pileup *p);
@@ -151,7 +166,9 @@ struct sgpu_pileup {
     uint64_t *d_row_ptr = nullptr;
     uint32_t *d_position = nullptr;
     uint32_t *d_read_id = nullptr;
-    uint16_t *d_gid_base = nullptr;
+    uint16_t *d_gid_base = nullptr;   // group id << 2 | base, 14-bit group ids (the reference's PosData)
+    uint32_t *d_gid_base32 = nullptr; // the same with 30-bit group ids (wide pileups: more than 16 383 cells / groups)
+    bool wide = false;                // d_gid_base32 is the one in use; NO_POS is 0xFFFFFFFF instead of 16383
     bool owns = true;
     // sgpu_pileup_upload_lazy_async: the read ids stay in the caller's pinned host memory (zc_read_id is its device
     // alias) and d_read_id is null until somebody other than the filter needs them (sgpu_pileup_materialize)
@@ -239,8 +256,16 @@ struct LinkResult {
     uint64_t n_tail_loci = 0;
     DevBuf<uint32_t> gmap;       // group_id_to_pos on the device
     uint32_t n_groups = 0, num_cells = 0;
+    // Ranged accumulation (sgpu_counts_accumulate_range): the pileup is a piece of its chromosomes plus halos; only the
+    // OWNED loci contribute first-order counts, and a multi-locus pair is accounted by the piece that owns its first
+    // common locus. Not ranged: everything is owned (owned.p == nullptr, own_loci.p == nullptr).
+    bool ranged = false;
+    DevBuf<uint8_t> owned;       // per locus
+    DevBuf<uint32_t> own_loci;   // owned loci, ascending
+    uint64_t n_own = 0;
     DevBuf<uint32_t> code;       // dense per-entry codes, only built for the pair-scatter path
     uint64_t n_reads = 0, n_multi = 0, n_dropped = 0, n_tail = 0;
+    uint64_t n_span_splits = 0;  // reads opened because a read id was chained over >= max_fragment_length (see split_span_kernel)
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -257,9 +282,23 @@ int sgpu_is_significant_impl(sgpu_ctx *ctx, const uint16_t *h_counts4, uint64_t 
                              int cell_proportion, uint8_t *h_out);
 
 // reads.cu
+// Ownership of a ranged call, one entry per chromosome of the pileup: the loci with position in [own_pos_begin,
+// own_pos_end) are owned; reads created at positions >= tail_position have index >= K (from sgpu_chromosome_cutoff).
+struct RangeSpec {
+    const uint32_t *own_pos_begin, *own_pos_end, *tail_position;
+};
+struct CutoffQuery { // suffix mode: only the cutoff is computed (host arrays, one entry per chromosome)
+    const uint8_t *whole;      // in: the chromosome is complete (not just its end)
+    uint32_t *tail_position;   // out
+    uint8_t *resolved;         // out
+};
 int sgpu_link_reads(sgpu_ctx *ctx, const sgpu_pileup *p, uint32_t num_cells, uint32_t L,
                     const uint32_t *h_group_id_to_pos, uint32_t n_groups, uint32_t num_threads,
-                    LinkResult *out);
+                    LinkResult *out, const RangeSpec *range = nullptr, const CutoffQuery *cutq = nullptr);
+// cutoff K of chromosomes of which only the END is given (suffix): per chromosome the position from which reads are
+// tail reads, and whether the suffix was long enough to decide it
+int sgpu_cutoff_from_suffix(sgpu_ctx *ctx, const sgpu_pileup *p, uint32_t L, uint32_t num_threads, const uint8_t *h_whole,
+                            uint32_t *h_tail_position, uint8_t *h_resolved);
 int sgpu_link_dense_codes(sgpu_ctx *ctx, const sgpu_pileup *p, LinkResult *lr);
 // (re)build the compact candidate list of the multi-locus correction from the reads that keep >= min_nst loci
 int sgpu_link_candidates(sgpu_ctx *ctx, LinkResult *lr, uint32_t min_nst);
@@ -283,8 +322,9 @@ int sgpu_log_probs_impl(sgpu_ctx *ctx, double eps, double h, double theta, uint3
 int sgpu_epilogue(sgpu_ctx *ctx, sgpu_counts *c, uint32_t L, double eps, double h, double theta,
                   int normalization, double *h_out, double **d_keep = nullptr, bool async_out = false);
 int sgpu_output_wait_impl(sgpu_ctx *ctx);
-int sgpu_slab_raw_impl(sgpu_ctx *ctx, sgpu_counts *c, const int32_t *const *peer_planes, uint32_t n_peers, uint32_t slab,
-                       uint32_t n_slabs, uint32_t L, double eps, double h, double theta, double **d_extrema);
+int sgpu_slab_raw_impl(sgpu_ctx *ctx, sgpu_counts *c, const int32_t *const *peer_planes, const double *const *peer_spill,
+                       uint32_t n_peers, uint32_t slab, uint32_t n_slabs, uint32_t L, double eps, double h, double theta,
+                       double **d_extrema);
 int sgpu_slab_finalize_impl(sgpu_ctx *ctx, sgpu_counts *c, int normalization, double *out, double **d_out);
 
 // em.cu
@@ -304,8 +344,11 @@ int sgpu_build_gtable(sgpu_ctx *ctx, double eps, double h, double theta, uint32_
 // gemm.cu — int8 tcgen05 path
 struct GemmInput {
     const uint64_t *row_ptr;   // CSR over n_loci loci
-    const uint16_t *gid_base;  // group << 2 | letter per entry
-    uint64_t n_loci, n_main;   // loci [0, n_main) are counted; loci >= n_main only through tail_loci
+    const uint16_t *gid_base;  // group << 2 | letter per entry (14-bit groups), or
+    const uint32_t *gid_base32; // the same with wide groups (exactly one of the two is set)
+    uint64_t n_loci, n_main;   // loci [0, n_main) are counted (main_loci != null: the loci main_loci[0 .. n_main)); other
+                               // loci only through tail_loci
+    const uint32_t *main_loci; // ascending list of the loci to count, or null
     uint64_t n_entries;
     const uint32_t *sp_bits;   // entries to leave out (staged from the special list instead)
     const uint32_t *gmap;      // group -> cell

@@ -309,6 +309,7 @@ __global__ void __launch_bounds__(TR_THREADS) finalize_kernel(TransformArgs a, c
 // ------------------------------------------------------------------------------------------------
 struct SlabArgs {
     const int32_t *peer[SGPU_MAX_PEERS];
+    const double *spill[SGPU_MAX_PEERS]; // fp64 spill planes of the GPUs (overlaps at >= 4 loci), null where there is none
     uint32_t n_peers;
     uint32_t n;
     uint64_t nn;
@@ -383,6 +384,11 @@ __global__ void __launch_bounds__(TR_THREADS) slab_raw_kernel(SlabArgs a, uint64
                     if (acc[PLANE_H3 + kk]) {
                         v += a.g3[kk] * acc[PLANE_H3 + kk];
                     }
+                }
+            }
+            for (uint32_t q = 0; q < a.n_peers; ++q) { // fixed order: every rank would add them in the same one
+                if (a.spill[q]) {
+                    v += a.spill[q][idx];
                 }
             }
             mn = fmin(mn, v);
@@ -628,19 +634,21 @@ int sgpu_epilogue(sgpu_ctx *ctx, sgpu_counts *c, uint32_t L, double eps, double 
 }
 
 // ---- multi-GPU epilogue over peer memory (see slab_raw_kernel) ---------------------------------------------------
-int sgpu_slab_raw_impl(sgpu_ctx *ctx, sgpu_counts *c, const int32_t *const *peer_planes, uint32_t n_peers, uint32_t slab,
-                       uint32_t n_slabs, uint32_t L, double eps, double h, double theta, double **d_extrema) {
+int sgpu_slab_raw_impl(sgpu_ctx *ctx, sgpu_counts *c, const int32_t *const *peer_planes, const double *const *peer_spill,
+                       uint32_t n_peers, uint32_t slab, uint32_t n_slabs, uint32_t L, double eps, double h, double theta,
+                       double **d_extrema) {
     cudaStream_t st = ctx->stream;
     if (n_peers == 0 || n_peers > SGPU_MAX_PEERS || n_slabs == 0 || slab >= n_slabs) {
         return sgpu_fail(ctx, SGPU_E_ARG, "slab epilogue: %u peers (1..%d), slab %u of %u", n_peers, SGPU_MAX_PEERS, slab, n_slabs);
     }
-    if (c->spill) {
-        return sgpu_fail(ctx, SGPU_E_ARG, "slab epilogue: read pairs overlapping at >= 4 loci (fp64 spill plane) need the reduce-to-one-rank route");
+    if (c->spill && !peer_spill) {
+        return sgpu_fail(ctx, SGPU_E_ARG, "slab epilogue: this GPU holds a spill plane (overlaps at >= 4 loci); pass the spill planes of all GPUs");
     }
     SGPU_TRY(ensure_ftable(ctx, L, eps, h, theta));
     SlabArgs a;
     for (uint32_t q = 0; q < SGPU_MAX_PEERS; ++q) {
         a.peer[q] = q < n_peers ? peer_planes[q] : nullptr;
+        a.spill[q] = (peer_spill && q < n_peers) ? peer_spill[q] : nullptr;
     }
     a.n_peers = n_peers;
     a.n = c->n;

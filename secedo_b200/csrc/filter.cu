@@ -103,13 +103,15 @@ constexpr int FILTER_THREADS = 256;
 // One WARP per locus (grid-stride over warps), 8 entries per 16-byte load and four loads in flight per lane (2 KB per
 // warp, 128 KB per SM): no CTA-wide barrier per locus, so the load latency of one locus is hidden by the other warps
 // (the CTA-per-locus version paid a barrier pair and an exposed load round trip per locus: 30 % of HBM).
+template <typename GB>
 __global__ void __launch_bounds__(FILTER_THREADS) filter_count_kernel(
-        const uint64_t *__restrict__ row_ptr, const uint16_t *__restrict__ gid_base, uint64_t n_loci,
+        const uint64_t *__restrict__ row_ptr, const GB *__restrict__ gid_base, uint64_t n_loci,
         const uint32_t *__restrict__ in_mask /* bit per group id */, uint32_t n_groups,
         uint4 *__restrict__ counts /* pooled A, C, G, T per locus */, int *__restrict__ err) {
-    __shared__ uint32_t s_mask[512]; // one bit per 14-bit group id
-    const uint32_t mask_words = (n_groups + 31) / 32;
-    for (uint32_t i = threadIdx.x; i < 512; i += blockDim.x) {
+    extern __shared__ uint32_t s_mask[]; // one bit per group id, at least 512 words (all 14-bit ids); bits behind n_groups are 0
+    constexpr int PER_VEC = 16 / sizeof(GB); // entries per 16-byte load
+    const uint32_t mask_words = (n_groups + 31) / 32, smem_words = max(512u, mask_words);
+    for (uint32_t i = threadIdx.x; i < smem_words; i += blockDim.x) {
         s_mask[i] = i < mask_words ? in_mask[i] : 0;
     }
     __syncthreads();
@@ -132,27 +134,37 @@ __global__ void __launch_bounds__(FILTER_THREADS) filter_count_kernel(
             since_flush = 0;
         };
         auto count = [&](uint32_t gb) {
-            const uint32_t gid = gb >> 2;
+            uint32_t gid = gb >> 2;
             max_gid = max(max_gid, gid);
-            // gid is 14 bits and the shared-memory mask covers all 16 384 of them (bits behind n_groups are 0)
+            if (sizeof(GB) == 4) {
+                gid = min(gid, smem_words * 32 - 1); // a wide id behind the mask is an error (reported below), not a fault
+            }
+            // 14-bit ids: the shared-memory mask covers all 16 384 of them
             const uint32_t in = (s_mask[gid >> 5] >> (gid & 31)) & 1u;
             packed += in << (8u * (gb & 3u));
         };
         auto count8 = [&](const uint4 &q) {
             const uint32_t w[4] = { q.x, q.y, q.z, q.w };
+            if (sizeof(GB) == 2) {
 #pragma unroll
-            for (int k = 0; k < 8; ++k) {
-                count((w[k >> 1] >> (16 * (k & 1))) & 0xFFFFu);
+                for (int k = 0; k < 8; ++k) {
+                    count((w[k >> 1] >> (16 * (k & 1))) & 0xFFFFu);
+                }
+            } else {
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    count(w[k]);
+                }
             }
         };
         // 16-byte aligned middle part (none if the caller's array itself is not aligned)
-        const uint64_t up = (e0 + 7) & ~static_cast<uint64_t>(7), down = e1 & ~static_cast<uint64_t>(7);
+        const uint64_t up = (e0 + PER_VEC - 1) & ~static_cast<uint64_t>(PER_VEC - 1), down = e1 & ~static_cast<uint64_t>(PER_VEC - 1);
         const uint64_t a0 = up < e1 ? up : e1, a1 = (aligned && down > a0) ? down : a0;
         for (uint64_t e = e0 + lane; e < a0; e += 32) { // < 8 entries
             count(gid_base[e]);
         }
         const uint4 *vec = reinterpret_cast<const uint4 *>(gid_base + a0);
-        const uint64_t nv = (a1 - a0) >> 3;
+        const uint64_t nv = (a1 - a0) / PER_VEC;
         for (uint64_t v = lane; v < nv; v += 128) {
             uint4 q[4];
 #pragma unroll
@@ -165,7 +177,7 @@ __global__ void __launch_bounds__(FILTER_THREADS) filter_count_kernel(
                     count8(q[u]);
                 }
             }
-            since_flush += 32;
+            since_flush += 4 * PER_VEC;
             if (since_flush > 200) {
                 flush();
             }
@@ -264,14 +276,15 @@ __global__ void __launch_bounds__(FILTER_THREADS) pull_read_ids_kernel(const uin
     }
 }
 
+template <typename GB>
 __global__ void __launch_bounds__(FILTER_THREADS) filter_compact_kernel(
         const uint64_t *__restrict__ row_ptr, const uint32_t *__restrict__ position,
-        const uint32_t *__restrict__ read_id, const uint16_t *__restrict__ gid_base, uint64_t n_loci,
+        const uint32_t *__restrict__ read_id, const GB *__restrict__ gid_base, uint64_t n_loci,
         const uint32_t *__restrict__ in_mask, uint32_t n_groups, const uint8_t *__restrict__ keep,
         const uint64_t *__restrict__ new_locus /* exclusive scan of keep */,
         const uint64_t *__restrict__ new_row /* exclusive scan of kept_cnt, n_loci + 1 */,
         uint64_t *__restrict__ out_row_ptr, uint32_t *__restrict__ out_position,
-        uint32_t *__restrict__ out_read_id, uint16_t *__restrict__ out_gid_base) {
+        uint32_t *__restrict__ out_read_id, GB *__restrict__ out_gid_base) {
     extern __shared__ uint32_t s_mask[];
     const uint32_t mask_words = (n_groups + 31) / 32;
     for (uint32_t i = threadIdx.x; i < mask_words; i += blockDim.x) {
@@ -310,7 +323,7 @@ __global__ void __launch_bounds__(FILTER_THREADS) filter_compact_kernel(
                 if (in[u]) {
                     const uint64_t dst = w + __popc(ballot & ((1u << lane) - 1u));
                     out_read_id[dst] = rid[u];
-                    out_gid_base[dst] = static_cast<uint16_t>(gb[u]);
+                    out_gid_base[dst] = static_cast<GB>(gb[u]);
                 }
                 w += __popc(ballot);
             }
@@ -383,12 +396,16 @@ int sgpu_filter_impl(sgpu_ctx *ctx, const sgpu_pileup *in, const uint32_t *h_id_
     // sub-cluster membership as a bit mask (id_to_pos[gid] != NO_POS, util/is_significant.cpp:169)
     const uint32_t mask_words = (n_groups + 31) / 32;
     std::vector<uint32_t> h_mask(mask_words ? mask_words : 1, 0);
+    const uint32_t no_pos = in->wide ? SGPU_NO_POS_WIDE : SGPU_NO_POS;
+    if (!in->wide && n_groups > 16384) {
+        return sgpu_fail(ctx, SGPU_E_ARG, "more than 16 384 groups need a wide pileup (sgpu_pileup_upload_wide)");
+    }
     for (uint32_t g = 0; g < n_groups; ++g) {
-        if (h_id_to_pos[g] != SGPU_NO_POS) {
+        if (h_id_to_pos[g] != no_pos) {
             h_mask[g >> 5] |= 1u << (g & 31);
         }
     }
-    const size_t smem = h_mask.size() * sizeof(uint32_t);
+    const size_t smem = std::max<size_t>(512, h_mask.size()) * sizeof(uint32_t);
     if (smem > 200 * 1024) {
         return sgpu_fail(ctx, SGPU_E_ARG, "n_groups too large for the shared-memory membership mask");
     }
@@ -406,21 +423,21 @@ int sgpu_filter_impl(sgpu_ctx *ctx, const sgpu_pileup *in, const uint32_t *h_id_
     SGPU_CUDA(ctx, d_new_row.alloc(P + 1, ctx));
     SGPU_CUDA(ctx, d_err.alloc(1, ctx));
     SGPU_CUDA(ctx, cudaMemsetAsync(d_err.p, 0, sizeof(int), st));
-    SGPU_CUDA(ctx, cudaMemcpyAsync(d_mask.p, h_mask.data(), smem, cudaMemcpyHostToDevice, st));
+    SGPU_CUDA(ctx, cudaMemcpyAsync(d_mask.p, h_mask.data(), h_mask.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
 
     const FilterParams fp = make_params(theta, cell_proportion);
     const unsigned grid = static_cast<unsigned>(std::min<uint64_t>(ceil_div_u64(P ? P : 1, FILTER_THREADS / 32),
                                                                   static_cast<uint64_t>(ctx->sm_count) * 32));
     if (smem > 48 * 1024) {
-        SGPU_CUDA(ctx, cudaFuncSetAttribute(filter_count_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        SGPU_CUDA(ctx, cudaFuncSetAttribute(filter_compact_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        SGPU_GB(in, (void)gid_base_; SGPU_CUDA(ctx, cudaFuncSetAttribute(filter_count_kernel<GB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                SGPU_CUDA(ctx, cudaFuncSetAttribute(filter_compact_kernel<GB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)));
     }
     if (P) {
         const unsigned cgrid = static_cast<unsigned>(std::min<uint64_t>(ceil_div_u64(P, FILTER_THREADS / 32), static_cast<uint64_t>(ctx->sm_count) * 8));
         DevBuf<uint4> d_counts;
         SGPU_CUDA(ctx, d_counts.alloc(P, ctx));
-        SGPU_LAUNCH(ctx, (filter_count_kernel<<<cgrid, FILTER_THREADS, smem, st>>>(in->d_row_ptr, in->d_gid_base, P, d_mask.p, n_groups,
-                                                                                   d_counts.p, d_err.p)));
+        SGPU_GB(in, SGPU_LAUNCH(ctx, (filter_count_kernel<GB><<<cgrid, FILTER_THREADS, smem, st>>>(in->d_row_ptr, gid_base_, P, d_mask.p, n_groups,
+                                                                                               d_counts.p, d_err.p))));
         SGPU_LAUNCH(ctx, (filter_decide_kernel<<<static_cast<unsigned>(ceil_div_u64(P, FILTER_THREADS)), FILTER_THREADS, 0, st>>>(
                                  d_counts.p, P, fp, d_keep.p, d_cnt.p, d_maxk.p)));
         SGPU_CUDA(ctx, cudaGetLastError());
@@ -444,12 +461,17 @@ int sgpu_filter_impl(sgpu_ctx *ctx, const sgpu_pileup *in, const uint32_t *h_id_
     out->n_entries = Ek;
     out->max_row = static_cast<uint32_t>(ctx->h_scratch[3] & 0xFFFFFFFFu); // read linking sizes its table by it
     out->owns = true;
+    out->wide = in->wide;
     out->h_chr_ptr = new uint64_t[in->n_chr + 1];
     SGPU_CUDA(ctx, sgpu_dev_alloc(ctx, reinterpret_cast<void **>(&out->d_chr_ptr), (in->n_chr + 1) * sizeof(uint64_t)));
     SGPU_CUDA(ctx, sgpu_dev_alloc(ctx, reinterpret_cast<void **>(&out->d_row_ptr), (Lk + 1) * sizeof(uint64_t)));
     SGPU_CUDA(ctx, sgpu_dev_alloc(ctx, reinterpret_cast<void **>(&out->d_position), (Lk ? Lk : 1) * sizeof(uint32_t)));
     SGPU_CUDA(ctx, sgpu_dev_alloc(ctx, reinterpret_cast<void **>(&out->d_read_id), (Ek ? Ek : 1) * sizeof(uint32_t)));
-    SGPU_CUDA(ctx, sgpu_dev_alloc(ctx, reinterpret_cast<void **>(&out->d_gid_base), (Ek ? Ek : 1) * sizeof(uint16_t)));
+    if (in->wide) {
+        SGPU_CUDA(ctx, sgpu_dev_alloc(ctx, reinterpret_cast<void **>(&out->d_gid_base32), (Ek ? Ek : 1) * sizeof(uint32_t)));
+    } else {
+        SGPU_CUDA(ctx, sgpu_dev_alloc(ctx, reinterpret_cast<void **>(&out->d_gid_base), (Ek ? Ek : 1) * sizeof(uint16_t)));
+    }
     if (P) {
         // lazily uploaded pileup: the read ids of the KEPT loci are pulled straight from pinned host memory (the
         // rejected loci's never cross PCIe)
@@ -460,10 +482,11 @@ int sgpu_filter_impl(sgpu_ctx *ctx, const sgpu_pileup *in, const uint32_t *h_id_
             SGPU_LAUNCH(ctx, (pull_read_ids_kernel<<<grid, FILTER_THREADS, 0, st>>>(in->d_row_ptr, P, d_keep.p, in->zc_read_id, pulled.p)));
             rid_src = pulled.p;
         }
-        SGPU_LAUNCH(ctx, (filter_compact_kernel<<<grid, FILTER_THREADS, smem, st>>>(in->d_row_ptr, in->d_position, rid_src, in->d_gid_base,
-                                                                 P, d_mask.p, n_groups, d_keep.p, d_new_locus.p, d_new_row.p,
-                                                                 out->d_row_ptr, out->d_position, out->d_read_id,
-                                                                 out->d_gid_base)));
+        SGPU_GB(in, SGPU_LAUNCH(ctx, (filter_compact_kernel<GB><<<grid, FILTER_THREADS, mask_words * sizeof(uint32_t), st>>>(
+                                in->d_row_ptr, in->d_position, rid_src, gid_base_, P, d_mask.p, n_groups, d_keep.p, d_new_locus.p,
+                                d_new_row.p, out->d_row_ptr, out->d_position, out->d_read_id,
+                                const_cast<GB *>(in->wide ? reinterpret_cast<const GB *>(out->d_gid_base32)
+                                                          : reinterpret_cast<const GB *>(out->d_gid_base))))));
     }
     SGPU_LAUNCH(ctx, (remap_chr_ptr_kernel<<<(in->n_chr + 256) / 256, 256, 0, st>>>(in->d_chr_ptr, in->n_chr, d_new_locus.p, out->d_chr_ptr,
                                                                  out->d_row_ptr, d_new_row.p, P)));

@@ -25,6 +25,7 @@
 
 #include <algorithm>
 #include <cstdlib>
+#include <type_traits>
 #include <vector>
 
 namespace {
@@ -90,16 +91,18 @@ constexpr uint32_t CB_SKIP = 0xFFFFu;   // cellbase of an entry the dense scan d
 // the last stripe (the special entries, staged from their own list, are left out). A staging CTA then reads
 // exactly the entries of its stripe. One CTA per locus: count per stripe, scan, scatter (order inside a
 // stripe does not matter).
+template <typename GB>
 struct PartitionArgs {
     const uint64_t *row_ptr;
-    const uint16_t *gid_base;
+    const GB *gid_base;
     const uint32_t *sp_bits;
     const uint32_t *gmap;
     uint32_t n_groups, n_cells;
     uint64_t n_loci;
     uint32_t n_stripes;
-    uint32_t stripe_magic; // cell / cells_per_cta = (cell * magic) >> 32, exact for 14-bit cells
-    uint16_t *cellbase;
+    uint32_t stripe_magic; // cell / cells_per_cta = (cell * magic) >> 32, exact for cells < 65 536
+    uint32_t cells_per_cta;
+    uint16_t *cellbase;    // (cell - first cell of its stripe) << 2 | base: fits 16 bits for any number of cells
     uint32_t *seg;
     int *err;
 };
@@ -111,7 +114,9 @@ constexpr uint32_t PART_CACHE = PART_ROUNDS * 2048 - 8;  // entries of a locus h
 // Gathers from the group map and scattered 2-byte stores cost one L1 wavefront per lane when they go to
 // global memory; both are done in shared memory here (the map is copied once per CTA, the partitioned
 // locus is assembled in shared memory and written out contiguously).
-__global__ void __launch_bounds__(256) partition_kernel(const PartitionArgs a) {
+template <typename GB>
+__global__ void __launch_bounds__(256) partition_kernel(const PartitionArgs<GB> a) {
+    constexpr int PER_VEC = 16 / sizeof(GB); // entries per 16-byte load: 8 (two loads of 4 for wide entries)
     extern __shared__ __align__(16) uint16_t s_dyn[];
     __shared__ uint32_t s_cnt[ST_MAX_STRIPES + 1]; // entries of the stripe seen so far / start of the stripe
     uint16_t *s_out = s_dyn;                       // [PART_OUT] the partitioned locus
@@ -122,9 +127,9 @@ __global__ void __launch_bounds__(256) partition_kernel(const PartitionArgs a) {
         s_map[g] = static_cast<uint16_t>(c < a.n_cells ? c : 0xFFFFu);
     }
     __syncthreads();
-    // value of entry e (CB_SKIP = left out)
+    // stripe << 16 | value of entry e (value = cell inside its stripe << 2 | base); 0xFFFFFFFF = left out
     auto classify = [&](uint64_t e) -> uint32_t {
-        uint32_t v = CB_SKIP;
+        uint32_t v = 0xFFFFFFFFu;
         const uint32_t gb = a.gid_base[e];
         if (!((a.sp_bits[e >> 5] >> (e & 31)) & 1u)) {
             const uint32_t gid = gb >> 2;
@@ -132,7 +137,8 @@ __global__ void __launch_bounds__(256) partition_kernel(const PartitionArgs a) {
             if (gid >= a.n_groups || (cell = s_map[gid]) == 0xFFFFu) {
                 atomicExch(a.err, SGPU_E_CELL_RANGE);
             } else {
-                v = (cell << 2) | (gb & 3u);
+                const uint32_t stripe = __umulhi(cell, a.stripe_magic);
+                v = (stripe << 16) | ((cell - stripe * a.cells_per_cta) << 2) | (gb & 3u);
             }
         }
         return v;
@@ -153,18 +159,21 @@ __global__ void __launch_bounds__(256) partition_kernel(const PartitionArgs a) {
             // window covers the locus; entries outside it are masked)
             const uint64_t e1 = e0 + n, base = e0 & ~7ull;
             const bool vec_ok = (reinterpret_cast<uintptr_t>(a.gid_base) & 15u) == 0;
-            uint32_t vr[PART_ROUNDS][8]; // value << 16 | rank inside the stripe; CB_SKIP << 16 = left out
+            uint32_t vr[PART_ROUNDS][8]; // stripe << 24 | value << 13 | rank inside the stripe; 0xFFFFFFFF = left out
 #pragma unroll
             for (int it = 0; it < PART_ROUNDS; ++it) {
                 const uint64_t v0 = base + 8ull * threadIdx.x + static_cast<uint64_t>(it) * (8 * 256);
 #pragma unroll
                 for (int k = 0; k < 8; ++k) {
-                    vr[it][k] = CB_SKIP << 16;
+                    vr[it][k] = 0xFFFFFFFFu;
                 }
                 if (v0 < e1) {
-                    __align__(16) uint16_t gb[8];
+                    __align__(16) GB gb[8];
                     if (vec_ok && v0 >= e0 && v0 + 8 <= e1) {
-                        *reinterpret_cast<uint4 *>(gb) = *reinterpret_cast<const uint4 *>(a.gid_base + v0);
+#pragma unroll
+                        for (int q = 0; q < 8 / PER_VEC; ++q) {
+                            reinterpret_cast<uint4 *>(gb)[q] = reinterpret_cast<const uint4 *>(a.gid_base + v0)[q];
+                        }
                     } else {
 #pragma unroll
                         for (int k = 0; k < 8; ++k) {
@@ -183,8 +192,9 @@ __global__ void __launch_bounds__(256) partition_kernel(const PartitionArgs a) {
                         if (gid >= a.n_groups || (cell = s_map[gid]) == 0xFFFFu) {
                             atomicExch(a.err, SGPU_E_CELL_RANGE);
                         } else {
-                            const uint32_t v = (cell << 2) | (gb[k] & 3u);
-                            vr[it][k] = (v << 16) | atomicAdd(&s_cnt[__umulhi(cell, a.stripe_magic)], 1u);
+                            const uint32_t stripe = __umulhi(cell, a.stripe_magic);
+                            const uint32_t v = ((cell - stripe * a.cells_per_cta) << 2) | (gb[k] & 3u);
+                            vr[it][k] = (stripe << 24) | (v << 13) | atomicAdd(&s_cnt[stripe], 1u);
                         }
                     }
                 }
@@ -224,9 +234,9 @@ __global__ void __launch_bounds__(256) partition_kernel(const PartitionArgs a) {
             for (int it = 0; it < PART_ROUNDS; ++it) {
 #pragma unroll
                 for (int k = 0; k < 8; ++k) {
-                    const uint32_t v = vr[it][k] >> 16;
-                    if (v != CB_SKIP) {
-                        s_out[shift + s_cnt[__umulhi(v >> 2, a.stripe_magic)] + (vr[it][k] & 0xFFFFu)] = static_cast<uint16_t>(v);
+                    const uint32_t x = vr[it][k];
+                    if (x != 0xFFFFFFFFu) {
+                        s_out[shift + s_cnt[x >> 24] + (x & 0x1FFFu)] = static_cast<uint16_t>((x >> 13) & 0x7FFu);
                     }
                 }
             }
@@ -261,8 +271,8 @@ __global__ void __launch_bounds__(256) partition_kernel(const PartitionArgs a) {
             __syncthreads();
             for (uint32_t i = threadIdx.x; i < n; i += 256) {
                 const uint32_t v = classify(e0 + i);
-                if (v != CB_SKIP) {
-                    atomicAdd(&s_cnt[__umulhi(v >> 2, a.stripe_magic)], 1u);
+                if (v != 0xFFFFFFFFu) {
+                    atomicAdd(&s_cnt[v >> 16], 1u);
                 }
             }
             __syncthreads();
@@ -279,8 +289,8 @@ __global__ void __launch_bounds__(256) partition_kernel(const PartitionArgs a) {
             __syncthreads();
             for (uint32_t i = threadIdx.x; i < n; i += 256) {
                 const uint32_t v = classify(e0 + i);
-                if (v != CB_SKIP) {
-                    a.cellbase[e0 + atomicAdd(&s_cnt[__umulhi(v >> 2, a.stripe_magic)], 1u)] = static_cast<uint16_t>(v);
+                if (v != 0xFFFFFFFFu) {
+                    a.cellbase[e0 + atomicAdd(&s_cnt[v >> 16], 1u)] = static_cast<uint16_t>(v & 0xFFFFu);
                 }
             }
             __syncthreads();
@@ -296,7 +306,8 @@ struct StageArgs {
     const uint32_t *sp_locus;
     const uint32_t *sp_start;  // per locus: first special entry of the locus (n_loci + 1 values)
     uint32_t n_pad;
-    uint32_t l0, nl;           // main k-blocks: loci [l0, l0 + nl), 32 per k-block
+    uint32_t l0, nl;           // main k-blocks: loci [l0, l0 + nl) (of main_loci, if given), 32 per k-block
+    const uint32_t *main_loci; // ranged accumulation: the owned loci (ascending), or null = all loci
     uint32_t kbs_main;
     const uint32_t *tail_loci; // tail k-blocks: loci tail_loci[0 .. n_tail), ascending
     uint32_t n_tail, kbs_tail; // Z goes to k-block kbs_main + t, -Z to kbs_main + kbs_tail + t
@@ -338,7 +349,7 @@ __global__ void __launch_bounds__(ST_THREADS, 4) stage_tile_kernel(const StageAr
         if (!tail) {
             const uint32_t col = kb * LOCI_PER_KB + j;
             if (col < a.nl) {
-                l = a.l0 + col;
+                l = a.main_loci ? a.main_loci[a.l0 + col] : a.l0 + col;
             }
         } else {
             const uint32_t t = (kb - a.kbs_main) * LOCI_PER_KB + j;
@@ -383,7 +394,7 @@ __global__ void __launch_bounds__(ST_THREADS, 4) stage_tile_kernel(const StageAr
             }
 #pragma unroll
             for (int u = 0; u < 8; ++u) {
-                const uint32_t r = (cb[u] >> 2) - c0;
+                const uint32_t r = cb[u] >> 2; // cell inside this stripe
                 if (cb[u] != CB_SKIP && r < nc) {
                     tile_add(tile, r, j, cb[u] & 3u);
                     ++n_added;
@@ -395,8 +406,20 @@ __global__ void __launch_bounds__(ST_THREADS, 4) stage_tile_kernel(const StageAr
     if (!tail) {
         // consecutive loci: their special entries are one contiguous range of the (ascending) list
         const uint32_t l_first = s_loc[0];
-        if (l_first != 0xFFFFFFFFu) {
-            const uint32_t n_valid = min(32u, a.nl - kb * LOCI_PER_KB);
+        const uint32_t n_valid = l_first != 0xFFFFFFFFu ? min(32u, a.nl - kb * LOCI_PER_KB) : 0;
+        if (n_valid && s_loc[n_valid - 1] - l_first != n_valid - 1) {
+            // a list of owned loci with a gap inside this k-block (the border between two chromosomes' ranges): locus by locus
+            for (uint32_t j = 0; j < n_valid; ++j) {
+                for (uint32_t s = s_sp0[j] + threadIdx.x; s < s_sp1[j]; s += ST_THREADS) {
+                    const uint32_t c = a.sp_code[s];
+                    const uint32_t r = code_cell(c) - c0;
+                    if (c != CODE_DROPPED && r < nc) {
+                        tile_add(tile, r, j, code_base(c));
+                        ++n_added;
+                    }
+                }
+            }
+        } else if (n_valid) {
             const uint32_t sp1 = s_sp1[n_valid - 1];
             for (uint32_t s = s_sp0[0] + threadIdx.x; s < sp1; s += ST_THREADS) {
                 const uint32_t c = a.sp_code[s];
@@ -1083,9 +1106,11 @@ int sgpu_gemm_counts(sgpu_ctx *ctx, const sgpu_pileup *p, const LinkResult &lr, 
     }
     GemmInput in;
     in.row_ptr = p->d_row_ptr;
-    in.gid_base = p->d_gid_base;
+    in.gid_base = p->wide ? nullptr : p->d_gid_base;
+    in.gid_base32 = p->wide ? p->d_gid_base32 : nullptr;
     in.n_loci = p->n_loci;
-    in.n_main = p->n_loci;
+    in.n_main = lr.ranged ? lr.n_own : p->n_loci;
+    in.main_loci = lr.ranged ? lr.own_loci.p : nullptr;
     in.n_entries = p->n_entries;
     in.sp_bits = lr.sp_bits.p;
     in.gmap = lr.gmap.p;
@@ -1108,8 +1133,8 @@ int sgpu_gemm_run(sgpu_ctx *ctx, const GemmInput &in, uint32_t N, int32_t *S_pla
     if (P == 0 || in.n_entries == 0 || N < 2) {
         return SGPU_OK;
     }
-    if (N > 16383) { // (cell << 2 | base) must fit 16 bits; the reference's PosData holds 14-bit group ids
-        return sgpu_fail(ctx, SGPU_E_ARG, "the GEMM path supports at most 16383 cells");
+    if (N > ST_MAX_STRIPES * (ST_MAX_CELLS & ~3u) - 256) { // stripes of the staging tiles; cells are 16-bit in the partition's group map
+        return sgpu_fail(ctx, SGPU_E_ARG, "the GEMM path supports at most %u cells", ST_MAX_STRIPES * (ST_MAX_CELLS & ~3u) - 256);
     }
     const uint32_t n_pad = (N + BN - 1) / BN * BN;
     // the tail k-blocks (Z and -Z) ride along with the first panel
@@ -1207,23 +1232,32 @@ int sgpu_gemm_run(sgpu_ctx *ctx, const GemmInput &in, uint32_t N, int32_t *S_pla
     SGPU_CUDA(ctx, seg.alloc(in.n_loci * (n_stripes + 1), ctx));
     mark(); // folded into the first panel's staging time
     {
-        PartitionArgs pa;
-        pa.row_ptr = in.row_ptr;
-        pa.gid_base = in.gid_base;
-        pa.sp_bits = in.sp_bits;
-        pa.gmap = in.gmap;
-        pa.n_groups = in.n_groups;
-        pa.n_cells = N;
-        pa.n_loci = in.n_loci;
-        pa.n_stripes = n_stripes;
-        pa.stripe_magic = static_cast<uint32_t>(((1ull << 32) + cells_per_cta - 1) / cells_per_cta);
-        pa.cellbase = cellbase.p;
-        pa.seg = seg.p;
-        pa.err = d_err.p;
         const unsigned grid = static_cast<unsigned>(std::min<uint64_t>(in.n_loci, static_cast<uint64_t>(sms) * 16));
         const size_t psmem = (static_cast<size_t>(PART_OUT) + in.n_groups) * sizeof(uint16_t);
-        SGPU_CUDA(ctx, cudaFuncSetAttribute(partition_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(psmem)));
-        SGPU_LAUNCH(ctx, (partition_kernel<<<grid, 256, psmem, st>>>(pa)));
+        if (psmem > 200 * 1024) {
+            return sgpu_fail(ctx, SGPU_E_ARG, "too many groups (%u) for the shared-memory group map of the GEMM path", in.n_groups);
+        }
+        auto run_partition = [&](auto *gid_base) -> int {
+            using GB = std::remove_const_t<std::remove_pointer_t<decltype(gid_base)>>;
+            PartitionArgs<GB> pa;
+            pa.row_ptr = in.row_ptr;
+            pa.gid_base = gid_base;
+            pa.sp_bits = in.sp_bits;
+            pa.gmap = in.gmap;
+            pa.n_groups = in.n_groups;
+            pa.n_cells = N;
+            pa.n_loci = in.n_loci;
+            pa.n_stripes = n_stripes;
+            pa.stripe_magic = static_cast<uint32_t>(((1ull << 32) + cells_per_cta - 1) / cells_per_cta);
+            pa.cells_per_cta = cells_per_cta;
+            pa.cellbase = cellbase.p;
+            pa.seg = seg.p;
+            pa.err = d_err.p;
+            SGPU_CUDA(ctx, cudaFuncSetAttribute(partition_kernel<GB>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(psmem)));
+            SGPU_LAUNCH(ctx, (partition_kernel<GB><<<grid, 256, psmem, st>>>(pa)));
+            return SGPU_OK;
+        };
+        SGPU_TRY(in.gid_base32 ? run_partition(in.gid_base32) : run_partition(in.gid_base));
     }
 
     bool first = true;
@@ -1245,6 +1279,7 @@ int sgpu_gemm_run(sgpu_ctx *ctx, const GemmInput &in, uint32_t N, int32_t *S_pla
         sa.sp_start = in.sp_start;
         sa.l0 = static_cast<uint32_t>(l0);
         sa.nl = static_cast<uint32_t>(nl);
+        sa.main_loci = in.main_loci;
         sa.kbs_main = kbs_main;
         sa.tail_loci = in.tail_loci;
         sa.n_tail = kt ? static_cast<uint32_t>(in.n_tail_loci) : 0;

@@ -50,6 +50,7 @@ struct MultiArgs {
     unsigned int *max_order;
     unsigned long long *n_pairs;
     int *err;
+    const uint8_t *owned;     // ranged accumulation: a pair is recorded by the piece that owns its first common locus (null = all)
 };
 
 __global__ void __launch_bounds__(TB) multilocus_kernel(MultiArgs a) {
@@ -70,7 +71,7 @@ __global__ void __launch_bounds__(TB) multilocus_kernel(MultiArgs a) {
     __syncthreads();
     unsigned long long local_pairs = 0;
     unsigned int local_max = 0;
-    if (ia < n_me) {
+    if (ia < n_me && (a.owned == nullptr || a.owned[a.me_locus[ia]])) {
         const uint32_t loc = a.me_locus[ia];
         const uint32_t ca = a.me_code[ia];
         const uint32_t a0 = a.me_beg[ia], ap = a.me_pos[ia], a1 = a.me_end[ia];
@@ -199,6 +200,7 @@ struct PairArgs {
     const uint32_t *g_list;   // stored loci
     const uint8_t *g_base;
     const uint32_t *g_nst;
+    const uint8_t *owned;     // ranged accumulation: the locus pair (l1, l2) belongs to the piece that owns l1 (null = all)
     unsigned long long *occ;  // per locus l1: bit d set = some read covers (l1, l1 + d + 1)
     const uint64_t *pair_base; // per locus: number of locus pairs before it (scan of popc(occ))
     uint64_t n_pairs;         // locus pairs
@@ -209,7 +211,7 @@ struct PairArgs {
     uint64_t n_z;
     uint32_t *cntA, *cntB;     // entries per pseudo-locus
     const uint64_t *rowA, *rowB;
-    uint16_t *gbA, *gbB;       // cell << 2 | letter
+    uint32_t *gbA, *gbB;       // cell << 2 | letter
     int *err;
 };
 
@@ -225,6 +227,9 @@ __global__ void __launch_bounds__(TB) pair_occ_kernel(PairArgs a) {
     const uint64_t o = a.g_off[h];
     const uint32_t n = a.g_nst[h];
     for (uint32_t p = 0; p + 1 < n; ++p) {
+        if (a.owned && !a.owned[a.g_list[o + p]]) {
+            continue;
+        }
         for (uint32_t q = p + 1; q < n; ++q) {
             const uint32_t d = a.g_list[o + q] - a.g_list[o + p] - 1;
             if (d >= 64) {
@@ -258,6 +263,9 @@ __global__ void __launch_bounds__(TB) pair_emit_kernel(PairArgs a) {
     const bool tail = (rc >> 1) & 1u;
     for (uint32_t p = 0; p + 1 < n; ++p) {
         const uint32_t l1 = a.g_list[o + p], b1 = a.g_base[o + p];
+        if (a.owned && !a.owned[l1]) {
+            continue;
+        }
         const unsigned long long occ = a.occ[l1];
         for (uint32_t q = p + 1; q < n; ++q) {
             const uint32_t d = a.g_list[o + q] - l1 - 1, b2 = a.g_base[o + q];
@@ -274,8 +282,8 @@ __global__ void __launch_bounds__(TB) pair_emit_kernel(PairArgs a) {
             for (int k = 0; k < n_out; ++k) {
                 const uint32_t ka = atomicAdd(&a.cntA[plA[k]], 1u), kb = atomicAdd(&a.cntB[plB[k]], 1u);
                 if (FILL) {
-                    a.gbA[a.rowA[plA[k]] + ka] = static_cast<uint16_t>((cell << 2) | b2);
-                    a.gbB[a.rowB[plB[k]] + kb] = static_cast<uint16_t>((cell << 2) | b2);
+                    a.gbA[a.rowA[plA[k]] + ka] = (cell << 2) | b2;
+                    a.gbB[a.rowB[plB[k]] + kb] = (cell << 2) | b2;
                 }
             }
         }
@@ -289,7 +297,7 @@ template <bool FILL>
 __global__ void __launch_bounds__(TB) pair_emit2_kernel(PairArgs a) {
     const uint64_t h = static_cast<uint64_t>(blockIdx.x) * TB + threadIdx.x;
     const uint32_t lane = threadIdx.x & 31;
-    const bool on = pair_head(a, h) && a.g_nst[h] == 2;
+    const bool on = pair_head(a, h) && a.g_nst[h] == 2 && (a.owned == nullptr || a.owned[a.g_list[a.g_off[h]]]);
     uint64_t plA = ~0ull, plB = ~0ull, zA = ~0ull, zB = ~0ull;
     uint32_t val = 0;
     if (on) {
@@ -321,11 +329,11 @@ __global__ void __launch_bounds__(TB) pair_emit2_kernel(PairArgs a) {
     const uint32_t ka = reserve(a.cntA, plA), kb = reserve(a.cntB, plB);
     const uint32_t kza = reserve(a.cntA, zA), kzb = reserve(a.cntB, zB);
     if (FILL && on) {
-        a.gbA[a.rowA[plA] + ka] = static_cast<uint16_t>(val);
-        a.gbB[a.rowB[plB] + kb] = static_cast<uint16_t>(val);
+        a.gbA[a.rowA[plA] + ka] = val;
+        a.gbB[a.rowB[plB] + kb] = val;
         if (zA != ~0ull) {
-            a.gbA[a.rowA[zA] + kza] = static_cast<uint16_t>(val);
-            a.gbB[a.rowB[zB] + kzb] = static_cast<uint16_t>(val);
+            a.gbA[a.rowA[zA] + kza] = val;
+            a.gbB[a.rowB[zB] + kzb] = val;
         }
     }
 }
@@ -415,6 +423,7 @@ static int second_order_gemm(sgpu_ctx *ctx, const sgpu_pileup *p, LinkResult &lr
     a.g_list = lr.g_list.p;
     a.g_base = lr.g_base.p;
     a.g_nst = lr.g_nst.p;
+    a.owned = lr.ranged ? lr.owned.p : nullptr;
     a.occ = occ.p;
     a.lchr = lr.lchr.p;
     a.err = d_err.p;
@@ -482,7 +491,7 @@ static int second_order_gemm(sgpu_ctx *ctx, const sgpu_pileup *p, LinkResult &lr
     if (EA >= 0x7FFFFFF0ull) {
         return 1;
     }
-    DevBuf<uint16_t> gbA, gbB;
+    DevBuf<uint32_t> gbA, gbB;
     DevBuf<uint32_t> zero_bits, zero_start, ident, tailA, tailB;
     DevBuf<int32_t> tmp;
     SGPU_CUDA(ctx, gbA.alloc(EA + 8, ctx));
@@ -513,9 +522,11 @@ static int second_order_gemm(sgpu_ctx *ctx, const sgpu_pileup *p, LinkResult &lr
     for (int run = 0; run < 2; ++run) {
         GemmInput in;
         in.row_ptr = run ? rowB.p : rowA.p;
-        in.gid_base = run ? gbB.p : gbA.p;
+        in.gid_base = nullptr;
+        in.gid_base32 = run ? gbB.p : gbA.p;
         in.n_loci = run ? RB : RA;
         in.n_main = run ? NP : 4 * NP;
+        in.main_loci = nullptr;
         in.n_entries = EA;
         in.sp_bits = zero_bits.p;
         in.gmap = ident.p;
@@ -613,6 +624,7 @@ int sgpu_multilocus(sgpu_ctx *ctx, const sgpu_pileup *p, LinkResult &lr, sgpu_co
     a.max_order = d_max.p;
     a.n_pairs = d_np.p;
     a.err = d_err.p;
+    a.owned = lr.ranged ? lr.owned.p : nullptr;
     SGPU_TRACE(ctx, "multi: before enumeration");
     SGPU_LAUNCH(ctx, (multilocus_kernel<<<blocks_for(NS), TB, 0, st>>>(a)));
     SGPU_CUDA(ctx, cudaGetLastError());

@@ -573,15 +573,60 @@ __global__ void __launch_bounds__(TB) nonfirst_kernel(const uint32_t *__restrict
     }
 }
 
+// A read id chained over >= L bp (e.g. a long-insert pair whose mates, and a locus in between, all fall on kept loci):
+// the reference retires a read once start + L <= position and makes a NEW read of the next entry with that id
+// (similarity_matrix.cpp:348-372, 379-382; exactly so whenever the batch fires at every locus, i.e. on any pileup with
+// >= 4 * num_threads new reads per locus; on sparser ones its outcome depends on batch timing). One thread per read:
+// sort the entries, walk them, and re-root every entry that lies >= L bp behind the start of its segment to the entry
+// that opens the next segment. sp_first holds ENTRY indices.
+__global__ void __launch_bounds__(TB) split_span_kernel(const uint32_t *__restrict__ sp_head, const uint32_t *__restrict__ sp_entry,
+                                                        const uint32_t *__restrict__ sp_locus, const uint64_t *__restrict__ g_off,
+                                                        uint64_t n_special, uint32_t *__restrict__ g_list /* sids of the read */,
+                                                        const uint32_t *__restrict__ position, uint32_t L,
+                                                        uint32_t *__restrict__ sp_first, unsigned long long *__restrict__ n_splits) {
+    const uint64_t h = static_cast<uint64_t>(blockIdx.x) * TB + threadIdx.x;
+    if (h >= n_special || sp_head[h] != h) {
+        return;
+    }
+    const uint64_t o = g_off[h];
+    const uint32_t n = static_cast<uint32_t>(g_off[h + 1] - o);
+    uint32_t *lst = g_list + o;
+    for (uint32_t i = 1; i < n; ++i) { // insertion sort, n is tiny
+        const uint32_t v = lst[i];
+        uint32_t j = i;
+        while (j > 0 && lst[j - 1] > v) {
+            lst[j] = lst[j - 1];
+            --j;
+        }
+        lst[j] = v;
+    }
+    uint32_t seg = lst[0], splits = 0;
+    uint32_t seg_pos = position[sp_locus[seg]];
+    for (uint32_t i = 1; i < n; ++i) {
+        const uint32_t s = lst[i];
+        const uint32_t pos = position[sp_locus[s]];
+        if (pos - seg_pos >= L) {
+            seg = s;
+            seg_pos = pos;
+            ++splits;
+        }
+        sp_first[s] = sp_entry[seg];
+    }
+    if (splits) {
+        atomicAdd(n_splits, static_cast<unsigned long long>(splits));
+    }
+}
+
 // One thread per read with >= 2 entries: sort its entries (entry order = the order in which the
 // reference meets them), replay the insertion rules (similarity_matrix.cpp:383-402) and leave the
 // stored (locus, base) list in place. g_nst[head] = number of loci the read keeps.
+template <typename GB>
 __global__ void __launch_bounds__(TB) mate_rule_kernel(const uint32_t *__restrict__ sp_head,
                                                        const uint32_t *__restrict__ sp_entry,
                                                        const uint32_t *__restrict__ sp_locus,
                                                        const uint64_t *__restrict__ g_off, uint64_t n_special,
                                                        uint32_t *__restrict__ g_list /* in: sids, out: stored loci */,
-                                                       uint8_t *__restrict__ g_base, const uint16_t *__restrict__ gid_base,
+                                                       uint8_t *__restrict__ g_base, const GB *__restrict__ gid_base,
                                                        const uint32_t *__restrict__ position, uint32_t L,
                                                        uint8_t *__restrict__ sp_drop, uint32_t *__restrict__ g_nst,
                                                        int *__restrict__ err) {
@@ -671,11 +716,17 @@ __device__ __forceinline__ uint64_t completed_at(const uint32_t *__restrict__ po
     return readbase[lo] - rb0; // reads with start + L <= p, all created before locus l
 }
 
+// exact_from (may be null): per chromosome the first locus from which the numbers of reads created per locus are exact
+// (a SUFFIX of a chromosome: the loci within L bp of its first locus may continue reads that started before it). Only
+// a sure trigger whose inputs are all exact may then anchor the replay; if there is none, resolved[c] = 0 and the
+// caller has to come back with a longer suffix.
 __global__ void __launch_bounds__(CUT_THREADS) cutoff_kernel(const uint64_t *__restrict__ chr_ptr, uint32_t n_chr,
                                                              const uint32_t *__restrict__ position,
                                                              const uint64_t *__restrict__ readbase, uint32_t L,
                                                              uint32_t num_threads, uint64_t *__restrict__ n_tail_reads,
-                                                             uint64_t *__restrict__ tail_locus) {
+                                                             uint64_t *__restrict__ tail_locus,
+                                                             const uint64_t *__restrict__ exact_from = nullptr,
+                                                             uint8_t *__restrict__ resolved = nullptr) {
     __shared__ uint64_t s_u[CUT_CHUNK + 1];
     __shared__ uint32_t s_j[CUT_CHUNK + 1];
     __shared__ unsigned long long s_sure; // 1 + last locus that fires for sure, 0 = none found yet
@@ -686,6 +737,7 @@ __global__ void __launch_bounds__(CUT_THREADS) cutoff_kernel(const uint64_t *__r
     const uint64_t l0 = chr_ptr[c], l1 = chr_ptr[c + 1];
     const uint64_t rb0 = readbase[l0];
     const uint64_t need = 4ull * num_threads; // BATCH_SIZE * num_threads (similarity_matrix.cpp:354-356)
+    const uint64_t ex0 = exact_from ? exact_from[c] : l0;
     if (threadIdx.x == 0) {
         s_sure = 0;
     }
@@ -698,10 +750,12 @@ __global__ void __launch_bounds__(CUT_THREADS) cutoff_kernel(const uint64_t *__r
         for (uint32_t i = threadIdx.x; i <= n; i += CUT_THREADS) {
             uint32_t j = 0;
             s_u[i] = (i == 0 && base == l0) ? 0 : completed_at(position, readbase, l0, base + i - 1, L, rb0, &j);
+            s_j[i] = j;
         }
         __syncthreads();
         for (uint32_t i = threadIdx.x; i < n; i += CUT_THREADS) {
-            if (s_u[i + 1] - s_u[i] >= need) {
+            // s_u[i + 1] - s_u[i] = reads created at the loci [l0 + s_j[i], l0 + s_j[i + 1])
+            if (s_u[i + 1] - s_u[i] >= need && l0 + s_j[i] >= ex0) {
                 atomicMax(&s_sure, static_cast<unsigned long long>(base + i + 1));
             }
         }
@@ -709,6 +763,9 @@ __global__ void __launch_bounds__(CUT_THREADS) cutoff_kernel(const uint64_t *__r
         if (s_sure) {
             break;
         }
+    }
+    if (resolved && threadIdx.x == 0) {
+        resolved[c] = (s_sure != 0 || ex0 <= l0) ? 1 : 0;
     }
     // ---- forwards from there: one thread replays the batching rule chunk by chunk
     uint64_t front = 0, jk = l0, start = l0; // used by thread 0 only
@@ -744,9 +801,79 @@ __global__ void __launch_bounds__(CUT_THREADS) cutoff_kernel(const uint64_t *__r
     }
 }
 
+// ranged accumulation: per chromosome the loci that hold tail reads and the owned loci, from positions
+__global__ void range_bounds_kernel(const uint64_t *__restrict__ chr_ptr, uint32_t n_chr, const uint32_t *__restrict__ position,
+                                    const uint32_t *__restrict__ own_pos_begin, const uint32_t *__restrict__ own_pos_end,
+                                    const uint32_t *__restrict__ tail_position, uint64_t *__restrict__ tail_locus,
+                                    uint64_t *__restrict__ own_lo, uint64_t *__restrict__ own_hi) {
+    const uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= n_chr) {
+        return;
+    }
+    const uint64_t l0 = chr_ptr[c], l1 = chr_ptr[c + 1];
+    auto lower = [&](uint32_t pos) { // first locus of the chromosome with position >= pos
+        uint64_t lo = l0, hi = l1;
+        while (lo < hi) {
+            const uint64_t mid = (lo + hi) >> 1;
+            if (position[mid] < pos) {
+                lo = mid + 1;
+            } else {
+                hi = mid;
+            }
+        }
+        return lo;
+    };
+    tail_locus[c] = lower(tail_position[c]);
+    own_lo[c] = lower(own_pos_begin[c]);
+    own_hi[c] = max(own_lo[c], lower(own_pos_end[c]));
+}
+
+// suffix mode of the cutoff: first locus of every chromosome whose number of created reads is exact
+__global__ void exact_from_kernel(const uint64_t *__restrict__ chr_ptr, uint32_t n_chr, const uint32_t *__restrict__ position,
+                                  uint32_t L, const uint8_t *__restrict__ whole, uint64_t *__restrict__ exact_from) {
+    const uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= n_chr) {
+        return;
+    }
+    const uint64_t l0 = chr_ptr[c], l1 = chr_ptr[c + 1];
+    uint64_t lo = l0, hi = l1;
+    if (!whole[c] && l1 > l0) {
+        const uint64_t want = static_cast<uint64_t>(position[l0]) + L;
+        while (lo < hi) {
+            const uint64_t mid = (lo + hi) >> 1;
+            if (position[mid] < want) {
+                lo = mid + 1;
+            } else {
+                hi = mid;
+            }
+        }
+    }
+    exact_from[c] = lo;
+}
+
+__global__ void tail_position_kernel(const uint64_t *__restrict__ chr_ptr, uint32_t n_chr, const uint32_t *__restrict__ position,
+                                     const uint64_t *__restrict__ tail_locus, uint32_t *__restrict__ tail_position) {
+    const uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c < n_chr) {
+        const uint64_t t = tail_locus[c];
+        tail_position[c] = t < chr_ptr[c + 1] ? position[t] : 0xFFFFFFFFu; // no tail reads at all
+    }
+}
+
+__global__ void __launch_bounds__(TB) owned_fill_kernel(const uint8_t *__restrict__ lchr, const uint64_t *__restrict__ own_lo,
+                                                        const uint64_t *__restrict__ own_hi, uint64_t n_loci,
+                                                        uint8_t *__restrict__ owned) {
+    const uint64_t l = static_cast<uint64_t>(blockIdx.x) * TB + threadIdx.x;
+    if (l < n_loci) {
+        const uint32_t c = lchr[l];
+        owned[l] = (l >= own_lo[c] && l < own_hi[c]) ? 1 : 0;
+    }
+}
+
+template <typename GB>
 __global__ void __launch_bounds__(TB) sp_finish_kernel(
         const uint32_t *__restrict__ sp_head, const uint32_t *__restrict__ sp_entry, const uint32_t *__restrict__ sp_locus,
-        const uint8_t *__restrict__ sp_drop, const uint32_t *__restrict__ g_nst, const uint16_t *__restrict__ gid_base,
+        const uint8_t *__restrict__ sp_drop, const uint32_t *__restrict__ g_nst, const GB *__restrict__ gid_base,
         const uint8_t *__restrict__ lchr, const uint64_t *__restrict__ tail_locus, const uint32_t *__restrict__ gmap,
         uint32_t n_groups, uint32_t num_cells, uint64_t n_special, uint32_t *__restrict__ sp_code,
         uint32_t *__restrict__ sp_rcode,
@@ -857,8 +984,9 @@ __global__ void __launch_bounds__(TB) me_compact_kernel(const uint32_t *__restri
 }
 
 // ---- dense codes (scatter path only) ----------------------------------------------------------------
+template <typename GB>
 __global__ void __launch_bounds__(TB) dense_codes_kernel(const uint64_t *__restrict__ row_ptr,
-                                                         const uint16_t *__restrict__ gid_base,
+                                                         const GB *__restrict__ gid_base,
                                                          const uint8_t *__restrict__ lchr,
                                                          const uint64_t *__restrict__ tail_locus,
                                                          const uint32_t *__restrict__ gmap, uint32_t n_groups,
@@ -895,7 +1023,7 @@ unsigned blocks_for(uint64_t n) { return static_cast<unsigned>(ceil_div_u64(n ? 
 
 int sgpu_link_reads(sgpu_ctx *ctx, const sgpu_pileup *p, uint32_t num_cells, uint32_t L,
                     const uint32_t *h_group_id_to_pos, uint32_t n_groups, uint32_t num_threads,
-                    LinkResult *out) {
+                    LinkResult *out, const RangeSpec *range, const CutoffQuery *cutq) {
     cudaStream_t st = ctx->stream;
     const uint64_t E = p->n_entries, P = p->n_loci;
     if (E >= 0x7FFFFFF0ull || P >= 0x7FFFFFF0ull) {
@@ -910,7 +1038,8 @@ int sgpu_link_reads(sgpu_ctx *ctx, const sgpu_pileup *p, uint32_t num_cells, uin
     if (num_cells >= (1u << 27)) {
         return sgpu_fail(ctx, SGPU_E_ARG, "num_cells too large");
     }
-    out->n_reads = out->n_multi = out->n_dropped = out->n_tail = out->n_special = out->n_tail_loci = 0;
+    out->n_reads = out->n_multi = out->n_dropped = out->n_tail = out->n_special = out->n_tail_loci = out->n_own = 0;
+    out->ranged = range != nullptr;
     out->n_groups = n_groups;
     out->num_cells = num_cells;
     SGPU_CUDA(ctx, out->gmap.alloc(n_groups ? n_groups : 1, ctx));
@@ -962,7 +1091,11 @@ int sgpu_link_reads(sgpu_ctx *ctx, const sgpu_pileup *p, uint32_t num_cells, uin
     // read ids of WIN_RING loci (each slot: the largest locus + up to 3 elements of alignment offset)
     const uint32_t id_cap = (max_n + 3 + 3) & ~3u;
     uint32_t slots = 1024;
-    while (slots < 3ull * max_n && slots < 65536) {
+    unsigned long long slot_factor = 3;
+    if (const char *env = getenv("SECEDO_B200_WIN_SLOT_FACTOR")) { // experiments (profiles/): table size / occupancy trade-off
+        slot_factor = static_cast<unsigned long long>(std::max(1, atoi(env)));
+    }
+    while (slots < slot_factor * max_n && slots < 65536) {
         slots <<= 1;
     }
     auto win_smem = [&](uint32_t s) {
@@ -1043,8 +1176,8 @@ int sgpu_link_reads(sgpu_ctx *ctx, const sgpu_pileup *p, uint32_t num_cells, uin
     if (NS == 0) {
         SGPU_CUDA(ctx, cudaMemsetAsync(out->sp_start.p, 0, (P + 1) * sizeof(uint32_t), st));
     }
+    DevBuf<uint32_t> sp_first, g_cnt, cursor;
     if (NS) {
-        DevBuf<uint32_t> sp_first, g_cnt, cursor;
         SGPU_CUDA(ctx, out->sp_entry.alloc(NS, ctx));
         SGPU_CUDA(ctx, out->sp_locus.alloc(NS, ctx));
         SGPU_CUDA(ctx, out->sp_head.alloc(NS, ctx));
@@ -1060,10 +1193,6 @@ int sgpu_link_reads(sgpu_ctx *ctx, const sgpu_pileup *p, uint32_t num_cells, uin
         SGPU_CUDA(ctx, cursor.alloc(NS, ctx));
         SGPU_CUDA(ctx, nf_locus.alloc(P, ctx));
         SGPU_CUDA(ctx, nf_scan.alloc(P + 1, ctx));
-        SGPU_CUDA(ctx, cudaMemsetAsync(g_cnt.p, 0, NS * sizeof(uint32_t), st));
-        SGPU_CUDA(ctx, cudaMemsetAsync(cursor.p, 0, NS * sizeof(uint32_t), st));
-        SGPU_CUDA(ctx, cudaMemsetAsync(out->g_nst.p, 0, NS * sizeof(uint32_t), st));
-        SGPU_CUDA(ctx, cudaMemsetAsync(out->sp_drop.p, 0, NS, st));
         {
             DevBuf<uint32_t> word_locus;
             SGPU_CUDA(ctx, word_locus.alloc(W, ctx));
@@ -1072,35 +1201,141 @@ int sgpu_link_reads(sgpu_ctx *ctx, const sgpu_pileup *p, uint32_t num_cells, uin
                                                                             out->sp_entry.p, sp_first.p, out->sp_locus.p)));
         }
         SGPU_LAUNCH(ctx, (sp_start_kernel<<<blocks_for(P + 1), TB, 0, st>>>(out->sp_locus.p, NS, P, out->sp_start.p)));
-        for (int sweep = 0; sweep < 3; ++sweep) {
-            SGPU_LAUNCH(ctx, (link_min_kernel<<<blocks_for(NL), TB, 0, st>>>(links.p, NL, out->sp_bits.p, out->sp_rank.p, sp_first.p,
-                                                                             d_err.p + 1)));
-            if (sweep == 1) {
-                SGPU_CUDA(ctx, cudaMemsetAsync(d_err.p + 1, 0, sizeof(int), st)); // only the verifying sweep counts
+    }
+    // reads from the links: first entry of every read, entry lists, mate rule. careful = false: two sweeps settle every
+    // read whose entries all lie within L bp of its first one (a third one verifies); careful = true (only after the fast
+    // pass reported a read id chained over >= L bp): sweep until nothing moves, then split such chains into reads
+    auto build_reads = [&](bool careful) -> int {
+        if (NS == 0) {
+            return SGPU_OK;
+        }
+        SGPU_CUDA(ctx, cudaMemsetAsync(g_cnt.p, 0, NS * sizeof(uint32_t), st));
+        SGPU_CUDA(ctx, cudaMemsetAsync(cursor.p, 0, NS * sizeof(uint32_t), st));
+        SGPU_CUDA(ctx, cudaMemsetAsync(out->g_nst.p, 0, NS * sizeof(uint32_t), st));
+        SGPU_CUDA(ctx, cudaMemsetAsync(out->sp_drop.p, 0, NS, st));
+        if (!careful) {
+            for (int sweep = 0; sweep < 3; ++sweep) {
+                SGPU_LAUNCH(ctx, (link_min_kernel<<<blocks_for(NL), TB, 0, st>>>(links.p, NL, out->sp_bits.p, out->sp_rank.p, sp_first.p,
+                                                                                 d_err.p + 1)));
+                if (sweep == 1) {
+                    SGPU_CUDA(ctx, cudaMemsetAsync(d_err.p + 1, 0, sizeof(int), st)); // only the verifying sweep counts
+                }
+            }
+        } else {
+            SGPU_CUDA(ctx, cudaMemcpyAsync(sp_first.p, out->sp_entry.p, NS * sizeof(uint32_t), cudaMemcpyDeviceToDevice, st));
+            for (int sweep = 0;; ++sweep) {
+                SGPU_CUDA(ctx, cudaMemsetAsync(d_err.p + 1, 0, sizeof(int), st));
+                SGPU_LAUNCH(ctx, (link_min_kernel<<<blocks_for(NL), TB, 0, st>>>(links.p, NL, out->sp_bits.p, out->sp_rank.p, sp_first.p,
+                                                                                 d_err.p + 1)));
+                SGPU_CUDA(ctx, cudaMemcpyAsync(&ctx->h_scratch[0], d_err.p + 1, sizeof(int), cudaMemcpyDeviceToHost, st));
+                SGPU_CUDA(ctx, cudaStreamSynchronize(st));
+                if (static_cast<int>(ctx->h_scratch[0] & 0xFFFFFFFFu) == 0) {
+                    break;
+                }
+                if (sweep > 100000) {
+                    return sgpu_fail(ctx, SGPU_E_FRAGMENT_SPAN, "read linking did not settle");
+                }
             }
         }
-        SGPU_LAUNCH(ctx, (group_count_kernel<<<blocks_for(NS), TB, 0, st>>>(out->sp_bits.p, out->sp_rank.p, sp_first.p, NS, out->sp_head.p, g_cnt.p)));
-        SGPU_TRY(sgpu_scan_u32_u64(ctx, g_cnt.p, out->g_off.p, NS));
-        SGPU_LAUNCH(ctx, (group_fill_kernel<<<blocks_for(NS), TB, 0, st>>>(out->sp_head.p, out->sp_locus.p, out->g_off.p, NS, cursor.p,
-                                                                           out->g_list.p)));
+        auto group = [&]() -> int {
+            SGPU_LAUNCH(ctx, (group_count_kernel<<<blocks_for(NS), TB, 0, st>>>(out->sp_bits.p, out->sp_rank.p, sp_first.p, NS, out->sp_head.p, g_cnt.p)));
+            SGPU_TRY(sgpu_scan_u32_u64(ctx, g_cnt.p, out->g_off.p, NS));
+            SGPU_LAUNCH(ctx, (group_fill_kernel<<<blocks_for(NS), TB, 0, st>>>(out->sp_head.p, out->sp_locus.p, out->g_off.p, NS, cursor.p,
+                                                                               out->g_list.p)));
+            return SGPU_OK;
+        };
+        SGPU_TRY(group());
+        if (careful) {
+            DevBuf<unsigned long long> d_splits;
+            SGPU_CUDA(ctx, d_splits.alloc(1, ctx));
+            SGPU_CUDA(ctx, cudaMemsetAsync(d_splits.p, 0, sizeof(unsigned long long), st));
+            SGPU_LAUNCH(ctx, (split_span_kernel<<<blocks_for(NS), TB, 0, st>>>(out->sp_head.p, out->sp_entry.p, out->sp_locus.p, out->g_off.p, NS,
+                                                                               out->g_list.p, p->d_position, L, sp_first.p, d_splits.p)));
+            SGPU_CUDA(ctx, cudaMemcpyAsync(&ctx->h_scratch[0], d_splits.p, sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
+            SGPU_CUDA(ctx, cudaStreamSynchronize(st));
+            out->n_span_splits = ctx->h_scratch[0];
+            SGPU_CUDA(ctx, cudaMemsetAsync(g_cnt.p, 0, NS * sizeof(uint32_t), st));
+            SGPU_CUDA(ctx, cudaMemsetAsync(cursor.p, 0, NS * sizeof(uint32_t), st));
+            SGPU_TRY(group());
+        }
         SGPU_LAUNCH(ctx, (nonfirst_kernel<<<locus_grid, TB, 0, st>>>(out->sp_head.p, out->sp_start.p, P, nf_locus.p)));
-        SGPU_LAUNCH(ctx, (mate_rule_kernel<<<blocks_for(NS), TB, 0, st>>>(out->sp_head.p, out->sp_entry.p, out->sp_locus.p, out->g_off.p, NS,
-                                                                          out->g_list.p, out->g_base.p, p->d_gid_base, p->d_position, L,
-                                                                          out->sp_drop.p, out->g_nst.p, d_err.p)));
+        SGPU_GB(p, SGPU_LAUNCH(ctx, (mate_rule_kernel<GB><<<blocks_for(NS), TB, 0, st>>>(out->sp_head.p, out->sp_entry.p, out->sp_locus.p, out->g_off.p, NS,
+                                                                          out->g_list.p, out->g_base.p, gid_base_, p->d_position, L,
+                                                                          out->sp_drop.p, out->g_nst.p, d_err.p))));
         SGPU_TRY(sgpu_scan_u32_u64(ctx, nf_locus.p, nf_scan.p, P));
+        return SGPU_OK;
+    };
+    // SECEDO_B200_STRICT_SPAN=1: a read id chained over >= max_fragment_length is an error instead of being split (tests)
+    const char *env_strict = getenv("SECEDO_B200_STRICT_SPAN");
+    const bool strict_span = env_strict && env_strict[0] == '1';
+    out->n_span_splits = 0;
+    for (int pass = 0;; ++pass) {
+    const bool careful = pass > 0;
+    if (careful) { // the fast pass met a read id chained over >= L bp: once more, settling and splitting such chains
+        SGPU_CUDA(ctx, cudaMemsetAsync(d_err.p, 0, 2 * sizeof(int), st));
+        SGPU_CUDA(ctx, cudaMemsetAsync(d_stats.p, 0, 2 * sizeof(unsigned long long), st));
+        out->n_tail = 0;
     }
-    links.release();
-
+    SGPU_TRY(build_reads(careful));
     SGPU_TRACE(ctx, "link: groups+mate rule");
     // ---- cutoff K per chromosome ----------------------------------------------------------------------
     SGPU_LAUNCH(ctx, (readbase_kernel<<<blocks_for(P + 1), TB, 0, st>>>(p->d_row_ptr, NS ? nf_scan.p : nullptr, P, readbase.p)));
-    SGPU_LAUNCH(ctx, (cutoff_kernel<<<p->n_chr, CUT_THREADS, 0, st>>>(p->d_chr_ptr, p->n_chr, p->d_position, readbase.p, L, num_threads,
-                                                                      n_tail_reads.p, out->tail_locus.p)));
+    DevBuf<uint64_t> own_lo, own_hi;
+    if (cutq) {
+        // the pileup holds only the END of every chromosome (unless whole[c]): decide the cutoff from there
+        DevBuf<uint8_t> d_whole, d_resolved;
+        DevBuf<uint64_t> exact_from;
+        DevBuf<uint32_t> d_tailpos;
+        SGPU_CUDA(ctx, d_whole.alloc(p->n_chr, ctx));
+        SGPU_CUDA(ctx, d_resolved.alloc(p->n_chr, ctx));
+        SGPU_CUDA(ctx, exact_from.alloc(p->n_chr, ctx));
+        SGPU_CUDA(ctx, d_tailpos.alloc(p->n_chr, ctx));
+        SGPU_CUDA(ctx, cudaMemcpyAsync(d_whole.p, cutq->whole, p->n_chr, cudaMemcpyHostToDevice, st));
+        SGPU_LAUNCH(ctx, (exact_from_kernel<<<(p->n_chr + 63) / 64, 64, 0, st>>>(p->d_chr_ptr, p->n_chr, p->d_position, L, d_whole.p, exact_from.p)));
+        SGPU_LAUNCH(ctx, (cutoff_kernel<<<p->n_chr, CUT_THREADS, 0, st>>>(p->d_chr_ptr, p->n_chr, p->d_position, readbase.p, L, num_threads,
+                                                                          n_tail_reads.p, out->tail_locus.p, exact_from.p, d_resolved.p)));
+        SGPU_LAUNCH(ctx, (tail_position_kernel<<<(p->n_chr + 63) / 64, 64, 0, st>>>(p->d_chr_ptr, p->n_chr, p->d_position, out->tail_locus.p, d_tailpos.p)));
+        SGPU_CUDA(ctx, cudaGetLastError());
+        SGPU_CUDA(ctx, cudaMemcpyAsync(cutq->tail_position, d_tailpos.p, p->n_chr * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+        SGPU_CUDA(ctx, cudaMemcpyAsync(cutq->resolved, d_resolved.p, p->n_chr, cudaMemcpyDeviceToHost, st));
+        SGPU_CUDA(ctx, cudaMemcpyAsync(&ctx->h_scratch[2], d_err.p, 2 * sizeof(int), cudaMemcpyDeviceToHost, st));
+        SGPU_CUDA(ctx, cudaStreamSynchronize(st));
+        const int err = static_cast<int>(ctx->h_scratch[2] & 0xFFFFFFFFu);
+        if (err == SGPU_E_POSITIONS) {
+            return sgpu_fail(ctx, err, "positions are not strictly increasing inside a chromosome");
+        }
+        if (err == SGPU_E_FRAGMENT_SPAN || static_cast<int>(ctx->h_scratch[2] >> 32)) {
+            if (careful || strict_span) {
+                return sgpu_fail(ctx, SGPU_E_FRAGMENT_SPAN, "a read id spans >= max_fragment_length (%u)", L);
+            }
+            continue;
+        }
+        return SGPU_OK;
+    }
+    if (!range) {
+        SGPU_LAUNCH(ctx, (cutoff_kernel<<<p->n_chr, CUT_THREADS, 0, st>>>(p->d_chr_ptr, p->n_chr, p->d_position, readbase.p, L, num_threads,
+                                                                          n_tail_reads.p, out->tail_locus.p)));
+    } else {
+        // a piece of the chromosomes: the cutoff comes from outside (sgpu_chromosome_cutoff), ownership from positions
+        DevBuf<uint32_t> spec;
+        SGPU_CUDA(ctx, spec.alloc(3 * static_cast<size_t>(p->n_chr), ctx));
+        SGPU_CUDA(ctx, own_lo.alloc(p->n_chr, ctx));
+        SGPU_CUDA(ctx, own_hi.alloc(p->n_chr, ctx));
+        SGPU_CUDA(ctx, out->owned.alloc(P, ctx));
+        SGPU_CUDA(ctx, cudaMemcpyAsync(spec.p, range->own_pos_begin, p->n_chr * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
+        SGPU_CUDA(ctx, cudaMemcpyAsync(spec.p + p->n_chr, range->own_pos_end, p->n_chr * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
+        SGPU_CUDA(ctx, cudaMemcpyAsync(spec.p + 2 * p->n_chr, range->tail_position, p->n_chr * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
+        SGPU_CUDA(ctx, cudaMemsetAsync(n_tail_reads.p, 0, p->n_chr * sizeof(uint64_t), st));
+        SGPU_LAUNCH(ctx, (range_bounds_kernel<<<(p->n_chr + 63) / 64, 64, 0, st>>>(p->d_chr_ptr, p->n_chr, p->d_position, spec.p, spec.p + p->n_chr,
+                                                                                  spec.p + 2 * p->n_chr, out->tail_locus.p, own_lo.p, own_hi.p)));
+        SGPU_LAUNCH(ctx, (owned_fill_kernel<<<blocks_for(P), TB, 0, st>>>(out->lchr.p, own_lo.p, own_hi.p, P, out->owned.p)));
+        SGPU_CUDA(ctx, cudaStreamSynchronize(st)); // the caller's arrays are pageable
+    }
     if (NS) {
-        SGPU_LAUNCH(ctx, (sp_finish_kernel<<<blocks_for(NS), TB, 0, st>>>(out->sp_head.p, out->sp_entry.p, out->sp_locus.p, out->sp_drop.p,
-                                                                          out->g_nst.p, p->d_gid_base, out->lchr.p, out->tail_locus.p,
+        SGPU_GB(p, SGPU_LAUNCH(ctx, (sp_finish_kernel<GB><<<blocks_for(NS), TB, 0, st>>>(out->sp_head.p, out->sp_entry.p, out->sp_locus.p, out->sp_drop.p,
+                                                                          out->g_nst.p, gid_base_, out->lchr.p, out->tail_locus.p,
                                                                           out->gmap.p, n_groups, num_cells, NS, out->sp_code.p,
-                                                                          out->sp_rcode.p, d_stats.p, d_err.p)));
+                                                                          out->sp_rcode.p, d_stats.p, d_err.p))));
         SGPU_TRY(sgpu_link_candidates(ctx, out, 2));
     }
     SGPU_CUDA(ctx, cudaGetLastError());
@@ -1123,17 +1358,41 @@ int sgpu_link_reads(sgpu_ctx *ctx, const sgpu_pileup *p, uint32_t num_cells, uin
         return sgpu_fail(ctx, err, "positions are not strictly increasing inside a chromosome");
     }
     if (err == SGPU_E_FRAGMENT_SPAN || unsettled) {
-        return sgpu_fail(ctx, SGPU_E_FRAGMENT_SPAN, "a read id spans >= max_fragment_length (%u): undefined in the reference", L);
+        if (careful || strict_span) {
+            return sgpu_fail(ctx, SGPU_E_FRAGMENT_SPAN, "a read id spans >= max_fragment_length (%u)%s", L,
+                             strict_span ? " (SECEDO_B200_STRICT_SPAN=1: not split)" : "");
+        }
+        continue;
     }
     out->n_dropped = ctx->h_scratch[4];
     out->n_multi = ctx->h_scratch[5];
     out->n_reads = ctx->h_scratch[6];
-    std::vector<uint32_t> h_tail_loci;
+    std::vector<uint32_t> h_tail_loci, h_own_loci;
+    std::vector<uint64_t> h_lo(p->n_chr), h_hi(p->n_chr);
     out->h_tail_locus = h_tl;
+    if (range) {
+        SGPU_CUDA(ctx, cudaMemcpyAsync(h_lo.data(), own_lo.p, p->n_chr * sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
+        SGPU_CUDA(ctx, cudaMemcpyAsync(h_hi.data(), own_hi.p, p->n_chr * sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
+        SGPU_CUDA(ctx, cudaStreamSynchronize(st));
+    }
     for (uint32_t c = 0; c < p->n_chr; ++c) {
         out->n_tail += h_nt[c];
-        for (uint64_t l = h_tl[c]; l < p->h_chr_ptr[c + 1]; ++l) {
+        const uint64_t lo = range ? h_lo[c] : p->h_chr_ptr[c], hi = range ? h_hi[c] : p->h_chr_ptr[c + 1];
+        for (uint64_t l = std::max(h_tl[c], lo); l < hi; ++l) { // tail x tail pairs are taken out at the OWNED loci only
             h_tail_loci.push_back(static_cast<uint32_t>(l));
+        }
+        if (range) {
+            for (uint64_t l = lo; l < hi; ++l) {
+                h_own_loci.push_back(static_cast<uint32_t>(l));
+            }
+        }
+    }
+    if (range) {
+        out->n_own = h_own_loci.size();
+        SGPU_CUDA(ctx, out->own_loci.alloc(h_own_loci.size() ? h_own_loci.size() : 1, ctx));
+        if (!h_own_loci.empty()) {
+            SGPU_CUDA(ctx, cudaMemcpyAsync(out->own_loci.p, h_own_loci.data(), h_own_loci.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
+            SGPU_CUDA(ctx, cudaStreamSynchronize(st));
         }
     }
     SGPU_TRACE(ctx, "link: scalars");
@@ -1144,6 +1403,7 @@ int sgpu_link_reads(sgpu_ctx *ctx, const sgpu_pileup *p, uint32_t num_cells, uin
         SGPU_CUDA(ctx, cudaStreamSynchronize(st)); // h_tail_loci is pageable
     }
     return SGPU_OK;
+    } // pass
 }
 
 int sgpu_link_candidates(sgpu_ctx *ctx, LinkResult *out, uint32_t min_nst) {
@@ -1185,8 +1445,8 @@ int sgpu_link_dense_codes(sgpu_ctx *ctx, const sgpu_pileup *p, LinkResult *lr) {
     SGPU_CUDA(ctx, d_err.alloc(1, ctx));
     SGPU_CUDA(ctx, cudaMemsetAsync(d_err.p, 0, sizeof(int), st));
     const unsigned grid = static_cast<unsigned>(std::min<uint64_t>(P, static_cast<uint64_t>(ctx->sm_count) * 16));
-    SGPU_LAUNCH(ctx, (dense_codes_kernel<<<grid, TB, 0, st>>>(p->d_row_ptr, p->d_gid_base, lr->lchr.p, lr->tail_locus.p, lr->gmap.p,
-                                                              lr->n_groups, lr->num_cells, P, lr->code.p, d_err.p)));
+    SGPU_GB(p, SGPU_LAUNCH(ctx, (dense_codes_kernel<GB><<<grid, TB, 0, st>>>(p->d_row_ptr, gid_base_, lr->lchr.p, lr->tail_locus.p, lr->gmap.p,
+                                                              lr->n_groups, lr->num_cells, P, lr->code.p, d_err.p))));
     if (lr->n_special) {
         SGPU_LAUNCH(ctx, (sp_codes_kernel<<<blocks_for(lr->n_special), TB, 0, st>>>(lr->sp_entry.p, lr->sp_code.p, lr->n_special, lr->code.p)));
     }
@@ -1197,4 +1457,22 @@ int sgpu_link_dense_codes(sgpu_ctx *ctx, const sgpu_pileup *p, LinkResult *lr) {
         return sgpu_fail(ctx, SGPU_E_CELL_RANGE, "a group id is >= n_groups or maps to a cell >= num_cells (filter the pileup first)");
     }
     return SGPU_OK;
+}
+
+int sgpu_cutoff_from_suffix(sgpu_ctx *ctx, const sgpu_pileup *p, uint32_t L, uint32_t num_threads, const uint8_t *h_whole,
+                            uint32_t *h_tail_position, uint8_t *h_resolved) {
+    for (uint32_t c = 0; c < p->n_chr; ++c) { // chromosomes without loci: nothing is tail, trivially decided
+        h_tail_position[c] = 0xFFFFFFFFu;
+        h_resolved[c] = 1;
+    }
+    if (p->n_entries == 0 || p->n_loci == 0) {
+        return SGPU_OK;
+    }
+    LinkResult lr;
+    CutoffQuery q;
+    q.whole = h_whole;
+    q.tail_position = h_tail_position;
+    q.resolved = h_resolved;
+    const uint32_t none = 0;
+    return sgpu_link_reads(ctx, p, 1, L, &none, 0, num_threads, &lr, nullptr, &q);
 }

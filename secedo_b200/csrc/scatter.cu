@@ -115,8 +115,8 @@ int sgpu_scatter_pairs(sgpu_ctx *ctx, const sgpu_pileup *p, const LinkResult &lr
     DevBuf<unsigned long long> d_np;
     SGPU_CUDA(ctx, d_np.alloc(1, ctx));
     SGPU_CUDA(ctx, cudaMemsetAsync(d_np.p, 0, sizeof(unsigned long long), st));
-    // tail x tail pairs only exist at the loci behind the cutoff of each chromosome
-    const uint64_t n_loci = only_tail_pairs ? lr.n_tail_loci : p->n_loci;
+    // tail x tail pairs only exist at the loci behind the cutoff of each chromosome; a ranged call counts its own loci
+    const uint64_t n_loci = only_tail_pairs ? lr.n_tail_loci : lr.ranged ? lr.n_own : p->n_loci;
     if (n_loci == 0) {
         return SGPU_OK;
     }
@@ -126,7 +126,7 @@ int sgpu_scatter_pairs(sgpu_ctx *ctx, const sgpu_pileup *p, const LinkResult &lr
     const dim3 grid(gx, gy);
     SGPU_LAUNCH(ctx, (scatter_pairs_kernel<<<grid, SC_THREADS, 0, st>>>(p->d_row_ptr, lr.code.p, n_loci, c->i32 + PLANE_S * c->nn,
                                                      c->i32 + PLANE_D * c->nn, c->n, sign, only_tail_pairs ? 1 : 0,
-                                                     only_tail_pairs ? lr.tail_loci.p : nullptr, d_np.p)));
+                                                     only_tail_pairs ? lr.tail_loci.p : lr.ranged ? lr.own_loci.p : nullptr, d_np.p)));
     SGPU_CUDA(ctx, cudaGetLastError());
     if (n_pairs) {
         SGPU_CUDA(ctx, cudaMemcpyAsync(&ctx->h_scratch[0], d_np.p, sizeof(uint64_t), cudaMemcpyDeviceToHost, st));

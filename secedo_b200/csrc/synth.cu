@@ -96,8 +96,9 @@ __global__ void __launch_bounds__(TB) synth_count_kernel(SynthP p, uint64_t n_lo
     }
 }
 
+template <typename GB>
 __global__ void __launch_bounds__(TB) synth_fill_kernel(SynthP p, uint64_t n_loci, const uint64_t *__restrict__ row_ptr,
-                                                        uint32_t *__restrict__ read_id, uint16_t *__restrict__ gid_base) {
+                                                        uint32_t *__restrict__ read_id, GB *__restrict__ gid_base) {
     const int lane = threadIdx.x & 31;
     const uint64_t g = (static_cast<uint64_t>(blockIdx.x) * TB + threadIdx.x) >> 5;
     if (g >= n_loci) {
@@ -123,7 +124,7 @@ __global__ void __launch_bounds__(TB) synth_fill_kernel(SynthP p, uint64_t n_loc
             rid *= 2654435761u; // odd multiplier: a bijection on 32 bits, ids are neither sorted nor dense
             base = observed_base(p, g, s, cell);
             read_id[e0 + s] = rid;
-            gid_base[e0 + s] = static_cast<uint16_t>((cell << 2) | base);
+            gid_base[e0 + s] = static_cast<GB>((cell << 2) | base);
             dup = has_mate(p, g, s);
         }
         const uint32_t ballot = __ballot_sync(0xffffffffu, dup);
@@ -132,7 +133,7 @@ __global__ void __launch_bounds__(TB) synth_fill_kernel(SynthP p, uint64_t n_loc
             const uint64_t hm = h3(p.seed, g, s, 7);
             const uint32_t b2 = u01(hm) < p.p_mate_mismatch ? (base + 1 + ((hm >> 4) % 3)) & 3u : base;
             read_id[d] = rid;
-            gid_base[d] = static_cast<uint16_t>((cell << 2) | b2);
+            gid_base[d] = static_cast<GB>((cell << 2) | b2);
         }
         dup_base += __popc(ballot);
     }
@@ -186,8 +187,14 @@ extern "C" int sgpu_synth_pileup(sgpu_ctx *ctx, const sgpu_synth_params *sp, sgp
         return sgpu_fail(ctx, SGPU_E_ARG, "synthetic pileup too large for 32-bit read ids");
     }
     SGPU_CUDA(ctx, sgpu_dev_alloc(ctx, reinterpret_cast<void **>(&pl->d_read_id), std::max<uint64_t>(pl->n_entries, 1) * sizeof(uint32_t)));
-    SGPU_CUDA(ctx, sgpu_dev_alloc(ctx, reinterpret_cast<void **>(&pl->d_gid_base), std::max<uint64_t>(pl->n_entries, 1) * sizeof(uint16_t)));
-    SGPU_LAUNCH(ctx, (synth_fill_kernel<<<grid, TB, 0, st>>>(p, P, pl->d_row_ptr, pl->d_read_id, pl->d_gid_base)));
+    pl->wide = sp->n_cells > 16383; // beyond the reference's 14-bit group ids (cfg5)
+    if (pl->wide) {
+        SGPU_CUDA(ctx, sgpu_dev_alloc(ctx, reinterpret_cast<void **>(&pl->d_gid_base32), std::max<uint64_t>(pl->n_entries, 1) * sizeof(uint32_t)));
+        SGPU_LAUNCH(ctx, (synth_fill_kernel<uint32_t><<<grid, TB, 0, st>>>(p, P, pl->d_row_ptr, pl->d_read_id, pl->d_gid_base32)));
+    } else {
+        SGPU_CUDA(ctx, sgpu_dev_alloc(ctx, reinterpret_cast<void **>(&pl->d_gid_base), std::max<uint64_t>(pl->n_entries, 1) * sizeof(uint16_t)));
+        SGPU_LAUNCH(ctx, (synth_fill_kernel<uint16_t><<<grid, TB, 0, st>>>(p, P, pl->d_row_ptr, pl->d_read_id, pl->d_gid_base)));
+    }
     SGPU_CUDA(ctx, cudaGetLastError());
     SGPU_CUDA(ctx, cudaStreamSynchronize(st));
     *out = pl;

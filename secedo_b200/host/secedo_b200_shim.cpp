@@ -9,15 +9,25 @@
 //
 // Build inside SECEDO:  add this file INSTEAD OF util/is_significant.cpp and similarity_matrix.cpp to
 // the `util` / `similarity_matrix` targets (and INSTEAD OF expectation_maximization.cpp), add <repo>/include to the include path and link
-// libsecedo_b200.so. Build stand-alone (tests): -Isecedo_b200/host/compat.
+// libsecedo_b200.so. Build stand-alone (tests): -Itests/compat.
 //
 // Same argument meaning and error behaviour as the reference: an unknown normalization throws
 // std::logic_error("Invalid normalization: ...") (similarity_matrix.cpp:264); every other failure
 // prints the message and exits with status 1 (the reference logs through spdlog and calls
 // std::exit(1)). There is no CPU fallback: without a B200 the first call fails.
+//
+// Device residency across divide_cluster's recursion (spectral_clustering.cpp:336-433): every node of the recursion
+// calls Filter::filter on the SAME whole pileup `pds` with another id_to_pos, then computeSimilarityMatrix (and
+// optionally expectation_maximization) on what Filter::filter returned. The shim therefore keeps two device pileups:
+// the last raw pileup it uploaded (recognised by the address of the caller's vector plus a fingerprint over every
+// locus) and the last filter result (recognised by the fingerprint of the vector<vector<PosData>> it returned). The
+// whole pileup crosses PCIe once per run instead of once per call, and the filtered one not at all.
+// SECEDO_B200_NO_CACHE=1 switches both off. SECEDO_B200_DEVICES=0,1,... (default: all visible GPUs) selects the GPUs
+// computeSimilarityMatrix spreads the loci over; SECEDO_B200_DEVICE=n the one everything else runs on.
 #include "expectation_maximization.hpp"
 #include "similarity_matrix.hpp"
 #include "util/is_significant.hpp"
+#include "util/logger.hpp"
 
 #include "secedo_b200.h"
 
@@ -25,6 +35,7 @@
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
+#include <cstring>
 #include <stdexcept>
 
 namespace {
@@ -47,6 +58,48 @@ void check(int rc) {
         std::fprintf(stderr, "secedo_b200: error %d: %s\n", rc, sgpu_last_error(context()));
         std::exit(1);
     }
+}
+
+bool cache_enabled() {
+    static const bool on = [] {
+        const char *e = std::getenv("SECEDO_B200_NO_CACHE");
+        return !(e && e[0] == '1');
+    }();
+    return on;
+}
+
+// what identifies the CONTENT of a vector<vector<PosData>> cheaply: sizes, every position and entry count, and the
+// first / last entry of every locus (O(loci), not O(entries))
+struct Fingerprint {
+    uint64_t n_chr = 0, n_loci = 0, n_entries = 0, hash = 0;
+    bool operator==(const Fingerprint &o) const {
+        return n_chr == o.n_chr && n_loci == o.n_loci && n_entries == o.n_entries && hash == o.hash;
+    }
+};
+
+Fingerprint fingerprint(const std::vector<std::vector<PosData>> &pds) {
+    Fingerprint f;
+    f.n_chr = pds.size();
+    uint64_t h = 0x9E3779B97F4A7C15ull;
+    auto mix = [&h](uint64_t v) {
+        h ^= v + 0x9E3779B97F4A7C15ull + (h << 6) + (h >> 2);
+        h *= 0xBF58476D1CE4E5B9ull;
+    };
+    for (const auto &chr : pds) {
+        f.n_loci += chr.size();
+        mix(chr.size());
+        for (const auto &pd : chr) {
+            const size_t n = pd.read_ids.size();
+            f.n_entries += n;
+            mix((static_cast<uint64_t>(pd.position) << 32) | n);
+            if (n) {
+                mix((static_cast<uint64_t>(pd.read_ids.front()) << 32) | pd.read_ids.back());
+                mix((static_cast<uint64_t>(pd.group_ids_bases.front()) << 16) | pd.group_ids_bases.back());
+            }
+        }
+    }
+    f.hash = h;
+    return f;
 }
 
 // vector<vector<PosData>> -> the five flat CSR arrays of the ABI
@@ -89,6 +142,46 @@ struct Csr {
     }
 };
 
+// a device pileup that outlives the call that created it
+struct Resident {
+    const void *address = nullptr; // of the caller's outer vector (raw pileup only)
+    Fingerprint fp;
+    sgpu_pileup *dev = nullptr;
+    void reset() {
+        if (dev) {
+            sgpu_pileup_free(context(), dev);
+        }
+        dev = nullptr;
+        address = nullptr;
+    }
+};
+Resident g_raw, g_filtered;
+uint64_t g_uploads = 0; // pileups flattened + uploaded so far (tests)
+
+// device pileup of pos_data; *owned = the caller frees it after use
+sgpu_pileup *stage(const std::vector<std::vector<PosData>> &pos_data, bool *owned) {
+    *owned = false;
+    if (cache_enabled()) {
+        const Fingerprint fp = fingerprint(pos_data);
+        if (g_filtered.dev && g_filtered.fp == fp) {
+            return g_filtered.dev; // what Filter::filter just returned: still on the device
+        }
+        if (g_raw.dev && g_raw.address == &pos_data && g_raw.fp == fp) {
+            return g_raw.dev;      // the whole pileup of an earlier node of the recursion
+        }
+        // a pileup not seen before takes the raw slot (divide_cluster passes the same one at every node)
+        g_raw.reset();
+        g_raw.dev = Csr(pos_data).upload();
+        g_raw.address = &pos_data;
+        g_raw.fp = fp;
+        ++g_uploads;
+        return g_raw.dev;
+    }
+    *owned = true;
+    ++g_uploads;
+    return Csr(pos_data).upload();
+}
+
 int normalization_code(const std::string &normalization) {
     if (normalization == "ADD_MIN") {
         return SGPU_NORM_ADD_MIN;
@@ -103,6 +196,9 @@ int normalization_code(const std::string &normalization) {
 }
 
 } // namespace
+
+// test hook: number of pileups the shim has flattened and uploaded
+extern "C" uint64_t secedo_b200_shim_uploads() { return g_uploads; }
 
 // ---- Filter -------------------------------------------------------------------------------------------
 
@@ -126,9 +222,13 @@ double Filter::log_fact(uint32_t n) {
 }
 
 bool Filter::is_significant(std::array<uint16_t, 4> &base_count) {
+    // the reference returns before sorting its in/out argument when the coverage is below 2 (util/is_significant.cpp:83-88)
+    if (base_count[0] + base_count[1] + base_count[2] + base_count[3] < 2) {
+        return false;
+    }
     uint8_t out = 0;
     check(sgpu_is_significant(context(), base_count.data(), 1, theta, cell_proportion, &out));
-    std::sort(base_count.begin(), base_count.end()); // the reference sorts its argument in place
+    std::sort(base_count.begin(), base_count.end()); // the reference sorts its argument in place (:88)
     return out != 0;
 }
 
@@ -144,15 +244,16 @@ bool Filter::is_significant(const PosData &pos_data, uint16_t *coverage) {
 std::pair<std::vector<std::vector<PosData>>, double> Filter::filter(const std::vector<std::vector<PosData>> &pos_data,
                                                                     const std::vector<uint32_t> &id_to_pos,
                                                                     const std::string &marker, uint32_t num_threads) {
-    (void)marker;      // only logged by the reference
     (void)num_threads; // the reference parallelises over chromosomes with it; the result does not depend on it
     sgpu_ctx *ctx = context();
-    const Csr csr(pos_data);
-    sgpu_pileup *in = csr.upload(), *kept = nullptr;
+    bool owned = false;
+    sgpu_pileup *in = stage(pos_data, &owned), *kept = nullptr;
     double avg_coverage = 0;
     check(sgpu_filter(ctx, in, id_to_pos.data(), static_cast<uint32_t>(id_to_pos.size()), theta, cell_proportion, &kept,
                       &avg_coverage));
-    sgpu_pileup_free(ctx, in);
+    if (owned) {
+        sgpu_pileup_free(ctx, in);
+    }
     uint32_t n_chr = 0;
     uint64_t n_loci = 0, n_entries = 0;
     check(sgpu_pileup_dims(kept, &n_chr, &n_loci, &n_entries));
@@ -160,7 +261,6 @@ std::pair<std::vector<std::vector<PosData>>, double> Filter::filter(const std::v
     std::vector<uint32_t> position(n_loci), read_id(n_entries);
     std::vector<uint16_t> gid_base(n_entries);
     check(sgpu_pileup_download(ctx, kept, chr_ptr.data(), row_ptr.data(), position.data(), read_id.data(), gid_base.data()));
-    sgpu_pileup_free(ctx, kept);
     std::vector<std::vector<PosData>> result(n_chr);
     for (uint32_t c = 0; c < n_chr; ++c) {
         result[c].reserve(chr_ptr[c + 1] - chr_ptr[c]);
@@ -169,6 +269,17 @@ std::pair<std::vector<std::vector<PosData>>, double> Filter::filter(const std::v
                                    std::vector<uint16_t>(gid_base.begin() + row_ptr[l], gid_base.begin() + row_ptr[l + 1]));
         }
     }
+    // the filtered pileup stays on the device for the computeSimilarityMatrix / expectation_maximization calls that
+    // divide_cluster makes with this very result (spectral_clustering.cpp:354-356, 375-383)
+    g_filtered.reset();
+    if (cache_enabled()) {
+        g_filtered.dev = kept;
+        g_filtered.fp = fingerprint(result);
+    } else {
+        sgpu_pileup_free(ctx, kept);
+    }
+    // util/is_significant.cpp:190-191
+    logger()->trace("Avg coverage for cluster {}: {}. Total positions: {}", marker, avg_coverage, n_loci);
     return { std::move(result), avg_coverage };
 }
 
@@ -181,13 +292,16 @@ Matd computeSimilarityMatrix(const std::vector<std::vector<PosData>> &pos_data, 
     (void)marker;
     const int norm = normalization_code(normalization); // throws like the reference, before any work
     sgpu_ctx *ctx = context();
-    const Csr csr(pos_data);
-    sgpu_pileup *p = csr.upload();
+    bool owned = false;
+    sgpu_pileup *p = stage(pos_data, &owned);
     Matd result(num_cells, num_cells);
+    logger()->trace("Normalizing similarity matrix..."); // similarity_matrix.cpp:272 (the epilogue is part of the call)
     check(sgpu_similarity(ctx, p, num_cells, max_fragment_length, group_id_to_pos.data(),
                           static_cast<uint32_t>(group_id_to_pos.size()), mutation_rate, homozygous_rate, seq_error_rate,
                           num_threads /* selects the reference's tail cutoff */, norm, SGPU_PATH_AUTO, result.data(), nullptr));
-    sgpu_pileup_free(ctx, p);
+    if (owned) {
+        sgpu_pileup_free(ctx, p);
+    }
     return result;
 }
 
@@ -197,9 +311,11 @@ void expectation_maximization(const std::vector<std::vector<PosData>> &pos_data,
                               uint32_t num_threads, double theta, std::vector<double> *prob_cluster_b) {
     (void)num_threads; // unused by the reference as well (expectation_maximization.cpp:133)
     sgpu_ctx *ctx = context();
-    const Csr csr(pos_data);
-    sgpu_pileup *p = csr.upload();
+    bool owned = false;
+    sgpu_pileup *p = stage(pos_data, &owned);
     check(sgpu_expectation_maximization(ctx, p, cell_id_to_cell_pos.data(), static_cast<uint32_t>(cell_id_to_cell_pos.size()), theta,
                                         prob_cluster_b->data(), static_cast<uint32_t>(prob_cluster_b->size()), 0, nullptr, nullptr));
-    sgpu_pileup_free(ctx, p);
+    if (owned) {
+        sgpu_pileup_free(ctx, p);
+    }
 }

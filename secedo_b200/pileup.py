@@ -10,6 +10,9 @@ can be staged to HBM with five copies:
     position[n_loci]   u32  genomic position, strictly increasing inside a chromosome
     read_id[n_entries] u32  read (fragment) id, unique inside a chromosome
     gid_base[n_entries] u16 group id << 2 | base   (14-bit group id, ``sequenced_data.hpp:29-36``)
+
+A pileup whose ``gid_base`` array is uint32 is WIDE: group ids beyond the reference's 14 bits (BASELINE config 5,
+20 000 cells); "not in the cluster" is then ``NO_POS_WIDE`` instead of ``NO_POS`` in the id maps.
 """
 from __future__ import annotations
 
@@ -19,6 +22,7 @@ from typing import List, Sequence, Tuple
 import numpy as np
 
 NO_POS = 16383  # util/is_significant.hpp:11
+NO_POS_WIDE = 0xFFFFFFFF
 _CHAR_TO_INT = {"A": 0, "a": 0, "C": 1, "c": 1, "G": 2, "g": 2, "T": 3, "t": 3}  # util/util.hpp:17-22
 
 
@@ -35,13 +39,18 @@ class Pileup:
         self.row_ptr = np.ascontiguousarray(self.row_ptr, dtype=np.uint64)
         self.position = np.ascontiguousarray(self.position, dtype=np.uint32)
         self.read_id = np.ascontiguousarray(self.read_id, dtype=np.uint32)
-        self.gid_base = np.ascontiguousarray(self.gid_base, dtype=np.uint16)
+        wide = np.asarray(self.gid_base).dtype == np.uint32
+        self.gid_base = np.ascontiguousarray(self.gid_base, dtype=np.uint32 if wide else np.uint16)
         assert self.chr_ptr.ndim == 1 and self.chr_ptr.size >= 1
         assert self.row_ptr.size == self.n_loci + 1
         assert self.position.size == self.n_loci
         assert self.read_id.size == self.n_entries == self.gid_base.size
 
     # ------------------------------------------------------------------ sizes
+    @property
+    def wide(self) -> bool:
+        return self.gid_base.dtype == np.uint32
+
     @property
     def n_chr(self) -> int:
         return int(self.chr_ptr.size - 1)

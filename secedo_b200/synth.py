@@ -121,6 +121,7 @@ def _make_chromosome(cfg: SynthConfig, clone: np.ndarray, rng) -> Pileup:
     counts = np.bincount(locus, minlength=P)
     keep = counts > 0                                       # a pileup never holds empty loci
     row_ptr = np.concatenate([[0], np.cumsum(counts[keep])]).astype(np.uint64)
-    gid_base = ((cell.astype(np.uint16) << 2) | base).astype(np.uint16)
+    gb_t = np.uint32 if cfg.n_cells > 16383 else np.uint16  # beyond the reference's 14-bit group ids: a wide pileup
+    gid_base = ((cell.astype(gb_t) << 2) | base.astype(gb_t)).astype(gb_t)
     n_loci = int(keep.sum())
     return Pileup(np.array([0, n_loci], np.uint64), row_ptr, position[keep].astype(np.uint32), read_id, gid_base)

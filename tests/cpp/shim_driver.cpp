@@ -5,10 +5,13 @@
 #include "similarity_matrix.hpp"
 #include "util/is_significant.hpp"
 
+#include <array>
 #include <cstdio>
 #include <cstdlib>
 #include <stdexcept>
 #include <string>
+
+extern "C" uint64_t secedo_b200_shim_uploads(); // pileups the shim has flattened + uploaded so far
 
 template <typename T>
 static std::vector<T> read_vec(FILE *f) {
@@ -57,6 +60,10 @@ int main(int argc, char **argv) {
     if (f001.is_significant(paradox) || paradox[3] != 3) {
         return 3;
     }
+    std::array<uint16_t, 4> low = { 0, 1, 0, 0 }; // coverage < 2: the reference returns before sorting its argument
+    if (f001.is_significant(low) || low[1] != 1) {
+        return 5;
+    }
     bool threw = false;
     try {
         computeSimilarityMatrix(pds, num_cells, L, id_to_pos, eps, h, theta, threads, "", "NOPE");
@@ -103,5 +110,20 @@ int main(int argc, char **argv) {
     expectation_maximization(root, all, threads, theta, &prob);
     write_vec(out, prob);
     fclose(out);
+    // device residency across the recursion: two Filter::filter calls on the same pds, computeSimilarityMatrix and
+    // expectation_maximization on what they returned -> the whole pileup was uploaded ONCE, the filtered ones never
+    const bool cached = !(std::getenv("SECEDO_B200_NO_CACHE") && std::getenv("SECEDO_B200_NO_CACHE")[0] == '1');
+    if (secedo_b200_shim_uploads() != (cached ? 1u : 4u)) {
+        std::fprintf(stderr, "uploads: %llu\n", static_cast<unsigned long long>(secedo_b200_shim_uploads()));
+        return 6;
+    }
+    // the same vector with other content is a different pileup
+    if (cached && !pds.empty() && !pds[0].empty() && !pds[0][0].read_ids.empty()) {
+        pds[0][0].read_ids[0] ^= 0x5A5A5A5Au;
+        filter.filter(pds, all, "", threads);
+        if (secedo_b200_shim_uploads() != 2u) {
+            return 7;
+        }
+    }
     return 0;
 }

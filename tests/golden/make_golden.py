@@ -69,6 +69,28 @@ def save_similarity_case(name, p, num_cells, L, gmap, eps, h, theta, threads, no
     print(name, "loci", p.n_loci, "entries", p.n_entries, "cells", num_cells)
 
 
+def span_chain_pileup():
+    """A read id chained over >= max_fragment_length: the same id at nine consecutive loci ~300 bp apart (a long-insert
+    pair with kept loci in between). The reference retires the read once start + L <= position and starts a new one at
+    the next entry with that id (similarity_matrix.cpp:348-372, 379-382); the pileup is dense enough (>= 4 * num_threads
+    new reads per locus) for the batch to fire at every locus, so its result does not depend on batch timing. Returns
+    (chained pileup, the same pileup with the chain relabelled into the reads the reference makes of it)."""
+    cfg = SynthConfig(n_cells=12, coverage=1.0, n_loci=60, n_chr=1, spacing=300, p_multi=0.2, p_mate=0.05, theta=0.05, seed=3)
+    p = make_pileup(cfg)
+    pos = p.position.astype(np.int64)
+    rid, gb = p.read_id.copy(), p.gid_base.copy()
+    relabel = rid.copy()
+    next_id, seg_start, cur = 4_000_000_100, None, None
+    for l in range(10, 19):
+        e = int(p.row_ptr[l])
+        rid[e] = np.uint32(4_000_000_001)
+        gb[e] = (3 << 2) | (gb[e] & 3)
+        if seg_start is None or pos[l] - seg_start >= 1000:
+            seg_start, cur, next_id = pos[l], np.uint32(next_id), next_id + 1
+        relabel[e] = cur
+    return (Pileup(p.chr_ptr, p.row_ptr, p.position, rid, gb), Pileup(p.chr_ptr, p.row_ptr, p.position, relabel, gb))
+
+
 def em_cases():
     """(name, filtered pileup, id_to_pos, theta, initial prob_cluster_b) for the EM refinement"""
     cases = []
@@ -114,6 +136,13 @@ def main():
     assert po.have_ref(), "build oracle/_ref first: make -C oracle ref"
     if "--only-em" in sys.argv:
         return make_em()
+    if "--only-span" in sys.argv:
+        chained, split = span_chain_pileup()
+        save_similarity_case("sim_span_chain", chained, 12, 1000, np.arange(12, dtype=np.uint32), 0.01, 0.5, 0.05, [1, 2])
+        g = dict(np.load(os.path.join(OUT, "sim_span_chain.npz")))
+        g["split_read_id"] = split.read_id
+        np.savez_compressed(os.path.join(OUT, "sim_span_chain.npz"), **g)
+        return
     make_em()
     tmp = tempfile.mkdtemp()
 
@@ -145,6 +174,12 @@ def main():
     f = Pileup(rf.chr_ptr, rf.row_ptr, rf.position, rf.read_id, rf.gid_base)
     save_similarity_case("sim_synth_multi", f, cfg.n_cells, 1000, ident, 0.01, 0.5, 0.01, [1, 2, 3, 8],
                          ("ADD_MIN", "EXPONENTIATE", "SCALE_MAX_1"))
+    # ---- a read id chained over >= L bp (a drop-in run must complete such pileups like the reference) ----
+    chained, split = span_chain_pileup()
+    save_similarity_case("sim_span_chain", chained, 12, 1000, np.arange(12, dtype=np.uint32), 0.01, 0.5, 0.05, [1, 2])
+    g = dict(np.load(os.path.join(OUT, "sim_span_chain.npz")))
+    g["split_read_id"] = split.read_id
+    np.savez_compressed(os.path.join(OUT, "sim_span_chain.npz"), **g)
     # sub-cluster: only the first clone's cells take part (id_to_pos with NO_POS)
     sub = np.full(cfg.n_cells, NO_POS, np.uint32)
     sub[:20] = np.arange(20)

@@ -69,6 +69,69 @@ def main():
             print(f"multi_gpu_check[{path}, sparse={sparse}] world={world}: counts bit-identical to 1 GPU and to the oracle, "
                   f"reduce {t_red * 1e3:.2f} ms OK", flush=True)
         dist.barrier()
+        counts.free()
+    # ---- the peer-memory epilogue: no reduction onto one rank; every rank sums the planes of all ranks over its share of
+    # the tiles through CUDA IPC mappings, transforms them in the same kernel and writes its share of the matrix into a
+    # host matrix shared by the ranks. Without read pairs of order >= 4 it must equal the single-GPU matrix BIT FOR BIT
+    # (integer sums, same fp64 expression); with them (fp64 spill planes, added in rank order) to rounding.
+    shared = sdist.SharedHostMatrix(ctx, cfg.n_cells)
+    cfg_exact = SynthConfig(n_cells=600, coverage=0.3, n_loci=700, n_chr=7, n_clones=3, p_multi=0.02, p_mate=0.05, seed=6)
+    for which, pp in (("spill", p), ("exact", make_pileup(cfg_exact))):
+        weights = [int(pp.chr_ptr[c + 1] - pp.chr_ptr[c]) for c in range(pp.n_chr)]
+        mine = sdist.partition_chromosomes(weights, world)[rank]
+        local_pp = Pileup.concat([pp.loci_range(c, 0, 1 << 40) for c in mine]) if mine else Pileup.empty(0)
+        for path in ("gemm", "scatter"):
+            f_local, _ = flt.filter_device(local_pp, ident)
+            counts = api.Counts(ctx, cfg.n_cells)
+            counts.accumulate(f_local, L, ident, eps, h, theta, T, path)
+            ep = sdist.SlabEpilogue(counts, device)
+            own_sum, peer_sum = ep.checksums()
+            assert own_sum == peer_sum, f"checksum of the ranks' planes {own_sum:#x} != checksum of the peer-summed shares {peer_sum:#x}"
+            refs = {}
+            for norm in ("ADD_MIN", "EXPONENTIATE", "SCALE_MAX_1"):
+                shared.array[:] = -7.0
+                dist.barrier()
+                ep.run(L, eps, h, theta, norm, out_ptr=shared.dev_ptr)
+                ctx.synchronize()
+                torch.cuda.synchronize()
+                dist.barrier()
+                if rank == 0:
+                    f_all, _ = flt.filter_device(pp, ident)
+                    single = api.Counts(ctx, cfg.n_cells)
+                    single.accumulate(f_all, L, ident, eps, h, theta, T, path)
+                    Ms = single.finalize(L, eps, h, theta, norm)
+                    has_spill = single.buffers()[3] > 0
+                    assert has_spill == (which == "spill"), "the two pileups must exercise both cases"
+                    if has_spill:
+                        assert np.abs(shared.array - Ms).max() <= 1e-12 * np.abs(Ms).max(), f"{path}/{norm}: peer-memory epilogue"
+                    else:
+                        assert np.array_equal(shared.array, Ms, equal_nan=True), f"{path}/{norm}: peer-memory epilogue differs from 1 GPU"
+                    refs[norm] = Ms
+                    single.free()
+                dist.barrier()
+            # the share kept on the device: only this rank's tiles (and their mirror images) are written
+            dptr = ep.run(L, eps, h, theta, "ADD_MIN")
+            ctx.synchronize()
+            mine_dev = sdist.tensor_from_ptr(dptr, cfg.n_cells ** 2, torch.float64, device).cpu().numpy().reshape(cfg.n_cells, -1)
+            t0_, t1_ = counts.slab_range()
+            assert (t0_, t1_) == sdist.slab_tiles(cfg.n_cells, rank, world)
+            nb = (cfg.n_cells + 31) // 32
+            ref = torch.from_numpy(refs["ADD_MIN"]).to(device) if rank == 0 else torch.empty((cfg.n_cells, cfg.n_cells),
+                                                                                           dtype=torch.float64, device=device)
+            dist.broadcast(ref, src=0)
+            ref = ref.cpu().numpy()
+            tol = 1e-12 * np.abs(ref).max() if which == "spill" else 0.0
+            for t in range(t0_, t1_, max(1, (t1_ - t0_) // 50)):
+                bi, bj = sdist.tri_tile(t, nb)
+                blk = (slice(bi * 32, bi * 32 + 32), slice(bj * 32, bj * 32 + 32))
+                assert np.abs(mine_dev[blk] - ref[blk]).max() <= tol and np.abs(mine_dev[blk[1], blk[0]] - ref[blk[1], blk[0]]).max() <= tol
+            if rank == 0:
+                print(f"multi_gpu_check[{path}, peer-memory epilogue, {which}] world={world}: checksums agree, matrix "
+                      f"{'within 1e-12 of' if which == 'spill' else 'bit-identical to'} 1 GPU OK", flush=True)
+            ep.close()
+            counts.free()
+            dist.barrier()
+    shared.close()
     dist.destroy_process_group()
 
 

@@ -31,6 +31,30 @@ def test_golden_matrices(gpu_ctx, name, path):
             assert_matrix_close(M, g[f"M_t{t}_{norm}"], TOL)
 
 
+@pytest.mark.parametrize("path", PATHS)
+def test_read_id_chained_over_fragment_length(gpu_ctx, path, monkeypatch):
+    """a read id chained over >= max_fragment_length (long-insert pair with kept loci in between) must not
+    abort a drop-in run. The chain is split where the reference retires the read; checked against the COMPILED REFERENCE
+    (golden) and, count for count, against the oracle on the relabelled pileup. SECEDO_B200_STRICT_SPAN=1 keeps the error."""
+    g = load_golden("sim_span_chain")
+    p = golden_pileup(g)
+    args = (int(g["num_cells"]), int(g["L"]), g["gmap"], float(g["eps"]), float(g["h"]), float(g["theta"]))
+    split = Pileup(p.chr_ptr, p.row_ptr, p.position, g["split_read_id"], p.gid_base)
+    for t in g["threads"]:
+        M = api.compute_similarity_matrix(p, *args, int(t), "", "ADD_MIN", ctx=gpu_ctx, path=path)
+        assert_matrix_close(M, g[f"M_t{t}_ADD_MIN"], TOL)
+        o = po.similarity(split, *args, int(t))
+        c = api.Counts(gpu_ctx, args[0])
+        st = c.accumulate(p, args[1], args[2], args[3], args[4], args[5], int(t), path)
+        S1, D1, H, _ = c.download()
+        assert np.array_equal(S1, o.S1) and np.array_equal(D1, o.D1) and np.array_equal(H, o.H)
+        assert st["n_span_splits"] == np.unique(split.read_id[p.read_id != split.read_id]).size - 1
+        c.free()
+    monkeypatch.setenv("SECEDO_B200_STRICT_SPAN", "1")
+    with pytest.raises(api.SgpuError):
+        api.compute_similarity_matrix(p, *args, 1, "", "ADD_MIN", ctx=gpu_ctx, path=path)
+
+
 def check_counts(ctx, f, n_cells, L, gmap, eps, h, theta, threads, path):
     o = po.similarity(f, n_cells, L, gmap, eps, h, theta, threads, "ADD_MIN")
     c = api.Counts(ctx, n_cells)

@@ -105,3 +105,52 @@ def test_against_compiled_reference(threads):
         M, _ = po.ref_similarity(f, cfg.n_cells, 1000, ident, 0.01, 0.5, 0.01, threads, norm)
         r = po.similarity(f, cfg.n_cells, 1000, ident, 0.01, 0.5, 0.01, threads, norm)
         assert_matrix_close(r.M, M, 1e-9)
+
+
+def test_wide_restatement_equals_the_pinned_one():
+    """BASELINE config 5 (20 000 cells) is beyond the reference's 14-bit group ids, so its oracle is the restatement on
+    32-bit entries. Below 16 384 groups the two entry widths must agree exactly (same code, other loads), which ties the
+    wide oracle to the compiled reference through the 16-bit one; and group ids >= 16 384 are carried through."""
+    from secedo_b200.pileup import NO_POS, NO_POS_WIDE, Pileup
+    cfg = SynthConfig(n_cells=50, coverage=0.4, n_loci=500, n_chr=2, p_multi=0.3, p_mate=0.1, theta=0.02, seed=41)
+    p = make_pileup(cfg)
+    wide = Pileup(p.chr_ptr, p.row_ptr, p.position, p.read_id, p.gid_base.astype(np.uint32))
+    assert wide.wide and not p.wide
+    members = np.r_[0:20, 25:50]
+    for no_pos, pile in ((NO_POS, p), (NO_POS_WIDE, wide)):
+        gmap = np.full(50, no_pos, np.uint32)
+        gmap[members] = np.arange(members.size)
+        kl, ke, cov, cov64 = po.filter_flags(pile, gmap, 0.01)
+        f = pile.select(kl, ke)
+        o = po.similarity(f, members.size, 1000, gmap, 0.01, 0.5, 0.01, 3, "ADD_MIN")
+        if no_pos == NO_POS:
+            ref = (kl, ke, cov64, o)
+        else:
+            assert np.array_equal(kl, ref[0]) and np.array_equal(ke, ref[1]) and cov64 == ref[2]
+            for name in ("M", "S1", "D1", "H", "class_hist", "K", "raw"):
+                assert np.array_equal(getattr(o, name), getattr(ref[3], name)), name
+    # the same reads under group ids shifted beyond 14 bits give the same matrix
+    shift = 20000
+    shifted = Pileup(p.chr_ptr, p.row_ptr, p.position, p.read_id,
+                     ((p.gid_base.astype(np.uint32) >> 2) + shift) << 2 | (p.gid_base.astype(np.uint32) & 3))
+    gmap = np.full(shift + 50, NO_POS_WIDE, np.uint32)
+    gmap[shift + members] = np.arange(members.size)
+    kl, ke, _, _ = po.filter_flags(shifted, gmap, 0.01)
+    assert np.array_equal(kl, ref[0]) and np.array_equal(ke, ref[1])
+    o = po.similarity(shifted.select(kl, ke), members.size, 1000, gmap, 0.01, 0.5, 0.01, 3, "ADD_MIN")
+    assert np.array_equal(o.M, ref[3].M) and np.array_equal(o.S1, ref[3].S1)
+
+
+def test_span_chain_golden():
+    """a read id chained over >= L bp: the compiled reference (golden) equals the restatement on the pileup whose chain
+    was relabelled into the reads the reference makes of it (retire at start + L <= position, new read at the next entry)
+    — the semantics the CUDA path implements by splitting; the restatement itself refuses the un-split input"""
+    g = load_golden("sim_span_chain")
+    p = golden_pileup(g)
+    split = Pileup(p.chr_ptr, p.row_ptr, p.position, g["split_read_id"], p.gid_base)
+    assert (p.read_id != split.read_id).sum() == 9
+    for t in g["threads"]:
+        o = po.similarity(split, int(g["num_cells"]), int(g["L"]), g["gmap"], float(g["eps"]), float(g["h"]), float(g["theta"]), int(t))
+        assert_matrix_close(o.M, g[f"M_t{t}_ADD_MIN"], 1e-9)
+        with pytest.raises(ValueError):
+            po.similarity(p, int(g["num_cells"]), int(g["L"]), g["gmap"], float(g["eps"]), float(g["h"]), float(g["theta"]), int(t))

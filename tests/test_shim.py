@@ -15,7 +15,7 @@ from secedo_b200.pileup import NO_POS, Pileup
 from secedo_b200.synth import SynthConfig, make_pileup
 
 SHIM = os.path.join(ROOT, "secedo_b200", "host", "secedo_b200_shim.cpp")
-COMPAT = os.path.join(ROOT, "secedo_b200", "host", "compat")
+COMPAT = os.path.join(ROOT, "tests", "compat")
 INC = os.path.join(ROOT, "include")
 REF = "/root/reference"
 
