@@ -50,6 +50,21 @@ WORKLOAD = dict(
     theta=0.001, eps=0.01, h=0.15, L=1000, normalization="ADD_MIN",
 )
 CPU_SAMPLE_LOCI = int(os.environ.get("SECEDO_BENCH_CPU_LOCI", 28))  # pre-filter loci of the CPU sample
+# BASELINE.json configs[4]: dense-filter stress, 20 000 cells at 1x (20 000 reads per locus), 1.6 GB int32 count planes;
+# beyond the reference's 14-bit group ids -> wide pileups, and the CPU arm is the (widened) oracle port
+CFG5 = dict(
+    name="cfg5: 20000 cells x 1x (wide group ids), %d sub-batches of 4 chromosomes x %d pre-filter loci per GPU and step, one "
+         "similarity matrix (1.6 GB int32 count planes) per step",
+    n_cells=20000, coverage=1.0, loci_per_chr=int(os.environ.get("SECEDO_BENCH_LOCI_PER_CHR", 2048)),
+    sub_batches=int(os.environ.get("SECEDO_BENCH_SUB_BATCHES", 2)), cpu_sample_loci=int(os.environ.get("SECEDO_BENCH_CPU_LOCI", 3)),
+)
+
+
+def select_workload(name):
+    global CPU_SAMPLE_LOCI
+    if name == "cfg5":
+        WORKLOAD.update({k: v for k, v in CFG5.items() if k != "cpu_sample_loci"})
+        CPU_SAMPLE_LOCI = CFG5["cpu_sample_loci"]
 # human chromosome lengths (the reference's own table, pileup.cpp:30-34): proportions of the whole-genome workload
 CHROMOSOME_LENGTHS = [248956422, 242193529, 198295559, 190214555, 181538259, 170805979, 159345973, 145138636, 138394717,
                       133797422, 135086622, 133275309, 114364328, 107043718, 101991189, 90338345, 83257441, 80373285,
@@ -153,7 +168,7 @@ def run_reference_step(p, threads, want_matrix=False):
     from secedo_b200.pileup import Pileup
     w = WORKLOAD
     ident = np.arange(w["n_cells"], dtype=np.uint32)
-    if po.have_ref():
+    if po.have_ref() and not p.wide:  # the reference holds 14-bit group ids: beyond them only the widened port exists
         t0 = time.perf_counter()
         rf, _, _ = po.ref_filter(p, ident, w["theta"], 4, threads)
         f = Pileup(rf.chr_ptr, rf.row_ptr, rf.position, rf.read_id, rf.gid_base)
@@ -184,6 +199,11 @@ def reference_threads():
         return max(1, os.cpu_count() or 1)
 
 
+def metric_name():
+    w = WORKLOAD
+    return "similarity-matrix significant loci/s (%dK cells, %gx)" % (w["n_cells"] // 1000, w["coverage"])
+
+
 def workload_name():
     w = WORKLOAD
     return w["name"] % (w["sub_batches"], w["loci_per_chr"])
@@ -205,7 +225,7 @@ def main_reference(args):
     sample = (f"{CPU_SAMPLE_LOCI} pre-filter loci ({loci} significant, {p.n_entries} pileup entries) of the workload per "
               f"step; Filter::filter + computeSimilarityMatrix, num_threads={threads}")
     line = {
-        "impl": "reference", "metric": "similarity-matrix significant loci/s (8K cells, 0.5x)", "value": value,
+        "impl": "reference", "metric": metric_name(), "value": value,
         "unit": "loci/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": 1e3 * total / len(times), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f64 log-likelihoods over integer read-pair counts", "data": "synthetic",
@@ -425,7 +445,18 @@ def main_ours(args):
         pinned.append(t)
         return t.numpy()
     chunks, h2d_fixed, h2d_full = [], 0, 0
-    for rd in raw_dev:
+    # page-locked host copies of this rank's sub-batches: all of them, unless the ranks together would pin more than
+    # 40 % of the host memory that is free (then the end-to-end step runs over the first sub-batches only, and says so)
+    e2e_sub = SUB
+    try:
+        import psutil
+        avail = psutil.virtual_memory().available
+        per_sub = 6.2 * E / SUB
+        while e2e_sub > 1 and world * e2e_sub * per_sub > 0.4 * avail:
+            e2e_sub -= 1
+    except Exception:  # noqa: BLE001
+        pass
+    for rd in raw_dev[:e2e_sub]:
         host = rd.download()
         pos_p, rid_p, gb_p = pin(host.position), pin(host.read_id), pin(host.gid_base)
         h2d_full += host.row_ptr.nbytes + host.position.nbytes + host.read_id.nbytes + host.gid_base.nbytes + host.chr_ptr.nbytes
@@ -457,7 +488,8 @@ def main_ours(args):
     def top_up(target):
         while len(state["queue"]) < target and state["issued"] < len(state["run"]):
             # read ids stay in pinned host memory: the filter pulls those of the loci it keeps (zero copy)
-            state["queue"].append(ctx.upload_lazy_async(chunks[state["run"][state["issued"]][1]]))
+            chunk = chunks[state["run"][state["issued"]][1]]
+            state["queue"].append(ctx.upload_async(chunk) if chunk.wide else ctx.upload_lazy_async(chunk))
             state["issued"] += 1
 
     def e2e_step():
@@ -489,10 +521,10 @@ def main_ours(args):
     # bytes that crossed PCIe host -> device per step: the CSR without the read ids, plus the read ids of the
     # entries of the loci the filter kept (all cells take part: every entry of a kept locus is pulled once)
     pulled = state.get("pulled_entries", 0) // (E2E_WARMUP + e2e_steps)
-    h2d = h2d_fixed + 4 * pulled
+    h2d = h2d_full if chunks[0].wide else h2d_fixed + 4 * pulled  # wide pileups are uploaded whole
     d2h = N * N * 8 // world
     sig_e2e = rig.sum_over_ranks(acc_e2e["sig_loci"] // e2e_steps)
-    assert sig_e2e == sig_total, "the chromosome-wise end-to-end path must see the same significant loci"
+    assert e2e_sub < SUB or sig_e2e == sig_total, "the chromosome-wise end-to-end path must see the same significant loci"
     if rank == 0:
         M = shared.array if shared else out_bufs[state["n_out"] % 2]
         assert np.array_equal(M, M.T) and not np.diag(M).any() and np.isfinite(M).all(), \
@@ -604,8 +636,9 @@ def main_ours(args):
         cpu_value = cpu_loci / secs
         what = f"{CPU_SAMPLE_LOCI} pre-filter loci ({cpu_loci} significant, {sample_p.n_entries} entries) of the same workload, " \
                f"Filter::filter + computeSimilarityMatrix"
-        cpu = {"value": cpu_value, "unit": "loci/s", "cores": threads, "kind": kind, "sample": f"{what}, {secs:.1f} s"}
-        secs1, _, _ = run_reference_step(sample_p, 1)
+        cpu = {"value": cpu_value, "unit": "loci/s", "cores": threads if kind == "reference" else 1, "kind": kind,
+               "sample": f"{what}, {secs:.1f} s"}
+        secs1 = secs if kind == "port" else run_reference_step(sample_p, 1)[0]  # the port is single-threaded anyway
         cpu["single_thread"] = {"value": cpu_loci / secs1, "unit": "loci/s", "cores": 1, "seconds": secs1,
                                 "note": "num_threads = 1 (SURVEY 8d: the reference often slows down with threads); its tail "
                                         "cutoff differs from the all-cores run, the significant loci are the same"}
@@ -617,13 +650,13 @@ def main_ours(args):
         parity = {"ok": bool(f_s.n_loci == cpu_loci and diff <= 1e-6 * max(scale, 1e-300)), "max_abs_diff": diff,
                   "max_abs_reference": scale, "tolerance": "1e-6 * max|M_reference|", "num_threads": threads,
                   "significant_loci": int(f_s.n_loci), "reference_kind": kind,
-                  "what": "Filter::filter + computeSimilarityMatrix through the C ABI on the CPU baseline's sample (8 000 "
-                          "cells), against the matrix of that reference run"}
+                  "what": "Filter::filter + computeSimilarityMatrix through the C ABI on the CPU baseline's sample (same cell "
+                          "count as the workload), against the matrix of that CPU run"}
         assert parity["ok"], f"GPU path differs from the reference on the baseline sample: {parity}"
         value = sig_total * args.steps / (ms_dev * 1e-3)
-        e2e_value = sig_total * e2e_steps / (ms_e2e * 1e-3)
+        e2e_value = sig_e2e * e2e_steps / (ms_e2e * 1e-3)
         line = {
-            "metric": "similarity-matrix significant loci/s (8K cells, 0.5x)", "value": value, "unit": "loci/s",
+            "metric": metric_name(), "value": value, "unit": "loci/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_dev / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "int8 tensor-core counts (int32 accumulate) + f64 log-likelihood epilogue", "data": "synthetic",
@@ -653,7 +686,8 @@ def main_ours(args):
             "roofline": roofline, "cpu_baseline": cpu, "parity_vs_reference": parity,
             "reduce_checksum_ok": reduce_checksum_ok,
             "e2e": {"value": e2e_value, "unit": "loci/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-                    "ms_per_step": ms_e2e / e2e_steps, "steps": e2e_steps,
+                    "ms_per_step": ms_e2e / e2e_steps, "steps": e2e_steps, "sub_batches_per_step": e2e_sub,
+                    "significant_loci_per_step_all_gpus": sig_e2e,
                     "host_pileup_bytes_per_step": int(h2d_full),
                     "how": "host pinned pileup -> sgpu_pileup_upload_lazy_async per chromosome (copy stream, running ahead of "
                            "the kernels; the read ids stay in pinned host memory) -> filter (pulls the read ids of the loci it "
@@ -676,10 +710,14 @@ def main_ours(args):
 # --------------------------------------------------------------------------------------- whole genome, strong scaling
 def main_genome(args):
     """BASELINE.json configs[2] as ONE job: 23 chromosomes with the human length ratios (pileup.cpp:30-34), 8 000 cells at
-    0.5x, sharded over the GPUs, accumulated into one set of count planes per GPU, ONE epilogue at the end. Strong
-    scaling: the same genome at every N; `value` = significant loci of the whole genome / seconds for the whole matrix.
-    SECEDO_BENCH_GENOME_LOCI sets the pre-filter loci of the genome (default: chromosome 1 = 131 072 loci, the whole
-    genome 1.63 M pre-filter loci = 40 GB of pileup, resident in HBM at every N)."""
+    0.5x, cut into segments of 32 768 pre-filter loci INSIDE the chromosomes, contiguous runs of segments per GPU
+    (balanced to one segment), accumulated into one set of count planes per GPU through sgpu_counts_accumulate_range
+    (a segment that ends a chromosome decides that chromosome's tail cutoff, the others have none), ONE peer-memory
+    epilogue at the end. Strong scaling: the same genome at every N; `value` = significant loci of the whole genome /
+    seconds for the whole matrix. SECEDO_BENCH_GENOME_LOCI sets the pre-filter loci of the genome: default 1.63 M (40 GB
+    of pileup, resident in HBM at every N); 16 300 000 is the real size (~8 M significant loci, 390 GB): a GPU whose
+    share does not fit in HBM regenerates every batch of segments in front of its timed region and the per-batch device
+    times (CUDA events) are added up — the generator is not part of the path."""
     from secedo_b200 import dist as sdist
     rig = Rig()
     torch, dist, api, ctx = rig.torch, rig.dist, rig.api, rig.ctx
@@ -689,43 +727,99 @@ def main_genome(args):
     threads = reference_threads()
     ident = np.arange(N, dtype=np.uint32)
     lik = (w["L"], w["eps"], w["h"], w["theta"])
+    SEG, PER_CALL = 32768, 4
     total_len = float(sum(CHROMOSOME_LENGTHS))
     G = int(os.environ.get("SECEDO_BENCH_GENOME_LOCI", round(131072 * total_len / CHROMOSOME_LENGTHS[0])))
-    sizes = [max(1024, int(round(G * x / total_len))) for x in CHROMOSOME_LENGTHS]
-    MAX_CALL = 131072  # pre-filter loci per accumulate call (one operand panel of the GEMM)
-    if max(sizes) > MAX_CALL:
-        raise SystemExit(f"chromosome 1 would hold {max(sizes)} pre-filter loci: more than one accumulate call ({MAX_CALL}); "
-                         "lower SECEDO_BENCH_GENOME_LOCI")
-    parts = sdist.partition_chromosomes(sizes, world)  # longest-processing-time assignment, same on every rank
-    mine = parts[rank]
-    raw = [ctx.synth_pileup(N, w["coverage"], 1, sizes[c], n_clones=w["n_clones"], frac_somatic=w["frac_somatic"],
-                            frac_germline=w["frac_germline"], theta=w["theta"], spacing=w["spacing"], p_multi=w["p_multi"],
-                            p_mate=w["p_mate"], p_mate_mismatch=w["p_mate_mismatch"], seed=5000 + c) for c in mine]
+    n_seg = [max(1, int(round(G * x / total_len / SEG))) for x in CHROMOSOME_LENGTHS]
+    segments = [(c, k) for c, n in enumerate(n_seg) for k in range(n)]       # in genome order
+    all_calls = [segments[i:i + PER_CALL] for i in range(0, len(segments), PER_CALL)]  # the same batches whatever N
+    n_calls_all = len(all_calls)
+    lo, hi = len(all_calls) * rank // world, len(all_calls) * (rank + 1) // world
+    calls = [(lo + i, call) for i, call in enumerate(all_calls[lo:hi])]
+    bytes_per_call = PER_CALL * SEG * N * w["coverage"] * 6.1
+    resident = len(calls) * bytes_per_call < float(os.environ.get("SECEDO_BENCH_RESIDENT_BYTES", 110e9))
+
+    def generate(call):
+        # the (up to 4) segments of a batch are the "chromosomes" of one device pileup; the seed names the batch
+        # -> the same genome whatever the number of GPUs
+        idx, segs = call
+        return ctx.synth_pileup(N, w["coverage"], len(segs), SEG, n_clones=w["n_clones"], frac_somatic=w["frac_somatic"],
+                                frac_germline=w["frac_germline"], theta=w["theta"], spacing=w["spacing"], p_multi=w["p_multi"],
+                                p_mate=w["p_mate"], p_mate_mismatch=w["p_mate_mismatch"], seed=7000 + idx)
+
     flt = api.Filter(w["theta"], 4, ctx)
     counts = api.Counts(ctx, N)
     epi = sdist.SlabEpilogue(counts, device) if world > 1 else None
+    raw = [generate(call) for call in calls] if resident else None
+    def accumulate_call(call, src, st):
+        segs = call[1]
+        filtered, _ = flt.filter_device(src, ident)
+        # every segment is owned whole; only a segment that ends a chromosome has tail reads, and decides them itself
+        tails = [api.TAIL_AUTO if k == n_seg[c] - 1 else api.TAIL_NONE for c, k in segs]
+        s1 = counts.accumulate_range(filtered, w["L"], ident, w["eps"], w["h"], w["theta"], [0] * len(segs),
+                                     [api.TAIL_NONE] * len(segs), tails, args.path, num_threads=threads)
+        st["sig_loci"] += filtered.n_loci
+        st["ms_gemm"] += s1["ms_gemm"]
+        st["gemm_launches"] += s1["gemm_launches"]
+        filtered.free()
 
-    def genome():
-        st = {"sig_loci": 0, "ms_gemm": 0.0, "gemm_launches": 0}
-        counts.zero()
-        for src in raw:
-            filtered, _ = flt.filter_device(src, ident)
-            s1 = counts.accumulate(filtered, w["L"], ident, w["eps"], w["h"], w["theta"], threads, args.path)
-            st["sig_loci"] += filtered.n_loci
-            st["ms_gemm"] += s1["ms_gemm"]
-            st["gemm_launches"] += s1["gemm_launches"]
-            filtered.free()
+    def finish(st):
         if world > 1:
             epi.run(*lik, w["normalization"], same_stream=True)
         else:
             counts.finalize(*lik, w["normalization"], to_host=False)
+
+    def genome_resident():
+        st = {"sig_loci": 0, "ms_gemm": 0.0, "gemm_launches": 0}
+        counts.zero()
+        for call, parts in zip(calls, raw):
+            accumulate_call(call, parts, st)
+        finish(st)
         return st
 
     steps, warmup = max(1, min(args.steps, 5)), max(1, min(args.warmup, 2))
-    ms, acc, launches, clocks = rig.timed(genome, steps, warmup)
+    if resident:
+        ms, acc, launches, clocks = rig.timed(genome_resident, steps, warmup)
+        how = "whole share resident in HBM; barrier + events around the whole genome, max over ranks"
+    else:
+        # one pass (after a one-call warm-up): every batch of segments is generated, then timed on its own
+        steps, warmup = 1, 0
+        st = {"sig_loci": 0, "ms_gemm": 0.0, "gemm_launches": 0}
+        parts = generate(calls[0])
+        counts.zero()
+        accumulate_call(calls[0], parts, dict(st))
+        parts.free()
+        stop, lines = threading.Event(), []
+        th = threading.Thread(target=clocks_sampler, args=(stop, lines, rig.local_rank), daemon=True)
+        if rank == 0:
+            th.start()
+        rig.barrier()
+        launches0 = ctx.launch_count()
+        counts.zero()
+        ms_local = 0.0
+        for call in calls:
+            parts = generate(call)
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(stream)
+            accumulate_call(call, parts, st)
+            e1.record(stream)
+            e1.synchronize()
+            ms_local += e0.elapsed_time(e1)
+            parts.free()
+        rig.barrier()  # the slowest rank's accumulation ends here
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        finish(st)
+        e1.record(stream)
+        torch.cuda.synchronize()
+        ms = rig.max_over_ranks(ms_local) + rig.max_over_ranks(e0.elapsed_time(e1))
+        stop.set()
+        acc, launches, clocks = st, ctx.launch_count() - launches0, summarize_clocks(lines)
+        how = ("share larger than HBM: every batch of 4 segments generated in front of its own timed region; time = max over "
+               "ranks of the summed per-batch device times + the epilogue")
     sig_local = acc["sig_loci"] // steps
     sig_total = rig.sum_over_ranks(sig_local)
-    load = rig.max_over_ranks(float(sum(sizes[c] for c in mine))) / (sum(sizes) / world)
     ok = None
     if world > 1:
         a, b = epi.checksums()
@@ -738,12 +832,14 @@ def main_genome(args):
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "int8 tensor-core counts (int32 accumulate) + f64 log-likelihood epilogue", "data": "synthetic",
             "whole_genome_matrix_seconds": secs,
-            "config": {"workload": f"cfg3-genome: 8000 cells x 0.5x, 23 chromosomes with the human length ratios, {sum(sizes)} "
-                                   f"pre-filter loci ({sig_total} significant), resident in HBM; one step = the whole matrix",
-                       "n_cells": N, "coverage": w["coverage"], "chromosome_loci": sizes, "assignment": parts,
-                       "largest_share_over_mean": load, "num_threads_for_cutoff": threads, "p_multi": w["p_multi"],
-                       "parallelism": f"whole chromosomes over {world} GPU(s) (longest-processing-time assignment), one "
-                                      "epilogue over peer memory at the end",
+            "config": {"workload": f"cfg3-genome: 8000 cells x 0.5x, 23 chromosomes with the human length ratios in segments of "
+                                   f"{SEG} pre-filter loci, {len(segments) * SEG} pre-filter loci ({sig_total} significant); one "
+                                   "step = the whole matrix",
+                       "n_cells": N, "coverage": w["coverage"], "segments_per_chromosome": n_seg,
+                       "batches_of_4_segments_per_gpu": [n_calls_all * (r + 1) // world - n_calls_all * r // world for r in range(world)],
+                       "num_threads_for_cutoff": threads, "p_multi": w["p_multi"], "timing": how,
+                       "parallelism": f"contiguous runs of segments (pieces of chromosomes) over {world} GPU(s), "
+                                      "sgpu_counts_accumulate_range; one epilogue over peer memory at the end",
                        "host_topology": rig.numa},
             "gemm_ms_per_genome_rank0": acc["ms_gemm"] / steps, "reduce_checksum_ok": ok,
             "gpu_launches": int(launches), "clocks": clocks,
@@ -764,9 +860,12 @@ if __name__ == "__main__":
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--path", default="auto", choices=["auto", "scatter", "gemm"])
-    ap.add_argument("--workload", default="cfg3", choices=["cfg3", "cfg3-genome"])
+    ap.add_argument("--workload", default="cfg3", choices=["cfg3", "cfg3-genome", "cfg5"])
     ap.add_argument("--skip-extras", action="store_true", help="skip the spectral / EM side measurements")
     a = ap.parse_args()
+    select_workload(a.workload)
+    if a.workload == "cfg5":
+        a.skip_extras = True  # the eigen-solver / EM side measurements belong to the headline workload
     if a.impl == "reference":
         sys.exit(main_reference(a))
     if a.workload == "cfg3-genome":

@@ -146,6 +146,9 @@ int sgpu_pileup_from_bin(sgpu_ctx *ctx, uint32_t n_chr, const void *const *file_
 int sgpu_pileup_upload_wide(sgpu_ctx *ctx, uint32_t n_chr, const uint64_t *chr_ptr, const uint64_t *row_ptr,
                             const uint32_t *position, const uint32_t *read_id, const uint32_t *gid_base32,
                             sgpu_pileup **out);
+int sgpu_pileup_upload_wide_async(sgpu_ctx *ctx, uint32_t n_chr, const uint64_t *chr_ptr, const uint64_t *row_ptr,
+                                  const uint32_t *position, const uint32_t *read_id, const uint32_t *gid_base32,
+                                  sgpu_pileup **out); /* like sgpu_pileup_upload_async */
 int sgpu_pileup_download_wide(sgpu_ctx *ctx, const sgpu_pileup *p, uint64_t *chr_ptr, uint64_t *row_ptr,
                               uint32_t *position, uint32_t *read_id, uint32_t *gid_base32);
 int sgpu_pileup_is_wide(const sgpu_pileup *p);
@@ -206,12 +209,16 @@ int sgpu_counts_accumulate(sgpu_ctx *ctx, sgpu_counts *c, const sgpu_pileup *fil
  * too short to decide (no batch trigger that fires whatever happened before it lies inside its exact part, i.e. more
  * than max_fragment_length bp behind its first locus): call again with a longer suffix. On dense pileups (>= 4 *
  * num_threads new reads per locus) a suffix of a few max_fragment_length always suffices. */
+#define SGPU_TAIL_NONE 0xFFFFFFFFu /* tail_position: no read of this chromosome is a tail read for this piece */
+#define SGPU_TAIL_AUTO 0xFFFFFFFEu /* tail_position: the piece holds the END of the chromosome: decide the cutoff from the piece
+                                      itself with num_threads (SGPU_E_ARG if the piece is too short for that) */
 int sgpu_chromosome_cutoff(sgpu_ctx *ctx, const sgpu_pileup *ends, uint32_t max_fragment_length, uint32_t num_threads,
                            const uint8_t *whole, uint32_t *tail_position, uint8_t *resolved);
 int sgpu_counts_accumulate_range(sgpu_ctx *ctx, sgpu_counts *c, const sgpu_pileup *piece, uint32_t max_fragment_length,
                                  const uint32_t *group_id_to_pos, uint32_t n_groups, double mutation_rate,
-                                 double homozygous_rate, double seq_error_rate, const uint32_t *own_pos_begin,
-                                 const uint32_t *own_pos_end, const uint32_t *tail_position, int path, sgpu_stats *stats);
+                                 double homozygous_rate, double seq_error_rate, uint32_t num_threads /* only for SGPU_TAIL_AUTO */,
+                                 const uint32_t *own_pos_begin, const uint32_t *own_pos_end, const uint32_t *tail_position,
+                                 int path, sgpu_stats *stats);
 /* Device buffers to be summed element-wise across ranks before finalize:
  *   i32     int32 [n_i32]  planes of num_cells^2: S, D (first order), then, when read pairs that
  *                          overlap at >= 2 loci occurred, the class planes (2,0) (1,1) (0,2)
@@ -296,6 +303,27 @@ int sgpu_host_unregister(sgpu_ctx *ctx, void *host);
  * `slab`; the shares of all GPUs add up to the checksum of the whole sum. */
 int sgpu_counts_checksum(sgpu_ctx *ctx, sgpu_counts *c, const int32_t *const *peer_planes, uint32_t n_peers, uint32_t slab,
                          uint32_t n_slabs, uint64_t *checksum);
+
+/* ---- several GPUs behind one call (single process; SURVEY 8(b): sgpu_init(devices, n_dev)) --------------------------
+ * For host programs that are not a multi-process job — SECEDO's divide_cluster through the C++ shim. devices = NULL
+ * takes every visible GPU. sgpu_multi_similarity is computeSimilarityMatrix (similarity_matrix.cpp:295-433) on a
+ * FILTERED host pileup (the five CSR arrays of the header comment): the loci are cut into one piece per GPU inside the
+ * chromosomes (halos of max_fragment_length bp), every GPU uploads and accumulates its piece on a host
+ * thread of its own, then the epilogue over peer memory (sgpu_slab_raw / sgpu_slab_finalize with peer access enabled
+ * between the GPUs) writes each GPU's share of the matrix; out = num_cells^2 doubles, row-major, caller-owned host
+ * memory. Same result as sgpu_similarity on one GPU: integer counts bit for bit, the matrix bit for bit unless read
+ * pairs overlap at >= 4 loci (fp64 spill planes are added in GPU order: agrees to rounding). */
+typedef struct sgpu_multi sgpu_multi;
+int sgpu_multi_init(const int *devices, int n_devices, sgpu_multi **out);
+void sgpu_multi_shutdown(sgpu_multi *m);
+const char *sgpu_multi_last_error(const sgpu_multi *m);
+int sgpu_multi_size(const sgpu_multi *m);
+sgpu_ctx *sgpu_multi_ctx(sgpu_multi *m, int i); /* the context of the i-th GPU (e.g. for sgpu_filter on GPU 0) */
+int sgpu_multi_similarity(sgpu_multi *m, uint32_t n_chr, const uint64_t *chr_ptr, const uint64_t *row_ptr,
+                          const uint32_t *position, const uint32_t *read_id, const uint16_t *gid_base, uint32_t num_cells,
+                          uint32_t max_fragment_length, const uint32_t *group_id_to_pos, uint32_t n_groups,
+                          double mutation_rate, double homozygous_rate, double seq_error_rate, uint32_t num_threads,
+                          int normalization, int path, double *out, sgpu_stats *stats);
 
 /* LS / LD tables as evaluated on the device, n*n row-major (parity with similarity_matrix.cpp:117-170). */
 int sgpu_log_probs(sgpu_ctx *ctx, double mutation_rate, double homozygous_rate, double seq_error_rate,

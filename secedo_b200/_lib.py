@@ -83,6 +83,7 @@ SIGNATURES = {
     "sgpu_pileup_from_bin": (C.c_int, [_vp, C.c_uint32, _vp, _vp, _vp, C.c_uint32, C.c_uint32, _vp, _vp, C.POINTER(_vp),
                                        _u32p, _u32p]),
     "sgpu_pileup_upload_wide": (C.c_int, [_vp, C.c_uint32, _vp, _vp, _vp, _vp, _vp, C.POINTER(_vp)]),
+    "sgpu_pileup_upload_wide_async": (C.c_int, [_vp, C.c_uint32, _vp, _vp, _vp, _vp, _vp, C.POINTER(_vp)]),
     "sgpu_pileup_download_wide": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "sgpu_pileup_is_wide": (C.c_int, [_vp]),
     "sgpu_pileup_wrap_device": (C.c_int, [_vp, C.c_uint32, _vp, _vp, _vp, _vp, _vp, C.POINTER(_vp)]),
@@ -99,7 +100,7 @@ SIGNATURES = {
     "sgpu_counts_accumulate": (C.c_int, [_vp, _vp, _vp, C.c_uint32, _vp, C.c_uint32, C.c_double, C.c_double,
                                          C.c_double, C.c_uint32, C.c_int, C.POINTER(Stats)]),
     "sgpu_counts_accumulate_range": (C.c_int, [_vp, _vp, _vp, C.c_uint32, _vp, C.c_uint32, C.c_double, C.c_double,
-                                               C.c_double, _vp, _vp, _vp, C.c_int, C.POINTER(Stats)]),
+                                               C.c_double, C.c_uint32, _vp, _vp, _vp, C.c_int, C.POINTER(Stats)]),
     "sgpu_chromosome_cutoff": (C.c_int, [_vp, _vp, C.c_uint32, C.c_uint32, _vp, _vp, _vp]),
     "sgpu_counts_buffers": (C.c_int, [_vp, C.POINTER(_vp), _u64p, C.POINTER(_vp), _u64p, C.POINTER(_vp), _u64p]),
     "sgpu_counts_set_layout": (C.c_int, [_vp, _vp, C.c_int, C.c_int]),
@@ -124,6 +125,13 @@ SIGNATURES = {
     "sgpu_host_register": (C.c_int, [_vp, _vp, C.c_uint64, C.POINTER(_vp)]),
     "sgpu_host_unregister": (C.c_int, [_vp, _vp]),
     "sgpu_counts_checksum": (C.c_int, [_vp, _vp, _vp, C.c_uint32, C.c_uint32, C.c_uint32, _u64p]),
+    "sgpu_multi_init": (C.c_int, [_vp, C.c_int, C.POINTER(_vp)]),
+    "sgpu_multi_shutdown": (None, [_vp]),
+    "sgpu_multi_last_error": (C.c_char_p, [_vp]),
+    "sgpu_multi_size": (C.c_int, [_vp]),
+    "sgpu_multi_ctx": (_vp, [_vp, C.c_int]),
+    "sgpu_multi_similarity": (C.c_int, [_vp, C.c_uint32, _vp, _vp, _vp, _vp, _vp, C.c_uint32, C.c_uint32, _vp, C.c_uint32,
+                                        C.c_double, C.c_double, C.c_double, C.c_uint32, C.c_int, C.c_int, _vp, C.POINTER(Stats)]),
     "sgpu_log_probs": (C.c_int, [_vp, C.c_double, C.c_double, C.c_double, C.c_uint32, C.c_uint32, _vp, _vp]),
     "sgpu_expectation_maximization": (C.c_int, [_vp, _vp, _vp, C.c_uint32, C.c_double, _vp, C.c_uint32, C.c_uint32, _u32p,
                                                 C.POINTER(C.c_float)]),

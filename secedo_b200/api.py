@@ -117,8 +117,9 @@ class Context:
         """Upload on the context's copy stream without waiting: overlaps the kernels of the work issued
         next. The host arrays must stay alive (and should be pinned) until the pileup is first used."""
         h = C.c_void_p()
-        self.check(self._lib.sgpu_pileup_upload_async(self._h, p.n_chr, _ptr(p.chr_ptr), _ptr(p.row_ptr), _ptr(p.position),
-                                                      _ptr(p.read_id), _ptr(p.gid_base), C.byref(h)))
+        fn = self._lib.sgpu_pileup_upload_wide_async if p.wide else self._lib.sgpu_pileup_upload_async
+        self.check(fn(self._h, p.n_chr, _ptr(p.chr_ptr), _ptr(p.row_ptr), _ptr(p.position), _ptr(p.read_id), _ptr(p.gid_base),
+                      C.byref(h)))
         dp = DevicePileup(self, h)
         dp._keepalive = p
         return dp
@@ -169,6 +170,59 @@ class Context:
         dp = DevicePileup(self, h)
         dp._keepalive = keepalive
         return dp
+
+
+TAIL_NONE, TAIL_AUTO = 0xFFFFFFFF, 0xFFFFFFFE  # tail_position values of Counts.accumulate_range
+
+
+class MultiContext:
+    """Several GPUs behind one call, in ONE process (``sgpu_multi_*``): what the C++ shim's computeSimilarityMatrix uses
+    when more than one GPU is visible. ``devices=None`` takes all visible GPUs."""
+
+    def __init__(self, devices: Optional[Sequence[int]] = None):
+        self._lib = _lib.load()
+        self._h = C.c_void_p()
+        arr = None if devices is None else (C.c_int * len(devices))(*devices)
+        rc = self._lib.sgpu_multi_init(arr, 0 if devices is None else len(devices), C.byref(self._h))
+        if rc != 0:
+            msg = self._lib.sgpu_multi_last_error(self._h).decode() if self._h else "sgpu_multi_init failed"
+            if self._h:
+                self._lib.sgpu_multi_shutdown(self._h)
+                self._h = C.c_void_p()
+            raise SgpuError(rc, msg)
+
+    @property
+    def size(self) -> int:
+        return int(self._lib.sgpu_multi_size(self._h))
+
+    def similarity(self, filtered: Pileup, num_cells: int, max_fragment_length: int, group_id_to_pos: Sequence[int],
+                   mutation_rate: float, homozygous_rate: float, seq_error_rate: float, num_threads: int,
+                   normalization: str = "ADD_MIN", path: str = "auto", return_stats: bool = False):
+        if normalization not in NORMALIZATIONS:
+            raise ValueError("Invalid normalization: " + str(normalization))
+        assert not filtered.wide, "sgpu_multi_similarity takes the reference's 14-bit group ids"
+        g = np.ascontiguousarray(group_id_to_pos, np.uint32)
+        out = np.zeros((int(num_cells), int(num_cells)), np.float64)
+        st = Stats()
+        rc = self._lib.sgpu_multi_similarity(self._h, filtered.n_chr, _ptr(filtered.chr_ptr), _ptr(filtered.row_ptr),
+                                             _ptr(filtered.position), _ptr(filtered.read_id), _ptr(filtered.gid_base),
+                                             int(num_cells), int(max_fragment_length), _ptr(g), g.size, float(mutation_rate),
+                                             float(homozygous_rate), float(seq_error_rate), int(num_threads),
+                                             NORMALIZATIONS[normalization], PATHS[path], _ptr(out), C.byref(st))
+        if rc != 0:
+            raise SgpuError(rc, self._lib.sgpu_multi_last_error(self._h).decode())
+        return (out, st.as_dict()) if return_stats else out
+
+    def close(self) -> None:
+        if self._h:
+            self._lib.sgpu_multi_shutdown(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
 
 _default_ctx: Optional[Context] = None
@@ -314,9 +368,10 @@ class Counts:
     def accumulate_range(self, piece: PosDataLike, max_fragment_length: int, group_id_to_pos: Sequence[int],
                          mutation_rate: float, homozygous_rate: float, seq_error_rate: float,
                          own_pos_begin: Sequence[int], own_pos_end: Sequence[int], tail_position: Sequence[int],
-                         path: str = "auto") -> dict:
+                         path: str = "auto", num_threads: int = 1) -> dict:
         """A piece of its chromosomes (owned loci by position range + halos of max_fragment_length bp): adds the piece's
-        share of the counts. ``tail_position`` comes from :func:`chromosome_cutoff`. See include/secedo_b200.h."""
+        share of the counts. ``tail_position`` comes from :func:`chromosome_cutoff`, or is ``TAIL_AUTO`` for a piece that
+        holds the end of its chromosome (decided from the piece, with ``num_threads``). See include/secedo_b200.h."""
         ctx = self.ctx
         g = np.ascontiguousarray(group_id_to_pos, np.uint32)
         lo, hi = np.ascontiguousarray(own_pos_begin, np.uint32), np.ascontiguousarray(own_pos_end, np.uint32)
@@ -327,7 +382,8 @@ class Counts:
         try:
             ctx.check(ctx._lib.sgpu_counts_accumulate_range(ctx._h, self._h, dp._h, int(max_fragment_length), _ptr(g), g.size,
                                                             float(mutation_rate), float(homozygous_rate), float(seq_error_rate),
-                                                            _ptr(lo), _ptr(hi), _ptr(tp), PATHS[path], C.byref(st)))
+                                                            int(num_threads), _ptr(lo), _ptr(hi), _ptr(tp), PATHS[path],
+                                                            C.byref(st)))
         finally:
             if owned:
                 dp.free()

@@ -254,7 +254,7 @@ struct EventTimer {
 //   GEMM:    0.15 + L * 4 N_pad^2 / 4.0e12 (the tcgen05 kernel at ~4 POP/s issued) + 4.4e-9 per entry (staging)
 // The dense path wins for every BASELINE config except the 500-cell one; scatter wins where fewer than ~50 reads
 // cover a locus of several thousand cells.
-int choose_path(const sgpu_pileup *p, uint32_t num_cells) {
+int choose_path_impl(const sgpu_pileup *p, uint32_t num_cells) {
     if (p->n_loci == 0 || num_cells < 256) {
         return SGPU_PATH_SCATTER;
     }
@@ -267,6 +267,8 @@ int choose_path(const sgpu_pileup *p, uint32_t num_cells) {
 }
 
 } // namespace
+
+int sgpu_choose_path(const sgpu_pileup *p, uint32_t num_cells) { return choose_path_impl(p, num_cells); }
 
 extern "C" {
 
@@ -455,6 +457,14 @@ int sgpu_pileup_upload_wide(sgpu_ctx *ctx, uint32_t n_chr, const uint64_t *chr_p
         return sgpu_fail(ctx, SGPU_E_ARG, "upload_wide: gid_base32 missing");
     }
     return pileup_upload(ctx, n_chr, chr_ptr, row_ptr, position, read_id, nullptr, false, out, false, gid_base32);
+}
+
+int sgpu_pileup_upload_wide_async(sgpu_ctx *ctx, uint32_t n_chr, const uint64_t *chr_ptr, const uint64_t *row_ptr,
+                                  const uint32_t *position, const uint32_t *read_id, const uint32_t *gid_base32, sgpu_pileup **out) {
+    if (!gid_base32) {
+        return sgpu_fail(ctx, SGPU_E_ARG, "upload_wide: gid_base32 missing");
+    }
+    return pileup_upload(ctx, n_chr, chr_ptr, row_ptr, position, read_id, nullptr, true, out, false, gid_base32);
 }
 
 int sgpu_pileup_is_wide(const sgpu_pileup *p) { return p && p->wide ? 1 : 0; }
@@ -695,7 +705,7 @@ static int accumulate_impl(sgpu_ctx *ctx, sgpu_counts *c, const sgpu_pileup *fil
     s.n_loci = filtered->n_loci;
     s.n_entries = filtered->n_entries;
     if (path == SGPU_PATH_AUTO) {
-        path = choose_path(filtered, c->n);
+        path = choose_path_impl(filtered, c->n);
     }
     s.path_used = path;
 
@@ -750,7 +760,7 @@ int sgpu_counts_accumulate(sgpu_ctx *ctx, sgpu_counts *c, const sgpu_pileup *fil
 
 int sgpu_counts_accumulate_range(sgpu_ctx *ctx, sgpu_counts *c, const sgpu_pileup *piece, uint32_t max_fragment_length,
                                  const uint32_t *group_id_to_pos, uint32_t n_groups, double mutation_rate,
-                                 double homozygous_rate, double seq_error_rate, const uint32_t *own_pos_begin,
+                                 double homozygous_rate, double seq_error_rate, uint32_t num_threads, const uint32_t *own_pos_begin,
                                  const uint32_t *own_pos_end, const uint32_t *tail_position, int path, sgpu_stats *stats) {
     if (!own_pos_begin || !own_pos_end || !tail_position) {
         return sgpu_fail(ctx, SGPU_E_ARG, "accumulate_range: own_pos_begin, own_pos_end and tail_position are required (one value per chromosome)");
@@ -759,9 +769,9 @@ int sgpu_counts_accumulate_range(sgpu_ctx *ctx, sgpu_counts *c, const sgpu_pileu
     rs.own_pos_begin = own_pos_begin;
     rs.own_pos_end = own_pos_end;
     rs.tail_position = tail_position;
-    // num_threads is not needed: the cutoff it selects arrives as tail_position
+    // num_threads only matters where tail_position is SGPU_TAIL_AUTO: elsewhere the cutoff it selects arrives as a position
     return accumulate_impl(ctx, c, piece, max_fragment_length, group_id_to_pos, n_groups, mutation_rate, homozygous_rate,
-                           seq_error_rate, 1, path, stats, &rs);
+                           seq_error_rate, num_threads ? num_threads : 1, path, stats, &rs);
 }
 
 int sgpu_chromosome_cutoff(sgpu_ctx *ctx, const sgpu_pileup *ends, uint32_t max_fragment_length, uint32_t num_threads,

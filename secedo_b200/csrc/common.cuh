@@ -303,6 +303,9 @@ int sgpu_link_dense_codes(sgpu_ctx *ctx, const sgpu_pileup *p, LinkResult *lr);
 // (re)build the compact candidate list of the multi-locus correction from the reads that keep >= min_nst loci
 int sgpu_link_candidates(sgpu_ctx *ctx, LinkResult *lr, uint32_t min_nst);
 
+// abi.cu — the measured cost model behind SGPU_PATH_AUTO (only n_loci and n_entries of the pileup are looked at)
+int sgpu_choose_path(const sgpu_pileup *p, uint32_t num_cells);
+
 // scatter.cu — first-order counts by pair enumeration; only_tail_pairs: enumerate just the pairs of
 // two tail reads (used with sign = -1 to correct the GEMM path)
 int sgpu_scatter_pairs(sgpu_ctx *ctx, const sgpu_pileup *p, const LinkResult &lr, sgpu_counts *c,

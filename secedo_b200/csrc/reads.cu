@@ -140,7 +140,7 @@ __device__ __forceinline__ void cp_async_wait() {
     asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
 }
 
-constexpr uint32_t WIN_RING = 3;   // loci whose read ids are resident in shared memory: the owner and the two after it
+constexpr uint32_t WIN_RING = 3;   // at most: loci whose read ids are resident in shared memory (the owner and the two after it)
 constexpr uint32_t WIN_META = 64;  // owners per block of locus metadata kept in shared memory
 constexpr uint32_t WIN_META_N = WIN_META + WIN_RING + 1;
 
@@ -154,11 +154,12 @@ constexpr uint32_t WIN_META_N = WIN_META + WIN_RING + 1;
 __global__ void __launch_bounds__(WIN_THREADS, 2) link_window_kernel(
         const uint64_t *__restrict__ row_ptr, const uint32_t *__restrict__ position, const uint32_t *__restrict__ read_id,
         const uint8_t *__restrict__ lchr, uint64_t n_loci, uint32_t L, uint32_t loci_per_cta,
-        uint32_t slots /* power of two */, uint32_t id_cap /* multiple of 4, >= largest locus + 4 */, uint2 *__restrict__ links,
-        uint64_t cap, WinCounters *__restrict__ ctr) {
+        uint32_t slots /* power of two */, uint32_t id_cap /* multiple of 4, >= largest locus + 4 */,
+        uint32_t n_ring /* 1 .. WIN_RING slots of id_cap ids: as many as shared memory holds (huge loci: 1) */,
+        uint2 *__restrict__ links, uint64_t cap, WinCounters *__restrict__ ctr) {
     extern __shared__ __align__(16) uint32_t s_mem[];
-    uint32_t *ring = s_mem;                                                          // [WIN_RING][id_cap]
-    uint2 *rbuf = reinterpret_cast<uint2 *>(s_mem + WIN_RING * id_cap);              // [REC_BUF]
+    uint32_t *ring = s_mem;                                                          // [n_ring][id_cap]
+    uint2 *rbuf = reinterpret_cast<uint2 *>(s_mem + n_ring * id_cap);                // [REC_BUF]
     unsigned short *tab = reinterpret_cast<unsigned short *>(rbuf + REC_BUF);       // [slots]
     __shared__ uint64_t s_row[WIN_META_N + 1];
     __shared__ uint32_t s_pos[WIN_META_N];
@@ -191,7 +192,7 @@ __global__ void __launch_bounds__(WIN_THREADS, 2) link_window_kernel(
     auto prefetch = [&](uint64_t l) {
         if (l < n_loci && l - meta0 < WIN_META_N) {
             const uint64_t e0 = s_row[l - meta0], e1 = s_row[l - meta0 + 1];
-            uint32_t *dst = ring + (l % WIN_RING) * id_cap + (e0 & 3u);
+            uint32_t *dst = ring + (l % n_ring) * id_cap + (e0 & 3u);
             const uint32_t *src = read_id + e0;
             const uint32_t n = static_cast<uint32_t>(e1 - e0);
             const uint32_t head = aligned16 ? min(n, static_cast<uint32_t>((4 - (e0 & 3u)) & 3u)) : n;
@@ -211,8 +212,9 @@ __global__ void __launch_bounds__(WIN_THREADS, 2) link_window_kernel(
     };
     load_meta(meta0);
     __syncthreads();
-    prefetch(la);
-    prefetch(la + 1);
+    for (uint32_t k = 0; k + 1 < n_ring; ++k) { // the ring runs n_ring - 1 loci ahead of the owner
+        prefetch(la + k);
+    }
     for (uint64_t lo = la; lo < lb; ++lo) {
         if (lo - meta0 >= WIN_META) { // next block of metadata (nothing is in flight that reads the old one: see the barrier below)
             cp_async_wait<0>();
@@ -226,7 +228,7 @@ __global__ void __launch_bounds__(WIN_THREADS, 2) link_window_kernel(
         const uint32_t n = static_cast<uint32_t>(s_row[mi + 1] - e0);
         const uint32_t p0 = s_pos[mi];
         const uint32_t chr = s_chr[mi];
-        const uint32_t *ids = ring + (lo % WIN_RING) * id_cap + (e0 & 3u);
+        const uint32_t *ids = ring + (lo % n_ring) * id_cap + (e0 & 3u);
         // flush the staged links while nobody emits (uniform: s_cnt is read after the barrier that ended the last owner)
         if (s_cnt > REC_BUF / 2) {
             const uint32_t m = min(s_cnt, REC_BUF);
@@ -244,11 +246,15 @@ __global__ void __launch_bounds__(WIN_THREADS, 2) link_window_kernel(
                 s_cnt = 0;
             }
         }
-        prefetch(lo + 2); // into the slot of owner lo - 1, which the barrier at the end of its turn released
+        prefetch(lo + n_ring - 1); // into the slot of owner lo - 1, which the barrier at the end of its turn released
         for (uint32_t i = threadIdx.x; i < slots / 2; i += WIN_THREADS) {
             reinterpret_cast<uint32_t *>(tab)[i] = 0xFFFFFFFFu;
         }
-        cp_async_wait<1>(); // loci lo and lo + 1 have arrived (issued at least one owner ago)
+        if (n_ring == 1) {
+            cp_async_wait<0>(); // the owner's ids were requested just now
+        } else {
+            cp_async_wait<1>(); // everything but the locus requested just now has arrived (issued at least one owner ago)
+        }
         __syncthreads();
         // round 1: optimistic placement at the home slot
         for (uint32_t i = threadIdx.x; i < n; i += WIN_THREADS) {
@@ -290,12 +296,12 @@ __global__ void __launch_bounds__(WIN_THREADS, 2) link_window_kernel(
             const uint64_t a0 = meta_here ? s_row[l - meta0] : row_ptr[l];
             const uint64_t a1 = meta_here ? s_row[l - meta0 + 1] : row_ptr[l + 1];
             const uint32_t nl = static_cast<uint32_t>(a1 - a0);
-            if (l <= lo + 2 && meta_here) {
-                if (l == lo + 2) { // the locus prefetched in this turn
+            if (l + 1 <= lo + n_ring && meta_here) {
+                if (l + 1 == lo + n_ring) { // the locus prefetched in this turn
                     cp_async_wait<0>();
                     __syncthreads();
                 }
-                const uint32_t *wid = ring + (l % WIN_RING) * id_cap + (a0 & 3u);
+                const uint32_t *wid = ring + (l % n_ring) * id_cap + (a0 & 3u);
                 for (uint32_t ib = threadIdx.x; ib < nl; ib += 4 * WIN_THREADS) {
                     uint32_t id4[4], cur4[4], s4[4];
 #pragma unroll
@@ -823,7 +829,9 @@ __global__ void range_bounds_kernel(const uint64_t *__restrict__ chr_ptr, uint32
         }
         return lo;
     };
-    tail_locus[c] = lower(tail_position[c]);
+    if (tail_position[c] != SGPU_TAIL_AUTO) { // else: decided by cutoff_kernel from this piece, which holds the chromosome's end
+        tail_locus[c] = lower(tail_position[c]);
+    }
     own_lo[c] = lower(own_pos_begin[c]);
     own_hi[c] = max(own_lo[c], lower(own_pos_end[c]));
 }
@@ -1098,9 +1106,14 @@ int sgpu_link_reads(sgpu_ctx *ctx, const sgpu_pileup *p, uint32_t num_cells, uin
     while (slots < slot_factor * max_n && slots < 65536) {
         slots <<= 1;
     }
+    uint32_t n_ring = WIN_RING;
     auto win_smem = [&](uint32_t s) {
-        return static_cast<size_t>(WIN_RING) * id_cap * 4 + REC_BUF * sizeof(uint2) + static_cast<size_t>(s) * 2;
+        return static_cast<size_t>(n_ring) * id_cap * 4 + REC_BUF * sizeof(uint2) + static_cast<size_t>(s) * 2;
     };
+    // huge loci (cfg5: 20 000 reads): fewer resident loci before the table is allowed to shrink
+    while (n_ring > 1 && win_smem(slots) > WIN_SMEM_LIMIT) {
+        --n_ring;
+    }
     while (slots > 1024 && win_smem(slots) > WIN_SMEM_LIMIT) {
         slots >>= 1;
     }
@@ -1125,7 +1138,7 @@ int sgpu_link_reads(sgpu_ctx *ctx, const sgpu_pileup *p, uint32_t num_cells, uin
             const uint32_t loci_per_cta = static_cast<uint32_t>(ceil_div_u64(P, want));
             const unsigned wgrid = static_cast<unsigned>(ceil_div_u64(P, loci_per_cta));
             SGPU_LAUNCH(ctx, (link_window_kernel<<<wgrid, WIN_THREADS, smem, st>>>(p->d_row_ptr, p->d_position, p->d_read_id, out->lchr.p, P, L,
-                                                                                  loci_per_cta, slots, id_cap, links.p, cap, d_ctr.p)));
+                                                                                  loci_per_cta, slots, id_cap, n_ring, links.p, cap, d_ctr.p)));
         } else {
             DevBuf<uint64_t> keys;
             DevBuf<uint32_t> vals;
@@ -1326,10 +1339,39 @@ int sgpu_link_reads(sgpu_ctx *ctx, const sgpu_pileup *p, uint32_t num_cells, uin
         SGPU_CUDA(ctx, cudaMemcpyAsync(spec.p + p->n_chr, range->own_pos_end, p->n_chr * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
         SGPU_CUDA(ctx, cudaMemcpyAsync(spec.p + 2 * p->n_chr, range->tail_position, p->n_chr * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
         SGPU_CUDA(ctx, cudaMemsetAsync(n_tail_reads.p, 0, p->n_chr * sizeof(uint64_t), st));
+        // SGPU_TAIL_AUTO: the piece holds the END of the chromosome, the cutoff is decided from the piece itself (the
+        // part of it more than L bp behind its first locus is exact; everything is, if the piece starts the chromosome)
+        bool any_auto = false;
+        std::vector<uint8_t> h_whole(p->n_chr, 0);
+        for (uint32_t c = 0; c < p->n_chr; ++c) {
+            any_auto = any_auto || range->tail_position[c] == SGPU_TAIL_AUTO;
+            h_whole[c] = range->own_pos_begin[c] == 0;
+        }
+        DevBuf<uint8_t> d_whole, d_resolved;
+        DevBuf<uint64_t> exact_from;
+        if (any_auto) {
+            SGPU_CUDA(ctx, d_whole.alloc(p->n_chr, ctx));
+            SGPU_CUDA(ctx, d_resolved.alloc(p->n_chr, ctx));
+            SGPU_CUDA(ctx, exact_from.alloc(p->n_chr, ctx));
+            SGPU_CUDA(ctx, cudaMemcpyAsync(d_whole.p, h_whole.data(), p->n_chr, cudaMemcpyHostToDevice, st));
+            SGPU_LAUNCH(ctx, (exact_from_kernel<<<(p->n_chr + 63) / 64, 64, 0, st>>>(p->d_chr_ptr, p->n_chr, p->d_position, L, d_whole.p, exact_from.p)));
+            SGPU_LAUNCH(ctx, (cutoff_kernel<<<p->n_chr, CUT_THREADS, 0, st>>>(p->d_chr_ptr, p->n_chr, p->d_position, readbase.p, L, num_threads,
+                                                                              n_tail_reads.p, out->tail_locus.p, exact_from.p, d_resolved.p)));
+        }
         SGPU_LAUNCH(ctx, (range_bounds_kernel<<<(p->n_chr + 63) / 64, 64, 0, st>>>(p->d_chr_ptr, p->n_chr, p->d_position, spec.p, spec.p + p->n_chr,
                                                                                   spec.p + 2 * p->n_chr, out->tail_locus.p, own_lo.p, own_hi.p)));
         SGPU_LAUNCH(ctx, (owned_fill_kernel<<<blocks_for(P), TB, 0, st>>>(out->lchr.p, own_lo.p, own_hi.p, P, out->owned.p)));
+        std::vector<uint8_t> h_resolved(p->n_chr, 1);
+        if (any_auto) {
+            SGPU_CUDA(ctx, cudaMemcpyAsync(h_resolved.data(), d_resolved.p, p->n_chr, cudaMemcpyDeviceToHost, st));
+        }
         SGPU_CUDA(ctx, cudaStreamSynchronize(st)); // the caller's arrays are pageable
+        for (uint32_t c = 0; c < p->n_chr; ++c) {
+            if (range->tail_position[c] == SGPU_TAIL_AUTO && !h_resolved[c]) {
+                return sgpu_fail(ctx, SGPU_E_ARG, "chromosome %u of the piece: too short to decide the tail cutoff from it (SGPU_TAIL_AUTO); "
+                                 "use sgpu_chromosome_cutoff with a longer suffix", c);
+            }
+        }
     }
     if (NS) {
         SGPU_GB(p, SGPU_LAUNCH(ctx, (sp_finish_kernel<GB><<<blocks_for(NS), TB, 0, st>>>(out->sp_head.p, out->sp_entry.p, out->sp_locus.p, out->sp_drop.p,

@@ -144,7 +144,7 @@ __global__ void __launch_bounds__(TB) synth_fill_kernel(SynthP p, uint64_t n_loc
 extern "C" int sgpu_synth_pileup(sgpu_ctx *ctx, const sgpu_synth_params *sp, sgpu_pileup **out) {
     SGPU_CUDA(ctx, cudaSetDevice(ctx->device));
     cudaStream_t st = ctx->stream;
-    if (sp->n_cells == 0 || sp->n_cells > 16383 || sp->n_clones == 0 || sp->spacing < 2 || sp->n_chr == 0 || sp->n_chr > 255) {
+    if (sp->n_cells == 0 || sp->n_cells >= (1u << 27) || sp->n_clones == 0 || sp->spacing < 2 || sp->n_chr == 0 || sp->n_chr > 255) {
         return sgpu_fail(ctx, SGPU_E_ARG, "invalid synthetic pileup parameters");
     }
     SynthP p;

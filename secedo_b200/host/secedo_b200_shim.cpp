@@ -60,6 +60,41 @@ void check(int rc) {
     }
 }
 
+// all GPUs computeSimilarityMatrix spreads the loci over (SECEDO_B200_DEVICES=0,1,...; default: every visible GPU), or
+// null when there is only one
+sgpu_multi *multi() {
+    static bool tried = false;
+    static sgpu_multi *m = nullptr;
+    if (!tried) {
+        tried = true;
+        std::vector<int> devs;
+        if (const char *e = std::getenv("SECEDO_B200_DEVICES")) {
+            for (const char *p = e; *p;) {
+                devs.push_back(std::atoi(p));
+                while (*p && *p != ',') {
+                    ++p;
+                }
+                if (*p == ',') {
+                    ++p;
+                }
+            }
+        }
+        if (devs.size() == 1) {
+            return nullptr;
+        }
+        const int rc = sgpu_multi_init(devs.empty() ? nullptr : devs.data(), static_cast<int>(devs.size()), &m);
+        if (rc != SGPU_OK) {
+            std::fprintf(stderr, "secedo_b200: %s\n", sgpu_multi_last_error(m));
+            std::exit(1);
+        }
+        if (sgpu_multi_size(m) < 2) {
+            sgpu_multi_shutdown(m);
+            m = nullptr;
+        }
+    }
+    return m;
+}
+
 bool cache_enabled() {
     static const bool on = [] {
         const char *e = std::getenv("SECEDO_B200_NO_CACHE");
@@ -291,11 +326,25 @@ Matd computeSimilarityMatrix(const std::vector<std::vector<PosData>> &pos_data, 
                              const uint32_t num_threads, const std::string &marker, const std::string &normalization) {
     (void)marker;
     const int norm = normalization_code(normalization); // throws like the reference, before any work
+    Matd result(num_cells, num_cells);
+    logger()->trace("Normalizing similarity matrix..."); // similarity_matrix.cpp:272 (the epilogue is part of the call)
+    if (sgpu_multi *m = multi()) {
+        // several GPUs: pieces of the chromosomes, one per GPU, uploaded over the GPUs' own PCIe links
+        const Csr csr(pos_data);
+        ++g_uploads;
+        const int rc = sgpu_multi_similarity(m, static_cast<uint32_t>(csr.chr_ptr.size() - 1), csr.chr_ptr.data(), csr.row_ptr.data(),
+                                             csr.position.data(), csr.read_id.data(), csr.gid_base.data(), num_cells, max_fragment_length,
+                                             group_id_to_pos.data(), static_cast<uint32_t>(group_id_to_pos.size()), mutation_rate,
+                                             homozygous_rate, seq_error_rate, num_threads, norm, SGPU_PATH_AUTO, result.data(), nullptr);
+        if (rc != SGPU_OK) {
+            std::fprintf(stderr, "secedo_b200: error %d: %s\n", rc, sgpu_multi_last_error(m));
+            std::exit(1);
+        }
+        return result;
+    }
     sgpu_ctx *ctx = context();
     bool owned = false;
     sgpu_pileup *p = stage(pos_data, &owned);
-    Matd result(num_cells, num_cells);
-    logger()->trace("Normalizing similarity matrix..."); // similarity_matrix.cpp:272 (the epilogue is part of the call)
     check(sgpu_similarity(ctx, p, num_cells, max_fragment_length, group_id_to_pos.data(),
                           static_cast<uint32_t>(group_id_to_pos.size()), mutation_rate, homozygous_rate, seq_error_rate,
                           num_threads /* selects the reference's tail cutoff */, norm, SGPU_PATH_AUTO, result.data(), nullptr));

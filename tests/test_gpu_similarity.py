@@ -152,11 +152,16 @@ def test_edge_cases(gpu_ctx):
     Mb = api.compute_similarity_matrix(Pileup.from_pos_data([ren]), 4, 1000, ident, 0.01, 0.5, 0.01, 1, ctx=gpu_ctx)
     assert np.array_equal(Ma, Mb) and Ma.any()
     assert_matrix_close(Mb, po.similarity(Pileup.from_pos_data([ren]), 4, 1000, ident, 0.01, 0.5, 0.01, 1).M, TOL)
-    # a read id chained over >= L bp through intermediate loci: undefined in the reference -> error
-    p = Pileup.from_pos_data([[(100, [1, 2], [0 << 2, 1 << 2]), (700, [1, 3], [0 << 2, 2 << 2]),
-                               (1300, [1, 4], [0 << 2, 2 << 2])]])
-    with pytest.raises(api.SgpuError):
-        api.compute_similarity_matrix(p, 4, 1000, ident, 0.01, 0.5, 0.01, 1, ctx=gpu_ctx)
+    # a read id chained over >= L bp through intermediate loci: split where the reference retires the read (start + L <=
+    # position: the entry at 1300 opens a new read); same result as renaming that entry
+    chain = [[(100, [1, 2], [0 << 2, 1 << 2]), (700, [1, 3], [0 << 2, 2 << 2]), (1300, [1, 4], [0 << 2, 2 << 2]),
+              (1400, [5, 6], [1 << 2, 3 << 2]), (2600, [7, 8], [1 << 2, 3 << 2])]]
+    renamed = [[(100, [1, 2], [0 << 2, 1 << 2]), (700, [1, 3], [0 << 2, 2 << 2]), (1300, [901, 4], [0 << 2, 2 << 2]),
+                (1400, [5, 6], [1 << 2, 3 << 2]), (2600, [7, 8], [1 << 2, 3 << 2])]]
+    Mc = api.compute_similarity_matrix(Pileup.from_pos_data(chain), 4, 1000, ident, 0.01, 0.5, 0.01, 1, ctx=gpu_ctx)
+    Mr = api.compute_similarity_matrix(Pileup.from_pos_data(renamed), 4, 1000, ident, 0.01, 0.5, 0.01, 1, ctx=gpu_ctx)
+    assert np.array_equal(Mc, Mr)
+    assert_matrix_close(Mr, po.similarity(Pileup.from_pos_data(renamed), 4, 1000, ident, 0.01, 0.5, 0.01, 1).M, TOL)
     # cell outside the matrix
     p = Pileup.from_pos_data([[(100, [1, 2], [0 << 2, 3 << 2])]])
     with pytest.raises(api.SgpuError):

@@ -28,8 +28,9 @@ def test_shim_compiles_against_standin_headers():
 @pytest.mark.skipif(not os.path.exists(os.path.join(REF, "similarity_matrix.hpp")), reason="needs /root/reference")
 def test_shim_compiles_against_reference_headers():
     # the reference builds with -Wall -Wextra -Werror (CMakeLists.txt:8,47); so must the replacement TU
-    subprocess.run(["g++", "-std=c++20", "-fsyntax-only", "-Wall", "-Wextra", "-Werror", "-I" + REF, "-I" + INC, SHIM],
-                   check=True)
+    # include paths of the reference's own build (CMakeLists.txt: the source root and the vendored spdlog)
+    subprocess.run(["g++", "-std=c++20", "-fsyntax-only", "-Wall", "-Wextra", "-Werror", "-I" + REF,
+                    "-I" + os.path.join(REF, "third_party", "spdlog", "include"), "-I" + INC, SHIM], check=True)
 
 
 def _write_vec(f, a):
@@ -43,7 +44,18 @@ def _read_vec(f, dtype):
 
 
 @pytest.mark.gpu
-def test_shim_end_to_end(tmp_path):
+@pytest.mark.parametrize("devices", ["0", "all"])
+def test_shim_end_to_end(tmp_path, devices):
+    """devices = "0": one GPU, with the device-resident pileup cache checked by the driver (one upload for the whole
+    divide_cluster-style call sequence); "all": computeSimilarityMatrix spread over every visible GPU (sgpu_multi_*)"""
+    import torch
+    if devices == "all" and torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    env = dict(os.environ)
+    if devices == "0":
+        env["SECEDO_B200_DEVICES"] = "0"
+    else:
+        env.pop("SECEDO_B200_DEVICES", None)
     exe = str(tmp_path / "shim_driver")
     subprocess.run(["g++", "-std=c++20", "-O2", "-I" + COMPAT, "-I" + INC, os.path.join(ROOT, "tests", "cpp", "shim_driver.cpp"),
                     SHIM, "-L" + os.path.join(ROOT, "secedo_b200"), "-lsecedo_b200",
@@ -59,7 +71,7 @@ def test_shim_end_to_end(tmp_path):
         for a in (p.chr_ptr, p.row_ptr, p.position, p.read_id, p.gid_base, id_to_pos):
             _write_vec(f, a)
     L, T, eps, h, theta = 1000, 4, 0.01, 0.5, 0.01
-    subprocess.run([exe, fin, fout, str(keep.size), str(L), str(T), str(eps), str(h), str(theta), "ADD_MIN"], check=True)
+    subprocess.run([exe, fin, fout, str(keep.size), str(L), str(T), str(eps), str(h), str(theta), "ADD_MIN"], check=True, env=env)
     with open(fout, "rb") as f:
         got = Pileup(_read_vec(f, np.uint64), _read_vec(f, np.uint64), _read_vec(f, np.uint32), _read_vec(f, np.uint32),
                      _read_vec(f, np.uint16))
