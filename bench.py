@@ -540,6 +540,54 @@ def main_ours(args):
                   if cb * 256 + 255 > rb * 128 and rb * 128 < N and cb * 256 < N)
     kbs = (sig_local + 31) // 32
     executed_ops_step = 2.0 * n_tiles * 128 * 256 * kbs * 128  # MACs x 2 the tcgen05 kernel issues: tiles x k-blocks of 128 B
+    # ---- CPU baseline: the unmodified reference on a bounded sample (all cores; at N = 1 also one core), and the GPU path
+    # on the SAME sample at the SAME num_threads, compared with the matrix of that very reference run. At N > 1 the sample
+    # goes through the multi-GPU path: cut into one piece per rank inside its chromosome, accumulated by the ranks,
+    # peer-memory epilogue into the shared host matrix.
+    cpu, parity = None, None
+    sample_p = cpu_sample()
+    M_ref = None
+    if rank == 0:
+        if ALL_CPUS:
+            os.sched_setaffinity(0, ALL_CPUS)  # the reference gets every core this process was given
+        secs, cpu_loci, kind, M_ref = run_reference_step(sample_p, threads, want_matrix=True)
+        what = f"{CPU_SAMPLE_LOCI} pre-filter loci ({cpu_loci} significant, {sample_p.n_entries} entries) of the same workload, " \
+               f"Filter::filter + computeSimilarityMatrix"
+        cpu = {"value": cpu_loci / secs, "unit": "loci/s", "cores": threads if kind == "reference" else 1, "kind": kind,
+               "sample": f"{what}, {secs:.1f} s"}
+        if world == 1:
+            secs1 = secs if kind == "port" else run_reference_step(sample_p, 1)[0]  # the port is single-threaded anyway
+            cpu["single_thread"] = {"value": cpu_loci / secs1, "unit": "loci/s", "cores": 1, "seconds": secs1,
+                                    "note": "num_threads = 1 (SURVEY 8d: the reference often slows down with threads); its tail "
+                                            "cutoff differs from the all-cores run, the significant loci are the same"}
+    f_s, _ = flt.filter(sample_p, ident, "", threads)
+    if world == 1:
+        M_gpu = api.compute_similarity_matrix(f_s, N, w["L"], ident, w["eps"], w["h"], w["theta"], threads, "",
+                                              w["normalization"], ctx=ctx, path=args.path)
+    else:
+        pos = [f_s.position[int(f_s.chr_ptr[c]):int(f_s.chr_ptr[c + 1])] for c in range(f_s.n_chr)]
+        tail, ok = api.chromosome_cutoff(f_s, w["L"], threads, [True] * f_s.n_chr, ctx=ctx)
+        piece = sdist.plan_pieces(pos, world, w["L"])[rank]
+        counts.zero()
+        if piece:
+            counts.accumulate_range(Pileup.concat([f_s.loci_range(d["chrom"], d["lo"], d["hi"]) for d in piece]), w["L"], ident,
+                                    w["eps"], w["h"], w["theta"], [d["own_pos_begin"] for d in piece],
+                                    [d["own_pos_end"] for d in piece], [tail[d["chrom"]] for d in piece], args.path)
+        epi.run(*lik, w["normalization"], out_ptr=shared.dev_ptr, same_stream=True)
+        ctx.synchronize()
+        rig.barrier()
+        M_gpu = shared.array
+    if rank == 0:
+        scale = float(np.abs(M_ref).max())
+        diff = float(np.abs(M_gpu - M_ref).max())
+        parity = {"ok": bool(f_s.n_loci == cpu_loci and diff <= 1e-6 * max(scale, 1e-300)), "max_abs_diff": diff,
+                  "max_abs_reference": scale, "tolerance": "1e-6 * max|M_reference|", "num_threads": threads,
+                  "significant_loci": int(f_s.n_loci), "reference_kind": kind, "n_gpus": world,
+                  "what": "Filter::filter + computeSimilarityMatrix through the C ABI on the CPU baseline's sample (same cell "
+                          "count as the workload" + (f", cut into {world} pieces, one per rank, peer-memory epilogue" if world > 1 else "")
+                          + "), against the matrix of that CPU run"}
+        assert parity["ok"], f"GPU path differs from the reference on the baseline sample: {parity}"
+    rig.barrier()
     line = None
     if rank == 0:
         int8_peak, bf16_peak, how = int8_peak_tops(torch, device)
@@ -581,7 +629,7 @@ def main_ours(args):
         }
         # ---- Laplacian + the 7 leading eigenpairs of a matrix of this workload, resident in HBM ----
         spectral, em = None, None
-        if not args.skip_extras:
+        if not args.skip_extras and world == 1:
             try:
                 one = api.Counts(ctx, N)
                 f1, _ = flt.filter_device(raw_dev[0], ident)
@@ -629,30 +677,6 @@ def main_ours(args):
                 em = em or {"error": f"{type(ex).__name__}: {ex}"}
         # ---- CPU baseline: the unmodified reference on a bounded sample, all cores and one core; and the GPU path on
         # the SAME sample at the SAME num_threads, compared with the matrix of that very reference run ---------------
-        if ALL_CPUS:
-            os.sched_setaffinity(0, ALL_CPUS)  # the reference gets every core this process was given
-        sample_p = cpu_sample()
-        secs, cpu_loci, kind, M_ref = run_reference_step(sample_p, threads, want_matrix=True)
-        cpu_value = cpu_loci / secs
-        what = f"{CPU_SAMPLE_LOCI} pre-filter loci ({cpu_loci} significant, {sample_p.n_entries} entries) of the same workload, " \
-               f"Filter::filter + computeSimilarityMatrix"
-        cpu = {"value": cpu_value, "unit": "loci/s", "cores": threads if kind == "reference" else 1, "kind": kind,
-               "sample": f"{what}, {secs:.1f} s"}
-        secs1 = secs if kind == "port" else run_reference_step(sample_p, 1)[0]  # the port is single-threaded anyway
-        cpu["single_thread"] = {"value": cpu_loci / secs1, "unit": "loci/s", "cores": 1, "seconds": secs1,
-                                "note": "num_threads = 1 (SURVEY 8d: the reference often slows down with threads); its tail "
-                                        "cutoff differs from the all-cores run, the significant loci are the same"}
-        f_s, _ = flt.filter(sample_p, ident, "", threads)
-        M_gpu = api.compute_similarity_matrix(f_s, N, w["L"], ident, w["eps"], w["h"], w["theta"], threads, "",
-                                              w["normalization"], ctx=ctx, path=args.path)
-        scale = float(np.abs(M_ref).max())
-        diff = float(np.abs(M_gpu - M_ref).max())
-        parity = {"ok": bool(f_s.n_loci == cpu_loci and diff <= 1e-6 * max(scale, 1e-300)), "max_abs_diff": diff,
-                  "max_abs_reference": scale, "tolerance": "1e-6 * max|M_reference|", "num_threads": threads,
-                  "significant_loci": int(f_s.n_loci), "reference_kind": kind,
-                  "what": "Filter::filter + computeSimilarityMatrix through the C ABI on the CPU baseline's sample (same cell "
-                          "count as the workload), against the matrix of that CPU run"}
-        assert parity["ok"], f"GPU path differs from the reference on the baseline sample: {parity}"
         value = sig_total * args.steps / (ms_dev * 1e-3)
         e2e_value = sig_e2e * e2e_steps / (ms_e2e * 1e-3)
         line = {

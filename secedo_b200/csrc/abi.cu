@@ -387,6 +387,7 @@ static int pileup_upload(sgpu_ctx *ctx, uint32_t n_chr, const uint64_t *chr_ptr,
         st = ctx->copy_stream;
     }
     sgpu_pileup *p = new sgpu_pileup();
+    PileupOwner p_owner(ctx, p);
     p->n_chr = n_chr;
     p->n_loci = chr_ptr[n_chr];
     p->n_entries = p->n_loci ? row_ptr[p->n_loci] : 0;
@@ -401,11 +402,6 @@ static int pileup_upload(sgpu_ctx *ctx, uint32_t n_chr, const uint64_t *chr_ptr,
         void *alias = nullptr;
         if (cudaHostGetDevicePointer(&alias, const_cast<uint32_t *>(read_id), 0) != cudaSuccess) {
             cudaGetLastError();
-            sgpu_dev_free(ctx, p->d_chr_ptr);
-            sgpu_dev_free(ctx, p->d_row_ptr);
-            sgpu_dev_free(ctx, p->d_position);
-            delete[] p->h_chr_ptr;
-            delete p;
             return sgpu_fail(ctx, SGPU_E_ARG, "lazy upload: read_id must be page-locked, mapped host memory (cudaHostAlloc / cudaHostRegister)");
         }
         p->zc_read_id = static_cast<const uint32_t *>(alias);
@@ -441,7 +437,7 @@ static int pileup_upload(sgpu_ctx *ctx, uint32_t n_chr, const uint64_t *chr_ptr,
     } else {
         SGPU_CUDA(ctx, cudaStreamSynchronize(st));
     }
-    *out = p;
+    *out = p_owner.release();
     return SGPU_OK;
 }
 
@@ -501,6 +497,7 @@ int sgpu_pileup_wrap_device(sgpu_ctx *ctx, uint32_t n_chr, const uint64_t *host_
                             sgpu_pileup **out) {
     SGPU_CUDA(ctx, cudaSetDevice(ctx->device));
     sgpu_pileup *p = new sgpu_pileup();
+    PileupOwner p_owner(ctx, p);
     p->n_chr = n_chr;
     p->n_loci = host_chr_ptr[n_chr];
     p->h_chr_ptr = new uint64_t[n_chr + 1];
@@ -520,7 +517,7 @@ int sgpu_pileup_wrap_device(sgpu_ctx *ctx, uint32_t n_chr, const uint64_t *host_
     }
     SGPU_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     p->n_entries = last;
-    *out = p;
+    *out = p_owner.release();
     return SGPU_OK;
 }
 
@@ -634,8 +631,15 @@ int sgpu_counts_create(sgpu_ctx *ctx, uint32_t num_cells, sgpu_counts **out) {
     sgpu_counts *c = new sgpu_counts();
     c->n = num_cells;
     c->nn = static_cast<uint64_t>(num_cells) * num_cells;
-    SGPU_CUDA(ctx, cudaMalloc(&c->i32, std::max<uint64_t>(1, N_PLANES * c->nn) * sizeof(int32_t)));
-    SGPU_CUDA(ctx, cudaMalloc(&c->hist, SGPU_MAX_CLASS * SGPU_MAX_CLASS * sizeof(uint64_t)));
+    cudaError_t e = cudaMalloc(&c->i32, std::max<uint64_t>(1, N_PLANES * c->nn) * sizeof(int32_t));
+    if (e == cudaSuccess) {
+        e = cudaMalloc(&c->hist, SGPU_MAX_CLASS * SGPU_MAX_CLASS * sizeof(uint64_t));
+    }
+    if (e != cudaSuccess) { // nothing half-built is left behind
+        cudaGetLastError();
+        sgpu_counts_free(ctx, c);
+        return sgpu_fail(ctx, SGPU_E_CUDA, "sgpu_counts_create(%u cells): %s", num_cells, cudaGetErrorString(e));
+    }
     *out = c;
     return sgpu_counts_zero(ctx, c);
 }
@@ -652,6 +656,7 @@ int sgpu_counts_zero(sgpu_ctx *ctx, sgpu_counts *c) {
     c->planes_dirty = 2;
     c->have_params = false;
     c->fresh = true;
+    c->poisoned = false;
     return SGPU_OK;
 }
 
@@ -704,10 +709,14 @@ static int accumulate_impl(sgpu_ctx *ctx, sgpu_counts *c, const sgpu_pileup *fil
     std::memset(&s, 0, sizeof(s));
     s.n_loci = filtered->n_loci;
     s.n_entries = filtered->n_entries;
-    if (path == SGPU_PATH_AUTO) {
+    const bool auto_path = path == SGPU_PATH_AUTO;
+    if (auto_path) {
         path = choose_path_impl(filtered, c->n);
     }
     s.path_used = path;
+    if (c->poisoned) {
+        return sgpu_fail(ctx, SGPU_E_ARG, "the counts object holds a partial sum after a failed call: sgpu_counts_zero first");
+    }
 
     LinkResult lr;
     {
@@ -729,7 +738,18 @@ static int accumulate_impl(sgpu_ctx *ctx, sgpu_counts *c, const sgpu_pileup *fil
             SGPU_TRY(sgpu_scatter_pairs(ctx, filtered, lr, c, +1, false, &s.n_pairs_first));
             c->fresh = false;
         } else {
-            SGPU_TRY(sgpu_gemm_counts(ctx, filtered, lr, c, &s.n_pairs_first)); // incl. the tail x tail correction
+            // incl. the tail x tail correction. More than 127 reads of one cell at one locus do not fit int8: with
+            // SGPU_PATH_AUTO the first panel is checked before the count planes are touched and the call takes the
+            // scatter path instead (only looked at when a locus is large enough for that at all)
+            const bool may_overflow = auto_path && filtered->max_row > 127;
+            int rc = sgpu_gemm_counts(ctx, filtered, lr, c, &s.n_pairs_first, may_overflow);
+            if (rc == SGPU_E_COUNT_RANGE && may_overflow && !c->poisoned) {
+                s.path_used = SGPU_PATH_SCATTER;
+                SGPU_TRY(sgpu_link_dense_codes(ctx, filtered, &lr));
+                rc = sgpu_scatter_pairs(ctx, filtered, lr, c, +1, false, &s.n_pairs_first);
+                c->fresh = false;
+            }
+            SGPU_TRY(rc);
         }
         s.ms_first_order = t.stop();
         s.ms_stage = ctx->ms_stage;

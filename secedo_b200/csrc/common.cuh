@@ -177,6 +177,27 @@ struct sgpu_pileup {
     mutable uint32_t max_row = 0;  // entries of the largest locus (0 = not known yet; cached by reads.cu)
 };
 
+// Owners of half-built objects: an error return (SGPU_CUDA / SGPU_TRY) between `new` and the hand-over to the caller frees
+// the object and gives its device blocks back to the context's cache.
+extern "C" void sgpu_pileup_free(sgpu_ctx *ctx, sgpu_pileup *p);
+struct PileupOwner {
+    sgpu_ctx *ctx;
+    sgpu_pileup *p;
+    PileupOwner(sgpu_ctx *c, sgpu_pileup *q) : ctx(c), p(q) {}
+    PileupOwner(const PileupOwner &) = delete;
+    PileupOwner &operator=(const PileupOwner &) = delete;
+    ~PileupOwner() {
+        if (p) {
+            sgpu_pileup_free(ctx, p);
+        }
+    }
+    sgpu_pileup *release() {
+        sgpu_pileup *q = p;
+        p = nullptr;
+        return q;
+    }
+};
+
 // plane indices inside sgpu_counts::i32
 enum { PLANE_S = 0, PLANE_D = 1, PLANE_H2 = 2 /* (2,0),(1,1),(0,2) */, PLANE_H3 = 5 /* (3,0)..(0,3) */, N_PLANES = 9 };
 
@@ -187,6 +208,7 @@ struct sgpu_counts {
     int planes_used = 2;        // 2, 5 or 9: planes that can be non-zero
     int planes_dirty = N_PLANES; // planes to clear at the next sgpu_counts_zero
     bool fresh = false;         // S and D are all zero (nothing accumulated since sgpu_counts_zero)
+    bool poisoned = false;      // a failed call left a partial sum in the planes: only sgpu_counts_zero / free are accepted
     int32_t *packed = nullptr;  // upper triangles of the planes in use, for the cross-rank reduction (lazy)
     uint64_t packed_n = 0;
     uint32_t *sp_idx = nullptr; // non-zeros of the sparse (second / third order) planes as (index, value) lists (lazy)
@@ -360,9 +382,13 @@ struct GemmInput {
     uint64_t n_special;
     const uint32_t *tail_loci; // loci whose entries are subtracted as Z Z^T (ascending)
     uint64_t n_tail_loci;
+    bool check_range_first = false; // look at the int8 range check of the first panel BEFORE its tensor kernel runs
 };
-int sgpu_gemm_run(sgpu_ctx *ctx, const GemmInput &in, uint32_t num_cells, int32_t *S_plane, int32_t *D_plane, bool *fresh);
+int sgpu_gemm_run(sgpu_ctx *ctx, const GemmInput &in, uint32_t num_cells, int32_t *S_plane, int32_t *D_plane, bool *fresh,
+                  bool *poisoned = nullptr);
+// check_range_first: SGPU_E_COUNT_RANGE of the first panel is returned with the count planes untouched (SGPU_PATH_AUTO falls
+// back to the scatter path); otherwise, and for later panels, the counts object is marked as holding a partial sum
 int sgpu_gemm_counts(sgpu_ctx *ctx, const sgpu_pileup *p, const LinkResult &lr, sgpu_counts *c,
-                     uint64_t *n_pairs);
+                     uint64_t *n_pairs, bool check_range_first = false);
 
 static inline uint64_t ceil_div_u64(uint64_t a, uint64_t b) { return (a + b - 1) / b; }

@@ -456,6 +456,7 @@ int sgpu_filter_impl(sgpu_ctx *ctx, const sgpu_pileup *in, const uint32_t *h_id_
     const uint64_t Lk = ctx->h_scratch[0], Ek = ctx->h_scratch[1];
 
     sgpu_pileup *out = new sgpu_pileup();
+    PileupOwner out_owner(ctx, out);
     out->n_chr = in->n_chr;
     out->n_loci = Lk;
     out->n_entries = Ek;
@@ -496,6 +497,6 @@ int sgpu_filter_impl(sgpu_ctx *ctx, const sgpu_pileup *in, const uint32_t *h_id_
     if (avg_coverage) {
         *avg_coverage = Lk == 0 ? 0.0 : static_cast<double>(Ek) / static_cast<double>(Lk); // :188, in 64 bits
     }
-    *filtered = out;
+    *filtered = out_owner.release();
     return SGPU_OK;
 }

@@ -1100,7 +1100,8 @@ static int tile_list(sgpu_ctx *ctx, uint32_t N, uint32_t n_pad, uint32_t bm /* t
     return SGPU_OK;
 }
 
-int sgpu_gemm_counts(sgpu_ctx *ctx, const sgpu_pileup *p, const LinkResult &lr, sgpu_counts *c, uint64_t *n_pairs) {
+int sgpu_gemm_counts(sgpu_ctx *ctx, const sgpu_pileup *p, const LinkResult &lr, sgpu_counts *c, uint64_t *n_pairs,
+                     bool check_range_first) {
     if (n_pairs) {
         *n_pairs = 0; // not enumerated on this path
     }
@@ -1121,13 +1122,14 @@ int sgpu_gemm_counts(sgpu_ctx *ctx, const sgpu_pileup *p, const LinkResult &lr, 
     in.n_special = lr.n_special;
     in.tail_loci = lr.tail_loci.p;
     in.n_tail_loci = lr.n_tail_loci;
-    return sgpu_gemm_run(ctx, in, c->n, c->i32 + PLANE_S * c->nn, c->i32 + PLANE_D * c->nn, &c->fresh);
+    in.check_range_first = check_range_first;
+    return sgpu_gemm_run(ctx, in, c->n, c->i32 + PLANE_S * c->nn, c->i32 + PLANE_D * c->nn, &c->fresh, &c->poisoned);
 }
 
 // The GEMM path on any CSR of (cell group, letter) entries: loci [0, n_main) are counted, the loci listed
 // in tail_loci are subtracted as Z Z^T. Used for the pileup itself and for the derived pileup of locus
 // pairs of the second-order correction (multilocus.cu).
-int sgpu_gemm_run(sgpu_ctx *ctx, const GemmInput &in, uint32_t N, int32_t *S_plane, int32_t *D_plane, bool *fresh) {
+int sgpu_gemm_run(sgpu_ctx *ctx, const GemmInput &in, uint32_t N, int32_t *S_plane, int32_t *D_plane, bool *fresh, bool *poisoned) {
     cudaStream_t st = ctx->stream;
     const uint64_t P = in.n_main;
     if (P == 0 || in.n_entries == 0 || N < 2) {
@@ -1208,8 +1210,17 @@ int sgpu_gemm_run(sgpu_ctx *ctx, const GemmInput &in, uint32_t N, int32_t *S_pla
     SGPU_TRY(tile_list(ctx, N, n_pad, pairs ? 256 : BM, &d_tiles, &n_tiles));
     SGPU_TRACE(ctx, "gemm: tensor map + tiles");
 
-    // CUDA events on the launching stream around the staging kernel and around the tcgen05 kernel
-    std::vector<cudaEvent_t> evs;
+    // CUDA events on the launching stream around the staging kernel and around the tcgen05 kernel (destroyed on every
+    // way out of this function)
+    struct EventList {
+        std::vector<cudaEvent_t> v;
+        ~EventList() {
+            for (cudaEvent_t e : v) {
+                cudaEventDestroy(e);
+            }
+        }
+    } event_list;
+    std::vector<cudaEvent_t> &evs = event_list.v;
     auto mark = [&]() {
         cudaEvent_t e;
         cudaEventCreateWithFlags(&e, cudaEventDefault);
@@ -1292,6 +1303,15 @@ int sgpu_gemm_run(sgpu_ctx *ctx, const GemmInput &in, uint32_t N, int32_t *S_pla
         SGPU_LAUNCH(ctx, (stage_tile_kernel<<<(kbs_main + kt) * n_stripes, ST_THREADS, st_smem, st>>>(sa)));
         SGPU_CUDA(ctx, cudaGetLastError());
         SGPU_TRACE(ctx, "gemm: stage");
+        if (in.check_range_first && first) {
+            // the caller can still take the scatter path if a cell shows more than 127 reads at a locus: look before the
+            // first tensor kernel touches the count planes (only asked for when a locus is large enough for that at all)
+            SGPU_CUDA(ctx, cudaMemcpyAsync(&ctx->h_scratch[2], d_err.p, sizeof(int), cudaMemcpyDeviceToHost, st));
+            SGPU_CUDA(ctx, cudaStreamSynchronize(st));
+            if (static_cast<int>(ctx->h_scratch[2] & 0xFFFFFFFFu) == SGPU_E_COUNT_RANGE) {
+                return sgpu_fail(ctx, SGPU_E_COUNT_RANGE, "more than 127 reads of one cell at one locus: outside the int8 GEMM path (count planes untouched)");
+            }
+        }
 
         WorkList wl;
         wl.tiles = d_tiles;
@@ -1342,15 +1362,16 @@ int sgpu_gemm_run(sgpu_ctx *ctx, const GemmInput &in, uint32_t N, int32_t *S_pla
         ctx->ms_stage += a;
         ctx->ms_syrk += b;
     }
-    for (cudaEvent_t e : evs) {
-        cudaEventDestroy(e);
-    }
     const int err = static_cast<int>(ctx->h_scratch[2] & 0xFFFFFFFFu);
     if (err == SGPU_E_CELL_RANGE) {
         return sgpu_fail(ctx, err, "a group id is >= n_groups or maps to a cell >= num_cells (filter the pileup first)");
     }
     if (err != 0) {
-        return sgpu_fail(ctx, SGPU_E_COUNT_RANGE, "more than 127 reads of one cell at one locus: outside the int8 GEMM path, use the scatter path");
+        if (poisoned) {
+            *poisoned = true; // some panels have been added: the planes hold a partial sum
+        }
+        return sgpu_fail(ctx, SGPU_E_COUNT_RANGE, "more than 127 reads of one cell at one locus: outside the int8 GEMM path, use the scatter "
+                         "path (the counts object holds a partial sum: sgpu_counts_zero before using it again)");
     }
     return SGPU_OK;
 }

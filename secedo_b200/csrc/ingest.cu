@@ -116,6 +116,7 @@ extern "C" int sgpu_pileup_from_bin(sgpu_ctx *ctx, uint32_t n_chr, const void *c
     }
     // ---- device: raw bytes + offsets up, unpack
     sgpu_pileup *p = new sgpu_pileup();
+    PileupOwner p_owner(ctx, p);
     p->n_chr = n_chr;
     p->n_loci = P;
     p->n_entries = E;
@@ -170,6 +171,6 @@ extern "C" int sgpu_pileup_from_bin(sgpu_ctx *ctx, uint32_t n_chr, const void *c
     if (n_groups) {
         *n_groups = static_cast<uint32_t>(ctx->h_scratch[0] >> 32) + 1;
     }
-    *out = p;
+    *out = p_owner.release();
     return SGPU_OK;
 }

@@ -163,6 +163,7 @@ extern "C" int sgpu_synth_pileup(sgpu_ctx *ctx, const sgpu_synth_params *sp, sgp
     p.seed = sp->seed;
     const uint64_t P = static_cast<uint64_t>(sp->n_chr) * sp->loci_per_chr;
     sgpu_pileup *pl = new sgpu_pileup();
+    PileupOwner pl_owner(ctx, pl);
     pl->n_chr = sp->n_chr;
     pl->n_loci = P;
     pl->owns = true;
@@ -197,6 +198,6 @@ extern "C" int sgpu_synth_pileup(sgpu_ctx *ctx, const sgpu_synth_params *sp, sgp
     }
     SGPU_CUDA(ctx, cudaGetLastError());
     SGPU_CUDA(ctx, cudaStreamSynchronize(st));
-    *out = pl;
+    *out = pl_owner.release();
     return SGPU_OK;
 }

@@ -412,6 +412,41 @@ def test_int8_count_range(gpu_ctx, reps):
             api.compute_similarity_matrix(p, 4, 1000, ident, 0.01, 0.5, 0.01, 1, ctx=gpu_ctx, path="gemm")
 
 
+def test_auto_path_falls_back_when_int8_overflows(gpu_ctx):
+    """with SGPU_PATH_AUTO a pileup dense enough for the GEMM path but with > 127 reads of one cell at one
+    locus must not fail half way: the first panel's range check is read before the tensor kernel touches the planes and
+    the call takes the scatter path. The explicit GEMM path still refuses, and the counts object stays usable."""
+    cfg = SynthConfig(n_cells=300, coverage=2.0, n_loci=400, n_chr=1, frac_somatic=1.0, frac_germline=0.0, seed=33)
+    p = make_pileup(cfg)
+    l = 7
+    a = int(p.row_ptr[l])
+    extra = 200
+    rid = np.concatenate([p.read_id[:a], (4_100_000_000 + np.arange(extra)).astype(np.uint32), p.read_id[a:]])
+    gb = np.concatenate([p.gid_base[:a], np.full(extra, (0 << 2) | 1, np.uint16), p.gid_base[a:]])
+    row = p.row_ptr.copy()
+    row[l + 1:] += np.uint64(extra)
+    q = Pileup(p.chr_ptr, row, p.position, rid, gb)
+    ident = np.arange(cfg.n_cells, dtype=np.uint32)
+    o = po.similarity(q, cfg.n_cells, 1000, ident, 0.01, 0.5, 0.01, 2, "ADD_MIN")
+    c = api.Counts(gpu_ctx, cfg.n_cells)
+    st = c.accumulate(q, 1000, ident, 0.01, 0.5, 0.01, 2, "auto")
+    assert st["path_used"] == "scatter"
+    S1, D1, H, _ = c.download()
+    assert np.array_equal(S1, o.S1) and np.array_equal(D1, o.D1) and np.array_equal(H, o.H)
+    # without the overflow the same shape takes the GEMM path
+    c.zero()
+    assert c.accumulate(p, 1000, ident, 0.01, 0.5, 0.01, 2, "auto")["path_used"] == "gemm"
+    # explicit GEMM: refused; the object says that it holds a partial sum until it is zeroed
+    c.zero()
+    with pytest.raises(api.SgpuError):
+        c.accumulate(q, 1000, ident, 0.01, 0.5, 0.01, 2, "gemm")
+    with pytest.raises(api.SgpuError):
+        c.accumulate(p, 1000, ident, 0.01, 0.5, 0.01, 2, "gemm")
+    c.zero()
+    c.accumulate(p, 1000, ident, 0.01, 0.5, 0.01, 2, "gemm")
+    c.free()
+
+
 def test_huge_loci(gpu_ctx):
     """loci of > 11 000 entries: the shared-memory link table runs at its largest geometry"""
     cfg = SynthConfig(n_cells=3000, coverage=4.0, n_loci=8, n_chr=1, frac_somatic=1.0, frac_germline=0.0,
