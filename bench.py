@@ -379,10 +379,42 @@ def main_ours(args):
     counts = api.Counts(ctx, N)
     epi = sdist.SlabEpilogue(counts, device) if world > 1 else None
     last = {}
+    # Filter::filter of sub-batch k + 1 next to computeSimilarityMatrix of sub-batch k: a second context (own stream, own
+    # host thread) filters ahead, so that its memory-bound kernels run under the tensor-bound GEMM of the sub-batch before
+    # (they need 2 KB of shared memory per CTA and fit beside the GEMM's CTAs). Measured at N = 1: 42.30 against 42.62 ms per
+    # step (profiles/r2_bench_overlap_ab.txt) - the filter slows the read linking it runs beside by as much as it hides
+    # itself - so it is off by default; SECEDO_BENCH_OVERLAP=1 switches it on.
+    overlap = os.environ.get("SECEDO_BENCH_OVERLAP", "0") == "1"
+    ctx2 = api.Context(rig.local_rank) if overlap else None
+    flt2 = api.Filter(w["theta"], 4, ctx2) if overlap else None
+
+    def filtered_stream(sources):
+        """the sources filtered in order; with `overlap` one sub-batch ahead on the second context's thread"""
+        if not overlap or len(sources) < 2:
+            for src in sources:
+                yield flt.filter_device(src, ident)[0]
+            return
+        import queue
+        q = queue.Queue(maxsize=1)
+        def producer():
+            try:
+                for src in sources:
+                    q.put(flt2.filter_device(src, ident)[0])
+            except Exception as ex:  # noqa: BLE001
+                q.put(ex)
+        th = threading.Thread(target=producer, daemon=True)
+        th.start()
+        for _ in sources:
+            item = q.get()
+            if isinstance(item, Exception):
+                raise item
+            yield item
+        th.join()
 
     def accumulate_all(sources, st, free_sources=False, top_up=None):
+        feed = filtered_stream(sources) if not (free_sources or top_up) else None
         for src in sources:
-            filtered, _ = flt.filter_device(src, ident)
+            filtered = next(feed) if feed else flt.filter_device(src, ident)[0]
             if top_up:
                 top_up()
             s1 = counts.accumulate(filtered, w["L"], ident, w["eps"], w["h"], w["theta"], threads, args.path)
@@ -421,7 +453,10 @@ def main_ours(args):
         return st
 
     # ---- device-resident input ------------------------------------------------------------------------
+    l2_0 = ctx2.launch_count() if ctx2 else 0
     ms_dev, acc, launches, clocks = rig.timed(step_resident, args.steps, args.warmup)
+    if ctx2:  # warm-up launches of the second context are not part of the timed region
+        launches += (ctx2.launch_count() - l2_0) * args.steps // (args.steps + args.warmup)
     sig_local = acc["sig_loci"] // args.steps
     sig_total = rig.sum_over_ranks(sig_local)
 
@@ -690,7 +725,7 @@ def main_ours(args):
                 "pileup_entries_per_gpu_step": E, "sub_batches_per_step": SUB, "p_multi": w["p_multi"], "p_mate": w["p_mate"],
                 "theta": w["theta"], "eps": w["eps"], "h": w["h"], "max_fragment_length": w["L"],
                 "num_threads_for_cutoff": threads, "normalization": w["normalization"],
-                "path": last.get("path_used"),
+                "path": last.get("path_used"), "filter_overlaps_previous_gemm": overlap,
                 "parallelism": f"loci sharded by chromosome over {world} GPU(s); per step every GPU accumulates its "
                                f"{SUB} sub-batches into its own int32 count planes" + (
                     ", then the peer-memory epilogue: each GPU sums the planes of all GPUs over 1/%d of the matrix through "

@@ -47,55 +47,71 @@ struct FilterParams {
     int cell_proportion;
 };
 
-// util/is_significant.cpp:78-138 on uint16 counts (the reference's base_count is uint16 and wraps)
+// The significance test of util/is_significant.cpp:78-138 on the pooled counts of one locus (uint16 like the reference's
+// base_count, which wraps). Four integer gates on the sorted counts, then a likelihood ratio in fp64: the log-probability
+// of "every read shows the majority base" against the log of an evidence that is the sum of five genotype models, each a
+// prior times powers of per-read probabilities. The products and the sum are formed in the reference's order (fp64
+// multiplication and addition are not associative; the decision must be bit-identical).
+struct GenotypeModel { // prior * x^nx * y^ny * z^nz
+    double prior, x, y, z;
+    uint32_t nx, ny, nz;
+};
+__device__ __forceinline__ double model_probability(const GenotypeModel &m) {
+    double p = m.prior * pow(m.x, static_cast<double>(m.nx));
+    if (m.y >= 0) {
+        p = p * pow(m.y, static_cast<double>(m.ny));
+    }
+    if (m.z >= 0) {
+        p = p * pow(m.z, static_cast<double>(m.nz));
+    }
+    return p;
+}
+
 __device__ bool is_significant_dev(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, const FilterParams &fp) {
-    uint32_t b[4] = { c0 & 0xFFFFu, c1 & 0xFFFFu, c2 & 0xFFFFu, c3 & 0xFFFFu };
-    const uint32_t coverage = b[0] + b[1] + b[2] + b[3];
-    if (coverage < 2) {
+    // ascending: n[3] = majority base, n[2] = runner-up (5-comparator sorting network)
+    uint32_t n[4] = { c0 & 0xFFFFu, c1 & 0xFFFFu, c2 & 0xFFFFu, c3 & 0xFFFFu };
+    const uint32_t depth = n[0] + n[1] + n[2] + n[3];
+    if (depth < 2) {
         return false;
     }
-    // sorting network, ascending
-#define CSWAP(i, j)                 \
-    if (b[i] > b[j]) {              \
-        uint32_t t = b[i];          \
-        b[i] = b[j];                \
-        b[j] = t;                   \
-    }
-    CSWAP(0, 1) CSWAP(2, 3) CSWAP(0, 2) CSWAP(1, 3) CSWAP(1, 2)
-#undef CSWAP
-    if (b[2] == 0) {
+    auto order = [&](int i, int j) {
+        const uint32_t lo = min(n[i], n[j]), hi = max(n[i], n[j]);
+        n[i] = lo;
+        n[j] = hi;
+    };
+    order(0, 1);
+    order(2, 3);
+    order(0, 2);
+    order(1, 3);
+    order(1, 2);
+    const uint32_t major = n[3], second = n[2], rest = n[0] + n[1];
+    // gates (:92-103): a second base must exist, >= 5 non-majority reads, and the majority must lead 3 : 2
+    if (second == 0 || second + rest < 5 || static_cast<double>(major) < 1.5 * static_cast<double>(second)) {
         return false;
     }
-    if (b[2] + b[1] + b[0] < 5) {
-        return false;
-    }
-    if (static_cast<double>(b[3]) < 1.5 * static_cast<double>(b[2])) {
-        return false;
-    }
-    // threshold for the closest coverage, round half to even (:67-70,106-107)
-    double t = rint(coverage / 10.) - 1;
-    t = fmin(fmax(t, 0.), 19.);
-    const uint32_t threshold_idx = static_cast<uint32_t>(t);
+    // threshold column for the nearest multiple of 10 (round half to even, :67-70,106-107), clamped to the table
+    const double column = fmin(fmax(rint(depth / 10.) - 1, 0.), 19.);
 
-    const double theta = fp.theta;
-    const double hetero_prior = 0.0005;
-    const double mut_prior = 1e-6;
-    const double homo_prior = 1 - hetero_prior - mut_prior;
-
-    double log_prob_homozygous = b[3] * fp.log_one_minus_theta + (coverage - b[3]) * fp.log_theta_3;
-    log_prob_homozygous += fp.log_1_4;
-    log_prob_homozygous += fp.log_homo_prior;
-
-    const double t3 = theta / 3;
-    double prob_all_c1 = homo_prior * pow(1 - theta, static_cast<double>(b[3])) * pow(t3, static_cast<double>(coverage - b[3]));
-    double prob_hetero = hetero_prior * pow(0.5 - t3, static_cast<double>(b[3] + b[2])) * pow(t3, static_cast<double>(b[0] + b[1]));
-    double prob_homo_som = homo_prior * mut_prior * pow(0.75 - 2 * theta / 3, static_cast<double>(b[3]))
-            * pow(0.25, static_cast<double>(b[2])) * pow(t3, static_cast<double>(b[0] + b[1]));
-    double prob_hetero_som = hetero_prior * mut_prior * pow(0.5 - theta, static_cast<double>(b[3]))
-            * pow(0.25, static_cast<double>(b[1] + b[2])) * pow(t3, static_cast<double>(b[0]));
-    double prob_two_somatic = hetero_prior * mut_prior * mut_prior * pow(1 - theta, static_cast<double>(coverage));
-    double log_evidence = log(prob_all_c1 + prob_hetero + prob_homo_som + prob_hetero_som + prob_two_somatic);
-    return log_prob_homozygous - log_evidence < c_Ks[fp.cell_proportion][threshold_idx];
+    const double theta = fp.theta, err3 = theta / 3;
+    const double prior_het = 0.0005, prior_mut = 1e-6, prior_hom = 1 - prior_het - prior_mut;
+    // log P(all reads from one homozygous genotype): the constants come from the host (Filter's constructor)
+    double log_homozygous = major * fp.log_one_minus_theta + (depth - major) * fp.log_theta_3;
+    log_homozygous += fp.log_1_4;
+    log_homozygous += fp.log_homo_prior;
+    // the five models of the evidence, summed in this order (:112-136); y / z < 0 marks an unused factor
+    const GenotypeModel models[5] = {
+        { prior_hom, 1 - theta, err3, -1., major, depth - major, 0 },                                  // homozygous, errors only
+        { prior_het, 0.5 - err3, err3, -1., major + second, rest, 0 },                                 // germline heterozygous
+        { prior_hom * prior_mut, 0.75 - 2 * theta / 3, 0.25, err3, major, second, rest },               // homozygous + somatic
+        { prior_het * prior_mut, 0.5 - theta, 0.25, err3, major, n[1] + second, n[0] },                 // heterozygous + somatic
+        { prior_het * prior_mut * prior_mut, 1 - theta, -1., -1., depth, 0, 0 },                        // two somatic mutations
+    };
+    double evidence = model_probability(models[0]);
+#pragma unroll
+    for (int k = 1; k < 5; ++k) {
+        evidence = evidence + model_probability(models[k]);
+    }
+    return log_homozygous - log(evidence) < c_Ks[fp.cell_proportion][static_cast<uint32_t>(column)];
 }
 
 constexpr int FILTER_THREADS = 256;

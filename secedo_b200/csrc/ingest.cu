@@ -159,8 +159,7 @@ extern "C" int sgpu_pileup_from_bin(sgpu_ctx *ctx, uint32_t n_chr, const void *c
     SGPU_CUDA(ctx, cudaMemcpyAsync(&ctx->h_scratch[0], d_max.p, 2 * sizeof(unsigned int), cudaMemcpyDeviceToHost, st));
     SGPU_CUDA(ctx, cudaMemcpyAsync(&ctx->h_scratch[1], d_err.p, sizeof(int), cudaMemcpyDeviceToHost, st));
     SGPU_CUDA(ctx, cudaStreamSynchronize(st)); // the host vectors above are pageable and die here
-    if (static_cast<int>(ctx->h_scratch[1] & 0xFFFFFFFFu) != 0) {
-        sgpu_pileup_free(ctx, p);
+    if (static_cast<int>(ctx->h_scratch[1] & 0xFFFFFFFFu) != 0) { // p_owner frees the half-built pileup
         return sgpu_fail(ctx, SGPU_E_CELL_RANGE, "Cell id is too large (>= %u). Increase --max_cell_count if using the default mapping, "
                          "or fix the mapping in --merge_file", n_ids);
     }

@@ -286,6 +286,8 @@ class SlabEpilogue:
     def checksums(self):
         """(sum over ranks of the checksums of their own planes, sum over ranks of the checksums of the peer-summed
         shares): equal iff every rank sees, through its peer mappings, exactly what the others accumulated."""
+        self.counts.ctx.synchronize()
+        self.agree()  # the same planes on every rank (the ones a rank never touched are zero), and everybody has accumulated
         own = _as_i64(self.counts.checksum())
         summed = _as_i64(self.counts.checksum(self.peers, self.rank, self.world))
         t = torch.tensor([own, summed], dtype=torch.int64, device=self.device)

@@ -76,9 +76,12 @@ def main():
     # (integer sums, same fp64 expression); with them (fp64 spill planes, added in rank order) to rounding.
     shared = sdist.SharedHostMatrix(ctx, cfg.n_cells)
     cfg_exact = SynthConfig(n_cells=600, coverage=0.3, n_loci=700, n_chr=7, n_clones=3, p_multi=0.02, p_mate=0.05, seed=6)
-    for which, pp in (("spill", p), ("exact", make_pileup(cfg_exact))):
+    for which, pp in (("spill", p), ("exact", make_pileup(cfg_exact)), ("lopsided", p)):
         weights = [int(pp.chr_ptr[c + 1] - pp.chr_ptr[c]) for c in range(pp.n_chr)]
         mine = sdist.partition_chromosomes(weights, world)[rank]
+        if which == "lopsided":  # rank 0 holds everything, the others nothing: layouts (planes in use, spill) differ
+            mine = list(range(pp.n_chr)) if rank == 0 else []
+            which = "spill"
         local_pp = Pileup.concat([pp.loci_range(c, 0, 1 << 40) for c in mine]) if mine else Pileup.empty(0)
         for path in ("gemm", "scatter"):
             f_local, _ = flt.filter_device(local_pp, ident)

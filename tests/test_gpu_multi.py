@@ -17,7 +17,7 @@ def test_two_gpus_match_one_gpu():
                         "--master-addr", "127.0.0.1", "--master-port", "29533",
                         os.path.join(ROOT, "tests", "multi_gpu_check.py")], capture_output=True, text=True, timeout=900)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-4000:]
-    assert r.stdout.count("OK") == 7
+    assert r.stdout.count("OK") == 9
 
 
 @pytest.mark.gpu
