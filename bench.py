@@ -331,6 +331,7 @@ class Rig:
             time.sleep(0.25)  # let nvidia-smi come up BEFORE the barrier, so that all ranks start together
         self.barrier()
         torch.cuda.synchronize()
+        self.ctx.tensor_times()  # tensor kernels of the warm-up steps: not part of the timed statistics
         launches0 = self.ctx.launch_count()
         acc = {}
         e0.record(self.stream)
@@ -341,6 +342,12 @@ class Rig:
                     acc[k] = acc.get(k, 0) + v
         if finish:
             finish()
+        # the first-order tensor kernels run on a stream of their own (beside the next sub-batch's filter / staging): the
+        # region ends when the last of them has, and the ones no accumulate() statistics reported yet are added here
+        ms_left, n_left = self.ctx.tensor_times()
+        if "ms_gemm" in acc:
+            acc["ms_gemm"] += ms_left
+            acc["gemm_launches"] = acc.get("gemm_launches", 0) + n_left
         e1.record(self.stream)
         self.barrier()
         torch.cuda.synchronize()
@@ -726,6 +733,7 @@ def main_ours(args):
                 "theta": w["theta"], "eps": w["eps"], "h": w["h"], "max_fragment_length": w["L"],
                 "num_threads_for_cutoff": threads, "normalization": w["normalization"],
                 "path": last.get("path_used"), "filter_overlaps_previous_gemm": overlap,
+                "tensor_kernel_overlaps_next_sub_batch": os.environ.get("SECEDO_B200_ASYNC_GEMM", "1") != "0",
                 "parallelism": f"loci sharded by chromosome over {world} GPU(s); per step every GPU accumulates its "
                                f"{SUB} sub-batches into its own int32 count planes" + (
                     ", then the peer-memory epilogue: each GPU sums the planes of all GPUs over 1/%d of the matrix through "
@@ -847,6 +855,7 @@ def main_genome(args):
         parts = generate(calls[0])
         counts.zero()
         accumulate_call(calls[0], parts, dict(st))
+        ctx.tensor_times()
         parts.free()
         stop, lines = threading.Event(), []
         th = threading.Thread(target=clocks_sampler, args=(stop, lines, rig.local_rank), daemon=True)
@@ -862,6 +871,11 @@ def main_genome(args):
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record(stream)
             accumulate_call(call, parts, st)
+            # this batch's tensor kernel (on its own stream) belongs to this batch's timed region: wait for it, so that it
+            # does not run hidden under the untimed generation of the next batch
+            ms_left, n_left = ctx.tensor_times()
+            st["ms_gemm"] += ms_left
+            st["gemm_launches"] += n_left
             e1.record(stream)
             e1.synchronize()
             ms_local += e0.elapsed_time(e1)

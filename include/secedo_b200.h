@@ -80,8 +80,8 @@ typedef struct sgpu_stats {
     float ms_multi;             /* device time: multi-locus correction */
     float ms_epilogue;          /* device time: log-likelihood transform + normalisation */
     float ms_stage;             /* GEMM path: count staging + Hadamard transform kernels */
-    float ms_gemm;              /* GEMM path: the tcgen05 kernel alone (sum over panels) */
-    uint64_t gemm_launches;     /* GEMM path: number of tcgen05 kernel launches */
+    float ms_gemm;              /* GEMM path: the tcgen05 kernels that finished during the call (see sgpu_tensor_times) */
+    uint64_t gemm_launches;     /* GEMM path: number of those kernels */
 } sgpu_stats;
 
 /* parameters of the device-side synthetic pileup generator (bench / large tests), DESIGN.md */
@@ -101,6 +101,13 @@ int sgpu_set_stream(sgpu_ctx *ctx, void *cuda_stream);
 int sgpu_synchronize(sgpu_ctx *ctx);
 /* number of CUDA kernels this context has launched so far */
 uint64_t sgpu_launch_count(const sgpu_ctx *ctx);
+/* The first-order tensor kernel of sgpu_counts_accumulate runs on a stream of its own and the call returns without
+ * waiting for it, so that the filter / read-linking / staging kernels of the caller's NEXT batch run beside it
+ * (SECEDO_B200_ASYNC_GEMM=0 switches that off). Every call that reads or writes the count planes is ordered behind it;
+ * sgpu_synchronize waits for it. sgpu_stats.ms_gemm / gemm_launches therefore cover the tensor kernels that FINISHED
+ * during the call (usually the one of the batch before). This call waits for the kernels still in flight and returns
+ * (and resets) the time and number of the kernels no sgpu_stats has reported yet. */
+int sgpu_tensor_times(sgpu_ctx *ctx, float *ms, uint64_t *launches);
 
 /* ---- pileup staging (replaces the host vector<vector<PosData>>) --------------------------- */
 int sgpu_pileup_upload(sgpu_ctx *ctx, uint32_t n_chr, const uint64_t *chr_ptr, const uint64_t *row_ptr,

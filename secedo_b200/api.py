@@ -63,6 +63,13 @@ class Context:
         """CUDA kernels launched by this context so far."""
         return int(self._lib.sgpu_launch_count(self._h))
 
+    def tensor_times(self):
+        """(ms, launches) of the first-order tensor kernels that no ``accumulate`` statistics have reported yet; waits for
+        the kernels still in flight (they run on a stream of their own, beside the next batch's filter and staging)."""
+        ms, n = C.c_float(0), C.c_uint64(0)
+        self.check(self._lib.sgpu_tensor_times(self._h, C.byref(ms), C.byref(n)))
+        return float(ms.value), int(n.value)
+
     def synth_pileup(self, n_cells: int, coverage: float, n_chr: int, loci_per_chr: int, *, n_clones: int = 2,
                      frac_somatic: float = 0.5, frac_germline: float = 0.1, theta: float = 0.001,
                      spacing: int = 400, p_multi: float = 0.0, p_mate: float = 0.0, p_mate_mismatch: float = 0.2,

@@ -304,6 +304,26 @@ int sgpu_init(int device, sgpu_ctx **out) {
     ctx->stream = ctx->own_stream;
     SGPU_CUDA(ctx, cudaMallocHost(&ctx->h_scratch, 64 * sizeof(uint64_t)));
     SGPU_CUDA(ctx, cudaMalloc(&ctx->d_scratch, 64 * sizeof(uint64_t)));
+    {
+        // the tensor kernels' own stream, highest priority: a pending tensor CTA is placed before the CTAs of the staging
+        // kernels it shares the SMs with
+        int least = 0, greatest = 0;
+        SGPU_CUDA(ctx, cudaDeviceGetStreamPriorityRange(&least, &greatest));
+        SGPU_CUDA(ctx, cudaStreamCreateWithPriority(&ctx->tensor_stream, cudaStreamNonBlocking, greatest));
+        // kernels that are to run beside the tensor kernel must accept the shared-memory / L1 split its large operand
+        // ring forces on the SM (profiles/coresidency_probe.cu)
+        const char *ps = getenv("SECEDO_B200_PREFER_SHARED");
+        if (ps && ps[0] == '1') {
+            SGPU_CUDA(ctx, cudaDeviceSetCacheConfig(cudaFuncCachePreferShared));
+        }
+        const char *as = getenv("SECEDO_B200_ASYNC_GEMM");
+        ctx->async_gemm = !(as && as[0] == '0');
+        // operand ring of the CTA-pair kernel: 6 stages fill the SM; 5 leave 64 KB per SM to the kernels beside it
+        const char *gs = getenv("SECEDO_B200_GEMM_STAGES");
+        ctx->gemm_stages = gs ? static_cast<uint32_t>(std::min(6, std::max(4, atoi(gs)))) : (ctx->async_gemm ? 5u : 6u);
+        const char *ws = getenv("SECEDO_B200_WIN_SMEM_KB");
+        ctx->win_smem_limit = ws ? static_cast<uint32_t>(std::max(16, atoi(ws))) * 1024u : (ctx->async_gemm ? 60u * 1024u : 0u);
+    }
     return SGPU_OK;
 }
 
@@ -314,6 +334,23 @@ void sgpu_shutdown(sgpu_ctx *ctx) {
     if (ctx->own_stream) { // contexts that failed in sgpu_init carry only the error text
         cudaSetDevice(ctx->device);
         cudaStreamSynchronize(ctx->stream);
+        if (ctx->tensor_stream) {
+            cudaStreamSynchronize(ctx->tensor_stream);
+            sgpu_tensor_poll(ctx, true);
+            for (auto &j : ctx->tensor_jobs) { // only after a failed kernel
+                cudaEventDestroy(j.t0);
+                cudaEventDestroy(j.t1);
+                sgpu_dev_free(ctx, j.U);
+                sgpu_dev_free(ctx, j.err);
+            }
+            ctx->tensor_jobs.clear();
+            for (cudaEvent_t e : ctx->event_pool) {
+                cudaEventDestroy(e);
+            }
+            ctx->event_pool.clear();
+            cudaStreamDestroy(ctx->tensor_stream);
+            ctx->tensor_stream = nullptr;
+        }
         if (ctx->d2h_stream) {
             cudaStreamSynchronize(ctx->d2h_stream);
             cudaStreamDestroy(ctx->d2h_stream);
@@ -353,6 +390,7 @@ int sgpu_set_stream(sgpu_ctx *ctx, void *cuda_stream) {
     SGPU_CUDA(ctx, cudaSetDevice(ctx->device));
     // cached blocks are only safe to reuse in the order of ONE stream: drain the old one first
     SGPU_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    SGPU_TRY(sgpu_tensor_poll(ctx, true));
     ctx->stream = cuda_stream ? static_cast<cudaStream_t>(cuda_stream) : ctx->own_stream;
     return SGPU_OK;
 }
@@ -364,6 +402,21 @@ int sgpu_synchronize(sgpu_ctx *ctx) {
         SGPU_CUDA(ctx, cudaStreamSynchronize(ctx->copy_stream));
     }
     SGPU_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    SGPU_TRY(sgpu_tensor_poll(ctx, true)); // tensor kernels still in flight (sgpu_ctx::tensor_jobs)
+    return SGPU_OK;
+}
+
+int sgpu_tensor_times(sgpu_ctx *ctx, float *ms, uint64_t *launches) {
+    SGPU_CUDA(ctx, cudaSetDevice(ctx->device));
+    SGPU_TRY(sgpu_tensor_poll(ctx, true));
+    if (ms) {
+        *ms = ctx->ms_syrk;
+    }
+    if (launches) {
+        *launches = ctx->n_syrk;
+    }
+    ctx->ms_syrk = 0.f;
+    ctx->n_syrk = 0;
     return SGPU_OK;
 }
 
@@ -631,6 +684,7 @@ int sgpu_counts_create(sgpu_ctx *ctx, uint32_t num_cells, sgpu_counts **out) {
     sgpu_counts *c = new sgpu_counts();
     c->n = num_cells;
     c->nn = static_cast<uint64_t>(num_cells) * num_cells;
+    c->owner = ctx;
     cudaError_t e = cudaMalloc(&c->i32, std::max<uint64_t>(1, N_PLANES * c->nn) * sizeof(int32_t));
     if (e == cudaSuccess) {
         e = cudaMalloc(&c->hist, SGPU_MAX_CLASS * SGPU_MAX_CLASS * sizeof(uint64_t));
@@ -645,6 +699,7 @@ int sgpu_counts_create(sgpu_ctx *ctx, uint32_t num_cells, sgpu_counts **out) {
 }
 
 int sgpu_counts_zero(sgpu_ctx *ctx, sgpu_counts *c) {
+    SGPU_TRY(sgpu_tensor_join(ctx)); // a first-order tensor kernel may still be adding to the planes (sgpu_ctx::tensor_jobs)
     SGPU_CUDA(ctx, cudaSetDevice(ctx->device));
     // only the planes that were used since the last zeroing can be non-zero
     SGPU_CUDA(ctx, cudaMemsetAsync(c->i32, 0, static_cast<uint64_t>(c->planes_dirty) * c->nn * sizeof(int32_t), ctx->stream));
@@ -667,6 +722,7 @@ void sgpu_counts_free(sgpu_ctx *ctx, sgpu_counts *c) {
     if (ctx) {
         cudaSetDevice(ctx->device);
         cudaStreamSynchronize(ctx->stream);
+        sgpu_tensor_poll(ctx, true);
     }
     cudaFree(c->i32);
     cudaFree(c->hist);
@@ -718,6 +774,8 @@ static int accumulate_impl(sgpu_ctx *ctx, sgpu_counts *c, const sgpu_pileup *fil
         return sgpu_fail(ctx, SGPU_E_ARG, "the counts object holds a partial sum after a failed call: sgpu_counts_zero first");
     }
 
+    // tensor kernels of earlier batches that have finished meanwhile: their time goes into this call's statistics
+    SGPU_TRY(sgpu_tensor_poll(ctx, false));
     LinkResult lr;
     {
         EventTimer t(ctx->stream);
@@ -729,23 +787,23 @@ static int accumulate_impl(sgpu_ctx *ctx, sgpu_counts *c, const sgpu_pileup *fil
     s.n_multi_reads = lr.n_multi;
     s.n_tail_reads = lr.n_tail;
     s.n_span_splits = static_cast<int32_t>(std::min<uint64_t>(lr.n_span_splits, 0x7FFFFFFF));
-    ctx->ms_syrk = ctx->ms_stage = 0.f;
-    ctx->n_syrk = 0;
+    ctx->ms_stage = 0.f;
     {
         EventTimer t(ctx->stream);
         if (path == SGPU_PATH_SCATTER) {
             SGPU_TRY(sgpu_link_dense_codes(ctx, filtered, &lr));
+            SGPU_TRY(sgpu_tensor_join(ctx)); // the atomics go to the planes a tensor kernel in flight adds to
             SGPU_TRY(sgpu_scatter_pairs(ctx, filtered, lr, c, +1, false, &s.n_pairs_first));
             c->fresh = false;
         } else {
-            // incl. the tail x tail correction. More than 127 reads of one cell at one locus do not fit int8: with
-            // SGPU_PATH_AUTO the first panel is checked before the count planes are touched and the call takes the
-            // scatter path instead (only looked at when a locus is large enough for that at all)
-            const bool may_overflow = auto_path && filtered->max_row > 127;
-            int rc = sgpu_gemm_counts(ctx, filtered, lr, c, &s.n_pairs_first, may_overflow);
-            if (rc == SGPU_E_COUNT_RANGE && may_overflow && !c->poisoned) {
+            // incl. the tail x tail correction. More than 127 reads of one cell at one locus do not fit int8: the first
+            // panel is checked before the count planes are touched and, with SGPU_PATH_AUTO, the call takes the scatter
+            // path instead
+            int rc = sgpu_gemm_counts(ctx, filtered, lr, c, &s.n_pairs_first);
+            if (rc == SGPU_E_COUNT_RANGE && auto_path && !c->poisoned) {
                 s.path_used = SGPU_PATH_SCATTER;
                 SGPU_TRY(sgpu_link_dense_codes(ctx, filtered, &lr));
+                SGPU_TRY(sgpu_tensor_join(ctx));
                 rc = sgpu_scatter_pairs(ctx, filtered, lr, c, +1, false, &s.n_pairs_first);
                 c->fresh = false;
             }
@@ -753,14 +811,21 @@ static int accumulate_impl(sgpu_ctx *ctx, sgpu_counts *c, const sgpu_pileup *fil
         }
         s.ms_first_order = t.stop();
         s.ms_stage = ctx->ms_stage;
-        s.ms_gemm = ctx->ms_syrk;
-        s.gemm_launches = ctx->n_syrk;
     }
     {
+        // second / third order planes, spill plane, histogram: none of them is touched by the first-order tensor kernel
+        // that may still be running
         EventTimer t(ctx->stream);
         SGPU_TRY(sgpu_multilocus(ctx, filtered, lr, c, max_fragment_length, &s.n_pairs_multi));
         s.ms_multi = t.stop();
     }
+    // Tensor kernels retired during this call (with SECEDO_B200_ASYNC_GEMM=0: this call's own; otherwise mostly the one of
+    // the batch before; sgpu_tensor_times returns what is left)
+    SGPU_TRY(sgpu_tensor_poll(ctx, false));
+    s.ms_gemm = ctx->ms_syrk;
+    s.gemm_launches = ctx->n_syrk;
+    ctx->ms_syrk = 0.f;
+    ctx->n_syrk = 0;
     c->planes_dirty = std::max(c->planes_dirty, c->planes_used);
     if (stats) {
         *stats = s;
@@ -813,6 +878,11 @@ int sgpu_counts_buffers(sgpu_counts *c, int32_t **i32, uint64_t *n_i32, double *
     if (!c) {
         return SGPU_E_ARG;
     }
+    if (c->owner) {
+        // whoever reads the planes through these pointers is ordered behind the context's stream (a collective, a peer's
+        // kernel after a barrier): make that stream wait for a first-order tensor kernel that is still adding to them
+        SGPU_TRY(sgpu_tensor_join(c->owner));
+    }
     if (i32) {
         *i32 = c->i32;
     }
@@ -835,6 +905,7 @@ int sgpu_counts_buffers(sgpu_counts *c, int32_t **i32, uint64_t *n_i32, double *
 }
 
 int sgpu_counts_set_layout(sgpu_ctx *ctx, sgpu_counts *c, int planes_used, int want_spill) {
+    SGPU_TRY(sgpu_tensor_join(ctx)); // a first-order tensor kernel may still be adding to the planes (sgpu_ctx::tensor_jobs)
     SGPU_CUDA(ctx, cudaSetDevice(ctx->device));
     if (planes_used != 2 && planes_used != PLANE_H3 && planes_used != N_PLANES) {
         return sgpu_fail(ctx, SGPU_E_ARG, "planes_used must be 2, %d or %d", PLANE_H3, N_PLANES);
@@ -849,6 +920,7 @@ int sgpu_counts_set_layout(sgpu_ctx *ctx, sgpu_counts *c, int planes_used, int w
 }
 
 int sgpu_counts_pack_range(sgpu_ctx *ctx, sgpu_counts *c, int first_plane, int n_planes, int32_t **packed, uint64_t *n) {
+    SGPU_TRY(sgpu_tensor_join(ctx)); // a first-order tensor kernel may still be adding to the planes (sgpu_ctx::tensor_jobs)
     SGPU_CUDA(ctx, cudaSetDevice(ctx->device));
     if (first_plane < 0 || n_planes < 0 || first_plane + n_planes > c->planes_used) {
         return sgpu_fail(ctx, SGPU_E_ARG, "plane range [%d, %d) outside the %d planes in use", first_plane, first_plane + n_planes, c->planes_used);
@@ -877,6 +949,7 @@ int sgpu_counts_pack_range(sgpu_ctx *ctx, sgpu_counts *c, int first_plane, int n
 }
 
 int sgpu_counts_unpack_range(sgpu_ctx *ctx, sgpu_counts *c, int first_plane, int n_planes) {
+    SGPU_TRY(sgpu_tensor_join(ctx)); // a first-order tensor kernel may still be adding to the planes (sgpu_ctx::tensor_jobs)
     SGPU_CUDA(ctx, cudaSetDevice(ctx->device));
     if (first_plane < 0 || n_planes < 0 || first_plane + n_planes > c->planes_used) {
         return sgpu_fail(ctx, SGPU_E_ARG, "plane range [%d, %d) outside the %d planes in use", first_plane, first_plane + n_planes, c->planes_used);
@@ -905,6 +978,7 @@ int sgpu_counts_unpack(sgpu_ctx *ctx, sgpu_counts *c) {
 }
 
 int sgpu_counts_sparse_pack(sgpu_ctx *ctx, sgpu_counts *c, int first_plane, uint32_t **idx, int32_t **val, uint64_t *nnz) {
+    SGPU_TRY(sgpu_tensor_join(ctx)); // a first-order tensor kernel may still be adding to the planes (sgpu_ctx::tensor_jobs)
     SGPU_CUDA(ctx, cudaSetDevice(ctx->device));
     cudaStream_t st = ctx->stream;
     const int n_planes = c->planes_used - first_plane;
@@ -957,6 +1031,7 @@ int sgpu_counts_sparse_pack(sgpu_ctx *ctx, sgpu_counts *c, int first_plane, uint
 }
 
 int sgpu_counts_sparse_add(sgpu_ctx *ctx, sgpu_counts *c, int first_plane, const uint32_t *idx, const int32_t *val, uint64_t nnz) {
+    SGPU_TRY(sgpu_tensor_join(ctx)); // a first-order tensor kernel may still be adding to the planes (sgpu_ctx::tensor_jobs)
     SGPU_CUDA(ctx, cudaSetDevice(ctx->device));
     if (first_plane < 0 || first_plane > c->planes_used) {
         return sgpu_fail(ctx, SGPU_E_ARG, "first plane %d outside the %d planes in use", first_plane, c->planes_used);
@@ -971,6 +1046,7 @@ int sgpu_counts_sparse_add(sgpu_ctx *ctx, sgpu_counts *c, int first_plane, const
 }
 
 int sgpu_counts_download(sgpu_ctx *ctx, sgpu_counts *c, int32_t *S1, int32_t *D1, int32_t *H, uint64_t *hist) {
+    SGPU_TRY(sgpu_tensor_join(ctx)); // a first-order tensor kernel may still be adding to the planes (sgpu_ctx::tensor_jobs)
     SGPU_CUDA(ctx, cudaSetDevice(ctx->device));
     cudaStream_t st = ctx->stream;
     const uint64_t nn = c->nn, n = c->n;
@@ -1007,6 +1083,7 @@ int sgpu_counts_download(sgpu_ctx *ctx, sgpu_counts *c, int32_t *S1, int32_t *D1
 int sgpu_similarity_finalize(sgpu_ctx *ctx, sgpu_counts *c, uint32_t max_fragment_length, double mutation_rate,
                              double homozygous_rate, double seq_error_rate, int normalization, double *out,
                              sgpu_stats *stats) {
+    SGPU_TRY(sgpu_tensor_join(ctx)); // a first-order tensor kernel may still be adding to the planes (sgpu_ctx::tensor_jobs)
     SGPU_CUDA(ctx, cudaSetDevice(ctx->device));
     if (c->have_params && c->spill
         && (c->eps != mutation_rate || c->h != homozygous_rate || c->theta != seq_error_rate || c->L != max_fragment_length)) {
@@ -1023,6 +1100,7 @@ int sgpu_similarity_finalize(sgpu_ctx *ctx, sgpu_counts *c, uint32_t max_fragmen
 
 int sgpu_similarity_finalize_async(sgpu_ctx *ctx, sgpu_counts *c, uint32_t max_fragment_length, double mutation_rate,
                                    double homozygous_rate, double seq_error_rate, int normalization, double *out) {
+    SGPU_TRY(sgpu_tensor_join(ctx)); // a first-order tensor kernel may still be adding to the planes (sgpu_ctx::tensor_jobs)
     SGPU_CUDA(ctx, cudaSetDevice(ctx->device));
     if (!out) {
         return sgpu_fail(ctx, SGPU_E_ARG, "finalize_async needs a (page-locked) host buffer");
@@ -1053,6 +1131,13 @@ int sgpu_similarity(sgpu_ctx *ctx, const sgpu_pileup *filtered, uint32_t num_cel
     std::memset(&s, 0, sizeof(s));
     int rc = sgpu_counts_accumulate(ctx, c, filtered, max_fragment_length, group_id_to_pos, n_groups, mutation_rate,
                                     homozygous_rate, seq_error_rate, num_threads, path, &s);
+    if (rc == SGPU_OK) { // one-shot call: nothing to overlap the tensor kernel with; its time belongs to these statistics
+        rc = sgpu_tensor_poll(ctx, true);
+        s.ms_gemm += ctx->ms_syrk;
+        s.gemm_launches += ctx->n_syrk;
+        ctx->ms_syrk = 0.f;
+        ctx->n_syrk = 0;
+    }
     if (rc == SGPU_OK) {
         rc = sgpu_similarity_finalize(ctx, c, max_fragment_length, mutation_rate, homozygous_rate, seq_error_rate,
                                       normalization, out, &s);
@@ -1068,6 +1153,7 @@ int sgpu_similarity(sgpu_ctx *ctx, const sgpu_pileup *filtered, uint32_t num_cel
 int sgpu_slab_raw(sgpu_ctx *ctx, sgpu_counts *c, const int32_t *const *peer_planes, const double *const *peer_spill,
                   uint32_t n_peers, uint32_t slab, uint32_t n_slabs, uint32_t max_fragment_length, double mutation_rate,
                   double homozygous_rate, double seq_error_rate, double **extrema) {
+    SGPU_TRY(sgpu_tensor_join(ctx)); // a first-order tensor kernel may still be adding to the planes (sgpu_ctx::tensor_jobs)
     SGPU_CUDA(ctx, cudaSetDevice(ctx->device));
     return sgpu_slab_raw_impl(ctx, c, peer_planes, peer_spill, n_peers, slab, n_slabs, max_fragment_length, mutation_rate,
                               homozygous_rate, seq_error_rate, extrema);
@@ -1134,6 +1220,7 @@ int sgpu_host_unregister(sgpu_ctx *ctx, void *host) {
 
 int sgpu_counts_checksum(sgpu_ctx *ctx, sgpu_counts *c, const int32_t *const *peer_planes, uint32_t n_peers, uint32_t slab,
                          uint32_t n_slabs, uint64_t *checksum) {
+    SGPU_TRY(sgpu_tensor_join(ctx)); // a first-order tensor kernel may still be adding to the planes (sgpu_ctx::tensor_jobs)
     SGPU_CUDA(ctx, cudaSetDevice(ctx->device));
     if (n_peers > SGPU_MAX_PEERS || n_slabs == 0 || slab >= n_slabs) {
         return sgpu_fail(ctx, SGPU_E_ARG, "checksum: %u peers, slab %u of %u", n_peers, slab, n_slabs);
@@ -1217,6 +1304,7 @@ int sgpu_similarity_finalize_spectral(sgpu_ctx *ctx, sgpu_counts *c, uint32_t ma
                                       double homozygous_rate, double seq_error_rate, int normalization, double *out,
                                       uint32_t k, double tol, double *eigenvalues, double *eigenvectors, sgpu_stats *stats,
                                       sgpu_spectral_stats *spectral_stats) {
+    SGPU_TRY(sgpu_tensor_join(ctx)); // a first-order tensor kernel may still be adding to the planes (sgpu_ctx::tensor_jobs)
     SGPU_CUDA(ctx, cudaSetDevice(ctx->device));
     if (c->have_params && c->spill
         && (c->eps != mutation_rate || c->h != homozygous_rate || c->theta != seq_error_rate || c->L != max_fragment_length)) {

@@ -6,6 +6,7 @@
 #include <cstdarg>
 #include <cstdint>
 #include <cstdio>
+#include <deque>
 #include <map>
 #include <string>
 #include <unordered_map>
@@ -31,10 +32,27 @@ struct sgpu_ctx {
     uint64_t *h_scratch = nullptr; // 64 x u64, pinned
     uint64_t *d_scratch = nullptr; // 64 x u64, device
     uint64_t launches = 0;         // kernels launched by this context (sgpu_launch_count)
-    // device time of the dominant kernels since the last sgpu_kernel_times() reset, from CUDA events
+    // device time of the dominant kernels not yet reported through sgpu_stats / sgpu_tensor_times, from CUDA events
     // recorded on ctx->stream around the launches
     float ms_syrk = 0.f, ms_stage = 0.f;
     uint64_t n_syrk = 0;
+    // gemm.cu: the tensor kernel of a first-order accumulation runs on a stream of its own (highest priority), behind an
+    // event of the staging kernel, and the call returns without waiting for it: the filter / read linking / staging
+    // kernels of the NEXT batch (issue and latency bound, on ctx->stream) then run beside it on the same SMs (the tensor
+    // kernel keeps one CTA of 6 warps per SM and leaves ~95 % of the issue slots idle). A job owns what its kernel reads
+    // (the operand panel) until its end event has been seen; everything that touches the count planes first makes
+    // ctx->stream wait for the last job (sgpu_tensor_join). SECEDO_B200_ASYNC_GEMM=0: the kernel runs on ctx->stream.
+    cudaStream_t tensor_stream = nullptr;
+    bool async_gemm = true;
+    struct TensorJob {
+        void *U = nullptr;   // operand panel (context cache)
+        int *err = nullptr;  // [0] range check of the staging, [1] wave counter of the tensor kernel (context cache)
+        cudaEvent_t t0 = nullptr, t1 = nullptr; // around the kernel, on the stream it was launched on
+    };
+    std::deque<TensorJob> tensor_jobs;
+    std::vector<cudaEvent_t> event_pool; // recycled timing events
+    uint32_t gemm_stages = 6;            // operand ring of syrk2_kernel (SECEDO_B200_GEMM_STAGES = 4, 5, 6)
+    uint32_t win_smem_limit = 0;         // reads.cu: shared memory a link_window CTA may use (0 = default)
     // gemm.cu: rasterised list of upper-triangle output tiles for tile_cache_cells cells (device memory)
     void *tile_cache = nullptr;
     uint32_t tile_cache_n = 0, tile_cache_cells = 0, tile_cache_bm = 0;
@@ -72,6 +90,9 @@ void sgpu_trace_point(sgpu_ctx *ctx, const char *what);
     } while (0)
 
 int sgpu_fail(sgpu_ctx *ctx, int code, const char *fmt, ...);
+// gemm.cu — tensor kernels in flight on ctx->tensor_stream (see sgpu_ctx::tensor_jobs)
+int sgpu_tensor_poll(sgpu_ctx *ctx, bool wait_all); // retire finished jobs (timing, operand panel back to the cache)
+int sgpu_tensor_join(sgpu_ctx *ctx);                // ctx->stream waits (on the device) for the last job
 // make the context's stream wait for an asynchronously uploaded pileup
 #define SGPU_WAIT_PILEUP(ctx, p)                                                                   \
     do {                                                                                           \
@@ -204,6 +225,7 @@ enum { PLANE_S = 0, PLANE_D = 1, PLANE_H2 = 2 /* (2,0),(1,1),(0,2) */, PLANE_H3 
 struct sgpu_counts {
     uint32_t n = 0;             // num_cells
     uint64_t nn = 0;            // n*n
+    sgpu_ctx *owner = nullptr;  // the context it was created with (sgpu_counts_buffers has no context argument)
     int32_t *i32 = nullptr;     // N_PLANES planes of n*n, only the upper triangle (i<j) is meaningful
     int planes_used = 2;        // 2, 5 or 9: planes that can be non-zero
     int planes_dirty = N_PLANES; // planes to clear at the next sgpu_counts_zero
@@ -382,13 +404,13 @@ struct GemmInput {
     uint64_t n_special;
     const uint32_t *tail_loci; // loci whose entries are subtracted as Z Z^T (ascending)
     uint64_t n_tail_loci;
-    bool check_range_first = false; // look at the int8 range check of the first panel BEFORE its tensor kernel runs
+    bool may_defer = false;    // the tensor kernel of the last panel may still be running when the call returns (see
+                               // sgpu_ctx::tensor_jobs); false: the result is complete in the order of ctx->stream
 };
 int sgpu_gemm_run(sgpu_ctx *ctx, const GemmInput &in, uint32_t num_cells, int32_t *S_plane, int32_t *D_plane, bool *fresh,
                   bool *poisoned = nullptr);
-// check_range_first: SGPU_E_COUNT_RANGE of the first panel is returned with the count planes untouched (SGPU_PATH_AUTO falls
-// back to the scatter path); otherwise, and for later panels, the counts object is marked as holding a partial sum
-int sgpu_gemm_counts(sgpu_ctx *ctx, const sgpu_pileup *p, const LinkResult &lr, sgpu_counts *c,
-                     uint64_t *n_pairs, bool check_range_first = false);
+// SGPU_E_COUNT_RANGE of the first panel is returned with the count planes untouched (SGPU_PATH_AUTO falls back to the
+// scatter path); for later panels the counts object is marked as holding a partial sum
+int sgpu_gemm_counts(sgpu_ctx *ctx, const sgpu_pileup *p, const LinkResult &lr, sgpu_counts *c, uint64_t *n_pairs);
 
 static inline uint64_t ceil_div_u64(uint64_t a, uint64_t b) { return (a + b - 1) / b; }

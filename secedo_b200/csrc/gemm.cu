@@ -819,10 +819,11 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) syrk_kernel(const __grid_cons
 // bandwidth). Only the leader CTA issues MMAs; both CTAs' TMA loads report to the leader's barrier; the
 // leader's commits release the stage / publish the accumulators in both CTAs (multicast).
 // ------------------------------------------------------------------------------------------------
-constexpr int STAGES2 = 6;
 constexpr int HALF_B_BYTES = 128 * KB_BYTES;             // 16 KB
 constexpr int STAGE2_BYTES = A_BYTES + HALF_B_BYTES;     // 32 KB per CTA
-constexpr int SMEM2_BYTES = STAGES2 * STAGE2_BYTES + 1024 + 256;
+// the operand ring is a template parameter: 6 stages (193 KB) when the kernel has the SM to itself, 5 or 4 (161 / 129 KB) to
+// leave shared memory to the staging kernels of the next batch that run beside it (sgpu_ctx::tensor_jobs)
+constexpr int smem2_bytes(int stages) { return stages * STAGE2_BYTES + 1024 + 256; }
 constexpr uint32_t IDESC2 = (2u << 4) | (1u << 7) | (1u << 10) | ((256u >> 3) << 17) | ((256u >> 4) << 24); // M = 256, N = 256
 
 __device__ __forceinline__ uint32_t cluster_ctarank() {
@@ -871,6 +872,7 @@ __device__ __forceinline__ void umma_commit_2sm(uint32_t bar) { // arrives on `b
 }
 
 // work item of a pair: tiles are (row block of 256, column block of 256)
+template <int STAGES2>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 1)
         syrk2_kernel(const __grid_constant__ CUtensorMap map_u, const WorkList wl, int32_t *__restrict__ S, int32_t *__restrict__ D,
                      uint32_t n_cells, int epi_mode) {
@@ -1100,8 +1102,7 @@ static int tile_list(sgpu_ctx *ctx, uint32_t N, uint32_t n_pad, uint32_t bm /* t
     return SGPU_OK;
 }
 
-int sgpu_gemm_counts(sgpu_ctx *ctx, const sgpu_pileup *p, const LinkResult &lr, sgpu_counts *c, uint64_t *n_pairs,
-                     bool check_range_first) {
+int sgpu_gemm_counts(sgpu_ctx *ctx, const sgpu_pileup *p, const LinkResult &lr, sgpu_counts *c, uint64_t *n_pairs) {
     if (n_pairs) {
         *n_pairs = 0; // not enumerated on this path
     }
@@ -1122,7 +1123,7 @@ int sgpu_gemm_counts(sgpu_ctx *ctx, const sgpu_pileup *p, const LinkResult &lr, 
     in.n_special = lr.n_special;
     in.tail_loci = lr.tail_loci.p;
     in.n_tail_loci = lr.n_tail_loci;
-    in.check_range_first = check_range_first;
+    in.may_defer = true;
     return sgpu_gemm_run(ctx, in, c->n, c->i32 + PLANE_S * c->nn, c->i32 + PLANE_D * c->nn, &c->fresh, &c->poisoned);
 }
 
@@ -1141,8 +1142,9 @@ int sgpu_gemm_run(sgpu_ctx *ctx, const GemmInput &in, uint32_t N, int32_t *S_pla
     const uint32_t n_pad = (N + BN - 1) / BN * BN;
     // the tail k-blocks (Z and -Z) ride along with the first panel
     const uint32_t kbs_tail = static_cast<uint32_t>((in.n_tail_loci + LOCI_PER_KB - 1) / LOCI_PER_KB);
-    // panel: at most ~2 GB of Hadamard planes
-    uint64_t panel = (1ull << 31) / (4ull * n_pad) / LOCI_PER_KB * LOCI_PER_KB;
+    // panel: at most 3 GB of Hadamard planes (98 304 loci at 8 192 padded cells: a bench sub-batch of ~65 700 significant
+    // loci used to spill a few hundred loci into a second panel, i.e. a second read-modify-write pass over the planes)
+    uint64_t panel = (3ull << 30) / (4ull * n_pad) / LOCI_PER_KB * LOCI_PER_KB;
     if (const char *env = getenv("SECEDO_B200_PANEL_LOCI")) { // tests: force several panels on small inputs
         panel = std::max(1, atoi(env)) / LOCI_PER_KB * LOCI_PER_KB;
     }
@@ -1160,6 +1162,12 @@ int sgpu_gemm_run(sgpu_ctx *ctx, const GemmInput &in, uint32_t N, int32_t *S_pla
     const uint64_t n_chunks_max = (kbs_max + ck - 1) / ck;
     SGPU_TRACE(ctx, "gemm: enter");
 
+    // tensor kernels of earlier batches: retire the finished ones; never more than two operand panels in flight
+    SGPU_TRY(sgpu_tensor_poll(ctx, false));
+    while (ctx->tensor_jobs.size() >= 2) {
+        SGPU_CUDA(ctx, cudaEventSynchronize(ctx->tensor_jobs.front().t1));
+        SGPU_TRY(sgpu_tensor_poll(ctx, false));
+    }
     DevBuf<uint32_t> U;
     DevBuf<int> d_err;
     SGPU_CUDA(ctx, U.alloc(n_chunks_max * pl.chunk_words, ctx));
@@ -1203,30 +1211,60 @@ int sgpu_gemm_run(sgpu_ctx *ctx, const GemmInput &in, uint32_t N, int32_t *S_pla
     const bool pairs = env_pair ? env_pair[0] == '1' : (ctx->sm_count % 2 == 0); // default; SECEDO_B200_GEMM_PAIRS=0 for single CTAs
     const char *env_ws = getenv("SECEDO_B200_WAVE_SYNC");
     const bool wave_sync = env_ws ? env_ws[0] == '1' : true;
+    const int stages2 = ctx->gemm_stages == 4 ? 4 : ctx->gemm_stages == 5 ? 5 : 6;
     SGPU_CUDA(ctx, cudaFuncSetAttribute(syrk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
-    SGPU_CUDA(ctx, cudaFuncSetAttribute(syrk2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM2_BYTES));
+    SGPU_CUDA(ctx, cudaFuncSetAttribute(syrk2_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem2_bytes(4)));
+    SGPU_CUDA(ctx, cudaFuncSetAttribute(syrk2_kernel<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem2_bytes(5)));
+    SGPU_CUDA(ctx, cudaFuncSetAttribute(syrk2_kernel<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem2_bytes(6)));
     const uint2 *d_tiles = nullptr;
     uint32_t n_tiles = 0;
     SGPU_TRY(tile_list(ctx, N, n_pad, pairs ? 256 : BM, &d_tiles, &n_tiles));
     SGPU_TRACE(ctx, "gemm: tensor map + tiles");
 
-    // CUDA events on the launching stream around the staging kernel and around the tcgen05 kernel (destroyed on every
-    // way out of this function)
-    struct EventList {
-        std::vector<cudaEvent_t> v;
-        ~EventList() {
-            for (cudaEvent_t e : v) {
-                cudaEventDestroy(e);
+    // The tensor kernel goes to the context's tensor stream behind an event of its staging kernel and the call returns
+    // without waiting for it (in.may_defer: the first-order counts of sgpu_counts_accumulate; callers that read the
+    // result right away keep the kernel on ctx->stream). The panel and the error / wave-counter words belong to the job of
+    // the LAST panel; an error return before that job exists waits for the kernels already launched.
+    const bool defer = in.may_defer && ctx->async_gemm && ctx->tensor_stream != nullptr;
+    cudaStream_t gs = defer ? ctx->tensor_stream : st;
+    struct PanelOwner {
+        sgpu_ctx *ctx;
+        cudaStream_t gs;
+        void *U;
+        int *err;
+        bool launched = false;
+        ~PanelOwner() {
+            if (U || err) {
+                if (launched) {
+                    cudaStreamSynchronize(gs);
+                }
+                sgpu_dev_free(ctx, U);
+                sgpu_dev_free(ctx, err);
             }
         }
-    } event_list;
-    std::vector<cudaEvent_t> &evs = event_list.v;
-    auto mark = [&]() {
-        cudaEvent_t e;
-        cudaEventCreateWithFlags(&e, cudaEventDefault);
-        cudaEventRecord(e, st);
-        evs.push_back(e);
+    } owner{ ctx, gs, U.take(), d_err.take() };
+    uint32_t *const Up = static_cast<uint32_t *>(owner.U);
+    int *const errp = owner.err;
+    auto get_event = [&](cudaEvent_t *e) -> cudaError_t {
+        if (!ctx->event_pool.empty()) {
+            *e = ctx->event_pool.back();
+            ctx->event_pool.pop_back();
+            return cudaSuccess;
+        }
+        return cudaEventCreateWithFlags(e, cudaEventDefault);
     };
+    // staging time: events on ctx->stream, read after the synchronisation that follows every staging kernel
+    cudaEvent_t ev_s0 = nullptr, ev_s1 = nullptr;
+    SGPU_CUDA(ctx, get_event(&ev_s0));
+    SGPU_CUDA(ctx, get_event(&ev_s1));
+    struct EventReturn {
+        sgpu_ctx *ctx;
+        cudaEvent_t *a, *b;
+        ~EventReturn() {
+            ctx->event_pool.push_back(*a);
+            ctx->event_pool.push_back(*b);
+        }
+    } event_return{ ctx, &ev_s0, &ev_s1 };
     const uint32_t sms = static_cast<uint32_t>(ctx->sm_count);
     // stripes of cells per staging CTA: as few as a 104 KB tile allows
     const uint32_t n_stripes = (n_pad + ST_MAX_CELLS - 1) / ST_MAX_CELLS;
@@ -1241,7 +1279,7 @@ int sgpu_gemm_run(sgpu_ctx *ctx, const GemmInput &in, uint32_t N, int32_t *S_pla
     const uint64_t E = in.n_entries;
     SGPU_CUDA(ctx, cellbase.alloc(E + 8, ctx));
     SGPU_CUDA(ctx, seg.alloc(in.n_loci * (n_stripes + 1), ctx));
-    mark(); // folded into the first panel's staging time
+    SGPU_CUDA(ctx, cudaEventRecord(ev_s0, st)); // the partition is folded into the first panel's staging time
     {
         const unsigned grid = static_cast<unsigned>(std::min<uint64_t>(in.n_loci, static_cast<uint64_t>(sms) * 16));
         const size_t psmem = (static_cast<size_t>(PART_OUT) + in.n_groups) * sizeof(uint16_t);
@@ -1263,7 +1301,7 @@ int sgpu_gemm_run(sgpu_ctx *ctx, const GemmInput &in, uint32_t N, int32_t *S_pla
             pa.cells_per_cta = cells_per_cta;
             pa.cellbase = cellbase.p;
             pa.seg = seg.p;
-            pa.err = d_err.p;
+            pa.err = errp;
             SGPU_CUDA(ctx, cudaFuncSetAttribute(partition_kernel<GB>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(psmem)));
             SGPU_LAUNCH(ctx, (partition_kernel<GB><<<grid, 256, psmem, st>>>(pa)));
             return SGPU_OK;
@@ -1275,10 +1313,11 @@ int sgpu_gemm_run(sgpu_ctx *ctx, const GemmInput &in, uint32_t N, int32_t *S_pla
     for (uint64_t l0 = 0; l0 < P; l0 += panel) {
         const uint64_t l1 = std::min<uint64_t>(P, l0 + panel);
         const uint64_t nl = l1 - l0;
+        const bool last = l1 == P;
         const uint32_t kbs_main = static_cast<uint32_t>((nl + LOCI_PER_KB - 1) / LOCI_PER_KB);
         const uint32_t kt = first ? kbs_tail : 0;
         if (!first) {
-            mark(); // [3k] staging begins
+            SGPU_CUDA(ctx, cudaEventRecord(ev_s0, st));
         }
         StageArgs sa;
         sa.row_ptr = in.row_ptr;
@@ -1298,19 +1337,38 @@ int sgpu_gemm_run(sgpu_ctx *ctx, const GemmInput &in, uint32_t N, int32_t *S_pla
         sa.cells_per_cta = cells_per_cta;
         sa.n_stripes = n_stripes;
         sa.pl = pl;
-        sa.U = U.p;
-        sa.err = d_err.p;
+        sa.U = Up;
+        sa.err = errp;
         SGPU_LAUNCH(ctx, (stage_tile_kernel<<<(kbs_main + kt) * n_stripes, ST_THREADS, st_smem, st>>>(sa)));
         SGPU_CUDA(ctx, cudaGetLastError());
+        SGPU_CUDA(ctx, cudaEventRecord(ev_s1, st));
         SGPU_TRACE(ctx, "gemm: stage");
-        if (in.check_range_first && first) {
-            // the caller can still take the scatter path if a cell shows more than 127 reads at a locus: look before the
-            // first tensor kernel touches the count planes (only asked for when a locus is large enough for that at all)
-            SGPU_CUDA(ctx, cudaMemcpyAsync(&ctx->h_scratch[2], d_err.p, sizeof(int), cudaMemcpyDeviceToHost, st));
-            SGPU_CUDA(ctx, cudaStreamSynchronize(st));
-            if (static_cast<int>(ctx->h_scratch[2] & 0xFFFFFFFFu) == SGPU_E_COUNT_RANGE) {
-                return sgpu_fail(ctx, SGPU_E_COUNT_RANGE, "more than 127 reads of one cell at one locus: outside the int8 GEMM path (count planes untouched)");
+        // The range checks of the partition and staging kernels are looked at BEFORE the tensor kernel touches the count
+        // planes: an input outside the int8 path (more than 127 reads of one cell at one locus) or with bad group ids
+        // leaves the planes as they were (first panel; SGPU_PATH_AUTO then takes the scatter path) or holding the sum of
+        // the panels before it. The tensor stream is busy with the previous batch meanwhile.
+        SGPU_CUDA(ctx, cudaMemcpyAsync(&ctx->h_scratch[2], errp, sizeof(int), cudaMemcpyDeviceToHost, st));
+        SGPU_CUDA(ctx, cudaStreamSynchronize(st));
+        {
+            float ms = 0.f;
+            if (cudaEventElapsedTime(&ms, ev_s0, ev_s1) == cudaSuccess) {
+                ctx->ms_stage += ms;
             }
+        }
+        const int err = static_cast<int>(ctx->h_scratch[2] & 0xFFFFFFFFu);
+        if (err == SGPU_E_CELL_RANGE) {
+            return sgpu_fail(ctx, err, "a group id is >= n_groups or maps to a cell >= num_cells (filter the pileup first)");
+        }
+        if (err != 0) {
+            if (first) {
+                return sgpu_fail(ctx, SGPU_E_COUNT_RANGE, "more than 127 reads of one cell at one locus: outside the int8 GEMM path, use the "
+                                 "scatter path (count planes untouched)");
+            }
+            if (poisoned) {
+                *poisoned = true; // the panels before this one have been added: the planes hold a partial sum
+            }
+            return sgpu_fail(ctx, SGPU_E_COUNT_RANGE, "more than 127 reads of one cell at one locus: outside the int8 GEMM path, use the scatter "
+                             "path (the counts object holds a partial sum: sgpu_counts_zero before using it again)");
         }
 
         WorkList wl;
@@ -1336,42 +1394,80 @@ int sgpu_gemm_run(sgpu_ctx *ctx, const GemmInput &in, uint32_t N, int32_t *S_pla
         // the planes are zero right after sgpu_counts_zero: the first panel stores, later ones add in place
         const int epi = *fresh ? EPI_STORE : EPI_RMW;
         const unsigned grid = static_cast<unsigned>(std::min<uint64_t>(wl.n_work, units));
+        sgpu_ctx::TensorJob job;
+        SGPU_CUDA(ctx, get_event(&job.t0));
+        SGPU_CUDA(ctx, get_event(&job.t1));
+        ctx->tensor_jobs.push_back(job); // from here on the events belong to the job list
+        if (defer) {
+            SGPU_CUDA(ctx, cudaStreamWaitEvent(gs, ev_s1, 0)); // staged (and everything before it on ctx->stream: the zeroed planes)
+        }
         if (pairs && wave_sync) {
-            wl.wave_ctr = reinterpret_cast<unsigned int *>(d_err.p + 1);
-            SGPU_CUDA(ctx, cudaMemsetAsync(d_err.p + 1, 0, sizeof(int), st));
+            wl.wave_ctr = reinterpret_cast<unsigned int *>(errp + 1);
+            SGPU_CUDA(ctx, cudaMemsetAsync(errp + 1, 0, sizeof(int), gs));
         }
-        mark(); // [3k+1] staging done, GEMM begins
+        SGPU_CUDA(ctx, cudaEventRecord(job.t0, gs));
         if (pairs) {
-            SGPU_LAUNCH(ctx, (syrk2_kernel<<<2 * grid, GEMM_THREADS, SMEM2_BYTES, st>>>(map, wl, S_plane, D_plane, N, epi)));
+            if (stages2 == 4) {
+                SGPU_LAUNCH(ctx, (syrk2_kernel<4><<<2 * grid, GEMM_THREADS, smem2_bytes(4), gs>>>(map, wl, S_plane, D_plane, N, epi)));
+            } else if (stages2 == 5) {
+                SGPU_LAUNCH(ctx, (syrk2_kernel<5><<<2 * grid, GEMM_THREADS, smem2_bytes(5), gs>>>(map, wl, S_plane, D_plane, N, epi)));
+            } else {
+                SGPU_LAUNCH(ctx, (syrk2_kernel<6><<<2 * grid, GEMM_THREADS, smem2_bytes(6), gs>>>(map, wl, S_plane, D_plane, N, epi)));
+            }
         } else {
-            SGPU_LAUNCH(ctx, (syrk_kernel<<<grid, GEMM_THREADS, SMEM_BYTES, st>>>(map, wl, S_plane, D_plane, N, 1, epi)));
+            SGPU_LAUNCH(ctx, (syrk_kernel<<<grid, GEMM_THREADS, SMEM_BYTES, gs>>>(map, wl, S_plane, D_plane, N, 1, epi)));
         }
+        owner.launched = true;
         SGPU_CUDA(ctx, cudaGetLastError());
+        SGPU_CUDA(ctx, cudaEventRecord(ctx->tensor_jobs.back().t1, gs));
         *fresh = false;
-        mark(); // [3k+2] GEMM done
-        ++ctx->n_syrk;
+        if (last) { // the job of the last panel owns the panel
+            ctx->tensor_jobs.back().U = owner.U;
+            ctx->tensor_jobs.back().err = owner.err;
+            owner.U = nullptr;
+            owner.err = nullptr;
+        } else if (defer) {
+            SGPU_CUDA(ctx, cudaStreamWaitEvent(st, ctx->tensor_jobs.back().t1, 0)); // the next panel is staged into the same buffer
+        }
         first = false;
         SGPU_TRACE(ctx, "gemm: syrk");
     }
-    SGPU_CUDA(ctx, cudaMemcpyAsync(&ctx->h_scratch[2], d_err.p, sizeof(int), cudaMemcpyDeviceToHost, st));
-    SGPU_CUDA(ctx, cudaStreamSynchronize(st));
-    for (size_t k = 0; k + 2 < evs.size(); k += 3) {
-        float a = 0.f, b = 0.f;
-        cudaEventElapsedTime(&a, evs[k], evs[k + 1]);
-        cudaEventElapsedTime(&b, evs[k + 1], evs[k + 2]);
-        ctx->ms_stage += a;
-        ctx->ms_syrk += b;
+    if (!defer) { // the caller goes on with the result on ctx->stream: nothing stays in flight
+        SGPU_CUDA(ctx, cudaStreamSynchronize(st));
+        SGPU_TRY(sgpu_tensor_poll(ctx, true));
     }
-    const int err = static_cast<int>(ctx->h_scratch[2] & 0xFFFFFFFFu);
-    if (err == SGPU_E_CELL_RANGE) {
-        return sgpu_fail(ctx, err, "a group id is >= n_groups or maps to a cell >= num_cells (filter the pileup first)");
-    }
-    if (err != 0) {
-        if (poisoned) {
-            *poisoned = true; // some panels have been added: the planes hold a partial sum
+    return SGPU_OK;
+}
+
+// Jobs whose end event has been reached: kernel time into the context's statistics, events back to the pool, operand
+// panel back to the cache (whoever gets it next is ordered behind this call on ctx->stream, and the kernel is done).
+int sgpu_tensor_poll(sgpu_ctx *ctx, bool wait_all) {
+    while (!ctx->tensor_jobs.empty()) {
+        sgpu_ctx::TensorJob &j = ctx->tensor_jobs.front();
+        cudaError_t q = wait_all ? cudaEventSynchronize(j.t1) : cudaEventQuery(j.t1);
+        if (q == cudaErrorNotReady) {
+            break; // jobs finish in order
         }
-        return sgpu_fail(ctx, SGPU_E_COUNT_RANGE, "more than 127 reads of one cell at one locus: outside the int8 GEMM path, use the scatter "
-                         "path (the counts object holds a partial sum: sgpu_counts_zero before using it again)");
+        if (q != cudaSuccess) {
+            return sgpu_fail(ctx, SGPU_E_CUDA, "tensor kernel failed: %s", cudaGetErrorString(q));
+        }
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, j.t0, j.t1) == cudaSuccess) {
+            ctx->ms_syrk += ms;
+            ++ctx->n_syrk;
+        }
+        ctx->event_pool.push_back(j.t0);
+        ctx->event_pool.push_back(j.t1);
+        sgpu_dev_free(ctx, j.U);
+        sgpu_dev_free(ctx, j.err);
+        ctx->tensor_jobs.pop_front();
+    }
+    return SGPU_OK;
+}
+
+int sgpu_tensor_join(sgpu_ctx *ctx) {
+    if (!ctx->tensor_jobs.empty()) {
+        SGPU_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->tensor_jobs.back().t1, 0));
     }
     return SGPU_OK;
 }

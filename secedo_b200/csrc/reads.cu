@@ -1118,28 +1118,51 @@ int sgpu_link_reads(sgpu_ctx *ctx, const sgpu_pileup *p, uint32_t num_cells, uin
     // table geometry: slots >= 3 x the largest locus if shared memory allows, never below 1.25 x; the ring holds the
     // read ids of WIN_RING loci (each slot: the largest locus + up to 3 elements of alignment offset)
     const uint32_t id_cap = (max_n + 3 + 3) & ~3u;
-    uint32_t slots = 1024;
     unsigned long long slot_factor = 3;
     if (const char *env = getenv("SECEDO_B200_WIN_SLOT_FACTOR")) { // experiments (profiles/): table size / occupancy trade-off
         slot_factor = static_cast<unsigned long long>(std::max(1, atoi(env)));
     }
-    while (slots < slot_factor * max_n && slots < 65536) {
-        slots <<= 1;
-    }
-    uint32_t n_ring = WIN_RING;
+    // shared memory a CTA may take: everything, or what the tensor kernel of the previous batch leaves on its SM
+    // (sgpu_ctx::tensor_jobs; a CTA that does not fit beside it would wait for that kernel to end)
+    const size_t win_limit = ctx->win_smem_limit ? std::min<size_t>(ctx->win_smem_limit, WIN_SMEM_LIMIT) : WIN_SMEM_LIMIT;
+    auto pow2_slots = [&](unsigned long long want) {
+        uint32_t sl = 1024;
+        while (sl < want && sl < 65536) {
+            sl <<= 1;
+        }
+        return sl;
+    };
+    uint32_t n_ring = WIN_RING, slots = 1024;
     auto win_smem = [&](uint32_t s) {
         return static_cast<size_t>(n_ring) * id_cap * 4 + REC_BUF * sizeof(uint2) + static_cast<size_t>(s) * 2;
     };
-    // huge loci (cfg5: 20 000 reads): fewer resident loci before the table is allowed to shrink
-    while (n_ring > 1 && win_smem(slots) > WIN_SMEM_LIMIT) {
-        --n_ring;
-    }
-    while (slots > 1024 && win_smem(slots) > WIN_SMEM_LIMIT) {
-        slots >>= 1;
+    // preference: a ring of at least two loci (no exposed global latency per owner) before a sparse table (fewer second
+    // probes); huge loci (cfg5: 20 000 reads) end at one resident locus and the largest table that fits
+    auto choose_geometry = [&](size_t limit) {
+        const uint32_t s_full = pow2_slots(slot_factor * max_n), s_half = std::min(s_full, pow2_slots(2ull * max_n));
+        const uint32_t cand[4][2] = { { WIN_RING, s_full }, { 2, s_full }, { WIN_RING, s_half }, { 2, s_half } };
+        const char *env_ring = getenv("SECEDO_B200_WIN_RING"); // experiments (profiles/): 1 = one resident locus, full table
+        for (const auto &cd : cand) {
+            n_ring = cd[0];
+            slots = cd[1];
+            if (win_smem(slots) <= limit && !(env_ring && env_ring[0] == '1')) {
+                return true;
+            }
+        }
+        n_ring = 1;
+        slots = s_full;
+        while (slots > 1024 && win_smem(slots) > limit) {
+            slots >>= 1;
+        }
+        return win_smem(slots) <= limit && 4ull * slots >= 5ull * max_n;
+    };
+    bool window_fits = choose_geometry(win_limit);
+    if (!window_fits && win_limit < WIN_SMEM_LIMIT) { // rather wait for the whole SM than fall back to the global hash
+        window_fits = choose_geometry(WIN_SMEM_LIMIT);
     }
     // SECEDO_B200_FORCE_GLOBAL_HASH=1 forces the large-locus path (tests)
     const char *force_global = getenv("SECEDO_B200_FORCE_GLOBAL_HASH");
-    const bool use_window = max_n <= WIN_MAX_ENTRIES && win_smem(slots) <= WIN_SMEM_LIMIT && 4ull * slots >= 5ull * max_n
+    const bool use_window = max_n <= WIN_MAX_ENTRIES && window_fits && 4ull * slots >= 5ull * max_n
             && !(force_global && force_global[0] == '1');
     const unsigned locus_grid = static_cast<unsigned>(std::min<uint64_t>(P, static_cast<uint64_t>(ctx->sm_count) * 16));
 
