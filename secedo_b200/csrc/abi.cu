@@ -242,6 +242,15 @@ struct EventTimer {
         cudaEventElapsedTime(&ms, a, b);
         return ms;
     }
+    // the same without making the host wait at the end of every phase (each wait leaves the stream empty for a launch
+    // latency): mark() now, ms() once the stream has been synchronised anyway
+    void mark() { cudaEventRecord(b, st); }
+    float ms() {
+        float v = 0;
+        cudaEventSynchronize(b);
+        cudaEventElapsedTime(&v, a, b);
+        return v;
+    }
     ~EventTimer() {
         cudaEventDestroy(a);
         cudaEventDestroy(b);
@@ -312,17 +321,22 @@ int sgpu_init(int device, sgpu_ctx **out) {
         SGPU_CUDA(ctx, cudaStreamCreateWithPriority(&ctx->tensor_stream, cudaStreamNonBlocking, greatest));
         // kernels that are to run beside the tensor kernel must accept the shared-memory / L1 split its large operand
         // ring forces on the SM (profiles/coresidency_probe.cu)
-        const char *ps = getenv("SECEDO_B200_PREFER_SHARED");
-        if (ps && ps[0] == '1') {
-            SGPU_CUDA(ctx, cudaDeviceSetCacheConfig(cudaFuncCachePreferShared));
-        }
         const char *as = getenv("SECEDO_B200_ASYNC_GEMM");
         ctx->async_gemm = !(as && as[0] == '0');
+        const char *lg = getenv("SECEDO_B200_GEMM_LATE");
+        ctx->late_gemm = !(lg && lg[0] == '0');
+        const char *ps = getenv("SECEDO_B200_PREFER_SHARED");
+        ctx->prefer_shared = ps ? atoi(ps) : (ctx->async_gemm ? 2 : 0);
+        if (ctx->prefer_shared == 1) {
+            SGPU_TRY(sgpu_cache_preference(ctx, true));
+        }
         // operand ring of the CTA-pair kernel: 6 stages fill the SM; 5 leave 64 KB per SM to the kernels beside it
         const char *gs = getenv("SECEDO_B200_GEMM_STAGES");
         ctx->gemm_stages = gs ? static_cast<uint32_t>(std::min(6, std::max(4, atoi(gs)))) : (ctx->async_gemm ? 5u : 6u);
         const char *ws = getenv("SECEDO_B200_WIN_SMEM_KB");
-        ctx->win_smem_limit = ws ? static_cast<uint32_t>(std::max(16, atoi(ws))) * 1024u : (ctx->async_gemm ? 60u * 1024u : 0u);
+        // read linking: a geometry that fits beside the tensor kernel (60 KB: one CTA per SM, a denser table) was slower than
+        // letting link_window wait for the whole SM (profiles/r2_overlap_probes.txt), so no limit by default
+        ctx->win_smem_limit = ws ? static_cast<uint32_t>(std::max(16, atoi(ws))) * 1024u : 0u;
     }
     return SGPU_OK;
 }
@@ -335,8 +349,8 @@ void sgpu_shutdown(sgpu_ctx *ctx) {
         cudaSetDevice(ctx->device);
         cudaStreamSynchronize(ctx->stream);
         if (ctx->tensor_stream) {
+            sgpu_tensor_poll(ctx, true); // issues a launch that is still pending, waits for all of them
             cudaStreamSynchronize(ctx->tensor_stream);
-            sgpu_tensor_poll(ctx, true);
             for (auto &j : ctx->tensor_jobs) { // only after a failed kernel
                 cudaEventDestroy(j.t0);
                 cudaEventDestroy(j.t1);
@@ -405,6 +419,19 @@ int sgpu_synchronize(sgpu_ctx *ctx) {
     SGPU_TRY(sgpu_tensor_poll(ctx, true)); // tensor kernels still in flight (sgpu_ctx::tensor_jobs)
     return SGPU_OK;
 }
+
+} // extern "C"
+
+int sgpu_cache_preference(sgpu_ctx *ctx, bool shared) {
+    if (ctx->prefer_shared == 0 || (ctx->prefer_shared == 1 && !shared) || ctx->cache_pref_now == (shared ? 1 : 0)) {
+        return SGPU_OK;
+    }
+    SGPU_CUDA(ctx, cudaDeviceSetCacheConfig(shared ? cudaFuncCachePreferShared : cudaFuncCachePreferNone));
+    ctx->cache_pref_now = shared ? 1 : 0;
+    return SGPU_OK;
+}
+
+extern "C" {
 
 int sgpu_tensor_times(sgpu_ctx *ctx, float *ms, uint64_t *launches) {
     SGPU_CUDA(ctx, cudaSetDevice(ctx->device));
@@ -532,12 +559,65 @@ int sgpu_pileup_upload_lazy_async(sgpu_ctx *ctx, uint32_t n_chr, const uint64_t 
 
 } // extern "C"
 
-int sgpu_pileup_materialize(sgpu_ctx *ctx, const sgpu_pileup *cp) {
+namespace {
+// read ids of a view: one warp per locus copies the locus' run of the source into the pileup's own array
+__global__ void __launch_bounds__(256) gather_view_kernel(const uint64_t *__restrict__ row_ptr, const uint64_t *__restrict__ view_off,
+                                                          uint64_t n_loci, const uint32_t *__restrict__ src, uint32_t *__restrict__ dst) {
+    const int lane = threadIdx.x & 31;
+    const uint64_t warps_total = static_cast<uint64_t>(gridDim.x) * 8;
+    for (uint64_t l = static_cast<uint64_t>(blockIdx.x) * 8 + (threadIdx.x >> 5); l < n_loci; l += warps_total) {
+        const uint64_t e0 = row_ptr[l], n = row_ptr[l + 1] - e0, s0 = view_off[l];
+        for (uint64_t i = lane; i < n; i += 128) {
+            uint32_t v[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                v[u] = i + 32 * u < n ? src[s0 + i + 32 * u] : 0;
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                if (i + 32 * u < n) {
+                    dst[e0 + i + 32 * u] = v[u];
+                }
+            }
+        }
+    }
+}
+
+// the last view of a pileup its owner has already freed: free it now
+void release_view(sgpu_pileup *p) {
+    sgpu_pileup *src = p->view_src;
+    p->view_src = nullptr;
+    p->view_read_id = nullptr;
+    if (src && src->view_refs.fetch_sub(1) == 1 && src->zombie) {
+        sgpu_pileup_free(src->zombie_ctx, src);
+    }
+}
+} // namespace
+
+int sgpu_pileup_materialize(sgpu_ctx *ctx, const sgpu_pileup *cp, bool keep_view) {
     sgpu_pileup *p = const_cast<sgpu_pileup *>(cp);
-    if (!p || p->d_read_id || !p->zc_read_id) {
+    if (!p || p->d_read_id) {
         return SGPU_OK;
     }
     const uint64_t E = p->n_entries;
+    if (p->view_read_id) {
+        if (keep_view) {
+            return SGPU_OK;
+        }
+        SGPU_CUDA(ctx, sgpu_dev_alloc(ctx, reinterpret_cast<void **>(&p->d_read_id), (E ? E : 1) * sizeof(uint32_t)));
+        if (p->n_loci) {
+            const unsigned grid = static_cast<unsigned>(std::min<uint64_t>(ceil_div_u64(p->n_loci, 8), static_cast<uint64_t>(ctx->sm_count) * 16));
+            SGPU_LAUNCH(ctx, (gather_view_kernel<<<grid, 256, 0, ctx->stream>>>(p->d_row_ptr, p->view_off, p->n_loci, p->view_read_id, p->d_read_id)));
+            SGPU_CUDA(ctx, cudaGetLastError());
+        }
+        sgpu_dev_free(ctx, p->view_off); // stream ordered behind the gather
+        p->view_off = nullptr;
+        release_view(p);
+        return SGPU_OK;
+    }
+    if (!p->zc_read_id) {
+        return SGPU_OK;
+    }
     SGPU_CUDA(ctx, sgpu_dev_alloc(ctx, reinterpret_cast<void **>(&p->d_read_id), (E ? E : 1) * sizeof(uint32_t)));
     SGPU_CUDA(ctx, cudaMemcpyAsync(p->d_read_id, p->zc_read_id, E * sizeof(uint32_t), cudaMemcpyDefault, ctx->stream));
     return SGPU_OK;
@@ -643,8 +723,20 @@ void sgpu_pileup_free(sgpu_ctx *ctx, sgpu_pileup *p) {
     if (!p) {
         return;
     }
+    if (p->view_refs.load() > 0) { // filtered pileups still read this one's ids (sgpu_pileup::view_read_id): the last of them frees it
+        p->zombie = true;
+        p->zombie_ctx = ctx;
+        return;
+    }
     if (ctx) {
         cudaSetDevice(ctx->device);
+    }
+    if (p->view_off) {
+        sgpu_dev_free(ctx, p->view_off);
+        p->view_off = nullptr;
+    }
+    if (p->view_src) {
+        release_view(p);
     }
     if (p->ready) {
         if (ctx) { // the blocks go back to the cache of the compute stream: order it behind the copies
@@ -748,7 +840,7 @@ static int accumulate_impl(sgpu_ctx *ctx, sgpu_counts *c, const sgpu_pileup *fil
                            sgpu_stats *stats, const RangeSpec *range) {
     SGPU_CUDA(ctx, cudaSetDevice(ctx->device));
     SGPU_WAIT_PILEUP(ctx, filtered);
-    SGPU_TRY(sgpu_pileup_materialize(ctx, filtered));
+    SGPU_TRY(sgpu_pileup_materialize(ctx, filtered, true)); // a view of the unfiltered pileup's read ids stays one
     if (path < SGPU_PATH_AUTO || path > SGPU_PATH_GEMM) {
         return sgpu_fail(ctx, SGPU_E_ARG, "unknown path %d", path);
     }
@@ -777,48 +869,45 @@ static int accumulate_impl(sgpu_ctx *ctx, sgpu_counts *c, const sgpu_pileup *fil
     // tensor kernels of earlier batches that have finished meanwhile: their time goes into this call's statistics
     SGPU_TRY(sgpu_tensor_poll(ctx, false));
     LinkResult lr;
-    {
-        EventTimer t(ctx->stream);
-        SGPU_TRY(sgpu_link_reads(ctx, filtered, c->n, max_fragment_length, group_id_to_pos, n_groups, num_threads, &lr, range));
-        s.ms_link = t.stop();
-    }
+    EventTimer t_link(ctx->stream);
+    SGPU_TRY(sgpu_link_reads(ctx, filtered, c->n, max_fragment_length, group_id_to_pos, n_groups, num_threads, &lr, range));
+    t_link.mark();
     s.n_reads = lr.n_reads;
     s.n_dropped_entries = lr.n_dropped;
     s.n_multi_reads = lr.n_multi;
     s.n_tail_reads = lr.n_tail;
     s.n_span_splits = static_cast<int32_t>(std::min<uint64_t>(lr.n_span_splits, 0x7FFFFFFF));
     ctx->ms_stage = 0.f;
-    {
-        EventTimer t(ctx->stream);
-        if (path == SGPU_PATH_SCATTER) {
+    EventTimer t_first(ctx->stream);
+    if (path == SGPU_PATH_SCATTER) {
+        SGPU_TRY(sgpu_link_dense_codes(ctx, filtered, &lr));
+        SGPU_TRY(sgpu_tensor_join(ctx)); // the atomics go to the planes a tensor kernel in flight adds to
+        SGPU_TRY(sgpu_scatter_pairs(ctx, filtered, lr, c, +1, false, &s.n_pairs_first));
+        c->fresh = false;
+    } else {
+        // incl. the tail x tail correction. More than 127 reads of one cell at one locus do not fit int8: the first
+        // panel is checked before the count planes are touched and, with SGPU_PATH_AUTO, the call takes the scatter
+        // path instead
+        int rc = sgpu_gemm_counts(ctx, filtered, lr, c, &s.n_pairs_first);
+        if (rc == SGPU_E_COUNT_RANGE && auto_path && !c->poisoned) {
+            s.path_used = SGPU_PATH_SCATTER;
             SGPU_TRY(sgpu_link_dense_codes(ctx, filtered, &lr));
-            SGPU_TRY(sgpu_tensor_join(ctx)); // the atomics go to the planes a tensor kernel in flight adds to
-            SGPU_TRY(sgpu_scatter_pairs(ctx, filtered, lr, c, +1, false, &s.n_pairs_first));
+            SGPU_TRY(sgpu_tensor_join(ctx));
+            rc = sgpu_scatter_pairs(ctx, filtered, lr, c, +1, false, &s.n_pairs_first);
             c->fresh = false;
-        } else {
-            // incl. the tail x tail correction. More than 127 reads of one cell at one locus do not fit int8: the first
-            // panel is checked before the count planes are touched and, with SGPU_PATH_AUTO, the call takes the scatter
-            // path instead
-            int rc = sgpu_gemm_counts(ctx, filtered, lr, c, &s.n_pairs_first);
-            if (rc == SGPU_E_COUNT_RANGE && auto_path && !c->poisoned) {
-                s.path_used = SGPU_PATH_SCATTER;
-                SGPU_TRY(sgpu_link_dense_codes(ctx, filtered, &lr));
-                SGPU_TRY(sgpu_tensor_join(ctx));
-                rc = sgpu_scatter_pairs(ctx, filtered, lr, c, +1, false, &s.n_pairs_first);
-                c->fresh = false;
-            }
-            SGPU_TRY(rc);
         }
-        s.ms_first_order = t.stop();
-        s.ms_stage = ctx->ms_stage;
+        SGPU_TRY(rc);
     }
-    {
-        // second / third order planes, spill plane, histogram: none of them is touched by the first-order tensor kernel
-        // that may still be running
-        EventTimer t(ctx->stream);
-        SGPU_TRY(sgpu_multilocus(ctx, filtered, lr, c, max_fragment_length, &s.n_pairs_multi));
-        s.ms_multi = t.stop();
-    }
+    t_first.mark();
+    s.ms_stage = ctx->ms_stage;
+    // second / third order planes, spill plane, histogram: none of them is touched by the first-order tensor kernel
+    // that may still be running
+    EventTimer t_multi(ctx->stream);
+    SGPU_TRY(sgpu_multilocus(ctx, filtered, lr, c, max_fragment_length, &s.n_pairs_multi));
+    t_multi.mark();
+    s.ms_multi = t_multi.ms(); // the one host wait for the three phases
+    s.ms_link = t_link.ms();
+    s.ms_first_order = t_first.ms();
     // Tensor kernels retired during this call (with SECEDO_B200_ASYNC_GEMM=0: this call's own; otherwise mostly the one of
     // the batch before; sgpu_tensor_times returns what is left)
     SGPU_TRY(sgpu_tensor_poll(ctx, false));
@@ -869,7 +958,7 @@ int sgpu_chromosome_cutoff(sgpu_ctx *ctx, const sgpu_pileup *ends, uint32_t max_
         return sgpu_fail(ctx, SGPU_E_ARG, "num_threads must be >= 1");
     }
     SGPU_WAIT_PILEUP(ctx, ends);
-    SGPU_TRY(sgpu_pileup_materialize(ctx, ends));
+    SGPU_TRY(sgpu_pileup_materialize(ctx, ends, true));
     return sgpu_cutoff_from_suffix(ctx, ends, max_fragment_length, num_threads, whole, tail_position, resolved);
 }
 

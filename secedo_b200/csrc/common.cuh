@@ -3,6 +3,7 @@
 
 #include <cuda_runtime.h>
 
+#include <atomic>
 #include <cstdarg>
 #include <cstdint>
 #include <cstdio>
@@ -50,7 +51,17 @@ struct sgpu_ctx {
         cudaEvent_t t0 = nullptr, t1 = nullptr; // around the kernel, on the stream it was launched on
     };
     std::deque<TensorJob> tensor_jobs;
+    void *pending_gemm = nullptr;        // gemm.cu: prepared launch of the last deferred tensor kernel, not issued yet
+    bool late_gemm = true;               // issue it behind the next batch's link_window kernel (SECEDO_B200_GEMM_LATE=0: at once)
     std::vector<cudaEvent_t> event_pool; // recycled timing events
+    // Kernels only share an SM with the tensor kernel while the DEVICE-WIDE cache preference is cudaFuncCachePreferShared: a
+    // kernel with 16 KB of static shared memory otherwise waited for the whole tensor kernel, and neither the carve-out
+    // attribute nor cudaFuncSetCacheConfig of that kernel changed it (profiles/coresidency_probe.cu, r2_coresidency.txt,
+    // r2_overlap_probes.txt). The preference costs the kernels that run alone ~4 % (less L1), so by default (2) it is only
+    // in force from the launch of a deferred tensor kernel to the launch of the next batch's link_window kernel (which
+    // never fits beside it). 0: never, 1: always, 2: toggled.
+    int prefer_shared = 0;
+    int cache_pref_now = -1;             // what this context last set (-1: nothing yet)
     uint32_t gemm_stages = 6;            // operand ring of syrk2_kernel (SECEDO_B200_GEMM_STAGES = 4, 5, 6)
     uint32_t win_smem_limit = 0;         // reads.cu: shared memory a link_window CTA may use (0 = default)
     // gemm.cu: rasterised list of upper-triangle output tiles for tile_cache_cells cells (device memory)
@@ -90,9 +101,12 @@ void sgpu_trace_point(sgpu_ctx *ctx, const char *what);
     } while (0)
 
 int sgpu_fail(sgpu_ctx *ctx, int code, const char *fmt, ...);
+// device-wide shared-memory / L1 preference, switched only when it changes (see sgpu_ctx::prefer_shared)
+int sgpu_cache_preference(sgpu_ctx *ctx, bool shared);
 // gemm.cu — tensor kernels in flight on ctx->tensor_stream (see sgpu_ctx::tensor_jobs)
 int sgpu_tensor_poll(sgpu_ctx *ctx, bool wait_all); // retire finished jobs (timing, operand panel back to the cache)
 int sgpu_tensor_join(sgpu_ctx *ctx);                // ctx->stream waits (on the device) for the last job
+int sgpu_tensor_flush(sgpu_ctx *ctx, bool after_main); // issue the prepared launch, if any (after_main: behind everything queued on ctx->stream)
 // make the context's stream wait for an asynchronously uploaded pileup
 #define SGPU_WAIT_PILEUP(ctx, p)                                                                   \
     do {                                                                                           \
@@ -134,8 +148,10 @@ int sgpu_tensor_join(sgpu_ctx *ctx);                // ctx->stream waits (on the
     } while (0)
 
 struct sgpu_pileup;
-// copy lazily uploaded read ids to the device (no-op otherwise); stream ordered on ctx->stream
-int sgpu_pileup_materialize(sgpu_ctx *ctx, const sgpu_pileup *p);
+// copy lazily uploaded read ids to the device and gather viewed ones (see sgpu_pileup::view_read_id) into an array of the
+// pileup's own (no-op otherwise); stream ordered on ctx->stream. keep_view: leave a view as it is (the read linking reads
+// through it)
+int sgpu_pileup_materialize(sgpu_ctx *ctx, const sgpu_pileup *p, bool keep_view = false);
 
 // device memory from the context's cache (see sgpu_ctx::free_blocks)
 cudaError_t sgpu_dev_alloc(sgpu_ctx *ctx, void **p, size_t bytes);
@@ -194,6 +210,17 @@ struct sgpu_pileup {
     // sgpu_pileup_upload_lazy_async: the read ids stay in the caller's pinned host memory (zc_read_id is its device
     // alias) and d_read_id is null until somebody other than the filter needs them (sgpu_pileup_materialize)
     const uint32_t *zc_read_id = nullptr;
+    // Filtered pileup whose read ids are a VIEW of the pileup the filter read (filter.cu; only when every group belongs to
+    // the sub-cluster, so that the entries of a kept locus are one contiguous run of the source): view_read_id is the
+    // source's array and view_off[l] the first source entry of locus l. The read linking - the only dense reader of the
+    // ids - reads through the view; d_read_id stays null until somebody else asks (sgpu_pileup_materialize gathers). The
+    // source outlives its views: sgpu_pileup_free of a pileup with live views is deferred until the last one is gone.
+    const uint32_t *view_read_id = nullptr;
+    uint64_t *view_off = nullptr;     // context cache, n_loci values
+    sgpu_pileup *view_src = nullptr;
+    std::atomic<int> view_refs{ 0 };  // views that read THIS pileup's ids
+    bool zombie = false;              // freed by the caller while views were alive
+    sgpu_ctx *zombie_ctx = nullptr;   // the context that free was asked of
     cudaEvent_t ready = nullptr;   // set by sgpu_pileup_upload_async: the copies are done
     mutable uint32_t max_row = 0;  // entries of the largest locus (0 = not known yet; cached by reads.cu)
 };
@@ -300,6 +327,7 @@ struct LinkResult {
     uint64_t n_tail_loci = 0;
     DevBuf<uint32_t> gmap;       // group_id_to_pos on the device
     uint32_t n_groups = 0, num_cells = 0;
+    bool gmap_identity = false;  // group g is cell g (the root of the recursion): the partition kernel needs no table
     // Ranged accumulation (sgpu_counts_accumulate_range): the pileup is a piece of its chromosomes plus halos; only the
     // OWNED loci contribute first-order counts, and a multi-locus pair is accounted by the piece that owns its first
     // common locus. Not ranged: everything is owned (owned.p == nullptr, own_loci.p == nullptr).
@@ -399,6 +427,7 @@ struct GemmInput {
     uint64_t n_entries;
     const uint32_t *sp_bits;   // entries to leave out (staged from the special list instead)
     const uint32_t *gmap;      // group -> cell
+    bool gmap_identity = false; // gmap[g] == g for every group
     uint32_t n_groups;
     const uint32_t *sp_code, *sp_locus, *sp_start; // special entries (may be empty: n_special = 0, sp_start all zero)
     uint64_t n_special;

@@ -292,7 +292,10 @@ __global__ void __launch_bounds__(FILTER_THREADS) pull_read_ids_kernel(const uin
     }
 }
 
-template <typename GB>
+// WITH_IDS = false: every group belongs to the sub-cluster, so a kept locus keeps all its entries in place: the read ids are
+// not copied (4 of the 6 bytes per entry), the filtered pileup reads them through a view of the source (view_off[locus] = the
+// locus' first source entry, sgpu_pileup::view_read_id)
+template <typename GB, bool WITH_IDS>
 __global__ void __launch_bounds__(FILTER_THREADS) filter_compact_kernel(
         const uint64_t *__restrict__ row_ptr, const uint32_t *__restrict__ position,
         const uint32_t *__restrict__ read_id, const GB *__restrict__ gid_base, uint64_t n_loci,
@@ -300,7 +303,7 @@ __global__ void __launch_bounds__(FILTER_THREADS) filter_compact_kernel(
         const uint64_t *__restrict__ new_locus /* exclusive scan of keep */,
         const uint64_t *__restrict__ new_row /* exclusive scan of kept_cnt, n_loci + 1 */,
         uint64_t *__restrict__ out_row_ptr, uint32_t *__restrict__ out_position,
-        uint32_t *__restrict__ out_read_id, GB *__restrict__ out_gid_base) {
+        uint32_t *__restrict__ out_read_id, GB *__restrict__ out_gid_base, uint64_t *__restrict__ view_off) {
     extern __shared__ uint32_t s_mask[];
     const uint32_t mask_words = (n_groups + 31) / 32;
     for (uint32_t i = threadIdx.x; i < mask_words; i += blockDim.x) {
@@ -316,11 +319,30 @@ __global__ void __launch_bounds__(FILTER_THREADS) filter_compact_kernel(
         }
         const uint64_t nl = new_locus[l];
         uint64_t w = new_row[l];
+        const uint64_t e0 = row_ptr[l], e1 = row_ptr[l + 1];
         if (lane == 0) {
             out_row_ptr[nl] = w;
             out_position[nl] = position[l];
+            if (!WITH_IDS) {
+                view_off[nl] = e0;
+            }
         }
-        const uint64_t e0 = row_ptr[l], e1 = row_ptr[l + 1];
+        if (!WITH_IDS) { // a plain copy of the locus' (group, base) entries
+            for (uint64_t i = lane; i < e1 - e0; i += 256) {
+                GB v[8];
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {
+                    v[u] = i + 32 * u < e1 - e0 ? gid_base[e0 + i + 32 * u] : GB(0);
+                }
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {
+                    if (i + 32 * u < e1 - e0) {
+                        out_gid_base[w + i + 32 * u] = v[u];
+                    }
+                }
+            }
+            continue;
+        }
         for (uint64_t base = e0; base < e1; base += 128) { // four independent 32-entry groups in flight
             uint32_t gb[4], rid[4];
             bool in[4];
@@ -409,6 +431,9 @@ int sgpu_filter_impl(sgpu_ctx *ctx, const sgpu_pileup *in, const uint32_t *h_id_
     }
     cudaStream_t st = ctx->stream;
     const uint64_t P = in->n_loci;
+    if (in->view_read_id) { // the input is itself a filtered pileup that reads its ids through a view: give it its own first
+        SGPU_TRY(sgpu_pileup_materialize(ctx, in));
+    }
     // sub-cluster membership as a bit mask (id_to_pos[gid] != NO_POS, util/is_significant.cpp:169)
     const uint32_t mask_words = (n_groups + 31) / 32;
     std::vector<uint32_t> h_mask(mask_words ? mask_words : 1, 0);
@@ -416,9 +441,12 @@ int sgpu_filter_impl(sgpu_ctx *ctx, const sgpu_pileup *in, const uint32_t *h_id_
     if (!in->wide && n_groups > 16384) {
         return sgpu_fail(ctx, SGPU_E_ARG, "more than 16 384 groups need a wide pileup (sgpu_pileup_upload_wide)");
     }
+    bool all_in = true; // every group belongs to the sub-cluster (the root of the recursion): kept loci keep all their entries
     for (uint32_t g = 0; g < n_groups; ++g) {
         if (h_id_to_pos[g] != no_pos) {
             h_mask[g >> 5] |= 1u << (g & 31);
+        } else {
+            all_in = false;
         }
     }
     const size_t smem = std::max<size_t>(512, h_mask.size()) * sizeof(uint32_t);
@@ -446,7 +474,8 @@ int sgpu_filter_impl(sgpu_ctx *ctx, const sgpu_pileup *in, const uint32_t *h_id_
                                                                   static_cast<uint64_t>(ctx->sm_count) * 32));
     if (smem > 48 * 1024) {
         SGPU_GB(in, (void)gid_base_; SGPU_CUDA(ctx, cudaFuncSetAttribute(filter_count_kernel<GB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-                SGPU_CUDA(ctx, cudaFuncSetAttribute(filter_compact_kernel<GB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)));
+                SGPU_CUDA(ctx, cudaFuncSetAttribute(filter_compact_kernel<GB, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                SGPU_CUDA(ctx, cudaFuncSetAttribute(filter_compact_kernel<GB, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)));
     }
     if (P) {
         const unsigned cgrid = static_cast<unsigned>(std::min<uint64_t>(ceil_div_u64(P, FILTER_THREADS / 32), static_cast<uint64_t>(ctx->sm_count) * 8));
@@ -483,7 +512,15 @@ int sgpu_filter_impl(sgpu_ctx *ctx, const sgpu_pileup *in, const uint32_t *h_id_
     SGPU_CUDA(ctx, sgpu_dev_alloc(ctx, reinterpret_cast<void **>(&out->d_chr_ptr), (in->n_chr + 1) * sizeof(uint64_t)));
     SGPU_CUDA(ctx, sgpu_dev_alloc(ctx, reinterpret_cast<void **>(&out->d_row_ptr), (Lk + 1) * sizeof(uint64_t)));
     SGPU_CUDA(ctx, sgpu_dev_alloc(ctx, reinterpret_cast<void **>(&out->d_position), (Lk ? Lk : 1) * sizeof(uint32_t)));
-    SGPU_CUDA(ctx, sgpu_dev_alloc(ctx, reinterpret_cast<void **>(&out->d_read_id), (Ek ? Ek : 1) * sizeof(uint32_t)));
+    // Read ids: copied, or - when nothing inside a kept locus is dropped and the source holds them on the device - left where
+    // they are (sgpu_pileup::view_read_id; SECEDO_B200_FILTER_VIEW=0 always copies)
+    const char *env_view = getenv("SECEDO_B200_FILTER_VIEW");
+    const bool as_view = all_in && P && in->d_read_id != nullptr && !(env_view && env_view[0] == '0');
+    if (as_view) {
+        SGPU_CUDA(ctx, sgpu_dev_alloc(ctx, reinterpret_cast<void **>(&out->view_off), (Lk ? Lk : 1) * sizeof(uint64_t)));
+    } else {
+        SGPU_CUDA(ctx, sgpu_dev_alloc(ctx, reinterpret_cast<void **>(&out->d_read_id), (Ek ? Ek : 1) * sizeof(uint32_t)));
+    }
     if (in->wide) {
         SGPU_CUDA(ctx, sgpu_dev_alloc(ctx, reinterpret_cast<void **>(&out->d_gid_base32), (Ek ? Ek : 1) * sizeof(uint32_t)));
     } else {
@@ -499,11 +536,25 @@ int sgpu_filter_impl(sgpu_ctx *ctx, const sgpu_pileup *in, const uint32_t *h_id_
             SGPU_LAUNCH(ctx, (pull_read_ids_kernel<<<grid, FILTER_THREADS, 0, st>>>(in->d_row_ptr, P, d_keep.p, in->zc_read_id, pulled.p)));
             rid_src = pulled.p;
         }
-        SGPU_GB(in, SGPU_LAUNCH(ctx, (filter_compact_kernel<GB><<<grid, FILTER_THREADS, mask_words * sizeof(uint32_t), st>>>(
-                                in->d_row_ptr, in->d_position, rid_src, gid_base_, P, d_mask.p, n_groups, d_keep.p, d_new_locus.p,
-                                d_new_row.p, out->d_row_ptr, out->d_position, out->d_read_id,
-                                const_cast<GB *>(in->wide ? reinterpret_cast<const GB *>(out->d_gid_base32)
-                                                          : reinterpret_cast<const GB *>(out->d_gid_base))))));
+        if (as_view) {
+            SGPU_GB(in, SGPU_LAUNCH(ctx, (filter_compact_kernel<GB, false><<<grid, FILTER_THREADS, mask_words * sizeof(uint32_t), st>>>(
+                                    in->d_row_ptr, in->d_position, rid_src, gid_base_, P, d_mask.p, n_groups, d_keep.p, d_new_locus.p,
+                                    d_new_row.p, out->d_row_ptr, out->d_position, nullptr,
+                                    const_cast<GB *>(in->wide ? reinterpret_cast<const GB *>(out->d_gid_base32)
+                                                              : reinterpret_cast<const GB *>(out->d_gid_base)),
+                                    out->view_off))));
+            sgpu_pileup *src = const_cast<sgpu_pileup *>(in);
+            src->view_refs.fetch_add(1);
+            out->view_src = src;
+            out->view_read_id = in->d_read_id;
+        } else {
+            SGPU_GB(in, SGPU_LAUNCH(ctx, (filter_compact_kernel<GB, true><<<grid, FILTER_THREADS, mask_words * sizeof(uint32_t), st>>>(
+                                    in->d_row_ptr, in->d_position, rid_src, gid_base_, P, d_mask.p, n_groups, d_keep.p, d_new_locus.p,
+                                    d_new_row.p, out->d_row_ptr, out->d_position, out->d_read_id,
+                                    const_cast<GB *>(in->wide ? reinterpret_cast<const GB *>(out->d_gid_base32)
+                                                              : reinterpret_cast<const GB *>(out->d_gid_base)),
+                                    nullptr))));
+        }
     }
     SGPU_LAUNCH(ctx, (remap_chr_ptr_kernel<<<(in->n_chr + 256) / 256, 256, 0, st>>>(in->d_chr_ptr, in->n_chr, d_new_locus.p, out->d_chr_ptr,
                                                                  out->d_row_ptr, d_new_row.p, P)));

@@ -98,6 +98,8 @@ struct PartitionArgs {
     const uint32_t *sp_bits;
     const uint32_t *gmap;
     uint32_t n_groups, n_cells;
+    uint32_t identity;     // group g is cell g: no table in shared memory (16 KB less per CTA at 8 000 cells: more CTAs per SM,
+                           // above all beside the tensor kernel of the previous batch)
     uint64_t n_loci;
     uint32_t n_stripes;
     uint32_t stripe_magic; // cell / cells_per_cta = (cell * magic) >> 32, exact for cells < 65 536
@@ -122,11 +124,14 @@ __global__ void __launch_bounds__(256) partition_kernel(const PartitionArgs<GB> 
     uint16_t *s_out = s_dyn;                       // [PART_OUT] the partitioned locus
     uint16_t *s_map = s_dyn + PART_OUT;            // [n_groups] cell of the group, 0xFFFF = outside the matrix
     const uint32_t ns = a.n_stripes;
-    for (uint32_t g = threadIdx.x; g < a.n_groups; g += 256) {
-        const uint32_t c = a.gmap[g];
-        s_map[g] = static_cast<uint16_t>(c < a.n_cells ? c : 0xFFFFu);
+    if (!a.identity) {
+        for (uint32_t g = threadIdx.x; g < a.n_groups; g += 256) {
+            const uint32_t c = a.gmap[g];
+            s_map[g] = static_cast<uint16_t>(c < a.n_cells ? c : 0xFFFFu);
+        }
     }
     __syncthreads();
+    auto cell_of = [&](uint32_t gid) -> uint32_t { return a.identity ? gid : s_map[gid]; }; // gid < n_groups (<= n_cells if identity)
     // stripe << 16 | value of entry e (value = cell inside its stripe << 2 | base); 0xFFFFFFFF = left out
     auto classify = [&](uint64_t e) -> uint32_t {
         uint32_t v = 0xFFFFFFFFu;
@@ -134,7 +139,7 @@ __global__ void __launch_bounds__(256) partition_kernel(const PartitionArgs<GB> 
         if (!((a.sp_bits[e >> 5] >> (e & 31)) & 1u)) {
             const uint32_t gid = gb >> 2;
             uint32_t cell;
-            if (gid >= a.n_groups || (cell = s_map[gid]) == 0xFFFFu) {
+            if (gid >= a.n_groups || (cell = cell_of(gid)) == 0xFFFFu) {
                 atomicExch(a.err, SGPU_E_CELL_RANGE);
             } else {
                 const uint32_t stripe = __umulhi(cell, a.stripe_magic);
@@ -189,7 +194,7 @@ __global__ void __launch_bounds__(256) partition_kernel(const PartitionArgs<GB> 
                         }
                         const uint32_t gid = gb[k] >> 2;
                         uint32_t cell;
-                        if (gid >= a.n_groups || (cell = s_map[gid]) == 0xFFFFu) {
+                        if (gid >= a.n_groups || (cell = cell_of(gid)) == 0xFFFFu) {
                             atomicExch(a.err, SGPU_E_CELL_RANGE);
                         } else {
                             const uint32_t stripe = __umulhi(cell, a.stripe_magic);
@@ -1060,6 +1065,83 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 1)
 
 } // namespace
 
+// One launch of the tensor kernel, with everything it needs held by value: the launch may be issued later than the call that
+// prepared it (sgpu_ctx::tensor_jobs, late launch).
+namespace {
+struct TensorLaunch {
+    CUtensorMap map;
+    WorkList wl;
+    int32_t *S = nullptr, *D = nullptr;
+    uint32_t N = 0;
+    int epi = EPI_RMW;
+    unsigned grid = 0;
+    int stages2 = 6;
+    bool pairs = true;
+    int *err = nullptr;                    // [1]: wave counter (null: no wave sync)
+    sgpu_ctx::TensorJob job;               // events + what the job will own
+    cudaEvent_t staged = nullptr;          // on ctx->stream, behind the staging kernel (late launches only)
+};
+
+// t0, memset of the wave counter, kernel, t1 on stream gs; the job joins the context's list
+int issue_tensor_launch(sgpu_ctx *ctx, cudaStream_t gs, TensorLaunch &tl) {
+    ctx->tensor_jobs.push_back(tl.job); // the list owns the events and the panel from here on, whatever happens below
+    if (tl.err && tl.wl.wave_ctr) {
+        SGPU_CUDA(ctx, cudaMemsetAsync(tl.err + 1, 0, sizeof(int), gs));
+    }
+    SGPU_CUDA(ctx, cudaEventRecord(tl.job.t0, gs));
+    if (tl.pairs) {
+        if (tl.stages2 == 4) {
+            SGPU_LAUNCH(ctx, (syrk2_kernel<4><<<2 * tl.grid, GEMM_THREADS, smem2_bytes(4), gs>>>(tl.map, tl.wl, tl.S, tl.D, tl.N, tl.epi)));
+        } else if (tl.stages2 == 5) {
+            SGPU_LAUNCH(ctx, (syrk2_kernel<5><<<2 * tl.grid, GEMM_THREADS, smem2_bytes(5), gs>>>(tl.map, tl.wl, tl.S, tl.D, tl.N, tl.epi)));
+        } else {
+            SGPU_LAUNCH(ctx, (syrk2_kernel<6><<<2 * tl.grid, GEMM_THREADS, smem2_bytes(6), gs>>>(tl.map, tl.wl, tl.S, tl.D, tl.N, tl.epi)));
+        }
+    } else {
+        SGPU_LAUNCH(ctx, (syrk_kernel<<<tl.grid, GEMM_THREADS, SMEM_BYTES, gs>>>(tl.map, tl.wl, tl.S, tl.D, tl.N, 1, tl.epi)));
+    }
+    const cudaError_t le = cudaGetLastError();
+    SGPU_CUDA(ctx, cudaEventRecord(tl.job.t1, gs));
+    SGPU_CUDA(ctx, le);
+    return SGPU_OK;
+}
+} // namespace
+
+// The prepared launch of the last deferred tensor kernel, if it has not been issued yet. It is issued behind the NEXT batch's
+// link_window kernel (after_main = true: that kernel needs whole SMs and would otherwise wait for the tensor kernel to end,
+// with the stream's other kernels queued behind it; issued in this order the tensor kernel runs beside the special-entry
+// chain, the partition and the staging of the next batch instead), or by whoever needs the result or the stream first.
+int sgpu_tensor_flush(sgpu_ctx *ctx, bool after_main) {
+    TensorLaunch *tl = static_cast<TensorLaunch *>(ctx->pending_gemm);
+    if (!tl) {
+        return SGPU_OK;
+    }
+    ctx->pending_gemm = nullptr;
+    struct Cleanup {
+        sgpu_ctx *ctx;
+        TensorLaunch *tl;
+        bool issued = false;
+        ~Cleanup() {
+            ctx->event_pool.push_back(tl->staged);
+            if (!issued) { // an error before the launch: the job never reached the list
+                ctx->event_pool.push_back(tl->job.t0);
+                ctx->event_pool.push_back(tl->job.t1);
+                sgpu_dev_free(ctx, tl->job.U);
+                sgpu_dev_free(ctx, tl->job.err);
+            }
+            delete tl;
+        }
+    } cleanup{ ctx, tl };
+    cudaStream_t gs = ctx->tensor_stream;
+    if (after_main) {
+        SGPU_CUDA(ctx, cudaEventRecord(tl->staged, ctx->stream)); // re-recorded: behind everything queued so far (incl. the staging)
+    }
+    SGPU_CUDA(ctx, cudaStreamWaitEvent(gs, tl->staged, 0));
+    SGPU_TRY(sgpu_cache_preference(ctx, true)); // what is launched from now on may run beside this kernel
+    cleanup.issued = true; // from here on the job is in the list (issue_tensor_launch appends it before it reports a launch error)
+    return issue_tensor_launch(ctx, gs, *tl);
+}
+
 // Upper-triangle output tiles in an order that keeps the tiles in flight (one per SM) inside a block
 // of ~18 row blocks x 8 column blocks, so that a wave touches ~4 400 distinct operand rows instead of
 // ~20 000: bands of 8 column blocks, row-block-major inside a band.
@@ -1116,6 +1198,7 @@ int sgpu_gemm_counts(sgpu_ctx *ctx, const sgpu_pileup *p, const LinkResult &lr, 
     in.n_entries = p->n_entries;
     in.sp_bits = lr.sp_bits.p;
     in.gmap = lr.gmap.p;
+    in.gmap_identity = lr.gmap_identity;
     in.n_groups = lr.n_groups;
     in.sp_code = lr.sp_code.p;
     in.sp_locus = lr.sp_locus.p;
@@ -1162,7 +1245,9 @@ int sgpu_gemm_run(sgpu_ctx *ctx, const GemmInput &in, uint32_t N, int32_t *S_pla
     const uint64_t n_chunks_max = (kbs_max + ck - 1) / ck;
     SGPU_TRACE(ctx, "gemm: enter");
 
-    // tensor kernels of earlier batches: retire the finished ones; never more than two operand panels in flight
+    // tensor kernels of earlier batches: issue the one still pending, retire the finished ones; never more than two operand
+    // panels in flight
+    SGPU_TRY(sgpu_tensor_flush(ctx, false));
     SGPU_TRY(sgpu_tensor_poll(ctx, false));
     while (ctx->tensor_jobs.size() >= 2) {
         SGPU_CUDA(ctx, cudaEventSynchronize(ctx->tensor_jobs.front().t1));
@@ -1267,7 +1352,11 @@ int sgpu_gemm_run(sgpu_ctx *ctx, const GemmInput &in, uint32_t N, int32_t *S_pla
     } event_return{ ctx, &ev_s0, &ev_s1 };
     const uint32_t sms = static_cast<uint32_t>(ctx->sm_count);
     // stripes of cells per staging CTA: as few as a 104 KB tile allows
-    const uint32_t n_stripes = (n_pad + ST_MAX_CELLS - 1) / ST_MAX_CELLS;
+    uint32_t st_cells = ST_MAX_CELLS;
+    if (const char *env = getenv("SECEDO_B200_STAGE_CELLS")) { // experiments (profiles/): smaller tiles, more staging CTAs per SM
+        st_cells = static_cast<uint32_t>(std::min<int>(ST_MAX_CELLS, std::max(64, atoi(env))));
+    }
+    const uint32_t n_stripes = std::min<uint32_t>(ST_MAX_STRIPES, (n_pad + st_cells - 1) / st_cells);
     const uint32_t cells_per_cta = ((n_pad + n_stripes - 1) / n_stripes + 3) / 4 * 4;
     const size_t st_smem = static_cast<size_t>(cells_per_cta) * 128;
     SGPU_CUDA(ctx, cudaFuncSetAttribute(stage_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(st_smem)));
@@ -1282,7 +1371,7 @@ int sgpu_gemm_run(sgpu_ctx *ctx, const GemmInput &in, uint32_t N, int32_t *S_pla
     SGPU_CUDA(ctx, cudaEventRecord(ev_s0, st)); // the partition is folded into the first panel's staging time
     {
         const unsigned grid = static_cast<unsigned>(std::min<uint64_t>(in.n_loci, static_cast<uint64_t>(sms) * 16));
-        const size_t psmem = (static_cast<size_t>(PART_OUT) + in.n_groups) * sizeof(uint16_t);
+        const size_t psmem = (static_cast<size_t>(PART_OUT) + (in.gmap_identity ? 0 : in.n_groups)) * sizeof(uint16_t);
         if (psmem > 200 * 1024) {
             return sgpu_fail(ctx, SGPU_E_ARG, "too many groups (%u) for the shared-memory group map of the GEMM path", in.n_groups);
         }
@@ -1295,6 +1384,7 @@ int sgpu_gemm_run(sgpu_ctx *ctx, const GemmInput &in, uint32_t N, int32_t *S_pla
             pa.gmap = in.gmap;
             pa.n_groups = in.n_groups;
             pa.n_cells = N;
+            pa.identity = in.gmap_identity ? 1u : 0u;
             pa.n_loci = in.n_loci;
             pa.n_stripes = n_stripes;
             pa.stripe_magic = static_cast<uint32_t>(((1ull << 32) + cells_per_cta - 1) / cells_per_cta);
@@ -1394,40 +1484,53 @@ int sgpu_gemm_run(sgpu_ctx *ctx, const GemmInput &in, uint32_t N, int32_t *S_pla
         // the planes are zero right after sgpu_counts_zero: the first panel stores, later ones add in place
         const int epi = *fresh ? EPI_STORE : EPI_RMW;
         const unsigned grid = static_cast<unsigned>(std::min<uint64_t>(wl.n_work, units));
-        sgpu_ctx::TensorJob job;
-        SGPU_CUDA(ctx, get_event(&job.t0));
-        SGPU_CUDA(ctx, get_event(&job.t1));
-        ctx->tensor_jobs.push_back(job); // from here on the events belong to the job list
-        if (defer) {
-            SGPU_CUDA(ctx, cudaStreamWaitEvent(gs, ev_s1, 0)); // staged (and everything before it on ctx->stream: the zeroed planes)
-        }
+        TensorLaunch tl;
+        tl.map = map;
+        tl.wl = wl;
+        tl.S = S_plane;
+        tl.D = D_plane;
+        tl.N = N;
+        tl.epi = epi;
+        tl.grid = grid;
+        tl.stages2 = stages2;
+        tl.pairs = pairs;
+        tl.err = errp;
         if (pairs && wave_sync) {
-            wl.wave_ctr = reinterpret_cast<unsigned int *>(errp + 1);
-            SGPU_CUDA(ctx, cudaMemsetAsync(errp + 1, 0, sizeof(int), gs));
+            tl.wl.wave_ctr = reinterpret_cast<unsigned int *>(errp + 1);
         }
-        SGPU_CUDA(ctx, cudaEventRecord(job.t0, gs));
-        if (pairs) {
-            if (stages2 == 4) {
-                SGPU_LAUNCH(ctx, (syrk2_kernel<4><<<2 * grid, GEMM_THREADS, smem2_bytes(4), gs>>>(map, wl, S_plane, D_plane, N, epi)));
-            } else if (stages2 == 5) {
-                SGPU_LAUNCH(ctx, (syrk2_kernel<5><<<2 * grid, GEMM_THREADS, smem2_bytes(5), gs>>>(map, wl, S_plane, D_plane, N, epi)));
-            } else {
-                SGPU_LAUNCH(ctx, (syrk2_kernel<6><<<2 * grid, GEMM_THREADS, smem2_bytes(6), gs>>>(map, wl, S_plane, D_plane, N, epi)));
-            }
-        } else {
-            SGPU_LAUNCH(ctx, (syrk_kernel<<<grid, GEMM_THREADS, SMEM_BYTES, gs>>>(map, wl, S_plane, D_plane, N, 1, epi)));
-        }
-        owner.launched = true;
-        SGPU_CUDA(ctx, cudaGetLastError());
-        SGPU_CUDA(ctx, cudaEventRecord(ctx->tensor_jobs.back().t1, gs));
+        SGPU_CUDA(ctx, get_event(&tl.job.t0));
+        SGPU_CUDA(ctx, get_event(&tl.job.t1));
         *fresh = false;
-        if (last) { // the job of the last panel owns the panel
-            ctx->tensor_jobs.back().U = owner.U;
-            ctx->tensor_jobs.back().err = owner.err;
+        if (last && defer && ctx->late_gemm) {
+            // prepared, not issued: sgpu_tensor_flush (behind the next batch's link_window kernel, or at the first join)
+            TensorLaunch *pending = new TensorLaunch(tl);
+            if (get_event(&pending->staged) != cudaSuccess || cudaEventRecord(pending->staged, st) != cudaSuccess) {
+                delete pending;
+                return sgpu_fail(ctx, SGPU_E_CUDA, "event for the deferred tensor kernel");
+            }
+            pending->job.U = owner.U;
+            pending->job.err = owner.err;
             owner.U = nullptr;
             owner.err = nullptr;
-        } else if (defer) {
-            SGPU_CUDA(ctx, cudaStreamWaitEvent(st, ctx->tensor_jobs.back().t1, 0)); // the next panel is staged into the same buffer
+            ctx->pending_gemm = pending;
+        } else {
+            if (defer) {
+                SGPU_CUDA(ctx, cudaStreamWaitEvent(gs, ev_s1, 0)); // staged (and everything before it on ctx->stream: the zeroed planes)
+                SGPU_TRY(sgpu_cache_preference(ctx, true));        // what is launched from now on may run beside this kernel
+            }
+            if (last) { // the job of the last panel owns the panel
+                tl.job.U = owner.U;
+                tl.job.err = owner.err;
+            }
+            owner.launched = true;
+            if (last) { // the job list owns them now (also if the launch fails: the job is in the list by then)
+                owner.U = nullptr;
+                owner.err = nullptr;
+            }
+            SGPU_TRY(issue_tensor_launch(ctx, gs, tl));
+            if (!last && defer) {
+                SGPU_CUDA(ctx, cudaStreamWaitEvent(st, ctx->tensor_jobs.back().t1, 0)); // the next panel is staged into the same buffer
+            }
         }
         first = false;
         SGPU_TRACE(ctx, "gemm: syrk");
@@ -1442,6 +1545,9 @@ int sgpu_gemm_run(sgpu_ctx *ctx, const GemmInput &in, uint32_t N, int32_t *S_pla
 // Jobs whose end event has been reached: kernel time into the context's statistics, events back to the pool, operand
 // panel back to the cache (whoever gets it next is ordered behind this call on ctx->stream, and the kernel is done).
 int sgpu_tensor_poll(sgpu_ctx *ctx, bool wait_all) {
+    if (wait_all) {
+        SGPU_TRY(sgpu_tensor_flush(ctx, false));
+    }
     while (!ctx->tensor_jobs.empty()) {
         sgpu_ctx::TensorJob &j = ctx->tensor_jobs.front();
         cudaError_t q = wait_all ? cudaEventSynchronize(j.t1) : cudaEventQuery(j.t1);
@@ -1466,8 +1572,9 @@ int sgpu_tensor_poll(sgpu_ctx *ctx, bool wait_all) {
 }
 
 int sgpu_tensor_join(sgpu_ctx *ctx) {
+    SGPU_TRY(sgpu_tensor_flush(ctx, false));
     if (!ctx->tensor_jobs.empty()) {
         SGPU_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->tensor_jobs.back().t1, 0));
     }
-    return SGPU_OK;
+    return sgpu_cache_preference(ctx, false); // nothing runs beside a tensor kernel until the next one is launched
 }

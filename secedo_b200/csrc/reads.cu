@@ -153,6 +153,7 @@ constexpr uint32_t WIN_META_N = WIN_META + WIN_RING + 1;
 // streamed from global memory.
 __global__ void __launch_bounds__(WIN_THREADS, 2) link_window_kernel(
         const uint64_t *__restrict__ row_ptr, const uint32_t *__restrict__ position, const uint32_t *__restrict__ read_id,
+        const uint64_t *__restrict__ src_off /* null, or: the ids of locus l start at read_id[src_off[l]] (sgpu_pileup::view_off) */,
         const uint8_t *__restrict__ lchr, uint64_t n_loci, uint32_t L, uint32_t loci_per_cta,
         uint32_t slots /* power of two */, uint32_t id_cap /* multiple of 4, >= largest locus + 4 */,
         uint32_t n_ring /* 1 .. WIN_RING slots of id_cap ids: as many as shared memory holds (huge loci: 1) */,
@@ -162,6 +163,7 @@ __global__ void __launch_bounds__(WIN_THREADS, 2) link_window_kernel(
     uint2 *rbuf = reinterpret_cast<uint2 *>(s_mem + n_ring * id_cap);                // [REC_BUF]
     unsigned short *tab = reinterpret_cast<unsigned short *>(rbuf + REC_BUF);       // [slots]
     __shared__ uint64_t s_row[WIN_META_N + 1];
+    __shared__ uint64_t s_src[WIN_META_N]; // first element of the locus in read_id (= s_row unless the ids are a view)
     __shared__ uint32_t s_pos[WIN_META_N];
     __shared__ uint8_t s_chr[WIN_META_N];
     __shared__ uint32_t s_cnt;
@@ -184,6 +186,7 @@ __global__ void __launch_bounds__(WIN_THREADS, 2) link_window_kernel(
             if (i < WIN_META_N) {
                 s_pos[i] = l < n_loci ? position[l] : 0;
                 s_chr[i] = l < n_loci ? lchr[l] : 0xFF;
+                s_src[i] = l < n_loci ? (src_off ? src_off[l] : row_ptr[l]) : 0;
             }
         }
     };
@@ -191,10 +194,10 @@ __global__ void __launch_bounds__(WIN_THREADS, 2) link_window_kernel(
     // congruent modulo 16 bytes, so the body goes in 16-byte copies
     auto prefetch = [&](uint64_t l) {
         if (l < n_loci && l - meta0 < WIN_META_N) {
-            const uint64_t e0 = s_row[l - meta0], e1 = s_row[l - meta0 + 1];
+            const uint64_t e0 = s_src[l - meta0];
             uint32_t *dst = ring + (l % n_ring) * id_cap + (e0 & 3u);
             const uint32_t *src = read_id + e0;
-            const uint32_t n = static_cast<uint32_t>(e1 - e0);
+            const uint32_t n = static_cast<uint32_t>(s_row[l - meta0 + 1] - s_row[l - meta0]);
             const uint32_t head = aligned16 ? min(n, static_cast<uint32_t>((4 - (e0 & 3u)) & 3u)) : n;
             const uint32_t body = (n - head) >> 2;
             for (uint32_t i = threadIdx.x; i < head; i += WIN_THREADS) {
@@ -228,7 +231,7 @@ __global__ void __launch_bounds__(WIN_THREADS, 2) link_window_kernel(
         const uint32_t n = static_cast<uint32_t>(s_row[mi + 1] - e0);
         const uint32_t p0 = s_pos[mi];
         const uint32_t chr = s_chr[mi];
-        const uint32_t *ids = ring + (lo % n_ring) * id_cap + (e0 & 3u);
+        const uint32_t *ids = ring + (lo % n_ring) * id_cap + (s_src[mi] & 3u);
         // flush the staged links while nobody emits (uniform: s_cnt is read after the barrier that ended the last owner)
         if (s_cnt > REC_BUF / 2) {
             const uint32_t m = min(s_cnt, REC_BUF);
@@ -301,7 +304,7 @@ __global__ void __launch_bounds__(WIN_THREADS, 2) link_window_kernel(
                     cp_async_wait<0>();
                     __syncthreads();
                 }
-                const uint32_t *wid = ring + (l % n_ring) * id_cap + (a0 & 3u);
+                const uint32_t *wid = ring + (l % n_ring) * id_cap + (s_src[l - meta0] & 3u);
                 for (uint32_t ib = threadIdx.x; ib < nl; ib += 4 * WIN_THREADS) {
                     uint32_t id4[4], cur4[4], s4[4];
 #pragma unroll
@@ -326,12 +329,14 @@ __global__ void __launch_bounds__(WIN_THREADS, 2) link_window_kernel(
                     }
                 }
             } else {
+                // where the ids of this locus start in read_id, relative to its entry numbers
+                const uint64_t shift_src = (meta_here ? s_src[l - meta0] : (src_off ? src_off[l] : a0)) - a0;
                 for (uint64_t eb = a0 + threadIdx.x; eb < a1; eb += 4 * WIN_THREADS) {
                     uint32_t id4[4];
 #pragma unroll
                     for (int u = 0; u < 4; ++u) { // four loads in flight
                         const uint64_t e = eb + u * WIN_THREADS;
-                        id4[u] = e < a1 ? read_id[e] : 0;
+                        id4[u] = e < a1 ? read_id[e + shift_src] : 0;
                     }
 #pragma unroll
                     for (int u = 0; u < 4; ++u) {
@@ -1072,6 +1077,10 @@ int sgpu_link_reads(sgpu_ctx *ctx, const sgpu_pileup *p, uint32_t num_cells, uin
     out->num_cells = num_cells;
     SGPU_CUDA(ctx, out->gmap.alloc(n_groups ? n_groups : 1, ctx));
     SGPU_CUDA(ctx, cudaMemcpyAsync(out->gmap.p, h_group_id_to_pos, n_groups * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
+    out->gmap_identity = n_groups <= num_cells;
+    for (uint32_t g = 0; g < n_groups && out->gmap_identity; ++g) {
+        out->gmap_identity = h_group_id_to_pos[g] == g;
+    }
     const uint64_t W = E / 32 + 1; // bitmap words
     SGPU_CUDA(ctx, out->sp_bits.alloc(W, ctx));
     SGPU_CUDA(ctx, cudaMemsetAsync(out->sp_bits.p, 0, W * sizeof(uint32_t), st));
@@ -1180,9 +1189,15 @@ int sgpu_link_reads(sgpu_ctx *ctx, const sgpu_pileup *p, uint32_t num_cells, uin
             const uint64_t want = std::min<uint64_t>(P, static_cast<uint64_t>(ctx->sm_count) * per_sm);
             const uint32_t loci_per_cta = static_cast<uint32_t>(ceil_div_u64(P, want));
             const unsigned wgrid = static_cast<unsigned>(ceil_div_u64(P, loci_per_cta));
-            SGPU_LAUNCH(ctx, (link_window_kernel<<<wgrid, WIN_THREADS, smem, st>>>(p->d_row_ptr, p->d_position, p->d_read_id, out->lchr.p, P, L,
+            // this kernel never fits beside the tensor kernel of the previous batch, so it and everything behind it on the
+            // stream run alone: back to the default shared-memory / L1 split
+            SGPU_TRY(sgpu_cache_preference(ctx, false));
+            SGPU_LAUNCH(ctx, (link_window_kernel<<<wgrid, WIN_THREADS, smem, st>>>(p->d_row_ptr, p->d_position,
+                                                                                  p->d_read_id ? p->d_read_id : p->view_read_id,
+                                                                                  p->d_read_id ? nullptr : p->view_off, out->lchr.p, P, L,
                                                                                   loci_per_cta, slots, id_cap, n_ring, links.p, cap, d_ctr.p)));
         } else {
+            SGPU_TRY(sgpu_pileup_materialize(ctx, p)); // the global hash reads the ids by entry number
             DevBuf<uint64_t> keys;
             DevBuf<uint32_t> vals;
             uint64_t hcap = 1024;
@@ -1198,6 +1213,9 @@ int sgpu_link_reads(sgpu_ctx *ctx, const sgpu_pileup *p, uint32_t num_cells, uin
                                                                             links.p, cap, d_ctr.p)));
         }
         SGPU_CUDA(ctx, cudaGetLastError());
+        // the previous batch's tensor kernel, if its launch has been held back: behind the dense linking pass, beside
+        // everything that follows (sgpu_tensor_flush)
+        SGPU_TRY(sgpu_tensor_flush(ctx, true));
         SGPU_CUDA(ctx, cudaMemcpyAsync(&ctx->h_scratch[0], d_ctr.p, sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
         SGPU_CUDA(ctx, cudaStreamSynchronize(st));
         NL = ctx->h_scratch[0];

@@ -223,6 +223,53 @@ def test_device_generated_pileup(gpu_ctx, path):
     assert st["n_multi_reads"] > 0 and st["n_dropped_entries"] > 0 and st["n_pairs_multi"] > 0
 
 
+@pytest.mark.parametrize("path", PATHS)
+def test_filtered_view_of_read_ids(gpu_ctx, path, monkeypatch):
+    """at the root of the recursion (every group in the sub-cluster) the filter does not copy the read ids: the filtered
+    pileup reads them through a view of the unfiltered one (sgpu_pileup::view_read_id). The read linking must see the same
+    ids through the view, the source must outlive its views (it is freed FIRST here), and a download gathers them."""
+    ident = np.arange(700, dtype=np.uint32)
+    dev = gpu_ctx.synth_pileup(700, 0.4, 3, 500, n_clones=2, theta=0.001, p_multi=0.08, p_mate=0.05, seed=19)
+    p = dev.download()
+    kl, ke, _, _ = po.filter_flags(p, ident, 0.001)
+    want = p.select(kl, ke)
+    o = po.similarity(want, 700, 1000, ident, 0.01, 0.15, 0.001, 8, "ADD_MIN")
+    flt = api.Filter(0.001, 4, gpu_ctx)
+    fdev, _ = flt.filter_device(dev, ident)
+    dev.free()  # the view keeps the source's read ids alive
+    c = api.Counts(gpu_ctx, 700)
+    st = c.accumulate(fdev, 1000, ident, 0.01, 0.15, 0.001, 8, path)
+    S1, D1, H, _ = c.download()
+    assert np.array_equal(S1, o.S1) and np.array_equal(D1, o.D1) and np.array_equal(H, o.H)
+    assert st["n_multi_reads"] > 0 and st["n_dropped_entries"] > 0
+    assert fdev.download() == want  # gathers the ids; the deferred free of the source happens here
+    c.zero()
+    c.accumulate(fdev, 1000, ident, 0.01, 0.15, 0.001, 8, path)  # now from the pileup's own ids
+    S2, D2, H2, _ = c.download()
+    assert np.array_equal(S2, o.S1) and np.array_equal(D2, o.D1) and np.array_equal(H2, o.H)
+    fdev.free()
+    # a sub-cluster (some groups outside) always copies; so does SECEDO_B200_FILTER_VIEW=0
+    dev = gpu_ctx.synth_pileup(700, 0.4, 3, 500, n_clones=2, theta=0.001, p_multi=0.08, p_mate=0.05, seed=19)
+    monkeypatch.setenv("SECEDO_B200_FILTER_VIEW", "0")
+    f0, _ = flt.filter_device(dev, ident)
+    assert f0.download() == want
+    f0.free()
+    monkeypatch.delenv("SECEDO_B200_FILTER_VIEW")
+    sub = ident.copy()
+    sub[::3] = NO_POS
+    kl, ke, _, _ = po.filter_flags(p, sub, 0.001)
+    fs, _ = flt.filter_device(dev, sub)
+    assert fs.download() == p.select(kl, ke)
+    fs.free()
+    # filtering a filtered pileup that still reads through a view
+    f1, _ = flt.filter_device(dev, ident)
+    f2, _ = flt.filter_device(f1, ident)
+    assert f2.download() == want
+    for x in (f1, f2, dev):
+        x.free()
+    c.free()
+
+
 def test_auto_path_and_stats(gpu_ctx):
     dev = gpu_ctx.synth_pileup(1024, 0.5, 1, 4000, theta=0.001, p_multi=0.01, seed=4)
     ident = np.arange(1024, dtype=np.uint32)
