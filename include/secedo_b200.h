@@ -108,6 +108,14 @@ uint64_t sgpu_launch_count(const sgpu_ctx *ctx);
  * during the call (usually the one of the batch before). This call waits for the kernels still in flight and returns
  * (and resets) the time and number of the kernels no sgpu_stats has reported yet. */
 int sgpu_tensor_times(sgpu_ctx *ctx, float *ms, uint64_t *launches);
+/* Scheduling knobs of a context (their defaults come from the environment variables of the same meaning, read by sgpu_init;
+ * the results never depend on them). Waits for the context's work first. Names:
+ *   "async_gemm"     1: the first-order tensor kernel runs on its own stream beside the next batch (SECEDO_B200_ASYNC_GEMM)
+ *   "late_gemm"      1: ... and is issued behind the next batch's dense read-linking kernel (SECEDO_B200_GEMM_LATE)
+ *   "gemm_stages"    4, 5, 6: operand ring of the tensor kernel (SECEDO_B200_GEMM_STAGES)
+ *   "prefer_shared"  0 never, 1 always, 2 around the co-run window: device-wide cudaFuncCachePreferShared (SECEDO_B200_PREFER_SHARED)
+ *   "win_smem_kb"    shared memory a read-linking CTA may use, 0 = all (SECEDO_B200_WIN_SMEM_KB) */
+int sgpu_set_option(sgpu_ctx *ctx, const char *name, int value);
 
 /* ---- pileup staging (replaces the host vector<vector<PosData>>) --------------------------- */
 int sgpu_pileup_upload(sgpu_ctx *ctx, uint32_t n_chr, const uint64_t *chr_ptr, const uint64_t *row_ptr,

@@ -77,6 +77,7 @@ SIGNATURES = {
     "sgpu_synchronize": (C.c_int, [_vp]),
     "sgpu_launch_count": (C.c_uint64, [_vp]),
     "sgpu_tensor_times": (C.c_int, [_vp, C.POINTER(C.c_float), C.POINTER(C.c_uint64)]),
+    "sgpu_set_option": (C.c_int, [_vp, C.c_char_p, C.c_int]),
     "sgpu_synth_pileup": (C.c_int, [_vp, C.POINTER(SynthParams), C.POINTER(_vp)]),
     "sgpu_pileup_upload": (C.c_int, [_vp, C.c_uint32, _vp, _vp, _vp, _vp, _vp, C.POINTER(_vp)]),
     "sgpu_pileup_upload_async": (C.c_int, [_vp, C.c_uint32, _vp, _vp, _vp, _vp, _vp, C.POINTER(_vp)]),

@@ -63,6 +63,11 @@ class Context:
         """CUDA kernels launched by this context so far."""
         return int(self._lib.sgpu_launch_count(self._h))
 
+    def set_option(self, name: str, value: int) -> None:
+        """Scheduling knobs (``async_gemm``, ``late_gemm``, ``gemm_stages``, ``prefer_shared``, ``win_smem_kb``): see
+        ``sgpu_set_option`` in include/secedo_b200.h. Results never depend on them."""
+        self.check(self._lib.sgpu_set_option(self._h, name.encode(), int(value)))
+
     def tensor_times(self):
         """(ms, launches) of the first-order tensor kernels that no ``accumulate`` statistics have reported yet; waits for
         the kernels still in flight (they run on a stream of their own, beside the next batch's filter and staging)."""

@@ -447,6 +447,42 @@ int sgpu_tensor_times(sgpu_ctx *ctx, float *ms, uint64_t *launches) {
     return SGPU_OK;
 }
 
+int sgpu_set_option(sgpu_ctx *ctx, const char *name, int value) {
+    if (!name) {
+        return sgpu_fail(ctx, SGPU_E_ARG, "sgpu_set_option: null name");
+    }
+    SGPU_CUDA(ctx, cudaSetDevice(ctx->device));
+    SGPU_TRY(sgpu_synchronize(ctx));
+    const std::string n(name);
+    if (n == "async_gemm") {
+        ctx->async_gemm = value != 0;
+    } else if (n == "late_gemm") {
+        ctx->late_gemm = value != 0;
+    } else if (n == "gemm_stages") {
+        if (value < 4 || value > 6) {
+            return sgpu_fail(ctx, SGPU_E_ARG, "gemm_stages must be 4, 5 or 6");
+        }
+        ctx->gemm_stages = static_cast<uint32_t>(value);
+    } else if (n == "prefer_shared") {
+        if (value < 0 || value > 2) {
+            return sgpu_fail(ctx, SGPU_E_ARG, "prefer_shared must be 0, 1 or 2");
+        }
+        if (ctx->cache_pref_now == 1) { // back to the default split before the mode changes
+            SGPU_CUDA(ctx, cudaDeviceSetCacheConfig(cudaFuncCachePreferNone));
+            ctx->cache_pref_now = 0;
+        }
+        ctx->prefer_shared = value;
+        if (value == 1) {
+            SGPU_TRY(sgpu_cache_preference(ctx, true));
+        }
+    } else if (n == "win_smem_kb") {
+        ctx->win_smem_limit = value > 0 ? static_cast<uint32_t>(std::max(16, value)) * 1024u : 0u;
+    } else {
+        return sgpu_fail(ctx, SGPU_E_ARG, "sgpu_set_option: unknown option '%s'", name);
+    }
+    return SGPU_OK;
+}
+
 // ---- pileup ---------------------------------------------------------------------------------------
 static int pileup_upload(sgpu_ctx *ctx, uint32_t n_chr, const uint64_t *chr_ptr, const uint64_t *row_ptr,
                          const uint32_t *position, const uint32_t *read_id, const uint16_t *gid_base, bool async,
