@@ -695,6 +695,20 @@ def main_ours(args):
                     "ops it reaches frac_executed_of_nominal of the 4.5 POP/s dense int8 rate",
             "traffic_source": traffic_src,
         }
+        # ---- the same path through the C++ drop-in shim (what an unmodified SECEDO calls): pageable vector<vector<PosData>>
+        # in, Matd out, host-side flattening and rebuilding inside the timed calls; a quarter sub-batch of the workload's shape
+        e2e_shim = None
+        if not args.skip_extras and world == 1:
+            try:
+                import subprocess
+                import __graft_entry__ as ge
+                exe = ge.build_shim_bench()
+                env = dict(os.environ, SECEDO_B200_DEVICES=str(rig.local_rank))
+                r = subprocess.run([exe, str(N), str(w["coverage"]), "4", str(int(os.environ.get("SECEDO_BENCH_SHIM_LOCI", 8192))),
+                                    str(threads), "2"], capture_output=True, text=True, timeout=600, env=env)
+                e2e_shim = json.loads(r.stdout.strip().splitlines()[-1]) if r.returncode == 0 else {"error": (r.stderr or r.stdout)[-300:]}
+            except Exception as ex:  # noqa: BLE001
+                e2e_shim = {"error": str(ex)[-300:]}
         # ---- Laplacian + the 7 leading eigenpairs of a matrix of this workload, resident in HBM ----
         spectral, em = None, None
         if not args.skip_extras and world == 1:
@@ -787,7 +801,7 @@ def main_ours(args):
                            "keeps straight over PCIe: h2d_bytes_per_step counts what crossed the bus, "
                            "host_pileup_bytes_per_step the whole input) -> accumulate -> epilogue -> N x N fp64 matrix in host "
                            "memory, every step (per rank: d2h_bytes_per_step = its share)"},
-            "gpu_launches": int(launches), "clocks": clocks, "spectral": spectral, "em": em,
+            "gpu_launches": int(launches), "clocks": clocks, "e2e_shim": e2e_shim, "spectral": spectral, "em": em,
         }
         print(json.dumps(line))
     rig.barrier()

@@ -325,6 +325,8 @@ int sgpu_init(int device, sgpu_ctx **out) {
         ctx->async_gemm = !(as && as[0] == '0');
         const char *lg = getenv("SECEDO_B200_GEMM_LATE");
         ctx->late_gemm = !(lg && lg[0] == '0');
+        const char *fp = getenv("SECEDO_B200_GEMM_FLUSH_AT");
+        ctx->flush_point = fp ? std::min(2, std::max(0, atoi(fp))) : 0;
         const char *ps = getenv("SECEDO_B200_PREFER_SHARED");
         ctx->prefer_shared = ps ? atoi(ps) : (ctx->async_gemm ? 2 : 0);
         if (ctx->prefer_shared == 1) {

@@ -53,6 +53,8 @@ struct sgpu_ctx {
     std::deque<TensorJob> tensor_jobs;
     void *pending_gemm = nullptr;        // gemm.cu: prepared launch of the last deferred tensor kernel, not issued yet
     bool late_gemm = true;               // issue it behind the next batch's link_window kernel (SECEDO_B200_GEMM_LATE=0: at once)
+    int flush_point = 0;                 // where exactly (SECEDO_B200_GEMM_FLUSH_AT): 0 behind link_window, 1 behind the
+                                         // special-entry chain, 2 behind the partition kernel
     std::vector<cudaEvent_t> event_pool; // recycled timing events
     // Kernels only share an SM with the tensor kernel while the DEVICE-WIDE cache preference is cudaFuncCachePreferShared: a
     // kernel with 16 KB of static shared memory otherwise waited for the whole tensor kernel, and neither the carve-out

@@ -1247,7 +1247,9 @@ int sgpu_gemm_run(sgpu_ctx *ctx, const GemmInput &in, uint32_t N, int32_t *S_pla
 
     // tensor kernels of earlier batches: issue the one still pending, retire the finished ones; never more than two operand
     // panels in flight
-    SGPU_TRY(sgpu_tensor_flush(ctx, false));
+    if (ctx->flush_point != 2) {
+        SGPU_TRY(sgpu_tensor_flush(ctx, false));
+    }
     SGPU_TRY(sgpu_tensor_poll(ctx, false));
     while (ctx->tensor_jobs.size() >= 2) {
         SGPU_CUDA(ctx, cudaEventSynchronize(ctx->tensor_jobs.front().t1));
@@ -1397,6 +1399,9 @@ int sgpu_gemm_run(sgpu_ctx *ctx, const GemmInput &in, uint32_t N, int32_t *S_pla
             return SGPU_OK;
         };
         SGPU_TRY(in.gid_base32 ? run_partition(in.gid_base32) : run_partition(in.gid_base));
+        if (ctx->flush_point == 2) {
+            SGPU_TRY(sgpu_tensor_flush(ctx, true));
+        }
     }
 
     bool first = true;

@@ -1215,7 +1215,9 @@ int sgpu_link_reads(sgpu_ctx *ctx, const sgpu_pileup *p, uint32_t num_cells, uin
         SGPU_CUDA(ctx, cudaGetLastError());
         // the previous batch's tensor kernel, if its launch has been held back: behind the dense linking pass, beside
         // everything that follows (sgpu_tensor_flush)
-        SGPU_TRY(sgpu_tensor_flush(ctx, true));
+        if (ctx->flush_point == 0) {
+            SGPU_TRY(sgpu_tensor_flush(ctx, true));
+        }
         SGPU_CUDA(ctx, cudaMemcpyAsync(&ctx->h_scratch[0], d_ctr.p, sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
         SGPU_CUDA(ctx, cudaStreamSynchronize(st));
         NL = ctx->h_scratch[0];
@@ -1445,6 +1447,9 @@ int sgpu_link_reads(sgpu_ctx *ctx, const sgpu_pileup *p, uint32_t num_cells, uin
     SGPU_CUDA(ctx, cudaGetLastError());
 
     SGPU_TRACE(ctx, "link: cutoff+finish");
+    if (ctx->flush_point == 1) { // the held-back tensor kernel behind the special-entry chain instead of behind link_window
+        SGPU_TRY(sgpu_tensor_flush(ctx, true));
+    }
     // scalars to the host: errors, stats, reads created, tail loci per chromosome
     std::vector<uint64_t> h_nt(p->n_chr), h_tl(p->n_chr);
     SGPU_CUDA(ctx, cudaMemcpyAsync(h_tl.data(), out->tail_locus.p, p->n_chr * sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
