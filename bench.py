@@ -386,6 +386,16 @@ def main_ours(args):
     counts = api.Counts(ctx, N)
     epi = sdist.SlabEpilogue(counts, device) if world > 1 else None
     last = {}
+    # Consecutive steps of the device-resident run alternate between TWO sets of count planes, and the epilogue of a step is
+    # issued after the first sub-batch of the next one: the last tensor kernel of a matrix (held back until the next
+    # link_window kernel has been issued, DESIGN 4 "Scheduling") then runs beside the next matrix's first sub-batch instead
+    # of alone in front of its epilogue (4.4 of 35 ms per step). Every step still filters and accumulates its four
+    # sub-batches and produces its own matrix; the K-th matrix is finished by finish_prev() inside the timed region.
+    # SECEDO_BENCH_PIPELINE_STEPS=0: one set of planes, the epilogue at the end of its own step.
+    pipeline = os.environ.get("SECEDO_BENCH_PIPELINE_STEPS", "1") == "1"
+    counts_ab = [counts, api.Counts(ctx, N)] if pipeline else [counts]
+    epi_ab = [epi, (sdist.SlabEpilogue(counts_ab[1], device) if world > 1 else None)] if pipeline else [epi]
+    pipe = {"i": 0, "prev": None, "ev": None}
     # Filter::filter of sub-batch k + 1 next to computeSimilarityMatrix of sub-batch k: a second context (own stream, own
     # host thread) filters ahead, so that its memory-bound kernels run under the tensor-bound GEMM of the sub-batch before
     # (they need 2 KB of shared memory per CTA and fit beside the GEMM's CTAs). Measured at N = 1: 42.30 against 42.62 ms per
@@ -418,13 +428,15 @@ def main_ours(args):
             yield item
         th.join()
 
-    def accumulate_all(sources, st, free_sources=False, top_up=None):
+    def accumulate_all(sources, st, free_sources=False, top_up=None, into=None, after_first=None):
         feed = filtered_stream(sources) if not (free_sources or top_up) else None
-        for src in sources:
+        for n_done, src in enumerate(sources):
             filtered = next(feed) if feed else flt.filter_device(src, ident)[0]
             if top_up:
                 top_up()
-            s1 = counts.accumulate(filtered, w["L"], ident, w["eps"], w["h"], w["theta"], threads, args.path)
+            s1 = (into or counts).accumulate(filtered, w["L"], ident, w["eps"], w["h"], w["theta"], threads, args.path)
+            if after_first and n_done == 0:
+                after_first()
             st["sig_loci"] = st.get("sig_loci", 0) + filtered.n_loci
             st["kept_entries"] = st.get("kept_entries", 0) + filtered.n_entries
             for k in PHASES:
@@ -434,34 +446,50 @@ def main_ours(args):
             if free_sources:
                 src.free()
 
-    def epilogue(st, out_ptr=None, out_host=None, async_out=False):
+    def epilogue(st, out_ptr=None, out_host=None, async_out=False, which=0):
         """N x N matrix from the planes of all ranks. One GPU: the single-GPU epilogue. Several: the peer-memory epilogue
         (every rank its share; into the shared host matrix at out_ptr, or left in the ranks' HBM)."""
         r0, r1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         r0.record(stream)
         if world > 1:
-            epi.run(*lik, w["normalization"], out_ptr=out_ptr, same_stream=True)
+            epi_ab[which].run(*lik, w["normalization"], out_ptr=out_ptr, same_stream=True)
         elif async_out:
-            counts.finalize_async(*lik, w["normalization"], out_host)
+            counts_ab[which].finalize_async(*lik, w["normalization"], out_host)
         else:
-            counts.finalize(*lik, w["normalization"], out=out_host, to_host=out_host is not None)
+            counts_ab[which].finalize(*lik, w["normalization"], out=out_host, to_host=out_host is not None)
         r1.record(stream)
         st["_ev"] = (r0, r1)
 
+    def finish_prev():
+        """the epilogue of the step before (pipelined steps): its matrix"""
+        if pipe["prev"] is not None:
+            e = {}
+            epilogue(e, which=pipe["prev"])
+            pipe["prev"], pipe["ev"] = None, e["_ev"]
+
     def step_resident():
         st = {}
-        counts.zero()
-        accumulate_all(raw_dev, st)
-        epilogue(st)
-        r0, r1 = st.pop("_ev")
-        r1.synchronize()
-        st["ms_epilogue_total"] = r0.elapsed_time(r1)
+        k = pipe["i"] % len(counts_ab)
+        pipe["i"] += 1
+        counts_ab[k].zero()
+        if pipeline:
+            accumulate_all(raw_dev, st, into=counts_ab[k], after_first=finish_prev)
+            pipe["prev"] = k
+        else:
+            accumulate_all(raw_dev, st)
+            epilogue(st)
+            pipe["ev"] = st.pop("_ev")
+        if pipe["ev"] is not None:  # pipelined: the epilogue issued during this step (the matrix of the step before)
+            r0, r1 = pipe["ev"]
+            pipe["ev"] = None
+            r1.synchronize()
+            st["ms_epilogue_total"] = r0.elapsed_time(r1)
         last.update(st)
         return st
 
     # ---- device-resident input ------------------------------------------------------------------------
     l2_0 = ctx2.launch_count() if ctx2 else 0
-    ms_dev, acc, launches, clocks = rig.timed(step_resident, args.steps, args.warmup)
+    ms_dev, acc, launches, clocks = rig.timed(step_resident, args.steps, args.warmup, finish=finish_prev)
     if ctx2:  # warm-up launches of the second context are not part of the timed region
         launches += (ctx2.launch_count() - l2_0) * args.steps // (args.steps + args.warmup)
     sig_local = acc["sig_loci"] // args.steps
@@ -483,6 +511,7 @@ def main_ours(args):
         ms_left, n_left = ctx.tensor_times()
         a2["ms_gemm"] += ms_left
         a2["gemm_launches"] += n_left
+        finish_prev()
         ctx.set_option("async_gemm", 1)
         alone = a2["ms_gemm"] / max(1, a2["gemm_launches"])
 
@@ -774,6 +803,7 @@ def main_ours(args):
                 "num_threads_for_cutoff": threads, "normalization": w["normalization"],
                 "path": last.get("path_used"), "filter_overlaps_previous_gemm": overlap,
                 "tensor_kernel_overlaps_next_sub_batch": os.environ.get("SECEDO_B200_ASYNC_GEMM", "1") != "0",
+                "steps_pipelined_over_two_sets_of_count_planes": pipeline,
                 "parallelism": f"loci sharded by chromosome over {world} GPU(s); per step every GPU accumulates its "
                                f"{SUB} sub-batches into its own int32 count planes" + (
                     ", then the peer-memory epilogue: each GPU sums the planes of all GPUs over 1/%d of the matrix through "
@@ -809,6 +839,8 @@ def main_ours(args):
         shared.close()
     if epi:
         epi.close()
+    if pipeline and epi_ab[1]:
+        epi_ab[1].close()
     if world > 1:
         dist.destroy_process_group()
     return 0

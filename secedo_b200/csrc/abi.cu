@@ -829,7 +829,7 @@ int sgpu_counts_create(sgpu_ctx *ctx, uint32_t num_cells, sgpu_counts **out) {
 }
 
 int sgpu_counts_zero(sgpu_ctx *ctx, sgpu_counts *c) {
-    SGPU_TRY(sgpu_tensor_join(ctx)); // a first-order tensor kernel may still be adding to the planes (sgpu_ctx::tensor_jobs)
+    SGPU_TRY(sgpu_tensor_join(ctx, c->i32)); // a first-order tensor kernel may still be adding to the planes (sgpu_ctx::tensor_jobs)
     SGPU_CUDA(ctx, cudaSetDevice(ctx->device));
     // only the planes that were used since the last zeroing can be non-zero
     SGPU_CUDA(ctx, cudaMemsetAsync(c->i32, 0, static_cast<uint64_t>(c->planes_dirty) * c->nn * sizeof(int32_t), ctx->stream));
@@ -919,7 +919,7 @@ static int accumulate_impl(sgpu_ctx *ctx, sgpu_counts *c, const sgpu_pileup *fil
     EventTimer t_first(ctx->stream);
     if (path == SGPU_PATH_SCATTER) {
         SGPU_TRY(sgpu_link_dense_codes(ctx, filtered, &lr));
-        SGPU_TRY(sgpu_tensor_join(ctx)); // the atomics go to the planes a tensor kernel in flight adds to
+        SGPU_TRY(sgpu_tensor_join(ctx, c->i32)); // the atomics go to the planes a tensor kernel in flight adds to
         SGPU_TRY(sgpu_scatter_pairs(ctx, filtered, lr, c, +1, false, &s.n_pairs_first));
         c->fresh = false;
     } else {
@@ -930,7 +930,7 @@ static int accumulate_impl(sgpu_ctx *ctx, sgpu_counts *c, const sgpu_pileup *fil
         if (rc == SGPU_E_COUNT_RANGE && auto_path && !c->poisoned) {
             s.path_used = SGPU_PATH_SCATTER;
             SGPU_TRY(sgpu_link_dense_codes(ctx, filtered, &lr));
-            SGPU_TRY(sgpu_tensor_join(ctx));
+            SGPU_TRY(sgpu_tensor_join(ctx, c->i32));
             rc = sgpu_scatter_pairs(ctx, filtered, lr, c, +1, false, &s.n_pairs_first);
             c->fresh = false;
         }
@@ -1008,7 +1008,7 @@ int sgpu_counts_buffers(sgpu_counts *c, int32_t **i32, uint64_t *n_i32, double *
     if (c->owner) {
         // whoever reads the planes through these pointers is ordered behind the context's stream (a collective, a peer's
         // kernel after a barrier): make that stream wait for a first-order tensor kernel that is still adding to them
-        SGPU_TRY(sgpu_tensor_join(c->owner));
+        SGPU_TRY(sgpu_tensor_join(c->owner, c->i32));
     }
     if (i32) {
         *i32 = c->i32;
@@ -1032,7 +1032,7 @@ int sgpu_counts_buffers(sgpu_counts *c, int32_t **i32, uint64_t *n_i32, double *
 }
 
 int sgpu_counts_set_layout(sgpu_ctx *ctx, sgpu_counts *c, int planes_used, int want_spill) {
-    SGPU_TRY(sgpu_tensor_join(ctx)); // a first-order tensor kernel may still be adding to the planes (sgpu_ctx::tensor_jobs)
+    SGPU_TRY(sgpu_tensor_join(ctx, c->i32)); // a first-order tensor kernel may still be adding to the planes (sgpu_ctx::tensor_jobs)
     SGPU_CUDA(ctx, cudaSetDevice(ctx->device));
     if (planes_used != 2 && planes_used != PLANE_H3 && planes_used != N_PLANES) {
         return sgpu_fail(ctx, SGPU_E_ARG, "planes_used must be 2, %d or %d", PLANE_H3, N_PLANES);
@@ -1047,7 +1047,7 @@ int sgpu_counts_set_layout(sgpu_ctx *ctx, sgpu_counts *c, int planes_used, int w
 }
 
 int sgpu_counts_pack_range(sgpu_ctx *ctx, sgpu_counts *c, int first_plane, int n_planes, int32_t **packed, uint64_t *n) {
-    SGPU_TRY(sgpu_tensor_join(ctx)); // a first-order tensor kernel may still be adding to the planes (sgpu_ctx::tensor_jobs)
+    SGPU_TRY(sgpu_tensor_join(ctx, c->i32)); // a first-order tensor kernel may still be adding to the planes (sgpu_ctx::tensor_jobs)
     SGPU_CUDA(ctx, cudaSetDevice(ctx->device));
     if (first_plane < 0 || n_planes < 0 || first_plane + n_planes > c->planes_used) {
         return sgpu_fail(ctx, SGPU_E_ARG, "plane range [%d, %d) outside the %d planes in use", first_plane, first_plane + n_planes, c->planes_used);
@@ -1076,7 +1076,7 @@ int sgpu_counts_pack_range(sgpu_ctx *ctx, sgpu_counts *c, int first_plane, int n
 }
 
 int sgpu_counts_unpack_range(sgpu_ctx *ctx, sgpu_counts *c, int first_plane, int n_planes) {
-    SGPU_TRY(sgpu_tensor_join(ctx)); // a first-order tensor kernel may still be adding to the planes (sgpu_ctx::tensor_jobs)
+    SGPU_TRY(sgpu_tensor_join(ctx, c->i32)); // a first-order tensor kernel may still be adding to the planes (sgpu_ctx::tensor_jobs)
     SGPU_CUDA(ctx, cudaSetDevice(ctx->device));
     if (first_plane < 0 || n_planes < 0 || first_plane + n_planes > c->planes_used) {
         return sgpu_fail(ctx, SGPU_E_ARG, "plane range [%d, %d) outside the %d planes in use", first_plane, first_plane + n_planes, c->planes_used);
@@ -1105,7 +1105,7 @@ int sgpu_counts_unpack(sgpu_ctx *ctx, sgpu_counts *c) {
 }
 
 int sgpu_counts_sparse_pack(sgpu_ctx *ctx, sgpu_counts *c, int first_plane, uint32_t **idx, int32_t **val, uint64_t *nnz) {
-    SGPU_TRY(sgpu_tensor_join(ctx)); // a first-order tensor kernel may still be adding to the planes (sgpu_ctx::tensor_jobs)
+    SGPU_TRY(sgpu_tensor_join(ctx, c->i32)); // a first-order tensor kernel may still be adding to the planes (sgpu_ctx::tensor_jobs)
     SGPU_CUDA(ctx, cudaSetDevice(ctx->device));
     cudaStream_t st = ctx->stream;
     const int n_planes = c->planes_used - first_plane;
@@ -1158,7 +1158,7 @@ int sgpu_counts_sparse_pack(sgpu_ctx *ctx, sgpu_counts *c, int first_plane, uint
 }
 
 int sgpu_counts_sparse_add(sgpu_ctx *ctx, sgpu_counts *c, int first_plane, const uint32_t *idx, const int32_t *val, uint64_t nnz) {
-    SGPU_TRY(sgpu_tensor_join(ctx)); // a first-order tensor kernel may still be adding to the planes (sgpu_ctx::tensor_jobs)
+    SGPU_TRY(sgpu_tensor_join(ctx, c->i32)); // a first-order tensor kernel may still be adding to the planes (sgpu_ctx::tensor_jobs)
     SGPU_CUDA(ctx, cudaSetDevice(ctx->device));
     if (first_plane < 0 || first_plane > c->planes_used) {
         return sgpu_fail(ctx, SGPU_E_ARG, "first plane %d outside the %d planes in use", first_plane, c->planes_used);
@@ -1173,7 +1173,7 @@ int sgpu_counts_sparse_add(sgpu_ctx *ctx, sgpu_counts *c, int first_plane, const
 }
 
 int sgpu_counts_download(sgpu_ctx *ctx, sgpu_counts *c, int32_t *S1, int32_t *D1, int32_t *H, uint64_t *hist) {
-    SGPU_TRY(sgpu_tensor_join(ctx)); // a first-order tensor kernel may still be adding to the planes (sgpu_ctx::tensor_jobs)
+    SGPU_TRY(sgpu_tensor_join(ctx, c->i32)); // a first-order tensor kernel may still be adding to the planes (sgpu_ctx::tensor_jobs)
     SGPU_CUDA(ctx, cudaSetDevice(ctx->device));
     cudaStream_t st = ctx->stream;
     const uint64_t nn = c->nn, n = c->n;
@@ -1210,7 +1210,7 @@ int sgpu_counts_download(sgpu_ctx *ctx, sgpu_counts *c, int32_t *S1, int32_t *D1
 int sgpu_similarity_finalize(sgpu_ctx *ctx, sgpu_counts *c, uint32_t max_fragment_length, double mutation_rate,
                              double homozygous_rate, double seq_error_rate, int normalization, double *out,
                              sgpu_stats *stats) {
-    SGPU_TRY(sgpu_tensor_join(ctx)); // a first-order tensor kernel may still be adding to the planes (sgpu_ctx::tensor_jobs)
+    SGPU_TRY(sgpu_tensor_join(ctx, c->i32)); // a first-order tensor kernel may still be adding to the planes (sgpu_ctx::tensor_jobs)
     SGPU_CUDA(ctx, cudaSetDevice(ctx->device));
     if (c->have_params && c->spill
         && (c->eps != mutation_rate || c->h != homozygous_rate || c->theta != seq_error_rate || c->L != max_fragment_length)) {
@@ -1227,7 +1227,7 @@ int sgpu_similarity_finalize(sgpu_ctx *ctx, sgpu_counts *c, uint32_t max_fragmen
 
 int sgpu_similarity_finalize_async(sgpu_ctx *ctx, sgpu_counts *c, uint32_t max_fragment_length, double mutation_rate,
                                    double homozygous_rate, double seq_error_rate, int normalization, double *out) {
-    SGPU_TRY(sgpu_tensor_join(ctx)); // a first-order tensor kernel may still be adding to the planes (sgpu_ctx::tensor_jobs)
+    SGPU_TRY(sgpu_tensor_join(ctx, c->i32)); // a first-order tensor kernel may still be adding to the planes (sgpu_ctx::tensor_jobs)
     SGPU_CUDA(ctx, cudaSetDevice(ctx->device));
     if (!out) {
         return sgpu_fail(ctx, SGPU_E_ARG, "finalize_async needs a (page-locked) host buffer");
@@ -1280,7 +1280,7 @@ int sgpu_similarity(sgpu_ctx *ctx, const sgpu_pileup *filtered, uint32_t num_cel
 int sgpu_slab_raw(sgpu_ctx *ctx, sgpu_counts *c, const int32_t *const *peer_planes, const double *const *peer_spill,
                   uint32_t n_peers, uint32_t slab, uint32_t n_slabs, uint32_t max_fragment_length, double mutation_rate,
                   double homozygous_rate, double seq_error_rate, double **extrema) {
-    SGPU_TRY(sgpu_tensor_join(ctx)); // a first-order tensor kernel may still be adding to the planes (sgpu_ctx::tensor_jobs)
+    SGPU_TRY(sgpu_tensor_join(ctx, c->i32)); // a first-order tensor kernel may still be adding to the planes (sgpu_ctx::tensor_jobs)
     SGPU_CUDA(ctx, cudaSetDevice(ctx->device));
     return sgpu_slab_raw_impl(ctx, c, peer_planes, peer_spill, n_peers, slab, n_slabs, max_fragment_length, mutation_rate,
                               homozygous_rate, seq_error_rate, extrema);
@@ -1347,7 +1347,7 @@ int sgpu_host_unregister(sgpu_ctx *ctx, void *host) {
 
 int sgpu_counts_checksum(sgpu_ctx *ctx, sgpu_counts *c, const int32_t *const *peer_planes, uint32_t n_peers, uint32_t slab,
                          uint32_t n_slabs, uint64_t *checksum) {
-    SGPU_TRY(sgpu_tensor_join(ctx)); // a first-order tensor kernel may still be adding to the planes (sgpu_ctx::tensor_jobs)
+    SGPU_TRY(sgpu_tensor_join(ctx, c->i32)); // a first-order tensor kernel may still be adding to the planes (sgpu_ctx::tensor_jobs)
     SGPU_CUDA(ctx, cudaSetDevice(ctx->device));
     if (n_peers > SGPU_MAX_PEERS || n_slabs == 0 || slab >= n_slabs) {
         return sgpu_fail(ctx, SGPU_E_ARG, "checksum: %u peers, slab %u of %u", n_peers, slab, n_slabs);
@@ -1431,7 +1431,7 @@ int sgpu_similarity_finalize_spectral(sgpu_ctx *ctx, sgpu_counts *c, uint32_t ma
                                       double homozygous_rate, double seq_error_rate, int normalization, double *out,
                                       uint32_t k, double tol, double *eigenvalues, double *eigenvectors, sgpu_stats *stats,
                                       sgpu_spectral_stats *spectral_stats) {
-    SGPU_TRY(sgpu_tensor_join(ctx)); // a first-order tensor kernel may still be adding to the planes (sgpu_ctx::tensor_jobs)
+    SGPU_TRY(sgpu_tensor_join(ctx, c->i32)); // a first-order tensor kernel may still be adding to the planes (sgpu_ctx::tensor_jobs)
     SGPU_CUDA(ctx, cudaSetDevice(ctx->device));
     if (c->have_params && c->spill
         && (c->eps != mutation_rate || c->h != homozygous_rate || c->theta != seq_error_rate || c->L != max_fragment_length)) {

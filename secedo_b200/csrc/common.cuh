@@ -46,6 +46,7 @@ struct sgpu_ctx {
     cudaStream_t tensor_stream = nullptr;
     bool async_gemm = true;
     struct TensorJob {
+        const void *planes = nullptr; // first of the count planes the kernel adds to (whom a join concerns)
         void *U = nullptr;   // operand panel (context cache)
         int *err = nullptr;  // [0] range check of the staging, [1] wave counter of the tensor kernel (context cache)
         cudaEvent_t t0 = nullptr, t1 = nullptr; // around the kernel, on the stream it was launched on
@@ -107,7 +108,10 @@ int sgpu_fail(sgpu_ctx *ctx, int code, const char *fmt, ...);
 int sgpu_cache_preference(sgpu_ctx *ctx, bool shared);
 // gemm.cu — tensor kernels in flight on ctx->tensor_stream (see sgpu_ctx::tensor_jobs)
 int sgpu_tensor_poll(sgpu_ctx *ctx, bool wait_all); // retire finished jobs (timing, operand panel back to the cache)
-int sgpu_tensor_join(sgpu_ctx *ctx);                // ctx->stream waits (on the device) for the last job
+// ctx->stream waits (on the device) for the last job that writes the count planes starting at `planes` (null: any job); a
+// launch still held back is issued first if it writes them. A caller that alternates between two counts objects thereby
+// keeps the other object's tensor kernel in flight (or held back) across its epilogue.
+int sgpu_tensor_join(sgpu_ctx *ctx, const void *planes = nullptr);
 int sgpu_tensor_flush(sgpu_ctx *ctx, bool after_main); // issue the prepared launch, if any (after_main: behind everything queued on ctx->stream)
 // make the context's stream wait for an asynchronously uploaded pileup
 #define SGPU_WAIT_PILEUP(ctx, p)                                                                   \

@@ -1500,6 +1500,7 @@ int sgpu_gemm_run(sgpu_ctx *ctx, const GemmInput &in, uint32_t N, int32_t *S_pla
         tl.stages2 = stages2;
         tl.pairs = pairs;
         tl.err = errp;
+        tl.job.planes = S_plane;
         if (pairs && wave_sync) {
             tl.wl.wave_ctr = reinterpret_cast<unsigned int *>(errp + 1);
         }
@@ -1576,10 +1577,16 @@ int sgpu_tensor_poll(sgpu_ctx *ctx, bool wait_all) {
     return SGPU_OK;
 }
 
-int sgpu_tensor_join(sgpu_ctx *ctx) {
-    SGPU_TRY(sgpu_tensor_flush(ctx, false));
-    if (!ctx->tensor_jobs.empty()) {
-        SGPU_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->tensor_jobs.back().t1, 0));
+int sgpu_tensor_join(sgpu_ctx *ctx, const void *planes) {
+    const TensorLaunch *pending = static_cast<const TensorLaunch *>(ctx->pending_gemm);
+    if (pending && (planes == nullptr || pending->job.planes == planes)) {
+        SGPU_TRY(sgpu_tensor_flush(ctx, false));
     }
-    return sgpu_cache_preference(ctx, false); // nothing runs beside a tensor kernel until the next one is launched
+    for (auto it = ctx->tensor_jobs.rbegin(); it != ctx->tensor_jobs.rend(); ++it) {
+        if (planes == nullptr || it->planes == planes) { // jobs finish in order: the last one of these planes covers the earlier ones
+            SGPU_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, it->t1, 0));
+            break;
+        }
+    }
+    return sgpu_cache_preference(ctx, false); // what the caller launches next runs alone (or at most beside another object's kernel)
 }

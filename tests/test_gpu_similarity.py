@@ -270,6 +270,39 @@ def test_filtered_view_of_read_ids(gpu_ctx, path, monkeypatch):
     c.free()
 
 
+def test_two_counts_objects_interleaved(gpu_ctx):
+    """the tensor kernel of an accumulation is held back until the next batch's read linking has been issued, and a join only
+    concerns the planes it is asked for: a caller that alternates between two counts objects (bench.py's pipelined steps)
+    must get each object's own sums, whatever is still in flight or held back for the other one"""
+    ident = np.arange(1024, dtype=np.uint32)
+    devs = [gpu_ctx.synth_pileup(1024, 0.5, 1, 1500, theta=0.001, p_multi=0.02, p_mate=0.02, seed=70 + k) for k in range(3)]
+    flt = api.Filter(0.001, 4, gpu_ctx)
+    fs = [flt.filter_device(d, ident)[0] for d in devs]
+    args = (1000, ident, 0.01, 0.15, 0.001, 8, "gemm")
+    single = []
+    for f in fs:  # each batch alone
+        c = api.Counts(gpu_ctx, 1024)
+        c.accumulate(f, *args)
+        single.append(c.download())
+        c.free()
+    a, b = api.Counts(gpu_ctx, 1024), api.Counts(gpu_ctx, 1024)
+    a.accumulate(fs[0], *args)          # a: batch 0 (kernel held back)
+    b.accumulate(fs[1], *args)          # b: batch 1 (a's kernel issued behind b's read linking, b's held back)
+    Ma = a.finalize(1000, 0.01, 0.15, 0.001, "ADD_MIN")   # concerns a only
+    b.accumulate(fs[2], *args)          # b: + batch 2
+    a.zero()
+    a.accumulate(fs[2], *args)
+    got_b, got_a = b.download(), a.download()
+    for k in range(3):
+        assert np.array_equal(got_b[k], single[1][k] + single[2][k])
+        assert np.array_equal(got_a[k], single[2][k])
+    one = api.Counts(gpu_ctx, 1024)
+    one.accumulate(fs[0], *args)
+    assert np.array_equal(Ma, one.finalize(1000, 0.01, 0.15, 0.001, "ADD_MIN"))
+    for x in (a, b, one, *fs, *devs):
+        x.free()
+
+
 def test_auto_path_and_stats(gpu_ctx):
     dev = gpu_ctx.synth_pileup(1024, 0.5, 1, 4000, theta=0.001, p_multi=0.01, seed=4)
     ident = np.arange(1024, dtype=np.uint32)
