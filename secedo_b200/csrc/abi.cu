@@ -414,6 +414,7 @@ int sgpu_set_stream(sgpu_ctx *ctx, void *cuda_stream) {
 uint64_t sgpu_launch_count(const sgpu_ctx *ctx) { return ctx ? ctx->launches : 0; }
 
 int sgpu_synchronize(sgpu_ctx *ctx) {
+    SGPU_CUDA(ctx, cudaSetDevice(ctx->device)); // a held-back tensor kernel may be launched here
     if (ctx->copy_stream) {
         SGPU_CUDA(ctx, cudaStreamSynchronize(ctx->copy_stream));
     }
@@ -1006,6 +1007,7 @@ int sgpu_counts_buffers(sgpu_counts *c, int32_t **i32, uint64_t *n_i32, double *
         return SGPU_E_ARG;
     }
     if (c->owner) {
+        SGPU_CUDA(c->owner, cudaSetDevice(c->owner->device)); // a held-back tensor kernel may be launched here
         // whoever reads the planes through these pointers is ordered behind the context's stream (a collective, a peer's
         // kernel after a barrier): make that stream wait for a first-order tensor kernel that is still adding to them
         SGPU_TRY(sgpu_tensor_join(c->owner, c->i32));
