@@ -9,16 +9,26 @@
 // so ONE K-dimension of 4 int8 values per (cell, locus) feeds two int32 accumulators — 4 MMA
 // K-slices per 32 loci instead of the 5 (four base planes + a total plane) of the direct form.
 //
-//   stage_count_kernel   entries -> packed per-(locus, cell) base counts (4 x u8 in a u32), L2 atomics
-//   transform_kernel     packed counts -> Hadamard planes, transposed into the K-major tile layout
-//                        U[cell][k-block][plane][32 loci] (one 128-byte row per cell and k-block)
-//   syrk_kernel          persistent, warp-specialised: warp 0 = TMA producer (cp.async.bulk.tensor,
-//                        128B swizzle, 4-stage mbarrier ring), warp 1 = tcgen05.mma.kind::i8 issuer
-//                        (M=128, N=256, K=32; accumulators Q = 4S - T and T in TMEM, 2 x 256
-//                        columns), warps 2-5 = epilogue (tcgen05.ld, S = (Q+T)/4, D = T - S,
-//                        RED.ADD into the int32 planes, upper triangle only)
-// Only output tiles that intersect the upper triangle are computed; the K range of a panel is
-// split across CTAs when there are fewer tiles than SMs.
+//   partition_kernel     per locus: (cell, base) of the entries that are the only entry of their read, with the
+//                        group map and the bitmap of special entries applied, sorted by stripe of cells
+//   stage_tile_kernel    per (k-block of 32 loci, stripe): base counts in a shared-memory tile -> Hadamard planes,
+//                        written as finished K-major operand rows U[chunk][cell][k-block][plane][32 loci]
+//                        (one 128-byte row per cell and k-block); tail k-blocks hold Z and -Z (S = C C^T - Z Z^T)
+//   syrk2_kernel<stages> persistent CTA pairs (cluster of 2, tcgen05 cta_group::2, 256 x 256 tiles): warp 0 of both
+//                        CTAs = TMA producer (cp.async.bulk.tensor.3d, 128B swizzle, mbarrier ring of 4 / 5 / 6
+//                        stages), warp 1 of the leader = tcgen05.mma.kind::i8 issuer (M=256, N=256, K=32;
+//                        accumulators Q = 4S - T and T in TMEM, 2 x 256 columns per CTA), warps 2-5 = epilogue
+//                        (tcgen05.ld, S = (Q+T)/4, D = T - S, vector stores / load-add-store into the int32 planes,
+//                        RED.ADD for edge and split tiles, upper triangle only); the pairs start the n-th tile
+//                        together (wave counter) so that a wave shares its operand slabs through L2
+//   syrk_kernel          the same on single CTAs (128 x 256 tiles, 4 stages): devices with an odd SM count,
+//                        SECEDO_B200_GEMM_PAIRS=0
+// Only output tiles that intersect the upper triangle are computed; the K range of a panel is split across CTAs for
+// the tiles that do not fill a whole round of the grid.
+//
+// Scheduling (sgpu_gemm_run, sgpu_tensor_flush / _poll / _join below): the tensor kernel of a first-order accumulation
+// runs on the context's tensor stream, and its launch is held back until the NEXT batch's link_window kernel has been
+// issued, so that it shares the SMs with that batch's special-entry chain, partition and staging.
 #include "common.cuh"
 
 #include <cuda.h>

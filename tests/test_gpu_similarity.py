@@ -454,7 +454,7 @@ def test_async_upload_pipeline(gpu_ctx):
 
 @pytest.mark.parametrize("panel_loci", [32, 96, 256])
 def test_several_gemm_panels(gpu_ctx, panel_loci, monkeypatch):
-    """inputs larger than one operand panel (2 GB) are processed panel by panel: the first panel stores
+    """inputs larger than one operand panel (3 GB) are processed panel by panel: the first panel stores
     into the fresh count planes and carries the tail k-blocks, the later ones add in place. Forced here
     with tiny panels; also accumulates twice into the same counts object (load-add-store epilogue)."""
     monkeypatch.setenv("SECEDO_B200_PANEL_LOCI", str(panel_loci))
