@@ -367,6 +367,10 @@ void sgpu_shutdown(sgpu_ctx *ctx) {
             cudaStreamDestroy(ctx->tensor_stream);
             ctx->tensor_stream = nullptr;
         }
+        if (ctx->cache_pref_now == 1) { // the device-wide preference this context switched on goes with it
+            cudaDeviceSetCacheConfig(cudaFuncCachePreferNone);
+            ctx->cache_pref_now = 0;
+        }
         if (ctx->d2h_stream) {
             cudaStreamSynchronize(ctx->d2h_stream);
             cudaStreamDestroy(ctx->d2h_stream);

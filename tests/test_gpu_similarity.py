@@ -270,6 +270,45 @@ def test_filtered_view_of_read_ids(gpu_ctx, path, monkeypatch):
     c.free()
 
 
+def test_scheduling_knobs_do_not_change_results():
+    """the tensor kernel beside the next batch (own stream, held-back launch, operand ring, cache preference): whatever the
+    knobs say, a filter -> accumulate loop over several batches gives the same count planes and the same matrix, and they
+    are the oracle's"""
+    ctx = api.Context(0)
+    n = 1536
+    ident = np.arange(n, dtype=np.uint32)
+    devs = [ctx.synth_pileup(n, 0.4, 2, 700, theta=0.001, p_multi=0.03, p_mate=0.02, seed=90 + k) for k in range(3)]
+    flt = api.Filter(0.001, 4, ctx)
+    want = None
+    for fd in devs:
+        f = flt.filter_device(fd, ident)[0].download()
+        o = po.similarity(f, n, 1000, ident, 0.01, 0.15, 0.001, 8, "ADD_MIN")
+        want = [o.S1, o.D1, o.H] if want is None else [want[0] + o.S1, want[1] + o.D1, want[2] + o.H]
+    c = api.Counts(ctx, n)
+    first_M = None
+    for knobs in ({"async_gemm": 0}, {"async_gemm": 1, "late_gemm": 0}, {"async_gemm": 1, "late_gemm": 1, "gemm_stages": 6},
+                  {"gemm_stages": 4, "prefer_shared": 1}, {"gemm_stages": 5, "prefer_shared": 0}, {"prefer_shared": 2}):
+        for k, v in knobs.items():
+            ctx.set_option(k, v)
+        c.zero()
+        for fd in devs:
+            f, _ = flt.filter_device(fd, ident)
+            c.accumulate(f, 1000, ident, 0.01, 0.15, 0.001, 8, "gemm")
+            f.free()
+        M = c.finalize(1000, 0.01, 0.15, 0.001, "ADD_MIN")
+        S1, D1, H, _ = c.download()
+        assert np.array_equal(S1, want[0]) and np.array_equal(D1, want[1]) and np.array_equal(H, want[2]), knobs
+        if first_M is None:
+            first_M = M
+        assert np.array_equal(M, first_M), knobs
+    with pytest.raises(api.SgpuError):
+        ctx.set_option("no_such_knob", 1)
+    c.free()
+    for fd in devs:
+        fd.free()
+    ctx.close()
+
+
 def test_two_counts_objects_interleaved(gpu_ctx):
     """the tensor kernel of an accumulation is held back until the next batch's read linking has been issued, and a join only
     concerns the planes it is asked for: a caller that alternates between two counts objects (bench.py's pipelined steps)
