@@ -185,7 +185,10 @@ int sgpu_is_significant(sgpu_ctx *ctx, const uint16_t *counts4, uint64_t n, doub
                         int cell_proportion, uint8_t *out);
 /* Filter::filter: keeps the entries whose group is in the sub-cluster (id_to_pos[gid] != NO_POS)
  * at the loci that pass is_significant; result stays on the device. avg_coverage is accumulated in
- * 64 bits (the reference wraps at 2^32, util/is_significant.cpp:156,187). */
+ * 64 bits (the reference wraps at 2^32, util/is_significant.cpp:156,187).
+ * When every group is in the sub-cluster (the root of the recursion) the read ids are not copied: the result reads them
+ * through a view of `in` until it is downloaded or freed. sgpu_pileup_free(in) before that is fine (the library keeps the
+ * ids alive); device arrays that the CALLER owns (sgpu_pileup_wrap_device) must outlive the result. */
 int sgpu_filter(sgpu_ctx *ctx, const sgpu_pileup *in, const uint32_t *id_to_pos, uint32_t n_groups,
                 double theta, int cell_proportion, sgpu_pileup **filtered, double *avg_coverage);
 
