@@ -319,14 +319,14 @@ int sgpu_init(int device, sgpu_ctx **out) {
         int least = 0, greatest = 0;
         SGPU_CUDA(ctx, cudaDeviceGetStreamPriorityRange(&least, &greatest));
         SGPU_CUDA(ctx, cudaStreamCreateWithPriority(&ctx->tensor_stream, cudaStreamNonBlocking, greatest));
-        // kernels that are to run beside the tensor kernel must accept the shared-memory / L1 split its large operand
-        // ring forces on the SM (profiles/coresidency_probe.cu)
         const char *as = getenv("SECEDO_B200_ASYNC_GEMM");
         ctx->async_gemm = !(as && as[0] == '0');
         const char *lg = getenv("SECEDO_B200_GEMM_LATE");
         ctx->late_gemm = !(lg && lg[0] == '0');
         const char *fp = getenv("SECEDO_B200_GEMM_FLUSH_AT");
         ctx->flush_point = fp ? std::min(2, std::max(0, atoi(fp))) : 0;
+        // kernels only run beside the tensor kernel while the device-wide cache preference is PreferShared (sgpu_ctx::prefer_shared,
+        // profiles/coresidency_probe.cu): 2 = switched on and off around the window in which that can happen
         const char *ps = getenv("SECEDO_B200_PREFER_SHARED");
         ctx->prefer_shared = ps ? atoi(ps) : (ctx->async_gemm ? 2 : 0);
         if (ctx->prefer_shared == 1) {

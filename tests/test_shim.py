@@ -33,6 +33,12 @@ def test_shim_compiles_against_reference_headers():
                     "-I" + os.path.join(REF, "third_party", "spdlog", "include"), "-I" + INC, SHIM], check=True)
 
 
+def test_shim_bench_driver_compiles():
+    """the C++ driver bench.py times the shim with (e2e_shim) builds against the stand-in headers of the reference interface"""
+    subprocess.run(["g++", "-std=c++20", "-fsyntax-only", "-Wall", "-Wextra", "-Werror", "-I" + COMPAT, "-I" + INC,
+                    os.path.join(ROOT, "tests", "cpp", "shim_bench.cpp")], check=True)
+
+
 def _write_vec(f, a):
     f.write(struct.pack("<Q", a.size))
     f.write(a.tobytes())
